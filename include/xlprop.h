@@ -1,0 +1,120 @@
+/*
+ * xlprop.h -- C ABI of libxlprop.so: B200-native (sm_100a) light propagation for XLuminA's hot path.
+ *
+ * This is the drop-in boundary.  Each entry point replaces one of the reference's jitted seam functions
+ * (paths relative to the XLuminA repository):
+ *
+ *   xl_rs_fwd / xl_rs_bwd          RS_propagation_jit            xlumina/wave_optics.py:281-289  (+ build_grid :265-279,
+ *                                                                transfer_function_RS :291-297) and its JAX VJP
+ *   xl_vrs_fwd / xl_vrs_bwd        VRS_propagation_jit           xlumina/vectorized_optics.py:364-373 (+ Ez, :258-261)
+ *   xl_czt_fwd / xl_czt_bwd        CZT_jit / VCZT_jit            xlumina/wave_optics.py:333-357, vectorized_optics.py:375-384
+ *                                  (+ build_CZT_grid :299-331, Bluestein_method :412-460, compute_fft :385-410)
+ *   xl_highna_fwd / xl_highna_bwd  _high_NA_objective_lens_ + vectorized_CZT_for_high_NA + cte
+ *                                  xlumina/optical_elements.py:515-638, vectorized_optics.py:386-394, wave_optics.py:359-371
+ *
+ * Conventions
+ *   - All array arguments are DEVICE pointers; complex data is interleaved float32 (re,im) = complex64, row-major
+ *     [..., y, x] exactly like the reference's arrays; geometry scalars are float64.
+ *   - `z` (propagation distance) is a traced value in the reference (wave_optics.py:281 marks only nx,ny,dx,dy,k static),
+ *     so it is a pointer to ONE float64 in device memory.  Everything that is static in the reference is passed by value.
+ *   - Coordinate grids (Xext/Yext/X/Y/Xout/Yout) are never passed: they are regenerated analytically from
+ *     (first coordinate, spacing); the input and output grids must be uniformly spaced (true for toolbox.space()).
+ *   - Backward functions compute the JAX-convention VJP (transpose, no conjugation).  XL_CONJ_IN / XL_CONJ_OUT conjugate
+ *     the cotangent on load / the result on store, which turns the call into torch's convention at no cost.
+ *   - Nothing here allocates, frees, or synchronises in steady state: scratch is a caller-provided workspace sized by the
+ *     matching *_workspace_bytes query, work is enqueued on `stream` (a cudaStream_t) only, and the calls are
+ *     CUDA-graph-capturable after the first (warm-up) call on a device, which uploads the twiddle table.
+ *   - Return value: 0 on success, a negative XL_E_* code otherwise; xl_last_error() gives a thread-local message.
+ *     No call aborts or throws across the ABI.  NaNs are produced only where the reference produces them
+ *     (high-NA lens with a sample at rho == 0, optical_elements.py:538).
+ */
+#ifndef XLPROP_H
+#define XLPROP_H
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define XLPROP_VERSION 100
+
+enum {
+    XL_OK = 0,
+    XL_E_BAD_ARG = -1,      /* null pointer / non-positive size */
+    XL_E_UNSUPPORTED = -2,  /* padded length outside [32, 4096], or m+M-1 a power of two (reference raises too) */
+    XL_E_WORKSPACE = -3,    /* workspace too small */
+    XL_E_CUDA = -4          /* CUDA runtime error (message in xl_last_error) */
+};
+
+enum {
+    XL_CONJ_IN = 1,   /* conjugate the (co)tangent operand while loading it */
+    XL_CONJ_OUT = 2,  /* conjugate results while storing them */
+    XL_REUSE_H = 16   /* forward only: `H` already holds the transfer function for this z (cache hit) */
+};
+
+int xl_version(void);
+const char* xl_last_error(void);
+
+/* Padded FFT length used for an N-sample RS axis: smallest power of two >= 2N-1 (the reference pads to 2N-1,
+ * wave_optics.py:286; any length >= 2N-1 gives the identical linear convolution). Returns 0 if unsupported. */
+int xl_rs_padded_length(int N);
+/* Bluestein length for m inputs -> M outputs: 2^ceil(log2(m+M-1)), wave_optics.py:373-383,440-441. */
+int xl_czt_padded_length(int m, int M);
+
+/* ---------------------------------------------------------------- RS / VRS ---------------------------------- */
+/* Bytes of one transfer-function buffer H (L*L complex64, private layout). */
+size_t xl_rs_transfer_bytes(int N);
+size_t xl_rs_workspace_bytes(int N, int nfields, int want_grad_z);
+
+/* H <- FFT2 of the sampled Rayleigh-Sommerfeld impulse response (deriv=0) or of dh/dz (deriv=1), times dx*dy/L^2.
+ * Replaces transfer_function_RS + fft2(H), wave_optics.py:285,288,291-297. */
+int xl_rs_transfer(void* H, const double* z, int N, double dx, double dy, double k, int deriv, void* stream);
+
+/* out[f] = (ifft2(fft2(pad(in[f])) * fft2(H)) * dx*dy)[N-1:, N-1:]  for f < nfields.      wave_optics.py:286-288
+ * H is written unless XL_REUSE_H is set (keep it for the backward call). */
+int xl_rs_fwd(const void* in, void* out, void* H, const double* z, int N, int nfields,
+              double dx, double dy, double k, int flags, void* ws, size_t ws_bytes, void* stream);
+
+/* VJP of xl_rs_fwd.  ct_in[f] = A^T ct_out[f] (A is complex-symmetric, so this is the forward operator);
+ * if grad_z != NULL:  *grad_z += Re sum_f sum ct_out[f] * d out[f]/dz   (needs the primal `in`). */
+int xl_rs_bwd(const void* in, const void* ct_out, void* ct_in, double* grad_z, const void* H, const double* z,
+              int N, int nfields, double dx, double dy, double k, int flags, void* ws, size_t ws_bytes, void* stream);
+
+/* exy = [Ex, Ey] (2,N,N) -> out = [Ex', Ey', Ez'] (3,N,N); Ez = (Ex X + Ey Y)/sqrt(X^2+Y^2+z^2) is formed while loading
+ * (vectorized_optics.py:258-261); x0,y0 = first grid coordinates.  Replaces VRS_propagation_jit (:364-373). */
+int xl_vrs_fwd(const void* exy, void* out, void* H, const double* z, int N, double x0, double y0,
+               double dx, double dy, double k, int flags, void* ws, size_t ws_bytes, void* stream);
+int xl_vrs_bwd(const void* exy, const void* ct_out, void* ct_exy, double* grad_z, const void* H, const double* z,
+               int N, double x0, double y0, double dx, double dy, double k, int flags,
+               void* ws, size_t ws_bytes, void* stream);
+
+/* ---------------------------------------------------------------- CZT / VCZT -------------------------------- */
+/* vectorial = 0: in (N,N) -> out (My,Mx)            CZT_jit,  wave_optics.py:333-357
+ * vectorial = 1: in = [Ex,Ey] (2,N,N) -> out (3,My,Mx); Ez = ((Ex X + Ey Y)/r) z/r   VCZT, vectorized_optics.py:341-344,375-384
+ * Input grid: x_j = x0 + j dx, y_i = y0 + i dy.  Output grid: Mx samples from xout0 to xoutl, My from yout0 to youtl.
+ * Dm = lambda*z/dx (wave_optics.py:322). */
+size_t xl_czt_workspace_bytes(int N, int Mx, int My, int vectorial);
+int xl_czt_fwd(const void* in, void* out, const double* z, double lambda, int N, int Mx, int My, int vectorial,
+               double x0, double dx, double y0, double dy, double xout0, double xoutl, double yout0, double youtl,
+               int flags, void* ws, size_t ws_bytes, void* stream);
+/* VJP with respect to the input field(s) (z, lambda and the grids are static in every reference caller). */
+int xl_czt_bwd(const void* ct_out, void* ct_in, const double* z, double lambda, int N, int Mx, int My, int vectorial,
+               double x0, double dx, double y0, double dy, double xout0, double xoutl, double yout0, double youtl,
+               int flags, void* ws, size_t ws_bytes, void* stream);
+
+/* ---------------------------------------------------------------- high-NA objective ------------------------- */
+/* exy = [Ex,Ey] (2,N,N) -> out = [Ex,Ey,Ez] (3,My,Mx) in the focal plane:
+ *   -i sin^2(theta_max)/(f lambda) * Bluestein_x(Bluestein_y( apod*G*RL(theta,phi) (Ex,Ey,Ez)^T )),  Dm = f lambda (N-1)/(2R).
+ * optical_elements.py:515-672. */
+size_t xl_highna_workspace_bytes(int N, int Mx, int My);
+int xl_highna_fwd(const void* exy, void* out, int N, int Mx, int My, double radius, double f, double lambda,
+                  double x0, double dx, double y0, double dy, double xout0, double xoutl, double yout0, double youtl,
+                  int flags, void* ws, size_t ws_bytes, void* stream);
+int xl_highna_bwd(const void* ct_out, void* ct_exy, int N, int Mx, int My, double radius, double f, double lambda,
+                  double x0, double dx, double y0, double dy, double xout0, double xoutl, double yout0, double youtl,
+                  int flags, void* ws, size_t ws_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* XLPROP_H */

@@ -1,0 +1,510 @@
+// xl_api.cu -- C ABI (include/xlprop.h) over the kernels in xl_kernels.cuh: workspace carving, dispatch on the padded
+// length, launches.  Compiled by nvcc for sm_100a (product) and, with -DXL_HOST_EMU, by g++ for the test-only host
+// emulation of the kernel bodies (tests/emu).
+#include "xl_kernels.cuh"
+#include "../../include/xlprop.h"
+#include <stdio.h>
+#include <string.h>
+#include <stdlib.h>
+#include <mutex>
+#include <vector>
+
+#ifdef XL_HOST_EMU
+thread_local xl_dim3 xl_emu_blockIdx;
+typedef void* xl_stream_t;
+#else
+typedef cudaStream_t xl_stream_t;
+#endif
+
+// ------------------------------------------------------------------------------------------------ errors
+static thread_local char g_err[512] = "";
+static int xl_fail(int code, const char* fmt, const char* a = "", long long b = 0) {
+    snprintf(g_err, sizeof(g_err), fmt, a, b);
+    return code;
+}
+extern "C" int xl_version(void) { return XLPROP_VERSION; }
+extern "C" const char* xl_last_error(void) { return g_err; }
+
+// ------------------------------------------------------------------------------------------------ launch
+struct XlDim { int x, y; };
+
+#ifndef XL_HOST_EMU
+template <class Body> __global__ void __launch_bounds__(Body::NT) xl_kernel(const typename Body::Params p) {
+    extern __shared__ float4 xl_smem[];
+    Body::run(p, (cf*)xl_smem);
+}
+#endif
+
+template <class Body> static int xl_launch(XlDim grid, size_t smem, xl_stream_t stream, const typename Body::Params& p) {
+    if (grid.x <= 0 || grid.y <= 0) return XL_OK;
+#ifdef XL_HOST_EMU
+    (void)stream;
+    std::vector<char> buf(smem + 64);
+    for (int by = 0; by < grid.y; ++by)
+        for (int bx = 0; bx < grid.x; ++bx) {
+            xl_emu_blockIdx.x = bx; xl_emu_blockIdx.y = by; xl_emu_blockIdx.z = 0;
+            Body::run(p, (cf*)buf.data());
+        }
+    return XL_OK;
+#else
+    static bool attr_set[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 64 && !attr_set[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(xl_kernel<Body>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return xl_fail(XL_E_CUDA, "cudaFuncSetAttribute: %s (smem %lld)", cudaGetErrorString(e), (long long)smem);
+        attr_set[dev] = true;
+    }
+    xl_kernel<Body><<<dim3(grid.x, grid.y, 1), dim3(Body::NT, 1, 1), smem, stream>>>(p);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return xl_fail(XL_E_CUDA, "kernel launch: %s", cudaGetErrorString(e));
+    return XL_OK;
+#endif
+}
+
+#define XL_FOR_L(L, CALL)                                     \
+    switch (L) {                                              \
+        case 32: { constexpr int XL = 32; CALL; } break;      \
+        case 64: { constexpr int XL = 64; CALL; } break;      \
+        case 128: { constexpr int XL = 128; CALL; } break;    \
+        case 256: { constexpr int XL = 256; CALL; } break;    \
+        case 512: { constexpr int XL = 512; CALL; } break;    \
+        case 1024: { constexpr int XL = 1024; CALL; } break;  \
+        case 2048: { constexpr int XL = 2048; CALL; } break;  \
+        case 4096: { constexpr int XL = 4096; CALL; } break;  \
+        default: return xl_fail(XL_E_UNSUPPORTED, "padded length %s%lld outside [32,4096]", "", (long long)(L)); \
+    }
+
+static size_t tile_bytes(int L) { return (size_t)xl_tile_elems(L, XL_CW) * sizeof(cf); }
+
+// ------------------------------------------------------------------------------------------------ twiddles
+static std::mutex g_tw_mutex;
+static cf* g_tw[64] = {0};
+static const cf* xl_twiddles() {
+    int dev = 0;
+#ifndef XL_HOST_EMU
+    cudaGetDevice(&dev);
+#endif
+    if (dev < 0 || dev >= 64) return 0;
+    std::lock_guard<std::mutex> lk(g_tw_mutex);
+    if (g_tw[dev]) return g_tw[dev];
+    std::vector<cf> h(XL_TWN);
+    for (int k = 0; k < XL_TWN; ++k) {
+        double a = 2.0 * M_PI * (double)k / (double)XL_TWN;
+        h[k].x = (float)cos(a);
+        h[k].y = (float)(-sin(a));
+    }
+#ifdef XL_HOST_EMU
+    g_tw[dev] = (cf*)malloc(sizeof(cf) * XL_TWN);
+    memcpy(g_tw[dev], h.data(), sizeof(cf) * XL_TWN);
+#else
+    cf* d = 0;
+    if (cudaMalloc(&d, sizeof(cf) * XL_TWN) != cudaSuccess) return 0;
+    if (cudaMemcpy(d, h.data(), sizeof(cf) * XL_TWN, cudaMemcpyHostToDevice) != cudaSuccess) return 0;
+    g_tw[dev] = d;
+#endif
+    return g_tw[dev];
+}
+
+// ------------------------------------------------------------------------------------------------ helpers
+static int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
+extern "C" int xl_rs_padded_length(int N) {
+    if (N < 2) return 0;
+    int L = next_pow2(2 * N - 1);
+    if (L < 32) L = 32;
+    return L <= 4096 ? L : 0;
+}
+extern "C" int xl_czt_padded_length(int m, int M) {
+    if (m < 1 || M < 2) return 0;
+    int mp = m + M - 1;
+    int L = next_pow2(mp);
+    if (L == mp) return 0;  // the reference slices b[m:mp+1] out of np2 == mp rows and raises; out of contract
+    if (L < 32) L = 32;
+    return L <= 4096 ? L : 0;
+}
+static size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
+struct Carver {
+    char* base; size_t off, cap;
+    void* take(size_t bytes) { void* p = base + off; off += align_up(bytes); return p; }
+    bool ok() const { return off <= cap; }
+};
+
+static int zero_async(void* p, size_t bytes, xl_stream_t s) {
+#ifdef XL_HOST_EMU
+    (void)s; memset(p, 0, bytes); return XL_OK;
+#else
+    cudaError_t e = cudaMemsetAsync(p, 0, bytes, s);
+    return e == cudaSuccess ? XL_OK : xl_fail(XL_E_CUDA, "cudaMemsetAsync: %s", cudaGetErrorString(e));
+#endif
+}
+
+// ================================================================================================ RS / VRS
+extern "C" size_t xl_rs_transfer_bytes(int N) {
+    size_t L = (size_t)xl_rs_padded_length(N);
+    return L * L * sizeof(cf);
+}
+extern "C" size_t xl_rs_workspace_bytes(int N, int nfields, int want_grad_z) {
+    size_t L = (size_t)xl_rs_padded_length(N);
+    if (!L || nfields < 1) return 0;
+    size_t spec = align_up((size_t)nfields * L * N * sizeof(cf));
+    size_t total = spec;
+    if (want_grad_z) total += spec + align_up(L * L * sizeof(cf)) + align_up((size_t)nfields * L * L * sizeof(cf));
+    total += align_up((size_t)3 * N * N * sizeof(cf));  // VRS backward: adjoint of the 3 components before the fold
+    return total;
+}
+
+static int rs_base_params(XlRsParams& p, int N, double dx, double dy, double k) {
+    memset(&p, 0, sizeof(p));
+    p.N = N;
+    p.L = xl_rs_padded_length(N);
+    if (!p.L) return xl_fail(XL_E_UNSUPPORTED, "RS: N=%s%lld unsupported (padded length must be in [32,4096])", "", N);
+    p.dx = dx; p.dy = dy; p.k = k;
+    p.hscale = (float)(dx * dy / ((double)p.L * (double)p.L));
+    p.tw = xl_twiddles();
+    if (!p.tw) return xl_fail(XL_E_CUDA, "twiddle table allocation failed%s", "");
+    return XL_OK;
+}
+
+static int rs_transfer_impl(XlRsParams p, cf* H, const double* z, int deriv, xl_stream_t st) {
+    p.H = H; p.z = z;
+    p.flags = deriv ? XL_F_DERIV : 0;
+    const int L = p.L;
+    int rc;
+    XL_FOR_L(L, rc = xl_launch<XlHRows<XL>>(XlDim{(L / 2 + 1 + XL_CW - 1) / XL_CW, 1}, tile_bytes(XL), st, p));
+    if (rc) return rc;
+    XL_FOR_L(L, rc = xl_launch<XlHCols<XL>>(XlDim{L / XL_CW, 1}, tile_bytes(XL), st, p));
+    return rc;
+}
+
+extern "C" int xl_rs_transfer(void* H, const double* z, int N, double dx, double dy, double k, int deriv, void* stream) {
+    if (!H || !z) return xl_fail(XL_E_BAD_ARG, "xl_rs_transfer: null pointer%s", "");
+    XlRsParams p;
+    int rc = rs_base_params(p, N, dx, dy, k);
+    if (rc) return rc;
+    return rs_transfer_impl(p, (cf*)H, z, deriv, (xl_stream_t)stream);
+}
+
+// rows fwd -> cols conv -> rows inv on `nfields` planes
+static int rs_apply_impl(XlRsParams p, xl_stream_t st) {
+    const int L = p.L, N = p.N;
+    int rc;
+    XL_FOR_L(L, rc = xl_launch<XlRsRowsFwd<XL>>(XlDim{(N + XL_CW - 1) / XL_CW, p.nfields}, tile_bytes(XL), st, p));
+    if (rc) return rc;
+    XL_FOR_L(L, rc = xl_launch<XlRsCols<XL>>(XlDim{L / XL_CW, p.nfields}, tile_bytes(XL), st, p));
+    if (rc) return rc;
+    XL_FOR_L(L, rc = xl_launch<XlRsRowsInv<XL>>(XlDim{(N + XL_CW - 1) / XL_CW, p.nfields}, tile_bytes(XL), st, p));
+    return rc;
+}
+
+static int rs_fwd_common(const void* in, void* out, void* H, const double* z, int N, int nfields, int vrs,
+                         double x0, double y0, double dx, double dy, double k, int flags,
+                         void* ws, size_t ws_bytes, xl_stream_t st) {
+    if (!in || !out || !H || !z || !ws) return xl_fail(XL_E_BAD_ARG, "rs_fwd: null pointer%s", "");
+    XlRsParams p;
+    int rc = rs_base_params(p, N, dx, dy, k);
+    if (rc) return rc;
+    if (ws_bytes < xl_rs_workspace_bytes(N, nfields, 0)) return xl_fail(XL_E_WORKSPACE, "rs_fwd: workspace too small%s", "");
+    if (!(flags & XL_REUSE_H)) { rc = rs_transfer_impl(p, (cf*)H, z, 0, st); if (rc) return rc; }
+    Carver c{(char*)ws, 0, ws_bytes};
+    p.spec = (cf*)c.take((size_t)nfields * p.L * N * sizeof(cf));
+    p.in = (const cf*)in; p.out = (cf*)out; p.H = (cf*)H; p.z = z;
+    p.nfields = nfields; p.x0 = x0; p.y0 = y0;
+    p.flags = (flags & (XL_CONJ_IN | XL_CONJ_OUT)) | (vrs ? XL_F_VRS : 0);
+    return rs_apply_impl(p, st);
+}
+
+extern "C" int xl_rs_fwd(const void* in, void* out, void* H, const double* z, int N, int nfields,
+                         double dx, double dy, double k, int flags, void* ws, size_t ws_bytes, void* stream) {
+    if (nfields < 1) return xl_fail(XL_E_BAD_ARG, "xl_rs_fwd: nfields < 1%s", "");
+    return rs_fwd_common(in, out, H, z, N, nfields, 0, 0.0, 0.0, dx, dy, k, flags, ws, ws_bytes, (xl_stream_t)stream);
+}
+extern "C" int xl_vrs_fwd(const void* exy, void* out, void* H, const double* z, int N, double x0, double y0,
+                          double dx, double dy, double k, int flags, void* ws, size_t ws_bytes, void* stream) {
+    return rs_fwd_common(exy, out, H, z, N, 3, 1, x0, y0, dx, dy, k, flags, ws, ws_bytes, (xl_stream_t)stream);
+}
+
+static int rs_bwd_common(const void* in, const void* ct_out, void* ct_in, double* grad_z, const void* H, const double* z,
+                         int N, int nfields, int vrs, double x0, double y0, double dx, double dy, double k, int flags,
+                         void* ws, size_t ws_bytes, xl_stream_t st) {
+    if (!ct_out || !ct_in || !H || !ws || !z) return xl_fail(XL_E_BAD_ARG, "rs_bwd: null pointer%s", "");
+    if (grad_z && !in) return xl_fail(XL_E_BAD_ARG, "rs_bwd: grad_z needs the primal input%s", "");
+    XlRsParams p;
+    int rc = rs_base_params(p, N, dx, dy, k);
+    if (rc) return rc;
+    if (ws_bytes < xl_rs_workspace_bytes(N, nfields, grad_z != 0)) return xl_fail(XL_E_WORKSPACE, "rs_bwd: workspace too small%s", "");
+    const int L = p.L;
+    Carver c{(char*)ws, 0, ws_bytes};
+    const size_t spec_bytes = (size_t)nfields * L * N * sizeof(cf);
+    p.spec = (cf*)c.take(spec_bytes);
+    cf* tmp3 = (cf*)c.take((size_t)3 * N * N * sizeof(cf));
+    p.nfields = nfields; p.H = (cf*)H; p.z = z; p.x0 = x0; p.y0 = y0;
+    cf* dst = vrs ? tmp3 : (cf*)ct_in;
+
+    if (grad_z) {
+        p.spec2 = (cf*)c.take(spec_bytes);
+        cf* Hz = (cf*)c.take((size_t)L * L * sizeof(cf));
+        p.scratch = (cf*)c.take((size_t)nfields * L * L * sizeof(cf));
+        rc = rs_transfer_impl(p, Hz, z, 1, st);
+        if (rc) return rc;
+        // row spectra of conj(U) -> spec2
+        XlRsParams pw = p;
+        pw.in = (const cf*)in; pw.spec = p.spec2;
+        pw.flags = XL_F_CONJ_IN | (vrs ? XL_F_VRS : 0);
+        XL_FOR_L(L, rc = xl_launch<XlRsRowsFwd<XL>>(XlDim{(N + XL_CW - 1) / XL_CW, nfields}, tile_bytes(XL), st, pw));
+        if (rc) return rc;
+        // row spectra of the cotangent -> spec
+        XlRsParams pc = p;
+        pc.in = (const cf*)ct_out;
+        pc.flags = (flags & XL_CONJ_IN);
+        XL_FOR_L(L, rc = xl_launch<XlRsRowsFwd<XL>>(XlDim{(N + XL_CW - 1) / XL_CW, nfields}, tile_bytes(XL), st, pc));
+        if (rc) return rc;
+        XlRsParams pg = p;
+        pg.H2 = Hz; pg.gz = grad_z;
+        XL_FOR_L(L, rc = xl_launch<XlRsColsGz<XL>>(XlDim{L / XL_CW, nfields},
+                                                   tile_bytes(XL) + (XlRsColsGz<XL>::NRED + 32) * sizeof(float), st, pg));
+        if (rc) return rc;
+        XlRsParams po = p;
+        po.out = dst;
+        po.flags = vrs ? 0 : (flags & XL_CONJ_OUT);
+        XL_FOR_L(L, rc = xl_launch<XlRsRowsInv<XL>>(XlDim{(N + XL_CW - 1) / XL_CW, nfields}, tile_bytes(XL), st, po));
+        if (rc) return rc;
+    } else {
+        XlRsParams pa = p;
+        pa.in = (const cf*)ct_out; pa.out = dst;
+        pa.flags = (flags & XL_CONJ_IN) | (vrs ? 0 : (flags & XL_CONJ_OUT));
+        rc = rs_apply_impl(pa, st);
+        if (rc) return rc;
+    }
+    if (vrs) {
+        XlFoldParams f;
+        memset(&f, 0, sizeof(f));
+        f.N = N; f.mode = XL_FOLD_VRS; f.flags = flags & XL_CONJ_OUT;
+        f.t = tmp3;
+        f.ex = (const cf*)in; f.ey = in ? (const cf*)in + (size_t)N * N : 0;
+        f.gx = (cf*)ct_in; f.gy = (cf*)ct_in + (size_t)N * N;
+        f.gz = grad_z; f.z = z; f.x0 = x0; f.y0 = y0; f.dx = dx; f.dy = dy;
+        const size_t NN = (size_t)N * N;
+        rc = xl_launch<XlFold>(XlDim{(int)((NN + XlFold::NT - 1) / XlFold::NT), 1}, XlFold::NT * sizeof(float), st, f);
+    }
+    return rc;
+}
+
+extern "C" int xl_rs_bwd(const void* in, const void* ct_out, void* ct_in, double* grad_z, const void* H, const double* z,
+                         int N, int nfields, double dx, double dy, double k, int flags, void* ws, size_t ws_bytes, void* stream) {
+    if (nfields < 1) return xl_fail(XL_E_BAD_ARG, "xl_rs_bwd: nfields < 1%s", "");
+    return rs_bwd_common(in, ct_out, ct_in, grad_z, H, z, N, nfields, 0, 0.0, 0.0, dx, dy, k, flags, ws, ws_bytes, (xl_stream_t)stream);
+}
+extern "C" int xl_vrs_bwd(const void* exy, const void* ct_out, void* ct_exy, double* grad_z, const void* H, const double* z,
+                          int N, double x0, double y0, double dx, double dy, double k, int flags,
+                          void* ws, size_t ws_bytes, void* stream) {
+    return rs_bwd_common(exy, ct_out, ct_exy, grad_z, H, z, N, 3, 1, x0, y0, dx, dy, k, flags, ws, ws_bytes, (xl_stream_t)stream);
+}
+
+// ================================================================================================ CZT family
+struct CztPlan {
+    int N, Mx, My, Ly, Lx, ncomp;
+    cf *pre_y, *post_y, *ft_y, *ftT_y, *pre_x, *post_x, *ft_x, *ftT_x;
+    cf* mid;   // [ncomp][N][My]
+    cf* tmp3;  // [3][N][N]
+};
+static size_t czt_ws_bytes(int N, int Mx, int My, int ncomp) {
+    int Ly = xl_czt_padded_length(N, My), Lx = xl_czt_padded_length(N, Mx);
+    if (!Ly || !Lx) return 0;
+    size_t t = 0;
+    t += 2 * align_up((size_t)N * sizeof(cf)) + align_up((size_t)My * sizeof(cf)) + align_up((size_t)Mx * sizeof(cf));
+    t += 2 * align_up((size_t)Ly * sizeof(cf)) + 2 * align_up((size_t)Lx * sizeof(cf));
+    t += align_up((size_t)ncomp * N * My * sizeof(cf));
+    t += align_up((size_t)3 * N * N * sizeof(cf));
+    return t;
+}
+extern "C" size_t xl_czt_workspace_bytes(int N, int Mx, int My, int vectorial) { return czt_ws_bytes(N, Mx, My, vectorial ? 3 : 1); }
+extern "C" size_t xl_highna_workspace_bytes(int N, int Mx, int My) { return czt_ws_bytes(N, Mx, My, 3); }
+
+static int czt_plan(CztPlan& pl, int N, int Mx, int My, int ncomp, void* ws, size_t ws_bytes) {
+    if (N < 2 || Mx < 2 || My < 2) return xl_fail(XL_E_BAD_ARG, "czt: sizes must be >= 2%s", "");
+    pl.N = N; pl.Mx = Mx; pl.My = My; pl.ncomp = ncomp;
+    pl.Ly = xl_czt_padded_length(N, My);
+    pl.Lx = xl_czt_padded_length(N, Mx);
+    if (!pl.Ly || !pl.Lx) return xl_fail(XL_E_UNSUPPORTED, "czt: m+M-1 is a power of two or padded length outside [32,4096]%s", "");
+    if (!ws || ws_bytes < czt_ws_bytes(N, Mx, My, ncomp)) return xl_fail(XL_E_WORKSPACE, "czt: workspace too small%s", "");
+    Carver c{(char*)ws, 0, ws_bytes};
+    pl.pre_y = (cf*)c.take((size_t)N * sizeof(cf));
+    pl.pre_x = (cf*)c.take((size_t)N * sizeof(cf));
+    pl.post_y = (cf*)c.take((size_t)My * sizeof(cf));
+    pl.post_x = (cf*)c.take((size_t)Mx * sizeof(cf));
+    pl.ft_y = (cf*)c.take((size_t)pl.Ly * sizeof(cf));
+    pl.ftT_y = (cf*)c.take((size_t)pl.Ly * sizeof(cf));
+    pl.ft_x = (cf*)c.take((size_t)pl.Lx * sizeof(cf));
+    pl.ftT_x = (cf*)c.take((size_t)pl.Lx * sizeof(cf));
+    pl.mid = (cf*)c.take((size_t)ncomp * N * My * sizeof(cf));
+    pl.tmp3 = (cf*)c.take((size_t)3 * N * N * sizeof(cf));
+    return XL_OK;
+}
+
+static int czt_setup(const CztPlan& pl, const double* z, double lambda_over_dx, double Dm_static,
+                     double xout0, double xoutl, double yout0, double youtl, const cf* tw, xl_stream_t st) {
+    int rc;
+    XlCztSetupParams s;
+    memset(&s, 0, sizeof(s));
+    s.z = z; s.lambda_over_dx = lambda_over_dx; s.Dm_static = Dm_static; s.tw = tw;
+    // y axis (first Bluestein pass, wave_optics.py:349)
+    s.L = pl.Ly; s.m = pl.N; s.M = pl.My; s.out0 = yout0; s.outl = youtl;
+    s.pre = pl.pre_y; s.post = pl.post_y; s.ft = pl.ft_y; s.ftT = pl.ftT_y;
+    XL_FOR_L(pl.Ly, rc = xl_launch<XlCztSetup<XL>>(XlDim{1, 1}, tile_bytes(XL), st, s));
+    if (rc) return rc;
+    // x axis (second pass, :352)
+    s.L = pl.Lx; s.m = pl.N; s.M = pl.Mx; s.out0 = xout0; s.outl = xoutl;
+    s.pre = pl.pre_x; s.post = pl.post_x; s.ft = pl.ft_x; s.ftT = pl.ftT_x;
+    XL_FOR_L(pl.Lx, rc = xl_launch<XlCztSetup<XL>>(XlDim{1, 1}, tile_bytes(XL), st, s));
+    return rc;
+}
+
+struct CztCall {
+    int N, Mx, My, mode;  // mode: 0 scalar CZT, 1 VCZT, 2 high-NA
+    const double* z; double lambda, k;
+    double x0, dx, y0, dy, xout0, xoutl, yout0, youtl;
+    double R, f, s2;
+    int flags;
+};
+
+static void czt_common_params(XlCztParams& a, const CztCall& cc, const cf* tw) {
+    memset(&a, 0, sizeof(a));
+    a.tw = tw; a.z = cc.z; a.k = cc.k;
+    a.lens_R = cc.R; a.lens_f = cc.f; a.lens_s2 = cc.s2;
+    a.epi_cr = 1.0; a.epi_ci = 0.0;
+}
+static void czt_out_const(XlCztParams& a, const CztCall& cc) {
+    if (cc.mode == 2) { a.epi_cr = 0.0; a.epi_ci = -cc.s2 / (cc.f * cc.lambda); a.epi_times_z = 0; }   // optical_elements.py:627
+    else { a.epi_cr = cc.dx * cc.dy * cc.lambda; a.epi_ci = 0.0; a.epi_times_z = 1; }                   // wave_optics.py:355
+}
+
+static int czt_forward(const CztCall& cc, const void* in, void* out, void* ws, size_t ws_bytes, xl_stream_t st) {
+    if (!in || !out) return xl_fail(XL_E_BAD_ARG, "czt_fwd: null pointer%s", "");
+    if (cc.mode != 2 && !cc.z) return xl_fail(XL_E_BAD_ARG, "czt_fwd: null z%s", "");
+    const int ncomp = cc.mode == 0 ? 1 : 3;
+    CztPlan pl;
+    int rc = czt_plan(pl, cc.N, cc.Mx, cc.My, ncomp, ws, ws_bytes);
+    if (rc) return rc;
+    const cf* tw = xl_twiddles();
+    if (!tw) return xl_fail(XL_E_CUDA, "twiddle table allocation failed%s", "");
+    const double Dm_static = cc.mode == 2 ? cc.f * cc.lambda * (cc.N - 1) / (2 * cc.R) : 0.0;  // optical_elements.py:663
+    rc = czt_setup(pl, cc.mode == 2 ? 0 : cc.z, cc.lambda / cc.dx, Dm_static, cc.xout0, cc.xoutl, cc.yout0, cc.youtl, tw, st);
+    if (rc) return rc;
+    const int N = cc.N, Mx = cc.Mx, My = cc.My;
+    const double dxo = (cc.xoutl - cc.xout0) / (Mx - 1), dyo = (cc.youtl - cc.yout0) / (My - 1);
+    // pass 1: Bluestein along y for every input column
+    XlCztParams a;
+    czt_common_params(a, cc, tw);
+    a.L = pl.Ly; a.nlines = N; a.ncomp = ncomp; a.m_in = N; a.out_off = N; a.m_out = My;
+    a.in = (const cf*)in; a.in_line = 1; a.in_pos = N; a.in_comp = (long long)N * N;
+    a.out = pl.mid; a.out_line = My; a.out_pos = 1; a.out_comp = (long long)N * My;
+    a.pre = pl.pre_y; a.ft = pl.ft_y; a.post = pl.post_y;
+    a.pro = cc.mode == 0 ? XL_PRO_RSF : (cc.mode == 1 ? XL_PRO_VCZT : XL_PRO_HIGHNA);
+    a.gpro = XlGridFactor{cc.x0, cc.dx, cc.y0, cc.dy, 0};
+    a.epi = XL_EPI_NONE;
+    XL_FOR_L(pl.Ly, rc = xl_launch<XlCztAxis<XL>>(XlDim{(N + XL_CW - 1) / XL_CW, ncomp}, tile_bytes(XL), st, a));
+    if (rc) return rc;
+    // pass 2: Bluestein along x for every column of the intermediate
+    XlCztParams b;
+    czt_common_params(b, cc, tw);
+    b.L = pl.Lx; b.nlines = My; b.ncomp = ncomp; b.m_in = N; b.out_off = N; b.m_out = Mx;
+    b.in = pl.mid; b.in_line = 1; b.in_pos = My; b.in_comp = (long long)N * My;
+    b.out = (cf*)out; b.out_line = Mx; b.out_pos = 1; b.out_comp = (long long)My * Mx;
+    b.pre = pl.pre_x; b.ft = pl.ft_x; b.post = pl.post_x;
+    b.pro = XL_PRO_NONE;
+    b.epi = cc.mode == 2 ? XL_EPI_NONE : XL_EPI_RSF;
+    b.gepi = XlGridFactor{cc.xout0, dxo, cc.yout0, dyo, 1};
+    czt_out_const(b, cc);
+    b.flags = cc.flags & XL_CONJ_OUT;
+    XL_FOR_L(pl.Lx, rc = xl_launch<XlCztAxis<XL>>(XlDim{(My + XL_CW - 1) / XL_CW, ncomp}, tile_bytes(XL), st, b));
+    return rc;
+}
+
+static int czt_backward(const CztCall& cc, const void* ct_out, void* ct_in, void* ws, size_t ws_bytes, xl_stream_t st) {
+    if (!ct_out || !ct_in) return xl_fail(XL_E_BAD_ARG, "czt_bwd: null pointer%s", "");
+    if (cc.mode != 2 && !cc.z) return xl_fail(XL_E_BAD_ARG, "czt_bwd: null z%s", "");
+    const int ncomp = cc.mode == 0 ? 1 : 3;
+    CztPlan pl;
+    int rc = czt_plan(pl, cc.N, cc.Mx, cc.My, ncomp, ws, ws_bytes);
+    if (rc) return rc;
+    const cf* tw = xl_twiddles();
+    if (!tw) return xl_fail(XL_E_CUDA, "twiddle table allocation failed%s", "");
+    const double Dm_static = cc.mode == 2 ? cc.f * cc.lambda * (cc.N - 1) / (2 * cc.R) : 0.0;
+    rc = czt_setup(pl, cc.mode == 2 ? 0 : cc.z, cc.lambda / cc.dx, Dm_static, cc.xout0, cc.xoutl, cc.yout0, cc.youtl, tw, st);
+    if (rc) return rc;
+    const int N = cc.N, Mx = cc.Mx, My = cc.My;
+    const double dxo = (cc.xoutl - cc.xout0) / (Mx - 1), dyo = (cc.youtl - cc.yout0) / (My - 1);
+    // transpose of pass 2: rows of ct_out (length Mx) -> columns of the intermediate cotangent
+    XlCztParams b;
+    czt_common_params(b, cc, tw);
+    b.L = pl.Lx; b.nlines = My; b.ncomp = ncomp; b.m_in = Mx; b.out_off = 0; b.m_out = N;
+    b.in = (const cf*)ct_out; b.in_line = Mx; b.in_pos = 1; b.in_comp = (long long)My * Mx;
+    b.out = pl.mid; b.out_line = 1; b.out_pos = My; b.out_comp = (long long)N * My;
+    b.pre = pl.post_x; b.ft = pl.ftT_x; b.post = pl.pre_x;
+    b.pro = cc.mode == 2 ? XL_PRO_NONE : XL_PRO_RSF;
+    b.gpro = XlGridFactor{cc.xout0, dxo, cc.yout0, dyo, 1};
+    b.epi = XL_EPI_NONE;
+    czt_out_const(b, cc);
+    b.flags = cc.flags & XL_CONJ_IN;
+    XL_FOR_L(pl.Lx, rc = xl_launch<XlCztAxis<XL>>(XlDim{(My + XL_CW - 1) / XL_CW, ncomp}, tile_bytes(XL), st, b));
+    if (rc) return rc;
+    // transpose of pass 1: rows of the intermediate cotangent (length My) -> columns of ct_field
+    XlCztParams a;
+    czt_common_params(a, cc, tw);
+    a.L = pl.Ly; a.nlines = N; a.ncomp = ncomp; a.m_in = My; a.out_off = 0; a.m_out = N;
+    a.in = pl.mid; a.in_line = My; a.in_pos = 1; a.in_comp = (long long)N * My;
+    a.out = cc.mode == 0 ? (cf*)ct_in : pl.tmp3; a.out_line = 1; a.out_pos = N; a.out_comp = (long long)N * N;
+    a.pre = pl.post_y; a.ft = pl.ftT_y; a.post = pl.pre_y;
+    a.pro = XL_PRO_NONE;
+    a.epi = cc.mode == 2 ? XL_EPI_NONE : XL_EPI_RSF;
+    a.gepi = XlGridFactor{cc.x0, cc.dx, cc.y0, cc.dy, 0};
+    a.flags = cc.mode == 0 ? (cc.flags & XL_CONJ_OUT) : 0;
+    XL_FOR_L(pl.Ly, rc = xl_launch<XlCztAxis<XL>>(XlDim{(N + XL_CW - 1) / XL_CW, ncomp}, tile_bytes(XL), st, a));
+    if (rc || cc.mode == 0) return rc;
+    XlFoldParams f;
+    memset(&f, 0, sizeof(f));
+    f.N = N; f.mode = cc.mode == 1 ? XL_FOLD_VCZT : XL_FOLD_HIGHNA; f.flags = cc.flags & XL_CONJ_OUT;
+    f.t = pl.tmp3; f.gx = (cf*)ct_in; f.gy = (cf*)ct_in + (size_t)N * N;
+    f.z = cc.mode == 1 ? cc.z : 0; f.x0 = cc.x0; f.y0 = cc.y0; f.dx = cc.dx; f.dy = cc.dy;
+    f.lens_R = cc.R; f.lens_f = cc.f; f.lens_s2 = cc.s2;
+    const size_t NN = (size_t)N * N;
+    return xl_launch<XlFold>(XlDim{(int)((NN + XlFold::NT - 1) / XlFold::NT), 1}, XlFold::NT * sizeof(float), st, f);
+}
+
+static CztCall make_czt_call(int mode, const double* z, double lambda, int N, int Mx, int My,
+                             double x0, double dx, double y0, double dy, double xout0, double xoutl, double yout0, double youtl,
+                             double R, double f, int flags) {
+    CztCall c;
+    memset(&c, 0, sizeof(c));
+    c.N = N; c.Mx = Mx; c.My = My; c.mode = mode; c.z = z; c.lambda = lambda; c.k = 2.0 * M_PI / lambda;
+    c.x0 = x0; c.dx = dx; c.y0 = y0; c.dy = dy; c.xout0 = xout0; c.xoutl = xoutl; c.yout0 = yout0; c.youtl = youtl;
+    c.R = R; c.f = f;
+    if (mode == 2) { double st = R / sqrt(R * R + f * f); c.s2 = st * st; }  // optical_elements.py:528
+    c.flags = flags;
+    return c;
+}
+
+extern "C" int xl_czt_fwd(const void* in, void* out, const double* z, double lambda, int N, int Mx, int My, int vectorial,
+                          double x0, double dx, double y0, double dy, double xout0, double xoutl, double yout0, double youtl,
+                          int flags, void* ws, size_t ws_bytes, void* stream) {
+    CztCall c = make_czt_call(vectorial ? 1 : 0, z, lambda, N, Mx, My, x0, dx, y0, dy, xout0, xoutl, yout0, youtl, 0, 0, flags);
+    return czt_forward(c, in, out, ws, ws_bytes, (xl_stream_t)stream);
+}
+extern "C" int xl_czt_bwd(const void* ct_out, void* ct_in, const double* z, double lambda, int N, int Mx, int My, int vectorial,
+                          double x0, double dx, double y0, double dy, double xout0, double xoutl, double yout0, double youtl,
+                          int flags, void* ws, size_t ws_bytes, void* stream) {
+    CztCall c = make_czt_call(vectorial ? 1 : 0, z, lambda, N, Mx, My, x0, dx, y0, dy, xout0, xoutl, yout0, youtl, 0, 0, flags);
+    return czt_backward(c, ct_out, ct_in, ws, ws_bytes, (xl_stream_t)stream);
+}
+extern "C" int xl_highna_fwd(const void* exy, void* out, int N, int Mx, int My, double radius, double f, double lambda,
+                             double x0, double dx, double y0, double dy, double xout0, double xoutl, double yout0, double youtl,
+                             int flags, void* ws, size_t ws_bytes, void* stream) {
+    CztCall c = make_czt_call(2, 0, lambda, N, Mx, My, x0, dx, y0, dy, xout0, xoutl, yout0, youtl, radius, f, flags);
+    return czt_forward(c, exy, out, ws, ws_bytes, (xl_stream_t)stream);
+}
+extern "C" int xl_highna_bwd(const void* ct_out, void* ct_exy, int N, int Mx, int My, double radius, double f, double lambda,
+                             double x0, double dx, double y0, double dy, double xout0, double xoutl, double yout0, double youtl,
+                             int flags, void* ws, size_t ws_bytes, void* stream) {
+    CztCall c = make_czt_call(2, 0, lambda, N, Mx, My, x0, dx, y0, dy, xout0, xoutl, yout0, youtl, radius, f, flags);
+    return czt_backward(c, ct_out, ct_exy, ws, ws_bytes, (xl_stream_t)stream);
+}
