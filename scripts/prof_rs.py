@@ -1,0 +1,21 @@
+"""Profile target: a few scalar-RS forward(+backward) calls at N (default 2048) -- run under ncu."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+import xlumina_b200 as xb
+from xlumina_b200 import ops
+N = int(sys.argv[1]) if len(sys.argv) > 1 else 2048
+mode = sys.argv[2] if len(sys.argv) > 2 else "fwd"
+dev = torch.device("cuda:0")
+x, y = xb.space(15000.0, N); lam = 0.6328; k = 2*np.pi/lam; dx = x[1]-x[0]
+u = torch.randn(N, N, dtype=torch.complex64, device=dev)
+z = torch.tensor([50000.0], dtype=torch.float64, device=dev)
+for it in range(3):
+    if mode == "fwd":
+        ops.rs_propagation(u, z, dx, dx, k)
+    elif mode == "grad":
+        uu = u.detach().requires_grad_(True); zz = z.detach().requires_grad_(True)
+        o = ops.rs_propagation(uu, zz, dx, dx, k); o.backward(o)
+    elif mode == "czt":
+        ops.czt(u, 5000.0, lam, x, y, x, y)
+torch.cuda.synchronize()

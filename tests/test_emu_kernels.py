@@ -1,0 +1,192 @@
+"""Kernel BODIES (xlumina_b200/csrc/*.cuh compiled with g++ -DXL_HOST_EMU, see conftest.emu) against the golden fixtures
+and the oracle, on the CPU.  This exercises every line of the device code's index math, butterflies, twiddles, chirp
+tables and fused factors through the same C ABI the GPU library exports; the GPU parity proper is tests/test_gpu_parity.py.
+Tolerance: rel-L2 <= 1e-4 vs the complex128 reference (BASELINE.json north_star); observed ~3e-7."""
+import ctypes
+
+import numpy as np
+import pytest
+
+from conftest import golden, rel_l2
+from oracle import oracle_np as o
+
+TOL = 1e-4
+TIGHT = 5e-6
+
+
+def ptr(a):
+    return a.ctypes.data_as(ctypes.c_void_p) if a is not None else None
+
+
+def c64(a):
+    return np.ascontiguousarray(a, dtype=np.complex64)
+
+
+def rs_fwd(emu, field, x, y, lam, z, nfields=1):
+    N = field.shape[-1]
+    fin = c64(field)
+    out = np.zeros_like(fin)
+    H = np.zeros(emu.xl_rs_transfer_bytes(N), np.uint8)
+    ws = np.zeros(emu.xl_rs_workspace_bytes(N, nfields, 1), np.uint8)
+    zz = np.array([z], np.float64)
+    rc = emu.xl_rs_fwd(ptr(fin), ptr(out), ptr(H), ptr(zz), N, nfields, x[1] - x[0], y[1] - y[0], 2 * np.pi / lam, 0,
+                       ptr(ws), ws.size, None)
+    assert rc == 0, emu.xl_last_error()
+    return out, H, ws, zz
+
+
+@pytest.mark.parametrize("name", ["rs_n32_zpos", "rs_n32_zneg", "rs_n48_far"])
+def test_rs_forward_and_vjp_golden(emu, name):
+    g = golden(name)
+    x, y, lam, z = g["x"], g["y"], float(g["wavelength"]), float(g["z"])
+    N = len(x)
+    out, H, ws, zz = rs_fwd(emu, g["field"], x, y, lam, z)
+    assert rel_l2(out, g["out"]) < TIGHT
+    ct = c64(g["ct"])
+    gin = np.zeros((N, N), np.complex64)
+    gz = np.zeros(1)
+    rc = emu.xl_rs_bwd(ptr(c64(g["field"])), ptr(ct), ptr(gin), ptr(gz), ptr(H), ptr(zz), N, 1, x[1] - x[0], y[1] - y[0],
+                       2 * np.pi / lam, 0, ptr(ws), ws.size, None)
+    assert rc == 0, emu.xl_last_error()
+    if "vjp_field" in g:
+        assert rel_l2(gin, g["vjp_field"]) < TIGHT
+    assert abs(gz[0] - float(g["vjp_z"])) < TOL * abs(float(g["vjp_z"]))
+
+
+def test_rs_batched_fields_and_reuse_flag(emu):
+    g = golden("rs_n32_zpos")
+    x, y, lam, z = g["x"], g["y"], float(g["wavelength"]), float(g["z"])
+    rng = np.random.default_rng(0)
+    f3 = np.stack([g["field"], rng.standard_normal((32, 32)) + 0j, 1j * g["field"]])
+    out, H, ws, zz = rs_fwd(emu, f3, x, y, lam, z, nfields=3)
+    assert rel_l2(out[0], g["out"]) < TIGHT and rel_l2(out[2], 1j * g["out"]) < TIGHT
+    out2 = np.zeros_like(out)
+    rc = emu.xl_rs_fwd(ptr(c64(f3)), ptr(out2), ptr(H), ptr(zz), 32, 3, x[1] - x[0], y[1] - y[0], 2 * np.pi / lam, 16,
+                       ptr(ws), ws.size, None)
+    assert rc == 0 and np.array_equal(out, out2)
+
+
+def test_rs_reference_test_config(emu):
+    g = golden("scalar_gaussian_n64")
+    out, *_ = rs_fwd(emu, g["field"], g["x"], g["y"], float(g["wavelength"]), float(g["z"]))
+    assert rel_l2(out, g["rs_out"]) < TIGHT
+
+
+@pytest.mark.parametrize("N", [9, 17, 50, 100])
+def test_rs_non_power_of_two_sizes(emu, N):
+    rng = np.random.default_rng(N)
+    x = np.linspace(-300, 300, N)
+    f = rng.standard_normal((N, N)) + 1j * rng.standard_normal((N, N))
+    ref, _ = o.RS_propagation(f, x, x, 0.6328, 2500.0)
+    out, *_ = rs_fwd(emu, f, x, x, 0.6328, 2500.0)
+    assert rel_l2(out, ref) < TIGHT
+
+
+@pytest.mark.parametrize("name", ["vrs_n24", "vrs_n40_zneg"])
+def test_vrs_forward_and_vjp_golden(emu, name):
+    g = golden(name)
+    x, y, lam, z = g["x"], g["y"], float(g["wavelength"]), float(g["z"])
+    N = len(x)
+    exy = c64(np.stack([g["Ex"], g["Ey"]]))
+    out = np.zeros((3, N, N), np.complex64)
+    H = np.zeros(emu.xl_rs_transfer_bytes(N), np.uint8)
+    ws = np.zeros(emu.xl_rs_workspace_bytes(N, 3, 1), np.uint8)
+    zz = np.array([z])
+    k = 2 * np.pi / lam
+    assert emu.xl_vrs_fwd(ptr(exy), ptr(out), ptr(H), ptr(zz), N, x[0], y[0], x[1] - x[0], y[1] - y[0], k, 0, ptr(ws), ws.size, None) == 0
+    assert rel_l2(out, g["out"]) < TIGHT
+    gin = np.zeros((2, N, N), np.complex64)
+    gz = np.zeros(1)
+    assert emu.xl_vrs_bwd(ptr(exy), ptr(c64(g["ct"])), ptr(gin), ptr(gz), ptr(H), ptr(zz), N, x[0], y[0], x[1] - x[0], y[1] - y[0],
+                          k, 0, ptr(ws), ws.size, None) == 0
+    if "vjp_field" in g:
+        assert rel_l2(gin, g["vjp_field"]) < TIGHT
+    assert abs(gz[0] - float(g["vjp_z"])) < TOL * abs(float(g["vjp_z"]))
+
+
+def czt_call(emu, fn, a, b, g, vect, flags=0):
+    x, y, xo, yo = g["x"], g["y"], g["xout"], g["yout"]
+    N, Mx, My = len(x), len(xo), len(yo)
+    ws = np.zeros(emu.xl_czt_workspace_bytes(N, Mx, My, vect), np.uint8)
+    zz = np.array([float(g["z"])])
+    rc = fn(ptr(a), ptr(b), ptr(zz), float(g["wavelength"]), N, Mx, My, vect, x[0], x[1] - x[0], y[0], y[1] - y[0],
+            xo[0], xo[-1], yo[0], yo[-1], flags, ptr(ws), ws.size, None)
+    assert rc == 0, emu.xl_last_error()
+
+
+@pytest.mark.parametrize("name", ["czt_n32_m24x40", "czt_n24_m50", "czt_n40_same"])
+def test_czt_forward_and_vjp_golden(emu, name):
+    g = golden(name)
+    out = np.zeros(g["out"].shape, np.complex64)
+    czt_call(emu, emu.xl_czt_fwd, c64(g["field"]), out, g, 0)
+    assert rel_l2(out, g["out"]) < TIGHT
+    if "vjp_field" in g:
+        gin = np.zeros(g["field"].shape, np.complex64)
+        czt_call(emu, emu.xl_czt_bwd, c64(g["ct"]), gin, g, 0)
+        assert rel_l2(gin, g["vjp_field"]) < TIGHT
+
+
+def test_czt_reference_test_config(emu):
+    g = golden("scalar_gaussian_n64")
+    g = dict(g, xout=g["x"], yout=g["y"])
+    out = np.zeros((64, 64), np.complex64)
+    czt_call(emu, emu.xl_czt_fwd, c64(g["field"]), out, g, 0)
+    assert rel_l2(out, g["czt_out"]) < TIGHT
+
+
+def test_vczt_forward_and_vjp_golden(emu):
+    g = golden("vczt_n24_m30")
+    out = np.zeros(g["out"].shape, np.complex64)
+    exy = c64(np.stack([g["Ex"], g["Ey"]]))
+    czt_call(emu, emu.xl_czt_fwd, exy, out, g, 1)
+    assert rel_l2(out, g["out"]) < TIGHT
+    gin = np.zeros((2, 24, 24), np.complex64)
+    czt_call(emu, emu.xl_czt_bwd, c64(g["ct"]), gin, g, 1)
+    assert rel_l2(gin, g["vjp_field"]) < TIGHT
+    # torch convention through the fused conjugation flags: conj(J^T conj(ct))
+    gin2 = np.zeros((2, 24, 24), np.complex64)
+    czt_call(emu, emu.xl_czt_bwd, c64(np.conj(g["ct"])), gin2, g, 1, flags=3)
+    assert rel_l2(np.conj(gin2), g["vjp_field"]) < TIGHT
+
+
+@pytest.mark.parametrize("name", ["highna_n24_m20", "highna_n40_m30x26"])
+def test_highna_forward_and_vjp_golden(emu, name):
+    g = golden(name)
+    x, y, xo, yo = g["x"], g["y"], g["xout"], g["yout"]
+    N, Mx, My = len(x), len(xo), len(yo)
+    exy = c64(np.stack([g["Ex"], g["Ey"]]))
+    out = np.zeros((3, My, Mx), np.complex64)
+    ws = np.zeros(emu.xl_highna_workspace_bytes(N, Mx, My), np.uint8)
+    args = (N, Mx, My, float(g["radius"]), float(g["f"]), float(g["wavelength"]), x[0], x[1] - x[0], y[0], y[1] - y[0],
+            xo[0], xo[-1], yo[0], yo[-1], 0, ptr(ws), ws.size, None)
+    assert emu.xl_highna_fwd(ptr(exy), ptr(out), *args) == 0, emu.xl_last_error()
+    assert rel_l2(out, g["out"]) < TIGHT
+    if "vjp_field" in g:
+        gin = np.zeros((2, N, N), np.complex64)
+        assert emu.xl_highna_bwd(ptr(c64(g["ct"])), ptr(gin), *args) == 0, emu.xl_last_error()
+        assert rel_l2(gin, g["vjp_field"]) < TIGHT
+
+
+def test_highna_odd_n_nan_like_reference(emu):
+    N, M = 9, 6
+    x = np.linspace(-100, 100, N)
+    xo = np.linspace(-1, 1, M)
+    exy = np.ones((2, N, N), np.complex64)
+    out = np.zeros((3, M, M), np.complex64)
+    ws = np.zeros(emu.xl_highna_workspace_bytes(N, M, M), np.uint8)
+    assert emu.xl_highna_fwd(ptr(exy), ptr(out), N, M, M, 90.0, 100.0, 0.635, x[0], x[1] - x[0], x[0], x[1] - x[0],
+                             xo[0], xo[-1], xo[0], xo[-1], 0, ptr(ws), ws.size, None) == 0
+    assert np.isnan(out).any()
+
+
+def test_error_codes(emu):
+    f = np.zeros((8, 8), np.complex64)
+    z = np.array([1.0])
+    ws = np.zeros(1 << 16, np.uint8)
+    H = np.zeros(1 << 16, np.uint8)
+    assert emu.xl_rs_fwd(None, ptr(f), ptr(H), ptr(z), 8, 1, 1.0, 1.0, 1.0, 0, ptr(ws), ws.size, None) == -1     # null
+    assert emu.xl_rs_fwd(ptr(f), ptr(f), ptr(H), ptr(z), 8, 1, 1.0, 1.0, 1.0, 0, ptr(ws), 16, None) == -3        # workspace
+    assert emu.xl_rs_padded_length(4096) == 0 and emu.xl_rs_padded_length(2048) == 4096
+    assert emu.xl_czt_padded_length(32, 33) == 0           # m+M-1 == 64: the reference raises too
+    assert emu.xl_czt_padded_length(2048, 2048) == 4096 and emu.xl_czt_padded_length(1024, 400) == 2048
+    assert b"workspace" in emu.xl_last_error() or emu.xl_last_error() is not None
