@@ -1,0 +1,261 @@
+"""GPU parity tests (run on the B200 with -m gpu).  Everything goes through the public Python API -> torch plumbing ->
+the C ABI of libxlprop.so -> the sm_100a kernels, and is compared with the CPU oracle / golden fixtures.
+Tolerance: rel-L2 <= 1e-4 vs the complex128 reference in fields and gradients (BASELINE.json north_star)."""
+import numpy as np
+import pytest
+
+from conftest import golden, rel_l2
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def xb():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import xlumina_b200 as xb
+    from xlumina_b200 import _lib
+    _lib.lib()           # must load the in-tree CUDA library; no fallback exists
+    return xb
+
+
+def dev_c64(a):
+    return torch.as_tensor(np.ascontiguousarray(a, dtype=np.complex64), device="cuda")
+
+
+def crand(rng, *shape):
+    return rng.standard_normal(shape) + 1j * rng.standard_normal(shape)
+
+
+# ------------------------------------------------------------------------------------------- golden fixtures
+@pytest.mark.parametrize("name", ["rs_n32_zpos", "rs_n32_zneg", "rs_n48_far"])
+def test_rs_golden_forward_and_gradients(xb, name):
+    g = golden(name)
+    lam, z = float(g["wavelength"]), float(g["z"])
+    light = xb.ScalarLight(g["x"], g["y"], lam)
+    light.field = dev_c64(g["field"]).requires_grad_(True)
+    zt = torch.tensor(z, dtype=torch.float64, device="cuda", requires_grad=True)
+    out, q = light.RS_propagation(zt)
+    assert rel_l2(out.field.detach().cpu().numpy(), g["out"]) < TOL
+    assert abs(float(q) - float(g["quality"])) < 1e-9 * float(g["quality"])
+    L = torch.real(torch.sum(dev_c64(g["ct"]) * out.field))      # JAX cotangent ct  <=>  torch grad conj(ct)
+    L.backward()
+    if "vjp_field" in g:
+        assert rel_l2(np.conj(light.field.grad.cpu().numpy()), g["vjp_field"]) < TOL
+    assert abs(float(zt.grad) - float(g["vjp_z"])) < TOL * abs(float(g["vjp_z"]))
+
+
+def test_reference_test_configs_scalar(xb):
+    """tests/test_wave_optics.py:43-53 of the reference (shape assertions) + values from the golden run at N=64."""
+    g = golden("scalar_gaussian_n64")
+    lam, z = float(g["wavelength"]), float(g["z"])
+    src = xb.LightSource(g["x"], g["y"], lam)
+    src.gaussian_beam(w0=(1200, 1200), E0=1)
+    assert rel_l2(src.field.cpu().numpy(), g["field"]) < 1e-6
+    out, _ = src.RS_propagation(z=z)
+    assert out.field.shape == (64, 64)
+    assert rel_l2(out.field.cpu().numpy(), g["rs_out"]) < TOL
+    c = src.CZT(z=z)
+    assert c.field.shape == (64, 64)
+    assert rel_l2(c.field.cpu().numpy(), g["czt_out"]) < TOL
+
+
+@pytest.mark.parametrize("name", ["vrs_n24", "vrs_n40_zneg"])
+def test_vrs_golden_forward_and_gradients(xb, name):
+    g = golden(name)
+    lam, z = float(g["wavelength"]), float(g["z"])
+    li = xb.VectorizedLight(g["x"], g["y"], lam)
+    li.Ex = dev_c64(g["Ex"]).requires_grad_(True)
+    li.Ey = dev_c64(g["Ey"]).requires_grad_(True)
+    zt = torch.tensor(z, dtype=torch.float64, device="cuda", requires_grad=True)
+    out, _ = li.VRS_propagation(zt)
+    E = torch.stack([out.Ex, out.Ey, out.Ez])
+    assert rel_l2(E.detach().cpu().numpy(), g["out"]) < TOL
+    torch.real(torch.sum(dev_c64(g["ct"]) * E)).backward()
+    if "vjp_field" in g:
+        got = np.conj(np.stack([li.Ex.grad.cpu().numpy(), li.Ey.grad.cpu().numpy()]))
+        assert rel_l2(got, g["vjp_field"]) < TOL
+    assert abs(float(zt.grad) - float(g["vjp_z"])) < TOL * abs(float(g["vjp_z"]))
+
+
+@pytest.mark.parametrize("name", ["czt_n32_m24x40", "czt_n24_m50", "czt_n40_same"])
+def test_czt_golden_forward_and_gradient(xb, name):
+    g = golden(name)
+    li = xb.ScalarLight(g["x"], g["y"], float(g["wavelength"]))
+    li.field = dev_c64(g["field"]).requires_grad_(True)
+    out = li.CZT(float(g["z"]), g["xout"], g["yout"])
+    assert out.field.shape == g["out"].shape
+    assert rel_l2(out.field.detach().cpu().numpy(), g["out"]) < TOL
+    if "vjp_field" in g:
+        torch.real(torch.sum(dev_c64(g["ct"]) * out.field)).backward()
+        assert rel_l2(np.conj(li.field.grad.cpu().numpy()), g["vjp_field"]) < TOL
+
+
+def test_vczt_golden_forward_and_gradient(xb):
+    g = golden("vczt_n24_m30")
+    li = xb.VectorizedLight(g["x"], g["y"], float(g["wavelength"]))
+    li.Ex = dev_c64(g["Ex"]).requires_grad_(True)
+    li.Ey = dev_c64(g["Ey"]).requires_grad_(True)
+    out = li.VCZT(float(g["z"]), g["xout"], g["yout"])
+    E = torch.stack([out.Ex, out.Ey, out.Ez])
+    assert rel_l2(E.detach().cpu().numpy(), g["out"]) < TOL
+    torch.real(torch.sum(dev_c64(g["ct"]) * E)).backward()
+    got = np.conj(np.stack([li.Ex.grad.cpu().numpy(), li.Ey.grad.cpu().numpy()]))
+    assert rel_l2(got, g["vjp_field"]) < TOL
+
+
+@pytest.mark.parametrize("name", ["highna_n24_m20", "highna_n40_m30x26"])
+def test_highna_golden_forward_and_gradient(xb, name):
+    g = golden(name)
+    li = xb.VectorizedLight(g["x"], g["y"], float(g["wavelength"]))
+    li.Ex = dev_c64(g["Ex"]).requires_grad_(True)
+    li.Ey = dev_c64(g["Ey"]).requires_grad_(True)
+    out = xb.VCZT_objective_lens(li, float(g["radius"]), float(g["f"]), g["xout"], g["yout"])
+    E = torch.stack([out.Ex, out.Ey, out.Ez])
+    assert rel_l2(E.detach().cpu().numpy(), g["out"]) < TOL
+    if "vjp_field" in g:
+        torch.real(torch.sum(dev_c64(g["ct"]) * E)).backward()
+        got = np.conj(np.stack([li.Ex.grad.cpu().numpy(), li.Ey.grad.cpu().numpy()]))
+        assert rel_l2(got, g["vjp_field"]) < TOL
+
+
+# ------------------------------------------------------------------------------------------- oracle, mid sizes
+@pytest.mark.parametrize("N,z", [(100, 4000.0), (256, 50000.0), (512, -20000.0), (1024, 1000.0)])
+def test_rs_vs_oracle(xb, N, z):
+    from oracle import oracle_np as o
+    o.set_workers(8)
+    rng = np.random.default_rng(N)
+    x, y = xb.space(1500.0, N)
+    u = crand(rng, N, N)
+    ref, _ = o.RS_propagation(u, x, y, 0.633, z)
+    li = xb.ScalarLight(x, y, 0.633)
+    li.field = dev_c64(u)
+    out, _ = li.RS_propagation(z)
+    assert rel_l2(out.field.cpu().numpy(), ref) < TOL
+
+
+def test_reference_test_configs_vectorial_n1024(xb):
+    """tests/test_vectorized_optics.py:54-74 and tests/test_optical_elements.py:128-136 of the reference (their shapes at
+    their sizes), plus values against the oracle."""
+    from oracle import oracle_np as o
+    o.set_workers(8)
+    N, lam = 1024, 633e-3
+    x = np.linspace(-1500, 1500, N)
+    src = xb.PolarizedLightSource(x, x, lam)
+    src.gaussian_beam(w0=(1200, 1200), jones_vector=(1, 1))
+    ex, ey = src.Ex.cpu().numpy().astype(complex), src.Ey.cpu().numpy().astype(complex)
+    v, _ = src.VRS_propagation(z=1000)
+    assert v.Ex.shape == v.Ey.shape == v.Ez.shape == (N, N)
+    ref, _ = o.VRS_propagation(ex, ey, x, x, lam, 1000)
+    assert rel_l2(torch.stack([v.Ex, v.Ey, v.Ez]).cpu().numpy(), ref) < TOL
+    c = src.VCZT(1000, x, x)
+    assert c.Ex.shape == (N, N)
+    assert rel_l2(torch.stack([c.Ex, c.Ey, c.Ez]).cpu().numpy(), o.VCZT(ex, ey, x, x, lam, 1000, x, x)) < TOL
+    N2 = 512
+    x2 = np.linspace(-1500, 1500, N2)
+    s2 = xb.PolarizedLightSource(x2, x2, lam)
+    s2.gaussian_beam(w0=(1200, 1200), jones_vector=(1, 0))
+    f = xb.VCZT_objective_lens(s2, 1800.0, 2000.0, x2, x2)
+    assert f.Ex.shape == (N2, N2)
+    ref = o.VCZT_objective_lens(s2.Ex.cpu().numpy().astype(complex), s2.Ey.cpu().numpy().astype(complex), x2, x2, lam,
+                                1800.0, 2000.0, x2, x2)
+    assert rel_l2(torch.stack([f.Ex, f.Ey, f.Ez]).cpu().numpy(), ref) < TOL
+
+
+def test_hybrid_config_highna_1024_to_400_with_gradient(xb):
+    """cfg 3 building block (experiments/hybrid_sharp_optical_table.py:26-46): N=1024, 2500 um window, 635 nm, NA 0.9."""
+    from oracle import oracle_torch as ot
+    rng = np.random.default_rng(5)
+    N = 1024
+    x, y = xb.space(2500.0, N)
+    xo, yo = xb.space(10.0, 400)
+    ex, ey = crand(rng, N, N), crand(rng, N, N)
+    ct = crand(rng, 3, 400, 400)
+    li = xb.VectorizedLight(x, y, 0.635)
+    li.Ex = dev_c64(ex).requires_grad_(True)
+    li.Ey = dev_c64(ey).requires_grad_(True)
+    out = xb.VCZT_objective_lens(li, 1800.0, 2000.0, xo, yo)
+    E = torch.stack([out.Ex, out.Ey, out.Ez])
+    torch.real(torch.sum(dev_c64(ct) * E)).backward()
+    tex = torch.tensor(ex, requires_grad=True)
+    tey = torch.tensor(ey, requires_grad=True)
+    ref = ot.VCZT_objective_lens(tex, tey, x, y, 0.635, 1800.0, 2000.0, xo, yo)
+    torch.real(torch.sum(torch.tensor(ct) * ref)).backward()
+    assert rel_l2(E.detach().cpu().numpy(), ref.detach().numpy()) < TOL
+    assert rel_l2(li.Ex.grad.cpu().numpy(), tex.grad.numpy()) < TOL
+    assert rel_l2(li.Ey.grad.cpu().numpy(), tey.grad.numpy()) < TOL
+
+
+# ------------------------------------------------------------------------------------------- full size (2048^2): properties
+def test_rs_2048_properties(xb):
+    """At BASELINE.json's size the oracle is slow, so use size-independent properties:
+    linearity, complex symmetry <ct, A u> = <A ct, u>, direct-sum spot checks and dz by finite differences."""
+    from oracle import oracle_np as o
+    rng = np.random.default_rng(7)
+    N, lam = 2048, 0.6328
+    x, y = xb.space(15000.0, N)
+    dx = x[1] - x[0]
+    k = 2 * np.pi / lam
+    u = rng.standard_normal((N, N)).astype(np.float32) + 1j * rng.standard_normal((N, N)).astype(np.float32)
+    ct = rng.standard_normal((N, N)).astype(np.float32) + 1j * rng.standard_normal((N, N)).astype(np.float32)
+    U, CT = dev_c64(u), dev_c64(ct)
+    z = torch.tensor([50000.0], dtype=torch.float64, device="cuda", requires_grad=True)
+    A = lambda f: xb.ops.rs_propagation(f, z, dx, dx, k)
+    Au, Act = A(U), A(CT)
+    lin = A(2.5 * U - 1j * CT)
+    assert rel_l2(lin.detach().cpu().numpy(), (2.5 * Au - 1j * Act).detach().cpu().numpy()) < 1e-5
+    lhs = torch.sum(CT.to(torch.complex128) * Au.detach().to(torch.complex128))
+    rhs = torch.sum(Act.detach().to(torch.complex128) * U.to(torch.complex128))
+    assert abs(lhs - rhs) / abs(lhs) < 1e-5
+    pts = [(0, 0), (5, 2040), (1024, 1024), (2047, 2047), (1300, 17)]
+    d = o.rs_direct_sum(u.astype(np.complex128), x, y, lam, 50000.0, pts)
+    got = Au.detach().cpu().numpy()
+    for i, (p, q) in enumerate(pts):
+        assert abs(got[p, q] - d[i]) < TOL * np.abs(d).max()
+    # d/dz of Re<ct, A(z) u> against central differences of the GPU forward itself (fp64 accumulation of the contraction)
+    L = torch.real(torch.sum(CT * Au))
+    L.backward()
+    eps = 0.01
+    with torch.no_grad():
+        fp = torch.real(torch.sum(CT.to(torch.complex128) * xb.ops.rs_propagation(U, z + eps, dx, dx, k).to(torch.complex128)))
+        fm = torch.real(torch.sum(CT.to(torch.complex128) * xb.ops.rs_propagation(U, z - eps, dx, dx, k).to(torch.complex128)))
+    fd = float((fp - fm) / (2 * eps))
+    assert abs(float(z.grad) - fd) < 2e-3 * abs(fd)     # FD truncation (k*eps)^2/6 ~ 1.6e-3 dominates this check
+
+
+def test_czt_2048_adjoint_identity(xb):
+    rng = np.random.default_rng(8)
+    N = 2048
+    x, y = xb.space(15000.0, N)
+    u = dev_c64(crand(rng, N, N)).requires_grad_(True)
+    ct = dev_c64(crand(rng, N, N))
+    du = dev_c64(crand(rng, N, N))
+    out = xb.ops.czt(u, 5000.0, 0.6328, x, y, x, y)
+    torch.real(torch.sum(ct * out)).backward()
+    with torch.no_grad():
+        lhs = torch.sum(ct.to(torch.complex128) * xb.ops.czt(du, 5000.0, 0.6328, x, y, x, y).to(torch.complex128))
+        rhs = torch.sum(torch.conj(u.grad).to(torch.complex128) * du.to(torch.complex128))
+    assert abs(lhs - rhs) / abs(lhs) < 1e-5
+
+
+def test_energy_conservation_well_sampled(xb):
+    """toolbox.is_conserving_energy (reference toolbox.py:74-96) ~ 1 for a well-sampled propagation."""
+    from xlumina_b200.toolbox import is_conserving_energy
+    x, y = xb.space(1500.0, 1024)
+    src = xb.LightSource(x, y, 0.6328)
+    src.gaussian_beam(w0=(400, 400), E0=1)
+    out, q = src.RS_propagation(20000.0)
+    assert abs(float(is_conserving_energy(src, out)) - 1.0) < 1e-3
+
+
+def test_errors_are_loud(xb):
+    from xlumina_b200._lib import XlpropError
+    x, y = xb.space(100.0, 33)
+    li = xb.ScalarLight(x, y, 0.5)
+    with pytest.raises(XlpropError):
+        li.CZT(100.0, np.linspace(-1, 1, 32), np.linspace(-1, 1, 32))   # m+M-1 == 64: reference raises too
+    with pytest.raises(XlpropError):
+        xb.ops.rs_propagation(torch.zeros(4096, 4096, dtype=torch.complex64, device="cuda"), 1.0, 1.0, 1.0, 1.0)
