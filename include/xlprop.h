@@ -114,6 +114,14 @@ int xl_highna_bwd(const void* ct_out, void* ct_exy, int N, int Mx, int My, doubl
                   double x0, double dx, double y0, double dy, double xout0, double xoutl, double yout0, double youtl,
                   int flags, void* ws, size_t ws_bytes, void* stream);
 
+/* ---------------------------------------------------------------- instrumentation (bench.py) ---------------- */
+/* Number of kernels this library has launched in this process. */
+long long xl_launch_count(void);
+/* Per-kernel timing with CUDA events recorded on the launching stream: xl_prof_enable(1) clears and starts recording,
+ * xl_prof_report() synchronises the recorded events and writes "name count total_ms" lines; xl_prof_enable(0) stops. */
+void xl_prof_enable(int on);
+int xl_prof_report(char* buf, int cap);
+
 #ifdef __cplusplus
 }
 #endif

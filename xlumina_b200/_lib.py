@@ -33,6 +33,9 @@ SIGNATURES = {
     "xl_czt_bwd": (_i, [_vp, _vp, _vp, _d, _i, _i, _i, _i, _d, _d, _d, _d, _d, _d, _d, _d, _i, _vp, _sz, _vp]),
     "xl_highna_workspace_bytes": (_sz, [_i, _i, _i]),
     "xl_highna_fwd": (_i, [_vp, _vp, _i, _i, _i, _d, _d, _d, _d, _d, _d, _d, _d, _d, _d, _d, _i, _vp, _sz, _vp]),
+    "xl_launch_count": (ctypes.c_longlong, []),
+    "xl_prof_enable": (None, [_i]),
+    "xl_prof_report": (_i, [ctypes.c_char_p, _i]),
     "xl_highna_bwd": (_i, [_vp, _vp, _i, _i, _i, _d, _d, _d, _d, _d, _d, _d, _d, _d, _d, _d, _i, _vp, _sz, _vp]),
 }
 

@@ -28,6 +28,48 @@ extern "C" const char* xl_last_error(void) { return g_err; }
 // ------------------------------------------------------------------------------------------------ launch
 struct XlDim { int x, y; };
 
+// Instrumentation for bench.py: a launch counter (always on) and optional per-kernel CUDA-event timing recorded on the
+// launching stream (xl_prof_enable(1); ...; xl_prof_report()).  Event pairs are pooled; nothing is allocated when off.
+static long long g_launches = 0;
+static int g_prof_on = 0;
+#ifndef XL_HOST_EMU
+struct XlProfRec { const char* name; cudaEvent_t e0, e1; };
+static std::vector<XlProfRec> g_prof;
+#endif
+extern "C" long long xl_launch_count(void) { return g_launches; }
+extern "C" void xl_prof_enable(int on) {
+    g_prof_on = on;
+#ifndef XL_HOST_EMU
+    if (on) {
+        for (auto& r : g_prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+        g_prof.clear();
+    }
+#endif
+}
+// Writes lines "name count total_ms\n" into buf (after synchronising the recorded events); returns bytes written.
+extern "C" int xl_prof_report(char* buf, int cap) {
+    int n = 0;
+    if (cap > 0) buf[0] = 0;
+#ifndef XL_HOST_EMU
+    struct Acc { const char* name; int count; double ms; };
+    std::vector<Acc> acc;
+    for (auto& r : g_prof) {
+        cudaEventSynchronize(r.e1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, r.e0, r.e1);
+        bool found = false;
+        for (auto& a : acc) if (a.name == r.name) { a.count++; a.ms += ms; found = true; break; }
+        if (!found) acc.push_back(Acc{r.name, 1, (double)ms});
+    }
+    for (auto& a : acc) {
+        int w = snprintf(buf + n, cap > n ? cap - n : 0, "%s %d %.6f\n", a.name, a.count, a.ms);
+        if (w < 0 || n + w >= cap) break;
+        n += w;
+    }
+#endif
+    return n;
+}
+
 #ifndef XL_HOST_EMU
 template <class Body> __global__ void __launch_bounds__(Body::NT) xl_kernel(const typename Body::Params p) {
     extern __shared__ float4 xl_smem[];
@@ -37,6 +79,7 @@ template <class Body> __global__ void __launch_bounds__(Body::NT) xl_kernel(cons
 
 template <class Body> static int xl_launch(XlDim grid, size_t smem, xl_stream_t stream, const typename Body::Params& p) {
     if (grid.x <= 0 || grid.y <= 0) return XL_OK;
+    ++g_launches;
 #ifdef XL_HOST_EMU
     (void)stream;
     std::vector<char> buf(smem + 64);
@@ -55,7 +98,14 @@ template <class Body> static int xl_launch(XlDim grid, size_t smem, xl_stream_t 
         if (e != cudaSuccess) return xl_fail(XL_E_CUDA, "cudaFuncSetAttribute: %s (smem %lld)", cudaGetErrorString(e), (long long)smem);
         attr_set[dev] = true;
     }
+    XlProfRec rec;
+    if (g_prof_on) {
+        rec.name = Body::name();
+        cudaEventCreate(&rec.e0); cudaEventCreate(&rec.e1);
+        cudaEventRecord(rec.e0, stream);
+    }
     xl_kernel<Body><<<dim3(grid.x, grid.y, 1), dim3(Body::NT, 1, 1), smem, stream>>>(p);
+    if (g_prof_on) { cudaEventRecord(rec.e1, stream); g_prof.push_back(rec); }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return xl_fail(XL_E_CUDA, "kernel launch: %s", cudaGetErrorString(e));
     return XL_OK;

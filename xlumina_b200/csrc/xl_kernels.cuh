@@ -106,6 +106,7 @@ template <int L> struct XlRsRowsFwdOp {
     XL_DEV void store(int, int, cf) const {}
 };
 template <int L> struct XlRsRowsFwd {
+    static const char* name() { return "rs_rows_fwd"; }
     typedef XlRsParams Params;
     static constexpr int NT = xl_threads(L, XL_CW);
     XL_DEV static void run(const Params& p, cf* s) {
@@ -125,6 +126,7 @@ template <int L> struct XlRsColsOp {
     XL_DEV void store(int c, int i, cf val) const { if (i < p.N) tile[(size_t)i * XL_CW + c] = val; }
 };
 template <int L> struct XlRsCols {
+    static const char* name() { return "rs_cols"; }
     typedef XlRsParams Params;
     static constexpr int NT = xl_threads(L, XL_CW);
     XL_DEV static void run(const Params& p, cf* s) {
@@ -155,6 +157,7 @@ template <int L> struct XlRsRowsInvOp {
     }
 };
 template <int L> struct XlRsRowsInv {
+    static const char* name() { return "rs_rows_inv"; }
     typedef XlRsParams Params;
     static constexpr int NT = xl_threads(L, XL_CW);
     XL_DEV static void run(const Params& p, cf* s) {
@@ -185,6 +188,7 @@ template <int L> struct XlHRowsOp {
     XL_DEV void store(int, int, cf) const {}
 };
 template <int L> struct XlHRows {
+    static const char* name() { return "h_rows"; }
     typedef XlRsParams Params;
     static constexpr int NT = xl_threads(L, XL_CW);
     XL_DEV static void run(const Params& p, cf* s) {
@@ -204,6 +208,7 @@ template <int L> struct XlHColsOp {
     XL_DEV void store(int, int, cf) const {}
 };
 template <int L> struct XlHCols {
+    static const char* name() { return "h_cols"; }
     typedef XlRsParams Params;
     static constexpr int NT = xl_threads(L, XL_CW);
     XL_DEV static void run(const Params& p, cf* s) {
@@ -241,6 +246,7 @@ template <int L> struct XlRsColsGzOp {
     XL_DEV void store(int c, int i, cf val) const { if (i < p.N) tile[(size_t)i * XL_CW + c] = val; }
 };
 template <int L> struct XlRsColsGz {
+    static const char* name() { return "rs_cols_gz"; }
     typedef XlRsParams Params;
     static constexpr int NT = xl_threads(L, XL_CW);
     static constexpr int NRED = (L / 16) * XL_CW;
@@ -385,6 +391,7 @@ template <int L> struct XlCztOp {
     }
 };
 template <int L> struct XlCztAxis {
+    static const char* name() { return "czt_axis"; }
     typedef XlCztParams Params;
     static constexpr int NT = xl_threads(L, XL_CW);
     XL_DEV static void run(const Params& p, cf* s) {
@@ -451,6 +458,7 @@ template <int L> struct XlCztSetupOp {
     XL_DEV void store(int, int, cf) const {}
 };
 template <int L> struct XlCztSetup {
+    static const char* name() { return "czt_setup"; }
     typedef XlCztSetupParams Params;
     static constexpr int NT = xl_threads(L, XL_CW);
     XL_DEV static void run(const Params& p, cf* s) {
@@ -496,6 +504,7 @@ struct XlFoldParams {
     double lens_R, lens_f, lens_s2;
 };
 struct XlFold {
+    static const char* name() { return "fold"; }
     typedef XlFoldParams Params;
     static constexpr int NT = 256;
     XL_DEV static void run(const Params& p, cf* s) {

@@ -174,9 +174,9 @@ def rs_propagation(field, z, dx, dy, k):
 
 
 def vrs_propagation(Ex, Ey, z, x0, y0, dx, dy, k):
-    """Vectorial RS: returns (3,N,N) = propagated [Ex, Ey, Ez]."""
+    """Vectorial RS: returns (3,N,N) = propagated [Ex, Ey, Ez].  Pass Ey=None if `Ex` is already the stacked (2,N,N) pair."""
     dt = Ex.dtype
-    exy = torch.stack([_c64(Ex), _c64(Ey)], dim=0)
+    exy = _c64(Ex) if Ey is None else torch.stack([_c64(Ex), _c64(Ey)], dim=0)
     zt = _as_z(z, exy)
     out = _VRS.apply(exy, zt, float(x0), float(y0), float(dx), float(dy), float(k))
     return out if dt == torch.complex64 or not torch.is_complex(Ex) else out.to(dt)
@@ -283,16 +283,18 @@ def czt(field, z, wavelength, x, y, xout, yout):
 
 
 def vczt(Ex, Ey, z, wavelength, x, y, xout, yout):
-    """Vectorial CZT: (Ex,Ey) -> (3, len(yout), len(xout)); Ez = ((Ex X + Ey Y)/r) z/r formed at load."""
+    """Vectorial CZT: (Ex,Ey) -> (3, len(yout), len(xout)); Ez = ((Ex X + Ey Y)/r) z/r formed at load.
+    Pass Ey=None if `Ex` is already the stacked (2,N,N) pair."""
     dt = Ex.dtype
-    exy = torch.stack([_c64(Ex), _c64(Ey)], dim=0)
+    exy = _c64(Ex) if Ey is None else torch.stack([_c64(Ex), _c64(Ey)], dim=0)
     out = _CZT.apply(exy, _as_z(z, exy).detach(), float(wavelength), 1, _gin(x, y, exy.shape[-1]), _gout(xout, yout))
     return out if dt == torch.complex64 or not torch.is_complex(Ex) else out.to(dt)
 
 
 def highna_focus(Ex, Ey, radius, f, wavelength, x, y, xout, yout):
-    """High-NA objective + Debye integral by 2-pass Bluestein: (Ex,Ey) -> focal-plane (3, len(yout), len(xout))."""
+    """High-NA objective + Debye integral by 2-pass Bluestein: (Ex,Ey) -> focal-plane (3, len(yout), len(xout)).
+    Pass Ey=None if `Ex` is already the stacked (2,N,N) pair."""
     dt = Ex.dtype
-    exy = torch.stack([_c64(Ex), _c64(Ey)], dim=0)
+    exy = _c64(Ex) if Ey is None else torch.stack([_c64(Ex), _c64(Ey)], dim=0)
     out = _HighNA.apply(exy, float(radius), float(f), float(wavelength), _gin(x, y, exy.shape[-1]), _gout(xout, yout))
     return out if dt == torch.complex64 or not torch.is_complex(Ex) else out.to(dt)
