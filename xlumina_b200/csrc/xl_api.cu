@@ -71,14 +71,16 @@ extern "C" int xl_prof_report(char* buf, int cap) {
 }
 
 #ifndef XL_HOST_EMU
-template <class Body> __global__ void __launch_bounds__(Body::NT) xl_kernel(const typename Body::Params p) {
+// register budget: at least 512/NT CTAs per SM (128 registers per thread), so two L=4096 CTAs overlap their phases on an SM
+template <class Body> __global__ void __launch_bounds__(Body::NT, (512 / Body::NT) > 16 ? 16 : (512 / Body::NT)) xl_kernel(const typename Body::Params p) {
     extern __shared__ float4 xl_smem[];
     Body::run(p, (cf*)xl_smem);
 }
 #endif
 
-template <class Body> static int xl_launch(XlDim grid, size_t smem, xl_stream_t stream, const typename Body::Params& p) {
+template <class Body> static int xl_launch(XlDim grid, xl_stream_t stream, const typename Body::Params& p) {
     if (grid.x <= 0 || grid.y <= 0) return XL_OK;
+    const size_t smem = Body::smem();
     ++g_launches;
 #ifdef XL_HOST_EMU
     (void)stream;
@@ -112,20 +114,20 @@ template <class Body> static int xl_launch(XlDim grid, size_t smem, xl_stream_t 
 #endif
 }
 
-#define XL_FOR_L(L, CALL)                                     \
+#define XL_FOR_L(L, ...)                                      \
     switch (L) {                                              \
-        case 32: { constexpr int XL = 32; CALL; } break;      \
-        case 64: { constexpr int XL = 64; CALL; } break;      \
-        case 128: { constexpr int XL = 128; CALL; } break;    \
-        case 256: { constexpr int XL = 256; CALL; } break;    \
-        case 512: { constexpr int XL = 512; CALL; } break;    \
-        case 1024: { constexpr int XL = 1024; CALL; } break;  \
-        case 2048: { constexpr int XL = 2048; CALL; } break;  \
-        case 4096: { constexpr int XL = 4096; CALL; } break;  \
+        case 32: { constexpr int XL = 32; __VA_ARGS__; } break;      \
+        case 64: { constexpr int XL = 64; __VA_ARGS__; } break;      \
+        case 128: { constexpr int XL = 128; __VA_ARGS__; } break;    \
+        case 256: { constexpr int XL = 256; __VA_ARGS__; } break;    \
+        case 512: { constexpr int XL = 512; __VA_ARGS__; } break;    \
+        case 1024: { constexpr int XL = 1024; __VA_ARGS__; } break;  \
+        case 2048: { constexpr int XL = 2048; __VA_ARGS__; } break;  \
+        case 4096: { constexpr int XL = 4096; __VA_ARGS__; } break;  \
         default: return xl_fail(XL_E_UNSUPPORTED, "padded length %s%lld outside [32,4096]", "", (long long)(L)); \
     }
 
-static size_t tile_bytes(int L) { return (size_t)xl_tile_elems(L, XL_CW) * sizeof(cf); }
+static int xl_groups(int n) { return (n + XL_V - 1) / XL_V; }   // CTAs needed for n lines
 
 // ------------------------------------------------------------------------------------------------ twiddles
 static std::mutex g_tw_mutex;
@@ -198,7 +200,7 @@ extern "C" size_t xl_rs_workspace_bytes(int N, int nfields, int want_grad_z) {
     if (!L || nfields < 1) return 0;
     size_t spec = align_up((size_t)nfields * L * N * sizeof(cf));
     size_t total = spec;
-    if (want_grad_z) total += spec + align_up(L * L * sizeof(cf)) + align_up((size_t)nfields * L * L * sizeof(cf));
+    if (want_grad_z) total += spec + align_up(L * L * sizeof(cf));
     total += align_up((size_t)3 * N * N * sizeof(cf));  // VRS backward: adjoint of the 3 components before the fold
     return total;
 }
@@ -220,9 +222,9 @@ static int rs_transfer_impl(XlRsParams p, cf* H, const double* z, int deriv, xl_
     p.flags = deriv ? XL_F_DERIV : 0;
     const int L = p.L;
     int rc;
-    XL_FOR_L(L, rc = xl_launch<XlHRows<XL>>(XlDim{(L / 2 + 1 + XL_CW - 1) / XL_CW, 1}, tile_bytes(XL), st, p));
+    XL_FOR_L(L, rc = xl_launch<XlHRows<XL>>(XlDim{xl_groups(L / 2 + 1), 1}, st, p));
     if (rc) return rc;
-    XL_FOR_L(L, rc = xl_launch<XlHCols<XL>>(XlDim{L / XL_CW, 1}, tile_bytes(XL), st, p));
+    XL_FOR_L(L, rc = xl_launch<XlHCols<XL>>(XlDim{L / XL_V, 1}, st, p));
     return rc;
 }
 
@@ -238,11 +240,11 @@ extern "C" int xl_rs_transfer(void* H, const double* z, int N, double dx, double
 static int rs_apply_impl(XlRsParams p, xl_stream_t st) {
     const int L = p.L, N = p.N;
     int rc;
-    XL_FOR_L(L, rc = xl_launch<XlRsRowsFwd<XL>>(XlDim{(N + XL_CW - 1) / XL_CW, p.nfields}, tile_bytes(XL), st, p));
+    XL_FOR_L(L, rc = xl_launch<XlRsRowsFwd<XL>>(XlDim{xl_groups(N), p.nfields}, st, p));
     if (rc) return rc;
-    XL_FOR_L(L, rc = xl_launch<XlRsCols<XL>>(XlDim{L / XL_CW, p.nfields}, tile_bytes(XL), st, p));
+    XL_FOR_L(L, rc = xl_launch<XlRsCols<XL>>(XlDim{L / XL_V, p.nfields}, st, p));
     if (rc) return rc;
-    XL_FOR_L(L, rc = xl_launch<XlRsRowsInv<XL>>(XlDim{(N + XL_CW - 1) / XL_CW, p.nfields}, tile_bytes(XL), st, p));
+    XL_FOR_L(L, rc = xl_launch<XlRsRowsInv<XL>>(XlDim{xl_groups(N), p.nfields}, st, p));
     return rc;
 }
 
@@ -293,30 +295,28 @@ static int rs_bwd_common(const void* in, const void* ct_out, void* ct_in, double
     if (grad_z) {
         p.spec2 = (cf*)c.take(spec_bytes);
         cf* Hz = (cf*)c.take((size_t)L * L * sizeof(cf));
-        p.scratch = (cf*)c.take((size_t)nfields * L * L * sizeof(cf));
         rc = rs_transfer_impl(p, Hz, z, 1, st);
         if (rc) return rc;
         // row spectra of conj(U) -> spec2
         XlRsParams pw = p;
         pw.in = (const cf*)in; pw.spec = p.spec2;
         pw.flags = XL_F_CONJ_IN | (vrs ? XL_F_VRS : 0);
-        XL_FOR_L(L, rc = xl_launch<XlRsRowsFwd<XL>>(XlDim{(N + XL_CW - 1) / XL_CW, nfields}, tile_bytes(XL), st, pw));
+        XL_FOR_L(L, rc = xl_launch<XlRsRowsFwd<XL>>(XlDim{xl_groups(N), nfields}, st, pw));
         if (rc) return rc;
         // row spectra of the cotangent -> spec
         XlRsParams pc = p;
         pc.in = (const cf*)ct_out;
         pc.flags = (flags & XL_CONJ_IN);
-        XL_FOR_L(L, rc = xl_launch<XlRsRowsFwd<XL>>(XlDim{(N + XL_CW - 1) / XL_CW, nfields}, tile_bytes(XL), st, pc));
+        XL_FOR_L(L, rc = xl_launch<XlRsRowsFwd<XL>>(XlDim{xl_groups(N), nfields}, st, pc));
         if (rc) return rc;
         XlRsParams pg = p;
         pg.H2 = Hz; pg.gz = grad_z;
-        XL_FOR_L(L, rc = xl_launch<XlRsColsGz<XL>>(XlDim{L / XL_CW, nfields},
-                                                   tile_bytes(XL) + (XlRsColsGz<XL>::NRED + 32) * sizeof(float), st, pg));
+        XL_FOR_L(L, rc = xl_launch<XlRsColsGz<XL>>(XlDim{L / XL_V, nfields}, st, pg));
         if (rc) return rc;
         XlRsParams po = p;
         po.out = dst;
         po.flags = vrs ? 0 : (flags & XL_CONJ_OUT);
-        XL_FOR_L(L, rc = xl_launch<XlRsRowsInv<XL>>(XlDim{(N + XL_CW - 1) / XL_CW, nfields}, tile_bytes(XL), st, po));
+        XL_FOR_L(L, rc = xl_launch<XlRsRowsInv<XL>>(XlDim{xl_groups(N), nfields}, st, po));
         if (rc) return rc;
     } else {
         XlRsParams pa = p;
@@ -334,7 +334,7 @@ static int rs_bwd_common(const void* in, const void* ct_out, void* ct_in, double
         f.gx = (cf*)ct_in; f.gy = (cf*)ct_in + (size_t)N * N;
         f.gz = grad_z; f.z = z; f.x0 = x0; f.y0 = y0; f.dx = dx; f.dy = dy;
         const size_t NN = (size_t)N * N;
-        rc = xl_launch<XlFold>(XlDim{(int)((NN + XlFold::NT - 1) / XlFold::NT), 1}, XlFold::NT * sizeof(float), st, f);
+        rc = xl_launch<XlFold>(XlDim{(int)((NN + XlFold::NT - 1) / XlFold::NT), 1}, st, f);
     }
     return rc;
 }
@@ -400,12 +400,12 @@ static int czt_setup(const CztPlan& pl, const double* z, double lambda_over_dx, 
     // y axis (first Bluestein pass, wave_optics.py:349)
     s.L = pl.Ly; s.m = pl.N; s.M = pl.My; s.out0 = yout0; s.outl = youtl;
     s.pre = pl.pre_y; s.post = pl.post_y; s.ft = pl.ft_y; s.ftT = pl.ftT_y;
-    XL_FOR_L(pl.Ly, rc = xl_launch<XlCztSetup<XL>>(XlDim{1, 1}, tile_bytes(XL), st, s));
+    XL_FOR_L(pl.Ly, rc = xl_launch<XlCztSetup<XL>>(XlDim{1, 1}, st, s));
     if (rc) return rc;
     // x axis (second pass, :352)
     s.L = pl.Lx; s.m = pl.N; s.M = pl.Mx; s.out0 = xout0; s.outl = xoutl;
     s.pre = pl.pre_x; s.post = pl.post_x; s.ft = pl.ft_x; s.ftT = pl.ftT_x;
-    XL_FOR_L(pl.Lx, rc = xl_launch<XlCztSetup<XL>>(XlDim{1, 1}, tile_bytes(XL), st, s));
+    XL_FOR_L(pl.Lx, rc = xl_launch<XlCztSetup<XL>>(XlDim{1, 1}, st, s));
     return rc;
 }
 
@@ -426,6 +426,21 @@ static void czt_common_params(XlCztParams& a, const CztCall& cc, const cf* tw) {
 static void czt_out_const(XlCztParams& a, const CztCall& cc) {
     if (cc.mode == 2) { a.epi_cr = 0.0; a.epi_ci = -cc.s2 / (cc.f * cc.lambda); a.epi_times_z = 0; }   // optical_elements.py:627
     else { a.epi_cr = cc.dx * cc.dy * cc.lambda; a.epi_ci = 0.0; a.epi_times_z = 1; }                   // wave_optics.py:355
+}
+
+template <int PRO, int EPI> static int czt_axis_launch_t(const XlCztParams& a, XlDim grid, xl_stream_t st) {
+    int rc;
+    XL_FOR_L(a.L, rc = xl_launch<XlCztAxis<XL, PRO, EPI>>(grid, st, a));
+    return rc;
+}
+// the five (prologue, epilogue) combinations the forward and adjoint chains use, each compiled branch-free
+static int czt_axis_launch(const XlCztParams& a, XlDim grid, xl_stream_t st) {
+    if (a.pro == XL_PRO_NONE && a.epi == XL_EPI_NONE) return czt_axis_launch_t<XL_PRO_NONE, XL_EPI_NONE>(a, grid, st);
+    if (a.pro == XL_PRO_NONE && a.epi == XL_EPI_RSF) return czt_axis_launch_t<XL_PRO_NONE, XL_EPI_RSF>(a, grid, st);
+    if (a.pro == XL_PRO_RSF && a.epi == XL_EPI_NONE) return czt_axis_launch_t<XL_PRO_RSF, XL_EPI_NONE>(a, grid, st);
+    if (a.pro == XL_PRO_VCZT && a.epi == XL_EPI_NONE) return czt_axis_launch_t<XL_PRO_VCZT, XL_EPI_NONE>(a, grid, st);
+    if (a.pro == XL_PRO_HIGHNA && a.epi == XL_EPI_NONE) return czt_axis_launch_t<XL_PRO_HIGHNA, XL_EPI_NONE>(a, grid, st);
+    return xl_fail(XL_E_BAD_ARG, "czt: unsupported prologue/epilogue combination%s", "");
 }
 
 static int czt_forward(const CztCall& cc, const void* in, void* out, void* ws, size_t ws_bytes, xl_stream_t st) {
@@ -452,7 +467,7 @@ static int czt_forward(const CztCall& cc, const void* in, void* out, void* ws, s
     a.pro = cc.mode == 0 ? XL_PRO_RSF : (cc.mode == 1 ? XL_PRO_VCZT : XL_PRO_HIGHNA);
     a.gpro = XlGridFactor{cc.x0, cc.dx, cc.y0, cc.dy, 0};
     a.epi = XL_EPI_NONE;
-    XL_FOR_L(pl.Ly, rc = xl_launch<XlCztAxis<XL>>(XlDim{(N + XL_CW - 1) / XL_CW, ncomp}, tile_bytes(XL), st, a));
+    rc = czt_axis_launch(a, XlDim{xl_groups(N), ncomp}, st);
     if (rc) return rc;
     // pass 2: Bluestein along x for every column of the intermediate
     XlCztParams b;
@@ -466,7 +481,7 @@ static int czt_forward(const CztCall& cc, const void* in, void* out, void* ws, s
     b.gepi = XlGridFactor{cc.xout0, dxo, cc.yout0, dyo, 1};
     czt_out_const(b, cc);
     b.flags = cc.flags & XL_CONJ_OUT;
-    XL_FOR_L(pl.Lx, rc = xl_launch<XlCztAxis<XL>>(XlDim{(My + XL_CW - 1) / XL_CW, ncomp}, tile_bytes(XL), st, b));
+    rc = czt_axis_launch(b, XlDim{xl_groups(My), ncomp}, st);
     return rc;
 }
 
@@ -496,7 +511,7 @@ static int czt_backward(const CztCall& cc, const void* ct_out, void* ct_in, void
     b.epi = XL_EPI_NONE;
     czt_out_const(b, cc);
     b.flags = cc.flags & XL_CONJ_IN;
-    XL_FOR_L(pl.Lx, rc = xl_launch<XlCztAxis<XL>>(XlDim{(My + XL_CW - 1) / XL_CW, ncomp}, tile_bytes(XL), st, b));
+    rc = czt_axis_launch(b, XlDim{xl_groups(My), ncomp}, st);
     if (rc) return rc;
     // transpose of pass 1: rows of the intermediate cotangent (length My) -> columns of ct_field
     XlCztParams a;
@@ -509,7 +524,7 @@ static int czt_backward(const CztCall& cc, const void* ct_out, void* ct_in, void
     a.epi = cc.mode == 2 ? XL_EPI_NONE : XL_EPI_RSF;
     a.gepi = XlGridFactor{cc.x0, cc.dx, cc.y0, cc.dy, 0};
     a.flags = cc.mode == 0 ? (cc.flags & XL_CONJ_OUT) : 0;
-    XL_FOR_L(pl.Ly, rc = xl_launch<XlCztAxis<XL>>(XlDim{(N + XL_CW - 1) / XL_CW, ncomp}, tile_bytes(XL), st, a));
+    rc = czt_axis_launch(a, XlDim{xl_groups(N), ncomp}, st);
     if (rc || cc.mode == 0) return rc;
     XlFoldParams f;
     memset(&f, 0, sizeof(f));
@@ -518,7 +533,7 @@ static int czt_backward(const CztCall& cc, const void* ct_out, void* ct_in, void
     f.z = cc.mode == 1 ? cc.z : 0; f.x0 = cc.x0; f.y0 = cc.y0; f.dx = cc.dx; f.dy = cc.dy;
     f.lens_R = cc.R; f.lens_f = cc.f; f.lens_s2 = cc.s2;
     const size_t NN = (size_t)N * N;
-    return xl_launch<XlFold>(XlDim{(int)((NN + XlFold::NT - 1) / XlFold::NT), 1}, XlFold::NT * sizeof(float), st, f);
+    return xl_launch<XlFold>(XlDim{(int)((NN + XlFold::NT - 1) / XlFold::NT), 1}, st, f);
 }
 
 static CztCall make_czt_call(int mode, const double* z, double lambda, int N, int Mx, int My,

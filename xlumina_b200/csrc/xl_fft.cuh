@@ -1,254 +1,345 @@
-// xl_fft.cuh -- shared-memory radix-decomposed complex64 FFT engine for one CTA.
+// xl_fft.cuh -- shared-memory radix-decomposed complex64 FFT engine for one CTA (engine v3).
 //
-// A CTA owns a tile of V "lines" (rows or columns of the 2-D problem), each of power-of-two length L, stored in shared
-// memory interleaved as tile[pad(i)][c] (c = line, innermost).  Thread work is always indexed (c fastest, then butterfly),
-// so that a warp touches V adjacent lines x 32/V adjacent positions: 32-byte (V=4 columns) or 64-byte (V=4 rows)
-// global segments and conflict-free shared-memory phases (pad(i) = i + i/16).
+// A CTA owns V "lines" (rows or columns of the 2-D problem; V = 1 or 2), each of power-of-two length L, in a shared-memory
+// tile tile[pad(i)][V] (pad(i) = i + i/16; one LDS.64 / LDS.128 per position, conflict-free in every pass).  A thread
+// owns the same butterfly of all V lines, so twiddle factors are loaded / derived once per thread and reused V times.
+// Complex numbers are (re, im) float2 register pairs and all arithmetic is Blackwell f32x2 (FADD2 / FMUL2 / FFMA2 with
+// swap / half-negate / broadcast operand modifiers, xl_platform.h): one instruction per complex add, two per complex multiply.
 //
 // Forward = in-place decimation-in-frequency:  natural order in  -> digit-permuted spectrum out.
 // Inverse = in-place decimation-in-time:       digit-permuted spectrum in -> natural order out.
-// Radix plan: L = r * 16^a, passes (r, 16, ..., 16) with r in {2,4,8,16} FIRST, so every pass but the last has
-// stride >= 16 and the last pass works on 16 contiguous elements.  After the last forward pass the thread that owns
-// butterfly `beta` holds, in v[q], the DFT bin of "slot" q*(L/16)+beta; the same thread starts the inverse from the
-// same registers, so  forward-last / spectrum multiply / inverse-first  are fused in registers (XlConv).
-// The slot order is an arbitrary but fixed permutation of the frequency bins: transfer functions are produced by the
-// same forward code, hence in the same order, and no reordering pass ever exists.
+// Radix plan: L = r * 16^a, passes (r, 16, ..., 16) with r in {2,4,8,16} FIRST, so every pass but the last has stride >= 16
+// and the last pass works on 16 contiguous positions.  After the last forward pass the thread that owns butterfly `beta`
+// holds, in v[q], the DFT bin of "slot" q*(L/16)+beta; the same thread starts the inverse from the same registers, so
+// forward-last / spectrum multiply / inverse-first  are fused in registers (conv()).
+// The slot order is an arbitrary but fixed permutation of the frequency bins: transfer functions are produced by the same
+// forward code, hence in the same order, and no reordering pass ever exists.
 //
-// The first forward pass reads its operands through op.load(c,i) and the last inverse pass emits through
-// op.store(c,i,v): zero padding, cropping, analytic factors and layout changes live in those functors and never touch HBM.
+// Twiddles: per pass level (block B, radix R) two small tables live in shared memory, A[n] = w_B^n and (R == 16)
+// C[n] = w_B^(8n), n < B/R (4.3 KB in total for L = 4096); the other powers are products of depth <= 3.
+//
+// The first forward pass reads through op.load(i, v, stride) (all V lines of position i) (with Op::kInLoHalf only the lower half: the upper half is zero
+// padding, pruned at compile time) and the last inverse pass emits through op.store_vec() (Op::kOutLoHalf: only the lower
+// half of the positions is computed): zero padding, cropping, analytic factors and layout changes live in those functors
+// and never touch HBM.
 #pragma once
 #include "xl_platform.h"
 
-#define XL_TWN 16384  // twiddle table: tw[k] = exp(-2*pi*i*k/XL_TWN), generated in fp64
+#define XL_TWN 16384  // master twiddle table in global memory: tw[k] = exp(-2*pi*i*k/XL_TWN), generated in fp64
 
-constexpr int xl_first_radix(int L) { return L > 16 ? xl_first_radix(L / 16) : L; }
-constexpr int xl_tile_elems(int L, int V) { return (L + L / 16) * V; }
-constexpr int xl_threads(int L, int V) { return (L * V / 32) < 32 ? 32 : ((L * V / 32) > 512 ? 512 : (L * V / 32)); }
+XL_HD constexpr int xl_first_radix(int L) { return L > 16 ? xl_first_radix(L / 16) : L; }
+XL_HD constexpr int xl_tile_elems(int L, int V) { return (L + L / 16) * V; }          // cf elements of the padded tile
+XL_HD constexpr int xl_threads(int L) { return (L / 16) < 32 ? 32 : (L / 16); }
+XL_HD constexpr int xl_tw_mids(int B) { return B >= 256 ? 2 * (B / 16) + xl_tw_mids(B / 16) : 0; }
+XL_HD constexpr int xl_tw_level0(int L) { return (L / xl_first_radix(L)) * (xl_first_radix(L) == 16 ? 2 : 1); }
+XL_HD constexpr int xl_tw_total(int L) { return xl_tw_level0(L) + xl_tw_mids(L / xl_first_radix(L)); }
+// offset (in cf) of the tables of the mid level with block size B
+XL_HD constexpr int xl_tw_off_mid(int L, int B) {
+    int off = xl_tw_level0(L);
+    for (int b = L / xl_first_radix(L); b > B; b /= 16) off += 2 * (b / 16);
+    return off;
+}
+XL_HD constexpr size_t xl_smem_bytes(int L, int V) { return (size_t)(xl_tile_elems(L, V) + xl_tw_total(L)) * 8; }
 
-template <int V> XL_DEV int xl_tidx(int i, int c) { return (i + (i >> 4)) * V + c; }
+XL_DEV int xl_pad(int i) { return i + (i >> 4); }
 
+// tile access: all V lines of one position in a single shared-memory transaction; line l lands in v[l * stride]
+template <int V> struct XlTile;
+template <> struct XlTile<1> {
+    XL_DEV static void ld(const cf* s, int i, cf* v, int) { v[0] = s[xl_pad(i)]; }
+    XL_DEV static void st(cf* s, int i, const cf* v, int) { s[xl_pad(i)] = v[0]; }
+};
+template <> struct XlTile<2> {
+    XL_DEV static void ld(const cf* s, int i, cf* v, int stride) {
+        const float4 t = *reinterpret_cast<const float4*>(s + 2 * xl_pad(i));
+        v[0] = make_float2(t.x, t.y);
+        v[stride] = make_float2(t.z, t.w);
+    }
+    XL_DEV static void st(cf* s, int i, const cf* v, int stride) {
+        *reinterpret_cast<float4*>(s + 2 * xl_pad(i)) = make_float4(v[0].x, v[0].y, v[stride].x, v[stride].y);
+    }
+};
+
+// a + DIR*i*b
+template <int DIR> XL_DEV cf xl_addi(cf a, cf b) { return DIR > 0 ? cf_add(a, cf_muli(b)) : cf_add(a, cf_mulni(b)); }
 // multiply by (wr + i*DIR*wi)
 template <int DIR> XL_DEV cf xl_mulw(cf a, float wr, float wi) {
-    return DIR < 0 ? make_float2(a.x * wr + a.y * wi, a.y * wr - a.x * wi)
-                   : make_float2(a.x * wr - a.y * wi, a.y * wr + a.x * wi);
+    return DIR < 0 ? cf_mulc(a, make_float2(wr, wi)) : cf_mul(a, make_float2(wr, wi));
 }
-// multiply by DIR*i
-template <int DIR> XL_DEV cf xl_muli(cf a) { return DIR < 0 ? make_float2(a.y, -a.x) : make_float2(-a.y, a.x); }
+template <int DIR> XL_DEV cf xl_muli(cf a) { return DIR < 0 ? cf_mulni(a) : cf_muli(a); }
 
-template <int DIR> XL_DEV void xl_fft4(cf& a0, cf& a1, cf& a2, cf& a3) {
-    cf t0 = cf_add(a0, a2), t1 = cf_sub(a0, a2), t2 = cf_add(a1, a3), t3 = xl_muli<DIR>(cf_sub(a1, a3));
-    a0 = cf_add(t0, t2); a2 = cf_sub(t0, t2); a1 = cf_add(t1, t3); a3 = cf_sub(t1, t3);
+// 4-point DFT, sign DIR.  INLO: a2 = a3 = 0 on entry (never read).  OUTLO: only a0, a1 are produced.
+template <int DIR, bool INLO, bool OUTLO> XL_DEV void xl_fft4(cf& a0, cf& a1, cf& a2, cf& a3) {
+    if (INLO) {
+        const cf x0 = a0, x1 = a1;
+        a0 = cf_add(x0, x1);
+        a1 = xl_addi<DIR>(x0, x1);
+        if (!OUTLO) { a2 = cf_sub(x0, x1); a3 = xl_addi<-DIR>(x0, x1); }
+    } else {
+        const cf t0 = cf_add(a0, a2), t1 = cf_sub(a0, a2), t2 = cf_add(a1, a3), d = cf_sub(a1, a3);
+        a0 = cf_add(t0, t2);
+        a1 = xl_addi<DIR>(t1, d);
+        if (!OUTLO) { a2 = cf_sub(t0, t2); a3 = xl_addi<-DIR>(t1, d); }
+    }
 }
 
 // In-register DFT of R points, sign DIR (-1: exp(-2 pi i jq/R)); result in natural order.
-template <int R, int DIR> struct XlBfly;
-template <int DIR> struct XlBfly<2, DIR> {
-    XL_DEV static void run(cf* v) { cf a = v[0]; v[0] = cf_add(a, v[1]); v[1] = cf_sub(a, v[1]); }
+// INLO: inputs v[R/2..R) are zero (never read).  OUTLO: only outputs v[0..R/2) are produced.
+template <int R, int DIR, bool INLO, bool OUTLO> struct XlBfly;
+template <int DIR, bool INLO, bool OUTLO> struct XlBfly<2, DIR, INLO, OUTLO> {
+    XL_DEV static void run(cf* v) {
+        if (INLO) { if (!OUTLO) v[1] = v[0]; }
+        else { const cf a = v[0]; v[0] = cf_add(a, v[1]); if (!OUTLO) v[1] = cf_sub(a, v[1]); }
+    }
 };
-template <int DIR> struct XlBfly<4, DIR> {
-    XL_DEV static void run(cf* v) { xl_fft4<DIR>(v[0], v[1], v[2], v[3]); }
+template <int DIR, bool INLO, bool OUTLO> struct XlBfly<4, DIR, INLO, OUTLO> {
+    XL_DEV static void run(cf* v) { xl_fft4<DIR, INLO, OUTLO>(v[0], v[1], v[2], v[3]); }
 };
-template <int DIR> struct XlBfly<8, DIR> {
+template <int DIR, bool INLO, bool OUTLO> struct XlBfly<8, DIR, INLO, OUTLO> {
     XL_DEV static void run(cf* v) {
         const float r = 0.70710678118654752f;
+        // layer 1: radix-2 over (j, j+4); outputs q1 = 0 -> v[j], q1 = 1 -> v[4+j]
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { cf a = v[j]; v[j] = cf_add(a, v[4 + j]); v[4 + j] = cf_sub(a, v[4 + j]); }
+        for (int j = 0; j < 4; ++j) {
+            if (INLO) v[4 + j] = v[j];
+            else { const cf a = v[j]; v[j] = cf_add(a, v[4 + j]); v[4 + j] = cf_sub(a, v[4 + j]); }
+        }
         v[5] = xl_mulw<DIR>(v[5], r, r);
         v[6] = xl_muli<DIR>(v[6]);
         v[7] = xl_mulw<DIR>(v[7], -r, r);
-        xl_fft4<DIR>(v[0], v[1], v[2], v[3]);
-        xl_fft4<DIR>(v[4], v[5], v[6], v[7]);
+        // layer 2: 4-point DFTs over j within each q1; output q = q1 + 2*q2 comes from v[4*q1 + q2]
+        xl_fft4<DIR, false, OUTLO>(v[0], v[1], v[2], v[3]);
+        xl_fft4<DIR, false, OUTLO>(v[4], v[5], v[6], v[7]);
         cf t[8];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) t[q] = v[4 * (q % 2) + q / 2];
+        for (int q = 0; q < (OUTLO ? 4 : 8); ++q) t[q] = v[4 * (q % 2) + q / 2];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) v[q] = t[q];
+        for (int q = 0; q < (OUTLO ? 4 : 8); ++q) v[q] = t[q];
     }
 };
-template <int DIR> struct XlBfly<16, DIR> {
+template <int DIR, bool INLO, bool OUTLO> struct XlBfly<16, DIR, INLO, OUTLO> {
     XL_DEV static void run(cf* v) {
         const float c1 = 0.92387953251128674f, s1 = 0.38268343236508977f, r = 0.70710678118654752f;
+        // layer 1: 4-point DFTs over j1 (inputs 4*j1 + j2); output q1 lands in v[4*q1 + j2]
 #pragma unroll
-        for (int j = 0; j < 4; ++j) xl_fft4<DIR>(v[j], v[4 + j], v[8 + j], v[12 + j]);
+        for (int j = 0; j < 4; ++j) xl_fft4<DIR, INLO, false>(v[j], v[4 + j], v[8 + j], v[12 + j]);
         // v[4*q1 + j2] *= w16^(j2*q1)
-        v[5] = xl_mulw<DIR>(v[5], c1, s1);    // e=1
-        v[6] = xl_mulw<DIR>(v[6], r, r);      // e=2
-        v[7] = xl_mulw<DIR>(v[7], s1, c1);    // e=3
-        v[9] = xl_mulw<DIR>(v[9], r, r);      // e=2
-        v[10] = xl_muli<DIR>(v[10]);          // e=4
-        v[11] = xl_mulw<DIR>(v[11], -r, r);   // e=6
-        v[13] = xl_mulw<DIR>(v[13], s1, c1);  // e=3
-        v[14] = xl_mulw<DIR>(v[14], -r, r);   // e=6
+        v[5] = xl_mulw<DIR>(v[5], c1, s1);      // e=1
+        v[6] = xl_mulw<DIR>(v[6], r, r);        // e=2
+        v[7] = xl_mulw<DIR>(v[7], s1, c1);      // e=3
+        v[9] = xl_mulw<DIR>(v[9], r, r);        // e=2
+        v[10] = xl_muli<DIR>(v[10]);            // e=4
+        v[11] = xl_mulw<DIR>(v[11], -r, r);     // e=6
+        v[13] = xl_mulw<DIR>(v[13], s1, c1);    // e=3
+        v[14] = xl_mulw<DIR>(v[14], -r, r);     // e=6
         v[15] = xl_mulw<DIR>(v[15], -c1, -s1);  // e=9
+        // layer 2: 4-point DFTs over j2 within each q1; output q = q1 + 4*q2 comes from v[4*q1 + q2]
 #pragma unroll
-        for (int q1 = 0; q1 < 4; ++q1) xl_fft4<DIR>(v[4 * q1], v[4 * q1 + 1], v[4 * q1 + 2], v[4 * q1 + 3]);
+        for (int q1 = 0; q1 < 4; ++q1) xl_fft4<DIR, false, OUTLO>(v[4 * q1], v[4 * q1 + 1], v[4 * q1 + 2], v[4 * q1 + 3]);
         cf t[16];
 #pragma unroll
-        for (int q = 0; q < 16; ++q) t[q] = v[4 * (q % 4) + q / 4];
+        for (int q = 0; q < (OUTLO ? 8 : 16); ++q) t[q] = v[4 * (q % 4) + q / 4];
 #pragma unroll
-        for (int q = 0; q < 16; ++q) v[q] = t[q];
+        for (int q = 0; q < (OUTLO ? 8 : 16); ++q) v[q] = t[q];
     }
 };
 
-// v[q] *= w^(q*e), w = exp(DIR*2*pi*i/XL_TWN); requires (R-1)*e < XL_TWN.  4 table loads + products of depth <= 2.
-template <int R, int DIR> XL_DEV void xl_twiddle(cf* v, const cf* XL_RESTRICT tw, int e) {
-#define XL_TWMUL(a, w) (DIR < 0 ? cf_mul(a, w) : cf_mulc(a, w))
-    cf w1 = xl_ldg(tw + e);
-    v[1] = XL_TWMUL(v[1], w1);
-    if constexpr (R >= 4) {
-        cf w2 = xl_ldg(tw + 2 * e);
-        cf w3 = cf_mul(w1, w2);
-        v[2] = XL_TWMUL(v[2], w2);
-        v[3] = XL_TWMUL(v[3], w3);
-        if constexpr (R >= 8) {
-            cf w4 = xl_ldg(tw + 4 * e);
-            cf w5 = cf_mul(w4, w1), w6 = cf_mul(w4, w2), w7 = cf_mul(w4, w3);
-            v[4] = XL_TWMUL(v[4], w4);
-            v[5] = XL_TWMUL(v[5], w5);
-            v[6] = XL_TWMUL(v[6], w6);
-            v[7] = XL_TWMUL(v[7], w7);
-            if constexpr (R >= 16) {
-                cf w8 = xl_ldg(tw + 8 * e);
-                v[8] = XL_TWMUL(v[8], w8);
-                v[9] = XL_TWMUL(v[9], cf_mul(w8, w1));
-                v[10] = XL_TWMUL(v[10], cf_mul(w8, w2));
-                v[11] = XL_TWMUL(v[11], cf_mul(w8, w3));
-                v[12] = XL_TWMUL(v[12], cf_mul(w8, w4));
-                v[13] = XL_TWMUL(v[13], cf_mul(w8, w5));
-                v[14] = XL_TWMUL(v[14], cf_mul(w8, w6));
-                v[15] = XL_TWMUL(v[15], cf_mul(w8, w7));
-            }
-        }
+// powers w[q] = w1^q, q < R, from w1 and (R == 16) w8 = w1^8; products of depth <= 3
+template <int R> XL_DEV void xl_tw_powers(cf* w, cf w1, cf w8) {
+    w[1] = w1;
+    if (R >= 4) { w[2] = cf_mul(w1, w1); w[3] = cf_mul(w1, w[2]); }
+    if (R >= 8) {
+        w[4] = cf_mul(w[2], w[2]);
+#pragma unroll
+        for (int q = 1; q < 4; ++q) w[4 + q] = cf_mul(w[4], w[q]);
     }
-#undef XL_TWMUL
+    if (R >= 16) {
+        w[8] = w8;
+#pragma unroll
+        for (int q = 1; q < 8; ++q) w[8 + q] = cf_mul(w8, w[q]);
+    }
+}
+// v[q] *= w[q] (DIR<0) or conj(w[q]) (DIR>0) for q in [1, NQ)
+template <int NQ, int DIR> XL_DEV void xl_twiddle(cf* v, const cf* w) {
+#pragma unroll
+    for (int q = 1; q < NQ; ++q) v[q] = DIR < 0 ? cf_mul(v[q], w[q]) : cf_mulc(v[q], w[q]);
 }
 
-template <int L, int V, int NT> struct XlFft {
+// Default functor pieces; ops derive from this and override what they need.
+struct XlOpBase {
+    static constexpr bool kInLoHalf = false;   // load() is identically zero for i >= L/2 (compile-time pruning)
+    static constexpr bool kOutLoHalf = false;  // store_vec() only receives positions < L/2
+};
+
+template <int L, int V> struct XlFft {
+    static constexpr int NT = xl_threads(L);
     static constexpr int R1 = xl_first_radix(L);
     static constexpr int S1 = L / R1;
+    static constexpr int TILE = xl_tile_elems(L, V);
     static_assert(L >= 32 && (L & (L - 1)) == 0, "L must be a power of two >= 32");
+    static_assert(V == 1 || V == 2, "1 or 2 lines per CTA");
+
+    // copy this L's twiddle tables (xl_tw_total(L) entries) from the global master table into shared memory `t`
+    XL_DEV static void init_tw(cf* t, const cf* XL_RESTRICT gtw) {
+        XL_THREADS(tid, NT) {
+            for (int n = tid; n < S1; n += NT) {
+                t[n] = xl_ldg(gtw + n * (XL_TWN / L));
+                if (R1 == 16) t[S1 + n] = xl_ldg(gtw + 8 * n * (XL_TWN / L));
+            }
+            int off = xl_tw_level0(L);
+            for (int B = L / R1; B >= 256; B /= 16) {
+                const int nb = B / 16;
+                for (int n = tid; n < nb; n += NT) {
+                    t[off + n] = xl_ldg(gtw + n * (XL_TWN / B));
+                    t[off + nb + n] = xl_ldg(gtw + 8 * n * (XL_TWN / B));
+                }
+                off += 2 * nb;
+            }
+        }
+        XL_SYNC();
+    }
 
     // ---- forward ----
-    template <class Op> XL_DEV static void fwd_first(cf* s, const cf* XL_RESTRICT tw, const Op& op) {
+    template <class Op> XL_DEV static void fwd_first(cf* s, const cf* t, const Op& op) {
         XL_THREADS(tid, NT) {
-            for (int u = tid; u < S1 * V; u += NT) {
-                const int c = u % V, n = u / V;
-                cf v[R1];
+            for (int n = tid; n < S1; n += NT) {
+                cf v[V * R1];
 #pragma unroll
-                for (int j = 0; j < R1; ++j) v[j] = op.load(c, n + S1 * j);
-                XlBfly<R1, -1>::run(v);
-                xl_twiddle<R1, -1>(v, tw, n * (XL_TWN / L));
+                for (int j = 0; j < (Op::kInLoHalf ? R1 / 2 : R1); ++j) op.load(n + S1 * j, v + j, R1);   // line l -> v[l*R1 + j]
+                cf w[R1];
+                xl_tw_powers<R1>(w, t[n], R1 == 16 ? t[S1 + n] : cf_zero());
 #pragma unroll
-                for (int q = 0; q < R1; ++q) s[xl_tidx<V>(n + S1 * q, c)] = v[q];
+                for (int l = 0; l < V; ++l) {
+                    XlBfly<R1, -1, Op::kInLoHalf, false>::run(v + l * R1);
+                    xl_twiddle<R1, -1>(v + l * R1, w);
+                }
+#pragma unroll
+                for (int q = 0; q < R1; ++q) XlTile<V>::st(s, n + S1 * q, v + q, R1);
             }
         }
         XL_SYNC();
     }
-    template <int B> XL_DEV static void fwd_mid(cf* s, const cf* XL_RESTRICT tw) {
+    template <int B> XL_DEV static void fwd_mid(cf* s, const cf* tw) {
         constexpr int S = B / 16;
+        const cf* t = tw + xl_tw_off_mid(L, B);
         XL_THREADS(tid, NT) {
-            for (int u = tid; u < (L / 16) * V; u += NT) {
-                const int c = u % V, beta = u / V, b = beta / S, n = beta % S, base = b * B + n;
-                cf v[16];
+            for (int beta = tid; beta < L / 16; beta += NT) {
+                const int b = beta / S, n = beta % S, base = b * B + n;
+                cf v[V * 16];
 #pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] = s[xl_tidx<V>(base + S * j, c)];
-                XlBfly<16, -1>::run(v);
-                xl_twiddle<16, -1>(v, tw, n * (XL_TWN / B));
+                for (int j = 0; j < 16; ++j) XlTile<V>::ld(s, base + S * j, v + j, 16);
+                cf w[16];
+                xl_tw_powers<16>(w, t[n], t[S + n]);
 #pragma unroll
-                for (int q = 0; q < 16; ++q) s[xl_tidx<V>(base + S * q, c)] = v[q];
+                for (int l = 0; l < V; ++l) {
+                    XlBfly<16, -1, false, false>::run(v + l * 16);
+                    xl_twiddle<16, -1>(v + l * 16, w);
+                }
+#pragma unroll
+                for (int q = 0; q < 16; ++q) XlTile<V>::st(s, base + S * q, v + q, 16);
             }
         }
         XL_SYNC();
     }
-    template <int B> XL_DEV static void fwd_mids(cf* s, const cf* XL_RESTRICT tw) {
+    template <int B> XL_DEV static void fwd_mids(cf* s, const cf* tw) {
         if constexpr (B >= 256) { fwd_mid<B>(s, tw); fwd_mids<B / 16>(s, tw); }
     }
     // ---- inverse ----
-    template <int B> XL_DEV static void inv_mid(cf* s, const cf* XL_RESTRICT tw) {
+    template <int B> XL_DEV static void inv_mid(cf* s, const cf* tw) {
         constexpr int S = B / 16;
+        const cf* t = tw + xl_tw_off_mid(L, B);
         XL_THREADS(tid, NT) {
-            for (int u = tid; u < (L / 16) * V; u += NT) {
-                const int c = u % V, beta = u / V, b = beta / S, n = beta % S, base = b * B + n;
-                cf v[16];
+            for (int beta = tid; beta < L / 16; beta += NT) {
+                const int b = beta / S, n = beta % S, base = b * B + n;
+                cf v[V * 16];
 #pragma unroll
-                for (int q = 0; q < 16; ++q) v[q] = s[xl_tidx<V>(base + S * q, c)];
-                xl_twiddle<16, +1>(v, tw, n * (XL_TWN / B));
-                XlBfly<16, +1>::run(v);
+                for (int q = 0; q < 16; ++q) XlTile<V>::ld(s, base + S * q, v + q, 16);
+                cf w[16];
+                xl_tw_powers<16>(w, t[n], t[S + n]);
 #pragma unroll
-                for (int j = 0; j < 16; ++j) s[xl_tidx<V>(base + S * j, c)] = v[j];
+                for (int l = 0; l < V; ++l) {
+                    xl_twiddle<16, +1>(v + l * 16, w);
+                    XlBfly<16, +1, false, false>::run(v + l * 16);
+                }
+#pragma unroll
+                for (int j = 0; j < 16; ++j) XlTile<V>::st(s, base + S * j, v + j, 16);
             }
         }
         XL_SYNC();
     }
-    template <int B> XL_DEV static void inv_mids(cf* s, const cf* XL_RESTRICT tw) {
+    template <int B> XL_DEV static void inv_mids(cf* s, const cf* tw) {
         if constexpr (B >= 256) { inv_mids<B / 16>(s, tw); inv_mid<B>(s, tw); }
     }
-    template <class Op> XL_DEV static void inv_last(cf* s, const cf* XL_RESTRICT tw, const Op& op) {
+    template <class Op> XL_DEV static void inv_last(cf* s, const cf* t, const Op& op) {
         XL_THREADS(tid, NT) {
-            for (int u = tid; u < S1 * V; u += NT) {
-                const int c = u % V, n = u / V;
-                cf v[R1];
+            for (int n = tid; n < S1; n += NT) {
+                cf v[V * R1];
 #pragma unroll
-                for (int q = 0; q < R1; ++q) v[q] = s[xl_tidx<V>(n + S1 * q, c)];
-                xl_twiddle<R1, +1>(v, tw, n * (XL_TWN / L));
-                XlBfly<R1, +1>::run(v);
+                for (int q = 0; q < R1; ++q) XlTile<V>::ld(s, n + S1 * q, v + q, R1);
+                cf w[R1];
+                xl_tw_powers<R1>(w, t[n], R1 == 16 ? t[S1 + n] : cf_zero());
 #pragma unroll
-                for (int j = 0; j < R1; ++j) op.store(c, n + S1 * j, v[j]);
+                for (int l = 0; l < V; ++l) {
+                    xl_twiddle<R1, +1>(v + l * R1, w);
+                    XlBfly<R1, +1, false, Op::kOutLoHalf>::run(v + l * R1);
+                }
+                op.store_vec(n, v);   // v[l*R1 + j] is position n + S1*j of line l (j < R1/2 only with kOutLoHalf)
             }
         }
     }
 
-    // ---- whole-tile drivers ----
-    // FWD: op.load -> spectrum; op.spec(c, beta, v) consumes v[q] = bin at slot q*(L/16)+beta.
-    template <class Op> XL_DEV static void forward(cf* s, const cf* XL_RESTRICT tw, const Op& op) {
-        fwd_first(s, tw, op);
-        fwd_mids<L / R1>(s, tw);
+    // ---- whole-tile drivers (s = tile of xl_tile_elems(L,V) cf, t = twiddle tables filled by init_tw) ----
+    // FWD: op.load -> spectrum; op.spec(beta, v) consumes v[l*16 + q] = bin at slot q*(L/16)+beta of line l.
+    template <class Op> XL_DEV static void forward(cf* s, const cf* t, const Op& op) {
+        fwd_first(s, t, op);
+        fwd_mids<L / R1>(s, t);
         XL_THREADS(tid, NT) {
-            for (int u = tid; u < (L / 16) * V; u += NT) {
-                const int c = u % V, beta = u / V;
-                cf v[16];
+            for (int beta = tid; beta < L / 16; beta += NT) {
+                cf v[V * 16];
 #pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] = s[xl_tidx<V>(16 * beta + j, c)];
-                XlBfly<16, -1>::run(v);
-                op.spec(c, beta, v);
+                for (int j = 0; j < 16; ++j) XlTile<V>::ld(s, 16 * beta + j, v + j, 16);
+#pragma unroll
+                for (int l = 0; l < V; ++l) XlBfly<16, -1, false, false>::run(v + l * 16);
+                op.spec(beta, v);
             }
         }
     }
-    // CONV: op.load -> forward -> op.spec multiplies in registers -> inverse -> op.store.  (1/L is the op's business.)
-    template <class Op> XL_DEV static void conv(cf* s, const cf* XL_RESTRICT tw, const Op& op) {
-        fwd_first(s, tw, op);
-        fwd_mids<L / R1>(s, tw);
+    // CONV: op.load -> forward -> op.spec multiplies in registers -> inverse -> op.store_vec.  (1/L is the op's business.)
+    template <class Op> XL_DEV static void conv(cf* s, const cf* t, const Op& op) {
+        fwd_first(s, t, op);
+        fwd_mids<L / R1>(s, t);
         XL_THREADS(tid, NT) {
-            for (int u = tid; u < (L / 16) * V; u += NT) {
-                const int c = u % V, beta = u / V;
-                cf v[16];
+            for (int beta = tid; beta < L / 16; beta += NT) {
+                cf v[V * 16];
 #pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] = s[xl_tidx<V>(16 * beta + j, c)];
-                XlBfly<16, -1>::run(v);
-                op.spec(c, beta, v);
-                XlBfly<16, +1>::run(v);
+                for (int j = 0; j < 16; ++j) XlTile<V>::ld(s, 16 * beta + j, v + j, 16);
 #pragma unroll
-                for (int j = 0; j < 16; ++j) s[xl_tidx<V>(16 * beta + j, c)] = v[j];
+                for (int l = 0; l < V; ++l) XlBfly<16, -1, false, false>::run(v + l * 16);
+                op.spec(beta, v);
+#pragma unroll
+                for (int l = 0; l < V; ++l) XlBfly<16, +1, false, false>::run(v + l * 16);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) XlTile<V>::st(s, 16 * beta + j, v + j, 16);
             }
         }
         XL_SYNC();
-        inv_mids<L / R1>(s, tw);
-        inv_last(s, tw, op);
+        inv_mids<L / R1>(s, t);
+        inv_last(s, t, op);
     }
-    // INV: op.spec fills v[q] from the stored spectrum -> inverse -> op.store.
-    template <class Op> XL_DEV static void inverse(cf* s, const cf* XL_RESTRICT tw, const Op& op) {
+    // INV: op.spec fills v from a stored spectrum -> inverse -> op.store_vec.
+    template <class Op> XL_DEV static void inverse(cf* s, const cf* t, const Op& op) {
         XL_THREADS(tid, NT) {
-            for (int u = tid; u < (L / 16) * V; u += NT) {
-                const int c = u % V, beta = u / V;
-                cf v[16];
-                op.spec(c, beta, v);
-                XlBfly<16, +1>::run(v);
+            for (int beta = tid; beta < L / 16; beta += NT) {
+                cf v[V * 16];
+                op.spec(beta, v);
 #pragma unroll
-                for (int j = 0; j < 16; ++j) s[xl_tidx<V>(16 * beta + j, c)] = v[j];
+                for (int l = 0; l < V; ++l) XlBfly<16, +1, false, false>::run(v + l * 16);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) XlTile<V>::st(s, 16 * beta + j, v + j, 16);
             }
         }
         XL_SYNC();
-        inv_mids<L / R1>(s, tw);
-        inv_last(s, tw, op);
+        inv_mids<L / R1>(s, t);
+        inv_last(s, t, op);
     }
 };

@@ -1,18 +1,18 @@
 // xl_kernels.cuh -- kernel bodies of the propagation hot path (RS/VRS convolution, Bluestein CZT/VCZT, high-NA lens).
 //
-// Every kernel is "one CTA = one tile of V=4 lines through XlFft"; what differs is the functor (op) that feeds the first
+// Every kernel is "one CTA = one set of V = 2 lines through XlFft"; what differs is the functor (op) that feeds the first
 // pass, multiplies the spectrum in registers and drains the last pass.  Reference lines replaced are cited per op.
 //
 // Data layouts (c64 everywhere, geometry in fp64):
 //   field            [f][y][x]                     row-major N x N planes (the reference's [..., y, x])
-//   row spectra  S   [f][L/4][N][4]                "blocked": 4 adjacent x-slots innermost, so the column kernel reads one
-//                                                   contiguous 32*N-byte tile and the row kernel writes 128-byte lines
-//   transfer fn  H   [L/4][L][4]                   same blocking, y in slot order, premultiplied by dx*dy/L^2
+//   row spectra  S   [f][L/2][N][2]                "blocked": 2 adjacent x-slots innermost, so a column-pair CTA reads one
+//                                                   contiguous 16*N-byte tile and a row-pair CTA fills whole 32-byte sectors
+//   transfer fn  H   [L/2][L][2]                   same blocking, y in slot order, premultiplied by dx*dy/L^2
 //   L = padded length (power of two >= 2N-1); slot order = XlFft's digit permutation (never undone).
 #pragma once
 #include "xl_fft.cuh"
 
-#define XL_CW 4  // lines per tile == column-group width of the blocked layouts
+#define XL_V 2  // lines per CTA == column-group width of the blocked layouts
 
 // flags shared by several kernels
 #define XL_F_CONJ_IN 1    // conjugate operand on load   (torch's conjugate-cotangent convention, fused)
@@ -20,38 +20,75 @@
 #define XL_F_VRS 4        // 3 fields, field 2 = Ez formed from (Ex,Ey) at load      (vectorized_optics.py:258-261)
 #define XL_F_DERIV 8      // transfer function of dh/dz instead of h
 
+XL_DEV cf xl_ld2(const cf* p) { return *p; }
+XL_DEV void xl_ld4(const cf* p, cf* a, cf* b) {   // two adjacent complex values with one 16-byte load (p 16-byte aligned)
+    const float4 t = *reinterpret_cast<const float4*>(p);
+    *a = make_float2(t.x, t.y);
+    *b = make_float2(t.z, t.w);
+}
+XL_DEV void xl_ldg4(const cf* p, cf* a, cf* b) {
+    const float4 t = xl_ldg(reinterpret_cast<const float4*>(p));
+    *a = make_float2(t.x, t.y);
+    *b = make_float2(t.z, t.w);
+}
+XL_DEV void xl_st4(cf* p, cf a, cf b) { *reinterpret_cast<float4*>(p) = make_float4(a.x, a.y, b.x, b.y); }
+
 // ------------------------------------------------------------------------------------------------------------------
 // Rayleigh-Sommerfeld impulse response, reference wave_optics.py:291-297:
 //   h = (1/2pi) * z/r^2 * (1/r - i k) * exp(sgn(z) i k r),  r = sqrt(X^2+Y^2+z^2)
-// Phase k*r reaches 4e5 rad: reduced in fp64 (r/lambda - rint) and only the fraction goes through fp32 sincospi.
+// The phase k*r reaches 4e5 rad, so r is formed in fp64 (fp32 rsqrt seed + one fp64 Newton step: rel. error ~1e-13),
+// reduced to a fraction of a cycle in fp64, and only that fraction goes through fp32 sincospi.
 // deriv=1: dh/dz = (e/2pi) * [ g + (z^2/r) * (g' + s i k g) ],  g = 1/r^3 - i k/r^2,  g' = -3/r^4 + 2 i k/r^3.
 // ------------------------------------------------------------------------------------------------------------------
-XL_DEV cf xl_rs_h(double X, double Y, double z, double k, int deriv) {
+// 1/sqrt(r2) to ~1e-13 relative, branch-free (fp32 rsqrt seed + one fp64 Newton step); NaN for r2 == 0
+XL_DEV double xl_rsqrt64(double r2) {
+#ifdef XL_HOST_EMU
+    const float y0 = 1.0f / sqrtf((float)r2);
+#else
+    const float y0 = rsqrtf((float)r2);
+#endif
+    const double y = (double)y0;
+    const double e = fma(-(r2 * y), 0.5 * y, 0.5);   // 0.5 - 0.5*r2*y^2
+    return fma(y, e, y);
+}
+struct XlRsHConst { double z, z2, k, kcyc, sg; };   // per-z constants shared by all samples
+XL_DEV XlRsHConst xl_rs_hconst(double z, double k) {
+    XlRsHConst c;
+    c.z = z;
+    c.z2 = z * z;
+    c.k = k;
+    c.kcyc = k * 0.15915494309189535;       // cycles per unit length (1/lambda)
+    c.sg = z > 0 ? 1.0 : -1.0;
+    return c;
+}
+XL_DEV cf xl_rs_h(double X, double Y, const XlRsHConst& c, int deriv) {
     const double inv2pi = 0.15915494309189535;
-    double r2 = X * X + Y * Y + z * z;
-    double r = sqrt(r2);
-    double cyc = r * (k * inv2pi);
-    double fr = cyc - rint(cyc);
+    const double r2 = X * X + Y * Y + c.z2;
+    const double y = xl_rsqrt64(r2);                  // 1/r
+    const double r = r2 * y;
+    const double cyc = r * c.kcyc;
+    const double fr = cyc - rint(cyc);
     float sn, cs;
     xl_sincospif(2.0f * (float)fr, &sn, &cs);
-    double sg = z > 0 ? 1.0 : -1.0;
-    double ir = 1.0 / r, ir2 = ir * ir, ir3 = ir2 * ir;
-    double ar, ai;  // amplitude (complex), multiplies exp(s i k r)
+    sn *= (float)c.sg;                                // exp(sgn(z) i k r)
+    // amplitude (complex, multiplies the phase factor) in fp64, rounded once: gradients of intensity-type losses with
+    // respect to z cancel the leading term of dh/dz, which amplifies amplitude rounding by ~k*r
+    const double ir2 = y * y, ir3 = ir2 * y;
+    double ar, ai;
     if (!deriv) {
-        ar = z * inv2pi * ir3;
-        ai = -z * inv2pi * k * ir2;
+        ar = c.z * inv2pi * ir3;
+        ai = -c.z * inv2pi * c.k * ir2;
     } else {
-        double gr = ir3, gi = -k * ir2;
-        double gpr = -3.0 * ir2 * ir2, gpi = 2.0 * k * ir3;
+        const double gr = ir3, gi = -c.k * ir2;
+        const double gpr = -3.0 * ir2 * ir2, gpi = 2.0 * c.k * ir3;
         // g' + s*i*k*g = (gpr - s*k*gi) + i (gpi + s*k*gr)
-        double tr = gpr - sg * k * gi, ti = gpi + sg * k * gr;
-        double f = z * z * ir;
+        const double tr = gpr - c.sg * c.k * gi, ti = gpi + c.sg * c.k * gr;
+        const double f = c.z2 * y;
         ar = (gr + f * tr) * inv2pi;
         ai = (gi + f * ti) * inv2pi;
     }
-    float c = cs, s = (float)sg * sn;
-    float far = (float)ar, fai = (float)ai;
-    return make_float2(far * c - fai * s, far * s + fai * c);
+    const float far = (float)ar, fai = (float)ai;
+    return make_float2(far * cs - fai * sn, far * sn + fai * cs);
 }
 
 // ==================================================================================================================
@@ -61,11 +98,10 @@ struct XlRsParams {
     int N, L, nfields, flags;
     const cf* in;      // [nfields][N][N]   (XL_F_VRS: [2][N][N] = Ex,Ey)
     cf* out;           // [nfields][N][N]
-    cf* spec;          // [nfields][L/4][N][4]
+    cf* spec;          // [nfields][L/2][N][2]
     cf* spec2;         // second spectra set (grad-z: spectra of conj(U))
-    cf* H;             // [L/4][L][4]
+    cf* H;             // [L/2][L][2]
     const cf* H2;      // dH/dz transfer function (grad-z)
-    cf* scratch;       // [L/4][nfields][L][4] (grad-z)
     double* gz;        // scalar accumulator (grad-z)
     const cf* tw;
     const double* z;   // device scalar
@@ -74,206 +110,301 @@ struct XlRsParams {
 };
 
 // K1: rows of the zero-padded field -> blocked row spectra.   replaces the row half of fft2(U), wave_optics.py:286-288
-template <int L> struct XlRsRowsFwdOp {
-    const XlRsParams& p; int f, yb; double z;
-    XL_DEV cf load(int c, int i) const {
-        const int y = yb + c, N = p.N;
-        if (y >= N || i >= N) return make_float2(0.f, 0.f);
-        const size_t NN = (size_t)N * N, o = (size_t)y * N + i;
+// EZ: this CTA's field is Ez = (Ex X + Ey Y)/r formed from (Ex,Ey) while loading (vectorized_optics.py:258-261).
+// The load path is branch-free so that all of a thread's global loads are in flight together.
+template <int L, bool EZ> struct XlRsRowsFwdOp : XlOpBase {
+    static constexpr bool kInLoHalf = true;   // N <= L/2: the upper half of every padded row is zero
+    const XlRsParams& p; int f, yb; double z2;
+    XL_DEV cf load1(int y, int i) const {
+        const int N = p.N;
+        const bool ok = y < N && i < N;
+        const size_t NN = (size_t)N * N, o = ok ? (size_t)y * N + i : 0;
         cf v;
-        if ((p.flags & XL_F_VRS) && f == 2) {
-            cf ex = p.in[o], ey = p.in[NN + o];
-            double X = p.x0 + i * p.dx, Y = p.y0 + y * p.dy;
-            double ir = 1.0 / sqrt(X * X + Y * Y + z * z);
-            float ax = (float)(X * ir), ay = (float)(Y * ir);
-            v = make_float2(ex.x * ax + ey.x * ay, ex.y * ax + ey.y * ay);
+        if (EZ) {
+            const cf ex = p.in[o], ey = p.in[NN + o];
+            const double X = p.x0 + i * p.dx, Y = p.y0 + y * p.dy;
+            const double ir = xl_rsqrt64(X * X + Y * Y + z2);
+            v = cf_lin2(ex, (float)(X * ir), ey, (float)(Y * ir));
         } else {
             v = p.in[(size_t)f * NN + o];
         }
-        if (p.flags & XL_F_CONJ_IN) v.y = -v.y;
-        return v;
+        if (p.flags & XL_F_CONJ_IN) v = cf_conj(v);
+        return ok ? v : cf_zero();
     }
-    XL_DEV void spec(int c, int beta, cf* v) const {
-        const int y = yb + c;
-        if (y >= p.N) return;
-        cf* base = p.spec + (size_t)f * L * p.N + (size_t)y * XL_CW;
+    XL_DEV void load(int i, cf* v, int stride) const {
 #pragma unroll
-        for (int q = 0; q < 16; ++q) {
-            const int g = q * (L / 16) + beta;
-            base[(size_t)(g / XL_CW) * p.N * XL_CW + (g % XL_CW)] = v[q];
+        for (int l = 0; l < XL_V; ++l) v[l * stride] = load1(yb + l, i);
+    }
+    XL_DEV void spec(int beta, const cf* v) const {
+        cf* base = p.spec + (size_t)f * L * p.N;
+#pragma unroll
+        for (int l = 0; l < XL_V; ++l) {
+            const int y = yb + l;
+            if (y >= p.N) continue;
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+                const int g = q * (L / 16) + beta;
+                base[((size_t)(g / XL_V) * p.N + y) * XL_V + (g % XL_V)] = v[l * 16 + q];
+            }
         }
     }
-    XL_DEV void store(int, int, cf) const {}
+    XL_DEV void store_vec(int, const cf*) const {}
 };
 template <int L> struct XlRsRowsFwd {
     static const char* name() { return "rs_rows_fwd"; }
     typedef XlRsParams Params;
-    static constexpr int NT = xl_threads(L, XL_CW);
+    static constexpr int NT = xl_threads(L);
+    static size_t smem() { return xl_smem_bytes(L, XL_V); }
     XL_DEV static void run(const Params& p, cf* s) {
-        XlRsRowsFwdOp<L> op{p, XL_BLOCK_Y, XL_BLOCK_X * XL_CW, p.z ? xl_ldg(p.z) : 0.0};
-        XlFft<L, XL_CW, NT>::forward(s, p.tw, op);
+        cf* t = s + xl_tile_elems(L, XL_V);
+        XlFft<L, XL_V>::init_tw(t, p.tw);
+        const int f = XL_BLOCK_Y, yb = XL_BLOCK_X * XL_V;
+        if ((p.flags & XL_F_VRS) && f == 2) {   // CTA-uniform
+            const double z = xl_ldg(p.z);
+            XlRsRowsFwdOp<L, true> op{{}, p, f, yb, z * z};
+            XlFft<L, XL_V>::forward(s, t, op);
+        } else {
+            XlRsRowsFwdOp<L, false> op{{}, p, f, yb, 0.0};
+            XlFft<L, XL_V>::forward(s, t, op);
+        }
     }
 };
 
 // K2: column FFT of the row spectra, x transfer function, inverse column FFT, keep rows [0,N).   wave_optics.py:288
-template <int L> struct XlRsColsOp {
+template <int L> struct XlRsColsOp : XlOpBase {
+    static constexpr bool kInLoHalf = true, kOutLoHalf = true;
+    static constexpr int R1 = xl_first_radix(L), S1 = L / R1;
     const XlRsParams& p; cf* tile; const cf* Ht;
-    XL_DEV cf load(int c, int i) const { return i < p.N ? tile[(size_t)i * XL_CW + c] : make_float2(0.f, 0.f); }
-    XL_DEV void spec(int c, int beta, cf* v) const {
-#pragma unroll
-        for (int q = 0; q < 16; ++q) v[q] = cf_mul(v[q], xl_ldg(Ht + (size_t)(q * (L / 16) + beta) * XL_CW + c));
+    XL_DEV void load(int i, cf* v, int stride) const {
+        if (i < p.N) xl_ld4(tile + (size_t)i * XL_V, v, v + stride);
+        else { v[0] = cf_zero(); v[stride] = cf_zero(); }
     }
-    XL_DEV void store(int c, int i, cf val) const { if (i < p.N) tile[(size_t)i * XL_CW + c] = val; }
+    XL_DEV void spec(int beta, cf* v) const {
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            cf h0, h1;
+            xl_ldg4(Ht + (size_t)(q * (L / 16) + beta) * XL_V, &h0, &h1);
+            v[q] = cf_mul(v[q], h0);
+            v[16 + q] = cf_mul(v[16 + q], h1);
+        }
+    }
+    XL_DEV void store_vec(int n, const cf* v) const {
+#pragma unroll
+        for (int j = 0; j < R1 / 2; ++j) {
+            const int i = n + S1 * j;
+            if (i < p.N) xl_st4(tile + (size_t)i * XL_V, v[j], v[R1 + j]);
+        }
+    }
 };
 template <int L> struct XlRsCols {
     static const char* name() { return "rs_cols"; }
     typedef XlRsParams Params;
-    static constexpr int NT = xl_threads(L, XL_CW);
+    static constexpr int NT = xl_threads(L);
+    static size_t smem() { return xl_smem_bytes(L, XL_V); }
     XL_DEV static void run(const Params& p, cf* s) {
+        cf* t = s + xl_tile_elems(L, XL_V);
+        XlFft<L, XL_V>::init_tw(t, p.tw);
         const int G = XL_BLOCK_X, f = XL_BLOCK_Y;
-        XlRsColsOp<L> op{p, p.spec + (size_t)f * L * p.N + (size_t)G * p.N * XL_CW, p.H + (size_t)G * L * XL_CW};
-        XlFft<L, XL_CW, NT>::conv(s, p.tw, op);
+        XlRsColsOp<L> op{{}, p, p.spec + (size_t)f * L * p.N + (size_t)G * p.N * XL_V, p.H + (size_t)G * L * XL_V};
+        XlFft<L, XL_V>::conv(s, t, op);
     }
 };
 
 // K3: inverse row FFT of the filtered spectra, crop columns [0,N).   wave_optics.py:288 (row half of ifft2 + crop)
-template <int L> struct XlRsRowsInvOp {
+template <int L> struct XlRsRowsInvOp : XlOpBase {
+    static constexpr bool kOutLoHalf = true;
+    static constexpr int R1 = xl_first_radix(L), S1 = L / R1;
     const XlRsParams& p; int f, yb;
-    XL_DEV cf load(int, int) const { return make_float2(0.f, 0.f); }
-    XL_DEV void spec(int c, int beta, cf* v) const {
-        const int y = yb + c;
-        const cf* base = p.spec + (size_t)f * L * p.N + (size_t)y * XL_CW;
+    XL_DEV void load(int, cf*, int) const {}
+    XL_DEV void spec(int beta, cf* v) const {
+        const cf* base = p.spec + (size_t)f * L * p.N;
 #pragma unroll
-        for (int q = 0; q < 16; ++q) {
-            const int g = q * (L / 16) + beta;
-            v[q] = y < p.N ? base[(size_t)(g / XL_CW) * p.N * XL_CW + (g % XL_CW)] : make_float2(0.f, 0.f);
+        for (int l = 0; l < XL_V; ++l) {
+            const int y = yb + l;
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+                const int g = q * (L / 16) + beta;
+                v[l * 16 + q] = y < p.N ? base[((size_t)(g / XL_V) * p.N + y) * XL_V + (g % XL_V)] : cf_zero();
+            }
         }
     }
-    XL_DEV void store(int c, int i, cf val) const {
-        const int y = yb + c;
-        if (y >= p.N || i >= p.N) return;
-        if (p.flags & XL_F_CONJ_OUT) val.y = -val.y;
-        p.out[(size_t)f * p.N * p.N + (size_t)y * p.N + i] = val;
+    XL_DEV void store_vec(int n, const cf* v) const {
+#pragma unroll
+        for (int l = 0; l < XL_V; ++l) {
+            const int y = yb + l;
+            if (y >= p.N) continue;
+#pragma unroll
+            for (int j = 0; j < R1 / 2; ++j) {
+                const int i = n + S1 * j;
+                if (i >= p.N) continue;
+                cf val = v[l * R1 + j];
+                if (p.flags & XL_F_CONJ_OUT) val = cf_conj(val);
+                p.out[(size_t)f * p.N * p.N + (size_t)y * p.N + i] = val;
+            }
+        }
     }
 };
 template <int L> struct XlRsRowsInv {
     static const char* name() { return "rs_rows_inv"; }
     typedef XlRsParams Params;
-    static constexpr int NT = xl_threads(L, XL_CW);
+    static constexpr int NT = xl_threads(L);
+    static size_t smem() { return xl_smem_bytes(L, XL_V); }
     XL_DEV static void run(const Params& p, cf* s) {
-        XlRsRowsInvOp<L> op{p, XL_BLOCK_Y, XL_BLOCK_X * XL_CW};
-        XlFft<L, XL_CW, NT>::inverse(s, p.tw, op);
+        cf* t = s + xl_tile_elems(L, XL_V);
+        XlFft<L, XL_V>::init_tw(t, p.tw);
+        XlRsRowsInvOp<L> op{{}, p, XL_BLOCK_Y, XL_BLOCK_X * XL_V};
+        XlFft<L, XL_V>::inverse(s, t, op);
     }
 };
 
 // K1h: rows y>=0 of the wrapped, analytically generated impulse response -> row spectra stored inside H
 //      (rows 0..L/2 of each group block).   replaces transfer_function_RS + row half of fft2(H), wave_optics.py:285,291-297
-template <int L> struct XlHRowsOp {
-    const XlRsParams& p; int yb; double z;
-    XL_DEV cf load(int c, int i) const {
-        const int yi = yb + c;
-        if (yi > L / 2) return make_float2(0.f, 0.f);
-        const int xi = i <= L / 2 ? i : i - L;
-        return xl_rs_h(xi * p.dx, yi * p.dy, z, p.k, (p.flags & XL_F_DERIV) ? 1 : 0);
+// h is even in x: each sample x in [0, L/2] is evaluated once into a staging buffer and read back mirrored.
+template <int L> struct XlHRowsOp : XlOpBase {
+    const XlRsParams& p; int yb; const cf* stage;   // stage[(L/2+1)][XL_V]
+    XL_DEV void load(int i, cf* v, int stride) const {
+        const int xi = i <= L / 2 ? i : L - i;
+        xl_ld4(stage + (size_t)xi * XL_V, v, v + stride);
     }
-    XL_DEV void spec(int c, int beta, cf* v) const {
-        const int yi = yb + c;
-        if (yi > L / 2) return;
+    XL_DEV void spec(int beta, const cf* v) const {
 #pragma unroll
-        for (int q = 0; q < 16; ++q) {
-            const int g = q * (L / 16) + beta;
-            p.H[(size_t)(g / XL_CW) * L * XL_CW + (size_t)yi * XL_CW + (g % XL_CW)] = v[q];
+        for (int l = 0; l < XL_V; ++l) {
+            const int yi = yb + l;
+            if (yi > L / 2) continue;
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+                const int g = q * (L / 16) + beta;
+                p.H[((size_t)(g / XL_V) * L + yi) * XL_V + (g % XL_V)] = v[l * 16 + q];
+            }
         }
     }
-    XL_DEV void store(int, int, cf) const {}
+    XL_DEV void store_vec(int, const cf*) const {}
 };
 template <int L> struct XlHRows {
     static const char* name() { return "h_rows"; }
     typedef XlRsParams Params;
-    static constexpr int NT = xl_threads(L, XL_CW);
+    static constexpr int NT = xl_threads(L);
+    static constexpr int NSTAGE = (L / 2 + 2) * XL_V;   // +1 sample of slack keeps the size even (16-byte rows)
+    static size_t smem() { return xl_smem_bytes(L, XL_V) + (size_t)NSTAGE * sizeof(cf); }
     XL_DEV static void run(const Params& p, cf* s) {
-        XlHRowsOp<L> op{p, XL_BLOCK_X * XL_CW, xl_ldg(p.z)};
-        XlFft<L, XL_CW, NT>::forward(s, p.tw, op);
+        cf* t = s + xl_tile_elems(L, XL_V);
+        cf* stage = t + xl_tw_total(L);
+        const int yb = XL_BLOCK_X * XL_V;
+        const XlRsHConst hc = xl_rs_hconst(xl_ldg(p.z), p.k);
+        const int deriv = (p.flags & XL_F_DERIV) ? 1 : 0;
+        XL_THREADS(tid, NT) {
+            for (int e = tid; e < (L / 2 + 1) * XL_V; e += NT) {
+                const int xi = e / XL_V, l = e % XL_V, yi = yb + l;
+                stage[e] = yi <= L / 2 ? xl_rs_h(xi * p.dx, yi * p.dy, hc, deriv) : cf_zero();
+            }
+        }
+        XlFft<L, XL_V>::init_tw(t, p.tw);   // ends with a barrier: stage[] is visible
+        XlHRowsOp<L> op{{}, p, yb, stage};
+        XlFft<L, XL_V>::forward(s, t, op);
     }
 };
 
 // K2h: column FFT of the impulse-response row spectra (even in y: row L-y == row y), result in slot order, scaled.
-template <int L> struct XlHColsOp {
+template <int L> struct XlHColsOp : XlOpBase {
     const XlRsParams& p; cf* Ht;
-    XL_DEV cf load(int c, int i) const { const int r = i <= L / 2 ? i : L - i; return Ht[(size_t)r * XL_CW + c]; }
-    XL_DEV void spec(int c, int beta, cf* v) const {
-#pragma unroll
-        for (int q = 0; q < 16; ++q) Ht[(size_t)(q * (L / 16) + beta) * XL_CW + c] = cf_scale(v[q], p.hscale);
+    XL_DEV void load(int i, cf* v, int stride) const {
+        const int r = i <= L / 2 ? i : L - i;
+        xl_ld4(Ht + (size_t)r * XL_V, v, v + stride);
     }
-    XL_DEV void store(int, int, cf) const {}
+    XL_DEV void spec(int beta, const cf* v) const {
+#pragma unroll
+        for (int q = 0; q < 16; ++q)
+            xl_st4(Ht + (size_t)(q * (L / 16) + beta) * XL_V, cf_scale(v[q], p.hscale), cf_scale(v[16 + q], p.hscale));
+    }
+    XL_DEV void store_vec(int, const cf*) const {}
 };
 template <int L> struct XlHCols {
     static const char* name() { return "h_cols"; }
     typedef XlRsParams Params;
-    static constexpr int NT = xl_threads(L, XL_CW);
+    static constexpr int NT = xl_threads(L);
+    static size_t smem() { return xl_smem_bytes(L, XL_V); }
     XL_DEV static void run(const Params& p, cf* s) {
-        XlHColsOp<L> op{p, p.H + (size_t)XL_BLOCK_X * L * XL_CW};
-        XlFft<L, XL_CW, NT>::forward(s, p.tw, op);
+        cf* t = s + xl_tile_elems(L, XL_V);
+        XlFft<L, XL_V>::init_tw(t, p.tw);
+        XlHColsOp<L> op{{}, p, p.H + (size_t)XL_BLOCK_X * L * XL_V};
+        // the in-place update is safe: every load of the first pass happens before the barrier that precedes the stores
+        XlFft<L, XL_V>::forward(s, t, op);
     }
 };
 
-// K4: backward column kernel.  Phase A: column spectra W of conj(U) (spec2) parked in scratch.  Phase B: column spectra C
-// of the cotangent; accumulates Re sum conj(W)*C*Hz (Parseval form of ct_z) and applies H for ct_field.
-template <int L> struct XlRsColsWOp {
-    const XlRsParams& p; const cf* tile; cf* scr;
-    XL_DEV cf load(int c, int i) const { return i < p.N ? tile[(size_t)i * XL_CW + c] : make_float2(0.f, 0.f); }
-    XL_DEV void spec(int c, int beta, cf* v) const {
+// K4: backward column kernel with d/dz.  One CTA owns one column PAIR and walks its two columns; per column, the column
+// spectrum W of conj(U) (from spec2) is parked in a second shared-memory tile, then the column spectrum C of the
+// cotangent meets it in registers:  gz += Re sum conj(W)*C*Hz  (Parseval form of ct_z), C*H goes back
+// through the inverse FFT for ct_field.  No scratch in HBM, three FFTs per column.
+template <int L> struct XlRsColsWOp : XlOpBase {
+    static constexpr bool kInLoHalf = true;
+    const XlRsParams& p; const cf* tile; int c; cf* wtile;
+    XL_DEV void load(int i, cf* v, int) const { v[0] = i < p.N ? tile[(size_t)i * XL_V + c] : cf_zero(); }
+    XL_DEV void spec(int beta, const cf* v) const {
 #pragma unroll
-        for (int q = 0; q < 16; ++q) scr[(size_t)(q * (L / 16) + beta) * XL_CW + c] = v[q];
+        for (int q = 0; q < 16; ++q) wtile[xl_pad(16 * beta + q)] = v[q];   // thread-private positions: no barrier needed
     }
-    XL_DEV void store(int, int, cf) const {}
+    XL_DEV void store_vec(int, const cf*) const {}
 };
-template <int L> struct XlRsColsGzOp {
-    const XlRsParams& p; cf* tile; const cf* Ht; const cf* Hzt; const cf* scr; float* red;
-    XL_DEV cf load(int c, int i) const { return i < p.N ? tile[(size_t)i * XL_CW + c] : make_float2(0.f, 0.f); }
-    XL_DEV void spec(int c, int beta, cf* v) const {
+template <int L> struct XlRsColsGzOp : XlOpBase {
+    static constexpr bool kInLoHalf = true, kOutLoHalf = true;
+    static constexpr int R1 = xl_first_radix(L), S1 = L / R1;
+    const XlRsParams& p; cf* tile; int c; const cf* Ht; const cf* Hzt; const cf* wtile; float* red;
+    XL_DEV void load(int i, cf* v, int) const { v[0] = i < p.N ? tile[(size_t)i * XL_V + c] : cf_zero(); }
+    XL_DEV void spec(int beta, cf* v) const {
         float acc = 0.f;
 #pragma unroll
         for (int q = 0; q < 16; ++q) {
-            const size_t o = (size_t)(q * (L / 16) + beta) * XL_CW + c;
-            cf w = scr[o];
-            cf t = cf_mul(v[q], xl_ldg(Hzt + o));
+            const size_t o = (size_t)(q * (L / 16) + beta) * XL_V + c;
+            const cf w = wtile[xl_pad(16 * beta + q)];
+            const cf t = cf_mul(v[q], xl_ldg(Hzt + o));
             acc += w.x * t.x + w.y * t.y;  // Re(conj(w) * t)
             v[q] = cf_mul(v[q], xl_ldg(Ht + o));
         }
-        red[beta * XL_CW + c] = acc;
+        red[beta] += acc;
     }
-    XL_DEV void store(int c, int i, cf val) const { if (i < p.N) tile[(size_t)i * XL_CW + c] = val; }
+    XL_DEV void store_vec(int n, const cf* v) const {
+#pragma unroll
+        for (int j = 0; j < R1 / 2; ++j) {
+            const int i = n + S1 * j;
+            if (i < p.N) tile[(size_t)i * XL_V + c] = v[j];
+        }
+    }
 };
 template <int L> struct XlRsColsGz {
     static const char* name() { return "rs_cols_gz"; }
     typedef XlRsParams Params;
-    static constexpr int NT = xl_threads(L, XL_CW);
-    static constexpr int NRED = (L / 16) * XL_CW;
-    static constexpr int TILE = xl_tile_elems(L, XL_CW);
+    static constexpr int NT = xl_threads(L);
+    static constexpr int NB = L / 16;   // butterflies per line == entries of the partial-sum array
+    static size_t smem() { return (size_t)(2 * xl_tile_elems(L, 1) + xl_tw_total(L)) * sizeof(cf) + (size_t)(NB + 32) * sizeof(float); }
     XL_DEV static void run(const Params& p, cf* s) {
+        cf* wtile = s + xl_tile_elems(L, 1);
+        cf* t = wtile + xl_tile_elems(L, 1);
+        float* red = (float*)(t + xl_tw_total(L));
+        XL_THREADS(tid, NT) { for (int i = tid; i < NB; i += NT) red[i] = 0.f; }
+        XlFft<L, 1>::init_tw(t, p.tw);
         const int G = XL_BLOCK_X, f = XL_BLOCK_Y;
-        float* red = (float*)(s + TILE);
-        cf* scr = p.scratch + ((size_t)G * p.nfields + f) * L * XL_CW;
-        const size_t toff = (size_t)f * L * p.N + (size_t)G * p.N * XL_CW;
-        XlRsColsWOp<L> opw{p, p.spec2 + toff, scr};
-        XlFft<L, XL_CW, NT>::forward(s, p.tw, opw);
-        XL_SYNC();
-        XlRsColsGzOp<L> op{p, p.spec + toff, p.H + (size_t)G * L * XL_CW, p.H2 + (size_t)G * L * XL_CW, scr, red};
-        XlFft<L, XL_CW, NT>::conv(s, p.tw, op);
-        XL_SYNC();
+        const size_t toff = (size_t)f * L * p.N + (size_t)G * p.N * XL_V;
+        for (int c = 0; c < XL_V; ++c) {
+            XlRsColsWOp<L> opw{{}, p, p.spec2 + toff, c, wtile};
+            XlFft<L, 1>::forward(s, t, opw);
+            XL_SYNC();
+            XlRsColsGzOp<L> op{{}, p, p.spec + toff, c, p.H + (size_t)G * L * XL_V, p.H2 + (size_t)G * L * XL_V, wtile, red};
+            XlFft<L, 1>::conv(s, t, op);
+            XL_SYNC();
+        }
         XL_THREADS(tid, NT) {
             if (tid < 32) {
                 float a = 0.f;
-                for (int i = tid; i < NRED; i += 32) a += red[i];
-                red[NRED + tid] = a;
+                for (int i = tid; i < NB; i += 32) a += red[i];
+                red[NB + tid] = a;
             }
         }
         XL_SYNC();
         XL_THREADS(tid, NT) {
             if (tid == 0) {
                 double a = 0.0;
-                for (int i = 0; i < 32; ++i) a += (double)red[NRED + i];
+                for (int i = 0; i < 32; ++i) a += (double)red[NB + i];
                 xl_atomic_add(p.gz, a);
             }
         }
@@ -300,7 +431,7 @@ struct XlCztParams {
     cf* out;      long long out_line, out_pos, out_comp;
     const cf* pre; const cf* ft; const cf* post;
     const cf* tw;
-    int pro, epi;
+    int pro, epi;          // host-side selectors of the compiled <PRO, EPI> variant
     XlGridFactor gpro, gepi;
     const double* z;      // device scalar (RSF / VCZT factors), may be null
     double k;             // wavenumber
@@ -310,96 +441,110 @@ struct XlCztParams {
 };
 
 // lens factor row `comp` applied to (Ex,Ey):  apod*G*(RL[comp][0] Ex + RL[comp][1] Ey + RL[comp][2] Ez), Ez=(Ex X+Ey Y)/rho
+// Branch-free; X/rho, Y/rho are 0/0 = NaN at the origin exactly like the reference (optical_elements.py:538).
 XL_DEV void xl_lens_row(double X, double Y, double R, double f, double s2, int comp, float* ax, float* ay) {
-    double rho2 = X * X + Y * Y;
-    double rho = sqrt(rho2);
-    float th = (float)(rho / f);
+    const double rho2 = X * X + Y * Y;
+    const double irho = xl_rsqrt64(rho2);          // NaN when rho2 == 0
+    const double rho = rho2 * irho;
     float st, ct;
-    xl_sincosf(th, &st, &ct);
-    float cp = rho == 0.0 ? 1.f : (float)(X / rho), sp = rho == 0.0 ? 0.f : (float)(Y / rho);
-    // Ez coefficients: X/rho, Y/rho -- 0/0 = NaN at the origin exactly like the reference (optical_elements.py:538)
-    float zx = (float)(X / rho), zy = (float)(Y / rho);
-    float pupil = (rho2 / (R * R) < 1.0) ? 1.f : 0.f;
-    double uv = (X / R) * (X / R) + (Y / R) * (Y / R);
-    float G = pupil / sqrtf(fabsf((float)(1.0 - uv * s2)));
-    float w = sqrtf(fabsf(ct)) * G;
+    xl_sincospif((float)(rho / f * 0.31830988618379067), &st, &ct);   // theta = rho/f
+    const float cp = (float)(X * irho), sp = (float)(Y * irho);       // cos(phi), sin(phi) (also the Ez coefficients)
+    const double uv = rho2 / (R * R);
+    const float pupil = uv < 1.0 ? 1.f : 0.f;
+    const float G = pupil / sqrtf(fabsf((float)(1.0 - uv * s2)));
+    const float w = sqrtf(fabsf(ct)) * G;
     float r0, r1, r2;
     if (comp == 0) { r0 = ct * cp * cp + sp * sp; r1 = ct * cp * sp - sp * cp; r2 = -cp * st; }
     else if (comp == 1) { r0 = sp * ct * cp - cp * sp; r1 = ct * sp * sp + cp * cp; r2 = -sp * st; }
     else { r0 = st * cp; r1 = st * sp; r2 = ct; }
-    *ax = w * (r0 + r2 * zx);
-    *ay = w * (r1 + r2 * zy);
+    *ax = w * (r0 + r2 * cp);
+    *ay = w * (r1 + r2 * sp);
 }
 
-template <int L> struct XlCztOp {
-    const XlCztParams& p; int lb, comp; double z; cf cst;
+template <int L, int PRO, int EPI> struct XlCztOp : XlOpBase {
+    static constexpr int R1 = xl_first_radix(L), S1 = L / R1;
+    const XlCztParams& p; int lb, comp; double z; XlRsHConst hc; cf cst;
     XL_DEV void coords(const XlGridFactor& g, int line, int pos, double* X, double* Y) const {
         if (g.swap) { *X = g.x0 + pos * g.dx; *Y = g.y0 + line * g.dy; }
         else { *X = g.x0 + line * g.dx; *Y = g.y0 + pos * g.dy; }
     }
-    XL_DEV cf load(int c, int i) const {
-        const int line = lb + c;
-        if (line >= p.nlines || i >= p.m_in) return make_float2(0.f, 0.f);
-        const long long o = (long long)line * p.in_line + (long long)i * p.in_pos;
+    // branch-free: out-of-range samples read element 0 and are zeroed afterwards
+    XL_DEV cf load1(int line, int i) const {
+        const bool ok = line < p.nlines && i < p.m_in;
+        const long long o = ok ? (long long)line * p.in_line + (long long)i * p.in_pos : 0;
         cf v;
-        if (p.pro == XL_PRO_NONE) {
+        if (PRO == XL_PRO_NONE) {
             v = p.in[(long long)comp * p.in_comp + o];
-            if (p.flags & XL_F_CONJ_IN) v.y = -v.y;
+            if (p.flags & XL_F_CONJ_IN) v = cf_conj(v);
         } else {
             double X, Y;
             coords(p.gpro, line, i, &X, &Y);
-            if (p.pro == XL_PRO_RSF) {
+            if (PRO == XL_PRO_RSF) {
                 v = p.in[(long long)comp * p.in_comp + o];
-                if (p.flags & XL_F_CONJ_IN) v.y = -v.y;
-                v = cf_mul(v, xl_rs_h(X, Y, z, p.k, 0));
-            } else if (p.pro == XL_PRO_VCZT) {
-                if (comp < 2) {
-                    v = p.in[(long long)comp * p.in_comp + o];
-                } else {  // Ez = ((Ex X + Ey Y)/r) * z/r     vectorized_optics.py:341-344
-                    cf ex = p.in[o], ey = p.in[p.in_comp + o];
-                    double ir2 = 1.0 / (X * X + Y * Y + z * z);
-                    float ax = (float)(X * z * ir2), ay = (float)(Y * z * ir2);
-                    v = make_float2(ex.x * ax + ey.x * ay, ex.y * ax + ey.y * ay);
-                }
-                v = cf_mul(v, xl_rs_h(X, Y, z, p.k, 0));
+                if (p.flags & XL_F_CONJ_IN) v = cf_conj(v);
+                v = cf_mul(v, xl_rs_h(X, Y, hc, 0));
+            } else if (PRO == XL_PRO_VCZT) {
+                const cf ex = p.in[o], ey = p.in[p.in_comp + o];
+                // comp 0/1: Ex / Ey;  comp 2: Ez = ((Ex X + Ey Y)/r) * z/r     vectorized_optics.py:341-344
+                const double ir2 = 1.0 / (X * X + Y * Y + z * z);
+                const float ax = comp == 0 ? 1.f : (comp == 1 ? 0.f : (float)(X * z * ir2));
+                const float ay = comp == 0 ? 0.f : (comp == 1 ? 1.f : (float)(Y * z * ir2));
+                v = cf_mul(cf_lin2(ex, ax, ey, ay), xl_rs_h(X, Y, hc, 0));
             } else {  // XL_PRO_HIGHNA
-                cf ex = p.in[o], ey = p.in[p.in_comp + o];
+                const cf ex = p.in[o], ey = p.in[p.in_comp + o];
                 float ax, ay;
                 xl_lens_row(X, Y, p.lens_R, p.lens_f, p.lens_s2, comp, &ax, &ay);
-                v = make_float2(ex.x * ax + ey.x * ay, ex.y * ax + ey.y * ay);
+                v = cf_lin2(ex, ax, ey, ay);
             }
         }
-        return cf_mul(v, xl_ldg(p.pre + i));
+        v = cf_mul(v, xl_ldg(p.pre + (ok ? i : 0)));
+        return ok ? v : cf_zero();
     }
-    XL_DEV void spec(int c, int beta, cf* v) const {
-        (void)c;
+    XL_DEV void load(int i, cf* v, int stride) const {
 #pragma unroll
-        for (int q = 0; q < 16; ++q) v[q] = cf_mul(v[q], xl_ldg(p.ft + q * (L / 16) + beta));
+        for (int l = 0; l < XL_V; ++l) v[l * stride] = load1(lb + l, i);
     }
-    XL_DEV void store(int c, int i, cf val) const {
-        const int line = lb + c, o = i - p.out_off;
+    XL_DEV void spec(int beta, cf* v) const {
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            const cf w = xl_ldg(p.ft + q * (L / 16) + beta);
+#pragma unroll
+            for (int l = 0; l < XL_V; ++l) v[l * 16 + q] = cf_mul(v[l * 16 + q], w);
+        }
+    }
+    XL_DEV void store1(int line, int i, cf val) const {
+        const int o = i - p.out_off;
         if (line >= p.nlines || o < 0 || o >= p.m_out) return;
         val = cf_mul(val, xl_ldg(p.post + o));
-        if (p.epi == XL_EPI_RSF) {
+        if (EPI == XL_EPI_RSF) {
             double X, Y;
             coords(p.gepi, line, o, &X, &Y);
-            val = cf_mul(val, xl_rs_h(X, Y, z, p.k, 0));
+            val = cf_mul(val, xl_rs_h(X, Y, hc, 0));
         }
         val = cf_mul(val, cst);
-        if (p.flags & XL_F_CONJ_OUT) val.y = -val.y;
+        if (p.flags & XL_F_CONJ_OUT) val = cf_conj(val);
         p.out[(long long)comp * p.out_comp + (long long)line * p.out_line + (long long)o * p.out_pos] = val;
     }
+    XL_DEV void store_vec(int n, const cf* v) const {
+#pragma unroll
+        for (int l = 0; l < XL_V; ++l)
+#pragma unroll
+            for (int j = 0; j < R1; ++j) store1(lb + l, n + S1 * j, v[l * R1 + j]);
+    }
 };
-template <int L> struct XlCztAxis {
+template <int L, int PRO, int EPI> struct XlCztAxis {
     static const char* name() { return "czt_axis"; }
     typedef XlCztParams Params;
-    static constexpr int NT = xl_threads(L, XL_CW);
+    static constexpr int NT = xl_threads(L);
+    static size_t smem() { return xl_smem_bytes(L, XL_V); }
     XL_DEV static void run(const Params& p, cf* s) {
+        cf* t = s + xl_tile_elems(L, XL_V);
+        XlFft<L, XL_V>::init_tw(t, p.tw);
         const double z = p.z ? xl_ldg(p.z) : 0.0;
         double cr = p.epi_cr, ci = p.epi_ci;
         if (p.epi_times_z) { cr *= z; ci *= z; }
-        XlCztOp<L> op{p, XL_BLOCK_X * XL_CW, XL_BLOCK_Y, z, make_float2((float)cr, (float)ci)};
-        XlFft<L, XL_CW, NT>::conv(s, p.tw, op);
+        XlCztOp<L, PRO, EPI> op{{}, p, XL_BLOCK_X * XL_V, XL_BLOCK_Y, z, xl_rs_hconst(z, p.k), make_float2((float)cr, (float)ci)};
+        XlFft<L, XL_V>::conv(s, t, op);
     }
 };
 
@@ -436,32 +581,36 @@ XL_DEV cf xl_chirp(double uw, double j, double sign) {   // exp(sign * 2 pi i * 
     xl_sincospi(2.0 * cyc, &s, &c);
     return make_float2((float)c, (float)(sign * s));
 }
-template <int L> struct XlCztSetupOp {
+template <int L> struct XlCztSetupOp : XlOpBase {
     const XlCztSetupParams& p; XlCztAxisConsts a;
-    XL_DEV cf load(int c, int i) const {
+    XL_DEV cf load1(int c, int i) const {
         int t;
         if (c == 0) t = i;
-        else if (c == 1) {
+        else {
             int sft;
-            if (i <= p.m - 1) sft = i; else if (i >= L - (p.M - 1)) sft = i - L; else return make_float2(0.f, 0.f);
+            if (i <= p.m - 1) sft = i; else if (i >= L - (p.M - 1)) sft = i - L; else return cf_zero();
             t = p.m - sft;
-        } else return make_float2(0.f, 0.f);
-        if (t < 0 || t >= a.Lh) return make_float2(0.f, 0.f);
+        }
+        if (t < 0 || t >= a.Lh) return cf_zero();
         return xl_chirp(a.uw, (double)(t - (p.m - 1)), -1.0);  // 1/h_j = conj(h_j)
     }
-    XL_DEV void spec(int c, int beta, cf* v) const {
-        cf* dst = c == 0 ? p.ft : (c == 1 ? p.ftT : (cf*)0);
-        if (!dst) return;
+    XL_DEV void load(int i, cf* v, int stride) const { v[0] = load1(0, i); v[stride] = load1(1, i); }
+    XL_DEV void spec(int beta, const cf* v) const {
 #pragma unroll
-        for (int q = 0; q < 16; ++q) dst[q * (L / 16) + beta] = cf_scale(v[q], 1.0f / L);
+        for (int q = 0; q < 16; ++q) {
+            p.ft[q * (L / 16) + beta] = cf_scale(v[q], 1.0f / L);
+            p.ftT[q * (L / 16) + beta] = cf_scale(v[16 + q], 1.0f / L);
+        }
     }
-    XL_DEV void store(int, int, cf) const {}
+    XL_DEV void store_vec(int, const cf*) const {}
 };
 template <int L> struct XlCztSetup {
     static const char* name() { return "czt_setup"; }
     typedef XlCztSetupParams Params;
-    static constexpr int NT = xl_threads(L, XL_CW);
+    static constexpr int NT = xl_threads(L);
+    static size_t smem() { return xl_smem_bytes(L, XL_V); }
     XL_DEV static void run(const Params& p, cf* s) {
+        cf* t = s + xl_tile_elems(L, XL_V);
         XlCztAxisConsts a = xl_czt_consts(p);
         XL_THREADS(tid, NT) {
             for (int k = tid; k < p.m; k += NT) {  // pre[k]
@@ -484,8 +633,9 @@ template <int L> struct XlCztSetup {
                 p.post[l] = cf_mul(make_float2((float)cs, (float)sn), h);
             }
         }
-        XlCztSetupOp<L> op{p, a};
-        XlFft<L, XL_CW, NT>::forward(s, p.tw, op);
+        XlFft<L, XL_V>::init_tw(t, p.tw);
+        XlCztSetupOp<L> op{{}, p, a};
+        XlFft<L, XL_V>::forward(s, t, op);
     }
 };
 
@@ -507,6 +657,7 @@ struct XlFold {
     static const char* name() { return "fold"; }
     typedef XlFoldParams Params;
     static constexpr int NT = 256;
+    static size_t smem() { return NT * sizeof(float); }
     XL_DEV static void run(const Params& p, cf* s) {
         float* red = (float*)s;
         const double z = p.z ? xl_ldg(p.z) : 0.0;
@@ -520,7 +671,7 @@ struct XlFold {
                 cf t0 = p.t[idx], t1 = p.t[NN + idx], t2 = p.t[2 * NN + idx];
                 cf gx, gy;
                 if (p.mode == XL_FOLD_VRS) {
-                    double ir = 1.0 / sqrt(X * X + Y * Y + z * z);
+                    double ir = xl_rsqrt64(X * X + Y * Y + z * z);
                     float ax = (float)(X * ir), ay = (float)(Y * ir);
                     gx = make_float2(t0.x + ax * t2.x, t0.y + ax * t2.y);
                     gy = make_float2(t1.x + ay * t2.x, t1.y + ay * t2.y);

@@ -14,9 +14,15 @@
 #ifdef XL_HOST_EMU
 struct float2 { float x, y; };
 struct double2 { double x, y; };
+struct alignas(16) float4 { float x, y, z, w; };
 static inline float2 make_float2(float x, float y) { float2 r; r.x = x; r.y = y; return r; }
+static inline float4 make_float4(float x, float y, float z, float w) { float4 r; r.x = x; r.y = y; r.z = z; r.w = w; return r; }
 static inline double2 make_double2(double x, double y) { double2 r; r.x = x; r.y = y; return r; }
+static inline float2 __fadd2_rn(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+static inline float2 __fmul2_rn(float2 a, float2 b) { return make_float2(a.x * b.x, a.y * b.y); }
+static inline float2 __ffma2_rn(float2 a, float2 b, float2 c) { return make_float2(a.x * b.x + c.x, a.y * b.y + c.y); }
 #define XL_DEV inline
+#define XL_HD
 #define XL_DEVFN static inline
 #define XL_RESTRICT
 struct xl_dim3 { int x, y, z; };
@@ -31,11 +37,13 @@ static inline void xl_sincospif(float a, float* s, float* c) { *s = (float)sin(M
 static inline void xl_sincosf(float a, float* s, float* c) { *s = sinf(a); *c = cosf(a); }
 static inline float xl_ldg(const float* p) { return *p; }
 static inline float2 xl_ldg(const float2* p) { return *p; }
+static inline float4 xl_ldg(const float4* p) { return *p; }
 static inline double xl_ldg(const double* p) { return *p; }
 static inline void xl_atomic_add(double* p, double v) { *p += v; }
 #else
 #include <cuda_runtime.h>
 #define XL_DEV __device__ __forceinline__
+#define XL_HD __host__ __device__
 #define XL_DEVFN __device__
 #define XL_RESTRICT __restrict__
 #define XL_BLOCK_X ((int)blockIdx.x)
@@ -48,19 +56,40 @@ XL_DEV void xl_sincospif(float a, float* s, float* c) { sincospif(a, s, c); }
 XL_DEV void xl_sincosf(float a, float* s, float* c) { sincosf(a, s, c); }
 XL_DEV float xl_ldg(const float* p) { return __ldg(p); }
 XL_DEV float2 xl_ldg(const float2* p) { return __ldg(p); }
+XL_DEV float4 xl_ldg(const float4* p) { return __ldg(p); }
 XL_DEV double xl_ldg(const double* p) { return __ldg(p); }
 XL_DEV void xl_atomic_add(double* p, double v) { atomicAdd(p, v); }
 #endif
 
+// ---- complex64 arithmetic on Blackwell's packed f32x2 pipe ---------------------------------------------------------
+// A complex number is one float2 (re, im) = one 64-bit register pair.  Every operation below is written as an f32x2
+// intrinsic whose operands are "swapped" / "half-negated" float2 temporaries; nvcc folds those into the operand
+// modifiers of FADD2 / FMUL2 / FFMA2 (.LO_HI swap, .NP/.PN per-half negation, .F32 scalar broadcast), so that
+//     complex add/sub        = 1 FADD2            multiply by +-i            = free (modifier on the consumer)
+//     complex * real         = 1 FMUL2            complex * complex          = 1 FMUL2 + 1 FFMA2
+// (checked with cuobjdump; measured on B200: a scalar 3-register FFMA issues at half rate, FFMA2 is the full-rate form,
+// profiles/ubench_r01.txt).
 typedef float2 cf;
 
 XL_DEV cf cf_make(float x, float y) { return make_float2(x, y); }
-XL_DEV cf cf_add(cf a, cf b) { return make_float2(a.x + b.x, a.y + b.y); }
-XL_DEV cf cf_sub(cf a, cf b) { return make_float2(a.x - b.x, a.y - b.y); }
-XL_DEV cf cf_mul(cf a, cf b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
-XL_DEV cf cf_mulc(cf a, cf b) { return make_float2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y); }  // a * conj(b)
+XL_DEV cf cf_zero() { return make_float2(0.f, 0.f); }
+XL_DEV cf cf_add(cf a, cf b) { return __fadd2_rn(a, b); }
+XL_DEV cf cf_sub(cf a, cf b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
+XL_DEV cf cf_neg(cf a) { return make_float2(-a.x, -a.y); }
 XL_DEV cf cf_conj(cf a) { return make_float2(a.x, -a.y); }
-XL_DEV cf cf_scale(cf a, float s) { return make_float2(a.x * s, a.y * s); }
-XL_DEV cf cf_fma(cf a, cf b, cf acc) {  // acc + a*b
-    return make_float2(acc.x + a.x * b.x - a.y * b.y, acc.y + a.x * b.y + a.y * b.x);
+XL_DEV cf cf_muli(cf a) { return make_float2(-a.y, a.x); }    // a * (+i)
+XL_DEV cf cf_mulni(cf a) { return make_float2(a.y, -a.x); }   // a * (-i)
+XL_DEV cf cf_scale(cf a, float s) { return __fmul2_rn(a, make_float2(s, s)); }
+XL_DEV cf cf_mul(cf a, cf b) {                                  // a * b
+    return __ffma2_rn(make_float2(-a.y, a.x), make_float2(b.y, b.y), __fmul2_rn(a, make_float2(b.x, b.x)));
+}
+XL_DEV cf cf_mulc(cf a, cf b) {                                 // a * conj(b)
+    return __ffma2_rn(make_float2(a.y, -a.x), make_float2(b.y, b.y), __fmul2_rn(a, make_float2(b.x, b.x)));
+}
+XL_DEV cf cf_fma(cf a, cf b, cf acc) {                          // acc + a*b
+    return __ffma2_rn(make_float2(-a.y, a.x), make_float2(b.y, b.y), __ffma2_rn(a, make_float2(b.x, b.x), acc));
+}
+// real coefficients on complex values: a*sx + b*sy
+XL_DEV cf cf_lin2(cf a, float sx, cf b, float sy) {
+    return __ffma2_rn(b, make_float2(sy, sy), __fmul2_rn(a, make_float2(sx, sx)));
 }
