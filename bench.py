@@ -33,6 +33,8 @@ HALF_WINDOW = 15000.0
 Z_RS = 50000.0      # 5 cm  (BASELINE.json configs[0])
 Z_CZT = 5000.0      # 5 mm  (examples/*_xlumina.py)
 PROPS_PER_STEP = 4
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture (profiles/), bytes
+NCU_TRAFFIC = {}
 METRIC = "RS/VRS/CZT propagations/s at 2048^2 (fwd+grad)"
 UNIT = "propagations/s"
 WORKLOAD = ("scalar RS + VRS (z=5cm) + CZT + VCZT (z=5mm, 2048->2048), each forward+gradient, 2048x2048 complex64, "
@@ -100,42 +102,65 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm (oracle port)
-def cpu_rs_fwd_grad(threads, reps):
-    """Scalar RS forward+gradient (d/dfield, d/dz) at 2048^2 with the torch-CPU complex128 restatement; returns s/prop."""
+def cpu_step_times(threads, reps, mix):
+    """Forward+gradient at 2048^2 with the torch-CPU complex128 restatement of the reference (oracle/oracle_torch.py).
+    mix=True : step i runs propagation i % 4 of the bench's own mix (scalar RS, VRS, CZT, VCZT; same shapes and z as the GPU
+               arm), i.e. every step is ONE propagation and 4 consecutive steps are one GPU-arm step.
+    mix=False: every step = scalar RS (the bounded sample used for the in-line cpu_baseline).  Returns seconds per step."""
     import numpy as np
     import torch
     from oracle import oracle_torch as ot
     torch.set_num_threads(threads)
     rng = np.random.default_rng(0)
     x = np.linspace(-HALF_WINDOW, HALF_WINDOW, N_GRID)
-    u0 = rng.standard_normal((N_GRID, N_GRID)) + 1j * rng.standard_normal((N_GRID, N_GRID))
-    ct = torch.tensor(rng.standard_normal((N_GRID, N_GRID)) + 1j * rng.standard_normal((N_GRID, N_GRID)))
+
+    def crand(*shape):
+        return rng.standard_normal(shape) + 1j * rng.standard_normal(shape)
+
+    u0, e0 = crand(N_GRID, N_GRID), crand(2, N_GRID, N_GRID)
+    ct1, ct3 = torch.tensor(crand(N_GRID, N_GRID)), torch.tensor(crand(3, N_GRID, N_GRID))
     times = []
     for r in range(reps):
-        u = torch.tensor(u0, requires_grad=True)
-        z = torch.tensor(Z_RS + r, dtype=torch.float64, requires_grad=True)
+        kind = r % 4 if mix else 0
         t0 = time.perf_counter()
-        out = ot.RS_propagation(u, x, x, LAMBDA, z)
-        torch.real(torch.sum(ct * out)).backward()
+        if kind == 0:
+            u = torch.tensor(u0, requires_grad=True)
+            z = torch.tensor(Z_RS + 0.37 * r, dtype=torch.float64, requires_grad=True)
+            torch.real(torch.sum(ct1 * ot.RS_propagation(u, x, x, LAMBDA, z))).backward()
+        elif kind == 1:
+            e = torch.tensor(e0, requires_grad=True)
+            zv = torch.tensor(Z_RS + 0.53 * r, dtype=torch.float64, requires_grad=True)
+            torch.real(torch.sum(ct3 * ot.VRS_propagation(e[0], e[1], x, x, LAMBDA, zv))).backward()
+        elif kind == 2:
+            c = torch.tensor(u0, requires_grad=True)
+            torch.real(torch.sum(ct1 * ot.CZT(c, x, x, LAMBDA, Z_CZT + 0.01 * r, x, x))).backward()
+        else:
+            v = torch.tensor(e0, requires_grad=True)
+            torch.real(torch.sum(ct3 * ot.VCZT(v[0], v[1], x, x, LAMBDA, Z_CZT + 0.02 * r, x, x))).backward()
         times.append(time.perf_counter() - t0)
     return times
 
 
 def run_reference(args, rank, world):
+    """The reference's CPU implementation of the path on this box's host cores.  JAX is not installable in this image
+    (DESIGN.md), so this is the line-by-line torch-CPU complex128 restatement, with autograd, on all host threads.  Each
+    step is a bounded sample of the GPU arm's step: ONE of its four propagations, cycling RS, VRS, CZT, VCZT."""
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    times = cpu_rs_fwd_grad(threads, args.warmup + args.steps)[args.warmup:]
+    w4 = 4 * ((args.warmup + 3) // 4)          # keep the cycle aligned: timed step 0 is scalar RS
+    times = cpu_step_times(threads, w4 + args.steps, mix=True)[w4:]
     total = sum(times)
     value = len(times) / total
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "c128", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "reference_step": "1 scalar RS forward+gradient at 2048^2 per step (bounded sample of the mix)"},
+        "config": {"workload": WORKLOAD, "l2": "n/a (CPU)", "sharding": "rank 0 only"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": "scalar RS fwd+grad 2048^2, torch-CPU complex128 restatement (oracle/oracle_torch.py); "
-                                   "JAX is not installable here so the reference itself cannot run"},
+                         "sample": "each step = ONE forward+gradient propagation at 2048^2, cycling scalar RS, VRS, CZT, VCZT "
+                                   "(4 steps = 1 step of the GPU arm); torch-CPU complex128 restatement of the reference "
+                                   "(oracle/oracle_torch.py) on all host threads; the reference itself needs JAX, not installable here"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -274,22 +299,25 @@ def run_ours(args, rank, local_rank, world):
             pass
         peak_gbs = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "6650 GB/s fallback (of fallback)"
-        # dominant kernel: the column convolution kernel (forward FFT x transfer function x inverse FFT in one pass).
-        # Algorithmic bytes per launch: per field 2u read + 2u write of the N x L row spectra, plus
-        # the transfer function once per launch at its y-even minimum 2u;  u = 8*N^2 bytes.
+        # Dominant kernel family: the column kernels of the RS path (rs_cols: column FFT x transfer function x inverse
+        # column FFT; rs_cols_gz: the same on the cotangent plus the column FFT of conj(U) and the Parseval sum for d/dz).
+        # Algorithmic bytes per launch (u = 8*N^2 bytes = one N x N complex64 plane):
+        #   rs_cols     per field: read 2u + write 2u of the N x L row spectra; per launch the transfer function, y-even: 2u
+        #   rs_cols_gz  per field: read 2u (cotangent spectra) + 2u (conj-field spectra) + write 2u; per launch H and Hz: 4u
         u_bytes = 8.0 * N_GRID * N_GRID
         roof = None
-        if "rs_cols" in kern:
-            cnt, tot = kern["rs_cols"]
-            # launches alternate: scalar RS (1 field) and VRS (3 fields): average fields per launch = 2
-            fields = 2.0
-            alg = (4.0 * fields + 2.0) * u_bytes
+        kname = max((kk for kk in ("rs_cols", "rs_cols_gz") if kk in kern), key=lambda kk: kern[kk][1], default=None)
+        if kname:
+            cnt, tot = kern[kname]
+            fields = 2.0   # launches alternate between scalar RS (1 field) and VRS (3 fields)
+            alg = ((4.0 * fields + 2.0) if kname == "rs_cols" else (6.0 * fields + 4.0)) * u_bytes
             avg_s = tot / cnt * 1e-3
             ach = alg / avg_s / 1e9
-            roof = {"kernel": "rs_cols (xl_kernel<XlRsCols<4096>>)", "bound": "hbm", "achieved": ach, "peak": peak_gbs, "unit": "GB/s",
-                    "frac": ach / peak_gbs, "traffic": None, "peak_source": peak_src,
-                    "alg_bytes_per_launch": alg, "avg_launch_us": avg_s * 1e6,
-                    "share_of_step": tot / ms}
+            roof = {"kernel": f"{kname} (xl_kernel<{'XlRsCols' if kname == 'rs_cols' else 'XlRsColsGz'}<4096>>)", "bound": "hbm",
+                    "achieved": ach, "peak": peak_gbs, "unit": "GB/s", "frac": ach / peak_gbs, "traffic": NCU_TRAFFIC.get(kname),
+                    "peak_source": peak_src, "alg_bytes_per_launch": alg, "avg_launch_us": avg_s * 1e6,
+                    "share_of_step": tot / ms,
+                    "note": "FFT arithmetic co-bounds this kernel (fp32 pipe ~55% busy, profiles/): see DESIGN.md section 4"}
         line = {
             "metric": METRIC, "value": world * PROPS_PER_STEP * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
@@ -305,7 +333,7 @@ def run_ours(args, rank, local_rank, world):
         }
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
-            tt = cpu_rs_fwd_grad(threads, 2)[1:]
+            tt = cpu_step_times(threads, 2, mix=False)[1:]
             line["cpu_baseline"] = {"value": 1.0 / (sum(tt) / len(tt)), "unit": UNIT, "cores": threads, "kind": "port",
                                     "sample": "1 scalar RS fwd+grad at 2048^2 after 1 warm-up, torch-CPU complex128 restatement "
                                               "(oracle/oracle_torch.py) on all host threads"}

@@ -237,9 +237,12 @@ extern "C" int xl_rs_transfer(void* H, const double* z, int N, double dx, double
 }
 
 // rows fwd -> cols conv -> rows inv on `nfields` planes
+// rows fwd -> cols conv -> rows inv on `nfields` planes, all fields of a stage in ONE launch: splitting the stages per
+// field keeps a field's spectra L2-resident but was measured slower (1024-CTA launches quantise into 3.5 waves of 296).
 static int rs_apply_impl(XlRsParams p, xl_stream_t st) {
     const int L = p.L, N = p.N;
     int rc;
+    p.f0 = 0;
     XL_FOR_L(L, rc = xl_launch<XlRsRowsFwd<XL>>(XlDim{xl_groups(N), p.nfields}, st, p));
     if (rc) return rc;
     XL_FOR_L(L, rc = xl_launch<XlRsCols<XL>>(XlDim{L / XL_V, p.nfields}, st, p));
@@ -394,18 +397,28 @@ static int czt_plan(CztPlan& pl, int N, int Mx, int My, int ncomp, void* ws, siz
 static int czt_setup(const CztPlan& pl, const double* z, double lambda_over_dx, double Dm_static,
                      double xout0, double xoutl, double yout0, double youtl, const cf* tw, xl_stream_t st) {
     int rc;
-    XlCztSetupParams s;
-    memset(&s, 0, sizeof(s));
-    s.z = z; s.lambda_over_dx = lambda_over_dx; s.Dm_static = Dm_static; s.tw = tw;
-    // y axis (first Bluestein pass, wave_optics.py:349)
-    s.L = pl.Ly; s.m = pl.N; s.M = pl.My; s.out0 = yout0; s.outl = youtl;
-    s.pre = pl.pre_y; s.post = pl.post_y; s.ft = pl.ft_y; s.ftT = pl.ftT_y;
-    XL_FOR_L(pl.Ly, rc = xl_launch<XlCztSetup<XL>>(XlDim{1, 1}, st, s));
+    XlCztSetup2Params sp;
+    memset(&sp, 0, sizeof(sp));
+    for (int ax = 0; ax < 2; ++ax) {
+        XlCztSetupParams& s = sp.a[ax];
+        s.z = z; s.lambda_over_dx = lambda_over_dx; s.Dm_static = Dm_static; s.tw = tw;
+        s.m = pl.N;
+        if (ax == 0) {   // y axis (first Bluestein pass, wave_optics.py:349)
+            s.L = pl.Ly; s.M = pl.My; s.out0 = yout0; s.outl = youtl;
+            s.pre = pl.pre_y; s.post = pl.post_y; s.ft = pl.ft_y; s.ftT = pl.ftT_y;
+        } else {         // x axis (second pass, :352)
+            s.L = pl.Lx; s.M = pl.Mx; s.out0 = xout0; s.outl = xoutl;
+            s.pre = pl.pre_x; s.post = pl.post_x; s.ft = pl.ft_x; s.ftT = pl.ftT_x;
+        }
+    }
+    if (pl.Ly == pl.Lx) {   // both axes in one launch (two CTAs)
+        XL_FOR_L(pl.Ly, rc = xl_launch<XlCztSetup<XL>>(XlDim{2, 1}, st, sp));
+        return rc;
+    }
+    XL_FOR_L(pl.Ly, rc = xl_launch<XlCztSetup<XL>>(XlDim{1, 1}, st, sp));
     if (rc) return rc;
-    // x axis (second pass, :352)
-    s.L = pl.Lx; s.m = pl.N; s.M = pl.Mx; s.out0 = xout0; s.outl = xoutl;
-    s.pre = pl.pre_x; s.post = pl.post_x; s.ft = pl.ft_x; s.ftT = pl.ftT_x;
-    XL_FOR_L(pl.Lx, rc = xl_launch<XlCztSetup<XL>>(XlDim{1, 1}, st, s));
+    sp.a[0] = sp.a[1];
+    XL_FOR_L(pl.Lx, rc = xl_launch<XlCztSetup<XL>>(XlDim{1, 1}, st, sp));
     return rc;
 }
 
@@ -428,18 +441,35 @@ static void czt_out_const(XlCztParams& a, const CztCall& cc) {
     else { a.epi_cr = cc.dx * cc.dy * cc.lambda; a.epi_ci = 0.0; a.epi_times_z = 1; }                   // wave_optics.py:355
 }
 
-template <int PRO, int EPI> static int czt_axis_launch_t(const XlCztParams& a, XlDim grid, xl_stream_t st) {
+template <int PRO, int EPI, int ACC> static int czt_axis_launch_t(const XlCztParams& a, XlDim grid, xl_stream_t st) {
     int rc;
-    XL_FOR_L(a.L, rc = xl_launch<XlCztAxis<XL, PRO, EPI>>(grid, st, a));
+    XL_FOR_L(a.L, rc = xl_launch<XlCztAxis<XL, PRO, EPI, ACC>>(grid, st, a));
     return rc;
 }
-// the five (prologue, epilogue) combinations the forward and adjoint chains use, each compiled branch-free
+static bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
+// The (prologue, epilogue, access shape) combinations the forward and adjoint chains use, each compiled branch-free.
+// Paired 16-byte accesses need an even number of lines and even strides (odd grid sizes take the generic variant).
 static int czt_axis_launch(const XlCztParams& a, XlDim grid, xl_stream_t st) {
-    if (a.pro == XL_PRO_NONE && a.epi == XL_EPI_NONE) return czt_axis_launch_t<XL_PRO_NONE, XL_EPI_NONE>(a, grid, st);
-    if (a.pro == XL_PRO_NONE && a.epi == XL_EPI_RSF) return czt_axis_launch_t<XL_PRO_NONE, XL_EPI_RSF>(a, grid, st);
-    if (a.pro == XL_PRO_RSF && a.epi == XL_EPI_NONE) return czt_axis_launch_t<XL_PRO_RSF, XL_EPI_NONE>(a, grid, st);
-    if (a.pro == XL_PRO_VCZT && a.epi == XL_EPI_NONE) return czt_axis_launch_t<XL_PRO_VCZT, XL_EPI_NONE>(a, grid, st);
-    if (a.pro == XL_PRO_HIGHNA && a.epi == XL_EPI_NONE) return czt_axis_launch_t<XL_PRO_HIGHNA, XL_EPI_NONE>(a, grid, st);
+    const bool even = a.nlines % 2 == 0;
+    const bool pin = even && a.in_line == 1 && a.in_pos % 2 == 0 && a.in_comp % 2 == 0 && aligned16(a.in);
+    const bool pout = even && a.out_line == 1 && a.out_pos % 2 == 0 && a.out_comp % 2 == 0 && aligned16(a.out);
+#define XL_CZT_CASE(P, E)                                                                               \
+    if (a.pro == P && a.epi == E) {                                                                     \
+        if (pin) return czt_axis_launch_t<P, E, XL_ACC_PAIR_IN>(a, grid, st);                           \
+        if (pout) return czt_axis_launch_t<P, E, XL_ACC_PAIR_OUT>(a, grid, st);                         \
+        return czt_axis_launch_t<P, E, XL_ACC_GENERIC>(a, grid, st);                                    \
+    }
+    XL_CZT_CASE(XL_PRO_NONE, XL_EPI_NONE)
+    XL_CZT_CASE(XL_PRO_NONE, XL_EPI_RSF)
+    XL_CZT_CASE(XL_PRO_RSF, XL_EPI_NONE)
+#undef XL_CZT_CASE
+    // the vectorial prologues only occur in the forward chain (column-direction input)
+    if (a.pro == XL_PRO_VCZT && a.epi == XL_EPI_NONE)
+        return pin ? czt_axis_launch_t<XL_PRO_VCZT, XL_EPI_NONE, XL_ACC_PAIR_IN>(a, grid, st)
+                   : czt_axis_launch_t<XL_PRO_VCZT, XL_EPI_NONE, XL_ACC_GENERIC>(a, grid, st);
+    if (a.pro == XL_PRO_HIGHNA && a.epi == XL_EPI_NONE)
+        return pin ? czt_axis_launch_t<XL_PRO_HIGHNA, XL_EPI_NONE, XL_ACC_PAIR_IN>(a, grid, st)
+                   : czt_axis_launch_t<XL_PRO_HIGHNA, XL_EPI_NONE, XL_ACC_GENERIC>(a, grid, st);
     return xl_fail(XL_E_BAD_ARG, "czt: unsupported prologue/epilogue combination%s", "");
 }
 
@@ -467,8 +497,6 @@ static int czt_forward(const CztCall& cc, const void* in, void* out, void* ws, s
     a.pro = cc.mode == 0 ? XL_PRO_RSF : (cc.mode == 1 ? XL_PRO_VCZT : XL_PRO_HIGHNA);
     a.gpro = XlGridFactor{cc.x0, cc.dx, cc.y0, cc.dy, 0};
     a.epi = XL_EPI_NONE;
-    rc = czt_axis_launch(a, XlDim{xl_groups(N), ncomp}, st);
-    if (rc) return rc;
     // pass 2: Bluestein along x for every column of the intermediate
     XlCztParams b;
     czt_common_params(b, cc, tw);
@@ -481,8 +509,9 @@ static int czt_forward(const CztCall& cc, const void* in, void* out, void* ws, s
     b.gepi = XlGridFactor{cc.xout0, dxo, cc.yout0, dyo, 1};
     czt_out_const(b, cc);
     b.flags = cc.flags & XL_CONJ_OUT;
-    rc = czt_axis_launch(b, XlDim{xl_groups(My), ncomp}, st);
-    return rc;
+    rc = czt_axis_launch(a, XlDim{xl_groups(N), ncomp}, st);
+    if (rc) return rc;
+    return czt_axis_launch(b, XlDim{xl_groups(My), ncomp}, st);
 }
 
 static int czt_backward(const CztCall& cc, const void* ct_out, void* ct_in, void* ws, size_t ws_bytes, xl_stream_t st) {
@@ -511,8 +540,6 @@ static int czt_backward(const CztCall& cc, const void* ct_out, void* ct_in, void
     b.epi = XL_EPI_NONE;
     czt_out_const(b, cc);
     b.flags = cc.flags & XL_CONJ_IN;
-    rc = czt_axis_launch(b, XlDim{xl_groups(My), ncomp}, st);
-    if (rc) return rc;
     // transpose of pass 1: rows of the intermediate cotangent (length My) -> columns of ct_field
     XlCztParams a;
     czt_common_params(a, cc, tw);
@@ -524,6 +551,8 @@ static int czt_backward(const CztCall& cc, const void* ct_out, void* ct_in, void
     a.epi = cc.mode == 2 ? XL_EPI_NONE : XL_EPI_RSF;
     a.gepi = XlGridFactor{cc.x0, cc.dx, cc.y0, cc.dy, 0};
     a.flags = cc.mode == 0 ? (cc.flags & XL_CONJ_OUT) : 0;
+    rc = czt_axis_launch(b, XlDim{xl_groups(My), ncomp}, st);
+    if (rc) return rc;
     rc = czt_axis_launch(a, XlDim{xl_groups(N), ncomp}, st);
     if (rc || cc.mode == 0) return rc;
     XlFoldParams f;

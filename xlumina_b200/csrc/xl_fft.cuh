@@ -43,6 +43,26 @@ XL_HD constexpr size_t xl_smem_bytes(int L, int V) { return (size_t)(xl_tile_ele
 
 XL_DEV int xl_pad(int i) { return i + (i >> 4); }
 
+// slot <-> DFT bin of XlFft<L>: with radices (r_1 = R1, 16, ..., 16) and k = q_1 + r_1 q_2 + r_1 r_2 q_3 + ..., the bin
+// k sits in slot  q_m (L/16) + sum_{i<m} q_i L / (16 r_1 ... r_i)   (for L = 4096: the two low hex digits swapped).
+XL_HD constexpr int xl_bin_to_slot(int L, int k) {
+    int P = xl_first_radix(L);
+    int slot = (k % P) * (L / (16 * P));
+    k /= P;
+    while (P * 16 < L) { P *= 16; slot += (k % 16) * (L / (16 * P)); k /= 16; }
+    return slot + k * (L / 16);
+}
+XL_HD constexpr int xl_slot_to_bin(int L, int s) {
+    int P = xl_first_radix(L);
+    int k = s / (L / 16) * (L / 16);          // q_m * (r_1 ... r_{m-1}) == q_m * L/16
+    int beta = s % (L / 16);
+    int w = L / (16 * P);
+    k += beta / w;
+    beta %= w;
+    while (P * 16 < L) { w /= 16; k += (beta / w) * P; beta %= w; P *= 16; }
+    return k;
+}
+
 // tile access: all V lines of one position in a single shared-memory transaction; line l lands in v[l * stride]
 template <int V> struct XlTile;
 template <> struct XlTile<1> {
@@ -169,6 +189,9 @@ template <int NQ, int DIR> XL_DEV void xl_twiddle(cf* v, const cf* w) {
 struct XlOpBase {
     static constexpr bool kInLoHalf = false;   // load() is identically zero for i >= L/2 (compile-time pruning)
     static constexpr bool kOutLoHalf = false;  // store_vec() only receives positions < L/2
+    // run-time (CTA-uniform) version of kInLoHalf: skips the loads and prologue math of the upper half, keeps the full
+    // butterfly -- for ops whose sizes are not known at compile time and whose variants are too many to double
+    XL_DEV bool in_lo_rt() const { return false; }
 };
 
 template <int L, int V> struct XlFft {
@@ -205,7 +228,14 @@ template <int L, int V> struct XlFft {
             for (int n = tid; n < S1; n += NT) {
                 cf v[V * R1];
 #pragma unroll
-                for (int j = 0; j < (Op::kInLoHalf ? R1 / 2 : R1); ++j) op.load(n + S1 * j, v + j, R1);   // line l -> v[l*R1 + j]
+                for (int j = 0; j < (Op::kInLoHalf ? R1 / 2 : R1); ++j) {   // line l -> v[l*R1 + j]
+                    if (!Op::kInLoHalf && j >= R1 / 2 && op.in_lo_rt()) {
+#pragma unroll
+                        for (int l = 0; l < V; ++l) v[l * R1 + j] = cf_zero();
+                    } else {
+                        op.load(n + S1 * j, v + j, R1);
+                    }
+                }
                 cf w[R1];
                 xl_tw_powers<R1>(w, t[n], R1 == 16 ? t[S1 + n] : cf_zero());
 #pragma unroll
@@ -323,6 +353,11 @@ template <int L, int V> struct XlFft {
             }
         }
         XL_SYNC();
+        inv_mids<L / R1>(s, t);
+        inv_last(s, t, op);
+    }
+    // the inverse passes after the first (whose output the caller has already put into the tile) -> op.store_vec
+    template <class Op> XL_DEV static void inverse_tail(cf* s, const cf* t, const Op& op) {
         inv_mids<L / R1>(s, t);
         inv_last(s, t, op);
     }

@@ -33,6 +33,36 @@ XL_DEV void xl_ldg4(const cf* p, cf* a, cf* b) {
 }
 XL_DEV void xl_st4(cf* p, cf a, cf b) { *reinterpret_cast<float4*>(p) = make_float4(a.x, a.y, b.x, b.y); }
 
+// Blocked pair layout  grp[y][2]  (grp = base of slot pair g/2).  The calling thread owns slot g (parity of g == parity of
+// its lane) of the two adjacent rows y0 (v0) and y0+1 (v1); rows >= nrows are not stored / read as zero.
+// GPU: lanes 2k and 2k+1 swap one value so that each issues ONE 16-byte access (even lane: row y0, slots g,g+1; odd lane:
+// row y0+1, slots g-1,g) -- 8-byte scattered accesses halve the L1<->L2 request efficiency (profiles/ubench_r01.txt).
+XL_DEV void xl_blocked_store2(cf* grp, int y0, int nrows, int g, cf v0, cf v1) {
+#ifdef XL_HOST_EMU
+    if (y0 < nrows) grp[(size_t)y0 * 2 + (g & 1)] = v0;
+    if (y0 + 1 < nrows) grp[(size_t)(y0 + 1) * 2 + (g & 1)] = v1;
+#else
+    const bool odd = g & 1;
+    const cf got = xl_xchg1(odd ? v0 : v1), keep = odd ? v1 : v0;
+    const int y = y0 + (odd ? 1 : 0);
+    if (y < nrows) xl_st4(grp + (size_t)y * 2, odd ? got : keep, odd ? keep : got);
+#endif
+}
+XL_DEV void xl_blocked_load2(const cf* grp, int y0, int nrows, int g, cf* v0, cf* v1) {
+#ifdef XL_HOST_EMU
+    *v0 = y0 < nrows ? grp[(size_t)y0 * 2 + (g & 1)] : cf_zero();
+    *v1 = y0 + 1 < nrows ? grp[(size_t)(y0 + 1) * 2 + (g & 1)] : cf_zero();
+#else
+    const bool odd = g & 1;
+    const int y = y0 + (odd ? 1 : 0);
+    cf lo = cf_zero(), hi = cf_zero();
+    if (y < nrows) xl_ld4(grp + (size_t)y * 2, &lo, &hi);
+    const cf got = xl_xchg1(odd ? lo : hi);
+    *v0 = odd ? got : lo;
+    *v1 = odd ? hi : got;
+#endif
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // Rayleigh-Sommerfeld impulse response, reference wave_optics.py:291-297:
 //   h = (1/2pi) * z/r^2 * (1/r - i k) * exp(sgn(z) i k r),  r = sqrt(X^2+Y^2+z^2)
@@ -96,9 +126,10 @@ XL_DEV cf xl_rs_h(double X, double Y, const XlRsHConst& c, int deriv) {
 // ==================================================================================================================
 struct XlRsParams {
     int N, L, nfields, flags;
+    int f0;            // first field of this launch (blockIdx.y counts from it)
     const cf* in;      // [nfields][N][N]   (XL_F_VRS: [2][N][N] = Ex,Ey)
     cf* out;           // [nfields][N][N]
-    cf* spec;          // [nfields][L/2][N][2]
+    cf* spec;          // [fields of this launch][L/2][N][2]   (indexed by blockIdx.y, not by the field number)
     cf* spec2;         // second spectra set (grad-z: spectra of conj(U))
     cf* H;             // [L/2][L][2]
     const cf* H2;      // dH/dz transfer function (grad-z)
@@ -136,16 +167,11 @@ template <int L, bool EZ> struct XlRsRowsFwdOp : XlOpBase {
         for (int l = 0; l < XL_V; ++l) v[l * stride] = load1(yb + l, i);
     }
     XL_DEV void spec(int beta, const cf* v) const {
-        cf* base = p.spec + (size_t)f * L * p.N;
+        cf* base = p.spec + (size_t)XL_BLOCK_Y * L * p.N;
 #pragma unroll
-        for (int l = 0; l < XL_V; ++l) {
-            const int y = yb + l;
-            if (y >= p.N) continue;
-#pragma unroll
-            for (int q = 0; q < 16; ++q) {
-                const int g = q * (L / 16) + beta;
-                base[((size_t)(g / XL_V) * p.N + y) * XL_V + (g % XL_V)] = v[l * 16 + q];
-            }
+        for (int q = 0; q < 16; ++q) {
+            const int g = q * (L / 16) + beta;
+            xl_blocked_store2(base + (size_t)(g / 2) * p.N * 2, yb, p.N, g, v[q], v[16 + q]);
         }
     }
     XL_DEV void store_vec(int, const cf*) const {}
@@ -158,7 +184,7 @@ template <int L> struct XlRsRowsFwd {
     XL_DEV static void run(const Params& p, cf* s) {
         cf* t = s + xl_tile_elems(L, XL_V);
         XlFft<L, XL_V>::init_tw(t, p.tw);
-        const int f = XL_BLOCK_Y, yb = XL_BLOCK_X * XL_V;
+        const int f = p.f0 + XL_BLOCK_Y, yb = XL_BLOCK_X * XL_V;
         if ((p.flags & XL_F_VRS) && f == 2) {   // CTA-uniform
             const double z = xl_ldg(p.z);
             XlRsRowsFwdOp<L, true> op{{}, p, f, yb, z * z};
@@ -170,22 +196,62 @@ template <int L> struct XlRsRowsFwd {
     }
 };
 
+// The impulse response is even in x, so its transfer function is even in the x frequency: only the columns of bins
+// kx <= L/2 are ever computed (h_cols) and the column of bin kx > L/2 is read from its mirror L - kx.
+// Returns the address of element [slot_y = 0] of the column that serves x-slot g; consecutive slot_y are 2 cf apart.
+template <int L> XL_DEV const cf* xl_h_column(const cf* H, int g) {
+    const int k = xl_slot_to_bin(L, g);
+    const int sc = xl_bin_to_slot(L, k <= L / 2 ? k : L - k);
+    return H + (size_t)(sc / 2) * L * 2 + (sc & 1);
+}
+template <int L> XL_DEV bool xl_h_pair_needed(int G) {   // does slot pair G hold a column with bin <= L/2 ?
+    return xl_slot_to_bin(L, 2 * G) <= L / 2 || xl_slot_to_bin(L, 2 * G + 1) <= L / 2;
+}
+
+// Row (slot_y) of the stored half of the transfer function that serves slot q*(L/16)+beta: the slot itself when its
+// bin is <= L/2, else the slot of the mirrored bin L - k.  With k = klow(beta) + q L/16 (q = top digit of the bin):
+// L - k = (15 - q) L/16 + (L/16 - klow)  for klow != 0, and (16 - q) L/16 for klow == 0.
+template <int L> struct XlHRow {
+    int beta, bm;
+    XL_DEV explicit XlHRow(int b) : beta(b), bm(0) {
+        const int klow = xl_slot_to_bin(L, b);
+        if (klow) bm = xl_bin_to_slot(L, L / 16 - klow);
+    }
+    XL_DEV int row(int q) const {
+        if (q < 8) return q * (L / 16) + beta;
+        if (beta == 0) return (16 - q) * (L / 16);
+        return (15 - q) * (L / 16) + bm;
+    }
+};
+
 // K2: column FFT of the row spectra, x transfer function, inverse column FFT, keep rows [0,N).   wave_optics.py:288
 template <int L> struct XlRsColsOp : XlOpBase {
     static constexpr bool kInLoHalf = true, kOutLoHalf = true;
     static constexpr int R1 = xl_first_radix(L), S1 = L / R1;
-    const XlRsParams& p; cf* tile; const cf* Ht;
+    const XlRsParams& p; cf* tile; const cf* H0; const cf* H1;   // transfer-function columns of the two lines (stride 2)
+    int hmode;   // 0: H0,H1 are the two halves of one 16-byte pair (H1 == H0+1); 1: swapped pair (H0 == H1+1); 2: unrelated
     XL_DEV void load(int i, cf* v, int stride) const {
         if (i < p.N) xl_ld4(tile + (size_t)i * XL_V, v, v + stride);
         else { v[0] = cf_zero(); v[stride] = cf_zero(); }
     }
     XL_DEV void spec(int beta, cf* v) const {
+        const XlHRow<L> hr(beta);
+        if (hmode == 2) {
 #pragma unroll
-        for (int q = 0; q < 16; ++q) {
-            cf h0, h1;
-            xl_ldg4(Ht + (size_t)(q * (L / 16) + beta) * XL_V, &h0, &h1);
-            v[q] = cf_mul(v[q], h0);
-            v[16 + q] = cf_mul(v[16 + q], h1);
+            for (int q = 0; q < 16; ++q) {
+                const size_t o = (size_t)hr.row(q) * XL_V;
+                v[q] = cf_mul(v[q], xl_ldg(H0 + o));
+                v[16 + q] = cf_mul(v[16 + q], xl_ldg(H1 + o));
+            }
+        } else {
+            const cf* Hp = hmode == 0 ? H0 : H1;
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+                cf lo, hi;
+                xl_ldg4(Hp + (size_t)hr.row(q) * XL_V, &lo, &hi);
+                v[q] = cf_mul(v[q], hmode == 0 ? lo : hi);
+                v[16 + q] = cf_mul(v[16 + q], hmode == 0 ? hi : lo);
+            }
         }
     }
     XL_DEV void store_vec(int n, const cf* v) const {
@@ -204,8 +270,21 @@ template <int L> struct XlRsCols {
     XL_DEV static void run(const Params& p, cf* s) {
         cf* t = s + xl_tile_elems(L, XL_V);
         XlFft<L, XL_V>::init_tw(t, p.tw);
-        const int G = XL_BLOCK_X, f = XL_BLOCK_Y;
-        XlRsColsOp<L> op{{}, p, p.spec + (size_t)f * L * p.N + (size_t)G * p.N * XL_V, p.H + (size_t)G * L * XL_V};
+        const int G = XL_BLOCK_X, f = p.f0 + XL_BLOCK_Y;
+        const cf* H0 = xl_h_column<L>(p.H, XL_V * G);
+        const cf* H1 = xl_h_column<L>(p.H, XL_V * G + 1);
+        const bool a0 = (((size_t)(H0 - p.H)) & 1) == 0, a1 = (((size_t)(H1 - p.H)) & 1) == 0;
+        const int hmode = (a0 && H1 == H0 + 1) ? 0 : ((a1 && H0 == H1 + 1) ? 1 : 2);
+        XL_THREADS(tid, NT) {   // the spectrum multiply is ~2 passes away: start moving the transfer function into L2 now
+            for (int beta = tid; beta < L / 16; beta += NT)
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {   // stored rows are the slots of y-bins <= L/2 (q < 8, plus slot L/2)
+                    if (beta & 1) continue;       // one prefetch per 32-byte sector
+                    xl_prefetch_l2(H0 + (size_t)(q * (L / 16) + beta) * XL_V);
+                    if (hmode == 2) xl_prefetch_l2(H1 + (size_t)(q * (L / 16) + beta) * XL_V);
+                }
+        }
+        XlRsColsOp<L> op{{}, p, p.spec + (size_t)XL_BLOCK_Y * L * p.N + (size_t)G * p.N * XL_V, H0, H1, hmode};
         XlFft<L, XL_V>::conv(s, t, op);
     }
 };
@@ -217,15 +296,11 @@ template <int L> struct XlRsRowsInvOp : XlOpBase {
     const XlRsParams& p; int f, yb;
     XL_DEV void load(int, cf*, int) const {}
     XL_DEV void spec(int beta, cf* v) const {
-        const cf* base = p.spec + (size_t)f * L * p.N;
+        const cf* base = p.spec + (size_t)XL_BLOCK_Y * L * p.N;
 #pragma unroll
-        for (int l = 0; l < XL_V; ++l) {
-            const int y = yb + l;
-#pragma unroll
-            for (int q = 0; q < 16; ++q) {
-                const int g = q * (L / 16) + beta;
-                v[l * 16 + q] = y < p.N ? base[((size_t)(g / XL_V) * p.N + y) * XL_V + (g % XL_V)] : cf_zero();
-            }
+        for (int q = 0; q < 16; ++q) {
+            const int g = q * (L / 16) + beta;
+            xl_blocked_load2(base + (size_t)(g / 2) * p.N * 2, yb, p.N, g, v + q, v + 16 + q);
         }
     }
     XL_DEV void store_vec(int n, const cf* v) const {
@@ -252,7 +327,7 @@ template <int L> struct XlRsRowsInv {
     XL_DEV static void run(const Params& p, cf* s) {
         cf* t = s + xl_tile_elems(L, XL_V);
         XlFft<L, XL_V>::init_tw(t, p.tw);
-        XlRsRowsInvOp<L> op{{}, p, XL_BLOCK_Y, XL_BLOCK_X * XL_V};
+        XlRsRowsInvOp<L> op{{}, p, p.f0 + XL_BLOCK_Y, XL_BLOCK_X * XL_V};
         XlFft<L, XL_V>::inverse(s, t, op);
     }
 };
@@ -268,14 +343,10 @@ template <int L> struct XlHRowsOp : XlOpBase {
     }
     XL_DEV void spec(int beta, const cf* v) const {
 #pragma unroll
-        for (int l = 0; l < XL_V; ++l) {
-            const int yi = yb + l;
-            if (yi > L / 2) continue;
-#pragma unroll
-            for (int q = 0; q < 16; ++q) {
-                const int g = q * (L / 16) + beta;
-                p.H[((size_t)(g / XL_V) * L + yi) * XL_V + (g % XL_V)] = v[l * 16 + q];
-            }
+        for (int q = 0; q <= 8; ++q) {   // x-bins <= L/2 only (q is the top digit of the bin); the rest is mirrored
+            const int g = q * (L / 16) + beta;
+            if (q == 8 && beta >= 2) continue;   // of the q = 8 slots only the pair holding bin L/2 is needed
+            xl_blocked_store2(p.H + (size_t)(g / 2) * L * 2, yb, L / 2 + 1, g, v[q], v[16 + q]);
         }
     }
     XL_DEV void store_vec(int, const cf*) const {}
@@ -313,8 +384,10 @@ template <int L> struct XlHColsOp : XlOpBase {
     }
     XL_DEV void spec(int beta, const cf* v) const {
 #pragma unroll
-        for (int q = 0; q < 16; ++q)
+        for (int q = 0; q <= 8; ++q) {   // y-bins <= L/2 only: H is even in the y frequency as well (XlHRow)
+            if (q == 8 && beta != 0) continue;
             xl_st4(Ht + (size_t)(q * (L / 16) + beta) * XL_V, cf_scale(v[q], p.hscale), cf_scale(v[16 + q], p.hscale));
+        }
     }
     XL_DEV void store_vec(int, const cf*) const {}
 };
@@ -324,6 +397,7 @@ template <int L> struct XlHCols {
     static constexpr int NT = xl_threads(L);
     static size_t smem() { return xl_smem_bytes(L, XL_V); }
     XL_DEV static void run(const Params& p, cf* s) {
+        if (!xl_h_pair_needed<L>(XL_BLOCK_X)) return;   // CTA-uniform: mirrored columns are never read
         cf* t = s + xl_tile_elems(L, XL_V);
         XlFft<L, XL_V>::init_tw(t, p.tw);
         XlHColsOp<L> op{{}, p, p.H + (size_t)XL_BLOCK_X * L * XL_V};
@@ -332,37 +406,43 @@ template <int L> struct XlHCols {
     }
 };
 
-// K4: backward column kernel with d/dz.  One CTA owns one column PAIR and walks its two columns; per column, the column
-// spectrum W of conj(U) (from spec2) is parked in a second shared-memory tile, then the column spectrum C of the
-// cotangent meets it in registers:  gz += Re sum conj(W)*C*Hz  (Parseval form of ct_z), C*H goes back
-// through the inverse FFT for ct_field.  No scratch in HBM, three FFTs per column.
-template <int L> struct XlRsColsWOp : XlOpBase {
+// K4: backward column kernel with d/dz.  One CTA owns one column PAIR and walks its two columns; per column the two
+// "lines" of the forward FFT are the cotangent spectra column C and the column W of the spectra of conj(U) (spec2), so
+// both column spectra meet in the registers of the same thread:  gz += Re sum conj(W)*C*Hz  (Parseval form of ct_z,
+// SURVEY.md A.1).  C*H then goes through a one-line inverse FFT in a second tile for ct_field.  Three FFTs per column,
+// nothing parked in HBM.
+template <int L> struct XlRsColsGzOp : XlOpBase {
     static constexpr bool kInLoHalf = true;
-    const XlRsParams& p; const cf* tile; int c; cf* wtile;
-    XL_DEV void load(int i, cf* v, int) const { v[0] = i < p.N ? tile[(size_t)i * XL_V + c] : cf_zero(); }
+    const XlRsParams& p; const cf* ctile; const cf* wtile; int c; const cf* Hc; const cf* Hzc; cf* itile; float* red;
+    XL_DEV void load(int i, cf* v, int stride) const {
+        const bool ok = i < p.N;
+        const size_t o = ok ? (size_t)i * XL_V + c : 0;
+        const cf a = ctile[o], w = wtile[o];
+        v[0] = ok ? a : cf_zero();
+        v[stride] = ok ? w : cf_zero();
+    }
     XL_DEV void spec(int beta, const cf* v) const {
+        float acc = 0.f;
+        cf u[16];
+        const XlHRow<L> hr(beta);
 #pragma unroll
-        for (int q = 0; q < 16; ++q) wtile[xl_pad(16 * beta + q)] = v[q];   // thread-private positions: no barrier needed
+        for (int q = 0; q < 16; ++q) {
+            const size_t o = (size_t)hr.row(q) * XL_V;
+            const cf t = cf_mul(v[q], xl_ldg(Hzc + o));
+            acc += v[16 + q].x * t.x + v[16 + q].y * t.y;  // Re(conj(w) * t)
+            u[q] = cf_mul(v[q], xl_ldg(Hc + o));
+        }
+        red[beta] += acc;
+        XlBfly<16, +1, false, false>::run(u);       // first inverse pass, fused
+#pragma unroll
+        for (int j = 0; j < 16; ++j) XlTile<1>::st(itile, 16 * beta + j, u + j, 16);
     }
     XL_DEV void store_vec(int, const cf*) const {}
 };
-template <int L> struct XlRsColsGzOp : XlOpBase {
-    static constexpr bool kInLoHalf = true, kOutLoHalf = true;
+template <int L> struct XlRsColsGzOutOp : XlOpBase {
+    static constexpr bool kOutLoHalf = true;
     static constexpr int R1 = xl_first_radix(L), S1 = L / R1;
-    const XlRsParams& p; cf* tile; int c; const cf* Ht; const cf* Hzt; const cf* wtile; float* red;
-    XL_DEV void load(int i, cf* v, int) const { v[0] = i < p.N ? tile[(size_t)i * XL_V + c] : cf_zero(); }
-    XL_DEV void spec(int beta, cf* v) const {
-        float acc = 0.f;
-#pragma unroll
-        for (int q = 0; q < 16; ++q) {
-            const size_t o = (size_t)(q * (L / 16) + beta) * XL_V + c;
-            const cf w = wtile[xl_pad(16 * beta + q)];
-            const cf t = cf_mul(v[q], xl_ldg(Hzt + o));
-            acc += w.x * t.x + w.y * t.y;  // Re(conj(w) * t)
-            v[q] = cf_mul(v[q], xl_ldg(Ht + o));
-        }
-        red[beta] += acc;
-    }
+    const XlRsParams& p; cf* tile; int c;
     XL_DEV void store_vec(int n, const cf* v) const {
 #pragma unroll
         for (int j = 0; j < R1 / 2; ++j) {
@@ -376,21 +456,22 @@ template <int L> struct XlRsColsGz {
     typedef XlRsParams Params;
     static constexpr int NT = xl_threads(L);
     static constexpr int NB = L / 16;   // butterflies per line == entries of the partial-sum array
-    static size_t smem() { return (size_t)(2 * xl_tile_elems(L, 1) + xl_tw_total(L)) * sizeof(cf) + (size_t)(NB + 32) * sizeof(float); }
+    static size_t smem() { return (size_t)(xl_tile_elems(L, 2) + xl_tile_elems(L, 1) + xl_tw_total(L)) * sizeof(cf) + (size_t)(NB + 32) * sizeof(float); }
     XL_DEV static void run(const Params& p, cf* s) {
-        cf* wtile = s + xl_tile_elems(L, 1);
-        cf* t = wtile + xl_tile_elems(L, 1);
+        cf* itile = s + xl_tile_elems(L, 2);
+        cf* t = itile + xl_tile_elems(L, 1);
         float* red = (float*)(t + xl_tw_total(L));
         XL_THREADS(tid, NT) { for (int i = tid; i < NB; i += NT) red[i] = 0.f; }
-        XlFft<L, 1>::init_tw(t, p.tw);
-        const int G = XL_BLOCK_X, f = XL_BLOCK_Y;
-        const size_t toff = (size_t)f * L * p.N + (size_t)G * p.N * XL_V;
+        XlFft<L, 2>::init_tw(t, p.tw);
+        const int G = XL_BLOCK_X, f = p.f0 + XL_BLOCK_Y;
+        const size_t toff = (size_t)XL_BLOCK_Y * L * p.N + (size_t)G * p.N * XL_V;
         for (int c = 0; c < XL_V; ++c) {
-            XlRsColsWOp<L> opw{{}, p, p.spec2 + toff, c, wtile};
-            XlFft<L, 1>::forward(s, t, opw);
+            XlRsColsGzOp<L> op{{}, p, p.spec + toff, p.spec2 + toff, c, xl_h_column<L>(p.H, XL_V * G + c),
+                               xl_h_column<L>(p.H2, XL_V * G + c), itile, red};
+            XlFft<L, 2>::forward(s, t, op);
             XL_SYNC();
-            XlRsColsGzOp<L> op{{}, p, p.spec + toff, c, p.H + (size_t)G * L * XL_V, p.H2 + (size_t)G * L * XL_V, wtile, red};
-            XlFft<L, 1>::conv(s, t, op);
+            XlRsColsGzOutOp<L> oo{{}, p, p.spec + toff, c};
+            XlFft<L, 1>::inverse_tail(itile, t, oo);
             XL_SYNC();
         }
         XL_THREADS(tid, NT) {
@@ -427,6 +508,8 @@ struct XlGridFactor {     // coordinates of (line, pos): swap=0 -> X from line, 
 
 struct XlCztParams {
     int L, nlines, ncomp, m_in, out_off, m_out, flags;
+    int c0;               // first component of this launch: component = c0 + blockIdx.y selects the Ez / lens row math,
+                          // blockIdx.y alone selects the memory planes (in_comp / out_comp strides)
     const cf* in; long long in_line, in_pos, in_comp;
     cf* out;      long long out_line, out_pos, out_comp;
     const cf* pre; const cf* ft; const cf* post;
@@ -461,48 +544,66 @@ XL_DEV void xl_lens_row(double X, double Y, double R, double f, double s2, int c
     *ay = w * (r1 + r2 * sp);
 }
 
-template <int L, int PRO, int EPI> struct XlCztOp : XlOpBase {
+// ACC selects the global access shape: 0 generic 8-byte accesses; 1 the two lines are adjacent in the INPUT (in_line == 1,
+// 16-byte aligned pairs): one 16-byte load serves both; 2 the same for the OUTPUT (out_line == 1): one 16-byte store.
+enum { XL_ACC_GENERIC = 0, XL_ACC_PAIR_IN = 1, XL_ACC_PAIR_OUT = 2 };
+template <int L, int PRO, int EPI, int ACC> struct XlCztOp : XlOpBase {
     static constexpr int R1 = xl_first_radix(L), S1 = L / R1;
-    const XlCztParams& p; int lb, comp; double z; XlRsHConst hc; cf cst;
+    const XlCztParams& p; int lb, cl, comp; double z; XlRsHConst hc; cf cst;   // cl: launch-local plane, comp: component
+    XL_DEV bool in_lo_rt() const { return p.m_in <= L / 2; }   // zero padding fills the upper half: skip its loads and factors
     XL_DEV void coords(const XlGridFactor& g, int line, int pos, double* X, double* Y) const {
         if (g.swap) { *X = g.x0 + pos * g.dx; *Y = g.y0 + line * g.dy; }
         else { *X = g.x0 + line * g.dx; *Y = g.y0 + pos * g.dy; }
     }
-    // branch-free: out-of-range samples read element 0 and are zeroed afterwards
-    XL_DEV cf load1(int line, int i) const {
-        const bool ok = line < p.nlines && i < p.m_in;
-        const long long o = ok ? (long long)line * p.in_line + (long long)i * p.in_pos : 0;
-        cf v;
-        if (PRO == XL_PRO_NONE) {
-            v = p.in[(long long)comp * p.in_comp + o];
-            if (p.flags & XL_F_CONJ_IN) v = cf_conj(v);
+    // raw operand(s) of both lines at position i (branch-free: out-of-range samples read a valid address, zeroed later)
+    XL_DEV void fetch(const cf* src, int i, bool ok_i, cf* a) const {
+        if (ACC == XL_ACC_PAIR_IN) {
+            xl_ld4(src + (ok_i ? (long long)lb + (long long)i * p.in_pos : 0), a, a + 1);
         } else {
-            double X, Y;
-            coords(p.gpro, line, i, &X, &Y);
-            if (PRO == XL_PRO_RSF) {
-                v = p.in[(long long)comp * p.in_comp + o];
-                if (p.flags & XL_F_CONJ_IN) v = cf_conj(v);
-                v = cf_mul(v, xl_rs_h(X, Y, hc, 0));
-            } else if (PRO == XL_PRO_VCZT) {
-                const cf ex = p.in[o], ey = p.in[p.in_comp + o];
-                // comp 0/1: Ex / Ey;  comp 2: Ez = ((Ex X + Ey Y)/r) * z/r     vectorized_optics.py:341-344
-                const double ir2 = 1.0 / (X * X + Y * Y + z * z);
-                const float ax = comp == 0 ? 1.f : (comp == 1 ? 0.f : (float)(X * z * ir2));
-                const float ay = comp == 0 ? 0.f : (comp == 1 ? 1.f : (float)(Y * z * ir2));
-                v = cf_mul(cf_lin2(ex, ax, ey, ay), xl_rs_h(X, Y, hc, 0));
-            } else {  // XL_PRO_HIGHNA
-                const cf ex = p.in[o], ey = p.in[p.in_comp + o];
-                float ax, ay;
-                xl_lens_row(X, Y, p.lens_R, p.lens_f, p.lens_s2, comp, &ax, &ay);
-                v = cf_lin2(ex, ax, ey, ay);
+#pragma unroll
+            for (int l = 0; l < XL_V; ++l) {
+                const bool ok = ok_i && lb + l < p.nlines;
+                a[l] = src[ok ? (long long)(lb + l) * p.in_line + (long long)i * p.in_pos : 0];
             }
         }
-        v = cf_mul(v, xl_ldg(p.pre + (ok ? i : 0)));
-        return ok ? v : cf_zero();
     }
     XL_DEV void load(int i, cf* v, int stride) const {
+        const bool ok_i = i < p.m_in;
+        cf a[XL_V], b[XL_V];
+        if (PRO == XL_PRO_NONE || PRO == XL_PRO_RSF) {
+            fetch(p.in + (long long)cl * p.in_comp, i, ok_i, a);
+        } else {
+            fetch(p.in, i, ok_i, a);                 // Ex
+            fetch(p.in + p.in_comp, i, ok_i, b);     // Ey
+        }
+        const cf pre = xl_ldg(p.pre + (ok_i ? i : 0));
 #pragma unroll
-        for (int l = 0; l < XL_V; ++l) v[l * stride] = load1(lb + l, i);
+        for (int l = 0; l < XL_V; ++l) {
+            const int line = lb + l;
+            cf x;
+            if (PRO == XL_PRO_NONE) {
+                x = (p.flags & XL_F_CONJ_IN) ? cf_conj(a[l]) : a[l];
+            } else {
+                double X, Y;
+                coords(p.gpro, line, i, &X, &Y);
+                if (PRO == XL_PRO_RSF) {          // F = h(X, Y; z), wave_optics.py:341,344
+                    x = (p.flags & XL_F_CONJ_IN) ? cf_conj(a[l]) : a[l];
+                    x = cf_mul(x, xl_rs_h(X, Y, hc, 0));
+                } else if (PRO == XL_PRO_VCZT) {
+                    // comp 0/1: Ex / Ey;  comp 2: Ez = ((Ex X + Ey Y)/r) * z/r     vectorized_optics.py:341-344
+                    const double ir = xl_rsqrt64(X * X + Y * Y + z * z), ir2 = ir * ir;
+                    const float ax = comp == 0 ? 1.f : (comp == 1 ? 0.f : (float)(X * z * ir2));
+                    const float ay = comp == 0 ? 0.f : (comp == 1 ? 1.f : (float)(Y * z * ir2));
+                    x = cf_mul(cf_lin2(a[l], ax, b[l], ay), xl_rs_h(X, Y, hc, 0));
+                } else {  // XL_PRO_HIGHNA
+                    float ax, ay;
+                    xl_lens_row(X, Y, p.lens_R, p.lens_f, p.lens_s2, comp, &ax, &ay);
+                    x = cf_lin2(a[l], ax, b[l], ay);
+                }
+            }
+            x = cf_mul(x, pre);
+            v[l * stride] = (ok_i && line < p.nlines) ? x : cf_zero();
+        }
     }
     XL_DEV void spec(int beta, cf* v) const {
 #pragma unroll
@@ -512,27 +613,34 @@ template <int L, int PRO, int EPI> struct XlCztOp : XlOpBase {
             for (int l = 0; l < XL_V; ++l) v[l * 16 + q] = cf_mul(v[l * 16 + q], w);
         }
     }
-    XL_DEV void store1(int line, int i, cf val) const {
-        const int o = i - p.out_off;
-        if (line >= p.nlines || o < 0 || o >= p.m_out) return;
-        val = cf_mul(val, xl_ldg(p.post + o));
-        if (EPI == XL_EPI_RSF) {
+    XL_DEV cf finish(int line, int o, cf val, cf post) const {
+        val = cf_mul(val, post);
+        if (EPI == XL_EPI_RSF) {                  // F0 = h(Xout, Yout; z), wave_optics.py:340,355
             double X, Y;
             coords(p.gepi, line, o, &X, &Y);
             val = cf_mul(val, xl_rs_h(X, Y, hc, 0));
         }
         val = cf_mul(val, cst);
-        if (p.flags & XL_F_CONJ_OUT) val = cf_conj(val);
-        p.out[(long long)comp * p.out_comp + (long long)line * p.out_line + (long long)o * p.out_pos] = val;
+        return (p.flags & XL_F_CONJ_OUT) ? cf_conj(val) : val;
     }
     XL_DEV void store_vec(int n, const cf* v) const {
 #pragma unroll
-        for (int l = 0; l < XL_V; ++l)
+        for (int j = 0; j < R1; ++j) {
+            const int o = n + S1 * j - p.out_off;
+            if (o < 0 || o >= p.m_out) continue;
+            const cf post = xl_ldg(p.post + o);
+            cf* dst = p.out + (long long)cl * p.out_comp + (long long)o * p.out_pos;
+            if (ACC == XL_ACC_PAIR_OUT) {
+                xl_st4(dst + lb, finish(lb, o, v[j], post), finish(lb + 1, o, v[R1 + j], post));
+            } else {
 #pragma unroll
-            for (int j = 0; j < R1; ++j) store1(lb + l, n + S1 * j, v[l * R1 + j]);
+                for (int l = 0; l < XL_V; ++l)
+                    if (lb + l < p.nlines) dst[(long long)(lb + l) * p.out_line] = finish(lb + l, o, v[l * R1 + j], post);
+            }
+        }
     }
 };
-template <int L, int PRO, int EPI> struct XlCztAxis {
+template <int L, int PRO, int EPI, int ACC> struct XlCztAxis {
     static const char* name() { return "czt_axis"; }
     typedef XlCztParams Params;
     static constexpr int NT = xl_threads(L);
@@ -543,7 +651,7 @@ template <int L, int PRO, int EPI> struct XlCztAxis {
         const double z = p.z ? xl_ldg(p.z) : 0.0;
         double cr = p.epi_cr, ci = p.epi_ci;
         if (p.epi_times_z) { cr *= z; ci *= z; }
-        XlCztOp<L, PRO, EPI> op{{}, p, XL_BLOCK_X * XL_V, XL_BLOCK_Y, z, xl_rs_hconst(z, p.k), make_float2((float)cr, (float)ci)};
+        XlCztOp<L, PRO, EPI, ACC> op{{}, p, XL_BLOCK_X * XL_V, XL_BLOCK_Y, p.c0 + XL_BLOCK_Y, z, xl_rs_hconst(z, p.k), make_float2((float)cr, (float)ci)};
         XlFft<L, XL_V>::conv(s, t, op);
     }
 };
@@ -604,12 +712,14 @@ template <int L> struct XlCztSetupOp : XlOpBase {
     }
     XL_DEV void store_vec(int, const cf*) const {}
 };
+struct XlCztSetup2Params { XlCztSetupParams a[2]; };   // one CTA per axis (blockIdx.x), both axes in one launch
 template <int L> struct XlCztSetup {
     static const char* name() { return "czt_setup"; }
-    typedef XlCztSetupParams Params;
+    typedef XlCztSetup2Params Params;
     static constexpr int NT = xl_threads(L);
     static size_t smem() { return xl_smem_bytes(L, XL_V); }
-    XL_DEV static void run(const Params& p, cf* s) {
+    XL_DEV static void run(const Params& pp, cf* s) {
+        const XlCztSetupParams& p = pp.a[XL_BLOCK_X];
         cf* t = s + xl_tile_elems(L, XL_V);
         XlCztAxisConsts a = xl_czt_consts(p);
         XL_THREADS(tid, NT) {

@@ -40,6 +40,7 @@ static inline float2 xl_ldg(const float2* p) { return *p; }
 static inline float4 xl_ldg(const float4* p) { return *p; }
 static inline double xl_ldg(const double* p) { return *p; }
 static inline void xl_atomic_add(double* p, double v) { *p += v; }
+static inline void xl_prefetch_l2(const void*) {}
 #else
 #include <cuda_runtime.h>
 #define XL_DEV __device__ __forceinline__
@@ -59,6 +60,13 @@ XL_DEV float2 xl_ldg(const float2* p) { return __ldg(p); }
 XL_DEV float4 xl_ldg(const float4* p) { return __ldg(p); }
 XL_DEV double xl_ldg(const double* p) { return __ldg(p); }
 XL_DEV void xl_atomic_add(double* p, double v) { atomicAdd(p, v); }
+XL_DEV void xl_prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// exchange one complex value with the neighbouring lane (lane ^ 1); callers guarantee that lanes 2k and 2k+1 are
+// active together (the host emulation runs threads one after another and uses plain 8-byte accesses instead)
+XL_DEV float2 xl_xchg1(float2 v) {
+    const unsigned m = __activemask();
+    return make_float2(__shfl_xor_sync(m, v.x, 1), __shfl_xor_sync(m, v.y, 1));
+}
 #endif
 
 // ---- complex64 arithmetic on Blackwell's packed f32x2 pipe ---------------------------------------------------------
