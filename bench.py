@@ -197,11 +197,13 @@ def run_ours(args, rank, local_rank, world):
     cts = {"u": torch.randn(N_GRID, N_GRID, dtype=torch.complex64, device=dev),
            "v3": torch.randn(3, N_GRID, N_GRID, dtype=torch.complex64, device=dev)}
     h2d_bytes = sum(v.numel() * 8 for v in host_sets[0].values())
+    z_base = torch.full((1,), Z_RS, dtype=torch.float64, device=dev)
 
     def step(i, s):
         """Public-API forward + gradient of the four propagators on input set `s`; returns device scalars."""
-        zr = torch.tensor([Z_RS + 0.37 * i], dtype=torch.float64, device=dev, requires_grad=True)
-        zv = torch.tensor([Z_RS + 0.53 * i], dtype=torch.float64, device=dev, requires_grad=True)
+        # fresh z every step, derived on the device (no pageable host-to-device copy that would make the host wait)
+        zr = (z_base + 0.37 * i).requires_grad_(True)
+        zv = (z_base + 0.53 * i).requires_grad_(True)
         u = s["u"].detach().requires_grad_(True)
         o1 = ops.rs_propagation(u, zr, dx, dx, k)
         o1.backward(cts["u"])

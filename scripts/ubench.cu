@@ -21,6 +21,8 @@ template <int MODE> __global__ void __launch_bounds__(256) k_fp(float* out, int 
             if (MODE == 1) { acc[i] = __fadd2_rn(acc[i], va); }                                              // 1 FADD2
             if (MODE == 2) { acc[i].x = fmaf(acc[i].x, va.x, vb.x); acc[i].y = fmaf(acc[i].y, va.y, vb.y); } // 2 FFMA
             if (MODE == 3) { acc[i] = __ffma2_rn(acc[i], va, vb); }                                          // 1 FFMA2
+            if (MODE == 4) { acc[i] = __fadd2_rn(va, make_float2(-acc[i].y, acc[i].x)); }                    // FADD2 with .LO_HI.NP operand
+            if (MODE == 5) { acc[i] = __ffma2_rn(make_float2(-acc[i].y, acc[i].x), make_float2(va.y, va.y), vb); }  // FFMA2 swizzle + broadcast
         }
     }
     float s = 0.f;
@@ -211,13 +213,15 @@ int main(int argc, char** argv) {
     printf("device %s, %d SMs, clock %d kHz\n", pr.name, pr.multiProcessorCount, pr.clockRate);
     float* out; CK(cudaMalloc(&out, 148 * 8 * 256 * sizeof(float)));
     const int iters = only >= 0 ? 1 : 4096;
-    const char* names[4] = {"FADD  x2", "FADD2   ", "FFMA  x2", "FFMA2   "};
-    for (int m = 0; m < 4; ++m) {
+    const char* names[6] = {"FADD  x2", "FADD2   ", "FFMA  x2", "FFMA2   ", "FADD2 swz", "FFMA2 swz"};
+    for (int m = 0; m < 6; ++m) {
         float ms = 0;
         if (m == 0) ms = time_ms([&] { k_fp<0><<<148 * 8, 256>>>(out, iters, 1.0001f, 0.5f); }, 5);
         if (m == 1) ms = time_ms([&] { k_fp<1><<<148 * 8, 256>>>(out, iters, 1.0001f, 0.5f); }, 5);
         if (m == 2) ms = time_ms([&] { k_fp<2><<<148 * 8, 256>>>(out, iters, 1.0001f, 0.5f); }, 5);
         if (m == 3) ms = time_ms([&] { k_fp<3><<<148 * 8, 256>>>(out, iters, 1.0001f, 0.5f); }, 5);
+        if (m == 4) ms = time_ms([&] { k_fp<4><<<148 * 8, 256>>>(out, iters, 1.0001f, 0.5f); }, 5);
+        if (m == 5) ms = time_ms([&] { k_fp<5><<<148 * 8, 256>>>(out, iters, 1.0001f, 0.5f); }, 5);
         double lane_ops = 148.0 * 8 * 256 * (double)iters * 16 * 2;  // fp32 lane-operations
         printf("%s: %.3f ms  %.1f lane-ops/clk/SM (@1.965 GHz)  %.2f T lane-op/s\n", names[m], ms, lane_ops / (ms * 1e-3) / 1.965e9 / 148, lane_ops / ms / 1e9);
     }

@@ -31,7 +31,8 @@ def up_to_date():
 def build(force=False, verbose=False):
     if not force and up_to_date():
         return OUT
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + [SRC, "-o", OUT]
+    fast = ["-DXL_DEV_FAST"] if os.environ.get("XL_FAST") else []   # development only: L in {2048, 4096}
+    cmd = [_nvcc()] + NVCC_FLAGS + fast + (["-Xptxas", "-v"] if verbose else []) + [SRC, "-o", OUT]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)

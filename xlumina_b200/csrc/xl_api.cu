@@ -72,7 +72,9 @@ extern "C" int xl_prof_report(char* buf, int cap) {
 
 #ifndef XL_HOST_EMU
 // register budget: at least 512/NT CTAs per SM (128 registers per thread), so two L=4096 CTAs overlap their phases on an SM
-template <class Body> __global__ void __launch_bounds__(Body::NT, (512 / Body::NT) > 16 ? 16 : (512 / Body::NT)) xl_kernel(const typename Body::Params p) {
+template <class Body, class = void> struct XlMinBlocks { static constexpr int value = (512 / Body::NT) > 16 ? 16 : (512 / Body::NT); };
+template <class Body> struct XlMinBlocks<Body, decltype((void)Body::MINB)> { static constexpr int value = Body::MINB; };   // per-kernel override
+template <class Body> __global__ void __launch_bounds__(Body::NT, XlMinBlocks<Body>::value) xl_kernel(const typename Body::Params p) {
     extern __shared__ float4 xl_smem[];
     Body::run(p, (cf*)xl_smem);
 }
@@ -114,14 +116,21 @@ template <class Body> static int xl_launch(XlDim grid, xl_stream_t stream, const
 #endif
 }
 
-#define XL_FOR_L(L, ...)                                      \
-    switch (L) {                                              \
+// XL_DEV_FAST (development builds only, `XL_FAST=1 python -m xlumina_b200.build`): instantiate the two large sizes only
+#ifdef XL_DEV_FAST
+#define XL_SMALL_L_CASES(...)
+#else
+#define XL_SMALL_L_CASES(...)                                        \
         case 32: { constexpr int XL = 32; __VA_ARGS__; } break;      \
         case 64: { constexpr int XL = 64; __VA_ARGS__; } break;      \
         case 128: { constexpr int XL = 128; __VA_ARGS__; } break;    \
         case 256: { constexpr int XL = 256; __VA_ARGS__; } break;    \
         case 512: { constexpr int XL = 512; __VA_ARGS__; } break;    \
-        case 1024: { constexpr int XL = 1024; __VA_ARGS__; } break;  \
+        case 1024: { constexpr int XL = 1024; __VA_ARGS__; } break;
+#endif
+#define XL_FOR_L(L, ...)                                      \
+    switch (L) {                                              \
+        XL_SMALL_L_CASES(__VA_ARGS__)                         \
         case 2048: { constexpr int XL = 2048; __VA_ARGS__; } break;  \
         case 4096: { constexpr int XL = 4096; __VA_ARGS__; } break;  \
         default: return xl_fail(XL_E_UNSUPPORTED, "padded length %s%lld outside [32,4096]", "", (long long)(L)); \
@@ -237,8 +246,10 @@ extern "C" int xl_rs_transfer(void* H, const double* z, int N, double dx, double
 }
 
 // rows fwd -> cols conv -> rows inv on `nfields` planes
-// rows fwd -> cols conv -> rows inv on `nfields` planes, all fields of a stage in ONE launch: splitting the stages per
-// field keeps a field's spectra L2-resident but was measured slower (1024-CTA launches quantise into 3.5 waves of 296).
+// rows fwd -> cols conv -> rows inv on `nfields` planes, all fields of a stage in ONE launch.  Measured alternatives that
+// were slower or no faster: one launch per field and stage (keeps a field's spectra L2-resident but quantises each
+// 1024-CTA launch into 3.5 waves of 296), and a per-field software pipeline over auxiliary streams (grids this large do
+// not co-schedule: the second kernel only fills the first one's tail).
 static int rs_apply_impl(XlRsParams p, xl_stream_t st) {
     const int L = p.L, N = p.N;
     int rc;
@@ -448,11 +459,13 @@ template <int PRO, int EPI, int ACC> static int czt_axis_launch_t(const XlCztPar
 }
 static bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 // The (prologue, epilogue, access shape) combinations the forward and adjoint chains use, each compiled branch-free.
-// Paired 16-byte accesses need an even number of lines and even strides (odd grid sizes take the generic variant).
+// Paired 16-byte accesses need an even number of lines and even strides, and the paired variants are compiled with the
+// zero-padded / discarded halves pruned (XlCztOp): other sizes take the generic variant.
 static int czt_axis_launch(const XlCztParams& a, XlDim grid, xl_stream_t st) {
-    const bool even = a.nlines % 2 == 0;
-    const bool pin = even && a.in_line == 1 && a.in_pos % 2 == 0 && a.in_comp % 2 == 0 && aligned16(a.in);
-    const bool pout = even && a.out_line == 1 && a.out_pos % 2 == 0 && a.out_comp % 2 == 0 && aligned16(a.out);
+    const bool even = a.nlines % 2 == 0, in_lo = a.m_in <= a.L / 2;
+    const bool pin = even && in_lo && a.in_line == 1 && a.in_pos % 2 == 0 && a.in_comp % 2 == 0 && aligned16(a.in);
+    const bool pout = even && in_lo && a.out_off == 0 && a.m_out <= a.L / 2 && a.out_line == 1 && a.out_pos % 2 == 0 &&
+                      a.out_comp % 2 == 0 && aligned16(a.out);
 #define XL_CZT_CASE(P, E)                                                                               \
     if (a.pro == P && a.epi == E) {                                                                     \
         if (pin) return czt_axis_launch_t<P, E, XL_ACC_PAIR_IN>(a, grid, st);                           \

@@ -129,7 +129,7 @@ struct XlRsParams {
     int f0;            // first field of this launch (blockIdx.y counts from it)
     const cf* in;      // [nfields][N][N]   (XL_F_VRS: [2][N][N] = Ex,Ey)
     cf* out;           // [nfields][N][N]
-    cf* spec;          // [fields of this launch][L/2][N][2]   (indexed by blockIdx.y, not by the field number)
+    cf* spec;          // [nfields][L/2][N][2]
     cf* spec2;         // second spectra set (grad-z: spectra of conj(U))
     cf* H;             // [L/2][L][2]
     const cf* H2;      // dH/dz transfer function (grad-z)
@@ -167,7 +167,7 @@ template <int L, bool EZ> struct XlRsRowsFwdOp : XlOpBase {
         for (int l = 0; l < XL_V; ++l) v[l * stride] = load1(yb + l, i);
     }
     XL_DEV void spec(int beta, const cf* v) const {
-        cf* base = p.spec + (size_t)XL_BLOCK_Y * L * p.N;
+        cf* base = p.spec + (size_t)f * L * p.N;
 #pragma unroll
         for (int q = 0; q < 16; ++q) {
             const int g = q * (L / 16) + beta;
@@ -284,7 +284,7 @@ template <int L> struct XlRsCols {
                     if (hmode == 2) xl_prefetch_l2(H1 + (size_t)(q * (L / 16) + beta) * XL_V);
                 }
         }
-        XlRsColsOp<L> op{{}, p, p.spec + (size_t)XL_BLOCK_Y * L * p.N + (size_t)G * p.N * XL_V, H0, H1, hmode};
+        XlRsColsOp<L> op{{}, p, p.spec + (size_t)f * L * p.N + (size_t)G * p.N * XL_V, H0, H1, hmode};
         XlFft<L, XL_V>::conv(s, t, op);
     }
 };
@@ -296,7 +296,7 @@ template <int L> struct XlRsRowsInvOp : XlOpBase {
     const XlRsParams& p; int f, yb;
     XL_DEV void load(int, cf*, int) const {}
     XL_DEV void spec(int beta, cf* v) const {
-        const cf* base = p.spec + (size_t)XL_BLOCK_Y * L * p.N;
+        const cf* base = p.spec + (size_t)f * L * p.N;
 #pragma unroll
         for (int q = 0; q < 16; ++q) {
             const int g = q * (L / 16) + beta;
@@ -464,7 +464,7 @@ template <int L> struct XlRsColsGz {
         XL_THREADS(tid, NT) { for (int i = tid; i < NB; i += NT) red[i] = 0.f; }
         XlFft<L, 2>::init_tw(t, p.tw);
         const int G = XL_BLOCK_X, f = p.f0 + XL_BLOCK_Y;
-        const size_t toff = (size_t)XL_BLOCK_Y * L * p.N + (size_t)G * p.N * XL_V;
+        const size_t toff = (size_t)f * L * p.N + (size_t)G * p.N * XL_V;
         for (int c = 0; c < XL_V; ++c) {
             XlRsColsGzOp<L> op{{}, p, p.spec + toff, p.spec2 + toff, c, xl_h_column<L>(p.H, XL_V * G + c),
                                xl_h_column<L>(p.H2, XL_V * G + c), itile, red};
@@ -549,6 +549,11 @@ XL_DEV void xl_lens_row(double X, double Y, double R, double f, double s2, int c
 enum { XL_ACC_GENERIC = 0, XL_ACC_PAIR_IN = 1, XL_ACC_PAIR_OUT = 2 };
 template <int L, int PRO, int EPI, int ACC> struct XlCztOp : XlOpBase {
     static constexpr int R1 = xl_first_radix(L), S1 = L / R1;
+    // The paired variants are also the pruned ones (the host selects them only when the sizes allow): the input fills at
+    // most the lower half of the padded line (m_in <= L/2), and the adjoint chain (PAIR_OUT) keeps outputs [0, m_out) with
+    // m_out <= L/2.  Pruning at compile time halves the unrolled prologue / epilogue code of these kernels as well.
+    static constexpr bool kInLoHalf = ACC != XL_ACC_GENERIC;
+    static constexpr bool kOutLoHalf = ACC == XL_ACC_PAIR_OUT;
     const XlCztParams& p; int lb, cl, comp; double z; XlRsHConst hc; cf cst;   // cl: launch-local plane, comp: component
     XL_DEV bool in_lo_rt() const { return p.m_in <= L / 2; }   // zero padding fills the upper half: skip its loads and factors
     XL_DEV void coords(const XlGridFactor& g, int line, int pos, double* X, double* Y) const {
@@ -625,7 +630,7 @@ template <int L, int PRO, int EPI, int ACC> struct XlCztOp : XlOpBase {
     }
     XL_DEV void store_vec(int n, const cf* v) const {
 #pragma unroll
-        for (int j = 0; j < R1; ++j) {
+        for (int j = 0; j < (kOutLoHalf ? R1 / 2 : R1); ++j) {
             const int o = n + S1 * j - p.out_off;
             if (o < 0 || o >= p.m_out) continue;
             const cf post = xl_ldg(p.post + o);

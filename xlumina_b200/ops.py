@@ -65,7 +65,8 @@ def _as_z(z, ref):
     if t is None:
         if len(_z_cache) > 4096:
             _z_cache.clear()
-        t = torch.tensor([float(z)], dtype=torch.float64, device=ref.device)
+        # torch.full is a device-side fill: no pageable host-to-device copy, so the host never waits for the stream
+        t = torch.full((1,), float(z), dtype=torch.float64, device=ref.device)
         _z_cache[key] = t
     return t
 
@@ -78,9 +79,17 @@ def _c64(t):
     return t.contiguous()
 
 
+_grid_cache = {}
+
+
 def _grid(coords):
-    """(first coordinate, spacing, last coordinate, n) of a uniformly spaced 1-D grid given as numpy/torch/list."""
+    """(first coordinate, spacing, last coordinate, n) of a uniformly spaced 1-D grid given as numpy/torch/list.
+    The uniformity check is cached per array object (the hot loop calls this with the same x/y arrays every step)."""
     import numpy as np
+    key = id(coords)
+    hit = _grid_cache.get(key)
+    if hit is not None and hit[0] is coords:
+        return hit[1]
     a = coords.detach().cpu().numpy() if isinstance(coords, torch.Tensor) else np.asarray(coords, dtype=np.float64)
     n = int(a.shape[0])
     first, last = float(a[0]), float(a[-1])
@@ -89,7 +98,11 @@ def _grid(coords):
         d = np.diff(a)
         if np.max(np.abs(d - step)) > 1e-6 * abs(step):
             raise ValueError("xlumina_b200 regenerates coordinate grids analytically: grids must be uniformly spaced")
-    return first, step, last, n
+    res = (first, step, last, n)
+    if len(_grid_cache) > 256:
+        _grid_cache.clear()
+    _grid_cache[key] = (coords, res)     # keeps the array alive, so the id stays valid
+    return res
 
 
 # ---------------------------------------------------------------------------------------------- RS / VRS
