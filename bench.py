@@ -33,8 +33,6 @@ HALF_WINDOW = 15000.0
 Z_RS = 50000.0      # 5 cm  (BASELINE.json configs[0])
 Z_CZT = 5000.0      # 5 mm  (examples/*_xlumina.py)
 PROPS_PER_STEP = 4
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture (profiles/), bytes
-NCU_TRAFFIC = {}
 METRIC = "RS/VRS/CZT propagations/s at 2048^2 (fwd+grad)"
 UNIT = "propagations/s"
 WORKLOAD = ("scalar RS + VRS (z=5cm) + CZT + VCZT (z=5mm, 2048->2048), each forward+gradient, 2048x2048 complex64, "
@@ -248,6 +246,22 @@ def run_ours(args, rank, local_rank, world):
         nm, cnt, tot = ln.split()
         kern[nm] = (int(cnt), float(tot))
 
+    # ---- roofline of the dominant kernel: CUDA events around each launch of the scalar-RS column kernels (1 field per
+    # launch, the shape the committed ncu capture has), inputs rotating through sets larger than L2 -------------------
+    L.xl_prof_enable(1)
+    for i in range(max(args.steps, 5)):
+        sset = dev_sets[i % NSETS]
+        zr = (z_base + 0.11 * i).requires_grad_(True)
+        u = sset["u"].detach().requires_grad_(True)
+        ops.rs_propagation(u, zr, dx, dx, k).backward(cts["u"])
+    torch.cuda.synchronize()
+    L.xl_prof_report(buf, len(buf))
+    L.xl_prof_enable(0)
+    kern1 = {}
+    for ln in buf.value.decode().strip().splitlines():
+        nm, cnt, tot = ln.split()
+        kern1[nm] = (int(cnt), float(tot))
+
     # ---- end-to-end timing through the public API with HOST buffers (e2e) ------------------------------------------
     copy_stream = torch.cuda.Stream(device=dev)
     staged = [dict((kk, torch.empty_like(v, device=dev)) for kk, v in host_sets[0].items()) for _ in range(2)]
@@ -308,18 +322,25 @@ def run_ours(args, rank, local_rank, world):
         #   rs_cols_gz  per field: read 2u (cotangent spectra) + 2u (conj-field spectra) + write 2u; per launch H and Hz: 4u
         u_bytes = 8.0 * N_GRID * N_GRID
         roof = None
+        try:
+            ncu_traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic_r01.json")))
+        except Exception:
+            ncu_traffic = {}
         kname = max((kk for kk in ("rs_cols", "rs_cols_gz") if kk in kern), key=lambda kk: kern[kk][1], default=None)
-        if kname:
-            cnt, tot = kern[kname]
-            fields = 2.0   # launches alternate between scalar RS (1 field) and VRS (3 fields)
-            alg = ((4.0 * fields + 2.0) if kname == "rs_cols" else (6.0 * fields + 4.0)) * u_bytes
+        if kname and kname in kern1:
+            cnt, tot = kern1[kname]                      # scalar-RS launches only: 1 field per launch
+            cls = "XlRsCols" if kname == "rs_cols" else "XlRsColsGz"
+            alg = (6.0 if kname == "rs_cols" else 10.0) * u_bytes
             avg_s = tot / cnt * 1e-3
             ach = alg / avg_s / 1e9
-            roof = {"kernel": f"{kname} (xl_kernel<{'XlRsCols' if kname == 'rs_cols' else 'XlRsColsGz'}<4096>>)", "bound": "hbm",
-                    "achieved": ach, "peak": peak_gbs, "unit": "GB/s", "frac": ach / peak_gbs, "traffic": NCU_TRAFFIC.get(kname),
+            roof = {"kernel": f"{kname} (xl_kernel<{cls}<4096>>, 1 field per launch)", "bound": "hbm",
+                    "achieved": ach, "peak": peak_gbs, "unit": "GB/s", "frac": ach / peak_gbs,
+                    "traffic": ncu_traffic.get(f"{cls}<4096>"),
                     "peak_source": peak_src, "alg_bytes_per_launch": alg, "avg_launch_us": avg_s * 1e6,
-                    "share_of_step": tot / ms,
-                    "note": "FFT arithmetic co-bounds this kernel (fp32 pipe ~55% busy, profiles/): see DESIGN.md section 4"}
+                    "share_of_step": kern[kname][1] / ms,
+                    "note": "algorithmic bytes: 2u+2u (+2u conj-field spectra for _gz) of row spectra per field + 2u per "
+                            "y-even transfer function (SURVEY 8d); the kernel is co-bound by fp32 FFT arithmetic "
+                            "(fp32 pipe 40-50% busy, profiles/summary_r01.txt); traffic = ncu dram read+write of the same launch shape"}
         line = {
             "metric": METRIC, "value": world * PROPS_PER_STEP * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
