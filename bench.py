@@ -26,6 +26,9 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# stdout carries exactly one JSON line: keep NCCL's version banner (NCCL_DEBUG=VERSION on the GPU boxes) off it
+if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+    os.environ["NCCL_DEBUG"] = "WARN"
 
 N_GRID = 2048
 LAMBDA = 0.6328
