@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define XLPROP_VERSION 100
+#define XLPROP_VERSION 101
 
 enum {
     XL_OK = 0,
@@ -76,16 +76,20 @@ int xl_rs_fwd(const void* in, void* out, void* H, const double* z, int N, int nf
               double dx, double dy, double k, int flags, void* ws, size_t ws_bytes, void* stream);
 
 /* VJP of xl_rs_fwd.  ct_in[f] = A^T ct_out[f] (A is complex-symmetric, so this is the forward operator);
- * if grad_z != NULL:  *grad_z += Re sum_f sum ct_out[f] * d out[f]/dz   (needs the primal `in`). */
-int xl_rs_bwd(const void* in, const void* ct_out, void* ct_in, double* grad_z, const void* H, const double* z,
-              int N, int nfields, double dx, double dy, double k, int flags, void* ws, size_t ws_bytes, void* stream);
+ * if grad_z != NULL:  *grad_z += Re sum_f sum ct_out[f] * d out[f]/dz, which needs the primal `in` AND the primal result
+ * `out` of the forward call: d out/dz = i k out + (reduced kernel) * in, and the first term -- which cancels identically
+ * for intensity-type losses and would otherwise drown the rest in complex64 rounding -- is evaluated exactly in real
+ * space as -k Im sum ct_out*out. */
+int xl_rs_bwd(const void* in, const void* out, const void* ct_out, void* ct_in, double* grad_z, const void* H,
+              const double* z, int N, int nfields, double dx, double dy, double k, int flags,
+              void* ws, size_t ws_bytes, void* stream);
 
 /* exy = [Ex, Ey] (2,N,N) -> out = [Ex', Ey', Ez'] (3,N,N); Ez = (Ex X + Ey Y)/sqrt(X^2+Y^2+z^2) is formed while loading
  * (vectorized_optics.py:258-261); x0,y0 = first grid coordinates.  Replaces VRS_propagation_jit (:364-373). */
 int xl_vrs_fwd(const void* exy, void* out, void* H, const double* z, int N, double x0, double y0,
                double dx, double dy, double k, int flags, void* ws, size_t ws_bytes, void* stream);
-int xl_vrs_bwd(const void* exy, const void* ct_out, void* ct_exy, double* grad_z, const void* H, const double* z,
-               int N, double x0, double y0, double dx, double dy, double k, int flags,
+int xl_vrs_bwd(const void* exy, const void* out, const void* ct_out, void* ct_exy, double* grad_z, const void* H,
+               const double* z, int N, double x0, double y0, double dx, double dy, double k, int flags,
                void* ws, size_t ws_bytes, void* stream);
 
 /* ---------------------------------------------------------------- CZT / VCZT -------------------------------- */

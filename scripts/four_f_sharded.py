@@ -1,0 +1,129 @@
+#!/usr/bin/env python
+"""
+cfg 4 of BASELINE.json: the 4f-system phase-mask optimizer with a batch of candidate input masks sharded over the GPUs of
+one box (reference: experiments/four_f_optical_table.py:36-141, experiments/four_f_optimizer.py:35-112,
+experiments/generate_synthetic_data.py:38-60).
+
+Per sample:  mask -> RS(z0) -> SLM(phase1) -> RS(z1) -> SLM(phase2) -> RS(z2) -> |.|^2,  loss = mean MSE-intensity against
+the 2x-magnified mask; parameters (3 distances, 2 phase masks) are shared by the whole batch, so every propagation uses ONE
+transfer function for all the samples of a rank (a batch of fields per library call), and the only collective is one
+flattened all-reduce of the parameter gradients per step (xlumina_b200.sharding.allreduce_grads).
+
+    python scripts/four_f_sharded.py [--batch 64] [--n 1024] [--steps 10] [--warmup 3]
+    python -m torch.distributed.run --nproc-per-node G --master-addr 127.0.0.1 scripts/four_f_sharded.py ...
+Prints one JSON line (optimizer steps/s; "strong" scaling: the global batch is fixed).
+"""
+import argparse
+import json
+import math
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+    os.environ["NCCL_DEBUG"] = "WARN"
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+import xlumina_b200 as xb
+from xlumina_b200 import ops
+from xlumina_b200.sharding import allreduce_grads, shard_range
+
+
+def synthetic_circles(n_samples, x, rng):
+    """Binary elliptical masks and their 2x-magnified target intensities |0.5 * mask(2r)|^2 (generate_synthetic_data.py:38-60)."""
+    X, Y = np.meshgrid(x, x)
+    masks, targets = [], []
+    for _ in range(n_samples):
+        r1, r2 = rng.uniform(100, 1000, size=2)
+        masks.append(((X / r1) ** 2 + (Y / r2) ** 2 < 1).astype(np.float32))
+        targets.append((0.25 * ((X / (2 * r1)) ** 2 + (Y / (2 * r2)) ** 2 < 1)).astype(np.float32))
+    return np.stack(masks), np.stack(targets)
+
+
+def forward_loss(params, masks, targets, beam, dx, k):
+    """loss_dualSLM of the reference (four_f_optical_table.py:103-141) on this rank's slice; returns the SUM of per-sample MSEs."""
+    p0, p1, p2, ph1, ph2 = params
+    cm, offset = 1e4, 1.2
+    f = beam[None] * masks
+    f = ops.rs_propagation(f, (p0.abs() * 100 + offset) * cm, dx, dx, k)
+    f = f * torch.exp(1j * (ph1 * (2 * math.pi) - math.pi))[None]
+    f = ops.rs_propagation(f, (p1.abs() * 100 + offset) * cm, dx, dx, k)
+    f = f * torch.exp(1j * (ph2 * (2 * math.pi) - math.pi))[None]
+    f = ops.rs_propagation(f, (p2.abs() * 100 + offset) * cm, dx, dx, k)
+    inten = f.real ** 2 + f.imag ** 2
+    return ((inten - targets) ** 2).sum(dim=(1, 2)).div(inten.shape[-1] * inten.shape[-2]).sum()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--batch", type=int, default=64)
+    ap.add_argument("--n", type=int, default=1024)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    N, lam = args.n, 0.6328
+    x, _ = xb.space(1500.0, N)
+    dx, k = float(x[1] - x[0]), 2 * math.pi / lam
+    rng = np.random.default_rng(0)                                    # same data on every rank; each takes its slice
+    masks_all, targets_all = synthetic_circles(args.batch, x, rng)
+    a, b = shard_range(args.batch, rank, world)
+    masks = torch.as_tensor(masks_all[a:b], device=dev).to(torch.complex64)
+    targets = torch.as_tensor(targets_all[a:b], device=dev)
+    X, Y = np.meshgrid(x, x)
+    beam = torch.as_tensor(np.exp(-(X ** 2 + Y ** 2) / 1200.0 ** 2).astype(np.complex64), device=dev)   # gaussian_beam, z_w0 = 0
+    prng = np.random.default_rng(1)                                   # four_f_optimizer.py:104-109
+    params = [torch.tensor([prng.uniform(0.027, 1)], dtype=torch.float64, device=dev, requires_grad=True) for _ in range(3)]
+    params += [torch.tensor(prng.uniform(0, 1, (N, N)).astype(np.float32), device=dev, requires_grad=True) for _ in range(2)]
+    opt = torch.optim.AdamW(params, lr=0.01, weight_decay=1e-4)       # optax.adamw(0.01, weight_decay=1e-4), :97-98,112
+
+    def step():
+        opt.zero_grad(set_to_none=False)
+        loss = forward_loss(params, masks, targets, beam, dx, k) / args.batch    # mean over the GLOBAL batch
+        loss.backward()
+        allreduce_grads([p.grad for p in params])
+        opt.step()
+        return loss.detach()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        loss = step()
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    lsum = loss.double().clone()
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(lsum, op=dist.ReduceOp.SUM)
+    if rank == 0:
+        ms = float(t[0]) / args.steps
+        print(json.dumps({"metric": "4f optimizer steps/s (batch %d, %d^2, 3 RS fwd+grad per sample, shared parameters)" % (args.batch, N),
+                          "value": 1e3 / ms, "unit": "steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                          "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "samples_per_rank": b - a,
+                          "propagations_per_s": 3 * args.batch * 1e3 / ms, "loss": float(lsum),
+                          "collective": "one all-reduce of 2*N^2 fp32 + 3 fp64 gradients per step"}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -45,7 +45,7 @@ def test_rs_forward_and_vjp_golden(emu, name):
     ct = c64(g["ct"])
     gin = np.zeros((N, N), np.complex64)
     gz = np.zeros(1)
-    rc = emu.xl_rs_bwd(ptr(c64(g["field"])), ptr(ct), ptr(gin), ptr(gz), ptr(H), ptr(zz), N, 1, x[1] - x[0], y[1] - y[0],
+    rc = emu.xl_rs_bwd(ptr(c64(g["field"])), ptr(out), ptr(ct), ptr(gin), ptr(gz), ptr(H), ptr(zz), N, 1, x[1] - x[0], y[1] - y[0],
                        2 * np.pi / lam, 0, ptr(ws), ws.size, None)
     assert rc == 0, emu.xl_last_error()
     if "vjp_field" in g:
@@ -97,7 +97,7 @@ def test_vrs_forward_and_vjp_golden(emu, name):
     assert rel_l2(out, g["out"]) < TIGHT
     gin = np.zeros((2, N, N), np.complex64)
     gz = np.zeros(1)
-    assert emu.xl_vrs_bwd(ptr(exy), ptr(c64(g["ct"])), ptr(gin), ptr(gz), ptr(H), ptr(zz), N, x[0], y[0], x[1] - x[0], y[1] - y[0],
+    assert emu.xl_vrs_bwd(ptr(exy), ptr(out), ptr(c64(g["ct"])), ptr(gin), ptr(gz), ptr(H), ptr(zz), N, x[0], y[0], x[1] - x[0], y[1] - y[0],
                           k, 0, ptr(ws), ws.size, None) == 0
     if "vjp_field" in g:
         assert rel_l2(gin, g["vjp_field"]) < TIGHT

@@ -259,3 +259,52 @@ def test_errors_are_loud(xb):
         li.CZT(100.0, np.linspace(-1, 1, 32), np.linspace(-1, 1, 32))   # m+M-1 == 64: reference raises too
     with pytest.raises(XlpropError):
         xb.ops.rs_propagation(torch.zeros(4096, 4096, dtype=torch.complex64, device="cuda"), 1.0, 1.0, 1.0, 1.0)
+
+
+@pytest.mark.gpu
+def test_four_f_table_loss_and_shared_parameter_gradients(xb):
+    """cfg 4 (experiments/four_f_optical_table.py:36-141): mask -> RS -> SLM -> RS -> SLM -> RS -> |.|^2 -> MSE over a batch
+    with shared parameters.  Loss and all parameter gradients (3 distances, 2 phase masks) against the torch-CPU
+    complex128 restatement."""
+    import math
+    import torch
+    from oracle import oracle_torch as ot
+    from scripts.four_f_sharded import forward_loss, synthetic_circles
+    N, B, lam = 64, 3, 0.6328
+    x, _ = xb.space(1500.0, N)
+    dx, k = float(x[1] - x[0]), 2 * math.pi / lam
+    rng = np.random.default_rng(5)
+    masks, targets = synthetic_circles(B, x, rng)
+    X, Y = np.meshgrid(x, x)
+    beam = np.exp(-(X ** 2 + Y ** 2) / 1200.0 ** 2)
+    pz = [rng.uniform(0.027, 1) for _ in range(3)]
+    ph = [rng.uniform(0, 1, (N, N)) for _ in range(2)]
+    dev = torch.device("cuda:0")
+    params = [torch.tensor([v], dtype=torch.float64, device=dev, requires_grad=True) for v in pz] + \
+             [torch.tensor(v.astype(np.float32), device=dev, requires_grad=True) for v in ph]
+    loss = forward_loss(params, torch.as_tensor(masks, device=dev).to(torch.complex64), torch.as_tensor(targets, device=dev),
+                        torch.as_tensor(beam.astype(np.complex64), device=dev), dx, k)
+    loss.backward()
+    # oracle
+    rp = [torch.tensor(v, dtype=torch.float64, requires_grad=True) for v in pz] + \
+         [torch.tensor(v.astype(np.float32).astype(np.float64), requires_grad=True) for v in ph]
+    tot = 0
+    for b in range(B):
+        f = torch.tensor(beam * masks[b], dtype=torch.complex128)
+        f = ot.RS_propagation(f, x, x, lam, (rp[0].abs() * 100 + 1.2) * 1e4)
+        f = f * torch.exp(1j * (rp[3] * (2 * math.pi) - math.pi))
+        f = ot.RS_propagation(f, x, x, lam, (rp[1].abs() * 100 + 1.2) * 1e4)
+        f = f * torch.exp(1j * (rp[4] * (2 * math.pi) - math.pi))
+        f = ot.RS_propagation(f, x, x, lam, (rp[2].abs() * 100 + 1.2) * 1e4)
+        inten = f.real ** 2 + f.imag ** 2
+        tot = tot + ((inten - torch.tensor(targets[b], dtype=torch.float64)) ** 2).sum() / (N * N)
+    tot.backward()
+    assert abs(float(loss) - float(tot)) < 1e-4 * abs(float(tot)), (float(loss), float(tot))
+    for i in (3, 4):
+        assert rel_l2(params[i].grad.cpu().numpy(), rp[i].grad.numpy()) < 1e-3      # fp32 parameters / fp32 phase factors
+    # distances: d loss/d z of an intensity loss is a cancellation residue (DESIGN.md section 2); the library evaluates the
+    # cancelling i*k*out term exactly, which leaves errors ~1e-4 of the LARGEST distance gradient of the table
+    gz = np.array([float(params[i].grad) for i in range(3)])
+    gz_ref = np.array([float(rp[i].grad) for i in range(3)])
+    print("four_f distance gradients", gz, gz_ref)
+    assert np.max(np.abs(gz - gz_ref)) < 1e-3 * np.max(np.abs(gz_ref))

@@ -25,9 +25,9 @@ SIGNATURES = {
     "xl_rs_workspace_bytes": (_sz, [_i, _i, _i]),
     "xl_rs_transfer": (_i, [_vp, _vp, _i, _d, _d, _d, _i, _vp]),
     "xl_rs_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _d, _d, _d, _i, _vp, _sz, _vp]),
-    "xl_rs_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _d, _d, _d, _i, _vp, _sz, _vp]),
+    "xl_rs_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _d, _d, _d, _i, _vp, _sz, _vp]),
     "xl_vrs_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _d, _d, _d, _d, _d, _i, _vp, _sz, _vp]),
-    "xl_vrs_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _d, _d, _d, _d, _d, _i, _vp, _sz, _vp]),
+    "xl_vrs_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _d, _d, _d, _d, _d, _i, _vp, _sz, _vp]),
     "xl_czt_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "xl_czt_fwd": (_i, [_vp, _vp, _vp, _d, _i, _i, _i, _i, _d, _d, _d, _d, _d, _d, _d, _d, _i, _vp, _sz, _vp]),
     "xl_czt_bwd": (_i, [_vp, _vp, _vp, _d, _i, _i, _i, _i, _d, _d, _d, _d, _d, _d, _d, _d, _i, _vp, _sz, _vp]),

@@ -289,11 +289,11 @@ extern "C" int xl_vrs_fwd(const void* exy, void* out, void* H, const double* z, 
     return rs_fwd_common(exy, out, H, z, N, 3, 1, x0, y0, dx, dy, k, flags, ws, ws_bytes, (xl_stream_t)stream);
 }
 
-static int rs_bwd_common(const void* in, const void* ct_out, void* ct_in, double* grad_z, const void* H, const double* z,
-                         int N, int nfields, int vrs, double x0, double y0, double dx, double dy, double k, int flags,
-                         void* ws, size_t ws_bytes, xl_stream_t st) {
+static int rs_bwd_common(const void* in, const void* out, const void* ct_out, void* ct_in, double* grad_z, const void* H,
+                         const double* z, int N, int nfields, int vrs, double x0, double y0, double dx, double dy, double k,
+                         int flags, void* ws, size_t ws_bytes, xl_stream_t st) {
     if (!ct_out || !ct_in || !H || !ws || !z) return xl_fail(XL_E_BAD_ARG, "rs_bwd: null pointer%s", "");
-    if (grad_z && !in) return xl_fail(XL_E_BAD_ARG, "rs_bwd: grad_z needs the primal input%s", "");
+    if (grad_z && (!in || !out)) return xl_fail(XL_E_BAD_ARG, "rs_bwd: grad_z needs the primal input and output%s", "");
     XlRsParams p;
     int rc = rs_base_params(p, N, dx, dy, k);
     if (rc) return rc;
@@ -309,8 +309,17 @@ static int rs_bwd_common(const void* in, const void* ct_out, void* ct_in, double
     if (grad_z) {
         p.spec2 = (cf*)c.take(spec_bytes);
         cf* Hz = (cf*)c.take((size_t)L * L * sizeof(cf));
-        rc = rs_transfer_impl(p, Hz, z, 1, st);
+        rc = rs_transfer_impl(p, Hz, z, 1, st);        // reduced derivative h_z - i k h (xl_rs_h)
         if (rc) return rc;
+        {   // the i k h part, exactly, in real space
+            XlDotZParams d;
+            memset(&d, 0, sizeof(d));
+            d.ct = (const cf*)ct_out; d.out = (const cf*)out; d.n = (size_t)nfields * N * N; d.flags = flags & XL_CONJ_IN;
+            d.k = k; d.gz = grad_z;
+            const size_t per = (size_t)XlDotZ::NT * XlDotZ::PER;
+            rc = xl_launch<XlDotZ>(XlDim{(int)((d.n + per - 1) / per), 1}, st, d);
+            if (rc) return rc;
+        }
         // row spectra of conj(U) -> spec2
         XlRsParams pw = p;
         pw.in = (const cf*)in; pw.spec = p.spec2;
@@ -325,7 +334,7 @@ static int rs_bwd_common(const void* in, const void* ct_out, void* ct_in, double
         if (rc) return rc;
         XlRsParams pg = p;
         pg.H2 = Hz; pg.gz = grad_z;
-        XL_FOR_L(L, rc = xl_launch<XlRsColsGz<XL>>(XlDim{L / XL_V, nfields}, st, pg));
+        XL_FOR_L(L, rc = xl_launch<XlRsColsGz<XL>>(XlDim{L, nfields}, st, pg));
         if (rc) return rc;
         XlRsParams po = p;
         po.out = dst;
@@ -353,15 +362,16 @@ static int rs_bwd_common(const void* in, const void* ct_out, void* ct_in, double
     return rc;
 }
 
-extern "C" int xl_rs_bwd(const void* in, const void* ct_out, void* ct_in, double* grad_z, const void* H, const double* z,
-                         int N, int nfields, double dx, double dy, double k, int flags, void* ws, size_t ws_bytes, void* stream) {
+extern "C" int xl_rs_bwd(const void* in, const void* out, const void* ct_out, void* ct_in, double* grad_z, const void* H,
+                         const double* z, int N, int nfields, double dx, double dy, double k, int flags,
+                         void* ws, size_t ws_bytes, void* stream) {
     if (nfields < 1) return xl_fail(XL_E_BAD_ARG, "xl_rs_bwd: nfields < 1%s", "");
-    return rs_bwd_common(in, ct_out, ct_in, grad_z, H, z, N, nfields, 0, 0.0, 0.0, dx, dy, k, flags, ws, ws_bytes, (xl_stream_t)stream);
+    return rs_bwd_common(in, out, ct_out, ct_in, grad_z, H, z, N, nfields, 0, 0.0, 0.0, dx, dy, k, flags, ws, ws_bytes, (xl_stream_t)stream);
 }
-extern "C" int xl_vrs_bwd(const void* exy, const void* ct_out, void* ct_exy, double* grad_z, const void* H, const double* z,
-                          int N, double x0, double y0, double dx, double dy, double k, int flags,
+extern "C" int xl_vrs_bwd(const void* exy, const void* out, const void* ct_out, void* ct_exy, double* grad_z, const void* H,
+                          const double* z, int N, double x0, double y0, double dx, double dy, double k, int flags,
                           void* ws, size_t ws_bytes, void* stream) {
-    return rs_bwd_common(exy, ct_out, ct_exy, grad_z, H, z, N, 3, 1, x0, y0, dx, dy, k, flags, ws, ws_bytes, (xl_stream_t)stream);
+    return rs_bwd_common(exy, out, ct_out, ct_exy, grad_z, H, z, N, 3, 1, x0, y0, dx, dy, k, flags, ws, ws_bytes, (xl_stream_t)stream);
 }
 
 // ================================================================================================ CZT family
@@ -463,8 +473,9 @@ static bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 // zero-padded / discarded halves pruned (XlCztOp): other sizes take the generic variant.
 static int czt_axis_launch(const XlCztParams& a, XlDim grid, xl_stream_t st) {
     const bool even = a.nlines % 2 == 0, in_lo = a.m_in <= a.L / 2;
-    const bool pin = even && in_lo && a.in_line == 1 && a.in_pos % 2 == 0 && a.in_comp % 2 == 0 && aligned16(a.in);
-    const bool pout = even && in_lo && a.out_off == 0 && a.m_out <= a.L / 2 && a.out_line == 1 && a.out_pos % 2 == 0 &&
+    const bool out_lo = a.out_off == 0 && a.m_out <= a.L / 2;
+    const bool pin = even && in_lo && out_lo && a.in_line == 1 && a.in_pos % 2 == 0 && a.in_comp % 2 == 0 && aligned16(a.in);
+    const bool pout = even && in_lo && out_lo && a.out_line == 1 && a.out_pos % 2 == 0 &&
                       a.out_comp % 2 == 0 && aligned16(a.out);
 #define XL_CZT_CASE(P, E)                                                                               \
     if (a.pro == P && a.epi == E) {                                                                     \
@@ -503,7 +514,7 @@ static int czt_forward(const CztCall& cc, const void* in, void* out, void* ws, s
     // pass 1: Bluestein along y for every input column
     XlCztParams a;
     czt_common_params(a, cc, tw);
-    a.L = pl.Ly; a.nlines = N; a.ncomp = ncomp; a.m_in = N; a.out_off = N; a.m_out = My;
+    a.L = pl.Ly; a.nlines = N; a.ncomp = ncomp; a.m_in = N; a.out_off = 0; a.m_out = My;
     a.in = (const cf*)in; a.in_line = 1; a.in_pos = N; a.in_comp = (long long)N * N;
     a.out = pl.mid; a.out_line = My; a.out_pos = 1; a.out_comp = (long long)N * My;
     a.pre = pl.pre_y; a.ft = pl.ft_y; a.post = pl.post_y;
@@ -513,7 +524,7 @@ static int czt_forward(const CztCall& cc, const void* in, void* out, void* ws, s
     // pass 2: Bluestein along x for every column of the intermediate
     XlCztParams b;
     czt_common_params(b, cc, tw);
-    b.L = pl.Lx; b.nlines = My; b.ncomp = ncomp; b.m_in = N; b.out_off = N; b.m_out = Mx;
+    b.L = pl.Lx; b.nlines = My; b.ncomp = ncomp; b.m_in = N; b.out_off = 0; b.m_out = Mx;
     b.in = pl.mid; b.in_line = 1; b.in_pos = My; b.in_comp = (long long)N * My;
     b.out = (cf*)out; b.out_line = Mx; b.out_pos = 1; b.out_comp = (long long)My * Mx;
     b.pre = pl.pre_x; b.ft = pl.ft_x; b.post = pl.post_x;

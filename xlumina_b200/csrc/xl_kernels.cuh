@@ -68,7 +68,12 @@ XL_DEV void xl_blocked_load2(const cf* grp, int y0, int nrows, int g, cf* v0, cf
 //   h = (1/2pi) * z/r^2 * (1/r - i k) * exp(sgn(z) i k r),  r = sqrt(X^2+Y^2+z^2)
 // The phase k*r reaches 4e5 rad, so r is formed in fp64 (fp32 rsqrt seed + one fp64 Newton step: rel. error ~1e-13),
 // reduced to a fraction of a cycle in fp64, and only that fraction goes through fp32 sincospi.
-// deriv=1: dh/dz = (e/2pi) * [ g + (z^2/r) * (g' + s i k g) ],  g = 1/r^3 - i k/r^2,  g' = -3/r^4 + 2 i k/r^3.
+// deriv=1: the REDUCED z-derivative  h_z - i k h,  with  dh/dz = (e/2pi) [ g + (z^2/r)(g' + s i k g) ],  g = 1/r^3 - i k/r^2,
+// g' = -3/r^4 + 2 i k/r^3:   h_z - i k h = (e/2pi) [ g + (z^2/r) g' + i k g z (|z|/r - 1) ],  |z|/r - 1 = -rho^2/(r (r + |z|)).
+// dh/dz is dominated by i k h (a pure phase rotation), whose contribution to the gradient of any intensity-type loss
+// cancels identically; in complex64 the cancellation residue of that term buries the answer.  The library therefore
+// evaluates it exactly in real space (gz += -k Im sum ct*out, XlDotZ) and pushes only the reduced kernel, 1e2-1e4 times
+// smaller, through the FFT pipeline.
 // ------------------------------------------------------------------------------------------------------------------
 // 1/sqrt(r2) to ~1e-13 relative, branch-free (fp32 rsqrt seed + one fp64 Newton step); NaN for r2 == 0
 XL_DEV double xl_rsqrt64(double r2) {
@@ -111,11 +116,12 @@ XL_DEV cf xl_rs_h(double X, double Y, const XlRsHConst& c, int deriv) {
     } else {
         const double gr = ir3, gi = -c.k * ir2;
         const double gpr = -3.0 * ir2 * ir2, gpi = 2.0 * c.k * ir3;
-        // g' + s*i*k*g = (gpr - s*k*gi) + i (gpi + s*k*gr)
-        const double tr = gpr - c.sg * c.k * gi, ti = gpi + c.sg * c.k * gr;
-        const double f = c.z2 * y;
-        ar = (gr + f * tr) * inv2pi;
-        ai = (gi + f * ti) * inv2pi;
+        const double f = c.z2 * y;                                   // z^2/r
+        const double az = c.z < 0 ? -c.z : c.z;
+        const double w = -c.k * c.z * (X * X + Y * Y) * y / (r + az);   // k z (|z|/r - 1)
+        // g + (z^2/r) g' + i w g
+        ar = (gr + f * gpr - w * gi) * inv2pi;
+        ai = (gi + f * gpi + w * gr) * inv2pi;
     }
     const float far = (float)ar, fai = (float)ai;
     return make_float2(far * cs - fai * sn, far * sn + fai * cs);
@@ -463,9 +469,9 @@ template <int L> struct XlRsColsGz {
         float* red = (float*)(t + xl_tw_total(L));
         XL_THREADS(tid, NT) { for (int i = tid; i < NB; i += NT) red[i] = 0.f; }
         XlFft<L, 2>::init_tw(t, p.tw);
-        const int G = XL_BLOCK_X, f = p.f0 + XL_BLOCK_Y;
+        const int G = XL_BLOCK_X >> 1, c = XL_BLOCK_X & 1, f = p.f0 + XL_BLOCK_Y;   // one column per CTA
         const size_t toff = (size_t)f * L * p.N + (size_t)G * p.N * XL_V;
-        for (int c = 0; c < XL_V; ++c) {
+        {
             XlRsColsGzOp<L> op{{}, p, p.spec + toff, p.spec2 + toff, c, xl_h_column<L>(p.H, XL_V * G + c),
                                xl_h_column<L>(p.H2, XL_V * G + c), itile, red};
             XlFft<L, 2>::forward(s, t, op);
@@ -550,10 +556,11 @@ enum { XL_ACC_GENERIC = 0, XL_ACC_PAIR_IN = 1, XL_ACC_PAIR_OUT = 2 };
 template <int L, int PRO, int EPI, int ACC> struct XlCztOp : XlOpBase {
     static constexpr int R1 = xl_first_radix(L), S1 = L / R1;
     // The paired variants are also the pruned ones (the host selects them only when the sizes allow): the input fills at
-    // most the lower half of the padded line (m_in <= L/2), and the adjoint chain (PAIR_OUT) keeps outputs [0, m_out) with
-    // m_out <= L/2.  Pruning at compile time halves the unrolled prologue / epilogue code of these kernels as well.
+    // most the lower half of the padded line (m_in <= L/2) and the kept outputs are [0, m_out) with m_out <= L/2 (the
+    // forward kernel table is rotated so that its slice starts at 0 too, XlCztSetupOp).  Pruning at compile time also
+    // halves the unrolled prologue / epilogue code of these kernels.
     static constexpr bool kInLoHalf = ACC != XL_ACC_GENERIC;
-    static constexpr bool kOutLoHalf = ACC == XL_ACC_PAIR_OUT;
+    static constexpr bool kOutLoHalf = ACC != XL_ACC_GENERIC;
     const XlCztParams& p; int lb, cl, comp; double z; XlRsHConst hc; cf cst;   // cl: launch-local plane, comp: component
     XL_DEV bool in_lo_rt() const { return p.m_in <= L / 2; }   // zero padding fills the upper half: skip its loads and factors
     XL_DEV void coords(const XlGridFactor& g, int line, int pos, double* X, double* Y) const {
@@ -698,7 +705,8 @@ template <int L> struct XlCztSetupOp : XlOpBase {
     const XlCztSetupParams& p; XlCztAxisConsts a;
     XL_DEV cf load1(int c, int i) const {
         int t;
-        if (c == 0) t = i;
+        if (c == 0) t = (i + p.m) & (L - 1);   // kernel rotated left by m: the kept slice b[m : m+M] (wave_optics.py:446) lands
+                                               // at positions [0, M) of the inverse transform, i.e. in its prunable lower half
         else {
             int sft;
             if (i <= p.m - 1) sft = i; else if (i >= L - (p.M - 1)) sft = i - L; else return cf_zero();
@@ -751,6 +759,43 @@ template <int L> struct XlCztSetup {
         XlFft<L, XL_V>::init_tw(t, p.tw);
         XlCztSetupOp<L> op{{}, p, a};
         XlFft<L, XL_V>::forward(s, t, op);
+    }
+};
+
+// gz += -k Im sum ct*out : the i k h part of dh/dz, evaluated exactly (fp32 x fp32 products are exact in fp64).
+struct XlDotZParams {
+    const cf* ct; const cf* out; size_t n; int flags; double k; double* gz;
+};
+struct XlDotZ {
+    static const char* name() { return "dot_z"; }
+    typedef XlDotZParams Params;
+    static constexpr int NT = 256;
+    static constexpr int PER = 8;   // elements per thread
+    static size_t smem() { return NT * sizeof(double); }
+    XL_DEV static void run(const Params& p, cf* s) {
+        double* red = (double*)s;
+        XL_THREADS(tid, NT) {
+            double acc = 0.0;
+            const size_t base = (size_t)XL_BLOCK_X * NT * PER + tid;
+#pragma unroll
+            for (int e = 0; e < PER; ++e) {
+                const size_t idx = base + (size_t)e * NT;
+                if (idx < p.n) {
+                    const cf c = p.ct[idx], o = p.out[idx];
+                    const double ci = (p.flags & XL_F_CONJ_IN) ? -(double)c.y : (double)c.y;
+                    acc += (double)c.x * (double)o.y + ci * (double)o.x;   // Im(ct*out)
+                }
+            }
+            red[tid] = acc;
+        }
+        XL_SYNC();
+        XL_THREADS(tid, NT) {
+            if (tid == 0) {
+                double a = 0.0;
+                for (int i = 0; i < NT; ++i) a += red[i];
+                xl_atomic_add(p.gz, -p.k * a);
+            }
+        }
     }
 };
 

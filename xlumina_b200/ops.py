@@ -120,13 +120,13 @@ class _RS(torch.autograd.Function):
         ws = _workspace(field, need)
         _lib.check(L.xl_rs_fwd(_ptr(field), _ptr(out), _ptr(H), _ptr(z), N, F, dx, dy, k, 0,
                                _ptr(ws), ws.numel(), _stream(field)), "xl_rs_fwd")
-        ctx.save_for_backward(field, z, H)
+        ctx.save_for_backward(field, z, H, out)      # out: the exact i*k*out part of d out/dz (include/xlprop.h)
         ctx.geom = (dx, dy, k)
         return out
 
     @staticmethod
     def backward(ctx, g):
-        field, z, H = ctx.saved_tensors
+        field, z, H, out = ctx.saved_tensors
         dx, dy, k = ctx.geom
         L = _lib.lib()
         F, N = field.shape[0], field.shape[-1]
@@ -136,7 +136,7 @@ class _RS(torch.autograd.Function):
         gz = torch.zeros(1, dtype=torch.float64, device=field.device) if want_z else None
         need = L.xl_rs_workspace_bytes(N, F, 1 if want_z else 0)
         ws = _workspace(field, need)
-        _lib.check(L.xl_rs_bwd(_ptr(field), _ptr(g), _ptr(gin), _ptr(gz), _ptr(H), _ptr(z), N, F, dx, dy, k,
+        _lib.check(L.xl_rs_bwd(_ptr(field), _ptr(out), _ptr(g), _ptr(gin), _ptr(gz), _ptr(H), _ptr(z), N, F, dx, dy, k,
                                _lib.XL_CONJ_IN | _lib.XL_CONJ_OUT, _ptr(ws), ws.numel(), _stream(field)), "xl_rs_bwd")
         return gin, gz, None, None, None
 
@@ -154,13 +154,13 @@ class _VRS(torch.autograd.Function):
         ws = _workspace(exy, L.xl_rs_workspace_bytes(N, 3, 0))
         _lib.check(L.xl_vrs_fwd(_ptr(exy), _ptr(out), _ptr(H), _ptr(z), N, x0, y0, dx, dy, k, 0,
                                 _ptr(ws), ws.numel(), _stream(exy)), "xl_vrs_fwd")
-        ctx.save_for_backward(exy, z, H)
+        ctx.save_for_backward(exy, z, H, out)
         ctx.geom = (x0, y0, dx, dy, k)
         return out
 
     @staticmethod
     def backward(ctx, g):
-        exy, z, H = ctx.saved_tensors
+        exy, z, H, out = ctx.saved_tensors
         x0, y0, dx, dy, k = ctx.geom
         L = _lib.lib()
         N = exy.shape[-1]
@@ -169,7 +169,7 @@ class _VRS(torch.autograd.Function):
         gin = torch.empty_like(exy)
         gz = torch.zeros(1, dtype=torch.float64, device=exy.device) if want_z else None
         ws = _workspace(exy, L.xl_rs_workspace_bytes(N, 3, 1 if want_z else 0))
-        _lib.check(L.xl_vrs_bwd(_ptr(exy), _ptr(g), _ptr(gin), _ptr(gz), _ptr(H), _ptr(z), N, x0, y0, dx, dy, k,
+        _lib.check(L.xl_vrs_bwd(_ptr(exy), _ptr(out), _ptr(g), _ptr(gin), _ptr(gz), _ptr(H), _ptr(z), N, x0, y0, dx, dy, k,
                                 _lib.XL_CONJ_IN | _lib.XL_CONJ_OUT, _ptr(ws), ws.numel(), _stream(exy)), "xl_vrs_bwd")
         return gin, gz, None, None, None, None, None
 
