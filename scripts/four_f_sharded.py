@@ -63,6 +63,8 @@ def main():
     ap.add_argument("--n", type=int, default=1024)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--graph", action="store_true", help="single GPU only: capture the whole optimizer step in ONE CUDA graph "
+                    "and replay it (the library neither allocates nor synchronises in steady state, so it captures as is)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -85,7 +87,7 @@ def main():
     prng = np.random.default_rng(1)                                   # four_f_optimizer.py:104-109
     params = [torch.tensor([prng.uniform(0.027, 1)], dtype=torch.float64, device=dev, requires_grad=True) for _ in range(3)]
     params += [torch.tensor(prng.uniform(0, 1, (N, N)).astype(np.float32), device=dev, requires_grad=True) for _ in range(2)]
-    opt = torch.optim.AdamW(params, lr=0.01, weight_decay=1e-4)       # optax.adamw(0.01, weight_decay=1e-4), :97-98,112
+    opt = torch.optim.AdamW(params, lr=0.01, weight_decay=1e-4, capturable=True)   # optax.adamw(0.01, weight_decay=1e-4), :97-98,112
 
     def step():
         opt.zero_grad(set_to_none=False)
@@ -100,6 +102,26 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    for p in params:
+        p.grad = torch.zeros_like(p)
+    if args.graph and world == 1:
+        # The whole optimizer step (3 RS forward, 3 backward with d/dz and AdamW) as ONE CUDA graph: measured 3.59 -> 3.22 ms
+        # per step at 8 samples per GPU.  Single GPU only: capturing the NCCL all-reduce hung in round 1 (not investigated).
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                step()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        barrier()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            static_loss = step()
+        eager_step = step
+
+        def step():   # noqa: F811
+            graph.replay()
+            return static_loss
     for _ in range(args.warmup):
         step()
     barrier()
