@@ -92,6 +92,24 @@ int xl_vrs_bwd(const void* exy, const void* out, const void* ct_out, void* ct_ex
                const double* z, int N, double x0, double y0, double dx, double dy, double k, int flags,
                void* ws, size_t ws_bytes, void* stream);
 
+/* ---------------------------------------------------------------- slab-decomposed RS (multi-GPU) ------------ */
+/* One N x N field split into row slabs over G ranks (N a multiple of 2G, L/2 a multiple of G, L = xl_rs_padded_length(N)):
+ * rank g owns field rows [g N/G, (g+1) N/G).  These are the per-rank STAGES; the caller moves data between them with an
+ * all-to-all (xlumina_b200/slab.py uses torch.distributed: NCCL over NVLink on GPUs).  Forward:
+ *     xl_slab_h_rows -> all-to-all -> xl_slab_h_cols                       (transfer-function slab, once per z)
+ *     xl_slab_rows_fwd -> all-to-all -> xl_slab_cols -> all-to-all -> xl_slab_rows_inv
+ * Buffers: a spectra buffer on the row side is [L/2 slot pairs][rows of this rank][2] complex64; after an all-to-all that
+ * sends peer r the slot pairs [r P, (r+1) P), P = (L/2)/G, it is [source rank][P][rows of that rank][2] on the column side,
+ * and the second all-to-all is the exact inverse.  The VJP with respect to the field is the same chain applied to the
+ * cotangent (the operator is complex-symmetric); d/dz is single-GPU only in this version.
+ * Replaces the same reference lines as xl_rs_fwd (wave_optics.py:281-297). */
+int xl_slab_h_rows_per_rank(int N, int G);   /* rows of the y >= 0 half of the impulse response each rank transforms */
+int xl_slab_h_rows(void* R, const double* z, int N, int G, int rank, double dx, double dy, double k, void* stream);
+int xl_slab_h_cols(const void* Th, void* Hloc, int N, int G, double dx, double dy, void* stream);
+int xl_slab_rows_fwd(const void* in_local, void* S, int N, int G, int flags, void* stream);
+int xl_slab_cols(void* T, const void* Hloc, int N, int G, void* stream);
+int xl_slab_rows_inv(const void* S, void* out_local, int N, int G, int flags, void* stream);
+
 /* ---------------------------------------------------------------- CZT / VCZT -------------------------------- */
 /* vectorial = 0: in (N,N) -> out (My,Mx)            CZT_jit,  wave_optics.py:333-357
  * vectorial = 1: in = [Ex,Ey] (2,N,N) -> out (3,My,Mx); Ez = ((Ex X + Ey Y)/r) z/r   VCZT, vectorized_optics.py:341-344,375-384

@@ -308,3 +308,22 @@ def test_four_f_table_loss_and_shared_parameter_gradients(xb):
     gz_ref = np.array([float(rp[i].grad) for i in range(3)])
     print("four_f distance gradients", gz, gz_ref)
     assert np.max(np.abs(gz - gz_ref)) < 1e-3 * np.max(np.abs(gz_ref))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("N", [256, 1024])
+def test_slab_stage_kernels_single_rank_equal_fused_path(xb, N):
+    """The slab-decomposed chain (xl_slab_* stage entry points, xlumina_b200/slab.py) with one rank must reproduce the
+    single-GPU path; the 2- and 4-rank decompositions are covered on CPU by tests/test_slab.py and on 2 GPUs by
+    scripts/slab_check.py (profiles/scaling_r01.md)."""
+    from xlumina_b200 import ops, slab
+    rng = np.random.default_rng(N)
+    x, _ = xb.space(1500.0, N)
+    dx, k = float(x[1] - x[0]), 2 * np.pi / 0.6328
+    u = dev_c64(crand(rng, N, N))
+    ref = ops.rs_propagation(u, 30000.0, dx, dx, k)
+    out, H = slab.rs_propagation_slab(u, 30000.0, dx, dx, k, return_transfer=True)
+    assert rel_l2(out.cpu().numpy(), ref.cpu().numpy()) < 2e-6
+    ct = dev_c64(crand(rng, N, N))
+    vjp = slab.rs_slab_vjp(ct, H)
+    assert rel_l2(vjp.cpu().numpy(), ops.rs_propagation(ct, 30000.0, dx, dx, k).cpu().numpy()) < 2e-6

@@ -219,6 +219,7 @@ static int rs_base_params(XlRsParams& p, int N, double dx, double dy, double k) 
     p.N = N;
     p.L = xl_rs_padded_length(N);
     if (!p.L) return xl_fail(XL_E_UNSUPPORTED, "RS: N=%s%lld unsupported (padded length must be in [32,4096])", "", N);
+    p.rows = N; p.chunk_rows = N;
     p.dx = dx; p.dy = dy; p.k = k;
     p.hscale = (float)(dx * dy / ((double)p.L * (double)p.L));
     p.tw = xl_twiddles();
@@ -230,6 +231,7 @@ static int rs_transfer_impl(XlRsParams p, cf* H, const double* z, int deriv, xl_
     p.H = H; p.z = z;
     p.flags = deriv ? XL_F_DERIV : 0;
     const int L = p.L;
+    p.rows = L; p.hrow0 = 0; p.hstore_all = 0;   // row spectra of h live inside H: [L/2][L][2], rows 0..L/2
     int rc;
     XL_FOR_L(L, rc = xl_launch<XlHRows<XL>>(XlDim{xl_groups(L / 2 + 1), 1}, st, p));
     if (rc) return rc;
@@ -372,6 +374,87 @@ extern "C" int xl_vrs_bwd(const void* exy, const void* out, const void* ct_out, 
                           const double* z, int N, double x0, double y0, double dx, double dy, double k, int flags,
                           void* ws, size_t ws_bytes, void* stream) {
     return rs_bwd_common(exy, out, ct_out, ct_exy, grad_z, H, z, N, 3, 1, x0, y0, dx, dy, k, flags, ws, ws_bytes, (xl_stream_t)stream);
+}
+
+// ================================================================================================ slab-decomposed RS
+// Stage-level entry points of the multi-GPU RS path: the N x N field is split into row slabs, one per
+// rank; the all-to-all transposes between the stages are the caller's (NCCL via torch.distributed in
+// xlumina_b200/slab.py).  Geometry for G ranks:  rows = N/G field rows per rank (even), pairs = (L/2)/G x-slot pairs per
+// rank, hrows = xl_slab_h_rows(N, G) rows of the y >= 0 half of the impulse response per rank.
+//   exchanged layout of a spectra buffer:  [source rank][pairs][rows of that rank][2]   (chunks contiguous per peer)
+extern "C" int xl_slab_h_rows_per_rank(int N, int G) {
+    const int L = xl_rs_padded_length(N);
+    if (!L || G < 1) return 0;
+    int r = (L / 2 + 1 + G - 1) / G;
+    return r + (r & 1);   // row pairs stay on one rank
+}
+static int slab_check(int N, int G, int L) {
+    if (!L) return xl_fail(XL_E_UNSUPPORTED, "slab: N=%s%lld unsupported (padded length must be in [32,4096])", "", N);
+    if (G < 1 || N % (2 * G) != 0 || (L / 2) % G != 0)
+        return xl_fail(XL_E_BAD_ARG, "slab: N must be a multiple of 2*G and L/2 a multiple of G (G=%s%lld)", "", G);
+    return XL_OK;
+}
+// row spectra of this rank's y rows [row0, row0 + hrows) of the impulse response: R[L/2][hrows][2]
+extern "C" int xl_slab_h_rows(void* R, const double* z, int N, int G, int rank, double dx, double dy, double k, void* stream) {
+    if (!R || !z) return xl_fail(XL_E_BAD_ARG, "xl_slab_h_rows: null pointer%s", "");
+    XlRsParams p;
+    int rc = rs_base_params(p, N, dx, dy, k);
+    if (rc) return rc;
+    if ((rc = slab_check(N, G, p.L))) return rc;
+    const int hr = xl_slab_h_rows_per_rank(N, G);
+    p.H = (cf*)R; p.z = z; p.flags = 0;
+    p.rows = hr; p.hrow0 = rank * hr; p.hstore_all = 1;
+    const int L = p.L;
+    XL_FOR_L(L, rc = xl_launch<XlHRows<XL>>(XlDim{xl_groups(hr), 1}, (xl_stream_t)stream, p));
+    return rc;
+}
+// Th = exchanged row spectra of h [G][pairs][hrows][2]  ->  this rank's transfer-function slab Hloc[pairs][L][2]
+extern "C" int xl_slab_h_cols(const void* Th, void* Hloc, int N, int G, double dx, double dy, void* stream) {
+    if (!Th || !Hloc) return xl_fail(XL_E_BAD_ARG, "xl_slab_h_cols: null pointer%s", "");
+    XlRsParams p;
+    int rc = rs_base_params(p, N, dx, dy, 0.0);
+    if (rc) return rc;
+    if ((rc = slab_check(N, G, p.L))) return rc;
+    const int L = p.L, pairs = (L / 2) / G;
+    p.spec = (cf*)Th; p.H = (cf*)Hloc; p.chunk_rows = xl_slab_h_rows_per_rank(N, G); p.nfields = pairs;
+    XL_FOR_L(L, rc = xl_launch<XlHColsSlab<XL>>(XlDim{pairs, 1}, (xl_stream_t)stream, p));
+    return rc;
+}
+// this rank's field rows in_local[rows][N]  ->  row spectra S[L/2][rows][2]
+extern "C" int xl_slab_rows_fwd(const void* in_local, void* S, int N, int G, int flags, void* stream) {
+    if (!in_local || !S) return xl_fail(XL_E_BAD_ARG, "xl_slab_rows_fwd: null pointer%s", "");
+    XlRsParams p;
+    int rc = rs_base_params(p, N, 1.0, 1.0, 0.0);
+    if (rc) return rc;
+    if ((rc = slab_check(N, G, p.L))) return rc;
+    p.in = (const cf*)in_local; p.spec = (cf*)S; p.nfields = 1; p.rows = N / G; p.flags = flags & XL_CONJ_IN;
+    const int L = p.L;
+    XL_FOR_L(L, rc = xl_launch<XlRsRowsFwd<XL>>(XlDim{xl_groups(p.rows), 1}, (xl_stream_t)stream, p));
+    return rc;
+}
+// T = exchanged spectra [G][pairs][N/G][2], filtered in place by this rank's transfer-function slab
+extern "C" int xl_slab_cols(void* T, const void* Hloc, int N, int G, void* stream) {
+    if (!T || !Hloc) return xl_fail(XL_E_BAD_ARG, "xl_slab_cols: null pointer%s", "");
+    XlRsParams p;
+    int rc = rs_base_params(p, N, 1.0, 1.0, 0.0);
+    if (rc) return rc;
+    if ((rc = slab_check(N, G, p.L))) return rc;
+    const int L = p.L, pairs = (L / 2) / G;
+    p.spec = (cf*)T; p.H = (cf*)Hloc; p.chunk_rows = N / G; p.nfields = pairs;
+    XL_FOR_L(L, rc = xl_launch<XlRsColsSlab<XL>>(XlDim{pairs, 1}, (xl_stream_t)stream, p));
+    return rc;
+}
+// S = spectra exchanged back, [L/2][rows][2]  ->  this rank's output rows out_local[rows][N]
+extern "C" int xl_slab_rows_inv(const void* S, void* out_local, int N, int G, int flags, void* stream) {
+    if (!S || !out_local) return xl_fail(XL_E_BAD_ARG, "xl_slab_rows_inv: null pointer%s", "");
+    XlRsParams p;
+    int rc = rs_base_params(p, N, 1.0, 1.0, 0.0);
+    if (rc) return rc;
+    if ((rc = slab_check(N, G, p.L))) return rc;
+    p.spec = (cf*)S; p.out = (cf*)out_local; p.nfields = 1; p.rows = N / G; p.flags = flags & XL_CONJ_OUT;
+    const int L = p.L;
+    XL_FOR_L(L, rc = xl_launch<XlRsRowsInv<XL>>(XlDim{xl_groups(p.rows), 1}, (xl_stream_t)stream, p));
+    return rc;
 }
 
 // ================================================================================================ CZT family

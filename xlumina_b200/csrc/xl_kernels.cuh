@@ -133,6 +133,9 @@ XL_DEV cf xl_rs_h(double X, double Y, const XlRsHConst& c, int deriv) {
 struct XlRsParams {
     int N, L, nfields, flags;
     int f0;            // first field of this launch (blockIdx.y counts from it)
+    int rows;          // rows of this launch's slab == row count of the blocked layouts (N on a single GPU)
+    int chunk_rows;    // slab column kernels: rows per source rank in the exchanged layout [rank][pair][chunk_rows][2]
+    int hrow0, hstore_all;   // slab h_rows: first y row of this rank; store every x slot pair (no x-mirror skipping)
     const cf* in;      // [nfields][N][N]   (XL_F_VRS: [2][N][N] = Ex,Ey)
     cf* out;           // [nfields][N][N]
     cf* spec;          // [nfields][L/2][N][2]
@@ -154,8 +157,8 @@ template <int L, bool EZ> struct XlRsRowsFwdOp : XlOpBase {
     const XlRsParams& p; int f, yb; double z2;
     XL_DEV cf load1(int y, int i) const {
         const int N = p.N;
-        const bool ok = y < N && i < N;
-        const size_t NN = (size_t)N * N, o = ok ? (size_t)y * N + i : 0;
+        const bool ok = y < p.rows && i < N;
+        const size_t NN = (size_t)p.rows * N, o = ok ? (size_t)y * N + i : 0;
         cf v;
         if (EZ) {
             const cf ex = p.in[o], ey = p.in[NN + o];
@@ -173,11 +176,11 @@ template <int L, bool EZ> struct XlRsRowsFwdOp : XlOpBase {
         for (int l = 0; l < XL_V; ++l) v[l * stride] = load1(yb + l, i);
     }
     XL_DEV void spec(int beta, const cf* v) const {
-        cf* base = p.spec + (size_t)f * L * p.N;
+        cf* base = p.spec + (size_t)f * L * p.rows;
 #pragma unroll
         for (int q = 0; q < 16; ++q) {
             const int g = q * (L / 16) + beta;
-            xl_blocked_store2(base + (size_t)(g / 2) * p.N * 2, yb, p.N, g, v[q], v[16 + q]);
+            xl_blocked_store2(base + (size_t)(g / 2) * p.rows * 2, yb, p.rows, g, v[q], v[16 + q]);
         }
     }
     XL_DEV void store_vec(int, const cf*) const {}
@@ -231,13 +234,20 @@ template <int L> struct XlHRow {
 };
 
 // K2: column FFT of the row spectra, x transfer function, inverse column FFT, keep rows [0,N).   wave_optics.py:288
-template <int L> struct XlRsColsOp : XlOpBase {
+// SLAB: the tile of a column pair is not contiguous but arrives from the all-to-all as [source rank][pair][chunk_rows][2]
+// (row i lives in chunk i / chunk_rows); chunk_stride = pairs_per_rank * chunk_rows * 2 elements.
+template <int L, bool SLAB = false> struct XlRsColsOp : XlOpBase {
     static constexpr bool kInLoHalf = true, kOutLoHalf = true;
     static constexpr int R1 = xl_first_radix(L), S1 = L / R1;
     const XlRsParams& p; cf* tile; const cf* H0; const cf* H1;   // transfer-function columns of the two lines (stride 2)
     int hmode;   // 0: H0,H1 are the two halves of one 16-byte pair (H1 == H0+1); 1: swapped pair (H0 == H1+1); 2: unrelated
+    size_t chunk_stride;
+    XL_DEV cf* row(int i) const {
+        if (!SLAB) return tile + (size_t)i * XL_V;
+        return tile + (size_t)(i / p.chunk_rows) * chunk_stride + (size_t)(i % p.chunk_rows) * XL_V;
+    }
     XL_DEV void load(int i, cf* v, int stride) const {
-        if (i < p.N) xl_ld4(tile + (size_t)i * XL_V, v, v + stride);
+        if (i < p.N) xl_ld4(row(i), v, v + stride);
         else { v[0] = cf_zero(); v[stride] = cf_zero(); }
     }
     XL_DEV void spec(int beta, cf* v) const {
@@ -264,7 +274,7 @@ template <int L> struct XlRsColsOp : XlOpBase {
 #pragma unroll
         for (int j = 0; j < R1 / 2; ++j) {
             const int i = n + S1 * j;
-            if (i < p.N) xl_st4(tile + (size_t)i * XL_V, v[j], v[R1 + j]);
+            if (i < p.N) xl_st4(row(i), v[j], v[R1 + j]);
         }
     }
 };
@@ -290,7 +300,24 @@ template <int L> struct XlRsCols {
                     if (hmode == 2) xl_prefetch_l2(H1 + (size_t)(q * (L / 16) + beta) * XL_V);
                 }
         }
-        XlRsColsOp<L> op{{}, p, p.spec + (size_t)f * L * p.N + (size_t)G * p.N * XL_V, H0, H1, hmode};
+        XlRsColsOp<L> op{{}, p, p.spec + (size_t)f * L * p.N + (size_t)G * p.N * XL_V, H0, H1, hmode, 0};
+        XlFft<L, XL_V>::conv(s, t, op);
+    }
+};
+// K2 of the slab-decomposed path: this rank owns gridDim.x slot pairs; its transfer-function slab H is [pairs][L][2]
+// (generated for exactly these columns, so no x-mirroring), its spectra arrive as [source rank][pairs][chunk_rows][2].
+template <int L> struct XlRsColsSlab {
+    static const char* name() { return "rs_cols_slab"; }
+    typedef XlRsParams Params;
+    static constexpr int NT = xl_threads(L);
+    static size_t smem() { return xl_smem_bytes(L, XL_V); }
+    XL_DEV static void run(const Params& p, cf* s) {
+        cf* t = s + xl_tile_elems(L, XL_V);
+        XlFft<L, XL_V>::init_tw(t, p.tw);
+        const int G = XL_BLOCK_X;
+        const cf* H0 = p.H + (size_t)G * L * XL_V;
+        XlRsColsOp<L, true> op{{}, p, p.spec + (size_t)G * p.chunk_rows * XL_V, H0, H0 + 1, 0,
+                               (size_t)p.nfields * p.chunk_rows * XL_V};   // nfields carries pairs-per-rank here
         XlFft<L, XL_V>::conv(s, t, op);
     }
 };
@@ -302,25 +329,25 @@ template <int L> struct XlRsRowsInvOp : XlOpBase {
     const XlRsParams& p; int f, yb;
     XL_DEV void load(int, cf*, int) const {}
     XL_DEV void spec(int beta, cf* v) const {
-        const cf* base = p.spec + (size_t)f * L * p.N;
+        const cf* base = p.spec + (size_t)f * L * p.rows;
 #pragma unroll
         for (int q = 0; q < 16; ++q) {
             const int g = q * (L / 16) + beta;
-            xl_blocked_load2(base + (size_t)(g / 2) * p.N * 2, yb, p.N, g, v + q, v + 16 + q);
+            xl_blocked_load2(base + (size_t)(g / 2) * p.rows * 2, yb, p.rows, g, v + q, v + 16 + q);
         }
     }
     XL_DEV void store_vec(int n, const cf* v) const {
 #pragma unroll
         for (int l = 0; l < XL_V; ++l) {
             const int y = yb + l;
-            if (y >= p.N) continue;
+            if (y >= p.rows) continue;
 #pragma unroll
             for (int j = 0; j < R1 / 2; ++j) {
                 const int i = n + S1 * j;
                 if (i >= p.N) continue;
                 cf val = v[l * R1 + j];
                 if (p.flags & XL_F_CONJ_OUT) val = cf_conj(val);
-                p.out[(size_t)f * p.N * p.N + (size_t)y * p.N + i] = val;
+                p.out[(size_t)f * p.rows * p.N + (size_t)y * p.N + i] = val;
             }
         }
     }
@@ -343,16 +370,19 @@ template <int L> struct XlRsRowsInv {
 // h is even in x: each sample x in [0, L/2] is evaluated once into a staging buffer and read back mirrored.
 template <int L> struct XlHRowsOp : XlOpBase {
     const XlRsParams& p; int yb; const cf* stage;   // stage[(L/2+1)][XL_V]
+    int nvalid;   // local rows that exist (global row <= L/2)
     XL_DEV void load(int i, cf* v, int stride) const {
         const int xi = i <= L / 2 ? i : L - i;
         xl_ld4(stage + (size_t)xi * XL_V, v, v + stride);
     }
     XL_DEV void spec(int beta, const cf* v) const {
 #pragma unroll
-        for (int q = 0; q <= 8; ++q) {   // x-bins <= L/2 only (q is the top digit of the bin); the rest is mirrored
+        for (int q = 0; q < 16; ++q) {
+            // single GPU: x-bins <= L/2 only (q is the top digit of the bin; of q = 8 only the pair holding bin L/2), the
+            // rest is mirrored.  slab: every slot pair, rows in a [pair][rows][2] buffer of this rank's y rows.
             const int g = q * (L / 16) + beta;
-            if (q == 8 && beta >= 2) continue;   // of the q = 8 slots only the pair holding bin L/2 is needed
-            xl_blocked_store2(p.H + (size_t)(g / 2) * L * 2, yb, L / 2 + 1, g, v[q], v[16 + q]);
+            if (!p.hstore_all && (q > 8 || (q == 8 && beta >= 2))) continue;
+            xl_blocked_store2(p.H + (size_t)(g / 2) * p.rows * 2, yb, nvalid, g, v[q], v[16 + q]);
         }
     }
     XL_DEV void store_vec(int, const cf*) const {}
@@ -371,12 +401,14 @@ template <int L> struct XlHRows {
         const int deriv = (p.flags & XL_F_DERIV) ? 1 : 0;
         XL_THREADS(tid, NT) {
             for (int e = tid; e < (L / 2 + 1) * XL_V; e += NT) {
-                const int xi = e / XL_V, l = e % XL_V, yi = yb + l;
+                const int xi = e / XL_V, l = e % XL_V, yi = p.hrow0 + yb + l;   // global y row
                 stage[e] = yi <= L / 2 ? xl_rs_h(xi * p.dx, yi * p.dy, hc, deriv) : cf_zero();
             }
         }
         XlFft<L, XL_V>::init_tw(t, p.tw);   // ends with a barrier: stage[] is visible
-        XlHRowsOp<L> op{{}, p, yb, stage};
+        int nvalid = L / 2 + 1 - p.hrow0;
+        if (nvalid > p.rows) nvalid = p.rows;
+        XlHRowsOp<L> op{{}, p, yb, stage, nvalid};
         XlFft<L, XL_V>::forward(s, t, op);
     }
 };
@@ -396,6 +428,37 @@ template <int L> struct XlHColsOp : XlOpBase {
         }
     }
     XL_DEV void store_vec(int, const cf*) const {}
+};
+// K2h of the slab path: rows arrive as [source rank][pairs][chunk_rows][2] (chunk_rows y rows per rank), the result goes
+// to this rank's transfer-function slab [pairs][L][2].
+template <int L> struct XlHColsSlabOp : XlOpBase {
+    const XlRsParams& p; const cf* src; cf* Ht; size_t chunk_stride;
+    XL_DEV void load(int i, cf* v, int stride) const {
+        const int r = i <= L / 2 ? i : L - i;
+        xl_ld4(src + (size_t)(r / p.chunk_rows) * chunk_stride + (size_t)(r % p.chunk_rows) * XL_V, v, v + stride);
+    }
+    XL_DEV void spec(int beta, const cf* v) const {
+#pragma unroll
+        for (int q = 0; q <= 8; ++q) {
+            if (q == 8 && beta != 0) continue;
+            xl_st4(Ht + (size_t)(q * (L / 16) + beta) * XL_V, cf_scale(v[q], p.hscale), cf_scale(v[16 + q], p.hscale));
+        }
+    }
+    XL_DEV void store_vec(int, const cf*) const {}
+};
+template <int L> struct XlHColsSlab {
+    static const char* name() { return "h_cols_slab"; }
+    typedef XlRsParams Params;
+    static constexpr int NT = xl_threads(L);
+    static size_t smem() { return xl_smem_bytes(L, XL_V); }
+    XL_DEV static void run(const Params& p, cf* s) {
+        cf* t = s + xl_tile_elems(L, XL_V);
+        XlFft<L, XL_V>::init_tw(t, p.tw);
+        const int G = XL_BLOCK_X;
+        XlHColsSlabOp<L> op{{}, p, p.spec + (size_t)G * p.chunk_rows * XL_V, p.H + (size_t)G * L * XL_V,
+                            (size_t)p.nfields * p.chunk_rows * XL_V};
+        XlFft<L, XL_V>::forward(s, t, op);
+    }
 };
 template <int L> struct XlHCols {
     static const char* name() { return "h_cols"; }

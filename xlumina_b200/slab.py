@@ -1,0 +1,114 @@
+"""
+Slab-decomposed scalar RS propagation of ONE N x N field over the G GPUs of a box (BASELINE.json cfg 5).
+
+Rank g owns field rows [g N/G, (g+1) N/G).  The 2-D FFT convolution of xlumina/wave_optics.py:281-297 becomes
+    row FFTs of the local rows  ->  ALL-TO-ALL  ->  column convolution on this rank's (L/2)/G slot pairs  ->  ALL-TO-ALL
+    ->  inverse row FFTs of the local rows
+and the transfer function is built the same way (local y rows of the analytic impulse response -> all-to-all -> column FFTs
+of this rank's slot pairs), so no rank ever holds a full padded plane.  The stages are the C-ABI entry points
+`xl_slab_*` (include/xlprop.h); the exchanges are `torch.distributed.all_to_all_single` (NCCL over NVLink/NVSwitch on GPUs;
+gloo in the CPU tests, which drive the host-emulated kernel bodies through the same code).
+
+The exchanged layouts are chosen so that every peer's chunk is contiguous on both sides and the second exchange is the
+exact inverse of the first: row side [L/2 pairs][rows][2], column side [source rank][(L/2)/G pairs][rows][2].
+
+Round-1 limits: padded length <= 4096 (N <= 2048: the long-line FFT that 16384^2 needs is not built yet), scalar fields,
+forward and field-VJP (the operator is complex-symmetric: `rs_slab_vjp`); d/dz is single-GPU only.
+"""
+import ctypes
+
+import torch
+import torch.distributed as dist
+
+from . import _lib
+
+__all__ = ["rs_propagation_slab", "rs_slab_vjp", "SlabPlan"]
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _stream_of(t):
+    return ctypes.c_void_p(torch.cuda.current_stream(t.device).cuda_stream) if t.is_cuda else None
+
+
+class SlabPlan:
+    """Geometry of one slab decomposition (all sizes in complex64 elements)."""
+
+    def __init__(self, N, world, lib):
+        self.N, self.G = int(N), int(world)
+        self.L = lib.xl_rs_padded_length(self.N)
+        if not self.L:
+            raise _lib.XlpropError(f"slab RS: N={N} unsupported in this version (padded length must be <= 4096)")
+        if self.N % (2 * self.G) or (self.L // 2) % self.G:
+            raise _lib.XlpropError(f"slab RS: N={N} must be a multiple of 2*G and L/2={self.L // 2} a multiple of G={world}")
+        self.rows = self.N // self.G                    # field rows per rank
+        self.pairs = (self.L // 2) // self.G            # x-slot pairs per rank
+        self.hrows = lib.xl_slab_h_rows_per_rank(self.N, self.G)
+        self.spec_elems = (self.L // 2) * self.rows * 2
+        self.hspec_elems = (self.L // 2) * self.hrows * 2
+        self.hloc_elems = self.pairs * self.L * 2
+
+
+def _all_to_all(buf, group):
+    """Equal-split all-to-all of a complex64 buffer whose G peer chunks are contiguous; returns the received buffer."""
+    out = torch.empty_like(buf)
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_to_all_single(torch.view_as_real(out).reshape(-1), torch.view_as_real(buf).reshape(-1), group=group)
+    else:
+        out.copy_(buf)
+    return out
+
+
+def _transfer_slab(plan, z, dx, dy, k, rank, ref, lib, group):
+    R = torch.empty(plan.hspec_elems, dtype=torch.complex64, device=ref.device)
+    _lib.check(lib.xl_slab_h_rows(_ptr(R), _ptr(z), plan.N, plan.G, rank, dx, dy, k, _stream_of(ref)), "xl_slab_h_rows")
+    Th = _all_to_all(R, group)
+    H = torch.empty(plan.hloc_elems, dtype=torch.complex64, device=ref.device)
+    _lib.check(lib.xl_slab_h_cols(_ptr(Th), _ptr(H), plan.N, plan.G, dx, dy, _stream_of(ref)), "xl_slab_h_cols")
+    return H
+
+
+def _apply(plan, field_local, H, flags, lib, group):
+    S = torch.empty(plan.spec_elems, dtype=torch.complex64, device=field_local.device)
+    st = _stream_of(field_local)
+    _lib.check(lib.xl_slab_rows_fwd(_ptr(field_local), _ptr(S), plan.N, plan.G, flags, st), "xl_slab_rows_fwd")
+    T = _all_to_all(S, group)
+    _lib.check(lib.xl_slab_cols(_ptr(T), _ptr(H), plan.N, plan.G, st), "xl_slab_cols")
+    S2 = _all_to_all(T, group)
+    out = torch.empty_like(field_local)
+    _lib.check(lib.xl_slab_rows_inv(_ptr(S2), _ptr(out), plan.N, plan.G, flags, st), "xl_slab_rows_inv")
+    return out
+
+
+def rs_propagation_slab(field_local, z, dx, dy, k, group=None, lib=None, transfer=None, return_transfer=False):
+    """Propagate the row slab `field_local` (N/G, N) complex64 of an N x N field by z; every rank of `group` calls this with
+    its own slab and the same z, dx, dy, k.  Returns this rank's rows of the result (and the transfer-function slab when
+    `return_transfer`, to be passed back as `transfer` for another field or the VJP at the same z)."""
+    lib = lib or _lib.lib()
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    if lib is _lib._lib and not field_local.is_cuda:
+        raise _lib.XlpropError("xlumina_b200 operators need CUDA tensors (no CPU fallback)")
+    f = field_local.to(torch.complex64).contiguous()
+    N = f.shape[-1]
+    plan = SlabPlan(N, world, lib)
+    if f.shape != (plan.rows, N):
+        raise ValueError(f"slab RS: this rank's slab must be ({plan.rows}, {N}), got {tuple(f.shape)}")
+    if transfer is None:
+        zt = z if isinstance(z, torch.Tensor) else torch.full((1,), float(z), dtype=torch.float64, device=f.device)
+        zt = zt.to(device=f.device, dtype=torch.float64).reshape(1)
+        transfer = _transfer_slab(plan, zt, float(dx), float(dy), float(k), rank, f, lib, group)
+    out = _apply(plan, f, transfer, 0, lib, group)
+    return (out, transfer) if return_transfer else out
+
+
+def rs_slab_vjp(ct_local, transfer, group=None, lib=None):
+    """Field VJP (JAX convention: plain transpose) of rs_propagation_slab at the same z: the operator is complex-symmetric,
+    so it is the forward chain on the cotangent slab with the saved transfer-function slab."""
+    lib = lib or _lib.lib()
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    c = ct_local.to(torch.complex64).contiguous()
+    plan = SlabPlan(c.shape[-1], world, lib)
+    return _apply(plan, c, transfer, 0, lib, group)
