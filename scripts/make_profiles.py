@@ -51,12 +51,13 @@ want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio", "smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio", "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio"]
 traffic = {}
-for name in ("rsgrad", "cztgrad"):
+for name in ("rsgrad", "k4", "cztgrad"):
     fn = os.path.join(G, f"ncu_{tag}_{name}_raw.csv")
     if not os.path.exists(fn): continue
     rows = list(csv.reader(open(fn)))
     hdr, units = rows[0], rows[1]
-    out.append(f"## ncu --set full --clock-control none, scripts/prof_rs.py 2048 {name.replace('rsgrad', 'grad')} (2nd iteration; one row per launch)")
+    mode = {"rsgrad": "grad", "k4": "grad (the d/dz column kernel and the inverse row kernel that follows it)"}.get(name, name)
+    out.append(f"## ncu --set full --clock-control none, scripts/prof_rs.py 2048 {mode} (2nd iteration; one row per launch)")
     short = [w.replace("smsp__average_warps_issue_stalled_", "stall_").replace("_per_issue_active.ratio", "").replace(".avg.pct_of_peak_sustained_active", "%").replace(".avg.pct_of_peak_sustained_elapsed", "%el") for w in want]
     for r_ in rows[2:]:
         kn = r_[hdr.index("Kernel Name")].replace("void xl_kernel<", "").replace(">(Params)", "")

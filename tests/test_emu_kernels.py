@@ -72,6 +72,19 @@ def test_rs_reference_test_config(emu):
     assert rel_l2(out, g["rs_out"]) < TIGHT
 
 
+@pytest.mark.parametrize("N", [300, 600, 1100])
+def test_rs_large_padded_lengths(emu, N):
+    """Padded lengths 1024, 2048 and 4096 (first radix 4, 8 and 16): pins the radix plans, the slot <-> bin maps behind the
+    x/y-mirrored transfer function and the pruned passes of the production sizes on the CPU.  Checked on a band of rows."""
+    rng = np.random.default_rng(N)
+    x = np.linspace(-3000, 3000, N)
+    f = np.zeros((N, N), np.complex128)
+    f[N // 3:N // 3 + 40, :] = rng.standard_normal((40, N)) + 1j * rng.standard_normal((40, N))
+    ref, _ = o.RS_propagation(f, x, x, 0.6328, 40000.0)
+    out, *_ = rs_fwd(emu, f, x, x, 0.6328, 40000.0)
+    assert rel_l2(out, ref) < TIGHT
+
+
 @pytest.mark.parametrize("N", [9, 17, 50, 100])
 def test_rs_non_power_of_two_sizes(emu, N):
     rng = np.random.default_rng(N)
@@ -124,6 +137,70 @@ def test_czt_forward_and_vjp_golden(emu, name):
         gin = np.zeros(g["field"].shape, np.complex64)
         czt_call(emu, emu.xl_czt_bwd, c64(g["ct"]), gin, g, 0)
         assert rel_l2(gin, g["vjp_field"]) < TIGHT
+
+
+@pytest.mark.parametrize("N,M", [(520, 300), (1100, 1100)])
+def test_czt_large_padded_lengths(emu, N, M):
+    """Bluestein lengths 1024 and 4096: the paired + pruned kernel variants and the rotated forward kernel table at
+    production sizes, forward and adjoint, against the oracle (adjoint through the dot-product identity)."""
+    rng = np.random.default_rng(N + M)
+    x = np.linspace(-1500, 1500, N)
+    xo = np.linspace(-400, 400, M)
+    f = np.zeros((N, N), np.complex128)
+    f[N // 2 - 8:N // 2 + 8, :] = rng.standard_normal((16, N)) + 1j * rng.standard_normal((16, N))
+    g = dict(x=x, y=x, xout=xo, yout=xo, z=30000.0, wavelength=0.6328)
+    ref = o.CZT(f, x, x, 0.6328, 30000.0, xo, xo)
+    out = np.zeros((M, M), np.complex64)
+    czt_call(emu, emu.xl_czt_fwd, c64(f), out, g, 0)
+    assert rel_l2(out, ref) < TIGHT
+    ct = np.zeros((M, M), np.complex64)
+    ct[M // 2 - 4:M // 2 + 4, :] = (rng.standard_normal((8, M)) + 1j * rng.standard_normal((8, M))).astype(np.complex64)
+    gin = np.zeros((N, N), np.complex64)
+    czt_call(emu, emu.xl_czt_bwd, ct, gin, g, 0)
+    lhs = np.sum(ct.astype(np.complex128) * ref)            # <ct, K f> = <K^T ct, f>   (no conjugation: JAX convention)
+    rhs = np.sum(gin.astype(np.complex128) * f)
+    assert abs(lhs - rhs) < 2e-5 * abs(lhs)
+
+
+@pytest.mark.parametrize("N,Mx,My", [(25, 31, 31), (27, 20, 33), (30, 45, 21), (22, 9, 9), (40, 70, 64)])
+def test_czt_odd_and_unequal_sizes_generic_variants(emu, N, Mx, My):
+    """Odd sizes break the 16-byte pairing, M > L/2 breaks the output pruning: these take the generic kernel variants (8-byte
+    accesses, run-time pruning).  Forward against the oracle, adjoint through the dot-product identity."""
+    if emu.xl_czt_padded_length(N, Mx) == 0 or emu.xl_czt_padded_length(N, My) == 0:
+        pytest.skip("m+M-1 is a power of two: the reference raises too")
+    rng = np.random.default_rng(N * 1000 + Mx * 10 + My)
+    x = np.linspace(-500, 500, N)
+    xo, yo = np.linspace(-150, 150, Mx), np.linspace(-100, 120, My)
+    f = rng.standard_normal((N, N)) + 1j * rng.standard_normal((N, N))
+    g = dict(x=x, y=x, xout=xo, yout=yo, z=9000.0, wavelength=0.6328)
+    ref = o.CZT(f, x, x, 0.6328, 9000.0, xo, yo)
+    out = np.zeros((My, Mx), np.complex64)
+    czt_call(emu, emu.xl_czt_fwd, c64(f), out, g, 0)
+    assert rel_l2(out, ref) < TIGHT
+    ct = c64(rng.standard_normal((My, Mx)) + 1j * rng.standard_normal((My, Mx)))
+    gin = np.zeros((N, N), np.complex64)
+    czt_call(emu, emu.xl_czt_bwd, ct, gin, g, 0)
+    lhs, rhs = np.sum(ct.astype(np.complex128) * ref), np.sum(gin.astype(np.complex128) * f)
+    assert abs(lhs - rhs) < 2e-5 * abs(lhs)
+
+
+def test_vczt_and_highna_odd_output_sizes(emu):
+    rng = np.random.default_rng(77)
+    N, Mx, My = 26, 15, 19
+    x = np.linspace(-400, 400, N)
+    xo, yo = np.linspace(-8, 8, Mx), np.linspace(-6, 7, My)
+    ex = rng.standard_normal((N, N)) + 1j * rng.standard_normal((N, N))
+    ey = rng.standard_normal((N, N)) + 1j * rng.standard_normal((N, N))
+    exy = c64(np.stack([ex, ey]))
+    g = dict(x=x, y=x, xout=xo, yout=yo, z=7000.0, wavelength=0.6328)
+    out = np.zeros((3, My, Mx), np.complex64)
+    czt_call(emu, emu.xl_czt_fwd, exy, out, g, 1)
+    assert rel_l2(out, o.VCZT(ex, ey, x, x, 0.6328, 7000.0, xo, yo)) < TIGHT
+    ws = np.zeros(emu.xl_highna_workspace_bytes(N, Mx, My), np.uint8)
+    out2 = np.zeros((3, My, Mx), np.complex64)
+    assert emu.xl_highna_fwd(ptr(exy), ptr(out2), N, Mx, My, 350.0, 500.0, 0.635, x[0], x[1] - x[0], x[0], x[1] - x[0],
+                             xo[0], xo[-1], yo[0], yo[-1], 0, ptr(ws), ws.size, None) == 0
+    assert rel_l2(out2, o.VCZT_objective_lens(ex, ey, x, x, 0.635, 350.0, 500.0, xo, yo)) < TIGHT
 
 
 def test_czt_reference_test_config(emu):

@@ -52,6 +52,25 @@ XL_HD constexpr int xl_bin_to_slot(int L, int k) {
     while (P * 16 < L) { P *= 16; slot += (k % 16) * (L / (16 * P)); k /= 16; }
     return slot + k * (L / 16);
 }
+// The same maps with L as a template constant: every divisor is a compile-time power of two (shifts and masks in SASS; the
+// run-time-L versions above cost real integer divisions when a kernel evaluates them per thread).
+template <int L> XL_DEV int xl_slot_to_bin_t(int s) {
+    constexpr int NB = L / 16, R1 = xl_first_radix(L), W1 = NB / R1;   // W1 = 16^(number of middle passes)
+    static_assert(W1 == 1 || W1 == 16 || W1 == 256, "radix plan deeper than L = 4096 * 16");
+    const int qm = s / NB, beta = s % NB, q1 = beta / W1, rem = beta % W1;
+    int k = qm * NB + q1;
+    if (W1 == 16) k += rem * R1;
+    if (W1 == 256) k += (rem / 16) * R1 + (rem % 16) * R1 * 16;
+    return k;
+}
+template <int L> XL_DEV int xl_bin_to_slot_t(int k) {
+    constexpr int NB = L / 16, R1 = xl_first_radix(L), W1 = NB / R1;
+    const int qm = k / NB, low = k % NB, q1 = low % R1, rest = low / R1;   // rest: the middle digits, least significant first
+    int beta = q1 * W1;
+    if (W1 == 16) beta += rest;
+    if (W1 == 256) beta += (rest % 16) * 16 + rest / 16;
+    return qm * NB + beta;
+}
 XL_HD constexpr int xl_slot_to_bin(int L, int s) {
     int P = xl_first_radix(L);
     int k = s / (L / 16) * (L / 16);          // q_m * (r_1 ... r_{m-1}) == q_m * L/16

@@ -209,12 +209,12 @@ template <int L> struct XlRsRowsFwd {
 // kx <= L/2 are ever computed (h_cols) and the column of bin kx > L/2 is read from its mirror L - kx.
 // Returns the address of element [slot_y = 0] of the column that serves x-slot g; consecutive slot_y are 2 cf apart.
 template <int L> XL_DEV const cf* xl_h_column(const cf* H, int g) {
-    const int k = xl_slot_to_bin(L, g);
-    const int sc = xl_bin_to_slot(L, k <= L / 2 ? k : L - k);
+    const int k = xl_slot_to_bin_t<L>(g);
+    const int sc = xl_bin_to_slot_t<L>(k <= L / 2 ? k : L - k);
     return H + (size_t)(sc / 2) * L * 2 + (sc & 1);
 }
 template <int L> XL_DEV bool xl_h_pair_needed(int G) {   // does slot pair G hold a column with bin <= L/2 ?
-    return xl_slot_to_bin(L, 2 * G) <= L / 2 || xl_slot_to_bin(L, 2 * G + 1) <= L / 2;
+    return xl_slot_to_bin_t<L>(2 * G) <= L / 2 || xl_slot_to_bin_t<L>(2 * G + 1) <= L / 2;
 }
 
 // Row (slot_y) of the stored half of the transfer function that serves slot q*(L/16)+beta: the slot itself when its
@@ -223,8 +223,8 @@ template <int L> XL_DEV bool xl_h_pair_needed(int G) {   // does slot pair G hol
 template <int L> struct XlHRow {
     int beta, bm;
     XL_DEV explicit XlHRow(int b) : beta(b), bm(0) {
-        const int klow = xl_slot_to_bin(L, b);
-        if (klow) bm = xl_bin_to_slot(L, L / 16 - klow);
+        const int klow = xl_slot_to_bin_t<L>(b);
+        if (klow) bm = xl_bin_to_slot_t<L>(L / 16 - klow);
     }
     XL_DEV int row(int q) const {
         if (q < 8) return q * (L / 16) + beta;
