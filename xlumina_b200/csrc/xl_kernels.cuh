@@ -7,7 +7,9 @@
 //   field            [f][y][x]                     row-major N x N planes (the reference's [..., y, x])
 //   row spectra  S   [f][L/2][N][2]                "blocked": 2 adjacent x-slots innermost, so a column-pair CTA reads one
 //                                                   contiguous 16*N-byte tile and a row-pair CTA fills whole 32-byte sectors
-//   transfer fn  H   [L/2][L][2]                   same blocking, y in slot order, premultiplied by dx*dy/L^2
+//   transfer fn  H   [L/2][L][2]                   same blocking, y in slot order, premultiplied by dx*dy/L^2; h is even in x
+//                                                   and y, so only the slot pairs holding an x-bin <= L/2 and, inside them, the
+//                                                   slots of y-bins <= L/2 (= slots 0..L/2) are ever written or read
 //   L = padded length (power of two >= 2N-1); slot order = XlFft's digit permutation (never undone).
 #pragma once
 #include "xl_fft.cuh"
@@ -20,7 +22,6 @@
 #define XL_F_VRS 4        // 3 fields, field 2 = Ez formed from (Ex,Ey) at load      (vectorized_optics.py:258-261)
 #define XL_F_DERIV 8      // transfer function of dh/dz instead of h
 
-XL_DEV cf xl_ld2(const cf* p) { return *p; }
 XL_DEV void xl_ld4(const cf* p, cf* a, cf* b) {   // two adjacent complex values with one 16-byte load (p 16-byte aligned)
     const float4 t = *reinterpret_cast<const float4*>(p);
     *a = make_float2(t.x, t.y);

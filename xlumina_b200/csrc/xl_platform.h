@@ -22,7 +22,6 @@ static inline float2 __fadd2_rn(float2 a, float2 b) { return make_float2(a.x + b
 static inline float2 __fmul2_rn(float2 a, float2 b) { return make_float2(a.x * b.x, a.y * b.y); }
 static inline float2 __ffma2_rn(float2 a, float2 b, float2 c) { return make_float2(a.x * b.x + c.x, a.y * b.y + c.y); }
 #define XL_DEV inline
-#define XL_NOINLINE inline
 #define XL_HD
 #define XL_DEVFN static inline
 #define XL_RESTRICT
@@ -45,7 +44,6 @@ static inline void xl_prefetch_l2(const void*) {}
 #else
 #include <cuda_runtime.h>
 #define XL_DEV __device__ __forceinline__
-#define XL_NOINLINE __device__ __noinline__
 #define XL_HD __host__ __device__
 #define XL_DEVFN __device__
 #define XL_RESTRICT __restrict__
