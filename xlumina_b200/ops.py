@@ -17,7 +17,7 @@ import torch
 
 from . import _lib
 
-__all__ = ["rs_propagation", "vrs_propagation", "czt", "vczt", "highna_focus", "rs_transfer"]
+__all__ = ["rs_propagation", "vrs_propagation", "czt", "vczt", "highna_focus", "rs_transfer", "set_transfer_cache"]
 
 
 # ---------------------------------------------------------------------------------------------- plumbing
@@ -105,20 +105,60 @@ def _grid(coords):
     return res
 
 
+# ---------------------------------------------------------------------------------------------- transfer-function cache
+# Optical tables propagate several beams over the SAME distance inside one loss evaluation (the reference's
+# hybrid_setup_sharp_focus uses z1_1 + z1_2 three times, optical_elements.py:1609,1622; the 6x6 ansatz uses each of
+# z8..z12 six times): SURVEY.md 8f-3.  With the cache on, calls that pass the same z OBJECT (same tensor, unmodified, or
+# the same Python float) on the same grid reuse one transfer function instead of regenerating it (XL_REUSE_H).
+# Off by default: every entry pins xl_rs_transfer_bytes(N) of device memory (128 MiB at N = 2048).
+import collections
+
+_transfer_cache = collections.OrderedDict()
+_transfer_cache_size = 0
+
+
+def set_transfer_cache(entries):
+    """Keep the transfer functions of the last `entries` distinct (z, grid) combinations; 0 disables and frees the cache."""
+    global _transfer_cache_size
+    _transfer_cache_size = max(0, int(entries))
+    while len(_transfer_cache) > _transfer_cache_size:
+        _transfer_cache.popitem(last=False)
+
+
+def _z_key(z):
+    return ("t", id(z), z._version) if isinstance(z, torch.Tensor) else ("f", float(z))
+
+
+def _cached_transfer(zkey, zobj, N, dx, dy, k, device, nbytes):
+    """(H, reuse): H is a device buffer for the transfer function, reuse says whether it already holds it."""
+    if _transfer_cache_size == 0 or zkey is None:
+        return torch.empty(nbytes, dtype=torch.uint8, device=device), False
+    key = (zkey, N, dx, dy, k, device, torch.cuda.current_stream(device).cuda_stream)
+    hit = _transfer_cache.get(key)
+    if hit is not None:
+        _transfer_cache.move_to_end(key)
+        return hit[1], True
+    H = torch.empty(nbytes, dtype=torch.uint8, device=device)
+    _transfer_cache[key] = (zobj, H)          # zobj is kept alive so that id(z) cannot be recycled while the entry lives
+    while len(_transfer_cache) > _transfer_cache_size:
+        _transfer_cache.popitem(last=False)
+    return H, False
+
+
 # ---------------------------------------------------------------------------------------------- RS / VRS
 class _RS(torch.autograd.Function):
     """field (F,N,N) c64, z (1,) f64 -> (F,N,N).  backward = same complex-symmetric operator + Parseval d/dz."""
 
     @staticmethod
-    def forward(ctx, field, z, dx, dy, k):
+    def forward(ctx, field, z, dx, dy, k, zkey=None, zobj=None):
         _require_device(field)
         L = _lib.lib()
         F, N = field.shape[0], field.shape[-1]
         out = torch.empty_like(field)
-        H = torch.empty(L.xl_rs_transfer_bytes(N), dtype=torch.uint8, device=field.device)
+        H, reuse = _cached_transfer(zkey, zobj, N, dx, dy, k, field.device, L.xl_rs_transfer_bytes(N))
         need = L.xl_rs_workspace_bytes(N, F, 0)
         ws = _workspace(field, need)
-        _lib.check(L.xl_rs_fwd(_ptr(field), _ptr(out), _ptr(H), _ptr(z), N, F, dx, dy, k, 0,
+        _lib.check(L.xl_rs_fwd(_ptr(field), _ptr(out), _ptr(H), _ptr(z), N, F, dx, dy, k, _lib.XL_REUSE_H if reuse else 0,
                                _ptr(ws), ws.numel(), _stream(field)), "xl_rs_fwd")
         ctx.save_for_backward(field, z, H, out)      # out: the exact i*k*out part of d out/dz (include/xlprop.h)
         ctx.geom = (dx, dy, k)
@@ -138,21 +178,21 @@ class _RS(torch.autograd.Function):
         ws = _workspace(field, need)
         _lib.check(L.xl_rs_bwd(_ptr(field), _ptr(out), _ptr(g), _ptr(gin), _ptr(gz), _ptr(H), _ptr(z), N, F, dx, dy, k,
                                _lib.XL_CONJ_IN | _lib.XL_CONJ_OUT, _ptr(ws), ws.numel(), _stream(field)), "xl_rs_bwd")
-        return gin, gz, None, None, None
+        return gin, gz, None, None, None, None, None
 
 
 class _VRS(torch.autograd.Function):
     """exy (2,N,N) -> (3,N,N); Ez = (Ex X + Ey Y)/r formed at load (vectorized_optics.py:258-261)."""
 
     @staticmethod
-    def forward(ctx, exy, z, x0, y0, dx, dy, k):
+    def forward(ctx, exy, z, x0, y0, dx, dy, k, zkey=None, zobj=None):
         _require_device(exy)
         L = _lib.lib()
         N = exy.shape[-1]
         out = torch.empty((3, N, N), dtype=exy.dtype, device=exy.device)
-        H = torch.empty(L.xl_rs_transfer_bytes(N), dtype=torch.uint8, device=exy.device)
+        H, reuse = _cached_transfer(zkey, zobj, N, dx, dy, k, exy.device, L.xl_rs_transfer_bytes(N))
         ws = _workspace(exy, L.xl_rs_workspace_bytes(N, 3, 0))
-        _lib.check(L.xl_vrs_fwd(_ptr(exy), _ptr(out), _ptr(H), _ptr(z), N, x0, y0, dx, dy, k, 0,
+        _lib.check(L.xl_vrs_fwd(_ptr(exy), _ptr(out), _ptr(H), _ptr(z), N, x0, y0, dx, dy, k, _lib.XL_REUSE_H if reuse else 0,
                                 _ptr(ws), ws.numel(), _stream(exy)), "xl_vrs_fwd")
         ctx.save_for_backward(exy, z, H, out)
         ctx.geom = (x0, y0, dx, dy, k)
@@ -171,7 +211,7 @@ class _VRS(torch.autograd.Function):
         ws = _workspace(exy, L.xl_rs_workspace_bytes(N, 3, 1 if want_z else 0))
         _lib.check(L.xl_vrs_bwd(_ptr(exy), _ptr(out), _ptr(g), _ptr(gin), _ptr(gz), _ptr(H), _ptr(z), N, x0, y0, dx, dy, k,
                                 _lib.XL_CONJ_IN | _lib.XL_CONJ_OUT, _ptr(ws), ws.numel(), _stream(exy)), "xl_vrs_bwd")
-        return gin, gz, None, None, None, None, None
+        return gin, gz, None, None, None, None, None, None, None
 
 
 def rs_propagation(field, z, dx, dy, k):
@@ -182,7 +222,7 @@ def rs_propagation(field, z, dx, dy, k):
         raise ValueError("RS propagation needs square fields")
     f = _c64(field).reshape(-1, N, N)
     zt = _as_z(z, f)
-    out = _RS.apply(f, zt, float(dx), float(dy), float(k)).reshape(field.shape)
+    out = _RS.apply(f, zt, float(dx), float(dy), float(k), _z_key(z) if _transfer_cache_size else None, z).reshape(field.shape)
     return out if dt == torch.complex64 or not torch.is_complex(field) else out.to(dt)
 
 
@@ -191,7 +231,8 @@ def vrs_propagation(Ex, Ey, z, x0, y0, dx, dy, k):
     dt = Ex.dtype
     exy = _c64(Ex) if Ey is None else torch.stack([_c64(Ex), _c64(Ey)], dim=0)
     zt = _as_z(z, exy)
-    out = _VRS.apply(exy, zt, float(x0), float(y0), float(dx), float(dy), float(k))
+    out = _VRS.apply(exy, zt, float(x0), float(y0), float(dx), float(dy), float(k),
+                     _z_key(z) if _transfer_cache_size else None, z)
     return out if dt == torch.complex64 or not torch.is_complex(Ex) else out.to(dt)
 
 
