@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define XLPROP_VERSION 101
+#define XLPROP_VERSION 102
 
 enum {
     XL_OK = 0,
@@ -103,12 +103,16 @@ int xl_vrs_bwd(const void* exy, const void* out, const void* ct_out, void* ct_ex
  * and the second all-to-all is the exact inverse.  The VJP with respect to the field is the same chain applied to the
  * cotangent (the operator is complex-symmetric); d/dz is single-GPU only in this version.
  * Replaces the same reference lines as xl_rs_fwd (wave_optics.py:281-297). */
+int xl_slab_padded_length(int N);            /* 2^ceil(log2(2N-1)) up to 32768 (N <= 16384); 0 if unsupported */
 int xl_slab_h_rows_per_rank(int N, int G);   /* rows of the y >= 0 half of the impulse response each rank transforms */
-int xl_slab_h_rows(void* R, const double* z, int N, int G, int rank, double dx, double dy, double k, void* stream);
+size_t xl_slab_scratch_bytes(int N, int G);  /* scratch of the split kernels (padded length > 4096); small otherwise */
+int xl_slab_h_rows(void* R, const double* z, int N, int G, int rank, double dx, double dy, double k, void* scratch, void* stream);
 int xl_slab_h_cols(const void* Th, void* Hloc, int N, int G, double dx, double dy, void* stream);
 int xl_slab_rows_fwd(const void* in_local, void* S, int N, int G, int flags, void* stream);
-int xl_slab_cols(void* T, const void* Hloc, int N, int G, void* stream);
-int xl_slab_rows_inv(const void* S, void* out_local, int N, int G, int flags, void* stream);
+int xl_slab_cols(void* T, const void* Hloc, int N, int G, void* scratch, void* stream);
+int xl_slab_rows_inv(const void* S, void* out_local, int N, int G, int flags, void* scratch, void* stream);
+/* Test hook: sub-line length of the split kernels (32 or 4096, default 4096), so that tests reach them at small N. */
+void xl_debug_set_max_line(int sub_line_length);
 
 /* ---------------------------------------------------------------- CZT / VCZT -------------------------------- */
 /* vectorial = 0: in (N,N) -> out (My,Mx)            CZT_jit,  wave_optics.py:333-357

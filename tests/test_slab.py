@@ -23,7 +23,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, emu_path, N, z, out_dir):
+def _worker(rank, world, port, emu_path, N, z, out_dir, max_line=4096):
     sys.path.insert(0, ROOT)
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -31,6 +31,7 @@ def _worker(rank, world, port, emu_path, N, z, out_dir):
     try:
         from xlumina_b200 import _lib, slab
         emu = _lib.declare(ctypes.CDLL(emu_path))
+        emu.xl_debug_set_max_line(max_line)
         rng = np.random.default_rng(7)
         field = (rng.standard_normal((N, N)) + 1j * rng.standard_normal((N, N))).astype(np.complex64)
         ct = (rng.standard_normal((N, N)) + 1j * rng.standard_normal((N, N))).astype(np.complex64)
@@ -64,11 +65,33 @@ def test_slab_rs_matches_oracle(emu, tmp_path, world, N, z):
     assert rel_l2(vgot, vref) < 5e-6
 
 
+@pytest.mark.parametrize("world,N,z", [(1, 32, 2500.0), (1, 128, 9000.0), (2, 64, -4000.0), (4, 128, 6000.0), (2, 24, 1500.0)])
+def test_slab_rs_split_lines_match_oracle(emu, tmp_path, world, N, z):
+    """The split-line kernels (csrc/xl_long.cuh: padded length = R x sub-line) with the sub-line length forced to 32, so that
+    R = 2, 4 and 8 are reached at N = 24..128: the same code path as 4096 < padded length <= 32768 in production."""
+    from conftest import rel_l2
+    from oracle import oracle_np as o
+    emu_path = os.path.join(ROOT, "tests", "emu", "libxlprop_emu.so")
+    mp.spawn(_worker, args=(world, _free_port(), emu_path, N, z, str(tmp_path), 32), nprocs=world, join=True)
+    rng = np.random.default_rng(7)
+    field = (rng.standard_normal((N, N)) + 1j * rng.standard_normal((N, N))).astype(np.complex64)
+    ct = (rng.standard_normal((N, N)) + 1j * rng.standard_normal((N, N))).astype(np.complex64)
+    x = np.linspace(-300.0, 300.0, N)
+    ref, _ = o.RS_propagation(field.astype(np.complex128), x, x, 0.6328, z)
+    got = np.concatenate([np.load(tmp_path / f"out{r}.npy") for r in range(world)])
+    assert rel_l2(got, ref) < 5e-6
+    vref, _ = o.RS_propagation(ct.astype(np.complex128), x, x, 0.6328, z)
+    vgot = np.concatenate([np.load(tmp_path / f"vjp{r}.npy") for r in range(world)])
+    assert rel_l2(vgot, vref) < 5e-6
+
+
 def test_slab_plan_rejects_bad_partitions(emu):
     from xlumina_b200 import slab, _lib
     with pytest.raises(_lib.XlpropError):
         slab.SlabPlan(30, 4, emu)          # 30 rows cannot be split into 4 slabs of whole row pairs
     with pytest.raises(_lib.XlpropError):
-        slab.SlabPlan(4096, 2, emu)        # padded length 8192: long-line FFT not built in this version
+        slab.SlabPlan(20000, 2, emu)       # padded length 65536 > 32768
     p = slab.SlabPlan(2048, 8, emu)
     assert (p.L, p.rows, p.pairs) == (4096, 256, 256) and p.hrows * 8 >= 2049 and p.hrows % 2 == 0
+    p = slab.SlabPlan(16384, 8, emu)       # BASELINE.json cfg 5
+    assert (p.L, p.rows, p.pairs) == (32768, 2048, 2048) and p.scratch_bytes == 2048 * 32768 * 2 * 8

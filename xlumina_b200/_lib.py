@@ -28,12 +28,15 @@ SIGNATURES = {
     "xl_rs_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _d, _d, _d, _i, _vp, _sz, _vp]),
     "xl_vrs_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _d, _d, _d, _d, _d, _i, _vp, _sz, _vp]),
     "xl_vrs_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _d, _d, _d, _d, _d, _i, _vp, _sz, _vp]),
+    "xl_slab_padded_length": (_i, [_i]),
     "xl_slab_h_rows_per_rank": (_i, [_i, _i]),
-    "xl_slab_h_rows": (_i, [_vp, _vp, _i, _i, _i, _d, _d, _d, _vp]),
+    "xl_slab_scratch_bytes": (_sz, [_i, _i]),
+    "xl_slab_h_rows": (_i, [_vp, _vp, _i, _i, _i, _d, _d, _d, _vp, _vp]),
     "xl_slab_h_cols": (_i, [_vp, _vp, _i, _i, _d, _d, _vp]),
     "xl_slab_rows_fwd": (_i, [_vp, _vp, _i, _i, _i, _vp]),
-    "xl_slab_cols": (_i, [_vp, _vp, _i, _i, _vp]),
-    "xl_slab_rows_inv": (_i, [_vp, _vp, _i, _i, _i, _vp]),
+    "xl_slab_cols": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
+    "xl_slab_rows_inv": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
+    "xl_debug_set_max_line": (None, [_i]),
     "xl_czt_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "xl_czt_fwd": (_i, [_vp, _vp, _vp, _d, _i, _i, _i, _i, _d, _d, _d, _d, _d, _d, _d, _d, _i, _vp, _sz, _vp]),
     "xl_czt_bwd": (_i, [_vp, _vp, _vp, _d, _i, _i, _i, _i, _d, _d, _d, _d, _d, _d, _d, _d, _i, _vp, _sz, _vp]),

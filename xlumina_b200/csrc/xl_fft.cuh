@@ -25,7 +25,7 @@
 #pragma once
 #include "xl_platform.h"
 
-#define XL_TWN 16384  // master twiddle table in global memory: tw[k] = exp(-2*pi*i*k/XL_TWN), generated in fp64
+#define XL_TWN 32768  // master twiddle table in global memory: tw[k] = exp(-2*pi*i*k/XL_TWN), generated in fp64
 
 XL_HD constexpr int xl_first_radix(int L) { return L > 16 ? xl_first_radix(L / 16) : L; }
 XL_HD constexpr int xl_tile_elems(int L, int V) { return (L + L / 16) * V; }          // cf elements of the padded tile

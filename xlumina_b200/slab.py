@@ -12,8 +12,11 @@ gloo in the CPU tests, which drive the host-emulated kernel bodies through the s
 The exchanged layouts are chosen so that every peer's chunk is contiguous on both sides and the second exchange is the
 exact inverse of the first: row side [L/2 pairs][rows][2], column side [source rank][(L/2)/G pairs][rows][2].
 
-Round-1 limits: padded length <= 4096 (N <= 2048: the long-line FFT that 16384^2 needs is not built yet), scalar fields,
-forward and field-VJP (the operator is complex-symmetric: `rs_slab_vjp`); d/dz is single-GPU only.
+Padded lengths up to 4096 (N <= 2048) run the single-pass FFT kernels; longer lines, up to 32768 (N <= 16384, the 16384^2
+configuration), are split into R <= 8 sub-lines of 4096 (csrc/xl_long.cuh: the forward radix-R step is fused into the
+loads, the inverse one is a pointwise combine kernel over a scratch buffer).  With one rank the same chain is the
+single-GPU path for grids above 2048^2.  Round-1 limits: scalar fields, forward and field-VJP (the operator is
+complex-symmetric: `rs_slab_vjp`); d/dz is available on the fused single-GPU path (N <= 2048) only.
 """
 import ctypes
 
@@ -38,9 +41,9 @@ class SlabPlan:
 
     def __init__(self, N, world, lib):
         self.N, self.G = int(N), int(world)
-        self.L = lib.xl_rs_padded_length(self.N)
+        self.L = lib.xl_slab_padded_length(self.N)
         if not self.L:
-            raise _lib.XlpropError(f"slab RS: N={N} unsupported in this version (padded length must be <= 4096)")
+            raise _lib.XlpropError(f"slab RS: N={N} unsupported (padded length must be <= 32768)")
         if self.N % (2 * self.G) or (self.L // 2) % self.G:
             raise _lib.XlpropError(f"slab RS: N={N} must be a multiple of 2*G and L/2={self.L // 2} a multiple of G={world}")
         self.rows = self.N // self.G                    # field rows per rank
@@ -49,6 +52,7 @@ class SlabPlan:
         self.spec_elems = (self.L // 2) * self.rows * 2
         self.hspec_elems = (self.L // 2) * self.hrows * 2
         self.hloc_elems = self.pairs * self.L * 2
+        self.scratch_bytes = int(lib.xl_slab_scratch_bytes(self.N, self.G))
 
 
 def _all_to_all(buf, group):
@@ -61,9 +65,14 @@ def _all_to_all(buf, group):
     return out
 
 
+def _scratch(plan, ref):
+    return torch.empty(plan.scratch_bytes, dtype=torch.uint8, device=ref.device)
+
+
 def _transfer_slab(plan, z, dx, dy, k, rank, ref, lib, group):
     R = torch.empty(plan.hspec_elems, dtype=torch.complex64, device=ref.device)
-    _lib.check(lib.xl_slab_h_rows(_ptr(R), _ptr(z), plan.N, plan.G, rank, dx, dy, k, _stream_of(ref)), "xl_slab_h_rows")
+    scr = _scratch(plan, ref)
+    _lib.check(lib.xl_slab_h_rows(_ptr(R), _ptr(z), plan.N, plan.G, rank, dx, dy, k, _ptr(scr), _stream_of(ref)), "xl_slab_h_rows")
     Th = _all_to_all(R, group)
     H = torch.empty(plan.hloc_elems, dtype=torch.complex64, device=ref.device)
     _lib.check(lib.xl_slab_h_cols(_ptr(Th), _ptr(H), plan.N, plan.G, dx, dy, _stream_of(ref)), "xl_slab_h_cols")
@@ -75,10 +84,11 @@ def _apply(plan, field_local, H, flags, lib, group):
     st = _stream_of(field_local)
     _lib.check(lib.xl_slab_rows_fwd(_ptr(field_local), _ptr(S), plan.N, plan.G, flags, st), "xl_slab_rows_fwd")
     T = _all_to_all(S, group)
-    _lib.check(lib.xl_slab_cols(_ptr(T), _ptr(H), plan.N, plan.G, st), "xl_slab_cols")
+    scr = _scratch(plan, field_local)
+    _lib.check(lib.xl_slab_cols(_ptr(T), _ptr(H), plan.N, plan.G, _ptr(scr), st), "xl_slab_cols")
     S2 = _all_to_all(T, group)
     out = torch.empty_like(field_local)
-    _lib.check(lib.xl_slab_rows_inv(_ptr(S2), _ptr(out), plan.N, plan.G, flags, st), "xl_slab_rows_inv")
+    _lib.check(lib.xl_slab_rows_inv(_ptr(S2), _ptr(out), plan.N, plan.G, flags, _ptr(scr), st), "xl_slab_rows_inv")
     return out
 
 
