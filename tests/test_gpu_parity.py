@@ -364,3 +364,23 @@ def test_transfer_function_cache_same_z_object(xb):
         assert len(ops._transfer_cache) == 2 and not torch.equal(o_new, ref[0])
     finally:
         ops.set_transfer_cache(0)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("N,z", [(64, 4000.0), (128, -9000.0)])
+def test_split_line_kernels_small_on_device(xb, N, z):
+    """csrc/xl_long.cuh on the device at small sizes (sub-line length forced to 32: padded length = 4 and 8 sub-lines), against
+    the fused path; production sizes (4096^2, 16384^2 point-source checks) are run by scripts/long_check.py."""
+    from xlumina_b200 import ops, slab, _lib
+    rng = np.random.default_rng(N)
+    x, _ = xb.space(600.0, N)
+    dx, k = float(x[1] - x[0]), 2 * np.pi / 0.6328
+    u = dev_c64(crand(rng, N, N))
+    ref = ops.rs_propagation(u, z, dx, dx, k)
+    L = _lib.lib()
+    L.xl_debug_set_max_line(32)
+    try:
+        out = slab.rs_propagation_slab(u, z, dx, dx, k)
+    finally:
+        L.xl_debug_set_max_line(4096)
+    assert rel_l2(out.cpu().numpy(), ref.cpu().numpy()) < 2e-6
