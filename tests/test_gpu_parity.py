@@ -258,7 +258,8 @@ def test_errors_are_loud(xb):
     with pytest.raises(XlpropError):
         li.CZT(100.0, np.linspace(-1, 1, 32), np.linspace(-1, 1, 32))   # m+M-1 == 64: reference raises too
     with pytest.raises(XlpropError):
-        xb.ops.rs_propagation(torch.zeros(4096, 4096, dtype=torch.complex64, device="cuda"), 1.0, 1.0, 1.0, 1.0)
+        # above the fused path the stage chain needs whole row pairs: an odd size must fail loudly, not approximately
+        xb.ops.rs_propagation(torch.zeros(2049, 2049, dtype=torch.complex64, device="cuda"), 1.0, 1.0, 1.0, 1.0)
 
 
 @pytest.mark.gpu
@@ -384,3 +385,50 @@ def test_split_line_kernels_small_on_device(xb, N, z):
     finally:
         L.xl_debug_set_max_line(4096)
     assert rel_l2(out.cpu().numpy(), ref.cpu().numpy()) < 2e-6
+
+
+@pytest.mark.gpu
+def test_public_api_routes_large_grids_through_stage_chain(xb):
+    """ops.rs_propagation above FUSED_MAX_N uses the slab / split-line stage chain with one rank (the route a 16384^2 field
+    takes); here the threshold is lowered so that a 64^2 batch takes it: forward and field gradient equal the fused path,
+    and d/dz raises instead of returning something wrong."""
+    from xlumina_b200 import ops, _lib
+    rng = np.random.default_rng(2)
+    N = 64
+    x, _ = xb.space(600.0, N)
+    dx, k = float(x[1] - x[0]), 2 * np.pi / 0.6328
+    u = dev_c64(crand(rng, 2, N, N))
+    ct = dev_c64(crand(rng, 2, N, N))
+
+    def run(zt):
+        a = u.clone().requires_grad_(True)
+        o = ops.rs_propagation(a, zt, dx, dx, k)
+        (o * ct).real.sum().backward()
+        return o.detach(), a.grad.detach()
+
+    o_ref, g_ref = run(7000.0)
+    old = ops.FUSED_MAX_N
+    ops.FUSED_MAX_N = 32
+    try:
+        o_big, g_big = run(7000.0)
+        zt = torch.tensor([7000.0], dtype=torch.float64, device="cuda", requires_grad=True)
+        with pytest.raises(_lib.XlpropError):
+            run(zt)
+    finally:
+        ops.FUSED_MAX_N = old
+    assert rel_l2(o_big.cpu().numpy(), o_ref.cpu().numpy()) < 2e-6
+    assert rel_l2(g_big.cpu().numpy(), g_ref.cpu().numpy()) < 2e-6
+
+
+@pytest.mark.gpu
+def test_lazily_conjugated_inputs_are_resolved(xb):
+    """torch's .conj() is a lazy view over the unconjugated storage: the raw-pointer boundary must materialise it."""
+    from xlumina_b200 import ops
+    rng = np.random.default_rng(4)
+    N = 64
+    x, _ = xb.space(600.0, N)
+    dx, k = float(x[1] - x[0]), 2 * np.pi / 0.6328
+    u = dev_c64(crand(rng, N, N))
+    a = ops.rs_propagation(u.conj(), 5000.0, dx, dx, k)
+    b = ops.rs_propagation(torch.conj_physical(u), 5000.0, dx, dx, k)
+    assert torch.equal(a, b)

@@ -76,7 +76,7 @@ def _c64(t):
         t = t.to(torch.complex64)
     elif t.dtype != torch.complex64:
         t = t.to(torch.complex64)
-    return t.contiguous()
+    return t.resolve_conj().contiguous()      # a lazily conjugated view shares storage with the unconjugated data
 
 
 _grid_cache = {}
@@ -170,7 +170,7 @@ class _RS(torch.autograd.Function):
         dx, dy, k = ctx.geom
         L = _lib.lib()
         F, N = field.shape[0], field.shape[-1]
-        g = g.contiguous()
+        g = g.resolve_conj().contiguous()
         want_z = ctx.needs_input_grad[1]
         gin = torch.empty_like(field)
         gz = torch.zeros(1, dtype=torch.float64, device=field.device) if want_z else None
@@ -204,7 +204,7 @@ class _VRS(torch.autograd.Function):
         x0, y0, dx, dy, k = ctx.geom
         L = _lib.lib()
         N = exy.shape[-1]
-        g = g.contiguous()
+        g = g.resolve_conj().contiguous()
         want_z = ctx.needs_input_grad[1]
         gin = torch.empty_like(exy)
         gz = torch.zeros(1, dtype=torch.float64, device=exy.device) if want_z else None
@@ -214,14 +214,48 @@ class _VRS(torch.autograd.Function):
         return gin, gz, None, None, None, None, None, None, None
 
 
+FUSED_MAX_N = 2048   # largest grid of the fused single-pass path (padded length 4096); above it: the stage chain of slab.py
+
+
+class _RSLarge(torch.autograd.Function):
+    """Grids above FUSED_MAX_N (up to 16384^2): the slab / split-line stage chain of xlumina_b200/slab.py with one rank.
+    Differentiable in the field (the operator is complex-symmetric); d/dz is not available on this path."""
+
+    @staticmethod
+    def forward(ctx, field, z, dx, dy, k):
+        from . import slab
+        _require_device(field)
+        outs, H = [], None
+        for f in field:                                   # the fields of a batch share one transfer-function slab
+            o, H = slab.rs_propagation_slab(f, z, dx, dy, k, transfer=H, return_transfer=True, group=slab._LOCAL)
+            outs.append(o)
+        ctx.save_for_backward(H)
+        return torch.stack(outs)
+
+    @staticmethod
+    def backward(ctx, g):
+        from . import slab
+        if ctx.needs_input_grad[1]:
+            raise _lib.XlpropError(f"RS propagation above {FUSED_MAX_N}^2 is not differentiable in z in this version")
+        (H,) = ctx.saved_tensors
+        # torch convention: conj(A^T conj(g)); A^T = A
+        gin = torch.stack([torch.conj_physical(slab.rs_slab_vjp(torch.conj_physical(gi), H, group=slab._LOCAL)) for gi in g])
+        return gin, None, None, None, None
+
+
+
 def rs_propagation(field, z, dx, dy, k):
-    """Scalar Rayleigh-Sommerfeld propagation of `field` (..., N, N) over distance z (differentiable in field and z)."""
+    """Scalar Rayleigh-Sommerfeld propagation of `field` (..., N, N) over distance z (differentiable in field and z; above
+    FUSED_MAX_N^2 in the field only)."""
     dt = field.dtype
     N = field.shape[-1]
     if field.shape[-2] != N:
         raise ValueError("RS propagation needs square fields")
     f = _c64(field).reshape(-1, N, N)
     zt = _as_z(z, f)
+    if N > FUSED_MAX_N:
+        out = _RSLarge.apply(f, zt, float(dx), float(dy), float(k)).reshape(field.shape)
+        return out if dt == torch.complex64 or not torch.is_complex(field) else out.to(dt)
     out = _RS.apply(f, zt, float(dx), float(dy), float(k), _z_key(z) if _transfer_cache_size else None, z).reshape(field.shape)
     return out if dt == torch.complex64 or not torch.is_complex(field) else out.to(dt)
 
@@ -274,7 +308,7 @@ class _CZT(torch.autograd.Function):
         (x0, dx, y0, dy) = gin
         (xo0, xol, Mx, yo0, yol, My) = gout
         L = _lib.lib()
-        g = g.contiguous()
+        g = g.resolve_conj().contiguous()
         ct = torch.empty(shape, dtype=g.dtype, device=g.device)
         ws = _workspace(g, L.xl_czt_workspace_bytes(N, Mx, My, vect))
         _lib.check(L.xl_czt_bwd(_ptr(g), _ptr(ct), _ptr(z), lam, N, Mx, My, vect, x0, dx, y0, dy, xo0, xol, yo0, yol,
@@ -306,7 +340,7 @@ class _HighNA(torch.autograd.Function):
         (x0, dx, y0, dy) = gin
         (xo0, xol, Mx, yo0, yol, My) = gout
         L = _lib.lib()
-        g = g.contiguous()
+        g = g.resolve_conj().contiguous()
         ct = torch.empty((2, N, N), dtype=g.dtype, device=g.device)
         ws = _workspace(g, L.xl_highna_workspace_bytes(N, Mx, My))
         _lib.check(L.xl_highna_bwd(_ptr(g), _ptr(ct), N, Mx, My, radius, f, lam, x0, dx, y0, dy, xo0, xol, yo0, yol,

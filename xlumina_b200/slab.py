@@ -55,13 +55,22 @@ class SlabPlan:
         self.scratch_bytes = int(lib.xl_slab_scratch_bytes(self.N, self.G))
 
 
+_LOCAL = object()   # group sentinel: single-rank chain even inside an initialised multi-rank job (no collective at all)
+
+
+def _world_rank(group):
+    if group is _LOCAL or not dist.is_initialized():
+        return 1, 0
+    return dist.get_world_size(group), dist.get_rank(group)
+
+
 def _all_to_all(buf, group):
     """Equal-split all-to-all of a complex64 buffer whose G peer chunks are contiguous; returns the received buffer."""
+    if _world_rank(group)[0] == 1:
+        return buf            # one rank: the exchanged layout [1][pairs][rows][2] IS the row-side layout
     out = torch.empty_like(buf)
-    if dist.is_initialized() and dist.get_world_size(group) > 1:
+    if True:
         dist.all_to_all_single(torch.view_as_real(out).reshape(-1), torch.view_as_real(buf).reshape(-1), group=group)
-    else:
-        out.copy_(buf)
     return out
 
 
@@ -94,14 +103,13 @@ def _apply(plan, field_local, H, flags, lib, group):
 
 def rs_propagation_slab(field_local, z, dx, dy, k, group=None, lib=None, transfer=None, return_transfer=False):
     """Propagate the row slab `field_local` (N/G, N) complex64 of an N x N field by z; every rank of `group` calls this with
-    its own slab and the same z, dx, dy, k.  Returns this rank's rows of the result (and the transfer-function slab when
+    its own slab and the same z, dx, dy, k (`group=slab._LOCAL`: this process alone, whole field, no collective).  Returns this rank's rows of the result (and the transfer-function slab when
     `return_transfer`, to be passed back as `transfer` for another field or the VJP at the same z)."""
     lib = lib or _lib.lib()
-    world = dist.get_world_size(group) if dist.is_initialized() else 1
-    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    world, rank = _world_rank(group)
     if lib is _lib._lib and not field_local.is_cuda:
         raise _lib.XlpropError("xlumina_b200 operators need CUDA tensors (no CPU fallback)")
-    f = field_local.to(torch.complex64).contiguous()
+    f = field_local.to(torch.complex64).resolve_conj().contiguous()
     N = f.shape[-1]
     plan = SlabPlan(N, world, lib)
     if f.shape != (plan.rows, N):
@@ -118,7 +126,7 @@ def rs_slab_vjp(ct_local, transfer, group=None, lib=None):
     """Field VJP (JAX convention: plain transpose) of rs_propagation_slab at the same z: the operator is complex-symmetric,
     so it is the forward chain on the cotangent slab with the saved transfer-function slab."""
     lib = lib or _lib.lib()
-    world = dist.get_world_size(group) if dist.is_initialized() else 1
-    c = ct_local.to(torch.complex64).contiguous()
+    world, _ = _world_rank(group)
+    c = ct_local.to(torch.complex64).resolve_conj().contiguous()
     plan = SlabPlan(c.shape[-1], world, lib)
     return _apply(plan, c, transfer, 0, lib, group)
