@@ -432,3 +432,31 @@ def test_lazily_conjugated_inputs_are_resolved(xb):
     a = ops.rs_propagation(u.conj(), 5000.0, dx, dx, k)
     b = ops.rs_propagation(torch.conj_physical(u), 5000.0, dx, dx, k)
     assert torch.equal(a, b)
+
+
+@pytest.mark.gpu
+def test_vrs_large_grid_route_equals_fused_path(xb):
+    """vrs_propagation above FUSED_MAX_N: Ez formed pointwise, three components through the stage chain as one batch."""
+    from xlumina_b200 import ops
+    rng = np.random.default_rng(9)
+    N = 64
+    x, _ = xb.space(600.0, N)
+    dx, k = float(x[1] - x[0]), 2 * np.pi / 0.6328
+    exy = dev_c64(crand(rng, 2, N, N))
+    ct = dev_c64(crand(rng, 3, N, N))
+
+    def run():
+        a = exy.clone().requires_grad_(True)
+        o = ops.vrs_propagation(a, None, 6000.0, float(x[0]), float(x[0]), dx, dx, k)
+        (o * ct).real.sum().backward()
+        return o.detach(), a.grad.detach()
+
+    o_ref, g_ref = run()
+    old = ops.FUSED_MAX_N
+    ops.FUSED_MAX_N = 32
+    try:
+        o_big, g_big = run()
+    finally:
+        ops.FUSED_MAX_N = old
+    assert rel_l2(o_big.cpu().numpy(), o_ref.cpu().numpy()) < 2e-6
+    assert rel_l2(g_big.cpu().numpy(), g_ref.cpu().numpy()) < 2e-6

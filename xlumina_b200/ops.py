@@ -265,6 +265,16 @@ def vrs_propagation(Ex, Ey, z, x0, y0, dx, dy, k):
     dt = Ex.dtype
     exy = _c64(Ex) if Ey is None else torch.stack([_c64(Ex), _c64(Ey)], dim=0)
     zt = _as_z(z, exy)
+    N = exy.shape[-1]
+    if N > FUSED_MAX_N:
+        # large grids: Ez = (Ex X + Ey Y)/r (vectorized_optics.py:258-261) is formed pointwise here and the three components
+        # go through the stage chain as one batch sharing the transfer function (differentiable in Ex, Ey only)
+        xs = float(x0) + float(dx) * torch.arange(N, dtype=torch.float64, device=exy.device)
+        ys = float(y0) + float(dy) * torch.arange(N, dtype=torch.float64, device=exy.device)
+        r = torch.sqrt(xs[None, :] ** 2 + ys[:, None] ** 2 + zt.detach() ** 2)
+        ez = exy[0] * (xs[None, :] / r).to(torch.float32) + exy[1] * (ys[:, None] / r).to(torch.float32)
+        out = _RSLarge.apply(torch.stack([exy[0], exy[1], ez]), zt, float(dx), float(dy), float(k))
+        return out if dt == torch.complex64 or not torch.is_complex(Ex) else out.to(dt)
     out = _VRS.apply(exy, zt, float(x0), float(y0), float(dx), float(dy), float(k),
                      _z_key(z) if _transfer_cache_size else None, z)
     return out if dt == torch.complex64 or not torch.is_complex(Ex) else out.to(dt)
