@@ -458,7 +458,7 @@ extern "C" int xl_slab_h_rows(void* Rb, const double* z, int N, int G, int rank,
     q.z = z; q.hrow0 = rank * g.hrows; q.hrows = g.hrows; q.scratch = (cf*)scratch; q.spec = (cf*)Rb;
     rc = xl_launch<XlHEval>(XlDim{pointwise_grid((size_t)g.hrows * (g.P / 2 + 1), XlHEval::NT), 1}, st, q);
     if (rc) return rc;
-    XL_FOR_L0(g.L0, rc = xl_launch<XlLongHRows<XL>>(XlDim{xl_groups(g.hrows), g.R}, st, q));
+    XL_FOR_L0(g.L0, rc = xl_launch<XlLongHRows<XL>>(XlDim{g.R, xl_groups(g.hrows)}, st, q));
     return rc;
 }
 // Th = exchanged row spectra of h [G][pairs][hrows][2]  ->  this rank's transfer-function slab Hloc[pairs][P][2]
@@ -479,7 +479,7 @@ extern "C" int xl_slab_h_cols(const void* Th, void* Hloc, int N, int G, double d
     XlLongParams q;
     if ((rc = long_params(q, g, N, dx, dy, 0.0))) return rc;
     q.spec = (cf*)Th; q.H = (cf*)Hloc; q.chunk_rows = g.hrows;
-    XL_FOR_L0(g.L0, rc = xl_launch<XlLongHCols<XL>>(XlDim{g.pairs, g.R}, st, q));
+    XL_FOR_L0(g.L0, rc = xl_launch<XlLongHCols<XL>>(XlDim{g.R, g.pairs}, st, q));
     return rc;
 }
 // this rank's field rows in_local[rows][N]  ->  row spectra S[P/2][rows][2]
@@ -500,7 +500,7 @@ extern "C" int xl_slab_rows_fwd(const void* in_local, void* S, int N, int G, int
     XlLongParams q;
     if ((rc = long_params(q, g, N, 1.0, 1.0, 0.0))) return rc;
     q.in = (const cf*)in_local; q.spec = (cf*)S; q.flags = flags & XL_CONJ_IN;
-    XL_FOR_L0(g.L0, rc = xl_launch<XlLongRowsFwd<XL>>(XlDim{xl_groups(g.rows), g.R}, st, q));
+    XL_FOR_L0(g.L0, rc = xl_launch<XlLongRowsFwd<XL>>(XlDim{g.R, xl_groups(g.rows)}, st, q));
     return rc;
 }
 // T = exchanged spectra [G][pairs][N/G][2], filtered in place by this rank's transfer-function slab
@@ -522,7 +522,7 @@ extern "C" int xl_slab_cols(void* T, const void* Hloc, int N, int G, void* scrat
     XlLongParams q;
     if ((rc = long_params(q, g, N, 1.0, 1.0, 0.0))) return rc;
     q.spec = (cf*)T; q.H = (cf*)Hloc; q.scratch = (cf*)scratch;
-    XL_FOR_L0(g.L0, rc = xl_launch<XlLongCols<XL>>(XlDim{g.pairs, g.R}, st, q));
+    XL_FOR_L0(g.L0, rc = xl_launch<XlLongCols<XL>>(XlDim{g.R, g.pairs}, st, q));
     if (rc) return rc;
     return xl_launch<XlLongColsCombine>(XlDim{pointwise_grid((size_t)g.pairs * g.L0, XlLongColsCombine::NT), 1}, st, q);
 }
@@ -545,7 +545,7 @@ extern "C" int xl_slab_rows_inv(const void* S, void* out_local, int N, int G, in
     XlLongParams q;
     if ((rc = long_params(q, g, N, 1.0, 1.0, 0.0))) return rc;
     q.spec = (cf*)S; q.out = (cf*)out_local; q.scratch = (cf*)scratch; q.flags = flags & XL_CONJ_OUT;
-    XL_FOR_L0(g.L0, rc = xl_launch<XlLongRowsInv<XL>>(XlDim{xl_groups(g.rows), g.R}, st, q));
+    XL_FOR_L0(g.L0, rc = xl_launch<XlLongRowsInv<XL>>(XlDim{g.R, xl_groups(g.rows)}, st, q));
     if (rc) return rc;
     return xl_launch<XlLongRowsCombine>(XlDim{pointwise_grid((size_t)g.rows * g.L0, XlLongRowsCombine::NT), 1}, st, q);
 }

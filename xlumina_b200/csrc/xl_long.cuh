@@ -18,7 +18,7 @@ struct XlLongParams {
     int N, P, R, L0;        // samples per line, padded length, split factor, sub-line length (P == R * L0)
     int rows;               // row kernels: rows of this launch == row count of the blocked layout
     int chunk_rows;         // column kernels: rows per source rank in the exchanged layout [rank][pairs][chunk_rows][2]
-    int pairs;              // column kernels: slot pairs owned by this rank (== gridDim.x)
+    int pairs;              // column kernels: slot pairs owned by this rank (== gridDim.y; blockIdx.x is the sub-line)
     int flags;
     const cf* in; cf* out;  // field rows [rows][N]
     cf* spec;               // row side: [P/2][rows][2]; column side: exchanged layout
@@ -71,7 +71,8 @@ template <int L0> struct XlLongRowsFwd {
     XL_DEV static void run(const Params& p, cf* s) {
         cf* t = s + xl_tile_elems(L0, XL_V);
         XlFft<L0, XL_V>::init_tw(t, p.tw);
-        XlLongRowsFwdOp<L0> op{{}, p, XL_BLOCK_Y, XL_BLOCK_X * XL_V};
+        XlLongRowsFwdOp<L0> op{{}, p, XL_BLOCK_X, XL_BLOCK_Y * XL_V};   // sub-line q varies fastest: the R CTAs that re-read one
+                                                                         // row pair are neighbours in launch order (L2 hits)
         XlFft<L0, XL_V>::forward(s, t, op);
     }
 };
@@ -108,7 +109,7 @@ template <int L0> struct XlLongRowsInv {
     XL_DEV static void run(const Params& p, cf* s) {
         cf* t = s + xl_tile_elems(L0, XL_V);
         XlFft<L0, XL_V>::init_tw(t, p.tw);
-        XlLongRowsInvOp<L0> op{{}, p, XL_BLOCK_Y, XL_BLOCK_X * XL_V};
+        XlLongRowsInvOp<L0> op{{}, p, XL_BLOCK_X, XL_BLOCK_Y * XL_V};
         XlFft<L0, XL_V>::inverse(s, t, op);
     }
 };
@@ -194,8 +195,8 @@ template <int L0> struct XlLongCols {
     XL_DEV static void run(const Params& p, cf* s) {
         cf* t = s + xl_tile_elems(L0, XL_V);
         XlFft<L0, XL_V>::init_tw(t, p.tw);
-        const int G = XL_BLOCK_X;
-        XlLongColsOp<L0> op{{}, p, G, XL_BLOCK_Y, p.spec + (size_t)G * p.chunk_rows * XL_V, p.H + (size_t)G * p.P * XL_V};
+        const int G = XL_BLOCK_Y;   // sub-line on blockIdx.x: the R CTAs of one column pair run back to back
+        XlLongColsOp<L0> op{{}, p, G, XL_BLOCK_X, p.spec + (size_t)G * p.chunk_rows * XL_V, p.H + (size_t)G * p.P * XL_V};
         XlFft<L0, XL_V>::conv(s, t, op);
     }
 };
@@ -290,7 +291,7 @@ template <int L0> struct XlLongHRows {
     XL_DEV static void run(const Params& p, cf* s) {
         cf* t = s + xl_tile_elems(L0, XL_V);
         XlFft<L0, XL_V>::init_tw(t, p.tw);
-        XlLongHRowsOp<L0> op{{}, p, XL_BLOCK_Y, XL_BLOCK_X * XL_V};
+        XlLongHRowsOp<L0> op{{}, p, XL_BLOCK_X, XL_BLOCK_Y * XL_V};
         XlFft<L0, XL_V>::forward(s, t, op);
     }
 };
@@ -331,8 +332,8 @@ template <int L0> struct XlLongHCols {
     XL_DEV static void run(const Params& p, cf* s) {
         cf* t = s + xl_tile_elems(L0, XL_V);
         XlFft<L0, XL_V>::init_tw(t, p.tw);
-        const int G = XL_BLOCK_X;
-        XlLongHColsOp<L0> op{{}, p, XL_BLOCK_Y, p.spec + (size_t)G * p.chunk_rows * XL_V, p.H + (size_t)G * p.P * XL_V};
+        const int G = XL_BLOCK_Y;
+        XlLongHColsOp<L0> op{{}, p, XL_BLOCK_X, p.spec + (size_t)G * p.chunk_rows * XL_V, p.H + (size_t)G * p.P * XL_V};
         XlFft<L0, XL_V>::forward(s, t, op);
     }
 };
