@@ -325,10 +325,13 @@ def run_ours(args, rank, local_rank, world):
         #   rs_cols_gz  per field: read 2u (cotangent spectra) + 2u (conj-field spectra) + write 2u; per launch H and Hz: 4u
         u_bytes = 8.0 * N_GRID * N_GRID
         roof = None
-        try:
-            ncu_traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic_r01.json")))
+        ncu_traffic = {}
+        try:   # the latest committed ncu --set full capture (scripts/make_profiles.py writes one file per round)
+            import glob
+            files = sorted(glob.glob(os.path.join(ROOT, "profiles", "ncu_traffic_r*.json")))
+            ncu_traffic = json.load(open(files[-1])) if files else {}
         except Exception:
-            ncu_traffic = {}
+            pass
         kname = max((kk for kk in ("rs_cols", "rs_cols_gz") if kk in kern), key=lambda kk: kern[kk][1], default=None)
         if kname and kname in kern1:
             cnt, tot = kern1[kname]                      # scalar-RS launches only: 1 field per launch

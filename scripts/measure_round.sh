@@ -1,0 +1,26 @@
+#!/usr/bin/env bash
+# One gpurun call's worth of evidence for a round (run it UNDER gpurun, 1 GPU, from the repo root):
+#   /usr/local/graft/bin/gpurun --timeout 600 -- 'bash scripts/measure_round.sh r02'
+# then, back in the build container:   python scripts/make_profiles.py r02
+# Every step has its own timeout; only CSV/JSON/log summaries are written to gpurun_out/ (the .ncu-rep files stay in /tmp:
+# gpurun_out/ is limited to 64 MiB).  ~4 GPU-minutes.
+set -u
+TAG=${1:-rXX}
+OUT=gpurun_out
+mkdir -p $OUT
+timeout 120 python -m pytest tests -m gpu -x -q > $OUT/pytest_gpu_$TAG.log 2>&1; tail -2 $OUT/pytest_gpu_$TAG.log
+timeout 60 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/smoke_$TAG.log 2>&1; tail -1 $OUT/smoke_$TAG.log
+timeout 150 python bench.py > $OUT/bench_${TAG}_final.json 2> $OUT/bench_${TAG}_final.err; tail -c 400 $OUT/bench_${TAG}_final.json
+timeout 90 python scripts/gpu_probe.py --nosmoke > $OUT/probe_$TAG.log 2>&1
+# launch list of the bench command itself (cold cache + serialised: shares only)
+timeout 90 ncu --metrics gpu__time_duration.sum --clock-control none -k xl_kernel -c 500 --csv \
+    --log-file $OUT/launches_$TAG.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > $OUT/bench_under_ncu.log 2>&1
+# full metrics: RS forward+gradient (12 launches per iteration; second iteration) and CZT forward+gradient (6 per iteration)
+timeout 240 ncu --set full --clock-control none -k xl_kernel -s 12 -c 12 -o /tmp/prof_rsgrad_$TAG \
+    python scripts/prof_rs.py 2048 grad 2 > $OUT/ncu_rsgrad.log 2>&1
+ncu -i /tmp/prof_rsgrad_$TAG.ncu-rep --page raw --csv > $OUT/ncu_${TAG}_rsgrad_raw.csv 2>/dev/null
+timeout 180 ncu --set full --clock-control none -k xl_kernel -s 6 -c 6 -o /tmp/prof_cztgrad_$TAG \
+    python scripts/prof_rs.py 2048 cztgrad 2 > $OUT/ncu_cztgrad.log 2>&1
+ncu -i /tmp/prof_cztgrad_$TAG.ncu-rep --page raw --csv > $OUT/ncu_${TAG}_cztgrad_raw.csv 2>/dev/null
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active --format=csv > $OUT/smi_$TAG.txt
+du -sh $OUT
