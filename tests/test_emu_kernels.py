@@ -85,6 +85,84 @@ def test_rs_large_padded_lengths(emu, N):
     assert rel_l2(out, ref) < TIGHT
 
 
+def test_rs_and_czt_at_the_baseline_size_2048(emu):
+    """BASELINE.json's size itself (2048 x 2048, lambda = 632.8 nm, window +-15 mm; z = 5 cm for RS, 5 mm for CZT,
+    examples/scalar_xlumina.py:22-33): the kernel bodies against the complex128 oracle at full size, on the CPU.  The GPU suite
+    checks the same size through properties only (no CPU oracle run on the GPU box's clock)."""
+    o.set_workers(8)
+    N, lam = 2048, 0.6328
+    x = np.linspace(-15000, 15000, N)
+    rng = np.random.default_rng(2048)
+    X, Y = np.meshgrid(x, x)
+    f = np.exp(-(X ** 2 + Y ** 2) / 1200.0 ** 2) * (1 + 0.05 * (rng.standard_normal((N, N)) + 1j * rng.standard_normal((N, N))))
+    ref, _ = o.RS_propagation(f, x, x, lam, 50000.0)
+    out, *_ = rs_fwd(emu, f, x, x, lam, 50000.0)
+    assert rel_l2(out, ref) < TIGHT
+    g = dict(x=x, y=x, xout=x, yout=x, z=5000.0, wavelength=lam)
+    cref = o.CZT(f, x, x, lam, 5000.0, x, x)
+    cout = np.zeros((N, N), np.complex64)
+    czt_call(emu, emu.xl_czt_fwd, c64(f), cout, g, 0)
+    assert rel_l2(cout, cref) < TIGHT
+
+
+def test_rs_gradients_at_the_baseline_size_2048(emu):
+    """Backward kernels at 2048 x 2048: the field VJP against the oracle (A is complex-symmetric: A^T ct = A ct) and d/dz
+    against a central difference of the oracle, with a random cotangent."""
+    o.set_workers(8)
+    N, lam, z = 2048, 0.6328, 50000.0
+    x = np.linspace(-15000, 15000, N)
+    rng = np.random.default_rng(4096)
+    X, Y = np.meshgrid(x, x)
+    env = np.exp(-(X ** 2 + Y ** 2) / 4000.0 ** 2)
+    f = env * (rng.standard_normal((N, N)) + 1j * rng.standard_normal((N, N)))
+    ct = env * (rng.standard_normal((N, N)) + 1j * rng.standard_normal((N, N)))
+    out, H, ws, zz = rs_fwd(emu, f, x, x, lam, z)
+    gin = np.zeros((N, N), np.complex64)
+    gz = np.zeros(1)
+    rc = emu.xl_rs_bwd(ptr(c64(f)), ptr(out), ptr(c64(ct)), ptr(gin), ptr(gz), ptr(H), ptr(zz), N, 1, x[1] - x[0], x[1] - x[0],
+                       2 * np.pi / lam, 0, ptr(ws), ws.size, None)
+    assert rc == 0, emu.xl_last_error()
+    vref, _ = o.RS_propagation(c64(ct).astype(np.complex128), x, x, lam, z)
+    assert rel_l2(gin, vref) < TIGHT
+    eps = 1e-3
+    fp = c64(f).astype(np.complex128)
+    lp = np.sum(c64(ct).astype(np.complex128) * o.RS_propagation(fp, x, x, lam, z + eps)[0]).real
+    lm = np.sum(c64(ct).astype(np.complex128) * o.RS_propagation(fp, x, x, lam, z - eps)[0]).real
+    gz_ref = (lp - lm) / (2 * eps)
+    assert abs(gz[0] - gz_ref) < TOL * abs(gz_ref)
+
+
+def test_vectorial_paths_at_2048(emu):
+    """VRS (examples/vectorial_xlumina.py:21-32 shape) and the high-NA focus 2048 -> 400 (examples/examples.ipynb:387-460
+    geometry: r = 1800, f = 2000, +-10 um output window) at full size against the oracle."""
+    o.set_workers(8)
+    N, lam = 2048, 0.6328
+    x = np.linspace(-15000, 15000, N)
+    rng = np.random.default_rng(6)
+    X, Y = np.meshgrid(x, x)
+    env = np.exp(-(X ** 2 + Y ** 2) / 3000.0 ** 2)
+    ex = env * (1 + 0.1 * (rng.standard_normal((N, N)) + 1j * rng.standard_normal((N, N))))
+    ey = env * (1j + 0.1 * (rng.standard_normal((N, N)) + 1j * rng.standard_normal((N, N))))
+    exy = c64(np.stack([ex, ey]))
+    k = 2 * np.pi / lam
+    out = np.zeros((3, N, N), np.complex64)
+    H = np.zeros(emu.xl_rs_transfer_bytes(N), np.uint8)
+    ws = np.zeros(emu.xl_rs_workspace_bytes(N, 3, 0), np.uint8)
+    zz = np.array([50000.0])
+    assert emu.xl_vrs_fwd(ptr(exy), ptr(out), ptr(H), ptr(zz), N, x[0], x[0], x[1] - x[0], x[1] - x[0], k, 0, ptr(ws), ws.size, None) == 0
+    ref, _ = o.VRS_propagation(exy[0].astype(np.complex128), exy[1].astype(np.complex128), x, x, lam, 50000.0)
+    assert rel_l2(out, ref) < TIGHT
+    del out, H, ws, ref
+    x2 = np.linspace(-1500, 1500, N)
+    xo = np.linspace(-10, 10, 400)
+    foc = np.zeros((3, 400, 400), np.complex64)
+    ws = np.zeros(emu.xl_highna_workspace_bytes(N, 400, 400), np.uint8)
+    assert emu.xl_highna_fwd(ptr(exy), ptr(foc), N, 400, 400, 1800.0, 2000.0, 0.65, x2[0], x2[1] - x2[0], x2[0], x2[1] - x2[0],
+                             xo[0], xo[-1], xo[0], xo[-1], 0, ptr(ws), ws.size, None) == 0, emu.xl_last_error()
+    fref = o.VCZT_objective_lens(exy[0].astype(np.complex128), exy[1].astype(np.complex128), x2, x2, 0.65, 1800.0, 2000.0, xo, xo)
+    assert rel_l2(foc, fref) < TIGHT
+
+
 @pytest.mark.parametrize("N", [9, 17, 50, 100])
 def test_rs_non_power_of_two_sizes(emu, N):
     rng = np.random.default_rng(N)
