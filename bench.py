@@ -362,9 +362,10 @@ def run_ours(args, rank, local_rank, world):
         }
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
-            tt = cpu_step_times(threads, 2, mix=False)[1:]
-            line["cpu_baseline"] = {"value": 1.0 / (sum(tt) / len(tt)), "unit": UNIT, "cores": threads, "kind": "port",
-                                    "sample": "1 scalar RS fwd+grad at 2048^2 after 1 warm-up, torch-CPU complex128 restatement "
+            tt = cpu_step_times(threads, 5, mix=True)[1:]     # warm-up (RS), then VRS, CZT, VCZT, RS: one of each
+            line["cpu_baseline"] = {"value": len(tt) / sum(tt), "unit": UNIT, "cores": threads, "kind": "port",
+                                    "sample": "one step of the same mix (scalar RS, VRS, CZT, VCZT forward+gradient at 2048^2) after "
+                                              "1 warm-up propagation, torch-CPU complex128 restatement of the reference "
                                               "(oracle/oracle_torch.py) on all host threads"}
         print(json.dumps(line), flush=True)
     if world > 1:
