@@ -28,7 +28,7 @@ import torch
 import torch.distributed as dist
 
 import xlumina_b200 as xb
-from xlumina_b200 import ops
+from xlumina_b200 import four_f
 from xlumina_b200.sharding import allreduce_grads, shard_range
 
 
@@ -43,18 +43,20 @@ def synthetic_circles(n_samples, x, rng):
     return np.stack(masks), np.stack(targets)
 
 
+class _Beam:
+    """The minimal light-source view four_f.vector_dualSLM_4f_system needs (axis, wavenumber, field)."""
+
+    def __init__(self, x, k, field):
+        self.x, self.k, self.field = x, k, field
+
+
 def forward_loss(params, masks, targets, beam, dx, k):
-    """loss_dualSLM of the reference (four_f_optical_table.py:103-141) on this rank's slice; returns the SUM of per-sample MSEs."""
-    p0, p1, p2, ph1, ph2 = params
-    cm, offset = 1e4, 1.2
-    f = beam[None] * masks
-    f = ops.rs_propagation(f, (p0.abs() * 100 + offset) * cm, dx, dx, k)
-    f = f * torch.exp(1j * (ph1 * (2 * math.pi) - math.pi))[None]
-    f = ops.rs_propagation(f, (p1.abs() * 100 + offset) * cm, dx, dx, k)
-    f = f * torch.exp(1j * (ph2 * (2 * math.pi) - math.pi))[None]
-    f = ops.rs_propagation(f, (p2.abs() * 100 + offset) * cm, dx, dx, k)
-    inten = f.real ** 2 + f.imag ** 2
-    return ((inten - targets) ** 2).sum(dim=(1, 2)).div(inten.shape[-1] * inten.shape[-2]).sum()
+    """loss_dualSLM of the reference (four_f_optical_table.py:103-141) on this rank's slice; returns the SUM of per-sample
+    MSEs (the caller divides by the GLOBAL batch).  The table itself lives in xlumina_b200/four_f.py."""
+    x = dx * (np.arange(beam.shape[-1]) - (beam.shape[-1] - 1) / 2)
+    p = [params[0], params[1], params[2], params[3], params[4]]
+    inten, _, _ = four_f.vector_dualSLM_4f_system(masks, _Beam(x, k, beam), p)
+    return four_f.MSE_Intensity(inten, targets).sum()
 
 
 def main():

@@ -46,8 +46,10 @@ class lax:
 class nn:
     @staticmethod
     def logsumexp(a, axis=None):
-        from scipy.special import logsumexp as _l
-        return _l(a, axis=axis)
+        a = _np.asarray(a)
+        m = _np.max(a, axis=axis, keepdims=True)
+        out = _np.log(_np.sum(_np.exp(a - m), axis=axis, keepdims=True)) + m
+        return out.reshape(()) if axis is None else _np.squeeze(out, axis=axis)
 
 
 class random:

@@ -42,3 +42,11 @@ def ones(shape, dtype=float):
 
 def array(obj, dtype=None):
     return _np.array(obj, dtype=dtype).view(_Arr)
+
+
+def fromfunction(function, shape, dtype=float, **kw):
+    """jax.numpy.fromfunction vmaps `function` over the index axes, so the callee sees SCALAR indices (the reference relies on
+    this to build (N, N, 2, 2) Jones tensors, optical_elements.py:208); numpy's version would pass whole index arrays."""
+    idx = _np.indices(shape).reshape(len(shape), -1).astype(dtype)
+    vals = [_np.asarray(function(*[ix[j] for ix in idx], **kw)) for j in range(idx.shape[1])]
+    return _np.stack(vals).reshape(tuple(shape) + vals[0].shape).view(_Arr)

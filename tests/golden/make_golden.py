@@ -182,7 +182,117 @@ def highna_cases():
         save(tag, **arrays)
 
 
+def element_cases():
+    """Pointwise elements (optical_elements.py:87-392, 678-703) on random fields: one fixture with every element's output."""
+    from xlumina.optical_elements import SLM, sSLM, sSLM_with_amplitude, LCD, linear_polarizer, BS_symmetric, lens
+    N, span, lam = 16, 900.0, 0.635
+    x = np.linspace(-span, span, N)
+    a = vector_light(x, x, lam, crand(N, N), crand(N, N))
+    a.Ez = crand(N, N)
+    b = vector_light(x, x, lam, crand(N, N), crand(N, N))
+    alpha, phi = rng.uniform(-np.pi, np.pi, (N, N)), rng.uniform(-np.pi, np.pi, (N, N))
+    A1, A2 = rng.uniform(0, 1, (N, N)), rng.uniform(0, 1, (N, N))
+    eta, theta, bs_theta = 1.234, -0.777, 2.2
+    pol = rng.uniform(-np.pi, np.pi, (N, N))
+    u = crand(N, N)
+    comps = lambda li: np.stack([li.Ex, li.Ey, li.Ez])   # noqa: E731
+    s_out, slm = SLM(scalar_light(x, x, lam, u), alpha, N)
+    c, d = BS_symmetric(a, b, bs_theta)
+    l_s, lens_s = lens(scalar_light(x, x, lam, u), (700.0, 500.0), (4.0e4, 6.0e4))
+    l_v, _ = lens(a, (700.0, 500.0), (4.0e4, 6.0e4))
+    save("elements_n16", x=x, wavelength=lam, a=comps(a), b=comps(b), alpha=alpha, phi=phi, A1=A1, A2=A2, eta=eta, theta=theta,
+         bs_theta=bs_theta, pol=pol, u=u, slm_out=np.asarray(s_out.field), slm=np.asarray(slm),
+         sslm=comps(sSLM(a, alpha, phi)), sslm_amp=comps(sSLM_with_amplitude(a, alpha, phi, A1, A2)),
+         lcd=comps(LCD(a, eta, theta)), lp=comps(linear_polarizer(a, pol)), bs_c=comps(c), bs_d=comps(d),
+         lens_radius=np.array([700.0, 500.0]), lens_focal=np.array([4.0e4, 6.0e4]), lens_scalar=np.asarray(l_s.field),
+         lens_mask=np.asarray(lens_s), lens_vector=comps(l_v))
+
+
+def table_cases():
+    """BASELINE config 3 at reduced size: hybrid_setup_sharp_focus (optical_elements.py:1503-1649) + small_area_hybrid +
+    softmin, and config 4: the dual-SLM 4f table (experiments/four_f_optical_table.py:36-141).  Directional derivatives of the
+    losses are finite differences of the reference itself (steps chosen per table, see below)."""
+    from xlumina.optical_elements import hybrid_setup_sharp_focus
+    from xlumina.loss_functions import vectorized_loss_hybrid
+    from xlumina.toolbox import softmin
+    N, M, lam = 32, 20, 0.635
+    x = np.linspace(-2500.0, 2500.0, N)
+    xo = np.linspace(-10.0, 10.0, M)
+    ls = PolarizedLightSource(x, x, lam)
+    ls.gaussian_beam(w0=(1200.0, 1200.0), jones_vector=(1, 1))
+    big = (0, 1, 6, 7, 12, 13)
+    params = [rng.uniform(0, 1, (N, N)) if i in big else rng.uniform(0, 1, (1,)) for i in range(29)]
+    W = rng.uniform(0.0, 1.0, (6, M, M))      # smooth surrogate loss sum(W * I): the small-area loss is piecewise smooth only
+
+    def losses(p):
+        inten, _ = quiet(hybrid_setup_sharp_focus, ls, ls, ls, ls, ls, ls, p, [1800.0, 2000.0, xo, xo])
+        lv = np.asarray(vectorized_loss_hybrid(inten))
+        return np.asarray(inten), lv, float(softmin(lv)), float(np.sum(W * np.asarray(inten)))
+    inten, lv, l_soft, l_lin = losses(params)
+    arrays = dict(x=x, xout=xo, wavelength=lam, radius=1800.0, f=2000.0, intensities=inten, loss_vec=lv, loss_softmin=l_soft,
+                  W=W, loss_linear=l_lin, Ex=np.asarray(ls.Ex), Ey=np.asarray(ls.Ey))
+    for i, p in enumerate(params):
+        arrays["p%02d" % i] = p
+    dist = (4, 5, 10, 11, 16, 17, 27, 28)
+    for tag, which in (("all", range(29)), ("dist", dist), ("other", [i for i in range(29) if i not in dist])):
+        v = [rng.standard_normal(np.shape(p)) if i in which else np.zeros(np.shape(p)) for i, p in enumerate(params)]
+        # The beams interfere after different path lengths, so the losses oscillate with the distances at the optical
+        # period: a 4th-order stencil with h = 1e-9 (1e-3 um) for directions that move distances (stable to ~1e-7 between
+        # h and 2h; smaller steps drown in the k*z ~ 1e7 rad rounding of float64, larger ones in truncation), h = 1e-7 otherwise.
+        h = 1e-7 if tag == "other" else 1e-9
+        at = {t: losses([p + t * h * d for p, d in zip(params, v)]) for t in (-2, -1, 1, 2)}
+        for j, name in ((3, "dlin_"), (2, "dsoft_")):
+            c1 = (at[1][j] - at[-1][j]) / (2 * h)
+            c2 = (at[2][j] - at[-2][j]) / (4 * h)
+            if name == "dlin_" or tag == "other":      # the small-area loss: only along directions that keep its mask fixed
+                arrays[name + tag] = (4 * c1 - c2) / 3
+            print("  sharp focus", name + tag, "h:", c1, "2h:", c2, "richardson:", (4 * c1 - c2) / 3)
+        for i, d in enumerate(v):
+            arrays["v_%s_%02d" % (tag, i)] = d
+    save("sharp_focus_n32", **arrays)
+
+    # 4f table: the experiment module builds its 1024^2 globals at import; they are replaced by a small grid afterwards
+    sys.path.insert(0, "/root/reference/experiments")
+    import four_f_optical_table as ff
+    N, lam, B = 32, 0.6328, 3
+    x = np.linspace(-1500.0, 1500.0, N)
+    src = LightSource(x, x, lam)
+    src.gaussian_beam(w0=(1200.0, 1200.0), E0=1)
+    beam = np.asarray(src.field).copy()
+    ff.x, ff.y, ff.wavelength, ff.shape, ff.input_light = x, x, lam, N, src
+    X, Y = np.meshgrid(x, x)
+    masks = np.stack([((X / r1) ** 2 + (Y / r2) ** 2 < 1).astype(float) for r1, r2 in rng.uniform(300, 1200, (B, 2))])
+    targets = rng.uniform(0, 0.3, (B, N, N))
+    p4 = [rng.uniform(0.027, 1, (1,)) for _ in range(3)] + [rng.uniform(0, 1, (N, N)) for _ in range(2)]
+
+    def run4(p):
+        outs = []
+        for m in masks:                       # vmap traces the body once, so the mask is applied to the pristine beam
+            src.field = beam.copy()
+            outs.append(np.asarray(quiet(ff.batch_dualSLM_4f, m, x, x, lam, p)[0]))
+        src.field = beam.copy()
+        o = np.stack(outs)
+        return o, float(ff.mean_batch_MSE_Intensity(o, targets)[0])
+    o4, l4 = run4(p4)
+    arrays = dict(x=x, wavelength=lam, beam=beam, masks=masks, targets=targets, intensities=o4, loss=l4)
+    for i, p in enumerate(p4):
+        arrays["p%d" % i] = p
+    # single beam path: the e^{ikz} carrier drops out of the intensities, so a 1e-6 step (1 um) sits on the plateau between
+    # float64 rounding of k*z and truncation (1e-10 is pure noise here)
+    for tag, which, eps in (("dist", (0, 1, 2), 1e-6), ("phase", (3, 4), 1e-6)):
+        v = [rng.standard_normal(np.shape(p)) if i in which else np.zeros(np.shape(p)) for i, p in enumerate(p4)]
+        arrays["dloss_" + tag] = (run4([p + eps * d for p, d in zip(p4, v)])[1] - run4([p - eps * d for p, d in zip(p4, v)])[1]) / (2 * eps)
+        for i, d in enumerate(v):
+            arrays["v_%s_%d" % (tag, i)] = d
+    save("four_f_n32", **arrays)
+
+
 if __name__ == "__main__":
+    if "--tables-only" in sys.argv:           # adds the element/table fixtures without redrawing the propagator ones
+        rng = np.random.default_rng(20261018)
+        element_cases()
+        table_cases()
+        sys.exit(0)
     rs_cases()
     vrs_cases()
     czt_cases()

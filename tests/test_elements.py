@@ -1,0 +1,177 @@
+"""Pointwise optical elements, loss functions and the two optical tables of BASELINE configs 3 and 4
+against fixtures produced by the reference's own source (tests/golden/make_golden.py --tables-only).
+
+CPU part: the elements are device-agnostic torch arithmetic, so they are compared directly; for the tables the propagation
+seam (ops.vrs_propagation / ops.highna_focus / ops.rs_propagation -- CUDA only) is replaced by the complex128 torch oracle,
+which pins the table wiring, parameter maps, losses and their gradients.  The same tables on the real CUDA seam are in
+tests/test_gpu_parity.py."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden, rel_l2
+
+import xlumina_b200 as xb
+from xlumina_b200 import four_f, loss_functions, ops, optical_elements as oe
+from xlumina_b200.toolbox import softmin
+from oracle import oracle_torch as ot
+
+
+def _vec(x, lam, comps, dtype):
+    li = xb.VectorizedLight(x, x, lam, device="cpu", _alloc=False)
+    li.Ex, li.Ey, li.Ez = (torch.as_tensor(c).to(dtype) for c in comps)
+    return li
+
+
+def _comps(li):
+    return torch.stack([li.Ex, li.Ey, li.Ez]).numpy()
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.complex128, 1e-13), (torch.complex64, 2e-6)])
+def test_elements_match_reference(dtype, tol):
+    g = golden("elements_n16")
+    x, lam = g["x"], float(g["wavelength"])
+    a, b = _vec(x, lam, g["a"], dtype), _vec(x, lam, g["b"], dtype)
+    assert rel_l2(_comps(oe.sSLM(a, g["alpha"], g["phi"])), g["sslm"]) < tol
+    assert rel_l2(_comps(oe.sSLM_with_amplitude(a, g["alpha"], g["phi"], g["A1"], g["A2"])), g["sslm_amp"]) < tol
+    assert rel_l2(_comps(oe.LCD(a, float(g["eta"]), float(g["theta"]))), g["lcd"]) < tol
+    assert rel_l2(_comps(oe.linear_polarizer(a, g["pol"])), g["lp"]) < tol
+    c, d = oe.BS_symmetric(a, b, float(g["bs_theta"]))
+    assert rel_l2(_comps(c), g["bs_c"]) < tol and rel_l2(_comps(d), g["bs_d"]) < tol
+    s = xb.ScalarLight(x, x, lam, device="cpu", _alloc=False)
+    s.field = torch.as_tensor(g["u"]).to(dtype)
+    out, slm = oe.SLM(s, torch.as_tensor(g["alpha"]), 16)
+    assert rel_l2(out.field.numpy(), g["slm_out"]) < tol and rel_l2(slm.numpy(), g["slm"]) < tol
+    ls, mask = oe.lens(s, tuple(g["lens_radius"]), tuple(g["lens_focal"]))
+    assert rel_l2(ls.field.numpy(), g["lens_scalar"]) < tol and rel_l2(mask.numpy(), g["lens_mask"]) < tol
+    lv, _ = oe.lens(a, tuple(g["lens_radius"]), tuple(g["lens_focal"]))
+    assert rel_l2(_comps(lv), g["lens_vector"]) < tol
+
+
+def test_elements_accept_tensor_parameters_and_differentiate():
+    g = golden("elements_n16")
+    a = _vec(g["x"], float(g["wavelength"]), g["a"], torch.complex128)
+    eta = torch.tensor([float(g["eta"])], dtype=torch.float64, requires_grad=True)
+    theta = torch.tensor([float(g["theta"])], dtype=torch.float64, requires_grad=True)
+    alpha = torch.tensor(g["alpha"], requires_grad=True)
+    out = oe.LCD(oe.sSLM(a, alpha, g["phi"]), eta, theta)
+    loss = (out.Ex.abs() ** 2 * torch.as_tensor(g["A1"])).sum() + (out.Ey.real * torch.as_tensor(g["A2"])).sum()
+    loss.backward()
+    # central differences through the same code
+    def f(e, t, al):
+        o = oe.LCD(oe.sSLM(a, al, g["phi"]), e, t)
+        return float((o.Ex.abs() ** 2 * torch.as_tensor(g["A1"])).sum() + (o.Ey.real * torch.as_tensor(g["A2"])).sum())
+    h = 1e-6
+    e0, t0, a0 = eta.detach(), theta.detach(), alpha.detach()
+    assert abs((f(e0 + h, t0, a0) - f(e0 - h, t0, a0)) / (2 * h) - float(eta.grad)) < 1e-6 * abs(float(eta.grad)) + 1e-7
+    assert abs((f(e0, t0 + h, a0) - f(e0, t0 - h, a0)) / (2 * h) - float(theta.grad)) < 1e-6 * abs(float(theta.grad)) + 1e-7
+    v = torch.as_tensor(g["pol"])
+    fd = (f(e0, t0, a0 + h * v) - f(e0, t0, a0 - h * v)) / (2 * h)
+    assert abs(fd - float((alpha.grad * v).sum())) < 1e-6 * abs(fd) + 1e-7
+
+
+def test_loss_functions_match_reference_definitions():
+    g = golden("sharp_focus_n32")
+    inten = torch.as_tensor(g["intensities"])
+    lv = loss_functions.vectorized_loss_hybrid(inten)
+    assert np.allclose(lv.numpy(), g["loss_vec"], rtol=1e-12)
+    assert abs(float(softmin(lv)) - float(g["loss_softmin"])) < 1e-12 * abs(float(g["loss_softmin"]))
+    assert abs(float(loss_functions.small_area_hybrid(inten[2])) - g["loss_vec"][2]) < 1e-12 * g["loss_vec"][2]
+    rng = np.random.default_rng(5)
+    a = torch.as_tensor(rng.standard_normal((3, 8, 8)) + 1j * rng.standard_normal((3, 8, 8)))
+    b = torch.as_tensor(rng.standard_normal((3, 8, 8)) + 1j * rng.standard_normal((3, 8, 8)))
+    an, bn = a.numpy(), b.numpy()
+    assert np.allclose(loss_functions.MSE_Intensity(a, b).numpy(), ((abs(an) ** 2 - abs(bn) ** 2) ** 2).sum((1, 2)) / 64)
+    assert np.allclose(loss_functions.MSE_Amplitude(a, b).numpy(), ((abs(an) - abs(bn)) ** 2).sum((1, 2)) / 64)
+    assert np.allclose(loss_functions.MSE_Phase(a, b).numpy(), ((np.angle(an) - np.angle(bn)) ** 2).sum((1, 2)) / 64)
+    m, per = loss_functions.mean_batch_MSE_Intensity(a, b)
+    assert np.allclose(float(m), per.numpy().mean())
+
+
+# ----------------------------------------------------------------------------------------------- tables on the oracle seam
+@pytest.fixture
+def oracle_seam(monkeypatch):
+    """Route the three seam functions the tables call to the complex128 torch oracle (CPU)."""
+    def vrs(Ex, Ey, z, x0, y0, dx, dy, k):
+        n = Ex.shape[-1]
+        x = x0 + dx * np.arange(n)
+        y = y0 + dy * np.arange(n)
+        return ot.VRS_propagation(Ex, Ey, x, y, 2 * math.pi / k, z)
+
+    def focus(Ex, Ey, radius, f, wavelength, x, y, xout, yout):
+        return ot.VCZT_objective_lens(Ex, Ey, x, y, wavelength, radius, f, xout, yout)
+
+    def rs(field, z, dx, dy, k):
+        n = field.shape[-1]
+        x = dx * (np.arange(n) - (n - 1) / 2)
+        return torch.stack([ot.RS_propagation(f, x, x, 2 * math.pi / k, z) for f in field.reshape(-1, n, n)]).reshape(field.shape)
+    monkeypatch.setattr(ops, "vrs_propagation", vrs)
+    monkeypatch.setattr(ops, "highna_focus", focus)
+    monkeypatch.setattr(ops, "rs_propagation", rs)
+
+
+def sharp_focus_problem(g, device, cdtype):
+    x, lam = g["x"], float(g["wavelength"])
+    ls = xb.PolarizedLightSource(x, x, lam, device=device)
+    ls.Ex = torch.as_tensor(g["Ex"]).to(device=device, dtype=cdtype)
+    ls.Ey = torch.as_tensor(g["Ey"]).to(device=device, dtype=cdtype)
+    ls.Ez = torch.zeros_like(ls.Ex)
+    params = [torch.tensor(g["p%02d" % i], dtype=torch.float64, device=device, requires_grad=True) for i in range(29)]
+    fixed = [float(g["radius"]), float(g["f"]), g["xout"], g["xout"]]
+    return ls, params, fixed
+
+
+def sharp_focus_losses(g, ls, params, fixed):
+    inten, dets = oe.hybrid_setup_sharp_focus(ls, ls, ls, ls, ls, ls, params, fixed)
+    lv = loss_functions.vectorized_loss_hybrid(inten.to(torch.float64))
+    W = torch.as_tensor(g["W"], device=lv.device)
+    return inten, lv, softmin(lv), (W * inten.to(torch.float64)).sum()     # small-area loss; smooth surrogate sum(W * I)
+
+
+def directional(g, params, grads, tag, fmt="v_%s_%02d"):
+    return sum(float((gr.cpu() * torch.as_tensor(g[fmt % (tag, i)])).sum()) for i, gr in enumerate(grads) if gr is not None)
+
+
+def test_sharp_focus_table_matches_reference_on_oracle_seam(oracle_seam):
+    g = golden("sharp_focus_n32")
+    ls, params, fixed = sharp_focus_problem(g, "cpu", torch.complex128)
+    inten, lv, l_soft, l_lin = sharp_focus_losses(g, ls, params, fixed)
+    assert rel_l2(inten.detach().numpy(), g["intensities"]) < 1e-8      # k*z ~ 1e7 rad in float64
+    assert np.allclose(lv.detach().numpy(), g["loss_vec"], rtol=1e-7)
+    assert abs(float(l_soft.detach()) - float(g["loss_softmin"])) < 1e-7 * abs(float(g["loss_softmin"]))
+    assert abs(float(l_lin.detach()) - float(g["loss_linear"])) < 1e-8 * abs(float(g["loss_linear"]))
+    gl = torch.autograd.grad(l_lin, params, retain_graph=True, allow_unused=True)
+    gm = torch.autograd.grad(l_soft, params, allow_unused=True)
+    for tag in ("all", "dist", "other"):
+        want = float(g["dlin_" + tag])
+        assert abs(directional(g, params, gl, tag) - want) < 1e-5 * abs(want), tag       # finite differences of the fixture
+    want = float(g["dsoft_other"])
+    assert abs(directional(g, params, gm, "other") - want) < 1e-5 * abs(want)
+
+
+def four_f_problem(g, device, cdtype):
+    x, lam = g["x"], float(g["wavelength"])
+    src = xb.LightSource(x, x, lam, device=device)
+    src.field = torch.as_tensor(g["beam"]).to(device=device, dtype=cdtype)
+    params = [torch.tensor(g["p%d" % i], dtype=torch.float64, device=device, requires_grad=True) for i in range(5)]
+    rd = torch.float64 if cdtype == torch.complex128 else torch.float32
+    masks = torch.as_tensor(g["masks"]).to(device=device, dtype=cdtype)
+    targets = torch.as_tensor(g["targets"]).to(device=device, dtype=rd)
+    return src, params, masks, targets
+
+
+def test_four_f_table_matches_reference_on_oracle_seam(oracle_seam):
+    g = golden("four_f_n32")
+    src, params, masks, targets = four_f_problem(g, "cpu", torch.complex128)
+    inten, slm1, slm2 = four_f.vector_dualSLM_4f_system(masks, src, params)
+    assert rel_l2(inten.detach().numpy(), g["intensities"]) < 1e-8      # k*z ~ 1e7 rad in float64
+    one, _, _ = four_f.batch_dualSLM_4f(masks[1], src, params)
+    assert rel_l2(one.detach().numpy(), g["intensities"][1]) < 1e-8
+    loss = four_f.loss_dualSLM(params, masks, targets, src)
+    assert abs(float(loss) - float(g["loss"])) < 1e-8 * abs(float(g["loss"]))
+    grads = torch.autograd.grad(loss, params)
+    for tag in ("dist", "phase"):
+        want = float(g["dloss_" + tag])
+        assert abs(directional(g, params, grads, tag, "v_%s_%d") - want) < 2e-4 * abs(want), tag

@@ -460,3 +460,55 @@ def test_vrs_large_grid_route_equals_fused_path(xb):
         ops.FUSED_MAX_N = old
     assert rel_l2(o_big.cpu().numpy(), o_ref.cpu().numpy()) < 2e-6
     assert rel_l2(g_big.cpu().numpy(), g_ref.cpu().numpy()) < 2e-6
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cache", [0, 8])
+def test_sharp_focus_table_matches_reference(xb, cache):
+    """BASELINE config 3 at reduced size: hybrid_setup_sharp_focus (16 VRS + 6 objective focusings between beam splitters,
+    sSLMs and wave plates, optical_elements.py:1503-1649) + small_area_hybrid + softmin against the fixture produced by the
+    reference's own source; loss gradients w.r.t. all 29 parameters against the fixture's finite differences.  With the
+    transfer-function cache on, the repeated distances reuse one transfer function (same results required)."""
+    import torch
+    from xlumina_b200 import ops
+    from test_elements import directional, sharp_focus_losses, sharp_focus_problem
+    g = golden("sharp_focus_n32")
+    ops.set_transfer_cache(cache)
+    try:
+        ls, params, fixed = sharp_focus_problem(g, "cuda", torch.complex64)
+        inten, lv, l_soft, l_lin = sharp_focus_losses(g, ls, params, fixed)
+        gl = torch.autograd.grad(l_lin, params, retain_graph=True, allow_unused=True)
+        gm = torch.autograd.grad(l_soft, params, allow_unused=True)
+    finally:
+        ops.set_transfer_cache(0)
+    e_int = rel_l2(inten.detach().cpu().numpy(), g["intensities"])
+    errs = {t: abs(directional(g, params, gl, t) - float(g["dlin_" + t])) / abs(float(g["dlin_" + t])) for t in ("all", "dist", "other")}
+    e_soft = abs(directional(g, params, gm, "other") - float(g["dsoft_other"])) / abs(float(g["dsoft_other"]))
+    print("sharp focus table: intensities", e_int, "gradients", errs, e_soft)
+    assert e_int < 1e-4
+    assert np.allclose(lv.detach().cpu().numpy(), g["loss_vec"], rtol=1e-3)
+    assert abs(float(l_soft.detach()) - float(g["loss_softmin"])) < 1e-3 * abs(float(g["loss_softmin"]))
+    assert max(errs.values()) < 1e-3 and e_soft < 1e-3
+
+
+@pytest.mark.gpu
+def test_four_f_module_matches_reference_fixture(xb):
+    """BASELINE config 4 at reduced size through xlumina_b200.four_f against the fixture produced by the reference's
+    experiments/four_f_optical_table.py (intensities, batch loss, finite-difference directional derivatives)."""
+    import torch
+    from xlumina_b200 import four_f
+    from test_elements import directional, four_f_problem
+    g = golden("four_f_n32")
+    src, params, masks, targets = four_f_problem(g, "cuda", torch.complex64)
+    inten, _, _ = four_f.vector_dualSLM_4f_system(masks, src, params)
+    loss = four_f.loss_dualSLM(params, masks, targets, src)
+    grads = torch.autograd.grad(loss, params)
+    e_int = rel_l2(inten.detach().cpu().numpy(), g["intensities"])
+    errs = {t: abs(directional(g, params, grads, t, "v_%s_%d") - float(g["dloss_" + t])) / abs(float(g["dloss_" + t])) for t in ("dist", "phase")}
+    print("4f table: intensities", e_int, "gradients", errs)
+    assert e_int < 1e-4
+    assert abs(float(loss.detach()) - float(g["loss"])) < 1e-4 * abs(float(g["loss"]))
+    assert errs["phase"] < 1e-4
+    # distance gradients of a phase-blind (intensity) loss are cancellation residues: see the comment in
+    # test_four_f_table_loss_and_shared_parameter_gradients and DESIGN.md section 2
+    assert errs["dist"] < 3e-3

@@ -19,3 +19,8 @@ def is_conserving_energy(light_source, propagated_light):
         i0 = sum(torch.sum(torch.abs(c ** 2)) for c in (light_source.Ex, light_source.Ey, light_source.Ez))
         i1 = sum(torch.sum(torch.abs(c ** 2)) for c in (propagated_light.Ex, propagated_light.Ey, propagated_light.Ez))
     return i1 / i0
+
+
+def softmin(args, beta=90):
+    """Differentiable min: -logsumexp(-beta * args) / beta.  Reference: toolbox.py:98-103."""
+    return -torch.logsumexp(-beta * args.reshape(-1), dim=0) / beta

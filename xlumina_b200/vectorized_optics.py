@@ -28,17 +28,20 @@ def VCZT_jit(Ex, Ey, z, wavelength, x, y, xout, yout):
 class VectorizedLight:
     """(Ex, Ey, Ez) on a square grid.  Reference: vectorized_optics.py:36-49."""
 
-    def __init__(self, x=None, y=None, wavelength=None, device=None):
+    def __init__(self, x=None, y=None, wavelength=None, device=None, _alloc=True):
         self.x = x
         self.y = y
         self.wavelength = wavelength
         self.k = 2 * math.pi / wavelength
         self.n = 1
         self.device = torch.device(device or DEFAULT_DEVICE)
-        shape = (len(y), len(x))
-        self.Ex = torch.zeros(shape, dtype=torch.complex64, device=self.device)
-        self.Ey = torch.zeros(shape, dtype=torch.complex64, device=self.device)
-        self.Ez = torch.zeros(shape, dtype=torch.complex64, device=self.device)
+        if _alloc:
+            shape = (len(y), len(x))
+            self.Ex = torch.zeros(shape, dtype=torch.complex64, device=self.device)
+            self.Ey = torch.zeros(shape, dtype=torch.complex64, device=self.device)
+            self.Ez = torch.zeros(shape, dtype=torch.complex64, device=self.device)
+        else:   # the caller assigns all three planes right away (skips three N^2 memsets per element of a table)
+            self.Ex = self.Ey = self.Ez = None
         self.info = 'Vectorized light'
 
     @property
@@ -55,7 +58,7 @@ class VectorizedLight:
         nx, ny, dx, dy = build_grid(self.x, self.y)
         quality_factor = _quality_factor(self.x, self.y, self.wavelength, z)
         E = VRS_propagation_jit(self.Ex, self.Ey, z, nx, ny, float(self.x[0]), float(self.y[0]), dx, dy, self.k)
-        out = VectorizedLight(self.x, self.y, self.wavelength, self.device)
+        out = VectorizedLight(self.x, self.y, self.wavelength, self.device, _alloc=False)
         out.Ex, out.Ey, out.Ez = E[0], E[1], E[2]
         if _wo.VERBOSE:
             print(f"Time taken to perform one VRS propagation (in seconds): {(time.perf_counter() - tic):.4f}")
@@ -81,7 +84,7 @@ class VectorizedLight:
         if yout is None:
             yout = self.y
         E = VCZT_jit(self.Ex, self.Ey, z, self.wavelength, self.x, self.y, xout, yout)
-        out = VectorizedLight(xout, yout, self.wavelength, self.device)
+        out = VectorizedLight(xout, yout, self.wavelength, self.device, _alloc=False)
         out.Ex, out.Ey, out.Ez = E[0], E[1], E[2]
         if _wo.VERBOSE:
             print(f"Time taken to perform one VCZT propagation (in seconds):  {(time.perf_counter() - tic):.4f}")

@@ -60,14 +60,15 @@ def CZT_jit(field, z, wavelength, x, y, xout, yout):
 class ScalarLight:
     """Scalar complex amplitude on a square grid.  Reference: wave_optics.py:43-54."""
 
-    def __init__(self, x, y, wavelength, device=None):
+    def __init__(self, x, y, wavelength, device=None, _alloc=True):
         self.x = x
         self.y = y
         self.wavelength = wavelength
         self.k = 2 * math.pi / wavelength
         self.n = 1
         self.device = torch.device(device or DEFAULT_DEVICE)
-        self.field = torch.zeros((len(y), len(x)), dtype=torch.complex64, device=self.device)
+        # _alloc=False: the caller assigns the field right away (skips one N^2 memset per element of a table)
+        self.field = torch.zeros((len(y), len(x)), dtype=torch.complex64, device=self.device) if _alloc else None
         self.info = 'Wave optics light'
 
     @property
@@ -83,7 +84,7 @@ class ScalarLight:
         tic = time.perf_counter()
         nx, ny, dx, dy = build_grid(self.x, self.y)
         quality_factor = _quality_factor(self.x, self.y, self.wavelength, z)
-        out = ScalarLight(self.x, self.y, self.wavelength, self.device)
+        out = ScalarLight(self.x, self.y, self.wavelength, self.device, _alloc=False)
         out.field = RS_propagation_jit(self.field, z, nx, ny, dx, dy, self.k)
         if VERBOSE:
             print(f"Time taken to perform one RS propagation (in seconds): {(time.perf_counter() - tic):.4f}")
@@ -108,7 +109,7 @@ class ScalarLight:
             xout = self.x
         if yout is None:
             yout = self.y
-        out = ScalarLight(xout, yout, self.wavelength, self.device)
+        out = ScalarLight(xout, yout, self.wavelength, self.device, _alloc=False)
         out.field = CZT_jit(self.field, z, self.wavelength, self.x, self.y, xout, yout)
         if VERBOSE:
             print(f"Time taken to perform one CZT propagation (in seconds): {(time.perf_counter() - tic):.4f}")
