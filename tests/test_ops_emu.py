@@ -69,3 +69,48 @@ def test_four_f_table_complex64(ops_on_emu):
     assert e_int < 1e-4
     assert abs(float(loss.detach()) - float(g["loss"])) < 1e-4 * abs(float(g["loss"]))
     assert max(errs.values()) < 1e-3
+
+
+def test_leading_batch_axes_and_per_item_distances(ops_on_emu):
+    """What the reference reaches with vmap (a table vmapped over masks / noisy distances): batches are independent calls,
+    a shared z shares the transfer function, a z per item is honoured, gradients flow to every item and every distance."""
+    rng = np.random.default_rng(11)
+    N, M = 16, 12
+    x = np.linspace(-300.0, 300.0, N)
+    xo = np.linspace(-40.0, 40.0, M)
+    dx, lam = float(x[1] - x[0]), 0.6328
+    k = 2 * np.pi / lam
+    c = lambda *s: torch.tensor((rng.standard_normal(s) + 1j * rng.standard_normal(s)).astype(np.complex64))   # noqa: E731
+    u = c(3, N, N).requires_grad_(True)
+    zs = torch.tensor([2000.0, 2500.0, -1800.0], dtype=torch.float64, requires_grad=True)
+    ct = c(3, N, N)
+    out = ops.rs_propagation(u, zs, dx, dx, k)
+    (out * ct).real.sum().backward()
+    for i in range(3):
+        ui = u.detach()[i].clone().requires_grad_(True)
+        zi = zs.detach()[i:i + 1].clone().requires_grad_(True)
+        oi = ops.rs_propagation(ui, zi, dx, dx, k)
+        (oi * ct[i]).real.sum().backward()
+        assert torch.equal(oi.detach(), out.detach()[i]) and torch.equal(ui.grad, u.grad[i])
+        assert float(zi.grad) == float(zs.grad[i])
+    with pytest.raises(ValueError):
+        ops.rs_propagation(u, zs[:2], dx, dx, k)
+
+    ex, ey = c(2, N, N).requires_grad_(True), c(2, N, N)
+    for z in (3000.0, torch.tensor([3000.0, 3300.0], dtype=torch.float64)):
+        ob = ops.vrs_propagation(ex, ey, z, float(x[0]), float(x[0]), dx, dx, k)
+        assert ob.shape == (2, 3, N, N)
+        for i in range(2):
+            zi = z if isinstance(z, float) else z[i:i + 1]
+            assert torch.equal(ob[i], ops.vrs_propagation(ex[i], ey[i], zi, float(x[0]), float(x[0]), dx, dx, k))
+    ob = ops.vrs_propagation(torch.stack([ex, ey], dim=1), None, 3000.0, float(x[0]), float(x[0]), dx, dx, k)
+    assert torch.equal(ob[1], ops.vrs_propagation(ex[1], ey[1], 3000.0, float(x[0]), float(x[0]), dx, dx, k))
+    g, = torch.autograd.grad((ob * c(2, 3, N, N)).real.sum(), ex)
+    assert g.shape == ex.shape and float(g.abs().min()) > 0
+
+    cb = ops.czt(u.detach(), torch.tensor([9000.0, 9500.0, 8000.0], dtype=torch.float64), lam, x, x, xo, xo)
+    assert cb.shape == (3, M, M) and torch.equal(cb[2], ops.czt(u.detach()[2], 8000.0, lam, x, x, xo, xo))
+    vb = ops.vczt(ex.detach(), ey, 9000.0, lam, x, x, xo, xo)
+    assert vb.shape == (2, 3, M, M) and torch.equal(vb[1], ops.vczt(ex.detach()[1], ey[1], 9000.0, lam, x, x, xo, xo))
+    hb = ops.highna_focus(ex.detach(), ey, 250.0, 400.0, lam, x, x, xo, xo)
+    assert hb.shape == (2, 3, M, M) and torch.equal(hb[0], ops.highna_focus(ex.detach()[0], ey[0], 250.0, 400.0, lam, x, x, xo, xo))

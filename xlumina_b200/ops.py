@@ -54,11 +54,22 @@ def _workspace(ref, nbytes):
 _z_cache = {}
 
 
+def _z_per_item(z, batch):
+    """None if `z` is one distance shared by the whole batch; else the list of `batch` per-item distances (the reference
+    reaches this case by vmapping a table over per-sample distances, e.g. noisy optical tables)."""
+    if not isinstance(z, torch.Tensor) or z.numel() == 1:
+        return None
+    if z.numel() != batch:
+        raise ValueError(f"z has {z.numel()} elements for a batch of {batch} fields: pass one distance or one per field")
+    zf = z.reshape(-1)
+    return [zf[i:i + 1] for i in range(batch)]
+
+
 def _as_z(z, ref):
     """Propagation distance as ONE float64 on the device (a traced value in the reference, wave_optics.py:281)."""
     if isinstance(z, torch.Tensor):
         if z.numel() != 1:
-            raise ValueError("z must have exactly one element (shape () or (1,)); batch over z with a loop")
+            raise ValueError("z must have exactly one element here (shape () or (1,))")
         return z.to(device=ref.device, dtype=torch.float64).reshape(1)
     key = (float(z), ref.device)
     t = _z_cache.get(key)
@@ -185,12 +196,17 @@ class _VRS(torch.autograd.Function):
     """exy (2,N,N) -> (3,N,N); Ez = (Ex X + Ey Y)/r formed at load (vectorized_optics.py:258-261)."""
 
     @staticmethod
-    def forward(ctx, exy, z, x0, y0, dx, dy, k, zkey=None, zobj=None):
+    def forward(ctx, exy, z, x0, y0, dx, dy, k, zkey=None, zobj=None, hshare=None):
         _require_device(exy)
         L = _lib.lib()
         N = exy.shape[-1]
         out = torch.empty((3, N, N), dtype=exy.dtype, device=exy.device)
-        H, reuse = _cached_transfer(zkey, zobj, N, dx, dy, k, exy.device, L.xl_rs_transfer_bytes(N))
+        if hshare is not None and hshare[0] is not None:       # later item of a batch that shares z: reuse its transfer function
+            H, reuse = hshare[0], True
+        else:
+            H, reuse = _cached_transfer(zkey, zobj, N, dx, dy, k, exy.device, L.xl_rs_transfer_bytes(N))
+            if hshare is not None:
+                hshare[0] = H
         ws = _workspace(exy, L.xl_rs_workspace_bytes(N, 3, 0))
         _lib.check(L.xl_vrs_fwd(_ptr(exy), _ptr(out), _ptr(H), _ptr(z), N, x0, y0, dx, dy, k, _lib.XL_REUSE_H if reuse else 0,
                                 _ptr(ws), ws.numel(), _stream(exy)), "xl_vrs_fwd")
@@ -211,7 +227,7 @@ class _VRS(torch.autograd.Function):
         ws = _workspace(exy, L.xl_rs_workspace_bytes(N, 3, 1 if want_z else 0))
         _lib.check(L.xl_vrs_bwd(_ptr(exy), _ptr(out), _ptr(g), _ptr(gin), _ptr(gz), _ptr(H), _ptr(z), N, x0, y0, dx, dy, k,
                                 _lib.XL_CONJ_IN | _lib.XL_CONJ_OUT, _ptr(ws), ws.numel(), _stream(exy)), "xl_vrs_bwd")
-        return gin, gz, None, None, None, None, None, None, None
+        return gin, gz, None, None, None, None, None, None, None, None
 
 
 FUSED_MAX_N = 2048   # largest grid of the fused single-pass path (padded length 4096); above it: the stage chain of slab.py
@@ -246,12 +262,17 @@ class _RSLarge(torch.autograd.Function):
 
 def rs_propagation(field, z, dx, dy, k):
     """Scalar Rayleigh-Sommerfeld propagation of `field` (..., N, N) over distance z (differentiable in field and z; above
-    FUSED_MAX_N^2 in the field only)."""
+    FUSED_MAX_N^2 in the field only).  `z`: one distance shared by all the fields (one transfer function, one library call),
+    or a tensor with one distance per field."""
     dt = field.dtype
     N = field.shape[-1]
     if field.shape[-2] != N:
         raise ValueError("RS propagation needs square fields")
     f = _c64(field).reshape(-1, N, N)
+    zs = _z_per_item(z, f.shape[0])
+    if zs is not None:                      # one distance per field: one call each (every item has its own transfer function)
+        out = torch.stack([rs_propagation(f[i], zs[i], dx, dy, k) for i in range(f.shape[0])]).reshape(field.shape)
+        return out if dt == torch.complex64 or not torch.is_complex(field) else out.to(dt)
     zt = _as_z(z, f)
     if N > FUSED_MAX_N:
         out = _RSLarge.apply(f, zt, float(dx), float(dy), float(k)).reshape(field.shape)
@@ -260,8 +281,20 @@ def rs_propagation(field, z, dx, dy, k):
     return out if dt == torch.complex64 or not torch.is_complex(field) else out.to(dt)
 
 
-def vrs_propagation(Ex, Ey, z, x0, y0, dx, dy, k):
-    """Vectorial RS: returns (3,N,N) = propagated [Ex, Ey, Ez].  Pass Ey=None if `Ex` is already the stacked (2,N,N) pair."""
+def _batch_of_pairs(fn, Ex, Ey, z):
+    """Leading batch axis for the vectorial operators: Ex, Ey (B,N,N) or a stacked (B,2,N,N) -> (B,3,...); `z` shared
+    or one per item.  Items are independent library calls; fn(ex, ey, z, hshare)."""
+    B = Ex.shape[0]
+    zs = _z_per_item(z, B)
+    hshare = [None] if zs is None else None
+    return torch.stack([fn(Ex[i], None if Ey is None else Ey[i], z if zs is None else zs[i], hshare) for i in range(B)])
+
+
+def vrs_propagation(Ex, Ey, z, x0, y0, dx, dy, k, _hshare=None):
+    """Vectorial RS: returns (3,N,N) = propagated [Ex, Ey, Ez].  Pass Ey=None if `Ex` is already the stacked (2,N,N) pair.
+    With a leading batch axis (Ex, Ey (B,N,N) or stacked (B,2,N,N)) returns (B,3,N,N); z shared or one per item."""
+    if Ex.dim() == (4 if Ey is None else 3):
+        return _batch_of_pairs(lambda a, b, zz, hs: vrs_propagation(a, b, zz, x0, y0, dx, dy, k, hs), Ex, Ey, z)
     dt = Ex.dtype
     exy = _c64(Ex) if Ey is None else torch.stack([_c64(Ex), _c64(Ey)], dim=0)
     zt = _as_z(z, exy)
@@ -276,7 +309,7 @@ def vrs_propagation(Ex, Ey, z, x0, y0, dx, dy, k):
         out = _RSLarge.apply(torch.stack([exy[0], exy[1], ez]), zt, float(dx), float(dy), float(k))
         return out if dt == torch.complex64 or not torch.is_complex(Ex) else out.to(dt)
     out = _VRS.apply(exy, zt, float(x0), float(y0), float(dx), float(dy), float(k),
-                     _z_key(z) if _transfer_cache_size else None, z)
+                     _z_key(z) if _transfer_cache_size else None, z, _hshare)
     return out if dt == torch.complex64 or not torch.is_complex(Ex) else out.to(dt)
 
 
@@ -373,7 +406,11 @@ def _gin(x, y, N):
 
 
 def czt(field, z, wavelength, x, y, xout, yout):
-    """Scalar chirped z-transform propagation (N,N) -> (len(yout), len(xout)); differentiable in `field`."""
+    """Scalar chirped z-transform propagation (N,N) -> (len(yout), len(xout)); differentiable in `field`.
+    A leading batch axis (B,N,N) is propagated item by item (z shared or one per item)."""
+    if field.dim() == 3:
+        zs = _z_per_item(z, field.shape[0])
+        return torch.stack([czt(field[i], z if zs is None else zs[i], wavelength, x, y, xout, yout) for i in range(field.shape[0])])
     dt = field.dtype
     f = _c64(field)
     out = _CZT.apply(f, _as_z(z, f).detach(), float(wavelength), 0, _gin(x, y, f.shape[-1]), _gout(xout, yout))
@@ -382,7 +419,9 @@ def czt(field, z, wavelength, x, y, xout, yout):
 
 def vczt(Ex, Ey, z, wavelength, x, y, xout, yout):
     """Vectorial CZT: (Ex,Ey) -> (3, len(yout), len(xout)); Ez = ((Ex X + Ey Y)/r) z/r formed at load.
-    Pass Ey=None if `Ex` is already the stacked (2,N,N) pair."""
+    Pass Ey=None if `Ex` is already the stacked (2,N,N) pair; a leading batch axis gives (B,3,...)."""
+    if Ex.dim() == (4 if Ey is None else 3):
+        return _batch_of_pairs(lambda a, b, zz, hs: vczt(a, b, zz, wavelength, x, y, xout, yout), Ex, Ey, z)
     dt = Ex.dtype
     exy = _c64(Ex) if Ey is None else torch.stack([_c64(Ex), _c64(Ey)], dim=0)
     out = _CZT.apply(exy, _as_z(z, exy).detach(), float(wavelength), 1, _gin(x, y, exy.shape[-1]), _gout(xout, yout))
@@ -391,7 +430,9 @@ def vczt(Ex, Ey, z, wavelength, x, y, xout, yout):
 
 def highna_focus(Ex, Ey, radius, f, wavelength, x, y, xout, yout):
     """High-NA objective + Debye integral by 2-pass Bluestein: (Ex,Ey) -> focal-plane (3, len(yout), len(xout)).
-    Pass Ey=None if `Ex` is already the stacked (2,N,N) pair."""
+    Pass Ey=None if `Ex` is already the stacked (2,N,N) pair; a leading batch axis gives (B,3,...)."""
+    if Ex.dim() == (4 if Ey is None else 3):
+        return _batch_of_pairs(lambda a, b, zz, hs: highna_focus(a, b, radius, f, wavelength, x, y, xout, yout), Ex, Ey, None)
     dt = Ex.dtype
     exy = _c64(Ex) if Ey is None else torch.stack([_c64(Ex), _c64(Ey)], dim=0)
     out = _HighNA.apply(exy, float(radius), float(f), float(wavelength), _gin(x, y, exy.shape[-1]), _gout(xout, yout))
