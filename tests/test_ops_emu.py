@@ -114,3 +114,79 @@ def test_leading_batch_axes_and_per_item_distances(ops_on_emu):
     assert vb.shape == (2, 3, M, M) and torch.equal(vb[1], ops.vczt(ex.detach()[1], ey[1], 9000.0, lam, x, x, xo, xo))
     hb = ops.highna_focus(ex.detach(), ey, 250.0, 400.0, lam, x, x, xo, xo)
     assert hb.shape == (2, 3, M, M) and torch.equal(hb[0], ops.highna_focus(ex.detach()[0], ey[0], 250.0, 400.0, lam, x, x, xo, xo))
+
+
+# --------------------------------------------------------------------------- randomised: torch-convention gradients vs autograd
+from hypothesis import given, settings, strategies as st, HealthCheck   # noqa: E402
+from oracle import oracle_torch as ot   # noqa: E402
+
+
+def _crand(rng, *s):
+    return (rng.standard_normal(s) + 1j * rng.standard_normal(s))
+
+
+def _grads(loss, leaves):
+    return [g.detach().numpy() for g in torch.autograd.grad(loss, leaves)]
+
+
+@settings(max_examples=12, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
+@given(N=st.integers(4, 28), half=st.floats(100.0, 2000.0), zmag=st.floats(500.0, 1e5), neg=st.booleans(),
+       vect=st.booleans(), seed=st.integers(0, 2 ** 16))
+def test_rs_vrs_autograd_random(ops_on_emu, N, half, zmag, neg, vect, seed):
+    """Gradients delivered to torch (field: conj-of-JAX convention; z) equal autograd through the complex128 oracle for a
+    generic complex-weighted loss Re sum(w * out)."""
+    rng = np.random.default_rng(seed)
+    x = np.linspace(-half, half, N)
+    dx, lam = float(x[1] - x[0]), 0.6328
+    k, zv = 2 * np.pi / lam, (-zmag if neg else zmag)
+    nf = 2 if vect else 1
+    u0, w0 = _crand(rng, nf, N, N), _crand(rng, 3 if vect else 1, N, N)
+
+    def run(cdtype, fwd):
+        u = torch.tensor(u0, dtype=cdtype, requires_grad=True)
+        z = torch.tensor([zv], dtype=torch.float64, requires_grad=True)
+        out = fwd(u, z)
+        loss = (torch.tensor(w0, dtype=cdtype) * out).real.sum()
+        return [out.detach().numpy()] + _grads(loss, (u, z))
+    if vect:
+        got = run(torch.complex64, lambda u, z: ops.vrs_propagation(u[0], u[1], z, float(x[0]), float(x[0]), dx, dx, k))
+        ref = run(torch.complex128, lambda u, z: ot.VRS_propagation(u[0], u[1], x, x, lam, z))
+    else:
+        got = run(torch.complex64, lambda u, z: ops.rs_propagation(u, z, dx, dx, k))
+        ref = run(torch.complex128, lambda u, z: ot.RS_propagation(u[0], x, x, lam, z)[None])
+    assert rel_l2(got[0], ref[0]) < 2e-5 and rel_l2(got[1], ref[1]) < 2e-5
+    scale = k * np.linalg.norm(w0) * np.linalg.norm(ref[0])       # natural size of d/dz (the i*k*out part)
+    assert abs(got[2].item() - ref[2].item()) < 2e-5 * scale + 1e-4 * abs(ref[2].item())
+
+
+@settings(max_examples=12, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
+@given(N=st.integers(4, 28), Mx=st.integers(2, 30), My=st.integers(2, 30), kind=st.sampled_from(["czt", "vczt", "highna"]),
+       seed=st.integers(0, 2 ** 16))
+def test_czt_family_autograd_random(ops_on_emu, emu, N, Mx, My, kind, seed):
+    if emu.xl_czt_padded_length(N, Mx) == 0 or emu.xl_czt_padded_length(N, My) == 0:
+        return                                                     # m+M-1 a power of two: the reference raises as well
+    rng = np.random.default_rng(seed)
+    N += N & 1 if kind == "highna" else 0                          # odd N: the reference's 0/0 at the origin pixel (NaN)
+    if emu.xl_czt_padded_length(N, Mx) == 0 or emu.xl_czt_padded_length(N, My) == 0:
+        return
+    x = np.linspace(-600.0, 600.0, N)
+    xo, yo = np.linspace(-50.0, 40.0, Mx), np.linspace(-30.0, 50.0, My)
+    lam, z = 0.6328, 20000.0
+    nf = 1 if kind == "czt" else 2
+    u0, w0 = _crand(rng, nf, N, N), _crand(rng, 1 if kind == "czt" else 3, My, Mx)
+
+    def run(cdtype, fwd):
+        u = torch.tensor(u0, dtype=cdtype, requires_grad=True)
+        out = fwd(u)
+        loss = (torch.tensor(w0, dtype=cdtype) * out).real.sum()
+        return [out.detach().numpy()] + _grads(loss, (u,))
+    if kind == "czt":
+        got = run(torch.complex64, lambda u: ops.czt(u[0], z, lam, x, x, xo, yo)[None])
+        ref = run(torch.complex128, lambda u: ot.CZT(u[0], x, x, lam, z, xo, yo)[None])
+    elif kind == "vczt":
+        got = run(torch.complex64, lambda u: ops.vczt(u[0], u[1], z, lam, x, x, xo, yo))
+        ref = run(torch.complex128, lambda u: ot.VCZT(u[0], u[1], x, x, lam, z, xo, yo))
+    else:
+        got = run(torch.complex64, lambda u: ops.highna_focus(u[0], u[1], 500.0, 700.0, lam, x, x, xo, yo))
+        ref = run(torch.complex128, lambda u: ot.VCZT_objective_lens(u[0], u[1], x, x, lam, 500.0, 700.0, xo, yo))
+    assert rel_l2(got[0], ref[0]) < 2e-5 and rel_l2(got[1], ref[1]) < 2e-5
