@@ -12,6 +12,9 @@ timeout 120 python -m pytest tests -m gpu -x -q > $OUT/pytest_gpu_$TAG.log 2>&1;
 timeout 60 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/smoke_$TAG.log 2>&1; tail -1 $OUT/smoke_$TAG.log
 timeout 150 python bench.py > $OUT/bench_${TAG}_final.json 2> $OUT/bench_${TAG}_final.err; tail -c 400 $OUT/bench_${TAG}_final.json
 timeout 90 python scripts/gpu_probe.py --nosmoke > $OUT/probe_$TAG.log 2>&1
+# BASELINE configs 3 and 4 as whole tables (value + gradient of the loss), one GPU
+timeout 90 python scripts/sharp_focus_table.py > $OUT/sharp_focus_$TAG.json 2> $OUT/sharp_focus_$TAG.err; tail -c 300 $OUT/sharp_focus_$TAG.json
+timeout 90 python scripts/four_f_sharded.py > $OUT/four_f_$TAG.json 2> $OUT/four_f_$TAG.err; tail -c 300 $OUT/four_f_$TAG.json
 # launch list of the bench command itself (cold cache + serialised: shares only)
 timeout 90 ncu --metrics gpu__time_duration.sum --clock-control none -k xl_kernel -c 500 --csv \
     --log-file $OUT/launches_$TAG.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > $OUT/bench_under_ncu.log 2>&1
