@@ -184,7 +184,8 @@ def highna_cases():
 
 def element_cases():
     """Pointwise elements (optical_elements.py:87-392, 678-703) on random fields: one fixture with every element's output."""
-    from xlumina.optical_elements import SLM, sSLM, sSLM_with_amplitude, LCD, linear_polarizer, BS_symmetric, lens
+    from xlumina.optical_elements import (SLM, sSLM, sSLM_with_amplitude, LCD, linear_polarizer, BS_symmetric, lens,
+                                          cylindrical_lens, axicon_lens)
     N, span, lam = 16, 900.0, 0.635
     x = np.linspace(-span, span, N)
     a = vector_light(x, x, lam, crand(N, N), crand(N, N))
@@ -200,12 +201,15 @@ def element_cases():
     c, d = BS_symmetric(a, b, bs_theta)
     l_s, lens_s = lens(scalar_light(x, x, lam, u), (700.0, 500.0), (4.0e4, 6.0e4))
     l_v, _ = lens(a, (700.0, 500.0), (4.0e4, 6.0e4))
+    _, cyl = cylindrical_lens(scalar_light(x, x, lam, u), 5.0e4, 1.5, 0.3)
+    ax_v, axi = axicon_lens(a, 0.05)
     save("elements_n16", x=x, wavelength=lam, a=comps(a), b=comps(b), alpha=alpha, phi=phi, A1=A1, A2=A2, eta=eta, theta=theta,
          bs_theta=bs_theta, pol=pol, u=u, slm_out=np.asarray(s_out.field), slm=np.asarray(slm),
          sslm=comps(sSLM(a, alpha, phi)), sslm_amp=comps(sSLM_with_amplitude(a, alpha, phi, A1, A2)),
          lcd=comps(LCD(a, eta, theta)), lp=comps(linear_polarizer(a, pol)), bs_c=comps(c), bs_d=comps(d),
          lens_radius=np.array([700.0, 500.0]), lens_focal=np.array([4.0e4, 6.0e4]), lens_scalar=np.asarray(l_s.field),
-         lens_mask=np.asarray(lens_s), lens_vector=comps(l_v))
+         lens_mask=np.asarray(lens_s), lens_vector=comps(l_v), cyl_mask=np.asarray(cyl), axicon_mask=np.asarray(axi),
+         axicon_vector=comps(ax_v))
 
 
 def table_cases():
@@ -291,7 +295,8 @@ if __name__ == "__main__":
     if "--tables-only" in sys.argv:           # adds the element/table fixtures without redrawing the propagator ones
         rng = np.random.default_rng(20261018)
         element_cases()
-        table_cases()
+        if "--elements-only" not in sys.argv:
+            table_cases()
         sys.exit(0)
     rs_cases()
     vrs_cases()

@@ -116,6 +116,23 @@ def test_leading_batch_axes_and_per_item_distances(ops_on_emu):
     assert hb.shape == (2, 3, M, M) and torch.equal(hb[0], ops.highna_focus(ex.detach()[0], ey[0], 250.0, 400.0, lam, x, x, xo, xo))
 
 
+def test_reference_propagating_element_tests(ops_on_emu):
+    """The reference's own tests of the elements that propagate (tests/test_optical_elements.py:128-136, 165-171:
+    VCZT_objective_lens and building_block shapes) at resolution 64 instead of 512."""
+    import math
+    import xlumina_b200 as xb
+    n, wavelength = 64, 633e-3
+    x = np.linspace(-1500, 1500, n)
+    light = xb.PolarizedLightSource(x, x, wavelength, device="cpu")
+    light.gaussian_beam(w0=(1200, 1200), jones_vector=(1, 0))
+    radius = 3.6 * 1e3 / 2
+    out = xb.VCZT_objective_lens(light, radius, radius / 0.9, x, x)
+    assert out.Ex.shape == out.Ey.shape == out.Ez.shape == (n, n)
+    out = xb.building_block(light, torch.zeros((n, n)), torch.zeros((n, n)), 1000, math.pi / 2, math.pi / 4)
+    assert out.Ex.shape == out.Ey.shape == out.Ez.shape == (n, n)
+    assert bool(torch.isfinite(out.Ex.abs()).all())
+
+
 # --------------------------------------------------------------------------- randomised: torch-convention gradients vs autograd
 from hypothesis import given, settings, strategies as st, HealthCheck   # noqa: E402
 from oracle import oracle_torch as ot   # noqa: E402

@@ -30,10 +30,11 @@ from .toolbox import space  # noqa: E402
 from .wave_optics import ScalarLight, LightSource  # noqa: E402
 from .vectorized_optics import VectorizedLight, PolarizedLightSource  # noqa: E402
 from .optical_elements import (VCZT_objective_lens, SLM, sSLM, sSLM_with_amplitude, LCD, linear_polarizer, BS_symmetric,  # noqa: E402
-                               lens, building_block, bb_amplitude_and_phase_mod, hybrid_setup_sharp_focus)
+                               lens, cylindrical_lens, axicon_lens, building_block, bb_amplitude_and_phase_mod,
+                               hybrid_setup_sharp_focus)
 from . import ops, loss_functions, four_f  # noqa: E402
 
 __all__ = ["um", "nm", "mm", "cm", "radians", "degrees", "space", "ScalarLight", "LightSource", "VectorizedLight",
            "PolarizedLightSource", "VCZT_objective_lens", "SLM", "sSLM", "sSLM_with_amplitude", "LCD", "linear_polarizer",
-           "BS_symmetric", "lens", "building_block", "bb_amplitude_and_phase_mod", "hybrid_setup_sharp_focus", "ops",
+           "BS_symmetric", "lens", "cylindrical_lens", "axicon_lens", "building_block", "bb_amplitude_and_phase_mod", "hybrid_setup_sharp_focus", "ops",
            "loss_functions", "four_f"]

@@ -168,27 +168,56 @@ def circular_mask(X, Y, r):
     return torch.where((X ** 2 / rx ** 2 + Y ** 2 / ry ** 2) < 1, 1, 0)
 
 
-def lens(input_field, radius, focal):
-    """Thin lens with a pupil of radii `radius` and focal lengths `focal` (both (x, y) pairs); returns (light, lens mask).
-    optical_elements.py:678-703.  The phase k*(X^2/2fx + Y^2/2fy) reaches 1e4-1e5 rad: evaluated in float64."""
-    fx, fy = focal
-    X = input_field.X.to(torch.float64)
-    Y = input_field.Y.to(torch.float64)
-    pupil = circular_mask(X, Y, radius)
-    ph = -input_field.k * (X ** 2 / (2 * fx) + Y ** 2 / (2 * fy))
+def _apply_mask(input_field, mask64):
+    """field * mask for scalar light, (Ex, Ey) * mask for vectorial light (Ez zero, as in the reference); `mask64` is a
+    complex128 plane built in float64 (lens phases reach 1e4-1e5 rad), cast once to the field dtype."""
     if input_field.info in ('Wave optics light', 'Wave optics light source'):
-        lens_ = (pupil * torch.polar(torch.ones_like(ph), ph)).to(input_field.field.dtype)
+        mask = mask64.to(input_field.field.dtype)
         out = ScalarLight(input_field.x, input_field.y, input_field.wavelength, input_field.device, _alloc=False)
-        out.field = input_field.field * lens_
+        out.field = input_field.field * mask
     elif input_field.info in ('Vectorized light', 'Vectorized light source'):
-        lens_ = (pupil * torch.polar(torch.ones_like(ph), ph)).to(input_field.Ex.dtype)
+        mask = mask64.to(input_field.Ex.dtype)
         out = _new_vector(input_field)
-        out.Ex = input_field.Ex * lens_
-        out.Ey = input_field.Ey * lens_
+        out.Ex = input_field.Ex * mask
+        out.Ey = input_field.Ey * mask
         out.Ez = _zeros_like_plane(input_field.Ex)
     else:
         raise ValueError("Invalid input. Please use ScalarLight or VectorizedLight object.")
-    return out, lens_
+    return out, mask
+
+
+def _unit_phasor(phase):
+    return torch.polar(torch.ones_like(phase), phase)
+
+
+def lens(input_field, radius, focal):
+    """Thin lens with a pupil of radii `radius` and focal lengths `focal` (both (x, y) pairs); returns (light, lens mask).
+    optical_elements.py:678-703."""
+    fx, fy = focal
+    X = input_field.X.to(torch.float64)
+    Y = input_field.Y.to(torch.float64)
+    ph = -input_field.k * (X ** 2 / (2 * fx) + Y ** 2 / (2 * fy))
+    return _apply_mask(input_field, circular_mask(X, Y, radius) * _unit_phasor(ph))
+
+
+def cylindrical_lens(input_field, focal_length, refractive_index=1.5, angle=0):
+    """Plano-convex cylindrical lens rotated by `angle`; returns (light, lens mask).  optical_elements.py:705-744."""
+    X = input_field.X.to(torch.float64)
+    Y = input_field.Y.to(torch.float64)
+    Xrot = X * math.cos(angle) + Y * math.sin(angle)
+    R = focal_length * (refractive_index - 1)
+    thickness = R - torch.sqrt(R ** 2 - Xrot ** 2)
+    phase = input_field.k * (refractive_index - 1) * (Xrot ** 2 / (2 * focal_length) + thickness)
+    return _apply_mask(input_field, _unit_phasor(-phase))
+
+
+def axicon_lens(input_field, alpha, n=1.5):
+    """Axicon of angle alpha (Bessel-beam generator); returns (light, axicon mask).  optical_elements.py:746-779."""
+    X = input_field.X.to(torch.float64)
+    Y = input_field.Y.to(torch.float64)
+    r = torch.sqrt(X ** 2 + Y ** 2)
+    phase_shift = input_field.k * r * (n - 1) * math.sin(alpha) * math.tan(alpha)
+    return _apply_mask(input_field, _unit_phasor(-phase_shift))
 
 
 # ------------------------------------------------------------------------------------------------------------------------
