@@ -240,3 +240,19 @@ def test_four_f_table_matches_reference_on_oracle_seam(oracle_seam):
     for tag in ("dist", "phase"):
         want = float(g["dloss_" + tag])
         assert abs(directional(g, params, grads, tag, "v_%s_%d") - want) < 2e-4 * abs(want), tag
+
+
+def test_reference_toolbox_tests_for_the_mirrored_helpers():
+    """tests/test_toolbox.py:33-56 of the reference (space, is_conserving_energy, softmin) on the mirror."""
+    from xlumina_b200.toolbox import is_conserving_energy, space
+    n = 128
+    x, y = space(1500, n)
+    assert np.allclose(x, np.linspace(-1500, 1500, n)) and np.allclose(y, np.linspace(-1500, 1500, n))
+    l1 = xb.VectorizedLight(x, y, 633e-3, device="cpu")
+    l2 = xb.VectorizedLight(x, y, 633e-3, device="cpu")
+    l1.Ex = torch.ones((n, n), dtype=torch.complex64)
+    l2.Ex = torch.ones((n, n), dtype=torch.complex64)
+    assert abs(float(is_conserving_energy(l1, l2)) - 1.0) < 1e-6
+    l2.Ex = 0 * l2.Ex
+    assert float(is_conserving_energy(l1, l2)) == 0
+    assert float(softmin(torch.tensor([1.0, 2.0, 3.0], dtype=torch.float64))) == 1.0
