@@ -65,3 +65,55 @@ def test_two_rank_gloo_shared_parameter_gradient(tmp_path):
     gc0 = np.load(tmp_path / "gc0.npy")
     assert np.allclose(gc0, 5 * 2 * (0.5 + 1.0j))            # torch convention for |pc|^2: 2*pc per unit
     assert int(np.load(tmp_path / "n0.npy")) + int(np.load(tmp_path / "n1.npy")) == 5
+
+
+def _four_f_worker(rank, world, port, emu_path, out_dir):
+    """BASELINE config 4 pattern on the real operators (host-emulated kernels): each rank evaluates the 4f table on its
+    slice of the masks with the SHARED parameters, gradients meet in one flattened all-reduce."""
+    import ctypes
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import sys
+        sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+        from conftest import golden
+        from test_elements import four_f_problem
+        from xlumina_b200 import _lib, four_f, ops
+        _lib._lib = _lib.declare(ctypes.CDLL(emu_path))          # test tooling: CPU tensors through the emulated kernels
+        ops._require_device = lambda t: None
+        ops._stream = lambda t: ctypes.c_void_p(0)
+        ops._stream_key = lambda t: ("cpu", 0)
+        g = golden("four_f_n32")
+        src, params, masks, targets = four_f_problem(g, "cpu", torch.complex64)
+        B = masks.shape[0]
+        a, b = shard_range(B, rank, world)
+        inten, _, _ = four_f.vector_dualSLM_4f_system(masks[a:b], src, params)
+        loss = four_f.MSE_Intensity(inten, targets[a:b]).sum() / B        # mean over the GLOBAL batch
+        loss.backward()
+        grads = allreduce_grads([p.grad for p in params])
+        total = loss.detach().clone()
+        dist.all_reduce(total)
+        np.savez(os.path.join(out_dir, f"r{rank}.npz"), loss=total.numpy(), **{f"g{i}": gr.numpy() for i, gr in enumerate(grads)})
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_four_f_table_equals_single_process(emu, tmp_path):
+    import ctypes
+    from conftest import golden, ROOT
+    emu_path = os.path.join(ROOT, "tests", "emu", "libxlprop_emu.so")
+    for world in (1, 2):
+        d = tmp_path / f"w{world}"
+        d.mkdir()
+        mp.spawn(_four_f_worker, args=(world, _free_port(), emu_path, str(d)), nprocs=world, join=True)
+    one = np.load(tmp_path / "w1" / "r0.npz")
+    g = golden("four_f_n32")
+    assert abs(float(one["loss"]) - float(g["loss"])) < 1e-4 * abs(float(g["loss"]))      # and equals the reference's loss
+    for rank in (0, 1):
+        two = np.load(tmp_path / "w2" / f"r{rank}.npz")
+        assert abs(float(two["loss"]) - float(one["loss"])) < 1e-6 * abs(float(one["loss"]))
+        for i in range(5):
+            # same kernels, different batch grouping: distances see fp32 summation-order noise of the cancelling terms only
+            tol = 2e-3 if i < 3 else 1e-5
+            assert np.linalg.norm(two[f"g{i}"] - one[f"g{i}"]) <= tol * np.linalg.norm(one[f"g{i}"]), i
