@@ -3,7 +3,7 @@
 #   /usr/local/graft/bin/gpurun --timeout 600 -- 'bash scripts/measure_round.sh r02'
 # then, back in the build container:   python scripts/make_profiles.py r02
 # Every step has its own timeout; only CSV/JSON/log summaries are written to gpurun_out/ (the .ncu-rep files stay in /tmp:
-# gpurun_out/ is limited to 64 MiB).  ~4 GPU-minutes.
+# gpurun_out/ is limited to 64 MiB).  ~8 GPU-minutes.
 set -u
 TAG=${1:-rXX}
 OUT=gpurun_out
@@ -25,5 +25,12 @@ ncu -i /tmp/prof_rsgrad_$TAG.ncu-rep --page raw --csv > $OUT/ncu_${TAG}_rsgrad_r
 timeout 180 ncu --set full --clock-control none -k xl_kernel -s 6 -c 6 -o /tmp/prof_cztgrad_$TAG \
     python scripts/prof_rs.py 2048 cztgrad 2 > $OUT/ncu_cztgrad.log 2>&1
 ncu -i /tmp/prof_cztgrad_$TAG.ncu-rep --page raw --csv > $OUT/ncu_${TAG}_cztgrad_raw.csv 2>/dev/null
+# shared-memory race and out-of-bounds checks of every kernel family at a small size (the host emulation runs the phases of
+# a CTA one after the other, so only the device can show a missing barrier)
+for m in grad vrsgrad cztgrad vczt; do
+    timeout 120 compute-sanitizer --tool racecheck --print-limit 5 python scripts/prof_rs.py 128 $m 1 > $OUT/racecheck_${m}_$TAG.log 2>&1
+    tail -2 $OUT/racecheck_${m}_$TAG.log
+done
+timeout 120 compute-sanitizer --tool memcheck --print-limit 5 python scripts/prof_rs.py 128 grad 1 > $OUT/memcheck_grad_$TAG.log 2>&1; tail -2 $OUT/memcheck_grad_$TAG.log
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active --format=csv > $OUT/smi_$TAG.txt
 du -sh $OUT
