@@ -6,7 +6,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc", "xl_api.cu")
-DEPS = [os.path.join(HERE, "csrc", f) for f in ("xl_api.cu", "xl_kernels.cuh", "xl_fft.cuh", "xl_platform.h")] + \
+DEPS = [os.path.join(HERE, "csrc", f) for f in ("xl_api.cu", "xl_kernels.cuh", "xl_long.cuh", "xl_fft.cuh", "xl_platform.h")] + \
        [os.path.join(os.path.dirname(HERE), "include", "xlprop.h")]
 OUT = os.path.join(HERE, "libxlprop.so")
 
