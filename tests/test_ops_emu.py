@@ -207,3 +207,19 @@ def test_czt_family_autograd_random(ops_on_emu, emu, N, Mx, My, kind, seed):
         got = run(torch.complex64, lambda u: ops.highna_focus(u[0], u[1], 500.0, 700.0, lam, x, x, xo, yo))
         ref = run(torch.complex128, lambda u: ot.VCZT_objective_lens(u[0], u[1], x, x, lam, 500.0, 700.0, xo, yo))
     assert rel_l2(got[0], ref[0]) < 2e-5 and rel_l2(got[1], ref[1]) < 2e-5
+
+
+def test_missing_distance_gradients_are_refused_not_dropped(ops_on_emu):
+    """CZT / VCZT have no d/dz: a distance that requires grad must raise, not lose its gradient silently."""
+    N = 8
+    x = np.linspace(-100.0, 100.0, N)
+    xo = np.linspace(-10.0, 10.0, 6)
+    u = torch.ones((N, N), dtype=torch.complex64)
+    z = torch.tensor([9000.0], dtype=torch.float64, requires_grad=True)
+    with pytest.raises(_lib.XlpropError):
+        ops.czt(u, z, 0.6328, x, x, xo, xo)
+    with pytest.raises(_lib.XlpropError):
+        ops.vczt(u, u, z, 0.6328, x, x, xo, xo)
+    with torch.no_grad():
+        assert ops.czt(u, z, 0.6328, x, x, xo, xo).shape == (6, 6)
+    assert ops.czt(u, z.detach(), 0.6328, x, x, xo, xo).shape == (6, 6)

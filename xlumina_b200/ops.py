@@ -65,6 +65,13 @@ def _z_per_item(z, batch):
     return [zf[i:i + 1] for i in range(batch)]
 
 
+def _refuse_z_gradient(z, what):
+    """Paths whose d/dz does not exist yet must not drop it silently (the reference differentiates through everything)."""
+    if isinstance(z, torch.Tensor) and z.requires_grad and torch.is_grad_enabled():
+        raise _lib.XlpropError(f"{what}: the gradient with respect to the distance z is not implemented; "
+                               "pass z.detach() if the distance is not being optimised")
+
+
 def _as_z(z, ref):
     """Propagation distance as ONE float64 on the device (a traced value in the reference, wave_optics.py:281)."""
     if isinstance(z, torch.Tensor):
@@ -411,6 +418,7 @@ def czt(field, z, wavelength, x, y, xout, yout):
     if field.dim() == 3:
         zs = _z_per_item(z, field.shape[0])
         return torch.stack([czt(field[i], z if zs is None else zs[i], wavelength, x, y, xout, yout) for i in range(field.shape[0])])
+    _refuse_z_gradient(z, "czt")
     dt = field.dtype
     f = _c64(field)
     out = _CZT.apply(f, _as_z(z, f).detach(), float(wavelength), 0, _gin(x, y, f.shape[-1]), _gout(xout, yout))
@@ -422,6 +430,7 @@ def vczt(Ex, Ey, z, wavelength, x, y, xout, yout):
     Pass Ey=None if `Ex` is already the stacked (2,N,N) pair; a leading batch axis gives (B,3,...)."""
     if Ex.dim() == (4 if Ey is None else 3):
         return _batch_of_pairs(lambda a, b, zz, hs: vczt(a, b, zz, wavelength, x, y, xout, yout), Ex, Ey, z)
+    _refuse_z_gradient(z, "vczt")
     dt = Ex.dtype
     exy = _c64(Ex) if Ey is None else torch.stack([_c64(Ex), _c64(Ey)], dim=0)
     out = _CZT.apply(exy, _as_z(z, exy).detach(), float(wavelength), 1, _gin(x, y, exy.shape[-1]), _gout(xout, yout))
