@@ -3,11 +3,12 @@ and the oracle, on the CPU.  This exercises every line of the device code's inde
 tables and fused factors through the same C ABI the GPU library exports; the GPU parity proper is tests/test_gpu_parity.py.
 Tolerance: rel-L2 <= 1e-4 vs the complex128 reference (BASELINE.json north_star); observed ~3e-7."""
 import ctypes
+import os
 
 import numpy as np
 import pytest
 
-from conftest import golden, rel_l2
+from conftest import golden, rel_l2, ROOT
 from oracle import oracle_np as o
 
 TOL = 1e-4
@@ -345,3 +346,36 @@ def test_error_codes(emu):
     assert emu.xl_czt_padded_length(32, 33) == 0           # m+M-1 == 64: the reference raises too
     assert emu.xl_czt_padded_length(2048, 2048) == 4096 and emu.xl_czt_padded_length(1024, 400) == 2048
     assert b"workspace" in emu.xl_last_error() or emu.xl_last_error() is not None
+
+
+def test_experiment_variant_tree_reduce_keeps_dz_parity(tmp_path):
+    """The experiment variants of the library (macros XL_EXP_*, built with `python -m xlumina_b200.build --exp`) must stay
+    parity-green before they are timed: XL_EXP_TREE_REDUCE (block reductions of dot_z / fold as shared-memory trees) against
+    the d/dz fixtures of RS and VRS, through the host emulation of the same sources."""
+    import subprocess
+    from xlumina_b200 import _lib
+    src = os.path.join(ROOT, "xlumina_b200", "csrc", "xl_api.cu")
+    so = str(tmp_path / "emu_tree.so")
+    subprocess.check_call(["g++", "-x", "c++", "-std=c++17", "-O1", "-DXL_HOST_EMU", "-DXL_EXP_TREE_REDUCE", "-shared", "-fPIC", "-w", src, "-o", so])
+    var = _lib.declare(ctypes.CDLL(so))
+    for name, vrs in (("rs_n32_zpos", False), ("rs_n48_far", False), ("vrs_n24", True), ("vrs_n40_zneg", True)):
+        g = golden(name)
+        N = len(g["x"])
+        dx, k = float(g["x"][1] - g["x"][0]), 2 * np.pi / float(g["wavelength"])
+        zz = np.array([float(g["z"])])
+        nf = 3 if vrs else 1
+        fin = c64(np.stack([g["Ex"], g["Ey"]]) if vrs else g["field"])
+        out = np.zeros((nf, N, N), np.complex64)
+        H = np.zeros(var.xl_rs_transfer_bytes(N), np.uint8)
+        ws = np.zeros(var.xl_rs_workspace_bytes(N, nf, 1), np.uint8)
+        ct, gin, gz = c64(g["ct"]), np.zeros_like(fin), np.zeros(1)
+        if vrs:
+            x0 = float(g["x"][0])
+            assert var.xl_vrs_fwd(ptr(fin), ptr(out), ptr(H), ptr(zz), N, x0, x0, dx, dx, k, 0, ptr(ws), ws.size, None) == 0
+            assert var.xl_vrs_bwd(ptr(fin), ptr(out), ptr(ct), ptr(gin), ptr(gz), ptr(H), ptr(zz), N, x0, x0, dx, dx, k, 0,
+                                  ptr(ws), ws.size, None) == 0
+        else:
+            assert var.xl_rs_fwd(ptr(fin), ptr(out), ptr(H), ptr(zz), N, 1, dx, dx, k, 0, ptr(ws), ws.size, None) == 0
+            assert var.xl_rs_bwd(ptr(fin), ptr(out), ptr(ct), ptr(gin), ptr(gz), ptr(H), ptr(zz), N, 1, dx, dx, k, 0,
+                                 ptr(ws), ws.size, None) == 0
+        assert abs(gz[0] - float(g["vjp_z"])) < 1e-4 * abs(float(g["vjp_z"])), name

@@ -8,7 +8,9 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libxlprop.so")
+# XLPROP_LIB: development only -- an alternative CUDA build of the same sources (an experiment variant made by
+# `python -m xlumina_b200.build --exp ...`) for A/B timing; it is still the C ABI of include/xlprop.h on the GPU.
+LIB_PATH = os.environ.get("XLPROP_LIB") or os.path.join(_HERE, "libxlprop.so")
 
 _vp = ctypes.c_void_p
 _i = ctypes.c_int

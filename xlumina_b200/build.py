@@ -28,19 +28,29 @@ def up_to_date():
     return all(os.path.getmtime(d) <= t for d in DEPS)
 
 
-def build(force=False, verbose=False):
-    if not force and up_to_date():
+def build(force=False, verbose=False, defines=(), out=None):
+    """Default: the product library, in-tree.  `defines` (e.g. ["XL_EXP_TREE_REDUCE"]) + `out` build an experiment variant
+    of the same sources somewhere else (build/...) for A/B timing with XLPROP_LIB; the product library is never a variant."""
+    if defines and not out:
+        raise ValueError("an experiment variant needs its own output path")
+    out = out or OUT
+    if out == OUT and not force and up_to_date():
         return OUT
+    os.makedirs(os.path.dirname(os.path.abspath(out)), exist_ok=True)
     fast = ["-DXL_DEV_FAST"] if os.environ.get("XL_FAST") else []   # development only: L in {2048, 4096}
-    cmd = [_nvcc()] + NVCC_FLAGS + fast + (["-Xptxas", "-v"] if verbose else []) + [SRC, "-o", OUT]
+    cmd = [_nvcc()] + NVCC_FLAGS + fast + ["-D" + d for d in defines] + (["-Xptxas", "-v"] if verbose else []) + [SRC, "-o", out]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
         raise RuntimeError("nvcc failed building libxlprop.so")
     if verbose:
         sys.stderr.write(r.stderr)
-    return OUT
+    return out
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    # python -m xlumina_b200.build [--force] [-v] [--exp MACRO[,MACRO...] --out build/libxlprop_<name>.so]
+    argv = sys.argv[1:]
+    exp = argv[argv.index("--exp") + 1].split(",") if "--exp" in argv else ()
+    dst = argv[argv.index("--out") + 1] if "--out" in argv else None
+    print(build(force="--force" in argv, verbose="-v" in argv, defines=exp, out=dst))

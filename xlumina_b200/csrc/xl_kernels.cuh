@@ -826,6 +826,18 @@ template <int L> struct XlCztSetup {
     }
 };
 
+#ifdef XL_EXP_TREE_REDUCE   // experiment (DESIGN.md queue item 4): not part of the default build
+// red[0] = sum of red[0..NT) by a shared-memory tree (NT a power of two); ends with a barrier.
+template <int NT, class T> XL_DEV void xl_block_sum(T* red) {
+    for (int st = NT / 2; st >= 1; st >>= 1) {
+        XL_THREADS(tid, NT) {
+            if (tid < st) red[tid] += red[tid + st];
+        }
+        XL_SYNC();
+    }
+}
+#endif
+
 // gz += -k Im sum ct*out : the i k h part of dh/dz, evaluated exactly (fp32 x fp32 products are exact in fp64).
 struct XlDotZParams {
     const cf* ct; const cf* out; size_t n; int flags; double k; double* gz;
@@ -853,6 +865,12 @@ struct XlDotZ {
             red[tid] = acc;
         }
         XL_SYNC();
+#ifdef XL_EXP_TREE_REDUCE
+        xl_block_sum<NT>(red);
+        XL_THREADS(tid, NT) {
+            if (tid == 0) xl_atomic_add(p.gz, -p.k * red[0]);
+        }
+#else
         XL_THREADS(tid, NT) {
             if (tid == 0) {
                 double a = 0.0;
@@ -860,6 +878,7 @@ struct XlDotZ {
                 xl_atomic_add(p.gz, -p.k * a);
             }
         }
+#endif
     }
 };
 
@@ -927,7 +946,13 @@ struct XlFold {
             red[tid] = acc;
         }
         XL_SYNC();
-        if (p.gz) {
+        if (p.gz) {   // kernel-uniform
+#ifdef XL_EXP_TREE_REDUCE
+            xl_block_sum<NT>(red);
+            XL_THREADS(tid, NT) {
+                if (tid == 0) xl_atomic_add(p.gz, (double)red[0]);
+            }
+#else
             XL_THREADS(tid, NT) {
                 if (tid == 0) {
                     double a = 0.0;
@@ -935,6 +960,7 @@ struct XlFold {
                     xl_atomic_add(p.gz, a);
                 }
             }
+#endif
         }
     }
 };
