@@ -190,6 +190,9 @@ template <int L> struct XlRsRowsFwd {
     static const char* name() { return "rs_rows_fwd"; }
     typedef XlRsParams Params;
     static constexpr int NT = xl_threads(L);
+#ifdef XL_EXP_ROWS_3CTA   // experiment (DESIGN.md queue item 1b): a third resident CTA for the 1024-CTA row grids (85 registers)
+    static constexpr int MINB = L == 4096 ? 3 : (512 / NT > 16 ? 16 : 512 / NT);
+#endif
     static size_t smem() { return xl_smem_bytes(L, XL_V); }
     XL_DEV static void run(const Params& p, cf* s) {
         cf* t = s + xl_tile_elems(L, XL_V);
@@ -357,6 +360,9 @@ template <int L> struct XlRsRowsInv {
     static const char* name() { return "rs_rows_inv"; }
     typedef XlRsParams Params;
     static constexpr int NT = xl_threads(L);
+#ifdef XL_EXP_ROWS_3CTA
+    static constexpr int MINB = L == 4096 ? 3 : (512 / NT > 16 ? 16 : 512 / NT);
+#endif
     static size_t smem() { return xl_smem_bytes(L, XL_V); }
     XL_DEV static void run(const Params& p, cf* s) {
         cf* t = s + xl_tile_elems(L, XL_V);
