@@ -1,6 +1,6 @@
 #!/usr/bin/env bash
 # A/B timing of experiment variants of the library (experiment queue).
-#   1. here (build container):   bash scripts/ab_variants.sh build XL_EXP_TREE_REDUCE [MORE_MACROS...]
+#   1. here (build container):   bash scripts/ab_variants.sh build XL_EXP_TREE_REDUCE XL_EXP_ROWS_3CTA split=2 ...
 #        -> build/libxlprop_<macro>.so per macro (build/ is git-ignored but travels with gpurun)
 #   2. on the GPU:   gpurun --timeout 600 -- 'bash scripts/ab_variants.sh time'
 #        -> gpurun_out/ab_<name>.log: scripts/gpu_probe.py timings of every operation for the product library and each variant,
@@ -13,7 +13,10 @@ case "${1:-}" in
 build)
     shift
     for m in "$@"; do
-        python -m xlumina_b200.build --exp "$m" --out "build/libxlprop_$m.so" || exit 1
+        case "$m" in
+        split=*) python -m xlumina_b200.build --split "${m#split=}" --out "build/libxlprop_split${m#split=}.so" || exit 1 ;;   # same source, other -split-compile partitioning
+        *)       python -m xlumina_b200.build --exp "$m" --out "build/libxlprop_$m.so" || exit 1 ;;
+        esac
     done
     ls -la build/libxlprop_*.so ;;
 time)

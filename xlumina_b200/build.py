@@ -13,8 +13,9 @@ OUT = os.path.join(HERE, "libxlprop.so")
 # -split-compile is pinned: the number of partitions changes inlining / register allocation of every kernel ("0" = one per
 # visible CPU gave two different binaries from the same source depending on where the build ran); 8 is the partitioning of
 # the binary that was validated and timed on the B200.
+SPLIT_COMPILE = "8"
 NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-              "-Xcompiler", "-fPIC", "-shared", "-split-compile", "8"]
+              "-Xcompiler", "-fPIC", "-shared"]
 
 
 def _nvcc():
@@ -31,17 +32,17 @@ def up_to_date():
     return all(os.path.getmtime(d) <= t for d in DEPS)
 
 
-def build(force=False, verbose=False, defines=(), out=None):
+def build(force=False, verbose=False, defines=(), out=None, split=None):
     """Default: the product library, in-tree.  `defines` (e.g. ["XL_EXP_TREE_REDUCE"]) + `out` build an experiment variant
     of the same sources somewhere else (build/...) for A/B timing with XLPROP_LIB; the product library is never a variant."""
-    if defines and not out:
+    if (defines or split) and not out:
         raise ValueError("an experiment variant needs its own output path")
     out = out or OUT
     if out == OUT and not force and up_to_date():
         return OUT
     os.makedirs(os.path.dirname(os.path.abspath(out)), exist_ok=True)
     fast = ["-DXL_DEV_FAST"] if os.environ.get("XL_FAST") else []   # development only: L in {2048, 4096}
-    cmd = [_nvcc()] + NVCC_FLAGS + fast + ["-D" + d for d in defines] + (["-Xptxas", "-v"] if verbose else []) + [SRC, "-o", out]
+    cmd = [_nvcc()] + NVCC_FLAGS + ["-split-compile", str(split or SPLIT_COMPILE)] + fast + ["-D" + d for d in defines if d] + (["-Xptxas", "-v"] if verbose else []) + [SRC, "-o", out]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
@@ -52,8 +53,9 @@ def build(force=False, verbose=False, defines=(), out=None):
 
 
 if __name__ == "__main__":
-    # python -m xlumina_b200.build [--force] [-v] [--exp MACRO[,MACRO...] --out build/libxlprop_<name>.so]
+    # python -m xlumina_b200.build [--force] [-v] [--exp MACRO[,MACRO...]] [--split N] [--out build/libxlprop_<name>.so]
     argv = sys.argv[1:]
     exp = argv[argv.index("--exp") + 1].split(",") if "--exp" in argv else ()
     dst = argv[argv.index("--out") + 1] if "--out" in argv else None
-    print(build(force="--force" in argv, verbose="-v" in argv, defines=exp, out=dst))
+    spl = argv[argv.index("--split") + 1] if "--split" in argv else None
+    print(build(force="--force" in argv, verbose="-v" in argv, defines=exp, out=dst, split=spl))
