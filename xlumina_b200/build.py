@@ -10,9 +10,9 @@ DEPS = [os.path.join(HERE, "csrc", f) for f in ("xl_api.cu", "xl_kernels.cuh", "
        [os.path.join(os.path.dirname(HERE), "include", "xlprop.h")]
 OUT = os.path.join(HERE, "libxlprop.so")
 
-# -split-compile is pinned: the number of partitions changes inlining / register allocation of every kernel ("0" = one per
-# visible CPU gave two different binaries from the same source depending on where the build ran); 8 is the partitioning of
-# the binary that was validated and timed on the B200.
+# -split-compile > 1 partitions the translation unit for optimisation; the partitioning (and with it the register allocation
+# of every kernel) is not reproducible from run to run -- two binaries have been seen from identical sources and flags
+# (build note).  Compare per-kernel SASS hashes before attributing a timing change to a source change.
 SPLIT_COMPILE = "8"
 NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-shared"]

@@ -541,6 +541,21 @@ template <int L> struct XlRsColsGz {
         XlFft<L, 2>::init_tw(t, p.tw);
         const int G = XL_BLOCK_X >> 1, c = XL_BLOCK_X & 1, f = p.f0 + XL_BLOCK_Y;   // one column per CTA
         const size_t toff = (size_t)f * L * p.N + (size_t)G * p.N * XL_V;
+#ifdef XL_EXP_K4_PREFETCH   // experiment: as in rs_cols, start moving both transfer-function columns into L2 before the FFT passes
+        {
+            const cf* Ha = xl_h_column<L>(p.H, XL_V * G + c);
+            const cf* Hb = xl_h_column<L>(p.H2, XL_V * G + c);
+            XL_THREADS(tid, NT) {
+                for (int beta = tid; beta < L / 16; beta += NT)
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        if (beta & 1) continue;       // one prefetch per 32-byte sector
+                        xl_prefetch_l2(Ha + (size_t)(q * (L / 16) + beta) * XL_V);
+                        xl_prefetch_l2(Hb + (size_t)(q * (L / 16) + beta) * XL_V);
+                    }
+            }
+        }
+#endif
         {
             XlRsColsGzOp<L> op{{}, p, p.spec + toff, p.spec2 + toff, c, xl_h_column<L>(p.H, XL_V * G + c),
                                xl_h_column<L>(p.H2, XL_V * G + c), itile, red};
