@@ -348,15 +348,18 @@ def test_error_codes(emu):
     assert b"workspace" in emu.xl_last_error() or emu.xl_last_error() is not None
 
 
-def test_experiment_variant_tree_reduce_keeps_dz_parity(tmp_path):
-    """The experiment variants of the library (macros XL_EXP_*, built with `python -m xlumina_b200.build --exp`) must stay
-    parity-green before they are timed: XL_EXP_TREE_REDUCE (block reductions of dot_z / fold as shared-memory trees) against
-    the d/dz fixtures of RS and VRS, through the host emulation of the same sources."""
+@pytest.mark.parametrize("macros", [["XL_EXP_TREE_REDUCE"], ["XL_EXP_K4_STAGE", "XL_EXP_K4_PREFETCH", "XL_EXP_ROWS_3CTA"]])
+def test_experiment_variants_keep_gradient_parity(tmp_path, macros):
+    """The experiment variants of the library (macros XL_EXP_*, built with `python -m xlumina_b200.build --exp`, never part
+    of the product build) must stay parity-green before they are timed: block reductions as shared-memory trees, and the
+    staged in-place rs_cols_gz, against the field-VJP and d/dz fixtures of RS and VRS, through the host emulation of the
+    same sources (the emulation copies at issue time where the device copies asynchronously)."""
     import subprocess
     from xlumina_b200 import _lib
     src = os.path.join(ROOT, "xlumina_b200", "csrc", "xl_api.cu")
-    so = str(tmp_path / "emu_tree.so")
-    subprocess.check_call(["g++", "-x", "c++", "-std=c++17", "-O1", "-DXL_HOST_EMU", "-DXL_EXP_TREE_REDUCE", "-shared", "-fPIC", "-w", src, "-o", so])
+    so = str(tmp_path / "emu_variant.so")
+    subprocess.check_call(["g++", "-x", "c++", "-std=c++17", "-O1", "-DXL_HOST_EMU"] + ["-D" + m for m in macros] +
+                          ["-shared", "-fPIC", "-w", src, "-o", so])
     var = _lib.declare(ctypes.CDLL(so))
     for name, vrs in (("rs_n32_zpos", False), ("rs_n48_far", False), ("vrs_n24", True), ("vrs_n40_zneg", True)):
         g = golden(name)
@@ -379,3 +382,5 @@ def test_experiment_variant_tree_reduce_keeps_dz_parity(tmp_path):
             assert var.xl_rs_bwd(ptr(fin), ptr(out), ptr(ct), ptr(gin), ptr(gz), ptr(H), ptr(zz), N, 1, dx, dx, k, 0,
                                  ptr(ws), ws.size, None) == 0
         assert abs(gz[0] - float(g["vjp_z"])) < 1e-4 * abs(float(g["vjp_z"])), name
+        if "vjp_field" in g:
+            assert rel_l2(gin.reshape(g["vjp_field"].shape), g["vjp_field"]) < TIGHT, name

@@ -337,7 +337,11 @@ static int rs_bwd_common(const void* in, const void* out, const void* ct_out, vo
         if (rc) return rc;
         XlRsParams pg = p;
         pg.H2 = Hz; pg.gz = grad_z;
+#ifdef XL_EXP_K4_STAGE
+        XL_FOR_L(L, rc = xl_launch<XlRsColsGzStage<XL>>(XlDim{L, nfields}, st, pg));
+#else
         XL_FOR_L(L, rc = xl_launch<XlRsColsGz<XL>>(XlDim{L, nfields}, st, pg));
+#endif
         if (rc) return rc;
         XlRsParams po = p;
         po.out = dst;

@@ -88,6 +88,11 @@ template <> struct XlTile<1> {
     XL_DEV static void ld(const cf* s, int i, cf* v, int) { v[0] = s[xl_pad(i)]; }
     XL_DEV static void st(cf* s, int i, const cf* v, int) { s[xl_pad(i)] = v[0]; }
 };
+// line 0 of a two-line tile, seen as a one-line tile (K4 variant: the inverse runs in place on the cotangent's line)
+struct XlTileLine0Of2 {
+    XL_DEV static void ld(const cf* s, int i, cf* v, int) { v[0] = s[2 * xl_pad(i)]; }
+    XL_DEV static void st(cf* s, int i, const cf* v, int) { s[2 * xl_pad(i)] = v[0]; }
+};
 template <> struct XlTile<2> {
     XL_DEV static void ld(const cf* s, int i, cf* v, int stride) {
         const float4 t = *reinterpret_cast<const float4*>(s + 2 * xl_pad(i));
@@ -211,9 +216,11 @@ struct XlOpBase {
     // run-time (CTA-uniform) version of kInLoHalf: skips the loads and prologue math of the upper half, keeps the full
     // butterfly -- for ops whose sizes are not known at compile time and whose variants are too many to double
     XL_DEV bool in_lo_rt() const { return false; }
+    // called by every thread after its first-pass work, before the first barrier of a transform
+    XL_DEV void before_first_sync() const {}
 };
 
-template <int L, int V> struct XlFft {
+template <int L, int V, class Tile = XlTile<V>> struct XlFft {
     static constexpr int NT = xl_threads(L);
     static constexpr int R1 = xl_first_radix(L);
     static constexpr int S1 = L / R1;
@@ -263,8 +270,9 @@ template <int L, int V> struct XlFft {
                     xl_twiddle<R1, -1>(v + l * R1, w);
                 }
 #pragma unroll
-                for (int q = 0; q < R1; ++q) XlTile<V>::st(s, n + S1 * q, v + q, R1);
+                for (int q = 0; q < R1; ++q) Tile::st(s, n + S1 * q, v + q, R1);
             }
+            op.before_first_sync();   // empty unless the op has asynchronous copies in flight
         }
         XL_SYNC();
     }
@@ -276,7 +284,7 @@ template <int L, int V> struct XlFft {
                 const int b = beta / S, n = beta % S, base = b * B + n;
                 cf v[V * 16];
 #pragma unroll
-                for (int j = 0; j < 16; ++j) XlTile<V>::ld(s, base + S * j, v + j, 16);
+                for (int j = 0; j < 16; ++j) Tile::ld(s, base + S * j, v + j, 16);
                 cf w[16];
                 xl_tw_powers<16>(w, t[n], t[S + n]);
 #pragma unroll
@@ -285,7 +293,7 @@ template <int L, int V> struct XlFft {
                     xl_twiddle<16, -1>(v + l * 16, w);
                 }
 #pragma unroll
-                for (int q = 0; q < 16; ++q) XlTile<V>::st(s, base + S * q, v + q, 16);
+                for (int q = 0; q < 16; ++q) Tile::st(s, base + S * q, v + q, 16);
             }
         }
         XL_SYNC();
@@ -302,7 +310,7 @@ template <int L, int V> struct XlFft {
                 const int b = beta / S, n = beta % S, base = b * B + n;
                 cf v[V * 16];
 #pragma unroll
-                for (int q = 0; q < 16; ++q) XlTile<V>::ld(s, base + S * q, v + q, 16);
+                for (int q = 0; q < 16; ++q) Tile::ld(s, base + S * q, v + q, 16);
                 cf w[16];
                 xl_tw_powers<16>(w, t[n], t[S + n]);
 #pragma unroll
@@ -311,7 +319,7 @@ template <int L, int V> struct XlFft {
                     XlBfly<16, +1, false, false>::run(v + l * 16);
                 }
 #pragma unroll
-                for (int j = 0; j < 16; ++j) XlTile<V>::st(s, base + S * j, v + j, 16);
+                for (int j = 0; j < 16; ++j) Tile::st(s, base + S * j, v + j, 16);
             }
         }
         XL_SYNC();
@@ -324,7 +332,7 @@ template <int L, int V> struct XlFft {
             for (int n = tid; n < S1; n += NT) {
                 cf v[V * R1];
 #pragma unroll
-                for (int q = 0; q < R1; ++q) XlTile<V>::ld(s, n + S1 * q, v + q, R1);
+                for (int q = 0; q < R1; ++q) Tile::ld(s, n + S1 * q, v + q, R1);
                 cf w[R1];
                 xl_tw_powers<R1>(w, t[n], R1 == 16 ? t[S1 + n] : cf_zero());
 #pragma unroll
@@ -346,7 +354,7 @@ template <int L, int V> struct XlFft {
             for (int beta = tid; beta < L / 16; beta += NT) {
                 cf v[V * 16];
 #pragma unroll
-                for (int j = 0; j < 16; ++j) XlTile<V>::ld(s, 16 * beta + j, v + j, 16);
+                for (int j = 0; j < 16; ++j) Tile::ld(s, 16 * beta + j, v + j, 16);
 #pragma unroll
                 for (int l = 0; l < V; ++l) XlBfly<16, -1, false, false>::run(v + l * 16);
                 op.spec(beta, v);
@@ -361,14 +369,14 @@ template <int L, int V> struct XlFft {
             for (int beta = tid; beta < L / 16; beta += NT) {
                 cf v[V * 16];
 #pragma unroll
-                for (int j = 0; j < 16; ++j) XlTile<V>::ld(s, 16 * beta + j, v + j, 16);
+                for (int j = 0; j < 16; ++j) Tile::ld(s, 16 * beta + j, v + j, 16);
 #pragma unroll
                 for (int l = 0; l < V; ++l) XlBfly<16, -1, false, false>::run(v + l * 16);
                 op.spec(beta, v);
 #pragma unroll
                 for (int l = 0; l < V; ++l) XlBfly<16, +1, false, false>::run(v + l * 16);
 #pragma unroll
-                for (int j = 0; j < 16; ++j) XlTile<V>::st(s, 16 * beta + j, v + j, 16);
+                for (int j = 0; j < 16; ++j) Tile::st(s, 16 * beta + j, v + j, 16);
             }
         }
         XL_SYNC();
@@ -389,7 +397,7 @@ template <int L, int V> struct XlFft {
 #pragma unroll
                 for (int l = 0; l < V; ++l) XlBfly<16, +1, false, false>::run(v + l * 16);
 #pragma unroll
-                for (int j = 0; j < 16; ++j) XlTile<V>::st(s, 16 * beta + j, v + j, 16);
+                for (int j = 0; j < 16; ++j) Tile::st(s, 16 * beta + j, v + j, 16);
             }
         }
         XL_SYNC();

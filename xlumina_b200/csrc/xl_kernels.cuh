@@ -527,6 +527,90 @@ template <int L> struct XlRsColsGzOutOp : XlOpBase {
         }
     }
 };
+#ifdef XL_EXP_K4_STAGE
+// Experiment (DESIGN.md queue item 1a), not in the default build.  Same arithmetic as XlRsColsGz below with two changes:
+//  * the fused first inverse pass is written back IN PLACE into line 0 of the two-line tile (same thread, same slots) and
+//    the inverse tail runs on that line only -- the separate one-line tile disappears;
+//  * its 34.8 KB stage both transfer-function columns (H and the reduced Hz, rows 0..L/2) with asynchronous copies issued
+//    at kernel start, so the spectrum phase reads shared memory instead of waiting on L2 in the middle of the transform.
+template <int L> struct XlRsColsGzStageOp : XlOpBase {
+    static constexpr bool kInLoHalf = true;
+    const XlRsParams& p; const cf* ctile; const cf* wtile; int c; const cf* Hs; const cf* Hzs; cf* tile2; float* red;
+    XL_DEV void load(int i, cf* v, int stride) const {
+        const bool ok = i < p.N;
+        const size_t o = ok ? (size_t)i * XL_V + c : 0;
+        const cf a = ctile[o], w = wtile[o];
+        v[0] = ok ? a : cf_zero();
+        v[stride] = ok ? w : cf_zero();
+    }
+    XL_DEV void before_first_sync() const { xl_cp_async_wait(); }   // this thread's staged entries; the barrier publishes them
+    XL_DEV void spec(int beta, const cf* v) const {
+        float acc = 0.f;
+        cf u[16];
+        const XlHRow<L> hr(beta);
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            const int r = hr.row(q);
+            const cf t = cf_mul(v[q], Hzs[r]);
+            acc += v[16 + q].x * t.x + v[16 + q].y * t.y;  // Re(conj(w) * t)
+            u[q] = cf_mul(v[q], Hs[r]);
+        }
+        red[beta] += acc;
+        XlBfly<16, +1, false, false>::run(u);       // first inverse pass, fused; back into line 0 of the slots just read
+#pragma unroll
+        for (int j = 0; j < 16; ++j) XlTileLine0Of2::st(tile2, 16 * beta + j, u + j, 16);
+    }
+    XL_DEV void store_vec(int, const cf*) const {}
+};
+template <int L> struct XlRsColsGzStage {
+    static const char* name() { return "rs_cols_gz"; }
+    typedef XlRsParams Params;
+    static constexpr int NT = xl_threads(L);
+    static constexpr int NB = L / 16;
+    static constexpr int HR = L / 2 + 1;          // stored rows of a transfer-function column
+    static size_t smem() { return (size_t)(xl_tile_elems(L, 2) + 2 * (HR + 1) + xl_tw_total(L)) * sizeof(cf) + (size_t)(NB + 32) * sizeof(float); }
+    XL_DEV static void run(const Params& p, cf* s) {
+        cf* Hs = s + xl_tile_elems(L, 2);
+        cf* Hzs = Hs + HR + 1;
+        cf* t = Hzs + HR + 1;
+        float* red = (float*)(t + xl_tw_total(L));
+        const int G = XL_BLOCK_X >> 1, c = XL_BLOCK_X & 1, f = p.f0 + XL_BLOCK_Y;   // one column per CTA
+        const cf* Hc = xl_h_column<L>(p.H, XL_V * G + c);
+        const cf* Hzc = xl_h_column<L>(p.H2, XL_V * G + c);
+        XL_THREADS(tid, NT) {
+            for (int r = tid; r < HR; r += NT) {
+                xl_cp_async8(Hs + r, Hc + (size_t)r * XL_V);
+                xl_cp_async8(Hzs + r, Hzc + (size_t)r * XL_V);
+            }
+            for (int i = tid; i < NB; i += NT) red[i] = 0.f;
+        }
+        XlFft<L, 2>::init_tw(t, p.tw);
+        const size_t toff = (size_t)f * L * p.N + (size_t)G * p.N * XL_V;
+        XlRsColsGzStageOp<L> op{{}, p, p.spec + toff, p.spec2 + toff, c, Hs, Hzs, s, red};
+        XlFft<L, 2>::forward(s, t, op);
+        XL_SYNC();
+        XlRsColsGzOutOp<L> oo{{}, p, p.spec + toff, c};
+        XlFft<L, 1, XlTileLine0Of2>::inverse_tail(s, t, oo);
+        XL_SYNC();
+        XL_THREADS(tid, NT) {
+            if (tid < 32) {
+                float a = 0.f;
+                for (int i = tid; i < NB; i += 32) a += red[i];
+                red[NB + tid] = a;
+            }
+        }
+        XL_SYNC();
+        XL_THREADS(tid, NT) {
+            if (tid == 0) {
+                double a = 0.0;
+                for (int i = 0; i < 32; ++i) a += (double)red[NB + i];
+                xl_atomic_add(p.gz, a);
+            }
+        }
+    }
+};
+#endif
+
 template <int L> struct XlRsColsGz {
     static const char* name() { return "rs_cols_gz"; }
     typedef XlRsParams Params;

@@ -41,6 +41,9 @@ static inline float4 xl_ldg(const float4* p) { return *p; }
 static inline double xl_ldg(const double* p) { return *p; }
 static inline void xl_atomic_add(double* p, double v) { *p += v; }
 static inline void xl_prefetch_l2(const void*) {}
+// asynchronous 8-byte global -> shared copy (the emulation copies at issue time; waiting is then a no-op)
+static inline void xl_cp_async8(float2* dst, const float2* src) { *dst = *src; }
+static inline void xl_cp_async_wait() {}
 #else
 #include <cuda_runtime.h>
 #define XL_DEV __device__ __forceinline__
@@ -61,6 +64,12 @@ XL_DEV float4 xl_ldg(const float4* p) { return __ldg(p); }
 XL_DEV double xl_ldg(const double* p) { return __ldg(p); }
 XL_DEV void xl_atomic_add(double* p, double v) { atomicAdd(p, v); }
 XL_DEV void xl_prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// asynchronous 8-byte global -> shared copy (LDGSTS: no registers, completion by xl_cp_async_wait of the issuing thread,
+// visibility to the other threads of the CTA by the next barrier)
+XL_DEV void xl_cp_async8(float2* dst, const float2* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+XL_DEV void xl_cp_async_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 // exchange one complex value with the neighbouring lane (lane ^ 1); callers guarantee that lanes 2k and 2k+1 are
 // active together (the host emulation runs threads one after another and uses plain 8-byte accesses instead)
 XL_DEV float2 xl_xchg1(float2 v) {
