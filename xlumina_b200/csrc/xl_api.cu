@@ -259,7 +259,11 @@ static int rs_apply_impl(XlRsParams p, xl_stream_t st) {
     p.f0 = 0;
     XL_FOR_L(L, rc = xl_launch<XlRsRowsFwd<XL>>(XlDim{xl_groups(N), p.nfields}, st, p));
     if (rc) return rc;
+#ifdef XL_EXP_K2_STAGE
+    XL_FOR_L(L, rc = xl_launch<XlRsColsStage<XL>>(XlDim{L / XL_V, p.nfields}, st, p));
+#else
     XL_FOR_L(L, rc = xl_launch<XlRsCols<XL>>(XlDim{L / XL_V, p.nfields}, st, p));
+#endif
     if (rc) return rc;
     XL_FOR_L(L, rc = xl_launch<XlRsRowsInv<XL>>(XlDim{xl_groups(N), p.nfields}, st, p));
     return rc;

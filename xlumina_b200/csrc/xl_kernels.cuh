@@ -308,6 +308,61 @@ template <int L> struct XlRsCols {
         XlFft<L, XL_V>::conv(s, t, op);
     }
 };
+#ifdef XL_EXP_K2_STAGE
+// Experiment (DESIGN.md queue item 1), not in the default build: rs_cols with both transfer-function columns of the pair
+// staged in shared memory by asynchronous copies issued at kernel start (interleaved {H0[r], H1[r]} so that the spectrum
+// phase needs one 16-byte shared load per bin pair, whatever the mirror mode of the pair was).
+template <int L> struct XlRsColsStageOp : XlOpBase {
+    static constexpr bool kInLoHalf = true, kOutLoHalf = true;
+    static constexpr int R1 = xl_first_radix(L), S1 = L / R1;
+    const XlRsParams& p; cf* tile; const cf* Hs;   // Hs[2*r], Hs[2*r+1]: the two lines' transfer function at stored row r
+    XL_DEV void load(int i, cf* v, int stride) const {
+        if (i < p.N) xl_ld4(tile + (size_t)i * XL_V, v, v + stride);
+        else { v[0] = cf_zero(); v[stride] = cf_zero(); }
+    }
+    XL_DEV void before_first_sync() const { xl_cp_async_wait(); }
+    XL_DEV void spec(int beta, cf* v) const {
+        const XlHRow<L> hr(beta);
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            const float4 h = *reinterpret_cast<const float4*>(Hs + 2 * hr.row(q));
+            v[q] = cf_mul(v[q], make_float2(h.x, h.y));
+            v[16 + q] = cf_mul(v[16 + q], make_float2(h.z, h.w));
+        }
+    }
+    XL_DEV void store_vec(int n, const cf* v) const {
+#pragma unroll
+        for (int j = 0; j < R1 / 2; ++j) {
+            const int i = n + S1 * j;
+            if (i < p.N) xl_st4(tile + (size_t)i * XL_V, v[j], v[R1 + j]);
+        }
+    }
+};
+template <int L> struct XlRsColsStage {
+    static const char* name() { return "rs_cols"; }
+    typedef XlRsParams Params;
+    static constexpr int NT = xl_threads(L);
+    static constexpr int HR = L / 2 + 1;
+    static size_t smem() { return xl_smem_bytes(L, XL_V) + (size_t)2 * (HR + 1) * sizeof(cf); }
+    XL_DEV static void run(const Params& p, cf* s) {
+        cf* Hs = s + xl_tile_elems(L, XL_V);          // 16-byte aligned: the tile holds an even number of cf
+        cf* t = Hs + 2 * (HR + 1);
+        const int G = XL_BLOCK_X, f = p.f0 + XL_BLOCK_Y;
+        const cf* H0 = xl_h_column<L>(p.H, XL_V * G);
+        const cf* H1 = xl_h_column<L>(p.H, XL_V * G + 1);
+        XL_THREADS(tid, NT) {
+            for (int r = tid; r < HR; r += NT) {
+                xl_cp_async8(Hs + 2 * r, H0 + (size_t)r * XL_V);
+                xl_cp_async8(Hs + 2 * r + 1, H1 + (size_t)r * XL_V);
+            }
+        }
+        XlFft<L, XL_V>::init_tw(t, p.tw);
+        XlRsColsStageOp<L> op{{}, p, p.spec + (size_t)f * L * p.N + (size_t)G * p.N * XL_V, Hs};
+        XlFft<L, XL_V>::conv(s, t, op);
+    }
+};
+#endif
+
 // K2 of the slab-decomposed path: this rank owns gridDim.x slot pairs; its transfer-function slab H is [pairs][L][2]
 // (generated for exactly these columns, so no x-mirroring), its spectra arrive as [source rank][pairs][chunk_rows][2].
 template <int L> struct XlRsColsSlab {
