@@ -12,6 +12,7 @@
 
 #ifdef XL_HOST_EMU
 thread_local xl_dim3 xl_emu_blockIdx;
+thread_local xl_dim3 xl_emu_gridDim;
 typedef void* xl_stream_t;
 #else
 typedef cudaStream_t xl_stream_t;
@@ -88,6 +89,7 @@ template <class Body> static int xl_launch(XlDim grid, xl_stream_t stream, const
 #ifdef XL_HOST_EMU
     (void)stream;
     std::vector<char> buf(smem + 64);
+    xl_emu_gridDim.x = grid.x; xl_emu_gridDim.y = grid.y; xl_emu_gridDim.z = 1;
     for (int by = 0; by < grid.y; ++by)
         for (int bx = 0; bx < grid.x; ++bx) {
             xl_emu_blockIdx.x = bx; xl_emu_blockIdx.y = by; xl_emu_blockIdx.z = 0;
@@ -259,7 +261,19 @@ static int rs_apply_impl(XlRsParams p, xl_stream_t st) {
     p.f0 = 0;
     XL_FOR_L(L, rc = xl_launch<XlRsRowsFwd<XL>>(XlDim{xl_groups(N), p.nfields}, st, p));
     if (rc) return rc;
-#ifdef XL_EXP_K2_STAGE
+#if defined(XL_EXP_K2_PERSIST)
+    {   // persistent CTAs, two per SM (the emulation uses 3 CTAs so that every CTA walks several items)
+        int slots = 3;
+#ifndef XL_HOST_EMU
+        int dev = 0, sms = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        slots = 2 * (sms > 0 ? sms : 148);
+#endif
+        const int items = (L / XL_V) * p.nfields;
+        XL_FOR_L(L, rc = xl_launch<XlRsColsPersist<XL>>(XlDim{items < slots ? items : slots, 1}, st, p));
+    }
+#elif defined(XL_EXP_K2_STAGE)
     XL_FOR_L(L, rc = xl_launch<XlRsColsStage<XL>>(XlDim{L / XL_V, p.nfields}, st, p));
 #else
     XL_FOR_L(L, rc = xl_launch<XlRsCols<XL>>(XlDim{L / XL_V, p.nfields}, st, p));

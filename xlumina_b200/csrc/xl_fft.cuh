@@ -218,6 +218,8 @@ struct XlOpBase {
     XL_DEV bool in_lo_rt() const { return false; }
     // called by every thread after its first-pass work, before the first barrier of a transform
     XL_DEV void before_first_sync() const {}
+    // called by every thread right after that barrier (the inputs of this transform are no longer needed)
+    XL_DEV void after_first_sync(int) const {}
 };
 
 template <int L, int V, class Tile = XlTile<V>> struct XlFft {
@@ -275,6 +277,7 @@ template <int L, int V, class Tile = XlTile<V>> struct XlFft {
             op.before_first_sync();   // empty unless the op has asynchronous copies in flight
         }
         XL_SYNC();
+        XL_THREADS(tid, NT) { op.after_first_sync(tid); }   // every load() of this transform has completed in every thread
     }
     template <int B> XL_DEV static void fwd_mid(cf* s, const cf* tw) {
         constexpr int S = B / 16;

@@ -363,6 +363,99 @@ template <int L> struct XlRsColsStage {
 };
 #endif
 
+#ifdef XL_EXP_K2_PERSIST
+// Experiment (DESIGN.md queue item 1), not in the default build: persistent rs_cols.  Each CTA walks the (column pair,
+// field) items blockIdx.x, blockIdx.x + gridDim.x, ...; the pruned input of an item (N rows x 2 lines, contiguous in the
+// spectra buffer) is staged in shared memory by asynchronous 16-byte copies, and the copies of the NEXT item are issued
+// right after the first barrier of the current transform, so they travel while the current item is being transformed.
+template <int L> struct XlRsColsPersistOp : XlOpBase {
+    static constexpr bool kInLoHalf = true, kOutLoHalf = true;
+    static constexpr int R1 = xl_first_radix(L), S1 = L / R1, NT = xl_threads(L);
+    const XlRsParams& p; cf* tile; cf* stage; const cf* next; const cf* H0; const cf* H1; int hmode;
+    XL_DEV void load(int i, cf* v, int stride) const {
+        if (i < p.N) xl_ld4(stage + (size_t)i * XL_V, v, v + stride);
+        else { v[0] = cf_zero(); v[stride] = cf_zero(); }
+    }
+    XL_DEV void after_first_sync(int tid) const {
+        if (next)
+            for (int i = tid; i < p.N; i += NT) xl_cp_async16(stage + (size_t)i * XL_V, next + (size_t)i * XL_V);
+    }
+    XL_DEV void spec(int beta, cf* v) const {
+        const XlHRow<L> hr(beta);
+        if (hmode == 2) {
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+                const size_t o = (size_t)hr.row(q) * XL_V;
+                v[q] = cf_mul(v[q], xl_ldg(H0 + o));
+                v[16 + q] = cf_mul(v[16 + q], xl_ldg(H1 + o));
+            }
+        } else {
+            const cf* Hp = hmode == 0 ? H0 : H1;
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+                cf lo, hi;
+                xl_ldg4(Hp + (size_t)hr.row(q) * XL_V, &lo, &hi);
+                v[q] = cf_mul(v[q], hmode == 0 ? lo : hi);
+                v[16 + q] = cf_mul(v[16 + q], hmode == 0 ? hi : lo);
+            }
+        }
+    }
+    XL_DEV void store_vec(int n, const cf* v) const {
+#pragma unroll
+        for (int j = 0; j < R1 / 2; ++j) {
+            const int i = n + S1 * j;
+            if (i < p.N) xl_st4(tile + (size_t)i * XL_V, v[j], v[R1 + j]);
+        }
+    }
+};
+template <int L> struct XlRsColsPersist {
+    static const char* name() { return "rs_cols"; }
+    typedef XlRsParams Params;
+    static constexpr int NT = xl_threads(L);
+    static size_t smem() { return xl_smem_bytes(L, XL_V) + (size_t)L * sizeof(cf); }   // + N <= L/2 rows of two lines
+    XL_DEV static const cf* item(const Params& p, int it) {
+        const int G = it % (L / XL_V), f = p.f0 + it / (L / XL_V);
+        return p.spec + (size_t)f * L * p.N + (size_t)G * p.N * XL_V;
+    }
+    XL_DEV static void run(const Params& p, cf* s) {
+        cf* stage = s + xl_tile_elems(L, XL_V);
+        cf* t = stage + L;
+        const int items = (L / XL_V) * p.nfields;
+        int it = XL_BLOCK_X;
+        if (it >= items) return;
+        {
+            const cf* first = item(p, it);
+            XL_THREADS(tid, NT) {
+                for (int i = tid; i < p.N; i += NT) xl_cp_async16(stage + (size_t)i * XL_V, first + (size_t)i * XL_V);
+                xl_cp_async_wait();
+            }
+        }
+        XlFft<L, XL_V>::init_tw(t, p.tw);               // ends with a barrier: the first item is staged for every thread
+        for (; it < items; it += XL_GRID_X) {
+            const int G = it % (L / XL_V);
+            const cf* H0 = xl_h_column<L>(p.H, XL_V * G);
+            const cf* H1 = xl_h_column<L>(p.H, XL_V * G + 1);
+            const bool a0 = (((size_t)(H0 - p.H)) & 1) == 0, a1 = (((size_t)(H1 - p.H)) & 1) == 0;
+            const int hmode = (a0 && H1 == H0 + 1) ? 0 : ((a1 && H0 == H1 + 1) ? 1 : 2);
+            XL_THREADS(tid, NT) {
+                for (int beta = tid; beta < L / 16; beta += NT)
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        if (beta & 1) continue;
+                        xl_prefetch_l2(H0 + (size_t)(q * (L / 16) + beta) * XL_V);
+                        if (hmode == 2) xl_prefetch_l2(H1 + (size_t)(q * (L / 16) + beta) * XL_V);
+                    }
+            }
+            const int nx = it + XL_GRID_X;
+            XlRsColsPersistOp<L> op{{}, p, const_cast<cf*>(item(p, it)), stage, nx < items ? item(p, nx) : (const cf*)0, H0, H1, hmode};
+            XlFft<L, XL_V>::conv(s, t, op);
+            XL_THREADS(tid, NT) { xl_cp_async_wait(); }
+            XL_SYNC();                                   // next input staged for every thread; tile free for the next transform
+        }
+    }
+};
+#endif
+
 // K2 of the slab-decomposed path: this rank owns gridDim.x slot pairs; its transfer-function slab H is [pairs][L][2]
 // (generated for exactly these columns, so no x-mirroring), its spectra arrive as [source rank][pairs][chunk_rows][2].
 template <int L> struct XlRsColsSlab {

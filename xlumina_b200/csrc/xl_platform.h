@@ -27,6 +27,8 @@ static inline float2 __ffma2_rn(float2 a, float2 b, float2 c) { return make_floa
 #define XL_RESTRICT
 struct xl_dim3 { int x, y, z; };
 extern thread_local xl_dim3 xl_emu_blockIdx;
+extern thread_local xl_dim3 xl_emu_gridDim;
+#define XL_GRID_X (xl_emu_gridDim.x)
 #define XL_BLOCK_X (xl_emu_blockIdx.x)
 #define XL_BLOCK_Y (xl_emu_blockIdx.y)
 #define XL_BLOCK_Z (xl_emu_blockIdx.z)
@@ -43,6 +45,7 @@ static inline void xl_atomic_add(double* p, double v) { *p += v; }
 static inline void xl_prefetch_l2(const void*) {}
 // asynchronous 8-byte global -> shared copy (the emulation copies at issue time; waiting is then a no-op)
 static inline void xl_cp_async8(float2* dst, const float2* src) { *dst = *src; }
+static inline void xl_cp_async16(float2* dst, const float2* src) { dst[0] = src[0]; dst[1] = src[1]; }
 static inline void xl_cp_async_wait() {}
 #else
 #include <cuda_runtime.h>
@@ -50,6 +53,7 @@ static inline void xl_cp_async_wait() {}
 #define XL_HD __host__ __device__
 #define XL_DEVFN __device__
 #define XL_RESTRICT __restrict__
+#define XL_GRID_X ((int)gridDim.x)
 #define XL_BLOCK_X ((int)blockIdx.x)
 #define XL_BLOCK_Y ((int)blockIdx.y)
 #define XL_BLOCK_Z ((int)blockIdx.z)
@@ -68,6 +72,9 @@ XL_DEV void xl_prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0
 // visibility to the other threads of the CTA by the next barrier)
 XL_DEV void xl_cp_async8(float2* dst, const float2* src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+XL_DEV void xl_cp_async16(float2* dst, const float2* src) {   // 16-byte aligned on both sides
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
 }
 XL_DEV void xl_cp_async_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 // exchange one complex value with the neighbouring lane (lane ^ 1); callers guarantee that lanes 2k and 2k+1 are
