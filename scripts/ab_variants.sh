@@ -21,6 +21,13 @@ build)
     ls -la build/libxlprop_*.so ;;
 time)
     mkdir -p gpurun_out
+    # a variant is timed only after it passes the golden parity tests on the device (XLPROP_LIB selects the library)
+    for lib in build/libxlprop_*.so; do
+        [ -f "$lib" ] || continue
+        name=$(basename "$lib" .so)
+        XLPROP_LIB="$PWD/$lib" timeout 300 python -m pytest tests/test_gpu_parity.py -q -x -k "golden or four_f or 2048" > "gpurun_out/ab_${name}_parity.log" 2>&1
+        echo "== $name parity: $(tail -1 "gpurun_out/ab_${name}_parity.log")"
+    done
     for pass in 1 2; do
         for lib in xlumina_b200/libxlprop.so build/libxlprop_*.so; do
             [ -f "$lib" ] || continue
