@@ -355,7 +355,19 @@ static int rs_bwd_common(const void* in, const void* out, const void* ct_out, vo
         if (rc) return rc;
         XlRsParams pg = p;
         pg.H2 = Hz; pg.gz = grad_z;
-#ifdef XL_EXP_K4_STAGE
+#if defined(XL_EXP_K4_PERSIST)
+        {
+            int slots = 3;
+#ifndef XL_HOST_EMU
+            int dev = 0, sms = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            slots = 2 * (sms > 0 ? sms : 148);
+#endif
+            const int items = L * nfields;
+            XL_FOR_L(L, rc = xl_launch<XlRsColsGzPersist<XL>>(XlDim{items < slots ? items : slots, 1}, st, pg));
+        }
+#elif defined(XL_EXP_K4_STAGE)
         XL_FOR_L(L, rc = xl_launch<XlRsColsGzStage<XL>>(XlDim{L, nfields}, st, pg));
 #else
         XL_FOR_L(L, rc = xl_launch<XlRsColsGz<XL>>(XlDim{L, nfields}, st, pg));

@@ -759,6 +759,119 @@ template <int L> struct XlRsColsGzStage {
 };
 #endif
 
+#ifdef XL_EXP_K4_PERSIST
+// Experiment (DESIGN.md queue items 1 / 1a), not in the default build: persistent rs_cols_gz.  In-place inverse on line 0 of
+// the two-line tile as in XlRsColsGzStage; the freed shared memory stages the NEXT column's inputs instead (cotangent
+// spectra column and conj-field spectra column, N rows each, 8-byte asynchronous copies issued right after the first
+// barrier of the current transform); the transfer-function columns are prefetched into L2 at the start of each item.
+template <int L> struct XlRsColsGzPersistOp : XlOpBase {
+    static constexpr bool kInLoHalf = true;
+    static constexpr int NT = xl_threads(L);
+    const XlRsParams& p; cf* stage; const cf* nextc; const cf* nextw; const cf* Hc; const cf* Hzc; cf* tile2; float* red;
+    XL_DEV void load(int i, cf* v, int stride) const {
+        if (i < p.N) xl_ld4(stage + (size_t)i * 2, v, v + stride);      // {cotangent, conj-field} of row i
+        else { v[0] = cf_zero(); v[stride] = cf_zero(); }
+    }
+    XL_DEV void after_first_sync(int tid) const {
+        if (nextc)
+            for (int i = tid; i < p.N; i += NT) {
+                xl_cp_async8(stage + (size_t)i * 2, nextc + (size_t)i * XL_V);
+                xl_cp_async8(stage + (size_t)i * 2 + 1, nextw + (size_t)i * XL_V);
+            }
+    }
+    XL_DEV void spec(int beta, const cf* v) const {
+        float acc = 0.f;
+        cf u[16];
+        const XlHRow<L> hr(beta);
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            const size_t o = (size_t)hr.row(q) * XL_V;
+            const cf t = cf_mul(v[q], xl_ldg(Hzc + o));
+            acc += v[16 + q].x * t.x + v[16 + q].y * t.y;  // Re(conj(w) * t)
+            u[q] = cf_mul(v[q], xl_ldg(Hc + o));
+        }
+        red[beta] += acc;
+        XlBfly<16, +1, false, false>::run(u);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) XlTileLine0Of2::st(tile2, 16 * beta + j, u + j, 16);
+    }
+    XL_DEV void store_vec(int, const cf*) const {}
+};
+template <int L> struct XlRsColsGzPersist {
+    static const char* name() { return "rs_cols_gz"; }
+    typedef XlRsParams Params;
+    static constexpr int NT = xl_threads(L);
+    static constexpr int NB = L / 16;
+    static size_t smem() { return (size_t)(xl_tile_elems(L, 2) + L + xl_tw_total(L)) * sizeof(cf) + (size_t)(NB + 32) * sizeof(float); }
+    XL_DEV static size_t column(const Params& p, int it, int* c, int* slot) {
+        const int col = it % L, f = p.f0 + it / L;
+        *c = col & 1;
+        *slot = col;
+        return (size_t)f * L * p.N + (size_t)(col >> 1) * p.N * XL_V + (col & 1);
+    }
+    XL_DEV static void run(const Params& p, cf* s) {
+        cf* stage = s + xl_tile_elems(L, 2);
+        cf* t = stage + L;
+        float* red = (float*)(t + xl_tw_total(L));
+        const int items = L * p.nfields;
+        int it = XL_BLOCK_X;
+        if (it >= items) return;
+        {
+            int c, slot;
+            const size_t o = column(p, it, &c, &slot);
+            XL_THREADS(tid, NT) {
+                for (int i = tid; i < p.N; i += NT) {
+                    xl_cp_async8(stage + (size_t)i * 2, p.spec + o + (size_t)i * XL_V);
+                    xl_cp_async8(stage + (size_t)i * 2 + 1, p.spec2 + o + (size_t)i * XL_V);
+                }
+                xl_cp_async_wait();
+                for (int i = tid; i < NB; i += NT) red[i] = 0.f;
+            }
+        }
+        XlFft<L, 2>::init_tw(t, p.tw);
+        for (; it < items; it += XL_GRID_X) {
+            int c, slot, cn, slotn;
+            const size_t o = column(p, it, &c, &slot);
+            const cf* Hc = xl_h_column<L>(p.H, slot);
+            const cf* Hzc = xl_h_column<L>(p.H2, slot);
+            XL_THREADS(tid, NT) {
+                for (int beta = tid; beta < L / 16; beta += NT)
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        if (beta & 1) continue;
+                        xl_prefetch_l2(Hc + (size_t)(q * (L / 16) + beta) * XL_V);
+                        xl_prefetch_l2(Hzc + (size_t)(q * (L / 16) + beta) * XL_V);
+                    }
+            }
+            const int nx = it + XL_GRID_X;
+            const size_t on = nx < items ? column(p, nx, &cn, &slotn) : 0;
+            XlRsColsGzPersistOp<L> op{{}, p, stage, nx < items ? p.spec + on : (const cf*)0, p.spec2 + on, Hc, Hzc, s, red};
+            XlFft<L, 2>::forward(s, t, op);
+            XL_SYNC();
+            XlRsColsGzOutOp<L> oo{{}, p, p.spec + (o - c), c};
+            XlFft<L, 1, XlTileLine0Of2>::inverse_tail(s, t, oo);
+            XL_THREADS(tid, NT) { xl_cp_async_wait(); }
+            XL_SYNC();
+        }
+        XL_THREADS(tid, NT) {
+            if (tid < 32) {
+                float a = 0.f;
+                for (int i = tid; i < NB; i += 32) a += red[i];
+                red[NB + tid] = a;
+            }
+        }
+        XL_SYNC();
+        XL_THREADS(tid, NT) {
+            if (tid == 0) {
+                double a = 0.0;
+                for (int i = 0; i < 32; ++i) a += (double)red[NB + i];
+                xl_atomic_add(p.gz, a);
+            }
+        }
+    }
+};
+#endif
+
 template <int L> struct XlRsColsGz {
     static const char* name() { return "rs_cols_gz"; }
     typedef XlRsParams Params;
