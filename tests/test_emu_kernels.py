@@ -348,7 +348,7 @@ def test_error_codes(emu):
     assert b"workspace" in emu.xl_last_error() or emu.xl_last_error() is not None
 
 
-@pytest.mark.parametrize("macros", [["XL_EXP_TREE_REDUCE", "XL_EXP_K2_PERSIST", "XL_EXP_K4_PERSIST"], ["XL_EXP_K4_STAGE", "XL_EXP_K2_STAGE", "XL_EXP_K4_PREFETCH", "XL_EXP_ROWS_3CTA"]])
+@pytest.mark.parametrize("macros", [["XL_EXP_TREE_REDUCE", "XL_EXP_K2_PERSIST", "XL_EXP_K4_PERSIST", "XL_EXP_CZT_PERSIST"], ["XL_EXP_K4_STAGE", "XL_EXP_K2_STAGE", "XL_EXP_K4_PREFETCH", "XL_EXP_ROWS_3CTA"]])
 def test_experiment_variants_keep_gradient_parity(tmp_path, macros):
     """The experiment variants of the library (macros XL_EXP_*, built with `python -m xlumina_b200.build --exp`, never part
     of the product build) must stay parity-green before they are timed: block reductions as shared-memory trees, and the
@@ -385,3 +385,26 @@ def test_experiment_variants_keep_gradient_parity(tmp_path, macros):
         assert abs(gz[0] - float(g["vjp_z"])) < 1e-4 * abs(float(g["vjp_z"])), name
         if "vjp_field" in g:
             assert rel_l2(gin.reshape(g["vjp_field"].shape), g["vjp_field"]) < TIGHT, name
+    # Bluestein family (paired access shapes are the ones the persistent variant replaces): forward and adjoint
+    for name, vect, key in (("czt_n32_m24x40", 0, "field"), ("czt_n40_same", 0, "field"), ("vczt_n24_m30", 1, None)):
+        g = golden(name)
+        fin = c64(g[key]) if key else c64(np.stack([g["Ex"], g["Ey"]]))
+        out = np.zeros(g["out"].shape, np.complex64)
+        czt_call(var, var.xl_czt_fwd, fin, out, g, vect)
+        assert rel_l2(out, g["out"]) < TIGHT, name
+        if "vjp_field" in g:
+            gin = np.zeros(fin.shape, np.complex64)
+            czt_call(var, var.xl_czt_bwd, c64(g["ct"]), gin, g, vect)
+            assert rel_l2(gin, g["vjp_field"]) < TIGHT, name
+    g = golden("highna_n24_m20")
+    x, xo, yo = g["x"], g["xout"], g["yout"]
+    N, Mx, My = len(x), len(xo), len(yo)
+    ws = np.zeros(var.xl_highna_workspace_bytes(N, Mx, My), np.uint8)
+    out = np.zeros(g["out"].shape, np.complex64)
+    args = (N, Mx, My, float(g["radius"]), float(g["f"]), float(g["wavelength"]), x[0], x[1] - x[0], x[0], x[1] - x[0],
+            xo[0], xo[-1], yo[0], yo[-1], 0, ptr(ws), ws.size, None)
+    assert var.xl_highna_fwd(ptr(c64(np.stack([g["Ex"], g["Ey"]]))), ptr(out), *args) == 0
+    assert rel_l2(out, g["out"]) < TIGHT
+    gin = np.zeros((2, N, N), np.complex64)
+    assert var.xl_highna_bwd(ptr(c64(g["ct"])), ptr(gin), *args) == 0
+    assert rel_l2(gin, g["vjp_field"]) < TIGHT

@@ -674,6 +674,22 @@ static void czt_out_const(XlCztParams& a, const CztCall& cc) {
 
 template <int PRO, int EPI, int ACC> static int czt_axis_launch_t(const XlCztParams& a, XlDim grid, xl_stream_t st) {
     int rc;
+#ifdef XL_EXP_CZT_PERSIST
+    if constexpr ((PRO == XL_PRO_NONE || PRO == XL_PRO_RSF) && ACC != XL_ACC_GENERIC) {
+        int slots = 3;      // the emulation uses 3 CTAs so that every CTA walks several items
+#ifndef XL_HOST_EMU
+        int dev = 0, sms = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        slots = 2 * (sms > 0 ? sms : 148);
+#endif
+        XlCztParams q = a;
+        q.pairs = grid.x;
+        const int items = grid.x * grid.y;
+        XL_FOR_L(a.L, rc = xl_launch<XlCztAxisPersist<XL, PRO, EPI, ACC>>(XlDim{items < slots ? items : slots, 1}, st, q));
+        return rc;
+    }
+#endif
     XL_FOR_L(a.L, rc = xl_launch<XlCztAxis<XL, PRO, EPI, ACC>>(grid, st, a));
     return rc;
 }

@@ -957,6 +957,9 @@ struct XlCztParams {
     double epi_cr, epi_ci; // complex constant on the output
     int epi_times_z;      // multiply the constant by z (CZT: z*dx*dy*lambda)
     double lens_R, lens_f, lens_s2;  // high-NA: radius, focal length, sin^2(theta_max)
+#ifdef XL_EXP_CZT_PERSIST
+    int pairs;            // line pairs per component (the persistent variant walks pairs * ncomp items)
+#endif
 };
 
 // lens factor row `comp` applied to (Ex,Ey):  apod*G*(RL[comp][0] Ex + RL[comp][1] Ey + RL[comp][2] Ez), Ez=(Ex X+Ey Y)/rho
@@ -1097,6 +1100,84 @@ template <int L, int PRO, int EPI, int ACC> struct XlCztAxis {
         XlFft<L, XL_V>::conv(s, t, op);
     }
 };
+
+#ifdef XL_EXP_CZT_PERSIST
+// Experiment (DESIGN.md queue item 1), not in the default build: persistent Bluestein axis pass for the single-plane
+// prologues (none / RS factor) of the paired, pruned access shapes.  2 x SM-count CTAs walk the (line pair, component)
+// items; the raw input of the NEXT item (m_in <= L/2 positions of both lines) is copied into a staging buffer by
+// asynchronous copies issued right after the first barrier of the current transform; the prologue factors are applied when
+// the staged operands are read.
+template <int L, int PRO, int EPI, int ACC> struct XlCztPersistOp : XlCztOp<L, PRO, EPI, ACC> {
+    static_assert(PRO == XL_PRO_NONE || PRO == XL_PRO_RSF, "single-plane prologues only");
+    static_assert(ACC != XL_ACC_GENERIC, "paired (pruned) access shapes only");
+    typedef XlCztOp<L, PRO, EPI, ACC> Base;
+    static constexpr int NT = xl_threads(L);
+    cf* stage; int next_lb, next_cl;   // next item of this CTA (next_lb < 0: none)
+    XL_DEV XlCztPersistOp(const Base& b, cf* st, int nlb, int ncl) : Base(b), stage(st), next_lb(nlb), next_cl(ncl) {}
+    XL_DEV static void issue(const XlCztParams& p, cf* stage, int lb, int cl, int tid) {
+        const cf* src = p.in + (long long)cl * p.in_comp;
+        for (int i = tid; i < p.m_in; i += NT) {
+            if (ACC == XL_ACC_PAIR_IN) {
+                xl_cp_async16(stage + 2 * i, src + lb + (long long)i * p.in_pos);
+            } else {
+                xl_cp_async8(stage + 2 * i, src + (long long)lb * p.in_line + (long long)i * p.in_pos);
+                xl_cp_async8(stage + 2 * i + 1, src + (long long)(lb + 1) * p.in_line + (long long)i * p.in_pos);
+            }
+        }
+    }
+    XL_DEV void after_first_sync(int tid) const {
+        if (next_lb >= 0) issue(this->p, stage, next_lb, next_cl, tid);
+    }
+    XL_DEV void load(int i, cf* v, int stride) const {
+        const XlCztParams& p = this->p;
+        const bool ok_i = i < p.m_in;
+        cf a[XL_V];
+        xl_ld4(stage + 2 * (ok_i ? i : 0), a, a + 1);
+        const cf pre = xl_ldg(p.pre + (ok_i ? i : 0));
+#pragma unroll
+        for (int l = 0; l < XL_V; ++l) {
+            cf x = (p.flags & XL_F_CONJ_IN) ? cf_conj(a[l]) : a[l];
+            if (PRO == XL_PRO_RSF) {          // F = h(X, Y; z), wave_optics.py:341,344
+                double X, Y;
+                this->coords(p.gpro, this->lb + l, i, &X, &Y);
+                x = cf_mul(x, xl_rs_h(X, Y, this->hc, 0));
+            }
+            x = cf_mul(x, pre);
+            v[l * stride] = ok_i ? x : cf_zero();
+        }
+    }
+};
+template <int L, int PRO, int EPI, int ACC> struct XlCztAxisPersist {
+    static const char* name() { return "czt_axis"; }
+    typedef XlCztParams Params;
+    static constexpr int NT = xl_threads(L);
+    static size_t smem() { return xl_smem_bytes(L, XL_V) + (size_t)L * sizeof(cf); }
+    XL_DEV static void run(const Params& p, cf* s) {
+        cf* stage = s + xl_tile_elems(L, XL_V);
+        cf* t = stage + L;
+        const int items = p.pairs * p.ncomp;
+        int it = XL_BLOCK_X;
+        if (it >= items) return;
+        XL_THREADS(tid, NT) {
+            XlCztPersistOp<L, PRO, EPI, ACC>::issue(p, stage, (it % p.pairs) * XL_V, it / p.pairs, tid);
+            xl_cp_async_wait();
+        }
+        XlFft<L, XL_V>::init_tw(t, p.tw);
+        const double z = p.z ? xl_ldg(p.z) : 0.0;
+        double cr = p.epi_cr, ci = p.epi_ci;
+        if (p.epi_times_z) { cr *= z; ci *= z; }
+        const XlRsHConst hc = xl_rs_hconst(z, p.k);
+        for (; it < items; it += XL_GRID_X) {
+            const int cl = it / p.pairs, lb = (it % p.pairs) * XL_V, nx = it + XL_GRID_X;
+            const XlCztOp<L, PRO, EPI, ACC> base{{}, p, lb, cl, p.c0 + cl, z, hc, make_float2((float)cr, (float)ci)};
+            const XlCztPersistOp<L, PRO, EPI, ACC> op(base, stage, nx < items ? (nx % p.pairs) * XL_V : -1, nx < items ? nx / p.pairs : 0);
+            XlFft<L, XL_V>::conv(s, t, op);
+            XL_THREADS(tid, NT) { xl_cp_async_wait(); }
+            XL_SYNC();
+        }
+    }
+};
+#endif
 
 // Bluestein tables for one axis (wave_optics.py:385-410, 430-459), all phases in fp64:
 //   pre[k]  = A^-k * h_k                       h_j = W^(j^2/2) on the principal branch of log W
