@@ -35,6 +35,7 @@ time)
             XLPROP_LIB="$PWD/$lib" timeout 120 python scripts/gpu_probe.py --nosmoke > "gpurun_out/ab_${name}_$pass.log" 2>&1
             echo "== $name (pass $pass)"; grep -E "us$|us " "gpurun_out/ab_${name}_$pass.log" | head -30
         done
-    done ;;
+    done
+    python scripts/ab_report.py gpurun_out | tee gpurun_out/ab_report.txt ;;
 *)  echo "usage: $0 build MACRO... | time"; exit 2 ;;
 esac
