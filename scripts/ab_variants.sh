@@ -25,6 +25,7 @@ time)
     for lib in build/libxlprop_*.so; do
         [ -f "$lib" ] || continue
         name=$(basename "$lib" .so)
+        case "$name" in *KEEP_SPECTRA*) export XL_KEEP_SPECTRA=1 ;; *) unset XL_KEEP_SPECTRA ;; esac
         XLPROP_LIB="$PWD/$lib" timeout 300 python -m pytest tests/test_gpu_parity.py -q -x -k "golden or four_f or 2048" > "gpurun_out/ab_${name}_parity.log" 2>&1
         echo "== $name parity: $(tail -1 "gpurun_out/ab_${name}_parity.log")"
     done
@@ -32,6 +33,7 @@ time)
         for lib in xlumina_b200/libxlprop.so build/libxlprop_*.so; do
             [ -f "$lib" ] || continue
             name=$(basename "$lib" .so)
+            case "$name" in *KEEP_SPECTRA*) export XL_KEEP_SPECTRA=1 ;; *) unset XL_KEEP_SPECTRA ;; esac
             XLPROP_LIB="$PWD/$lib" timeout 120 python scripts/gpu_probe.py --nosmoke > "gpurun_out/ab_${name}_$pass.log" 2>&1
             echo "== $name (pass $pass)"; grep -E "us$|us " "gpurun_out/ab_${name}_$pass.log" | head -30
         done

@@ -408,3 +408,49 @@ def test_experiment_variants_keep_gradient_parity(tmp_path, macros):
     gin = np.zeros((2, N, N), np.complex64)
     assert var.xl_highna_bwd(ptr(c64(g["ct"])), ptr(gin), *args) == 0
     assert rel_l2(gin, g["vjp_field"]) < TIGHT
+
+
+def test_experiment_variant_keep_spectra(tmp_path):
+    """XL_EXP_KEEP_SPECTRA (DESIGN.md queue item 2): the forward pass keeps its row spectra, the backward pass reads the
+    spectra of conj(U) from their mirrored columns instead of recomputing them.  Forward output, field VJP and d/dz through
+    the variant-only entry points against the RS and VRS fixtures (host emulation of the same sources)."""
+    import subprocess
+    src = os.path.join(ROOT, "xlumina_b200", "csrc", "xl_api.cu")
+    so = str(tmp_path / "emu_keep.so")
+    subprocess.check_call(["g++", "-x", "c++", "-std=c++17", "-O1", "-DXL_HOST_EMU", "-DXL_EXP_KEEP_SPECTRA", "-shared", "-fPIC", "-w", src, "-o", so])
+    var = ctypes.CDLL(so)
+    var.xl_rs_spectra_bytes.restype = ctypes.c_size_t
+    var.xl_rs_transfer_bytes.restype = ctypes.c_size_t
+    var.xl_rs_workspace_bytes.restype = ctypes.c_size_t
+    d, sz, vp, i32 = ctypes.c_double, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_int
+    var.xl_rs_fwd_keep.argtypes = [vp, vp, vp, vp, i32, i32, d, d, d, i32, vp, vp, sz, vp]
+    var.xl_vrs_fwd_keep.argtypes = [vp, vp, vp, vp, i32, d, d, d, d, d, i32, vp, vp, sz, vp]
+    var.xl_rs_bwd_kept.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, i32, d, d, d, i32, vp, vp, sz, vp]
+    var.xl_vrs_bwd_kept.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, d, d, d, d, d, i32, vp, vp, sz, vp]
+    for name, vrs in (("rs_n32_zpos", False), ("rs_n32_zneg", False), ("rs_n48_far", False), ("vrs_n24", True), ("vrs_n40_zneg", True)):
+        g = golden(name)
+        N = len(g["x"])
+        dx, k = float(g["x"][1] - g["x"][0]), 2 * np.pi / float(g["wavelength"])
+        zz = np.array([float(g["z"])])
+        nf = 3 if vrs else 1
+        fin = c64(np.stack([g["Ex"], g["Ey"]]) if vrs else g["field"])
+        out = np.zeros((nf, N, N), np.complex64)
+        H = np.zeros(var.xl_rs_transfer_bytes(N), np.uint8)
+        ws = np.zeros(var.xl_rs_workspace_bytes(N, nf, 1), np.uint8)
+        keep = np.zeros(var.xl_rs_spectra_bytes(N, nf), np.uint8)
+        ct, gin, gz = c64(g["ct"]), np.zeros_like(fin), np.zeros(1)
+        if vrs:
+            x0 = float(g["x"][0])
+            assert var.xl_vrs_fwd_keep(ptr(fin), ptr(out), ptr(H), ptr(zz), N, x0, x0, dx, dx, k, 0, ptr(keep), ptr(ws), ws.size, None) == 0
+            ws[:] = 0xA5                                  # the workspace is scratch: nothing of the forward pass may be needed from it
+            assert var.xl_vrs_bwd_kept(ptr(fin), ptr(out), ptr(ct), ptr(gin), ptr(gz), ptr(H), ptr(zz), N, x0, x0, dx, dx, k, 0,
+                                       ptr(keep), ptr(ws), ws.size, None) == 0
+        else:
+            assert var.xl_rs_fwd_keep(ptr(fin), ptr(out), ptr(H), ptr(zz), N, 1, dx, dx, k, 0, ptr(keep), ptr(ws), ws.size, None) == 0
+            ws[:] = 0xA5
+            assert var.xl_rs_bwd_kept(ptr(fin), ptr(out), ptr(ct), ptr(gin), ptr(gz), ptr(H), ptr(zz), N, 1, dx, dx, k, 0,
+                                      ptr(keep), ptr(ws), ws.size, None) == 0
+        assert rel_l2(out.reshape(g["out"].shape), g["out"]) < TIGHT, name
+        assert abs(gz[0] - float(g["vjp_z"])) < 1e-4 * abs(float(g["vjp_z"])), name
+        if "vjp_field" in g:
+            assert rel_l2(gin.reshape(g["vjp_field"].shape), g["vjp_field"]) < TIGHT, name

@@ -255,10 +255,23 @@ extern "C" int xl_rs_transfer(void* H, const double* z, int N, double dx, double
 // were slower or no faster: one launch per field and stage (keeps a field's spectra L2-resident but quantises each
 // 1024-CTA launch into 3.5 waves of 296), and a per-field software pipeline over auxiliary streams (grids this large do
 // not co-schedule: the second kernel only fills the first one's tail).
-static int rs_apply_impl(XlRsParams p, xl_stream_t st) {
+static int rs_apply_impl(XlRsParams p, xl_stream_t st, cf* keep = 0) {
     const int L = p.L, N = p.N;
     int rc;
     p.f0 = 0;
+#ifdef XL_EXP_KEEP_SPECTRA
+    if (keep) {   // row spectra into `keep` (left intact), column pass keep -> p.spec, inverse rows from p.spec
+        XlRsParams q = p;
+        q.spec = keep; q.spec2 = p.spec;
+        XL_FOR_L(L, rc = xl_launch<XlRsRowsFwd<XL>>(XlDim{xl_groups(N), p.nfields}, st, q));
+        if (rc) return rc;
+        XL_FOR_L(L, rc = xl_launch<XlRsColsKeep<XL>>(XlDim{L / XL_V, p.nfields}, st, q));
+        if (rc) return rc;
+        XL_FOR_L(L, rc = xl_launch<XlRsRowsInv<XL>>(XlDim{xl_groups(N), p.nfields}, st, p));
+        return rc;
+    }
+#endif
+    (void)keep;
     XL_FOR_L(L, rc = xl_launch<XlRsRowsFwd<XL>>(XlDim{xl_groups(N), p.nfields}, st, p));
     if (rc) return rc;
 #if defined(XL_EXP_K2_PERSIST)
@@ -285,7 +298,7 @@ static int rs_apply_impl(XlRsParams p, xl_stream_t st) {
 
 static int rs_fwd_common(const void* in, void* out, void* H, const double* z, int N, int nfields, int vrs,
                          double x0, double y0, double dx, double dy, double k, int flags,
-                         void* ws, size_t ws_bytes, xl_stream_t st) {
+                         void* ws, size_t ws_bytes, xl_stream_t st, void* keep = 0) {
     if (!in || !out || !H || !z || !ws) return xl_fail(XL_E_BAD_ARG, "rs_fwd: null pointer%s", "");
     XlRsParams p;
     int rc = rs_base_params(p, N, dx, dy, k);
@@ -297,7 +310,8 @@ static int rs_fwd_common(const void* in, void* out, void* H, const double* z, in
     p.in = (const cf*)in; p.out = (cf*)out; p.H = (cf*)H; p.z = z;
     p.nfields = nfields; p.x0 = x0; p.y0 = y0;
     p.flags = (flags & (XL_CONJ_IN | XL_CONJ_OUT)) | (vrs ? XL_F_VRS : 0);
-    return rs_apply_impl(p, st);
+    if (keep && (flags & XL_CONJ_IN)) return xl_fail(XL_E_BAD_ARG, "rs_fwd_keep: kept spectra are those of the unconjugated field%s", "");
+    return rs_apply_impl(p, st, (cf*)keep);
 }
 
 extern "C" int xl_rs_fwd(const void* in, void* out, void* H, const double* z, int N, int nfields,
@@ -312,7 +326,7 @@ extern "C" int xl_vrs_fwd(const void* exy, void* out, void* H, const double* z, 
 
 static int rs_bwd_common(const void* in, const void* out, const void* ct_out, void* ct_in, double* grad_z, const void* H,
                          const double* z, int N, int nfields, int vrs, double x0, double y0, double dx, double dy, double k,
-                         int flags, void* ws, size_t ws_bytes, xl_stream_t st) {
+                         int flags, void* ws, size_t ws_bytes, xl_stream_t st, const void* kept = 0) {
     if (!ct_out || !ct_in || !H || !ws || !z) return xl_fail(XL_E_BAD_ARG, "rs_bwd: null pointer%s", "");
     if (grad_z && (!in || !out)) return xl_fail(XL_E_BAD_ARG, "rs_bwd: grad_z needs the primal input and output%s", "");
     XlRsParams p;
@@ -341,12 +355,14 @@ static int rs_bwd_common(const void* in, const void* out, const void* ct_out, vo
             rc = xl_launch<XlDotZ>(XlDim{(int)((d.n + per - 1) / per), 1}, st, d);
             if (rc) return rc;
         }
-        // row spectra of conj(U) -> spec2
-        XlRsParams pw = p;
-        pw.in = (const cf*)in; pw.spec = p.spec2;
-        pw.flags = XL_F_CONJ_IN | (vrs ? XL_F_VRS : 0);
-        XL_FOR_L(L, rc = xl_launch<XlRsRowsFwd<XL>>(XlDim{xl_groups(N), nfields}, st, pw));
-        if (rc) return rc;
+        // row spectra of conj(U) -> spec2 (not needed when the forward pass kept its row spectra)
+        if (!kept) {
+            XlRsParams pw = p;
+            pw.in = (const cf*)in; pw.spec = p.spec2;
+            pw.flags = XL_F_CONJ_IN | (vrs ? XL_F_VRS : 0);
+            XL_FOR_L(L, rc = xl_launch<XlRsRowsFwd<XL>>(XlDim{xl_groups(N), nfields}, st, pw));
+            if (rc) return rc;
+        }
         // row spectra of the cotangent -> spec
         XlRsParams pc = p;
         pc.in = (const cf*)ct_out;
@@ -355,6 +371,12 @@ static int rs_bwd_common(const void* in, const void* out, const void* ct_out, vo
         if (rc) return rc;
         XlRsParams pg = p;
         pg.H2 = Hz; pg.gz = grad_z;
+#ifdef XL_EXP_KEEP_SPECTRA
+        if (kept) {
+            pg.spec2 = (cf*)kept;
+            XL_FOR_L(L, rc = xl_launch<XlRsColsGzKept<XL>>(XlDim{L, nfields}, st, pg));
+        } else
+#endif
 #if defined(XL_EXP_K4_PERSIST)
         {
             int slots = 3;
@@ -410,6 +432,37 @@ extern "C" int xl_vrs_bwd(const void* exy, const void* out, const void* ct_out, 
                           void* ws, size_t ws_bytes, void* stream) {
     return rs_bwd_common(exy, out, ct_out, ct_exy, grad_z, H, z, N, 3, 1, x0, y0, dx, dy, k, flags, ws, ws_bytes, (xl_stream_t)stream);
 }
+
+#ifdef XL_EXP_KEEP_SPECTRA
+// Entry points of the keep-spectra experiment (variant builds only; not part of include/xlprop.h).
+extern "C" size_t xl_rs_spectra_bytes(int N, int nfields) {
+    const int L = xl_rs_padded_length(N);
+    return L ? (size_t)nfields * L * N * sizeof(cf) : 0;
+}
+extern "C" int xl_rs_fwd_keep(const void* in, void* out, void* H, const double* z, int N, int nfields, double dx, double dy,
+                              double k, int flags, void* spectra, void* ws, size_t ws_bytes, void* stream) {
+    if (nfields < 1 || !spectra) return xl_fail(XL_E_BAD_ARG, "xl_rs_fwd_keep: bad argument%s", "");
+    return rs_fwd_common(in, out, H, z, N, nfields, 0, 0.0, 0.0, dx, dy, k, flags, ws, ws_bytes, (xl_stream_t)stream, spectra);
+}
+extern "C" int xl_vrs_fwd_keep(const void* exy, void* out, void* H, const double* z, int N, double x0, double y0, double dx,
+                               double dy, double k, int flags, void* spectra, void* ws, size_t ws_bytes, void* stream) {
+    if (!spectra) return xl_fail(XL_E_BAD_ARG, "xl_vrs_fwd_keep: bad argument%s", "");
+    return rs_fwd_common(exy, out, H, z, N, 3, 1, x0, y0, dx, dy, k, flags, ws, ws_bytes, (xl_stream_t)stream, spectra);
+}
+extern "C" int xl_rs_bwd_kept(const void* in, const void* out, const void* ct_out, void* ct_in, double* grad_z, const void* H,
+                              const double* z, int N, int nfields, double dx, double dy, double k, int flags,
+                              const void* spectra, void* ws, size_t ws_bytes, void* stream) {
+    if (nfields < 1) return xl_fail(XL_E_BAD_ARG, "xl_rs_bwd_kept: nfields < 1%s", "");
+    return rs_bwd_common(in, out, ct_out, ct_in, grad_z, H, z, N, nfields, 0, 0.0, 0.0, dx, dy, k, flags, ws, ws_bytes,
+                         (xl_stream_t)stream, spectra);
+}
+extern "C" int xl_vrs_bwd_kept(const void* exy, const void* out, const void* ct_out, void* ct_exy, double* grad_z, const void* H,
+                               const double* z, int N, double x0, double y0, double dx, double dy, double k, int flags,
+                               const void* spectra, void* ws, size_t ws_bytes, void* stream) {
+    return rs_bwd_common(exy, out, ct_out, ct_exy, grad_z, H, z, N, 3, 1, x0, y0, dx, dy, k, flags, ws, ws_bytes,
+                         (xl_stream_t)stream, spectra);
+}
+#endif
 
 // ================================================================================================ slab-decomposed RS
 // Stage-level entry points of the multi-GPU RS path (BASELINE.json cfg 5): the N x N field is split

@@ -759,6 +759,64 @@ template <int L> struct XlRsColsGzStage {
 };
 #endif
 
+#ifdef XL_EXP_KEEP_SPECTRA
+// Experiment (DESIGN.md queue item 2), not in the default build: the forward pass keeps its row spectra U^ (rs_cols then
+// writes its result to a second buffer instead of in place) and the d/dz column kernel reads the spectra of conj(U) from
+// them -- FFT(conj u)[kx] = conj(FFT(u)[-kx]): the mirrored column, conjugated -- so the backward pass does not recompute
+// them (one rs_rows_fwd launch per field less).
+template <int L> struct XlRsColsKeepOp : XlRsColsOp<L, false> {
+    typedef XlRsColsOp<L, false> Base;
+    cf* otile;
+    XL_DEV XlRsColsKeepOp(const Base& b, cf* o) : Base(b), otile(o) {}
+    XL_DEV void store_vec(int n, const cf* v) const {
+#pragma unroll
+        for (int j = 0; j < Base::R1 / 2; ++j) {
+            const int i = n + Base::S1 * j;
+            if (i < this->p.N) xl_st4(otile + (size_t)i * XL_V, v[j], v[Base::R1 + j]);
+        }
+    }
+};
+template <int L> struct XlRsColsKeep {       // p.spec: kept row spectra (read only), p.spec2: filtered spectra (written)
+    static const char* name() { return "rs_cols"; }
+    typedef XlRsParams Params;
+    static constexpr int NT = xl_threads(L);
+    static size_t smem() { return xl_smem_bytes(L, XL_V); }
+    XL_DEV static void run(const Params& p, cf* s) {
+        cf* t = s + xl_tile_elems(L, XL_V);
+        XlFft<L, XL_V>::init_tw(t, p.tw);
+        const int G = XL_BLOCK_X, f = p.f0 + XL_BLOCK_Y;
+        const cf* H0 = xl_h_column<L>(p.H, XL_V * G);
+        const cf* H1 = xl_h_column<L>(p.H, XL_V * G + 1);
+        const bool a0 = (((size_t)(H0 - p.H)) & 1) == 0, a1 = (((size_t)(H1 - p.H)) & 1) == 0;
+        const int hmode = (a0 && H1 == H0 + 1) ? 0 : ((a1 && H0 == H1 + 1) ? 1 : 2);
+        const size_t toff = (size_t)f * L * p.N + (size_t)G * p.N * XL_V;
+        const XlRsColsOp<L, false> base{{}, p, p.spec + toff, H0, H1, hmode, 0};
+        const XlRsColsKeepOp<L> op(base, p.spec2 + toff);
+        XlFft<L, XL_V>::conv(s, t, op);
+    }
+};
+template <int L> struct XlRsColsGzKeptOp : XlRsColsGzOp<L> {
+    typedef XlRsColsGzOp<L> Base;
+    int cm;          // half of the mirrored pair that holds the mirrored column
+    XL_DEV XlRsColsGzKeptOp(const Base& b, int m) : Base(b), cm(m) {}
+    XL_DEV void load(int i, cf* v, int stride) const {
+        const bool ok = i < this->p.N;
+        const cf a = this->ctile[ok ? (size_t)i * XL_V + this->c : 0];
+        const cf w = this->wtile[ok ? (size_t)i * XL_V + cm : 0];     // wtile: the MIRRORED pair of the kept forward spectra
+        v[0] = ok ? a : cf_zero();
+        v[stride] = ok ? cf_conj(w) : cf_zero();
+    }
+};
+template <int L> struct XlRsColsGzKept {     // p.spec: cotangent row spectra (in/out), p.spec2: kept forward row spectra of U
+    static const char* name() { return "rs_cols_gz"; }
+    typedef XlRsParams Params;
+    static constexpr int NT = xl_threads(L);
+    static constexpr int NB = L / 16;
+    static size_t smem() { return (size_t)(xl_tile_elems(L, 2) + xl_tile_elems(L, 1) + xl_tw_total(L)) * sizeof(cf) + (size_t)(NB + 32) * sizeof(float); }
+    XL_DEV static void run(const Params& p, cf* s);
+};
+#endif
+
 #ifdef XL_EXP_K4_PERSIST
 // Experiment (DESIGN.md queue items 1 / 1a), not in the default build: persistent rs_cols_gz.  In-place inverse on line 0 of
 // the two-line tile as in XlRsColsGzStage; the freed shared memory stages the NEXT column's inputs instead (cotangent
@@ -927,6 +985,46 @@ template <int L> struct XlRsColsGz {
         }
     }
 };
+
+#ifdef XL_EXP_KEEP_SPECTRA
+template <int L> XL_DEV void XlRsColsGzKept<L>::run(const Params& p, cf* s) {
+    cf* itile = s + xl_tile_elems(L, 2);
+    cf* t = itile + xl_tile_elems(L, 1);
+    float* red = (float*)(t + xl_tw_total(L));
+    XL_THREADS(tid, NT) { for (int i = tid; i < NB; i += NT) red[i] = 0.f; }
+    XlFft<L, 2>::init_tw(t, p.tw);
+    const int G = XL_BLOCK_X >> 1, c = XL_BLOCK_X & 1, f = p.f0 + XL_BLOCK_Y;   // one column per CTA
+    const size_t toff = (size_t)f * L * p.N + (size_t)G * p.N * XL_V;
+    const int slot = XL_V * G + c;
+    const int sm = xl_bin_to_slot_t<L>((L - xl_slot_to_bin_t<L>(slot)) & (L - 1));       // slot of the mirrored x frequency
+    const size_t moff = (size_t)f * L * p.N + (size_t)(sm >> 1) * p.N * XL_V;
+    {
+        const XlRsColsGzOp<L> base{{}, p, p.spec + toff, p.spec2 + moff, c, xl_h_column<L>(p.H, slot),
+                                   xl_h_column<L>(p.H2, slot), itile, red};
+        const XlRsColsGzKeptOp<L> op(base, sm & 1);
+        XlFft<L, 2>::forward(s, t, op);
+        XL_SYNC();
+        XlRsColsGzOutOp<L> oo{{}, p, p.spec + toff, c};
+        XlFft<L, 1>::inverse_tail(itile, t, oo);
+        XL_SYNC();
+    }
+    XL_THREADS(tid, NT) {
+        if (tid < 32) {
+            float a = 0.f;
+            for (int i = tid; i < NB; i += 32) a += red[i];
+            red[NB + tid] = a;
+        }
+    }
+    XL_SYNC();
+    XL_THREADS(tid, NT) {
+        if (tid == 0) {
+            double a = 0.0;
+            for (int i = 0; i < 32; ++i) a += (double)red[NB + i];
+            xl_atomic_add(p.gz, a);
+        }
+    }
+}
+#endif
 
 // ==================================================================================================================
 // Bluestein chirp-z axis pass  (wave_optics.py:385-460), with the fused prologue/epilogue factors of CZT_jit (:333-357),
