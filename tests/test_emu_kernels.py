@@ -348,7 +348,7 @@ def test_error_codes(emu):
     assert b"workspace" in emu.xl_last_error() or emu.xl_last_error() is not None
 
 
-@pytest.mark.parametrize("macros", [["XL_EXP_TREE_REDUCE", "XL_EXP_K2_PERSIST", "XL_EXP_K4_PERSIST", "XL_EXP_CZT_PERSIST"], ["XL_EXP_K4_STAGE", "XL_EXP_K2_STAGE", "XL_EXP_K4_PREFETCH", "XL_EXP_ROWS_3CTA"]])
+@pytest.mark.parametrize("macros", [["XL_EXP_TREE_REDUCE", "XL_EXP_K2_PERSIST", "XL_EXP_K4_PERSIST", "XL_EXP_CZT_PERSIST"], ["XL_EXP_K4_STAGE", "XL_EXP_K2_STAGE", "XL_EXP_K4_PREFETCH", "XL_EXP_ROWS_3CTA"], ["XL_EXP_FIELD_MINOR", "XL_EXP_K4_PREFETCH"]])
 def test_experiment_variants_keep_gradient_parity(tmp_path, macros):
     """The experiment variants of the library (macros XL_EXP_*, built with `python -m xlumina_b200.build --exp`, never part
     of the product build) must stay parity-green before they are timed: block reductions as shared-memory trees, and the

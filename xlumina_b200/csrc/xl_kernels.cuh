@@ -290,7 +290,11 @@ template <int L> struct XlRsCols {
     XL_DEV static void run(const Params& p, cf* s) {
         cf* t = s + xl_tile_elems(L, XL_V);
         XlFft<L, XL_V>::init_tw(t, p.tw);
+#ifdef XL_EXP_FIELD_MINOR   // experiment: the fields of one column pair run back to back, so they share its transfer function in L2
+        const int lin = XL_BLOCK_Y * XL_GRID_X + XL_BLOCK_X, G = lin / p.nfields, f = p.f0 + lin % p.nfields;
+#else
         const int G = XL_BLOCK_X, f = p.f0 + XL_BLOCK_Y;
+#endif
         const cf* H0 = xl_h_column<L>(p.H, XL_V * G);
         const cf* H1 = xl_h_column<L>(p.H, XL_V * G + 1);
         const bool a0 = (((size_t)(H0 - p.H)) & 1) == 0, a1 = (((size_t)(H1 - p.H)) & 1) == 0;
@@ -942,7 +946,12 @@ template <int L> struct XlRsColsGz {
         float* red = (float*)(t + xl_tw_total(L));
         XL_THREADS(tid, NT) { for (int i = tid; i < NB; i += NT) red[i] = 0.f; }
         XlFft<L, 2>::init_tw(t, p.tw);
+#ifdef XL_EXP_FIELD_MINOR
+        const int lin = XL_BLOCK_Y * XL_GRID_X + XL_BLOCK_X, col = lin / p.nfields, f = p.f0 + lin % p.nfields;
+        const int G = col >> 1, c = col & 1;
+#else
         const int G = XL_BLOCK_X >> 1, c = XL_BLOCK_X & 1, f = p.f0 + XL_BLOCK_Y;   // one column per CTA
+#endif
         const size_t toff = (size_t)f * L * p.N + (size_t)G * p.N * XL_V;
 #ifdef XL_EXP_K4_PREFETCH   // experiment: as in rs_cols, start moving both transfer-function columns into L2 before the FFT passes
         {
