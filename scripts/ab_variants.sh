@@ -15,7 +15,7 @@ build)
     # "all": every experiment of DESIGN.md's queue that exists in the tree, one library each, plus the other partitioning
     if [ "${1:-}" = "all" ]; then
         set -- XL_EXP_K4_PERSIST XL_EXP_K4_STAGE XL_EXP_K2_PERSIST XL_EXP_K2_STAGE XL_EXP_CZT_PERSIST XL_EXP_KEEP_SPECTRA \
-               XL_EXP_K4_PREFETCH XL_EXP_TREE_REDUCE XL_EXP_ROWS_3CTA split=2 \
+               XL_EXP_K4_PREFETCH XL_EXP_TREE_REDUCE XL_EXP_ROWS_3CTA XL_EXP_FIELD_MINOR split=2 \
                XL_EXP_K4_PERSIST,XL_EXP_K2_PERSIST,XL_EXP_CZT_PERSIST,XL_EXP_TREE_REDUCE
     fi
     for m in "$@"; do
