@@ -354,13 +354,9 @@ def test_experiment_variants_keep_gradient_parity(tmp_path, macros):
     of the product build) must stay parity-green before they are timed: block reductions as shared-memory trees, and the
     staged in-place rs_cols_gz, against the field-VJP and d/dz fixtures of RS and VRS, through the host emulation of the
     same sources (the emulation copies at issue time where the device copies asynchronously)."""
-    import subprocess
+    from conftest import emu_variant_path
     from xlumina_b200 import _lib
-    src = os.path.join(ROOT, "xlumina_b200", "csrc", "xl_api.cu")
-    so = str(tmp_path / "emu_variant.so")
-    subprocess.check_call(["g++", "-x", "c++", "-std=c++17", "-O1", "-DXL_HOST_EMU"] + ["-D" + m for m in macros] +
-                          ["-shared", "-fPIC", "-w", src, "-o", so])
-    var = _lib.declare(ctypes.CDLL(so))
+    var = _lib.declare(ctypes.CDLL(emu_variant_path(macros)))
     for name, vrs in (("rs_n32_zpos", False), ("rs_n48_far", False), ("vrs_n24", True), ("vrs_n40_zneg", True)):
         g = golden(name)
         N = len(g["x"])
@@ -414,11 +410,8 @@ def test_experiment_variant_keep_spectra(tmp_path):
     """XL_EXP_KEEP_SPECTRA (DESIGN.md queue item 2): the forward pass keeps its row spectra, the backward pass reads the
     spectra of conj(U) from their mirrored columns instead of recomputing them.  Forward output, field VJP and d/dz through
     the variant-only entry points against the RS and VRS fixtures (host emulation of the same sources)."""
-    import subprocess
-    src = os.path.join(ROOT, "xlumina_b200", "csrc", "xl_api.cu")
-    so = str(tmp_path / "emu_keep.so")
-    subprocess.check_call(["g++", "-x", "c++", "-std=c++17", "-O1", "-DXL_HOST_EMU", "-DXL_EXP_KEEP_SPECTRA", "-shared", "-fPIC", "-w", src, "-o", so])
-    var = ctypes.CDLL(so)
+    from conftest import emu_variant_path
+    var = ctypes.CDLL(emu_variant_path(["XL_EXP_KEEP_SPECTRA"]))
     var.xl_rs_spectra_bytes.restype = ctypes.c_size_t
     var.xl_rs_transfer_bytes.restype = ctypes.c_size_t
     var.xl_rs_workspace_bytes.restype = ctypes.c_size_t

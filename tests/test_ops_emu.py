@@ -228,14 +228,9 @@ def test_missing_distance_gradients_are_refused_not_dropped(ops_on_emu):
 def test_keep_spectra_experiment_through_the_host_layer(monkeypatch, tmp_path):
     """ops.KEEP_SPECTRA with a library built with XL_EXP_KEEP_SPECTRA (development only): the sharp-focus table (16 VRS with
     distance gradients) gives the same loss gradients as the fixtures; with the product library the switch does nothing."""
-    import os
-    import subprocess
-    from conftest import ROOT
+    from conftest import emu_variant_path
     from test_elements import directional, sharp_focus_losses, sharp_focus_problem
-    src = os.path.join(ROOT, "xlumina_b200", "csrc", "xl_api.cu")
-    so = str(tmp_path / "emu_keep.so")
-    subprocess.check_call(["g++", "-x", "c++", "-std=c++17", "-O1", "-DXL_HOST_EMU", "-DXL_EXP_KEEP_SPECTRA", "-shared", "-fPIC", "-w", src, "-o", so])
-    var = _lib.declare(ctypes.CDLL(so))
+    var = _lib.declare(ctypes.CDLL(emu_variant_path(["XL_EXP_KEEP_SPECTRA"])))
     monkeypatch.setattr(_lib, "_lib", var)
     monkeypatch.setattr(ops, "_require_device", lambda t: None)
     monkeypatch.setattr(ops, "_stream", lambda t: ctypes.c_void_p(0))
