@@ -11,7 +11,9 @@ torch is plumbing only (device memory, streams, autograd graph); all arithmetic 
 on a CUDA device; there is no CPU path.  complex128 inputs are cast to complex64 on entry and back on exit (the reference
 runs in x64; the kernels are complex64 with fp64 phase generation).
 """
+import contextlib
 import ctypes
+import functools
 import os
 
 import torch
@@ -25,6 +27,18 @@ __all__ = ["rs_propagation", "vrs_propagation", "czt", "vczt", "highna_focus", "
 def _require_device(t):
     if not t.is_cuda:
         raise _lib.XlpropError("xlumina_b200 operators need CUDA tensors (no CPU fallback)")
+
+
+def _on_device(fn):
+    """Run an autograd.Function forward / backward with the CUDA device of its first tensor argument current: the library
+    uses the current device for its per-device tables and kernel attributes, the stream comes from the tensor's device."""
+    @functools.wraps(fn)
+    def wrapped(ctx, *args):
+        t = next((a for a in args if isinstance(a, torch.Tensor)), None)
+        guard = torch.cuda.device(t.device) if t is not None and t.is_cuda else contextlib.nullcontext()
+        with guard:
+            return fn(ctx, *args)
+    return wrapped
 
 
 def _stream(t):
@@ -193,6 +207,7 @@ class _RS(torch.autograd.Function):
     """field (F,N,N) c64, z (1,) f64 -> (F,N,N).  backward = same complex-symmetric operator + Parseval d/dz."""
 
     @staticmethod
+    @_on_device
     def forward(ctx, field, z, dx, dy, k, zkey=None, zobj=None):
         _require_device(field)
         L = _lib.lib()
@@ -215,6 +230,7 @@ class _RS(torch.autograd.Function):
         return out
 
     @staticmethod
+    @_on_device
     def backward(ctx, g):
         field, z, H, out = ctx.saved_tensors[:4]
         spectra = ctx.saved_tensors[4] if len(ctx.saved_tensors) > 4 else None
@@ -241,6 +257,7 @@ class _VRS(torch.autograd.Function):
     """exy (2,N,N) -> (3,N,N); Ez = (Ex X + Ey Y)/r formed at load (vectorized_optics.py:258-261)."""
 
     @staticmethod
+    @_on_device
     def forward(ctx, exy, z, x0, y0, dx, dy, k, zkey=None, zobj=None, hshare=None):
         _require_device(exy)
         L = _lib.lib()
@@ -268,6 +285,7 @@ class _VRS(torch.autograd.Function):
         return out
 
     @staticmethod
+    @_on_device
     def backward(ctx, g):
         exy, z, H, out = ctx.saved_tensors[:4]
         spectra = ctx.saved_tensors[4] if len(ctx.saved_tensors) > 4 else None
@@ -297,6 +315,7 @@ class _RSLarge(torch.autograd.Function):
     Differentiable in the field (the operator is complex-symmetric); d/dz is not available on this path."""
 
     @staticmethod
+    @_on_device
     def forward(ctx, field, z, dx, dy, k):
         from . import slab
         _require_device(field)
@@ -308,6 +327,7 @@ class _RSLarge(torch.autograd.Function):
         return torch.stack(outs)
 
     @staticmethod
+    @_on_device
     def backward(ctx, g):
         from . import slab
         if ctx.needs_input_grad[1]:
@@ -378,14 +398,16 @@ def rs_transfer(z, N, dx, dy, k, device, deriv=False):
     H = torch.empty(L.xl_rs_transfer_bytes(N), dtype=torch.uint8, device=device)
     _require_device(H)
     zt = _as_z(z, H)
-    _lib.check(L.xl_rs_transfer(_ptr(H), _ptr(zt), N, float(dx), float(dy), float(k), 1 if deriv else 0, _stream(H)),
-               "xl_rs_transfer")
+    with torch.cuda.device(H.device):
+        _lib.check(L.xl_rs_transfer(_ptr(H), _ptr(zt), N, float(dx), float(dy), float(k), 1 if deriv else 0, _stream(H)),
+                   "xl_rs_transfer")
     return H
 
 
 # ---------------------------------------------------------------------------------------------- CZT / VCZT / high-NA
 class _CZT(torch.autograd.Function):
     @staticmethod
+    @_on_device
     def forward(ctx, fin, z, lam, vect, gin, gout):
         _require_device(fin)
         L = _lib.lib()
@@ -404,6 +426,7 @@ class _CZT(torch.autograd.Function):
         return out
 
     @staticmethod
+    @_on_device
     def backward(ctx, g):
         (z,) = ctx.saved_tensors
         lam, vect, gin, gout, N, shape = ctx.meta
@@ -420,6 +443,7 @@ class _CZT(torch.autograd.Function):
 
 class _HighNA(torch.autograd.Function):
     @staticmethod
+    @_on_device
     def forward(ctx, exy, radius, f, lam, gin, gout):
         _require_device(exy)
         L = _lib.lib()
@@ -437,6 +461,7 @@ class _HighNA(torch.autograd.Function):
         return out
 
     @staticmethod
+    @_on_device
     def backward(ctx, g):
         radius, f, lam, gin, gout, N = ctx.meta
         (x0, dx, y0, dy) = gin

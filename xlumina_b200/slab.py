@@ -18,6 +18,7 @@ loads, the inverse one is a pointwise combine kernel over a scratch buffer).  Wi
 single-GPU path for grids above 2048^2.  Round-1 limits: scalar fields, forward and field-VJP (the operator is
 complex-symmetric: `rs_slab_vjp`); d/dz is available on the fused single-GPU path (N <= 2048) only.
 """
+import contextlib
 import ctypes
 
 import torch
@@ -30,6 +31,11 @@ __all__ = ["rs_propagation_slab", "rs_slab_vjp", "SlabPlan"]
 
 def _ptr(t):
     return ctypes.c_void_p(t.data_ptr())
+
+
+def _device_of(t):
+    """Context that makes the tensor's CUDA device current (the library keys its tables on the current device)."""
+    return torch.cuda.device(t.device) if t.is_cuda else contextlib.nullcontext()
 
 
 def _stream_of(t):
@@ -69,8 +75,7 @@ def _all_to_all(buf, group):
     if _world_rank(group)[0] == 1:
         return buf            # one rank: the exchanged layout [1][pairs][rows][2] IS the row-side layout
     out = torch.empty_like(buf)
-    if True:
-        dist.all_to_all_single(torch.view_as_real(out).reshape(-1), torch.view_as_real(buf).reshape(-1), group=group)
+    dist.all_to_all_single(torch.view_as_real(out).reshape(-1), torch.view_as_real(buf).reshape(-1), group=group)
     return out
 
 
@@ -114,11 +119,12 @@ def rs_propagation_slab(field_local, z, dx, dy, k, group=None, lib=None, transfe
     plan = SlabPlan(N, world, lib)
     if f.shape != (plan.rows, N):
         raise ValueError(f"slab RS: this rank's slab must be ({plan.rows}, {N}), got {tuple(f.shape)}")
-    if transfer is None:
-        zt = z if isinstance(z, torch.Tensor) else torch.full((1,), float(z), dtype=torch.float64, device=f.device)
-        zt = zt.to(device=f.device, dtype=torch.float64).reshape(1)
-        transfer = _transfer_slab(plan, zt, float(dx), float(dy), float(k), rank, f, lib, group)
-    out = _apply(plan, f, transfer, 0, lib, group)
+    with _device_of(f):
+        if transfer is None:
+            zt = z if isinstance(z, torch.Tensor) else torch.full((1,), float(z), dtype=torch.float64, device=f.device)
+            zt = zt.to(device=f.device, dtype=torch.float64).reshape(1)
+            transfer = _transfer_slab(plan, zt, float(dx), float(dy), float(k), rank, f, lib, group)
+        out = _apply(plan, f, transfer, 0, lib, group)
     return (out, transfer) if return_transfer else out
 
 
@@ -129,4 +135,5 @@ def rs_slab_vjp(ct_local, transfer, group=None, lib=None):
     world, _ = _world_rank(group)
     c = ct_local.to(torch.complex64).resolve_conj().contiguous()
     plan = SlabPlan(c.shape[-1], world, lib)
-    return _apply(plan, c, transfer, 0, lib, group)
+    with _device_of(c):
+        return _apply(plan, c, transfer, 0, lib, group)

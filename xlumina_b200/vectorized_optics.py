@@ -101,7 +101,7 @@ class PolarizedLightSource(VectorizedLight):
     def gaussian_beam(self, w0, jones_vector, center=(0, 0), z_w0=(0, 0), alpha=0):
         """vectorized_optics.py:402-465."""
         g = _gaussian_beam(self.x, self.y, self.k, self.n, w0, 1.0, center, z_w0, alpha)
-        j = np.array(jones_vector, dtype=np.float64)
+        j = np.asarray(jones_vector, dtype=np.complex128)   # complex Jones vectors (circular polarisation) as in the reference
         j = j / np.linalg.norm(j)
         self.Ex = torch.as_tensor((j[0] * g).astype(np.complex64), device=self.device)
         self.Ey = torch.as_tensor((j[1] * g).astype(np.complex64), device=self.device)
@@ -109,7 +109,7 @@ class PolarizedLightSource(VectorizedLight):
 
     def plane_wave(self, jones_vector, theta=0, phi=0, z0=0):
         """vectorized_optics.py:467-490."""
-        j = np.array(jones_vector, dtype=np.float64)
+        j = np.asarray(jones_vector, dtype=np.complex128)   # complex Jones vectors (circular polarisation) as in the reference
         j = j / np.linalg.norm(j)
         X, Y = np.meshgrid(self.x, self.y)
         pw = np.exp(1j * self.k * (X * np.sin(theta) * np.cos(phi) + Y * np.sin(theta) * np.sin(phi) + z0 * np.cos(theta)))
