@@ -35,7 +35,8 @@ def emu():
     from xlumina_b200 import _lib
     out = os.path.join(ROOT, "tests", "emu", "libxlprop_emu.so")
     src = os.path.join(ROOT, "xlumina_b200", "csrc", "xl_api.cu")
-    deps = [os.path.join(ROOT, "xlumina_b200", "csrc", f) for f in ("xl_api.cu", "xl_kernels.cuh", "xl_long.cuh", "xl_fft.cuh", "xl_platform.h")]
+    import glob
+    deps = glob.glob(os.path.join(ROOT, "xlumina_b200", "csrc", "*"))
     if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
         os.makedirs(os.path.dirname(out), exist_ok=True)
         subprocess.check_call(["g++", "-x", "c++", "-std=c++17", "-O2", "-DXL_HOST_EMU", "-shared", "-fPIC", "-w", src, "-o", out])
@@ -47,7 +48,8 @@ def emu_variant_path(macros):
     tag = "_".join(m.replace("XL_EXP_", "") for m in macros)
     out = os.path.join(ROOT, "tests", "emu", f"libxlprop_emu_{tag}.so")
     src = os.path.join(ROOT, "xlumina_b200", "csrc", "xl_api.cu")
-    deps = [os.path.join(ROOT, "xlumina_b200", "csrc", f) for f in ("xl_api.cu", "xl_kernels.cuh", "xl_long.cuh", "xl_fft.cuh", "xl_platform.h")]
+    import glob
+    deps = glob.glob(os.path.join(ROOT, "xlumina_b200", "csrc", "*"))
     if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
         os.makedirs(os.path.dirname(out), exist_ok=True)
         subprocess.check_call(["g++", "-x", "c++", "-std=c++17", "-O1", "-DXL_HOST_EMU"] + ["-D" + m for m in macros] +

@@ -346,104 +346,3 @@ def test_error_codes(emu):
     assert emu.xl_czt_padded_length(32, 33) == 0           # m+M-1 == 64: the reference raises too
     assert emu.xl_czt_padded_length(2048, 2048) == 4096 and emu.xl_czt_padded_length(1024, 400) == 2048
     assert b"workspace" in emu.xl_last_error() or emu.xl_last_error() is not None
-
-
-@pytest.mark.parametrize("macros", [["XL_EXP_TREE_REDUCE", "XL_EXP_K2_PERSIST", "XL_EXP_K4_PERSIST", "XL_EXP_CZT_PERSIST"], ["XL_EXP_K4_STAGE", "XL_EXP_K2_STAGE", "XL_EXP_K4_PREFETCH", "XL_EXP_ROWS_3CTA"], ["XL_EXP_FIELD_MINOR", "XL_EXP_K4_PREFETCH"]])
-def test_experiment_variants_keep_gradient_parity(tmp_path, macros):
-    """The experiment variants of the library (macros XL_EXP_*, built with `python -m xlumina_b200.build --exp`, never part
-    of the product build) must stay parity-green before they are timed: block reductions as shared-memory trees, and the
-    staged in-place rs_cols_gz, against the field-VJP and d/dz fixtures of RS and VRS, through the host emulation of the
-    same sources (the emulation copies at issue time where the device copies asynchronously)."""
-    from conftest import emu_variant_path
-    from xlumina_b200 import _lib
-    var = _lib.declare(ctypes.CDLL(emu_variant_path(macros)))
-    for name, vrs in (("rs_n32_zpos", False), ("rs_n48_far", False), ("vrs_n24", True), ("vrs_n40_zneg", True)):
-        g = golden(name)
-        N = len(g["x"])
-        dx, k = float(g["x"][1] - g["x"][0]), 2 * np.pi / float(g["wavelength"])
-        zz = np.array([float(g["z"])])
-        nf = 3 if vrs else 1
-        fin = c64(np.stack([g["Ex"], g["Ey"]]) if vrs else g["field"])
-        out = np.zeros((nf, N, N), np.complex64)
-        H = np.zeros(var.xl_rs_transfer_bytes(N), np.uint8)
-        ws = np.zeros(var.xl_rs_workspace_bytes(N, nf, 1), np.uint8)
-        ct, gin, gz = c64(g["ct"]), np.zeros_like(fin), np.zeros(1)
-        if vrs:
-            x0 = float(g["x"][0])
-            assert var.xl_vrs_fwd(ptr(fin), ptr(out), ptr(H), ptr(zz), N, x0, x0, dx, dx, k, 0, ptr(ws), ws.size, None) == 0
-            assert var.xl_vrs_bwd(ptr(fin), ptr(out), ptr(ct), ptr(gin), ptr(gz), ptr(H), ptr(zz), N, x0, x0, dx, dx, k, 0,
-                                  ptr(ws), ws.size, None) == 0
-        else:
-            assert var.xl_rs_fwd(ptr(fin), ptr(out), ptr(H), ptr(zz), N, 1, dx, dx, k, 0, ptr(ws), ws.size, None) == 0
-            assert var.xl_rs_bwd(ptr(fin), ptr(out), ptr(ct), ptr(gin), ptr(gz), ptr(H), ptr(zz), N, 1, dx, dx, k, 0,
-                                 ptr(ws), ws.size, None) == 0
-        assert rel_l2(out.reshape(g["out"].shape), g["out"]) < TIGHT, name
-        assert abs(gz[0] - float(g["vjp_z"])) < 1e-4 * abs(float(g["vjp_z"])), name
-        if "vjp_field" in g:
-            assert rel_l2(gin.reshape(g["vjp_field"].shape), g["vjp_field"]) < TIGHT, name
-    # Bluestein family (paired access shapes are the ones the persistent variant replaces): forward and adjoint
-    for name, vect, key in (("czt_n32_m24x40", 0, "field"), ("czt_n40_same", 0, "field"), ("vczt_n24_m30", 1, None)):
-        g = golden(name)
-        fin = c64(g[key]) if key else c64(np.stack([g["Ex"], g["Ey"]]))
-        out = np.zeros(g["out"].shape, np.complex64)
-        czt_call(var, var.xl_czt_fwd, fin, out, g, vect)
-        assert rel_l2(out, g["out"]) < TIGHT, name
-        if "vjp_field" in g:
-            gin = np.zeros(fin.shape, np.complex64)
-            czt_call(var, var.xl_czt_bwd, c64(g["ct"]), gin, g, vect)
-            assert rel_l2(gin, g["vjp_field"]) < TIGHT, name
-    g = golden("highna_n24_m20")
-    x, xo, yo = g["x"], g["xout"], g["yout"]
-    N, Mx, My = len(x), len(xo), len(yo)
-    ws = np.zeros(var.xl_highna_workspace_bytes(N, Mx, My), np.uint8)
-    out = np.zeros(g["out"].shape, np.complex64)
-    args = (N, Mx, My, float(g["radius"]), float(g["f"]), float(g["wavelength"]), x[0], x[1] - x[0], x[0], x[1] - x[0],
-            xo[0], xo[-1], yo[0], yo[-1], 0, ptr(ws), ws.size, None)
-    assert var.xl_highna_fwd(ptr(c64(np.stack([g["Ex"], g["Ey"]]))), ptr(out), *args) == 0
-    assert rel_l2(out, g["out"]) < TIGHT
-    gin = np.zeros((2, N, N), np.complex64)
-    assert var.xl_highna_bwd(ptr(c64(g["ct"])), ptr(gin), *args) == 0
-    assert rel_l2(gin, g["vjp_field"]) < TIGHT
-
-
-def test_experiment_variant_keep_spectra(tmp_path):
-    """XL_EXP_KEEP_SPECTRA (DESIGN.md queue item 2): the forward pass keeps its row spectra, the backward pass reads the
-    spectra of conj(U) from their mirrored columns instead of recomputing them.  Forward output, field VJP and d/dz through
-    the variant-only entry points against the RS and VRS fixtures (host emulation of the same sources)."""
-    from conftest import emu_variant_path
-    var = ctypes.CDLL(emu_variant_path(["XL_EXP_KEEP_SPECTRA"]))
-    var.xl_rs_spectra_bytes.restype = ctypes.c_size_t
-    var.xl_rs_transfer_bytes.restype = ctypes.c_size_t
-    var.xl_rs_workspace_bytes.restype = ctypes.c_size_t
-    d, sz, vp, i32 = ctypes.c_double, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_int
-    var.xl_rs_fwd_keep.argtypes = [vp, vp, vp, vp, i32, i32, d, d, d, i32, vp, vp, sz, vp]
-    var.xl_vrs_fwd_keep.argtypes = [vp, vp, vp, vp, i32, d, d, d, d, d, i32, vp, vp, sz, vp]
-    var.xl_rs_bwd_kept.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, i32, d, d, d, i32, vp, vp, sz, vp]
-    var.xl_vrs_bwd_kept.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, d, d, d, d, d, i32, vp, vp, sz, vp]
-    for name, vrs in (("rs_n32_zpos", False), ("rs_n32_zneg", False), ("rs_n48_far", False), ("vrs_n24", True), ("vrs_n40_zneg", True)):
-        g = golden(name)
-        N = len(g["x"])
-        dx, k = float(g["x"][1] - g["x"][0]), 2 * np.pi / float(g["wavelength"])
-        zz = np.array([float(g["z"])])
-        nf = 3 if vrs else 1
-        fin = c64(np.stack([g["Ex"], g["Ey"]]) if vrs else g["field"])
-        out = np.zeros((nf, N, N), np.complex64)
-        H = np.zeros(var.xl_rs_transfer_bytes(N), np.uint8)
-        ws = np.zeros(var.xl_rs_workspace_bytes(N, nf, 1), np.uint8)
-        keep = np.zeros(var.xl_rs_spectra_bytes(N, nf), np.uint8)
-        ct, gin, gz = c64(g["ct"]), np.zeros_like(fin), np.zeros(1)
-        if vrs:
-            x0 = float(g["x"][0])
-            assert var.xl_vrs_fwd_keep(ptr(fin), ptr(out), ptr(H), ptr(zz), N, x0, x0, dx, dx, k, 0, ptr(keep), ptr(ws), ws.size, None) == 0
-            ws[:] = 0xA5                                  # the workspace is scratch: nothing of the forward pass may be needed from it
-            assert var.xl_vrs_bwd_kept(ptr(fin), ptr(out), ptr(ct), ptr(gin), ptr(gz), ptr(H), ptr(zz), N, x0, x0, dx, dx, k, 0,
-                                       ptr(keep), ptr(ws), ws.size, None) == 0
-        else:
-            assert var.xl_rs_fwd_keep(ptr(fin), ptr(out), ptr(H), ptr(zz), N, 1, dx, dx, k, 0, ptr(keep), ptr(ws), ws.size, None) == 0
-            ws[:] = 0xA5
-            assert var.xl_rs_bwd_kept(ptr(fin), ptr(out), ptr(ct), ptr(gin), ptr(gz), ptr(H), ptr(zz), N, 1, dx, dx, k, 0,
-                                      ptr(keep), ptr(ws), ws.size, None) == 0
-        assert rel_l2(out.reshape(g["out"].shape), g["out"]) < TIGHT, name
-        assert abs(gz[0] - float(g["vjp_z"])) < 1e-4 * abs(float(g["vjp_z"])), name
-        if "vjp_field" in g:
-            assert rel_l2(gin.reshape(g["vjp_field"].shape), g["vjp_field"]) < TIGHT, name

@@ -1,0 +1,254 @@
+// xl_czt.cu -- C ABI of the CZT / VCZT / high-NA path (include/xlprop.h) over the Bluestein kernels in xl_kernels.cuh.
+#include "xl_host.h"
+
+// ================================================================================================ CZT family
+struct CztPlan {
+    int N, Mx, My, Ly, Lx, ncomp;
+    cf *pre_y, *post_y, *ft_y, *ftT_y, *pre_x, *post_x, *ft_x, *ftT_x;
+    cf* mid;   // [ncomp][N][My]
+    cf* tmp3;  // [3][N][N]
+};
+static size_t czt_ws_bytes(int N, int Mx, int My, int ncomp) {
+    int Ly = xl_czt_padded_length(N, My), Lx = xl_czt_padded_length(N, Mx);
+    if (!Ly || !Lx) return 0;
+    size_t t = 0;
+    t += 2 * align_up((size_t)N * sizeof(cf)) + align_up((size_t)My * sizeof(cf)) + align_up((size_t)Mx * sizeof(cf));
+    t += 2 * align_up((size_t)Ly * sizeof(cf)) + 2 * align_up((size_t)Lx * sizeof(cf));
+    t += align_up((size_t)ncomp * N * My * sizeof(cf));
+    t += align_up((size_t)3 * N * N * sizeof(cf));
+    return t;
+}
+extern "C" size_t xl_czt_workspace_bytes(int N, int Mx, int My, int vectorial) { return czt_ws_bytes(N, Mx, My, vectorial ? 3 : 1); }
+extern "C" size_t xl_highna_workspace_bytes(int N, int Mx, int My) { return czt_ws_bytes(N, Mx, My, 3); }
+
+static int czt_plan(CztPlan& pl, int N, int Mx, int My, int ncomp, void* ws, size_t ws_bytes) {
+    if (N < 2 || Mx < 2 || My < 2) return xl_fail(XL_E_BAD_ARG, "czt: sizes must be >= 2%s", "");
+    pl.N = N; pl.Mx = Mx; pl.My = My; pl.ncomp = ncomp;
+    pl.Ly = xl_czt_padded_length(N, My);
+    pl.Lx = xl_czt_padded_length(N, Mx);
+    if (!pl.Ly || !pl.Lx) return xl_fail(XL_E_UNSUPPORTED, "czt: m+M-1 is a power of two or padded length outside [32,4096]%s", "");
+    if (!ws || ws_bytes < czt_ws_bytes(N, Mx, My, ncomp)) return xl_fail(XL_E_WORKSPACE, "czt: workspace too small%s", "");
+    Carver c{(char*)ws, 0, ws_bytes};
+    pl.pre_y = (cf*)c.take((size_t)N * sizeof(cf));
+    pl.pre_x = (cf*)c.take((size_t)N * sizeof(cf));
+    pl.post_y = (cf*)c.take((size_t)My * sizeof(cf));
+    pl.post_x = (cf*)c.take((size_t)Mx * sizeof(cf));
+    pl.ft_y = (cf*)c.take((size_t)pl.Ly * sizeof(cf));
+    pl.ftT_y = (cf*)c.take((size_t)pl.Ly * sizeof(cf));
+    pl.ft_x = (cf*)c.take((size_t)pl.Lx * sizeof(cf));
+    pl.ftT_x = (cf*)c.take((size_t)pl.Lx * sizeof(cf));
+    pl.mid = (cf*)c.take((size_t)ncomp * N * My * sizeof(cf));
+    pl.tmp3 = (cf*)c.take((size_t)3 * N * N * sizeof(cf));
+    return XL_OK;
+}
+
+static int czt_setup(const CztPlan& pl, const double* z, double lambda_over_dx, double Dm_static,
+                     double xout0, double xoutl, double yout0, double youtl, const cf* tw, xl_stream_t st) {
+    int rc;
+    XlCztSetup2Params sp;
+    memset(&sp, 0, sizeof(sp));
+    for (int ax = 0; ax < 2; ++ax) {
+        XlCztSetupParams& s = sp.a[ax];
+        s.z = z; s.lambda_over_dx = lambda_over_dx; s.Dm_static = Dm_static; s.tw = tw;
+        s.m = pl.N;
+        if (ax == 0) {   // y axis (first Bluestein pass, wave_optics.py:349)
+            s.L = pl.Ly; s.M = pl.My; s.out0 = yout0; s.outl = youtl;
+            s.pre = pl.pre_y; s.post = pl.post_y; s.ft = pl.ft_y; s.ftT = pl.ftT_y;
+        } else {         // x axis (second pass, :352)
+            s.L = pl.Lx; s.M = pl.Mx; s.out0 = xout0; s.outl = xoutl;
+            s.pre = pl.pre_x; s.post = pl.post_x; s.ft = pl.ft_x; s.ftT = pl.ftT_x;
+        }
+    }
+    if (pl.Ly == pl.Lx) {   // both axes in one launch (two CTAs)
+        XL_FOR_L(pl.Ly, rc = xl_launch<XlCztSetup<XL>>(XlDim{2, 1}, st, sp));
+        return rc;
+    }
+    XL_FOR_L(pl.Ly, rc = xl_launch<XlCztSetup<XL>>(XlDim{1, 1}, st, sp));
+    if (rc) return rc;
+    sp.a[0] = sp.a[1];
+    XL_FOR_L(pl.Lx, rc = xl_launch<XlCztSetup<XL>>(XlDim{1, 1}, st, sp));
+    return rc;
+}
+
+struct CztCall {
+    int N, Mx, My, mode;  // mode: 0 scalar CZT, 1 VCZT, 2 high-NA
+    const double* z; double lambda, k;
+    double x0, dx, y0, dy, xout0, xoutl, yout0, youtl;
+    double R, f, s2;
+    int flags;
+};
+
+static void czt_common_params(XlCztParams& a, const CztCall& cc, const cf* tw) {
+    memset(&a, 0, sizeof(a));
+    a.tw = tw; a.z = cc.z; a.k = cc.k;
+    a.lens_R = cc.R; a.lens_f = cc.f; a.lens_s2 = cc.s2;
+    a.epi_cr = 1.0; a.epi_ci = 0.0;
+}
+static void czt_out_const(XlCztParams& a, const CztCall& cc) {
+    if (cc.mode == 2) { a.epi_cr = 0.0; a.epi_ci = -cc.s2 / (cc.f * cc.lambda); a.epi_times_z = 0; }   // optical_elements.py:627
+    else { a.epi_cr = cc.dx * cc.dy * cc.lambda; a.epi_ci = 0.0; a.epi_times_z = 1; }                   // wave_optics.py:355
+}
+
+template <int PRO, int EPI, int ACC> static int czt_axis_launch_t(const XlCztParams& a, XlDim grid, xl_stream_t st) {
+    int rc;
+    XL_FOR_L(a.L, rc = xl_launch<XlCztAxis<XL, PRO, EPI, ACC>>(grid, st, a));
+    return rc;
+}
+// The (prologue, epilogue, access shape) combinations the forward and adjoint chains use, each compiled branch-free.
+// Paired 16-byte accesses need an even number of lines and even strides, and the paired variants are compiled with the
+// zero-padded / discarded halves pruned (XlCztOp): other sizes take the generic variant.
+static int czt_axis_launch(const XlCztParams& a, XlDim grid, xl_stream_t st) {
+    const bool even = a.nlines % 2 == 0, in_lo = a.m_in <= a.L / 2;
+    const bool out_lo = a.out_off == 0 && a.m_out <= a.L / 2;
+    const bool pin = even && in_lo && out_lo && a.in_line == 1 && a.in_pos % 2 == 0 && a.in_comp % 2 == 0 && aligned16(a.in);
+    const bool pout = even && in_lo && out_lo && a.out_line == 1 && a.out_pos % 2 == 0 &&
+                      a.out_comp % 2 == 0 && aligned16(a.out);
+#define XL_CZT_CASE(P, E)                                                                               \
+    if (a.pro == P && a.epi == E) {                                                                     \
+        if (pin) return czt_axis_launch_t<P, E, XL_ACC_PAIR_IN>(a, grid, st);                           \
+        if (pout) return czt_axis_launch_t<P, E, XL_ACC_PAIR_OUT>(a, grid, st);                         \
+        return czt_axis_launch_t<P, E, XL_ACC_GENERIC>(a, grid, st);                                    \
+    }
+    XL_CZT_CASE(XL_PRO_NONE, XL_EPI_NONE)
+    XL_CZT_CASE(XL_PRO_NONE, XL_EPI_RSF)
+    XL_CZT_CASE(XL_PRO_RSF, XL_EPI_NONE)
+#undef XL_CZT_CASE
+    // the vectorial prologues only occur in the forward chain (column-direction input)
+    if (a.pro == XL_PRO_VCZT && a.epi == XL_EPI_NONE)
+        return pin ? czt_axis_launch_t<XL_PRO_VCZT, XL_EPI_NONE, XL_ACC_PAIR_IN>(a, grid, st)
+                   : czt_axis_launch_t<XL_PRO_VCZT, XL_EPI_NONE, XL_ACC_GENERIC>(a, grid, st);
+    if (a.pro == XL_PRO_HIGHNA && a.epi == XL_EPI_NONE)
+        return pin ? czt_axis_launch_t<XL_PRO_HIGHNA, XL_EPI_NONE, XL_ACC_PAIR_IN>(a, grid, st)
+                   : czt_axis_launch_t<XL_PRO_HIGHNA, XL_EPI_NONE, XL_ACC_GENERIC>(a, grid, st);
+    return xl_fail(XL_E_BAD_ARG, "czt: unsupported prologue/epilogue combination%s", "");
+}
+
+static int czt_forward(const CztCall& cc, const void* in, void* out, void* ws, size_t ws_bytes, xl_stream_t st) {
+    if (!in || !out) return xl_fail(XL_E_BAD_ARG, "czt_fwd: null pointer%s", "");
+    if (cc.mode != 2 && !cc.z) return xl_fail(XL_E_BAD_ARG, "czt_fwd: null z%s", "");
+    const int ncomp = cc.mode == 0 ? 1 : 3;
+    CztPlan pl;
+    int rc = czt_plan(pl, cc.N, cc.Mx, cc.My, ncomp, ws, ws_bytes);
+    if (rc) return rc;
+    const cf* tw = xl_twiddles();
+    if (!tw) return xl_fail(XL_E_CUDA, "twiddle table allocation failed%s", "");
+    const double Dm_static = cc.mode == 2 ? cc.f * cc.lambda * (cc.N - 1) / (2 * cc.R) : 0.0;  // optical_elements.py:663
+    rc = czt_setup(pl, cc.mode == 2 ? 0 : cc.z, cc.lambda / cc.dx, Dm_static, cc.xout0, cc.xoutl, cc.yout0, cc.youtl, tw, st);
+    if (rc) return rc;
+    const int N = cc.N, Mx = cc.Mx, My = cc.My;
+    const double dxo = (cc.xoutl - cc.xout0) / (Mx - 1), dyo = (cc.youtl - cc.yout0) / (My - 1);
+    // pass 1: Bluestein along y for every input column
+    XlCztParams a;
+    czt_common_params(a, cc, tw);
+    a.L = pl.Ly; a.nlines = N; a.ncomp = ncomp; a.m_in = N; a.out_off = 0; a.m_out = My;
+    a.in = (const cf*)in; a.in_line = 1; a.in_pos = N; a.in_comp = (long long)N * N;
+    a.out = pl.mid; a.out_line = My; a.out_pos = 1; a.out_comp = (long long)N * My;
+    a.pre = pl.pre_y; a.ft = pl.ft_y; a.post = pl.post_y;
+    a.pro = cc.mode == 0 ? XL_PRO_RSF : (cc.mode == 1 ? XL_PRO_VCZT : XL_PRO_HIGHNA);
+    a.gpro = XlGridFactor{cc.x0, cc.dx, cc.y0, cc.dy, 0};
+    a.epi = XL_EPI_NONE;
+    // pass 2: Bluestein along x for every column of the intermediate
+    XlCztParams b;
+    czt_common_params(b, cc, tw);
+    b.L = pl.Lx; b.nlines = My; b.ncomp = ncomp; b.m_in = N; b.out_off = 0; b.m_out = Mx;
+    b.in = pl.mid; b.in_line = 1; b.in_pos = My; b.in_comp = (long long)N * My;
+    b.out = (cf*)out; b.out_line = Mx; b.out_pos = 1; b.out_comp = (long long)My * Mx;
+    b.pre = pl.pre_x; b.ft = pl.ft_x; b.post = pl.post_x;
+    b.pro = XL_PRO_NONE;
+    b.epi = cc.mode == 2 ? XL_EPI_NONE : XL_EPI_RSF;
+    b.gepi = XlGridFactor{cc.xout0, dxo, cc.yout0, dyo, 1};
+    czt_out_const(b, cc);
+    b.flags = cc.flags & XL_CONJ_OUT;
+    rc = czt_axis_launch(a, XlDim{xl_groups(N), ncomp}, st);
+    if (rc) return rc;
+    return czt_axis_launch(b, XlDim{xl_groups(My), ncomp}, st);
+}
+
+static int czt_backward(const CztCall& cc, const void* ct_out, void* ct_in, void* ws, size_t ws_bytes, xl_stream_t st) {
+    if (!ct_out || !ct_in) return xl_fail(XL_E_BAD_ARG, "czt_bwd: null pointer%s", "");
+    if (cc.mode != 2 && !cc.z) return xl_fail(XL_E_BAD_ARG, "czt_bwd: null z%s", "");
+    const int ncomp = cc.mode == 0 ? 1 : 3;
+    CztPlan pl;
+    int rc = czt_plan(pl, cc.N, cc.Mx, cc.My, ncomp, ws, ws_bytes);
+    if (rc) return rc;
+    const cf* tw = xl_twiddles();
+    if (!tw) return xl_fail(XL_E_CUDA, "twiddle table allocation failed%s", "");
+    const double Dm_static = cc.mode == 2 ? cc.f * cc.lambda * (cc.N - 1) / (2 * cc.R) : 0.0;
+    rc = czt_setup(pl, cc.mode == 2 ? 0 : cc.z, cc.lambda / cc.dx, Dm_static, cc.xout0, cc.xoutl, cc.yout0, cc.youtl, tw, st);
+    if (rc) return rc;
+    const int N = cc.N, Mx = cc.Mx, My = cc.My;
+    const double dxo = (cc.xoutl - cc.xout0) / (Mx - 1), dyo = (cc.youtl - cc.yout0) / (My - 1);
+    // transpose of pass 2: rows of ct_out (length Mx) -> columns of the intermediate cotangent
+    XlCztParams b;
+    czt_common_params(b, cc, tw);
+    b.L = pl.Lx; b.nlines = My; b.ncomp = ncomp; b.m_in = Mx; b.out_off = 0; b.m_out = N;
+    b.in = (const cf*)ct_out; b.in_line = Mx; b.in_pos = 1; b.in_comp = (long long)My * Mx;
+    b.out = pl.mid; b.out_line = 1; b.out_pos = My; b.out_comp = (long long)N * My;
+    b.pre = pl.post_x; b.ft = pl.ftT_x; b.post = pl.pre_x;
+    b.pro = cc.mode == 2 ? XL_PRO_NONE : XL_PRO_RSF;
+    b.gpro = XlGridFactor{cc.xout0, dxo, cc.yout0, dyo, 1};
+    b.epi = XL_EPI_NONE;
+    czt_out_const(b, cc);
+    b.flags = cc.flags & XL_CONJ_IN;
+    // transpose of pass 1: rows of the intermediate cotangent (length My) -> columns of ct_field
+    XlCztParams a;
+    czt_common_params(a, cc, tw);
+    a.L = pl.Ly; a.nlines = N; a.ncomp = ncomp; a.m_in = My; a.out_off = 0; a.m_out = N;
+    a.in = pl.mid; a.in_line = My; a.in_pos = 1; a.in_comp = (long long)N * My;
+    a.out = cc.mode == 0 ? (cf*)ct_in : pl.tmp3; a.out_line = 1; a.out_pos = N; a.out_comp = (long long)N * N;
+    a.pre = pl.post_y; a.ft = pl.ftT_y; a.post = pl.pre_y;
+    a.pro = XL_PRO_NONE;
+    a.epi = cc.mode == 2 ? XL_EPI_NONE : XL_EPI_RSF;
+    a.gepi = XlGridFactor{cc.x0, cc.dx, cc.y0, cc.dy, 0};
+    a.flags = cc.mode == 0 ? (cc.flags & XL_CONJ_OUT) : 0;
+    rc = czt_axis_launch(b, XlDim{xl_groups(My), ncomp}, st);
+    if (rc) return rc;
+    rc = czt_axis_launch(a, XlDim{xl_groups(N), ncomp}, st);
+    if (rc || cc.mode == 0) return rc;
+    XlFoldParams f;
+    memset(&f, 0, sizeof(f));
+    f.N = N; f.mode = cc.mode == 1 ? XL_FOLD_VCZT : XL_FOLD_HIGHNA; f.flags = cc.flags & XL_CONJ_OUT;
+    f.t = pl.tmp3; f.gx = (cf*)ct_in; f.gy = (cf*)ct_in + (size_t)N * N;
+    f.z = cc.mode == 1 ? cc.z : 0; f.x0 = cc.x0; f.y0 = cc.y0; f.dx = cc.dx; f.dy = cc.dy;
+    f.lens_R = cc.R; f.lens_f = cc.f; f.lens_s2 = cc.s2;
+    const size_t NN = (size_t)N * N;
+    return xl_launch<XlFold>(XlDim{(int)((NN + XlFold::NT - 1) / XlFold::NT), 1}, st, f);
+}
+
+static CztCall make_czt_call(int mode, const double* z, double lambda, int N, int Mx, int My,
+                             double x0, double dx, double y0, double dy, double xout0, double xoutl, double yout0, double youtl,
+                             double R, double f, int flags) {
+    CztCall c;
+    memset(&c, 0, sizeof(c));
+    c.N = N; c.Mx = Mx; c.My = My; c.mode = mode; c.z = z; c.lambda = lambda; c.k = 2.0 * M_PI / lambda;
+    c.x0 = x0; c.dx = dx; c.y0 = y0; c.dy = dy; c.xout0 = xout0; c.xoutl = xoutl; c.yout0 = yout0; c.youtl = youtl;
+    c.R = R; c.f = f;
+    if (mode == 2) { double st = R / sqrt(R * R + f * f); c.s2 = st * st; }  // optical_elements.py:528
+    c.flags = flags;
+    return c;
+}
+
+extern "C" int xl_czt_fwd(const void* in, void* out, const double* z, double lambda, int N, int Mx, int My, int vectorial,
+                          double x0, double dx, double y0, double dy, double xout0, double xoutl, double yout0, double youtl,
+                          int flags, void* ws, size_t ws_bytes, void* stream) {
+    CztCall c = make_czt_call(vectorial ? 1 : 0, z, lambda, N, Mx, My, x0, dx, y0, dy, xout0, xoutl, yout0, youtl, 0, 0, flags);
+    return czt_forward(c, in, out, ws, ws_bytes, (xl_stream_t)stream);
+}
+extern "C" int xl_czt_bwd(const void* ct_out, void* ct_in, const double* z, double lambda, int N, int Mx, int My, int vectorial,
+                          double x0, double dx, double y0, double dy, double xout0, double xoutl, double yout0, double youtl,
+                          int flags, void* ws, size_t ws_bytes, void* stream) {
+    CztCall c = make_czt_call(vectorial ? 1 : 0, z, lambda, N, Mx, My, x0, dx, y0, dy, xout0, xoutl, yout0, youtl, 0, 0, flags);
+    return czt_backward(c, ct_out, ct_in, ws, ws_bytes, (xl_stream_t)stream);
+}
+extern "C" int xl_highna_fwd(const void* exy, void* out, int N, int Mx, int My, double radius, double f, double lambda,
+                             double x0, double dx, double y0, double dy, double xout0, double xoutl, double yout0, double youtl,
+                             int flags, void* ws, size_t ws_bytes, void* stream) {
+    CztCall c = make_czt_call(2, 0, lambda, N, Mx, My, x0, dx, y0, dy, xout0, xoutl, yout0, youtl, radius, f, flags);
+    return czt_forward(c, exy, out, ws, ws_bytes, (xl_stream_t)stream);
+}
+extern "C" int xl_highna_bwd(const void* ct_out, void* ct_exy, int N, int Mx, int My, double radius, double f, double lambda,
+                             double x0, double dx, double y0, double dy, double xout0, double xoutl, double yout0, double youtl,
+                             int flags, void* ws, size_t ws_bytes, void* stream) {
+    CztCall c = make_czt_call(2, 0, lambda, N, Mx, My, x0, dx, y0, dy, xout0, xoutl, yout0, youtl, radius, f, flags);
+    return czt_backward(c, ct_out, ct_exy, ws, ws_bytes, (xl_stream_t)stream);
+}

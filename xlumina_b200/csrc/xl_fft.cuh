@@ -216,10 +216,17 @@ struct XlOpBase {
     // run-time (CTA-uniform) version of kInLoHalf: skips the loads and prologue math of the upper half, keeps the full
     // butterfly -- for ops whose sizes are not known at compile time and whose variants are too many to double
     XL_DEV bool in_lo_rt() const { return false; }
+    // Hooks for ops that stage their operands in shared memory with asynchronous copies (xl_async.cuh); all empty here.
+    // called by every thread before its first load() of a transform (wait for the staged input)
+    XL_DEV void before_first() const {}
     // called by every thread after its first-pass work, before the first barrier of a transform
     XL_DEV void before_first_sync() const {}
     // called by every thread right after that barrier (the inputs of this transform are no longer needed)
     XL_DEV void after_first_sync(int) const {}
+    // called by every thread before its first spec() of a transform (wait for staged spectrum factors)
+    XL_DEV void before_spec() const {}
+    // conv() only: called by every thread right after the barrier that ends the spectrum phase
+    XL_DEV void after_spec_sync(int) const {}
 };
 
 template <int L, int V, class Tile = XlTile<V>> struct XlFft {
@@ -253,6 +260,7 @@ template <int L, int V, class Tile = XlTile<V>> struct XlFft {
     // ---- forward ----
     template <class Op> XL_DEV static void fwd_first(cf* s, const cf* t, const Op& op) {
         XL_THREADS(tid, NT) {
+            op.before_first();
             for (int n = tid; n < S1; n += NT) {
                 cf v[V * R1];
 #pragma unroll
@@ -354,6 +362,7 @@ template <int L, int V, class Tile = XlTile<V>> struct XlFft {
         fwd_first(s, t, op);
         fwd_mids<L / R1>(s, t);
         XL_THREADS(tid, NT) {
+            op.before_spec();
             for (int beta = tid; beta < L / 16; beta += NT) {
                 cf v[V * 16];
 #pragma unroll
@@ -369,6 +378,7 @@ template <int L, int V, class Tile = XlTile<V>> struct XlFft {
         fwd_first(s, t, op);
         fwd_mids<L / R1>(s, t);
         XL_THREADS(tid, NT) {
+            op.before_spec();
             for (int beta = tid; beta < L / 16; beta += NT) {
                 cf v[V * 16];
 #pragma unroll
@@ -383,6 +393,7 @@ template <int L, int V, class Tile = XlTile<V>> struct XlFft {
             }
         }
         XL_SYNC();
+        XL_THREADS(tid, NT) { op.after_spec_sync(tid); }
         inv_mids<L / R1>(s, t);
         inv_last(s, t, op);
     }

@@ -148,6 +148,7 @@ struct XlRsParams {
     const double* z;   // device scalar
     double x0, y0, dx, dy, k;
     float hscale;      // dx*dy/L^2
+    unsigned stagger_ns;   // persistent kernels: the second CTA of an SM starts this much later (de-phases the two CTAs)
 };
 
 // K1: rows of the zero-padded field -> blocked row spectra.   replaces the row half of fft2(U), wave_optics.py:286-288
@@ -190,9 +191,6 @@ template <int L> struct XlRsRowsFwd {
     static const char* name() { return "rs_rows_fwd"; }
     typedef XlRsParams Params;
     static constexpr int NT = xl_threads(L);
-#ifdef XL_EXP_ROWS_3CTA   // experiment (DESIGN.md queue item 1b): a third resident CTA for the 1024-CTA row grids (85 registers)
-    static constexpr int MINB = L == 4096 ? 3 : (512 / NT > 16 ? 16 : 512 / NT);
-#endif
     static size_t smem() { return xl_smem_bytes(L, XL_V); }
     XL_DEV static void run(const Params& p, cf* s) {
         cf* t = s + xl_tile_elems(L, XL_V);
@@ -290,11 +288,7 @@ template <int L> struct XlRsCols {
     XL_DEV static void run(const Params& p, cf* s) {
         cf* t = s + xl_tile_elems(L, XL_V);
         XlFft<L, XL_V>::init_tw(t, p.tw);
-#ifdef XL_EXP_FIELD_MINOR   // experiment: the fields of one column pair run back to back, so they share its transfer function in L2
-        const int lin = XL_BLOCK_Y * XL_GRID_X + XL_BLOCK_X, G = lin / p.nfields, f = p.f0 + lin % p.nfields;
-#else
         const int G = XL_BLOCK_X, f = p.f0 + XL_BLOCK_Y;
-#endif
         const cf* H0 = xl_h_column<L>(p.H, XL_V * G);
         const cf* H1 = xl_h_column<L>(p.H, XL_V * G + 1);
         const bool a0 = (((size_t)(H0 - p.H)) & 1) == 0, a1 = (((size_t)(H1 - p.H)) & 1) == 0;
@@ -312,153 +306,7 @@ template <int L> struct XlRsCols {
         XlFft<L, XL_V>::conv(s, t, op);
     }
 };
-#ifdef XL_EXP_K2_STAGE
-// Experiment (DESIGN.md queue item 1), not in the default build: rs_cols with both transfer-function columns of the pair
-// staged in shared memory by asynchronous copies issued at kernel start (interleaved {H0[r], H1[r]} so that the spectrum
-// phase needs one 16-byte shared load per bin pair, whatever the mirror mode of the pair was).
-template <int L> struct XlRsColsStageOp : XlOpBase {
-    static constexpr bool kInLoHalf = true, kOutLoHalf = true;
-    static constexpr int R1 = xl_first_radix(L), S1 = L / R1;
-    const XlRsParams& p; cf* tile; const cf* Hs;   // Hs[2*r], Hs[2*r+1]: the two lines' transfer function at stored row r
-    XL_DEV void load(int i, cf* v, int stride) const {
-        if (i < p.N) xl_ld4(tile + (size_t)i * XL_V, v, v + stride);
-        else { v[0] = cf_zero(); v[stride] = cf_zero(); }
-    }
-    XL_DEV void before_first_sync() const { xl_cp_async_wait(); }
-    XL_DEV void spec(int beta, cf* v) const {
-        const XlHRow<L> hr(beta);
-#pragma unroll
-        for (int q = 0; q < 16; ++q) {
-            const float4 h = *reinterpret_cast<const float4*>(Hs + 2 * hr.row(q));
-            v[q] = cf_mul(v[q], make_float2(h.x, h.y));
-            v[16 + q] = cf_mul(v[16 + q], make_float2(h.z, h.w));
-        }
-    }
-    XL_DEV void store_vec(int n, const cf* v) const {
-#pragma unroll
-        for (int j = 0; j < R1 / 2; ++j) {
-            const int i = n + S1 * j;
-            if (i < p.N) xl_st4(tile + (size_t)i * XL_V, v[j], v[R1 + j]);
-        }
-    }
-};
-template <int L> struct XlRsColsStage {
-    static const char* name() { return "rs_cols"; }
-    typedef XlRsParams Params;
-    static constexpr int NT = xl_threads(L);
-    static constexpr int HR = L / 2 + 1;
-    static size_t smem() { return xl_smem_bytes(L, XL_V) + (size_t)2 * (HR + 1) * sizeof(cf); }
-    XL_DEV static void run(const Params& p, cf* s) {
-        cf* Hs = s + xl_tile_elems(L, XL_V);          // 16-byte aligned: the tile holds an even number of cf
-        cf* t = Hs + 2 * (HR + 1);
-        const int G = XL_BLOCK_X, f = p.f0 + XL_BLOCK_Y;
-        const cf* H0 = xl_h_column<L>(p.H, XL_V * G);
-        const cf* H1 = xl_h_column<L>(p.H, XL_V * G + 1);
-        XL_THREADS(tid, NT) {
-            for (int r = tid; r < HR; r += NT) {
-                xl_cp_async8(Hs + 2 * r, H0 + (size_t)r * XL_V);
-                xl_cp_async8(Hs + 2 * r + 1, H1 + (size_t)r * XL_V);
-            }
-        }
-        XlFft<L, XL_V>::init_tw(t, p.tw);
-        XlRsColsStageOp<L> op{{}, p, p.spec + (size_t)f * L * p.N + (size_t)G * p.N * XL_V, Hs};
-        XlFft<L, XL_V>::conv(s, t, op);
-    }
-};
-#endif
 
-#ifdef XL_EXP_K2_PERSIST
-// Experiment (DESIGN.md queue item 1), not in the default build: persistent rs_cols.  Each CTA walks the (column pair,
-// field) items blockIdx.x, blockIdx.x + gridDim.x, ...; the pruned input of an item (N rows x 2 lines, contiguous in the
-// spectra buffer) is staged in shared memory by asynchronous 16-byte copies, and the copies of the NEXT item are issued
-// right after the first barrier of the current transform, so they travel while the current item is being transformed.
-template <int L> struct XlRsColsPersistOp : XlOpBase {
-    static constexpr bool kInLoHalf = true, kOutLoHalf = true;
-    static constexpr int R1 = xl_first_radix(L), S1 = L / R1, NT = xl_threads(L);
-    const XlRsParams& p; cf* tile; cf* stage; const cf* next; const cf* H0; const cf* H1; int hmode;
-    XL_DEV void load(int i, cf* v, int stride) const {
-        if (i < p.N) xl_ld4(stage + (size_t)i * XL_V, v, v + stride);
-        else { v[0] = cf_zero(); v[stride] = cf_zero(); }
-    }
-    XL_DEV void after_first_sync(int tid) const {
-        if (next)
-            for (int i = tid; i < p.N; i += NT) xl_cp_async16(stage + (size_t)i * XL_V, next + (size_t)i * XL_V);
-    }
-    XL_DEV void spec(int beta, cf* v) const {
-        const XlHRow<L> hr(beta);
-        if (hmode == 2) {
-#pragma unroll
-            for (int q = 0; q < 16; ++q) {
-                const size_t o = (size_t)hr.row(q) * XL_V;
-                v[q] = cf_mul(v[q], xl_ldg(H0 + o));
-                v[16 + q] = cf_mul(v[16 + q], xl_ldg(H1 + o));
-            }
-        } else {
-            const cf* Hp = hmode == 0 ? H0 : H1;
-#pragma unroll
-            for (int q = 0; q < 16; ++q) {
-                cf lo, hi;
-                xl_ldg4(Hp + (size_t)hr.row(q) * XL_V, &lo, &hi);
-                v[q] = cf_mul(v[q], hmode == 0 ? lo : hi);
-                v[16 + q] = cf_mul(v[16 + q], hmode == 0 ? hi : lo);
-            }
-        }
-    }
-    XL_DEV void store_vec(int n, const cf* v) const {
-#pragma unroll
-        for (int j = 0; j < R1 / 2; ++j) {
-            const int i = n + S1 * j;
-            if (i < p.N) xl_st4(tile + (size_t)i * XL_V, v[j], v[R1 + j]);
-        }
-    }
-};
-template <int L> struct XlRsColsPersist {
-    static const char* name() { return "rs_cols"; }
-    typedef XlRsParams Params;
-    static constexpr int NT = xl_threads(L);
-    static size_t smem() { return xl_smem_bytes(L, XL_V) + (size_t)L * sizeof(cf); }   // + N <= L/2 rows of two lines
-    XL_DEV static const cf* item(const Params& p, int it) {
-        const int G = it % (L / XL_V), f = p.f0 + it / (L / XL_V);
-        return p.spec + (size_t)f * L * p.N + (size_t)G * p.N * XL_V;
-    }
-    XL_DEV static void run(const Params& p, cf* s) {
-        cf* stage = s + xl_tile_elems(L, XL_V);
-        cf* t = stage + L;
-        const int items = (L / XL_V) * p.nfields;
-        int it = XL_BLOCK_X;
-        if (it >= items) return;
-        {
-            const cf* first = item(p, it);
-            XL_THREADS(tid, NT) {
-                for (int i = tid; i < p.N; i += NT) xl_cp_async16(stage + (size_t)i * XL_V, first + (size_t)i * XL_V);
-                xl_cp_async_wait();
-            }
-        }
-        XlFft<L, XL_V>::init_tw(t, p.tw);               // ends with a barrier: the first item is staged for every thread
-        for (; it < items; it += XL_GRID_X) {
-            const int G = it % (L / XL_V);
-            const cf* H0 = xl_h_column<L>(p.H, XL_V * G);
-            const cf* H1 = xl_h_column<L>(p.H, XL_V * G + 1);
-            const bool a0 = (((size_t)(H0 - p.H)) & 1) == 0, a1 = (((size_t)(H1 - p.H)) & 1) == 0;
-            const int hmode = (a0 && H1 == H0 + 1) ? 0 : ((a1 && H0 == H1 + 1) ? 1 : 2);
-            XL_THREADS(tid, NT) {
-                for (int beta = tid; beta < L / 16; beta += NT)
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        if (beta & 1) continue;
-                        xl_prefetch_l2(H0 + (size_t)(q * (L / 16) + beta) * XL_V);
-                        if (hmode == 2) xl_prefetch_l2(H1 + (size_t)(q * (L / 16) + beta) * XL_V);
-                    }
-            }
-            const int nx = it + XL_GRID_X;
-            XlRsColsPersistOp<L> op{{}, p, const_cast<cf*>(item(p, it)), stage, nx < items ? item(p, nx) : (const cf*)0, H0, H1, hmode};
-            XlFft<L, XL_V>::conv(s, t, op);
-            XL_THREADS(tid, NT) { xl_cp_async_wait(); }
-            XL_SYNC();                                   // next input staged for every thread; tile free for the next transform
-        }
-    }
-};
-#endif
 
 // K2 of the slab-decomposed path: this rank owns gridDim.x slot pairs; its transfer-function slab H is [pairs][L][2]
 // (generated for exactly these columns, so no x-mirroring), its spectra arrive as [source rank][pairs][chunk_rows][2].
@@ -512,9 +360,6 @@ template <int L> struct XlRsRowsInv {
     static const char* name() { return "rs_rows_inv"; }
     typedef XlRsParams Params;
     static constexpr int NT = xl_threads(L);
-#ifdef XL_EXP_ROWS_3CTA
-    static constexpr int MINB = L == 4096 ? 3 : (512 / NT > 16 ? 16 : 512 / NT);
-#endif
     static size_t smem() { return xl_smem_bytes(L, XL_V); }
     XL_DEV static void run(const Params& p, cf* s) {
         cf* t = s + xl_tile_elems(L, XL_V);
@@ -679,260 +524,8 @@ template <int L> struct XlRsColsGzOutOp : XlOpBase {
         }
     }
 };
-#ifdef XL_EXP_K4_STAGE
-// Experiment (DESIGN.md queue item 1a), not in the default build.  Same arithmetic as XlRsColsGz below with two changes:
-//  * the fused first inverse pass is written back IN PLACE into line 0 of the two-line tile (same thread, same slots) and
-//    the inverse tail runs on that line only -- the separate one-line tile disappears;
-//  * its 34.8 KB stage both transfer-function columns (H and the reduced Hz, rows 0..L/2) with asynchronous copies issued
-//    at kernel start, so the spectrum phase reads shared memory instead of waiting on L2 in the middle of the transform.
-template <int L> struct XlRsColsGzStageOp : XlOpBase {
-    static constexpr bool kInLoHalf = true;
-    const XlRsParams& p; const cf* ctile; const cf* wtile; int c; const cf* Hs; const cf* Hzs; cf* tile2; float* red;
-    XL_DEV void load(int i, cf* v, int stride) const {
-        const bool ok = i < p.N;
-        const size_t o = ok ? (size_t)i * XL_V + c : 0;
-        const cf a = ctile[o], w = wtile[o];
-        v[0] = ok ? a : cf_zero();
-        v[stride] = ok ? w : cf_zero();
-    }
-    XL_DEV void before_first_sync() const { xl_cp_async_wait(); }   // this thread's staged entries; the barrier publishes them
-    XL_DEV void spec(int beta, const cf* v) const {
-        float acc = 0.f;
-        cf u[16];
-        const XlHRow<L> hr(beta);
-#pragma unroll
-        for (int q = 0; q < 16; ++q) {
-            const int r = hr.row(q);
-            const cf t = cf_mul(v[q], Hzs[r]);
-            acc += v[16 + q].x * t.x + v[16 + q].y * t.y;  // Re(conj(w) * t)
-            u[q] = cf_mul(v[q], Hs[r]);
-        }
-        red[beta] += acc;
-        XlBfly<16, +1, false, false>::run(u);       // first inverse pass, fused; back into line 0 of the slots just read
-#pragma unroll
-        for (int j = 0; j < 16; ++j) XlTileLine0Of2::st(tile2, 16 * beta + j, u + j, 16);
-    }
-    XL_DEV void store_vec(int, const cf*) const {}
-};
-template <int L> struct XlRsColsGzStage {
-    static const char* name() { return "rs_cols_gz"; }
-    typedef XlRsParams Params;
-    static constexpr int NT = xl_threads(L);
-    static constexpr int NB = L / 16;
-    static constexpr int HR = L / 2 + 1;          // stored rows of a transfer-function column
-    static size_t smem() { return (size_t)(xl_tile_elems(L, 2) + 2 * (HR + 1) + xl_tw_total(L)) * sizeof(cf) + (size_t)(NB + 32) * sizeof(float); }
-    XL_DEV static void run(const Params& p, cf* s) {
-        cf* Hs = s + xl_tile_elems(L, 2);
-        cf* Hzs = Hs + HR + 1;
-        cf* t = Hzs + HR + 1;
-        float* red = (float*)(t + xl_tw_total(L));
-        const int G = XL_BLOCK_X >> 1, c = XL_BLOCK_X & 1, f = p.f0 + XL_BLOCK_Y;   // one column per CTA
-        const cf* Hc = xl_h_column<L>(p.H, XL_V * G + c);
-        const cf* Hzc = xl_h_column<L>(p.H2, XL_V * G + c);
-        XL_THREADS(tid, NT) {
-            for (int r = tid; r < HR; r += NT) {
-                xl_cp_async8(Hs + r, Hc + (size_t)r * XL_V);
-                xl_cp_async8(Hzs + r, Hzc + (size_t)r * XL_V);
-            }
-            for (int i = tid; i < NB; i += NT) red[i] = 0.f;
-        }
-        XlFft<L, 2>::init_tw(t, p.tw);
-        const size_t toff = (size_t)f * L * p.N + (size_t)G * p.N * XL_V;
-        XlRsColsGzStageOp<L> op{{}, p, p.spec + toff, p.spec2 + toff, c, Hs, Hzs, s, red};
-        XlFft<L, 2>::forward(s, t, op);
-        XL_SYNC();
-        XlRsColsGzOutOp<L> oo{{}, p, p.spec + toff, c};
-        XlFft<L, 1, XlTileLine0Of2>::inverse_tail(s, t, oo);
-        XL_SYNC();
-        XL_THREADS(tid, NT) {
-            if (tid < 32) {
-                float a = 0.f;
-                for (int i = tid; i < NB; i += 32) a += red[i];
-                red[NB + tid] = a;
-            }
-        }
-        XL_SYNC();
-        XL_THREADS(tid, NT) {
-            if (tid == 0) {
-                double a = 0.0;
-                for (int i = 0; i < 32; ++i) a += (double)red[NB + i];
-                xl_atomic_add(p.gz, a);
-            }
-        }
-    }
-};
-#endif
 
-#ifdef XL_EXP_KEEP_SPECTRA
-// Experiment (DESIGN.md queue item 2), not in the default build: the forward pass keeps its row spectra U^ (rs_cols then
-// writes its result to a second buffer instead of in place) and the d/dz column kernel reads the spectra of conj(U) from
-// them -- FFT(conj u)[kx] = conj(FFT(u)[-kx]): the mirrored column, conjugated -- so the backward pass does not recompute
-// them (one rs_rows_fwd launch per field less).
-template <int L> struct XlRsColsKeepOp : XlRsColsOp<L, false> {
-    typedef XlRsColsOp<L, false> Base;
-    cf* otile;
-    XL_DEV XlRsColsKeepOp(const Base& b, cf* o) : Base(b), otile(o) {}
-    XL_DEV void store_vec(int n, const cf* v) const {
-#pragma unroll
-        for (int j = 0; j < Base::R1 / 2; ++j) {
-            const int i = n + Base::S1 * j;
-            if (i < this->p.N) xl_st4(otile + (size_t)i * XL_V, v[j], v[Base::R1 + j]);
-        }
-    }
-};
-template <int L> struct XlRsColsKeep {       // p.spec: kept row spectra (read only), p.spec2: filtered spectra (written)
-    static const char* name() { return "rs_cols"; }
-    typedef XlRsParams Params;
-    static constexpr int NT = xl_threads(L);
-    static size_t smem() { return xl_smem_bytes(L, XL_V); }
-    XL_DEV static void run(const Params& p, cf* s) {
-        cf* t = s + xl_tile_elems(L, XL_V);
-        XlFft<L, XL_V>::init_tw(t, p.tw);
-        const int G = XL_BLOCK_X, f = p.f0 + XL_BLOCK_Y;
-        const cf* H0 = xl_h_column<L>(p.H, XL_V * G);
-        const cf* H1 = xl_h_column<L>(p.H, XL_V * G + 1);
-        const bool a0 = (((size_t)(H0 - p.H)) & 1) == 0, a1 = (((size_t)(H1 - p.H)) & 1) == 0;
-        const int hmode = (a0 && H1 == H0 + 1) ? 0 : ((a1 && H0 == H1 + 1) ? 1 : 2);
-        const size_t toff = (size_t)f * L * p.N + (size_t)G * p.N * XL_V;
-        const XlRsColsOp<L, false> base{{}, p, p.spec + toff, H0, H1, hmode, 0};
-        const XlRsColsKeepOp<L> op(base, p.spec2 + toff);
-        XlFft<L, XL_V>::conv(s, t, op);
-    }
-};
-template <int L> struct XlRsColsGzKeptOp : XlRsColsGzOp<L> {
-    typedef XlRsColsGzOp<L> Base;
-    int cm;          // half of the mirrored pair that holds the mirrored column
-    XL_DEV XlRsColsGzKeptOp(const Base& b, int m) : Base(b), cm(m) {}
-    XL_DEV void load(int i, cf* v, int stride) const {
-        const bool ok = i < this->p.N;
-        const cf a = this->ctile[ok ? (size_t)i * XL_V + this->c : 0];
-        const cf w = this->wtile[ok ? (size_t)i * XL_V + cm : 0];     // wtile: the MIRRORED pair of the kept forward spectra
-        v[0] = ok ? a : cf_zero();
-        v[stride] = ok ? cf_conj(w) : cf_zero();
-    }
-};
-template <int L> struct XlRsColsGzKept {     // p.spec: cotangent row spectra (in/out), p.spec2: kept forward row spectra of U
-    static const char* name() { return "rs_cols_gz"; }
-    typedef XlRsParams Params;
-    static constexpr int NT = xl_threads(L);
-    static constexpr int NB = L / 16;
-    static size_t smem() { return (size_t)(xl_tile_elems(L, 2) + xl_tile_elems(L, 1) + xl_tw_total(L)) * sizeof(cf) + (size_t)(NB + 32) * sizeof(float); }
-    XL_DEV static void run(const Params& p, cf* s);
-};
-#endif
 
-#ifdef XL_EXP_K4_PERSIST
-// Experiment (DESIGN.md queue items 1 / 1a), not in the default build: persistent rs_cols_gz.  In-place inverse on line 0 of
-// the two-line tile as in XlRsColsGzStage; the freed shared memory stages the NEXT column's inputs instead (cotangent
-// spectra column and conj-field spectra column, N rows each, 8-byte asynchronous copies issued right after the first
-// barrier of the current transform); the transfer-function columns are prefetched into L2 at the start of each item.
-template <int L> struct XlRsColsGzPersistOp : XlOpBase {
-    static constexpr bool kInLoHalf = true;
-    static constexpr int NT = xl_threads(L);
-    const XlRsParams& p; cf* stage; const cf* nextc; const cf* nextw; const cf* Hc; const cf* Hzc; cf* tile2; float* red;
-    XL_DEV void load(int i, cf* v, int stride) const {
-        if (i < p.N) xl_ld4(stage + (size_t)i * 2, v, v + stride);      // {cotangent, conj-field} of row i
-        else { v[0] = cf_zero(); v[stride] = cf_zero(); }
-    }
-    XL_DEV void after_first_sync(int tid) const {
-        if (nextc)
-            for (int i = tid; i < p.N; i += NT) {
-                xl_cp_async8(stage + (size_t)i * 2, nextc + (size_t)i * XL_V);
-                xl_cp_async8(stage + (size_t)i * 2 + 1, nextw + (size_t)i * XL_V);
-            }
-    }
-    XL_DEV void spec(int beta, const cf* v) const {
-        float acc = 0.f;
-        cf u[16];
-        const XlHRow<L> hr(beta);
-#pragma unroll
-        for (int q = 0; q < 16; ++q) {
-            const size_t o = (size_t)hr.row(q) * XL_V;
-            const cf t = cf_mul(v[q], xl_ldg(Hzc + o));
-            acc += v[16 + q].x * t.x + v[16 + q].y * t.y;  // Re(conj(w) * t)
-            u[q] = cf_mul(v[q], xl_ldg(Hc + o));
-        }
-        red[beta] += acc;
-        XlBfly<16, +1, false, false>::run(u);
-#pragma unroll
-        for (int j = 0; j < 16; ++j) XlTileLine0Of2::st(tile2, 16 * beta + j, u + j, 16);
-    }
-    XL_DEV void store_vec(int, const cf*) const {}
-};
-template <int L> struct XlRsColsGzPersist {
-    static const char* name() { return "rs_cols_gz"; }
-    typedef XlRsParams Params;
-    static constexpr int NT = xl_threads(L);
-    static constexpr int NB = L / 16;
-    static size_t smem() { return (size_t)(xl_tile_elems(L, 2) + L + xl_tw_total(L)) * sizeof(cf) + (size_t)(NB + 32) * sizeof(float); }
-    XL_DEV static size_t column(const Params& p, int it, int* c, int* slot) {
-        const int col = it % L, f = p.f0 + it / L;
-        *c = col & 1;
-        *slot = col;
-        return (size_t)f * L * p.N + (size_t)(col >> 1) * p.N * XL_V + (col & 1);
-    }
-    XL_DEV static void run(const Params& p, cf* s) {
-        cf* stage = s + xl_tile_elems(L, 2);
-        cf* t = stage + L;
-        float* red = (float*)(t + xl_tw_total(L));
-        const int items = L * p.nfields;
-        int it = XL_BLOCK_X;
-        if (it >= items) return;
-        {
-            int c, slot;
-            const size_t o = column(p, it, &c, &slot);
-            XL_THREADS(tid, NT) {
-                for (int i = tid; i < p.N; i += NT) {
-                    xl_cp_async8(stage + (size_t)i * 2, p.spec + o + (size_t)i * XL_V);
-                    xl_cp_async8(stage + (size_t)i * 2 + 1, p.spec2 + o + (size_t)i * XL_V);
-                }
-                xl_cp_async_wait();
-                for (int i = tid; i < NB; i += NT) red[i] = 0.f;
-            }
-        }
-        XlFft<L, 2>::init_tw(t, p.tw);
-        for (; it < items; it += XL_GRID_X) {
-            int c, slot, cn, slotn;
-            const size_t o = column(p, it, &c, &slot);
-            const cf* Hc = xl_h_column<L>(p.H, slot);
-            const cf* Hzc = xl_h_column<L>(p.H2, slot);
-            XL_THREADS(tid, NT) {
-                for (int beta = tid; beta < L / 16; beta += NT)
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        if (beta & 1) continue;
-                        xl_prefetch_l2(Hc + (size_t)(q * (L / 16) + beta) * XL_V);
-                        xl_prefetch_l2(Hzc + (size_t)(q * (L / 16) + beta) * XL_V);
-                    }
-            }
-            const int nx = it + XL_GRID_X;
-            const size_t on = nx < items ? column(p, nx, &cn, &slotn) : 0;
-            XlRsColsGzPersistOp<L> op{{}, p, stage, nx < items ? p.spec + on : (const cf*)0, p.spec2 + on, Hc, Hzc, s, red};
-            XlFft<L, 2>::forward(s, t, op);
-            XL_SYNC();
-            XlRsColsGzOutOp<L> oo{{}, p, p.spec + (o - c), c};
-            XlFft<L, 1, XlTileLine0Of2>::inverse_tail(s, t, oo);
-            XL_THREADS(tid, NT) { xl_cp_async_wait(); }
-            XL_SYNC();
-        }
-        XL_THREADS(tid, NT) {
-            if (tid < 32) {
-                float a = 0.f;
-                for (int i = tid; i < NB; i += 32) a += red[i];
-                red[NB + tid] = a;
-            }
-        }
-        XL_SYNC();
-        XL_THREADS(tid, NT) {
-            if (tid == 0) {
-                double a = 0.0;
-                for (int i = 0; i < 32; ++i) a += (double)red[NB + i];
-                xl_atomic_add(p.gz, a);
-            }
-        }
-    }
-};
-#endif
 
 template <int L> struct XlRsColsGz {
     static const char* name() { return "rs_cols_gz"; }
@@ -946,28 +539,8 @@ template <int L> struct XlRsColsGz {
         float* red = (float*)(t + xl_tw_total(L));
         XL_THREADS(tid, NT) { for (int i = tid; i < NB; i += NT) red[i] = 0.f; }
         XlFft<L, 2>::init_tw(t, p.tw);
-#ifdef XL_EXP_FIELD_MINOR
-        const int lin = XL_BLOCK_Y * XL_GRID_X + XL_BLOCK_X, col = lin / p.nfields, f = p.f0 + lin % p.nfields;
-        const int G = col >> 1, c = col & 1;
-#else
         const int G = XL_BLOCK_X >> 1, c = XL_BLOCK_X & 1, f = p.f0 + XL_BLOCK_Y;   // one column per CTA
-#endif
         const size_t toff = (size_t)f * L * p.N + (size_t)G * p.N * XL_V;
-#ifdef XL_EXP_K4_PREFETCH   // experiment: as in rs_cols, start moving both transfer-function columns into L2 before the FFT passes
-        {
-            const cf* Ha = xl_h_column<L>(p.H, XL_V * G + c);
-            const cf* Hb = xl_h_column<L>(p.H2, XL_V * G + c);
-            XL_THREADS(tid, NT) {
-                for (int beta = tid; beta < L / 16; beta += NT)
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        if (beta & 1) continue;       // one prefetch per 32-byte sector
-                        xl_prefetch_l2(Ha + (size_t)(q * (L / 16) + beta) * XL_V);
-                        xl_prefetch_l2(Hb + (size_t)(q * (L / 16) + beta) * XL_V);
-                    }
-            }
-        }
-#endif
         {
             XlRsColsGzOp<L> op{{}, p, p.spec + toff, p.spec2 + toff, c, xl_h_column<L>(p.H, XL_V * G + c),
                                xl_h_column<L>(p.H2, XL_V * G + c), itile, red};
@@ -995,45 +568,6 @@ template <int L> struct XlRsColsGz {
     }
 };
 
-#ifdef XL_EXP_KEEP_SPECTRA
-template <int L> XL_DEV void XlRsColsGzKept<L>::run(const Params& p, cf* s) {
-    cf* itile = s + xl_tile_elems(L, 2);
-    cf* t = itile + xl_tile_elems(L, 1);
-    float* red = (float*)(t + xl_tw_total(L));
-    XL_THREADS(tid, NT) { for (int i = tid; i < NB; i += NT) red[i] = 0.f; }
-    XlFft<L, 2>::init_tw(t, p.tw);
-    const int G = XL_BLOCK_X >> 1, c = XL_BLOCK_X & 1, f = p.f0 + XL_BLOCK_Y;   // one column per CTA
-    const size_t toff = (size_t)f * L * p.N + (size_t)G * p.N * XL_V;
-    const int slot = XL_V * G + c;
-    const int sm = xl_bin_to_slot_t<L>((L - xl_slot_to_bin_t<L>(slot)) & (L - 1));       // slot of the mirrored x frequency
-    const size_t moff = (size_t)f * L * p.N + (size_t)(sm >> 1) * p.N * XL_V;
-    {
-        const XlRsColsGzOp<L> base{{}, p, p.spec + toff, p.spec2 + moff, c, xl_h_column<L>(p.H, slot),
-                                   xl_h_column<L>(p.H2, slot), itile, red};
-        const XlRsColsGzKeptOp<L> op(base, sm & 1);
-        XlFft<L, 2>::forward(s, t, op);
-        XL_SYNC();
-        XlRsColsGzOutOp<L> oo{{}, p, p.spec + toff, c};
-        XlFft<L, 1>::inverse_tail(itile, t, oo);
-        XL_SYNC();
-    }
-    XL_THREADS(tid, NT) {
-        if (tid < 32) {
-            float a = 0.f;
-            for (int i = tid; i < NB; i += 32) a += red[i];
-            red[NB + tid] = a;
-        }
-    }
-    XL_SYNC();
-    XL_THREADS(tid, NT) {
-        if (tid == 0) {
-            double a = 0.0;
-            for (int i = 0; i < 32; ++i) a += (double)red[NB + i];
-            xl_atomic_add(p.gz, a);
-        }
-    }
-}
-#endif
 
 // ==================================================================================================================
 // Bluestein chirp-z axis pass  (wave_optics.py:385-460), with the fused prologue/epilogue factors of CZT_jit (:333-357),
@@ -1064,9 +598,6 @@ struct XlCztParams {
     double epi_cr, epi_ci; // complex constant on the output
     int epi_times_z;      // multiply the constant by z (CZT: z*dx*dy*lambda)
     double lens_R, lens_f, lens_s2;  // high-NA: radius, focal length, sin^2(theta_max)
-#ifdef XL_EXP_CZT_PERSIST
-    int pairs;            // line pairs per component (the persistent variant walks pairs * ncomp items)
-#endif
 };
 
 // lens factor row `comp` applied to (Ex,Ey):  apod*G*(RL[comp][0] Ex + RL[comp][1] Ey + RL[comp][2] Ez), Ez=(Ex X+Ey Y)/rho
@@ -1208,83 +739,6 @@ template <int L, int PRO, int EPI, int ACC> struct XlCztAxis {
     }
 };
 
-#ifdef XL_EXP_CZT_PERSIST
-// Experiment (DESIGN.md queue item 1), not in the default build: persistent Bluestein axis pass for the single-plane
-// prologues (none / RS factor) of the paired, pruned access shapes.  2 x SM-count CTAs walk the (line pair, component)
-// items; the raw input of the NEXT item (m_in <= L/2 positions of both lines) is copied into a staging buffer by
-// asynchronous copies issued right after the first barrier of the current transform; the prologue factors are applied when
-// the staged operands are read.
-template <int L, int PRO, int EPI, int ACC> struct XlCztPersistOp : XlCztOp<L, PRO, EPI, ACC> {
-    static_assert(PRO == XL_PRO_NONE || PRO == XL_PRO_RSF, "single-plane prologues only");
-    static_assert(ACC != XL_ACC_GENERIC, "paired (pruned) access shapes only");
-    typedef XlCztOp<L, PRO, EPI, ACC> Base;
-    static constexpr int NT = xl_threads(L);
-    cf* stage; int next_lb, next_cl;   // next item of this CTA (next_lb < 0: none)
-    XL_DEV XlCztPersistOp(const Base& b, cf* st, int nlb, int ncl) : Base(b), stage(st), next_lb(nlb), next_cl(ncl) {}
-    XL_DEV static void issue(const XlCztParams& p, cf* stage, int lb, int cl, int tid) {
-        const cf* src = p.in + (long long)cl * p.in_comp;
-        for (int i = tid; i < p.m_in; i += NT) {
-            if (ACC == XL_ACC_PAIR_IN) {
-                xl_cp_async16(stage + 2 * i, src + lb + (long long)i * p.in_pos);
-            } else {
-                xl_cp_async8(stage + 2 * i, src + (long long)lb * p.in_line + (long long)i * p.in_pos);
-                xl_cp_async8(stage + 2 * i + 1, src + (long long)(lb + 1) * p.in_line + (long long)i * p.in_pos);
-            }
-        }
-    }
-    XL_DEV void after_first_sync(int tid) const {
-        if (next_lb >= 0) issue(this->p, stage, next_lb, next_cl, tid);
-    }
-    XL_DEV void load(int i, cf* v, int stride) const {
-        const XlCztParams& p = this->p;
-        const bool ok_i = i < p.m_in;
-        cf a[XL_V];
-        xl_ld4(stage + 2 * (ok_i ? i : 0), a, a + 1);
-        const cf pre = xl_ldg(p.pre + (ok_i ? i : 0));
-#pragma unroll
-        for (int l = 0; l < XL_V; ++l) {
-            cf x = (p.flags & XL_F_CONJ_IN) ? cf_conj(a[l]) : a[l];
-            if (PRO == XL_PRO_RSF) {          // F = h(X, Y; z), wave_optics.py:341,344
-                double X, Y;
-                this->coords(p.gpro, this->lb + l, i, &X, &Y);
-                x = cf_mul(x, xl_rs_h(X, Y, this->hc, 0));
-            }
-            x = cf_mul(x, pre);
-            v[l * stride] = ok_i ? x : cf_zero();
-        }
-    }
-};
-template <int L, int PRO, int EPI, int ACC> struct XlCztAxisPersist {
-    static const char* name() { return "czt_axis"; }
-    typedef XlCztParams Params;
-    static constexpr int NT = xl_threads(L);
-    static size_t smem() { return xl_smem_bytes(L, XL_V) + (size_t)L * sizeof(cf); }
-    XL_DEV static void run(const Params& p, cf* s) {
-        cf* stage = s + xl_tile_elems(L, XL_V);
-        cf* t = stage + L;
-        const int items = p.pairs * p.ncomp;
-        int it = XL_BLOCK_X;
-        if (it >= items) return;
-        XL_THREADS(tid, NT) {
-            XlCztPersistOp<L, PRO, EPI, ACC>::issue(p, stage, (it % p.pairs) * XL_V, it / p.pairs, tid);
-            xl_cp_async_wait();
-        }
-        XlFft<L, XL_V>::init_tw(t, p.tw);
-        const double z = p.z ? xl_ldg(p.z) : 0.0;
-        double cr = p.epi_cr, ci = p.epi_ci;
-        if (p.epi_times_z) { cr *= z; ci *= z; }
-        const XlRsHConst hc = xl_rs_hconst(z, p.k);
-        for (; it < items; it += XL_GRID_X) {
-            const int cl = it / p.pairs, lb = (it % p.pairs) * XL_V, nx = it + XL_GRID_X;
-            const XlCztOp<L, PRO, EPI, ACC> base{{}, p, lb, cl, p.c0 + cl, z, hc, make_float2((float)cr, (float)ci)};
-            const XlCztPersistOp<L, PRO, EPI, ACC> op(base, stage, nx < items ? (nx % p.pairs) * XL_V : -1, nx < items ? nx / p.pairs : 0);
-            XlFft<L, XL_V>::conv(s, t, op);
-            XL_THREADS(tid, NT) { xl_cp_async_wait(); }
-            XL_SYNC();
-        }
-    }
-};
-#endif
 
 // Bluestein tables for one axis (wave_optics.py:385-410, 430-459), all phases in fp64:
 //   pre[k]  = A^-k * h_k                       h_j = W^(j^2/2) on the principal branch of log W
@@ -1380,7 +834,6 @@ template <int L> struct XlCztSetup {
     }
 };
 
-#ifdef XL_EXP_TREE_REDUCE   // experiment (DESIGN.md queue item 4): not part of the default build
 // red[0] = sum of red[0..NT) by a shared-memory tree (NT a power of two); ends with a barrier.
 template <int NT, class T> XL_DEV void xl_block_sum(T* red) {
     for (int st = NT / 2; st >= 1; st >>= 1) {
@@ -1390,7 +843,6 @@ template <int NT, class T> XL_DEV void xl_block_sum(T* red) {
         XL_SYNC();
     }
 }
-#endif
 
 // gz += -k Im sum ct*out : the i k h part of dh/dz, evaluated exactly (fp32 x fp32 products are exact in fp64).
 struct XlDotZParams {
@@ -1419,20 +871,10 @@ struct XlDotZ {
             red[tid] = acc;
         }
         XL_SYNC();
-#ifdef XL_EXP_TREE_REDUCE
         xl_block_sum<NT>(red);
         XL_THREADS(tid, NT) {
             if (tid == 0) xl_atomic_add(p.gz, -p.k * red[0]);
         }
-#else
-        XL_THREADS(tid, NT) {
-            if (tid == 0) {
-                double a = 0.0;
-                for (int i = 0; i < NT; ++i) a += red[i];
-                xl_atomic_add(p.gz, -p.k * a);
-            }
-        }
-#endif
     }
 };
 
@@ -1501,20 +943,10 @@ struct XlFold {
         }
         XL_SYNC();
         if (p.gz) {   // kernel-uniform
-#ifdef XL_EXP_TREE_REDUCE
             xl_block_sum<NT>(red);
             XL_THREADS(tid, NT) {
                 if (tid == 0) xl_atomic_add(p.gz, (double)red[0]);
             }
-#else
-            XL_THREADS(tid, NT) {
-                if (tid == 0) {
-                    double a = 0.0;
-                    for (int i = 0; i < NT; ++i) a += (double)red[i];
-                    xl_atomic_add(p.gz, a);
-                }
-            }
-#endif
         }
     }
 };

@@ -47,6 +47,7 @@ static inline void xl_prefetch_l2(const void*) {}
 static inline void xl_cp_async8(float2* dst, const float2* src) { *dst = *src; }
 static inline void xl_cp_async16(float2* dst, const float2* src) { dst[0] = src[0]; dst[1] = src[1]; }
 static inline void xl_cp_async_wait() {}
+static inline void xl_nanosleep(unsigned) {}
 #else
 #include <cuda_runtime.h>
 #define XL_DEV __device__ __forceinline__
@@ -77,6 +78,7 @@ XL_DEV void xl_cp_async16(float2* dst, const float2* src) {   // 16-byte aligned
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
 }
 XL_DEV void xl_cp_async_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+XL_DEV void xl_nanosleep(unsigned ns) { __nanosleep(ns); }
 // exchange one complex value with the neighbouring lane (lane ^ 1); callers guarantee that lanes 2k and 2k+1 are
 // active together (the host emulation runs threads one after another and uses plain 8-byte accesses instead)
 XL_DEV float2 xl_xchg1(float2 v) {

@@ -1,0 +1,187 @@
+// xl_rs.cu -- C ABI of the RS / VRS path (include/xlprop.h) over the kernels in xl_kernels.cuh / xl_async.cuh.
+#include "xl_host.h"
+#include "xl_async.cuh"
+
+// ================================================================================================ RS / VRS
+extern "C" size_t xl_rs_transfer_bytes(int N) {
+    size_t L = (size_t)xl_rs_padded_length(N);
+    return L * L * sizeof(cf);
+}
+extern "C" size_t xl_rs_workspace_bytes(int N, int nfields, int want_grad_z) {
+    size_t L = (size_t)xl_rs_padded_length(N);
+    if (!L || nfields < 1) return 0;
+    size_t spec = align_up((size_t)nfields * L * N * sizeof(cf));
+    size_t total = spec;
+    if (want_grad_z) total += spec + align_up(L * L * sizeof(cf));
+    total += align_up((size_t)3 * N * N * sizeof(cf));  // VRS backward: adjoint of the 3 components before the fold
+    return total;
+}
+
+static int rs_transfer_impl(XlRsParams p, cf* H, const double* z, int deriv, xl_stream_t st) {
+    p.H = H; p.z = z;
+    p.flags = deriv ? XL_F_DERIV : 0;
+    const int L = p.L;
+    p.rows = L; p.hrow0 = 0; p.hstore_all = 0;   // row spectra of h live inside H: [L/2][L][2], rows 0..L/2
+    int rc;
+    XL_FOR_L(L, rc = xl_launch<XlHRows<XL>>(XlDim{xl_groups(L / 2 + 1), 1}, st, p));
+    if (rc) return rc;
+    XL_FOR_L(L, rc = xl_launch<XlHCols<XL>>(XlDim{L / XL_V, 1}, st, p));
+    return rc;
+}
+
+extern "C" int xl_rs_transfer(void* H, const double* z, int N, double dx, double dy, double k, int deriv, void* stream) {
+    if (!H || !z) return xl_fail(XL_E_BAD_ARG, "xl_rs_transfer: null pointer%s", "");
+    XlRsParams p;
+    int rc = rs_base_params(p, N, dx, dy, k);
+    if (rc) return rc;
+    return rs_transfer_impl(p, (cf*)H, z, deriv, (xl_stream_t)stream);
+}
+
+
+// Row spectra of `nfields` planes (field 2 formed as Ez when XL_F_VRS is set).  Even N: persistent CTAs with bulk-staged
+// row pairs (xl_async.cuh); odd N (rows are not 16-byte multiples): one CTA per row pair with direct loads.
+static int rs_rows_fwd_launch(XlRsParams p, xl_stream_t st) {
+    const int L = p.L, N = p.N;
+    int rc;
+    if (N % 2 == 0 && aligned16(p.in)) {
+        const int groups = xl_groups(p.rows);
+        p.chunk_rows = groups * (p.nfields - ((p.flags & XL_F_VRS) ? 1 : 0));   // staged items; the Ez items come last
+        XL_FOR_L(L, rc = xl_launch_persistent<XlRsRowsFwdAsync<XL>>(groups * p.nfields, 2, st, p));
+        return rc;
+    }
+    XL_FOR_L(L, rc = xl_launch<XlRsRowsFwd<XL>>(XlDim{xl_groups(p.rows), p.nfields}, st, p));
+    return rc;
+}
+
+// rows fwd -> cols conv -> rows inv on `nfields` planes, all fields of a stage in ONE launch.  The column stage is the
+// persistent bulk-asynchronous kernel (work items walk the column pairs with the fields of a pair back to back).
+static int rs_apply_impl(XlRsParams p, xl_stream_t st) {
+    const int L = p.L, N = p.N;
+    int rc;
+    p.f0 = 0;
+    rc = rs_rows_fwd_launch(p, st);
+    if (rc) return rc;
+    if (aligned16(p.H) && aligned16(p.spec)) {
+        XL_FOR_L(L, rc = xl_launch_persistent<XlRsColsAsync<XL>>((L / XL_V) * p.nfields, 2, st, p));
+    } else {
+        XL_FOR_L(L, rc = xl_launch<XlRsCols<XL>>(XlDim{L / XL_V, p.nfields}, st, p));
+    }
+    if (rc) return rc;
+    XL_FOR_L(L, rc = xl_launch<XlRsRowsInv<XL>>(XlDim{xl_groups(N), p.nfields}, st, p));
+    return rc;
+}
+
+static int rs_fwd_common(const void* in, void* out, void* H, const double* z, int N, int nfields, int vrs,
+                         double x0, double y0, double dx, double dy, double k, int flags,
+                         void* ws, size_t ws_bytes, xl_stream_t st) {
+    if (!in || !out || !H || !z || !ws) return xl_fail(XL_E_BAD_ARG, "rs_fwd: null pointer%s", "");
+    XlRsParams p;
+    int rc = rs_base_params(p, N, dx, dy, k);
+    if (rc) return rc;
+    if (ws_bytes < xl_rs_workspace_bytes(N, nfields, 0)) return xl_fail(XL_E_WORKSPACE, "rs_fwd: workspace too small%s", "");
+    if (!(flags & XL_REUSE_H)) { rc = rs_transfer_impl(p, (cf*)H, z, 0, st); if (rc) return rc; }
+    Carver c{(char*)ws, 0, ws_bytes};
+    p.spec = (cf*)c.take((size_t)nfields * p.L * N * sizeof(cf));
+    p.in = (const cf*)in; p.out = (cf*)out; p.H = (cf*)H; p.z = z;
+    p.nfields = nfields; p.x0 = x0; p.y0 = y0;
+    p.flags = (flags & (XL_CONJ_IN | XL_CONJ_OUT)) | (vrs ? XL_F_VRS : 0);
+    return rs_apply_impl(p, st);
+}
+
+extern "C" int xl_rs_fwd(const void* in, void* out, void* H, const double* z, int N, int nfields,
+                         double dx, double dy, double k, int flags, void* ws, size_t ws_bytes, void* stream) {
+    if (nfields < 1) return xl_fail(XL_E_BAD_ARG, "xl_rs_fwd: nfields < 1%s", "");
+    return rs_fwd_common(in, out, H, z, N, nfields, 0, 0.0, 0.0, dx, dy, k, flags, ws, ws_bytes, (xl_stream_t)stream);
+}
+extern "C" int xl_vrs_fwd(const void* exy, void* out, void* H, const double* z, int N, double x0, double y0,
+                          double dx, double dy, double k, int flags, void* ws, size_t ws_bytes, void* stream) {
+    return rs_fwd_common(exy, out, H, z, N, 3, 1, x0, y0, dx, dy, k, flags, ws, ws_bytes, (xl_stream_t)stream);
+}
+
+static int rs_bwd_common(const void* in, const void* out, const void* ct_out, void* ct_in, double* grad_z, const void* H,
+                         const double* z, int N, int nfields, int vrs, double x0, double y0, double dx, double dy, double k,
+                         int flags, void* ws, size_t ws_bytes, xl_stream_t st) {
+    if (!ct_out || !ct_in || !H || !ws || !z) return xl_fail(XL_E_BAD_ARG, "rs_bwd: null pointer%s", "");
+    if (grad_z && (!in || !out)) return xl_fail(XL_E_BAD_ARG, "rs_bwd: grad_z needs the primal input and output%s", "");
+    XlRsParams p;
+    int rc = rs_base_params(p, N, dx, dy, k);
+    if (rc) return rc;
+    if (ws_bytes < xl_rs_workspace_bytes(N, nfields, grad_z != 0)) return xl_fail(XL_E_WORKSPACE, "rs_bwd: workspace too small%s", "");
+    const int L = p.L;
+    Carver c{(char*)ws, 0, ws_bytes};
+    const size_t spec_bytes = (size_t)nfields * L * N * sizeof(cf);
+    p.spec = (cf*)c.take(spec_bytes);
+    cf* tmp3 = (cf*)c.take((size_t)3 * N * N * sizeof(cf));
+    p.nfields = nfields; p.H = (cf*)H; p.z = z; p.x0 = x0; p.y0 = y0;
+    cf* dst = vrs ? tmp3 : (cf*)ct_in;
+
+    if (grad_z) {
+        p.spec2 = (cf*)c.take(spec_bytes);
+        cf* Hz = (cf*)c.take((size_t)L * L * sizeof(cf));
+        rc = rs_transfer_impl(p, Hz, z, 1, st);        // reduced derivative h_z - i k h (xl_rs_h)
+        if (rc) return rc;
+        {   // the i k h part, exactly, in real space
+            XlDotZParams d;
+            memset(&d, 0, sizeof(d));
+            d.ct = (const cf*)ct_out; d.out = (const cf*)out; d.n = (size_t)nfields * N * N; d.flags = flags & XL_CONJ_IN;
+            d.k = k; d.gz = grad_z;
+            const size_t per = (size_t)XlDotZ::NT * XlDotZ::PER;
+            rc = xl_launch<XlDotZ>(XlDim{(int)((d.n + per - 1) / per), 1}, st, d);
+            if (rc) return rc;
+        }
+        // row spectra of conj(U) -> spec2
+        {
+            XlRsParams pw = p;
+            pw.in = (const cf*)in; pw.spec = p.spec2;
+            pw.flags = XL_F_CONJ_IN | (vrs ? XL_F_VRS : 0);
+            rc = rs_rows_fwd_launch(pw, st);
+            if (rc) return rc;
+        }
+        // row spectra of the cotangent -> spec
+        XlRsParams pc = p;
+        pc.in = (const cf*)ct_out;
+        pc.flags = (flags & XL_CONJ_IN);
+        rc = rs_rows_fwd_launch(pc, st);
+        if (rc) return rc;
+        XlRsParams pg = p;
+        pg.H2 = Hz; pg.gz = grad_z;
+        XL_FOR_L(L, rc = xl_launch<XlRsColsGz<XL>>(XlDim{L, nfields}, st, pg));
+        if (rc) return rc;
+        XlRsParams po = p;
+        po.out = dst;
+        po.flags = vrs ? 0 : (flags & XL_CONJ_OUT);
+        XL_FOR_L(L, rc = xl_launch<XlRsRowsInv<XL>>(XlDim{xl_groups(N), nfields}, st, po));
+        if (rc) return rc;
+    } else {
+        XlRsParams pa = p;
+        pa.in = (const cf*)ct_out; pa.out = dst;
+        pa.flags = (flags & XL_CONJ_IN) | (vrs ? 0 : (flags & XL_CONJ_OUT));
+        rc = rs_apply_impl(pa, st);
+        if (rc) return rc;
+    }
+    if (vrs) {
+        XlFoldParams f;
+        memset(&f, 0, sizeof(f));
+        f.N = N; f.mode = XL_FOLD_VRS; f.flags = flags & XL_CONJ_OUT;
+        f.t = tmp3;
+        f.ex = (const cf*)in; f.ey = in ? (const cf*)in + (size_t)N * N : 0;
+        f.gx = (cf*)ct_in; f.gy = (cf*)ct_in + (size_t)N * N;
+        f.gz = grad_z; f.z = z; f.x0 = x0; f.y0 = y0; f.dx = dx; f.dy = dy;
+        const size_t NN = (size_t)N * N;
+        rc = xl_launch<XlFold>(XlDim{(int)((NN + XlFold::NT - 1) / XlFold::NT), 1}, st, f);
+    }
+    return rc;
+}
+
+extern "C" int xl_rs_bwd(const void* in, const void* out, const void* ct_out, void* ct_in, double* grad_z, const void* H,
+                         const double* z, int N, int nfields, double dx, double dy, double k, int flags,
+                         void* ws, size_t ws_bytes, void* stream) {
+    if (nfields < 1) return xl_fail(XL_E_BAD_ARG, "xl_rs_bwd: nfields < 1%s", "");
+    return rs_bwd_common(in, out, ct_out, ct_in, grad_z, H, z, N, nfields, 0, 0.0, 0.0, dx, dy, k, flags, ws, ws_bytes, (xl_stream_t)stream);
+}
+extern "C" int xl_vrs_bwd(const void* exy, const void* out, const void* ct_out, void* ct_exy, double* grad_z, const void* H,
+                          const double* z, int N, double x0, double y0, double dx, double dy, double k, int flags,
+                          void* ws, size_t ws_bytes, void* stream) {
+    return rs_bwd_common(exy, out, ct_out, ct_exy, grad_z, H, z, N, 3, 1, x0, y0, dx, dy, k, flags, ws, ws_bytes, (xl_stream_t)stream);
+}
+

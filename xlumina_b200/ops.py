@@ -178,30 +178,6 @@ def _cached_transfer(zkey, zobj, N, dx, dy, k, device, nbytes):
     return H, False
 
 
-# ---------------------------------------------------------------------------------------------- keep-spectra experiment
-# Development only (experiment queue item 2): with a library built with XL_EXP_KEEP_SPECTRA (selected by
-# XLPROP_LIB) and KEEP_SPECTRA = True, the forward pass keeps its row spectra (2u of device memory per field until the
-# backward pass) and d/dz does not recompute them.  The product library does not export these entry points.
-KEEP_SPECTRA = bool(os.environ.get("XL_KEEP_SPECTRA"))
-_keep_declared = set()
-
-
-def _keep_lib(L):
-    """The library if it is a keep-spectra variant and the experiment is on, else None."""
-    if not KEEP_SPECTRA or not hasattr(L, "xl_rs_fwd_keep"):
-        return None
-    if id(L) not in _keep_declared:
-        d, sz, vp, i32 = ctypes.c_double, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_int
-        L.xl_rs_spectra_bytes.restype = sz
-        L.xl_rs_spectra_bytes.argtypes = [i32, i32]
-        L.xl_rs_fwd_keep.argtypes = [vp, vp, vp, vp, i32, i32, d, d, d, i32, vp, vp, sz, vp]
-        L.xl_vrs_fwd_keep.argtypes = [vp, vp, vp, vp, i32, d, d, d, d, d, i32, vp, vp, sz, vp]
-        L.xl_rs_bwd_kept.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, i32, d, d, d, i32, vp, vp, sz, vp]
-        L.xl_vrs_bwd_kept.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, d, d, d, d, d, i32, vp, vp, sz, vp]
-        _keep_declared.add(id(L))
-    return L
-
-
 # ---------------------------------------------------------------------------------------------- RS / VRS
 class _RS(torch.autograd.Function):
     """field (F,N,N) c64, z (1,) f64 -> (F,N,N).  backward = same complex-symmetric operator + Parseval d/dz."""
@@ -216,24 +192,16 @@ class _RS(torch.autograd.Function):
         H, reuse = _cached_transfer(zkey, zobj, N, dx, dy, k, field.device, L.xl_rs_transfer_bytes(N))
         need = L.xl_rs_workspace_bytes(N, F, 0)
         ws = _workspace(field, need)
-        K = _keep_lib(L) if ctx.needs_input_grad[1] else None
-        if K is not None:
-            spectra = torch.empty(K.xl_rs_spectra_bytes(N, F), dtype=torch.uint8, device=field.device)
-            _lib.check(K.xl_rs_fwd_keep(_ptr(field), _ptr(out), _ptr(H), _ptr(z), N, F, dx, dy, k, _lib.XL_REUSE_H if reuse else 0,
-                                        _ptr(spectra), _ptr(ws), ws.numel(), _stream(field)), "xl_rs_fwd_keep")
-            ctx.save_for_backward(field, z, H, out, spectra)
-        else:
-            _lib.check(L.xl_rs_fwd(_ptr(field), _ptr(out), _ptr(H), _ptr(z), N, F, dx, dy, k, _lib.XL_REUSE_H if reuse else 0,
-                                   _ptr(ws), ws.numel(), _stream(field)), "xl_rs_fwd")
-            ctx.save_for_backward(field, z, H, out)      # out: the exact i*k*out part of d out/dz (include/xlprop.h)
+        _lib.check(L.xl_rs_fwd(_ptr(field), _ptr(out), _ptr(H), _ptr(z), N, F, dx, dy, k, _lib.XL_REUSE_H if reuse else 0,
+                               _ptr(ws), ws.numel(), _stream(field)), "xl_rs_fwd")
+        ctx.save_for_backward(field, z, H, out)      # out: the exact i*k*out part of d out/dz (include/xlprop.h)
         ctx.geom = (dx, dy, k)
         return out
 
     @staticmethod
     @_on_device
     def backward(ctx, g):
-        field, z, H, out = ctx.saved_tensors[:4]
-        spectra = ctx.saved_tensors[4] if len(ctx.saved_tensors) > 4 else None
+        field, z, H, out = ctx.saved_tensors
         dx, dy, k = ctx.geom
         L = _lib.lib()
         F, N = field.shape[0], field.shape[-1]
@@ -243,11 +211,6 @@ class _RS(torch.autograd.Function):
         gz = torch.zeros(1, dtype=torch.float64, device=field.device) if want_z else None
         need = L.xl_rs_workspace_bytes(N, F, 1 if want_z else 0)
         ws = _workspace(field, need)
-        if spectra is not None and want_z:
-            _lib.check(L.xl_rs_bwd_kept(_ptr(field), _ptr(out), _ptr(g), _ptr(gin), _ptr(gz), _ptr(H), _ptr(z), N, F, dx, dy, k,
-                                        _lib.XL_CONJ_IN | _lib.XL_CONJ_OUT, _ptr(spectra), _ptr(ws), ws.numel(), _stream(field)),
-                       "xl_rs_bwd_kept")
-            return gin, gz, None, None, None, None, None
         _lib.check(L.xl_rs_bwd(_ptr(field), _ptr(out), _ptr(g), _ptr(gin), _ptr(gz), _ptr(H), _ptr(z), N, F, dx, dy, k,
                                _lib.XL_CONJ_IN | _lib.XL_CONJ_OUT, _ptr(ws), ws.numel(), _stream(field)), "xl_rs_bwd")
         return gin, gz, None, None, None, None, None
@@ -270,14 +233,6 @@ class _VRS(torch.autograd.Function):
             if hshare is not None:
                 hshare[0] = H
         ws = _workspace(exy, L.xl_rs_workspace_bytes(N, 3, 0))
-        K = _keep_lib(L) if ctx.needs_input_grad[1] else None
-        if K is not None:
-            spectra = torch.empty(K.xl_rs_spectra_bytes(N, 3), dtype=torch.uint8, device=exy.device)
-            _lib.check(K.xl_vrs_fwd_keep(_ptr(exy), _ptr(out), _ptr(H), _ptr(z), N, x0, y0, dx, dy, k, _lib.XL_REUSE_H if reuse else 0,
-                                         _ptr(spectra), _ptr(ws), ws.numel(), _stream(exy)), "xl_vrs_fwd_keep")
-            ctx.save_for_backward(exy, z, H, out, spectra)
-            ctx.geom = (x0, y0, dx, dy, k)
-            return out
         _lib.check(L.xl_vrs_fwd(_ptr(exy), _ptr(out), _ptr(H), _ptr(z), N, x0, y0, dx, dy, k, _lib.XL_REUSE_H if reuse else 0,
                                 _ptr(ws), ws.numel(), _stream(exy)), "xl_vrs_fwd")
         ctx.save_for_backward(exy, z, H, out)
@@ -287,8 +242,7 @@ class _VRS(torch.autograd.Function):
     @staticmethod
     @_on_device
     def backward(ctx, g):
-        exy, z, H, out = ctx.saved_tensors[:4]
-        spectra = ctx.saved_tensors[4] if len(ctx.saved_tensors) > 4 else None
+        exy, z, H, out = ctx.saved_tensors
         x0, y0, dx, dy, k = ctx.geom
         L = _lib.lib()
         N = exy.shape[-1]
@@ -297,11 +251,6 @@ class _VRS(torch.autograd.Function):
         gin = torch.empty_like(exy)
         gz = torch.zeros(1, dtype=torch.float64, device=exy.device) if want_z else None
         ws = _workspace(exy, L.xl_rs_workspace_bytes(N, 3, 1 if want_z else 0))
-        if spectra is not None and want_z:
-            _lib.check(L.xl_vrs_bwd_kept(_ptr(exy), _ptr(out), _ptr(g), _ptr(gin), _ptr(gz), _ptr(H), _ptr(z), N, x0, y0, dx, dy, k,
-                                         _lib.XL_CONJ_IN | _lib.XL_CONJ_OUT, _ptr(spectra), _ptr(ws), ws.numel(), _stream(exy)),
-                       "xl_vrs_bwd_kept")
-            return gin, gz, None, None, None, None, None, None, None, None
         _lib.check(L.xl_vrs_bwd(_ptr(exy), _ptr(out), _ptr(g), _ptr(gin), _ptr(gz), _ptr(H), _ptr(z), N, x0, y0, dx, dy, k,
                                 _lib.XL_CONJ_IN | _lib.XL_CONJ_OUT, _ptr(ws), ws.numel(), _stream(exy)), "xl_vrs_bwd")
         return gin, gz, None, None, None, None, None, None, None, None
