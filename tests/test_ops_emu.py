@@ -223,34 +223,3 @@ def test_missing_distance_gradients_are_refused_not_dropped(ops_on_emu):
     with torch.no_grad():
         assert ops.czt(u, z, 0.6328, x, x, xo, xo).shape == (6, 6)
     assert ops.czt(u, z.detach(), 0.6328, x, x, xo, xo).shape == (6, 6)
-
-
-def test_keep_spectra_experiment_through_the_host_layer(monkeypatch, tmp_path):
-    """ops.KEEP_SPECTRA with a library built with XL_EXP_KEEP_SPECTRA (development only): the sharp-focus table (16 VRS with
-    distance gradients) gives the same loss gradients as the fixtures; with the product library the switch does nothing."""
-    from conftest import emu_variant_path
-    from test_elements import directional, sharp_focus_losses, sharp_focus_problem
-    var = _lib.declare(ctypes.CDLL(emu_variant_path(["XL_EXP_KEEP_SPECTRA"])))
-    monkeypatch.setattr(_lib, "_lib", var)
-    monkeypatch.setattr(ops, "_require_device", lambda t: None)
-    monkeypatch.setattr(ops, "_stream", lambda t: ctypes.c_void_p(0))
-    monkeypatch.setattr(ops, "_stream_key", lambda t: ("cpu", 0))
-    monkeypatch.setattr(ops, "_workspaces", {})
-    monkeypatch.setattr(ops, "KEEP_SPECTRA", True)
-    calls = {"n": 0}
-    real = var.xl_vrs_bwd_kept
-
-    def counted(*a):
-        calls["n"] += 1
-        return real(*a)
-    ops._keep_lib(var)                                   # declares the argtypes on the real functions first
-    monkeypatch.setattr(var, "xl_vrs_bwd_kept", counted, raising=False)
-    g = golden("sharp_focus_n32")
-    ls, params, fixed = sharp_focus_problem(g, "cpu", torch.complex64)
-    inten, lv, l_soft, l_lin = sharp_focus_losses(g, ls, params, fixed)
-    gl = torch.autograd.grad(l_lin, params, allow_unused=True)
-    assert calls["n"] == 16                              # every VRS of the table went through the kept-spectra backward
-    assert rel_l2(inten.detach().numpy(), g["intensities"]) < 1e-4
-    for t in ("all", "dist", "other"):
-        want = float(g["dlin_" + t])
-        assert abs(directional(g, params, gl, t) - want) < 1e-3 * abs(want), t

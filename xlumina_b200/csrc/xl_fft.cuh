@@ -30,6 +30,8 @@
 XL_HD constexpr int xl_first_radix(int L) { return L > 16 ? xl_first_radix(L / 16) : L; }
 XL_HD constexpr int xl_tile_elems(int L, int V) { return (L + L / 16) * V; }          // cf elements of the padded tile
 XL_HD constexpr int xl_threads(int L) { return (L / 16) < 32 ? 32 : (L / 16); }
+// lanes of a warp that run the butterfly loops `for (beta = tid; beta < L/16; beta += NT)` of XlFft<L>
+XL_HD constexpr unsigned xl_lane_mask(int L) { return (L / 16) >= 32 ? 0xffffffffu : ((1u << (L / 16)) - 1u); }
 XL_HD constexpr int xl_tw_mids(int B) { return B >= 256 ? 2 * (B / 16) + xl_tw_mids(B / 16) : 0; }
 XL_HD constexpr int xl_tw_level0(int L) { return (L / xl_first_radix(L)) * (xl_first_radix(L) == 16 ? 2 : 1); }
 XL_HD constexpr int xl_tw_total(int L) { return xl_tw_level0(L) + xl_tw_mids(L / xl_first_radix(L)); }

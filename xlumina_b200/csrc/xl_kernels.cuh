@@ -38,18 +38,18 @@ XL_DEV void xl_st4(cf* p, cf a, cf b) { *reinterpret_cast<float4*>(p) = make_flo
 // its lane) of the two adjacent rows y0 (v0) and y0+1 (v1); rows >= nrows are not stored / read as zero.
 // GPU: lanes 2k and 2k+1 swap one value so that each issues ONE 16-byte access (even lane: row y0, slots g,g+1; odd lane:
 // row y0+1, slots g-1,g) -- 8-byte scattered accesses halve the L1<->L2 request efficiency (profiles/ubench_r01.txt).
-XL_DEV void xl_blocked_store2(cf* grp, int y0, int nrows, int g, cf v0, cf v1) {
+template <unsigned MASK> XL_DEV void xl_blocked_store2(cf* grp, int y0, int nrows, int g, cf v0, cf v1) {
 #ifdef XL_HOST_EMU
     if (y0 < nrows) grp[(size_t)y0 * 2 + (g & 1)] = v0;
     if (y0 + 1 < nrows) grp[(size_t)(y0 + 1) * 2 + (g & 1)] = v1;
 #else
     const bool odd = g & 1;
-    const cf got = xl_xchg1(odd ? v0 : v1), keep = odd ? v1 : v0;
+    const cf got = xl_xchg1<MASK>(odd ? v0 : v1), keep = odd ? v1 : v0;
     const int y = y0 + (odd ? 1 : 0);
     if (y < nrows) xl_st4(grp + (size_t)y * 2, odd ? got : keep, odd ? keep : got);
 #endif
 }
-XL_DEV void xl_blocked_load2(const cf* grp, int y0, int nrows, int g, cf* v0, cf* v1) {
+template <unsigned MASK> XL_DEV void xl_blocked_load2(const cf* grp, int y0, int nrows, int g, cf* v0, cf* v1) {
 #ifdef XL_HOST_EMU
     *v0 = y0 < nrows ? grp[(size_t)y0 * 2 + (g & 1)] : cf_zero();
     *v1 = y0 + 1 < nrows ? grp[(size_t)(y0 + 1) * 2 + (g & 1)] : cf_zero();
@@ -58,7 +58,7 @@ XL_DEV void xl_blocked_load2(const cf* grp, int y0, int nrows, int g, cf* v0, cf
     const int y = y0 + (odd ? 1 : 0);
     cf lo = cf_zero(), hi = cf_zero();
     if (y < nrows) xl_ld4(grp + (size_t)y * 2, &lo, &hi);
-    const cf got = xl_xchg1(odd ? lo : hi);
+    const cf got = xl_xchg1<MASK>(odd ? lo : hi);
     *v0 = odd ? got : lo;
     *v1 = odd ? hi : got;
 #endif
@@ -138,6 +138,7 @@ struct XlRsParams {
     int chunk_rows;    // slab column kernels: rows per source rank in the exchanged layout [rank][pair][chunk_rows][2]
     int hrow0, hstore_all;   // slab h_rows: first y row of this rank; store every x slot pair (no x-mirror skipping)
     const cf* in;      // [nfields][N][N]   (XL_F_VRS: [2][N][N] = Ex,Ey)
+    const cf* in2;     // rs_rows_dual: the primal field(s) whose conjugate is the second line (same shape rules as `in`)
     cf* out;           // [nfields][N][N]
     cf* spec;          // [nfields][L/2][N][2]
     cf* spec2;         // second spectra set (grad-z: spectra of conj(U))
@@ -182,7 +183,7 @@ template <int L, bool EZ> struct XlRsRowsFwdOp : XlOpBase {
 #pragma unroll
         for (int q = 0; q < 16; ++q) {
             const int g = q * (L / 16) + beta;
-            xl_blocked_store2(base + (size_t)(g / 2) * p.rows * 2, yb, p.rows, g, v[q], v[16 + q]);
+            xl_blocked_store2<xl_lane_mask(L)>(base + (size_t)(g / 2) * p.rows * 2, yb, p.rows, g, v[q], v[16 + q]);
         }
     }
     XL_DEV void store_vec(int, const cf*) const {}
@@ -207,6 +208,61 @@ template <int L> struct XlRsRowsFwd {
     }
 };
 
+// K1d: one row of the cotangent AND the same row of conj(primal field) as the two lines of one transform -> interleaved
+// row spectra  CW[f][L/2 slot pairs][y][4] = (C_g, W_g, C_g+1, W_g+1):  the d/dz column kernel needs both column spectra of
+// one x frequency in the registers of one thread (XlRsColsGzAsync) and reads them with one 16-byte load per row; two
+// adjacent lanes (slots g, g+1) fill one 32-byte sector here.  Replaces the two separate row-spectra launches of the
+// backward pass (JAX autodiff of wave_optics.py:286-288).
+template <int L, bool EZ> struct XlRsRowsDualOp : XlOpBase {
+    static constexpr bool kInLoHalf = true;
+    const XlRsParams& p; int f, y; double z2;
+    XL_DEV void load(int i, cf* v, int stride) const {
+        const int N = p.N;
+        const bool ok = i < N;
+        const size_t NN = (size_t)p.rows * N, o = ok ? (size_t)y * N + i : 0;
+        cf c = p.in[(size_t)f * NN + o], w;
+        if (p.flags & XL_F_CONJ_IN) c = cf_conj(c);
+        if (EZ) {
+            const cf ex = p.in2[o], ey = p.in2[NN + o];
+            const double X = p.x0 + i * p.dx, Y = p.y0 + y * p.dy;
+            const double ir = xl_rsqrt64(X * X + Y * Y + z2);
+            w = cf_lin2(ex, (float)(X * ir), ey, (float)(Y * ir));
+        } else {
+            w = p.in2[(size_t)f * NN + o];
+        }
+        v[0] = ok ? c : cf_zero();
+        v[stride] = ok ? cf_conj(w) : cf_zero();
+    }
+    XL_DEV void spec(int beta, const cf* v) const {
+        cf* base = p.spec + (size_t)f * L * p.rows * 2 + (size_t)y * 4;
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            const int g = q * (L / 16) + beta;
+            xl_st4(base + (size_t)(g >> 1) * p.rows * 4 + (g & 1) * 2, v[q], v[16 + q]);
+        }
+    }
+    XL_DEV void store_vec(int, const cf*) const {}
+};
+template <int L> struct XlRsRowsDual {
+    static const char* name() { return "rs_rows_dual"; }
+    typedef XlRsParams Params;
+    static constexpr int NT = xl_threads(L);
+    static size_t smem() { return xl_smem_bytes(L, XL_V); }
+    XL_DEV static void run(const Params& p, cf* s) {
+        cf* t = s + xl_tile_elems(L, XL_V);
+        XlFft<L, XL_V>::init_tw(t, p.tw);
+        const int f = p.f0 + XL_BLOCK_Y, y = XL_BLOCK_X;
+        if ((p.flags & XL_F_VRS) && f == 2) {   // CTA-uniform
+            const double z = xl_ldg(p.z);
+            XlRsRowsDualOp<L, true> op{{}, p, f, y, z * z};
+            XlFft<L, XL_V>::forward(s, t, op);
+        } else {
+            XlRsRowsDualOp<L, false> op{{}, p, f, y, 0.0};
+            XlFft<L, XL_V>::forward(s, t, op);
+        }
+    }
+};
+
 // The impulse response is even in x, so its transfer function is even in the x frequency: only the columns of bins
 // kx <= L/2 are ever computed (h_cols) and the column of bin kx > L/2 is read from its mirror L - kx.
 // Returns the address of element [slot_y = 0] of the column that serves x-slot g; consecutive slot_y are 2 cf apart.
@@ -217,6 +273,19 @@ template <int L> XL_DEV const cf* xl_h_column(const cf* H, int g) {
 }
 template <int L> XL_DEV bool xl_h_pair_needed(int G) {   // does slot pair G hold a column with bin <= L/2 ?
     return xl_slot_to_bin_t<L>(2 * G) <= L / 2 || xl_slot_to_bin_t<L>(2 * G + 1) <= L / 2;
+}
+
+// Column copies.  Pair G holds a needed column (x-bin <= L/2) exactly when G <= L/4 (the top digit of a bin is the top digit
+// of its slot), so the blocks G > L/4 of the [L/2][L][2] buffer are never touched by the pair layout.  That space holds a
+// second copy of every needed column as a CONTIGUOUS array  Hc[slot <= L/2 + 1][xl_hc_stride]  (rows = y slots 0..L/2), the
+// shape the bulk-asynchronous column kernels stage with one copy per column (xl_async.cuh).
+XL_HD constexpr int xl_hc_stride(int L) { return L / 2 + 4; }                              // cf per column copy (16-byte multiple)
+XL_HD constexpr int xl_hc_rows(int L) { return L / 2 + 2; }                                // cf staged per column (16-byte multiple)
+XL_HD constexpr size_t xl_hc_offset(int L) { return (size_t)(L / 4 + 1) * L * 2; }         // cf offset of the copies inside H
+template <int L> XL_DEV const cf* xl_h_colcopy(const cf* H, int g) {                       // the copy that serves x-slot g
+    const int k = xl_slot_to_bin_t<L>(g);
+    const int sc = xl_bin_to_slot_t<L>(k <= L / 2 ? k : L - k);
+    return H + xl_hc_offset(L) + (size_t)sc * xl_hc_stride(L);
 }
 
 // Row (slot_y) of the stored half of the transfer function that serves slot q*(L/16)+beta: the slot itself when its
@@ -280,34 +349,6 @@ template <int L, bool SLAB = false> struct XlRsColsOp : XlOpBase {
         }
     }
 };
-template <int L> struct XlRsCols {
-    static const char* name() { return "rs_cols"; }
-    typedef XlRsParams Params;
-    static constexpr int NT = xl_threads(L);
-    static size_t smem() { return xl_smem_bytes(L, XL_V); }
-    XL_DEV static void run(const Params& p, cf* s) {
-        cf* t = s + xl_tile_elems(L, XL_V);
-        XlFft<L, XL_V>::init_tw(t, p.tw);
-        const int G = XL_BLOCK_X, f = p.f0 + XL_BLOCK_Y;
-        const cf* H0 = xl_h_column<L>(p.H, XL_V * G);
-        const cf* H1 = xl_h_column<L>(p.H, XL_V * G + 1);
-        const bool a0 = (((size_t)(H0 - p.H)) & 1) == 0, a1 = (((size_t)(H1 - p.H)) & 1) == 0;
-        const int hmode = (a0 && H1 == H0 + 1) ? 0 : ((a1 && H0 == H1 + 1) ? 1 : 2);
-        XL_THREADS(tid, NT) {   // the spectrum multiply is ~2 passes away: start moving the transfer function into L2 now
-            for (int beta = tid; beta < L / 16; beta += NT)
-#pragma unroll
-                for (int q = 0; q < 8; ++q) {   // stored rows are the slots of y-bins <= L/2 (q < 8, plus slot L/2)
-                    if (beta & 1) continue;       // one prefetch per 32-byte sector
-                    xl_prefetch_l2(H0 + (size_t)(q * (L / 16) + beta) * XL_V);
-                    if (hmode == 2) xl_prefetch_l2(H1 + (size_t)(q * (L / 16) + beta) * XL_V);
-                }
-        }
-        XlRsColsOp<L> op{{}, p, p.spec + (size_t)f * L * p.N + (size_t)G * p.N * XL_V, H0, H1, hmode, 0};
-        XlFft<L, XL_V>::conv(s, t, op);
-    }
-};
-
-
 // K2 of the slab-decomposed path: this rank owns gridDim.x slot pairs; its transfer-function slab H is [pairs][L][2]
 // (generated for exactly these columns, so no x-mirroring), its spectra arrive as [source rank][pairs][chunk_rows][2].
 template <int L> struct XlRsColsSlab {
@@ -337,7 +378,7 @@ template <int L> struct XlRsRowsInvOp : XlOpBase {
 #pragma unroll
         for (int q = 0; q < 16; ++q) {
             const int g = q * (L / 16) + beta;
-            xl_blocked_load2(base + (size_t)(g / 2) * p.rows * 2, yb, p.rows, g, v + q, v + 16 + q);
+            xl_blocked_load2<xl_lane_mask(L)>(base + (size_t)(g / 2) * p.rows * 2, yb, p.rows, g, v + q, v + 16 + q);
         }
     }
     XL_DEV void store_vec(int n, const cf* v) const {
@@ -386,7 +427,7 @@ template <int L> struct XlHRowsOp : XlOpBase {
             // rest is mirrored.  slab: every slot pair, rows in a [pair][rows][2] buffer of this rank's y rows.
             const int g = q * (L / 16) + beta;
             if (!p.hstore_all && (q > 8 || (q == 8 && beta >= 2))) continue;
-            xl_blocked_store2(p.H + (size_t)(g / 2) * p.rows * 2, yb, nvalid, g, v[q], v[16 + q]);
+            xl_blocked_store2<xl_lane_mask(L)>(p.H + (size_t)(g / 2) * p.rows * 2, yb, nvalid, g, v[q], v[16 + q]);
         }
     }
     XL_DEV void store_vec(int, const cf*) const {}
@@ -419,7 +460,7 @@ template <int L> struct XlHRows {
 
 // K2h: column FFT of the impulse-response row spectra (even in y: row L-y == row y), result in slot order, scaled.
 template <int L> struct XlHColsOp : XlOpBase {
-    const XlRsParams& p; cf* Ht;
+    const XlRsParams& p; cf* Ht; cf* Hc0; cf* Hc1;   // pair block (in place) and the two column copies
     XL_DEV void load(int i, cf* v, int stride) const {
         const int r = i <= L / 2 ? i : L - i;
         xl_ld4(Ht + (size_t)r * XL_V, v, v + stride);
@@ -428,7 +469,11 @@ template <int L> struct XlHColsOp : XlOpBase {
 #pragma unroll
         for (int q = 0; q <= 8; ++q) {   // y-bins <= L/2 only: H is even in the y frequency as well (XlHRow)
             if (q == 8 && beta != 0) continue;
-            xl_st4(Ht + (size_t)(q * (L / 16) + beta) * XL_V, cf_scale(v[q], p.hscale), cf_scale(v[16 + q], p.hscale));
+            const int r = q * (L / 16) + beta;
+            const cf a = cf_scale(v[q], p.hscale), b = cf_scale(v[16 + q], p.hscale);
+            xl_st4(Ht + (size_t)r * XL_V, a, b);
+            Hc0[r] = a;
+            Hc1[r] = b;
         }
     }
     XL_DEV void store_vec(int, const cf*) const {}
@@ -473,45 +518,15 @@ template <int L> struct XlHCols {
         if (!xl_h_pair_needed<L>(XL_BLOCK_X)) return;   // CTA-uniform: mirrored columns are never read
         cf* t = s + xl_tile_elems(L, XL_V);
         XlFft<L, XL_V>::init_tw(t, p.tw);
-        XlHColsOp<L> op{{}, p, p.H + (size_t)XL_BLOCK_X * L * XL_V};
+        cf* Hc = p.H + xl_hc_offset(L) + (size_t)XL_BLOCK_X * XL_V * xl_hc_stride(L);
+        XlHColsOp<L> op{{}, p, p.H + (size_t)XL_BLOCK_X * L * XL_V, Hc, Hc + xl_hc_stride(L)};
         // the in-place update is safe: every load of the first pass happens before the barrier that precedes the stores
         XlFft<L, XL_V>::forward(s, t, op);
     }
 };
 
-// K4: backward column kernel with d/dz.  One CTA owns one column PAIR and walks its two columns; per column the two
-// "lines" of the forward FFT are the cotangent spectra column C and the column W of the spectra of conj(U) (spec2), so
-// both column spectra meet in the registers of the same thread:  gz += Re sum conj(W)*C*Hz  (Parseval form of ct_z,
-// SURVEY.md A.1).  C*H then goes through a one-line inverse FFT in a second tile for ct_field.  Three FFTs per column,
-// nothing parked in HBM.
-template <int L> struct XlRsColsGzOp : XlOpBase {
-    static constexpr bool kInLoHalf = true;
-    const XlRsParams& p; const cf* ctile; const cf* wtile; int c; const cf* Hc; const cf* Hzc; cf* itile; float* red;
-    XL_DEV void load(int i, cf* v, int stride) const {
-        const bool ok = i < p.N;
-        const size_t o = ok ? (size_t)i * XL_V + c : 0;
-        const cf a = ctile[o], w = wtile[o];
-        v[0] = ok ? a : cf_zero();
-        v[stride] = ok ? w : cf_zero();
-    }
-    XL_DEV void spec(int beta, const cf* v) const {
-        float acc = 0.f;
-        cf u[16];
-        const XlHRow<L> hr(beta);
-#pragma unroll
-        for (int q = 0; q < 16; ++q) {
-            const size_t o = (size_t)hr.row(q) * XL_V;
-            const cf t = cf_mul(v[q], xl_ldg(Hzc + o));
-            acc += v[16 + q].x * t.x + v[16 + q].y * t.y;  // Re(conj(w) * t)
-            u[q] = cf_mul(v[q], xl_ldg(Hc + o));
-        }
-        red[beta] += acc;
-        XlBfly<16, +1, false, false>::run(u);       // first inverse pass, fused
-#pragma unroll
-        for (int j = 0; j < 16; ++j) XlTile<1>::st(itile, 16 * beta + j, u + j, 16);
-    }
-    XL_DEV void store_vec(int, const cf*) const {}
-};
+// K4 (the backward column kernel with d/dz, XlRsColsGzAsync) lives in xl_async.cuh; this functor drains its one-line inverse
+// into the blocked pair layout the inverse row kernel reads.
 template <int L> struct XlRsColsGzOutOp : XlOpBase {
     static constexpr bool kOutLoHalf = true;
     static constexpr int R1 = xl_first_radix(L), S1 = L / R1;
@@ -525,48 +540,6 @@ template <int L> struct XlRsColsGzOutOp : XlOpBase {
     }
 };
 
-
-
-template <int L> struct XlRsColsGz {
-    static const char* name() { return "rs_cols_gz"; }
-    typedef XlRsParams Params;
-    static constexpr int NT = xl_threads(L);
-    static constexpr int NB = L / 16;   // butterflies per line == entries of the partial-sum array
-    static size_t smem() { return (size_t)(xl_tile_elems(L, 2) + xl_tile_elems(L, 1) + xl_tw_total(L)) * sizeof(cf) + (size_t)(NB + 32) * sizeof(float); }
-    XL_DEV static void run(const Params& p, cf* s) {
-        cf* itile = s + xl_tile_elems(L, 2);
-        cf* t = itile + xl_tile_elems(L, 1);
-        float* red = (float*)(t + xl_tw_total(L));
-        XL_THREADS(tid, NT) { for (int i = tid; i < NB; i += NT) red[i] = 0.f; }
-        XlFft<L, 2>::init_tw(t, p.tw);
-        const int G = XL_BLOCK_X >> 1, c = XL_BLOCK_X & 1, f = p.f0 + XL_BLOCK_Y;   // one column per CTA
-        const size_t toff = (size_t)f * L * p.N + (size_t)G * p.N * XL_V;
-        {
-            XlRsColsGzOp<L> op{{}, p, p.spec + toff, p.spec2 + toff, c, xl_h_column<L>(p.H, XL_V * G + c),
-                               xl_h_column<L>(p.H2, XL_V * G + c), itile, red};
-            XlFft<L, 2>::forward(s, t, op);
-            XL_SYNC();
-            XlRsColsGzOutOp<L> oo{{}, p, p.spec + toff, c};
-            XlFft<L, 1>::inverse_tail(itile, t, oo);
-            XL_SYNC();
-        }
-        XL_THREADS(tid, NT) {
-            if (tid < 32) {
-                float a = 0.f;
-                for (int i = tid; i < NB; i += 32) a += red[i];
-                red[NB + tid] = a;
-            }
-        }
-        XL_SYNC();
-        XL_THREADS(tid, NT) {
-            if (tid == 0) {
-                double a = 0.0;
-                for (int i = 0; i < 32; ++i) a += (double)red[NB + i];
-                xl_atomic_add(p.gz, a);
-            }
-        }
-    }
-};
 
 
 // ==================================================================================================================

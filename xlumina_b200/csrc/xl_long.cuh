@@ -58,7 +58,7 @@ template <int L0> struct XlLongRowsFwdOp : XlOpBase {
 #pragma unroll
         for (int qq = 0; qq < 16; ++qq) {
             const int g = q * L0 + qq * (L0 / 16) + beta;
-            xl_blocked_store2(p.spec + (size_t)(g / 2) * p.rows * 2, yb, p.rows, g, v[qq], v[16 + qq]);
+            xl_blocked_store2<xl_lane_mask(L0)>(p.spec + (size_t)(g / 2) * p.rows * 2, yb, p.rows, g, v[qq], v[16 + qq]);
         }
     }
     XL_DEV void store_vec(int, const cf*) const {}
@@ -85,7 +85,7 @@ template <int L0> struct XlLongRowsInvOp : XlOpBase {
 #pragma unroll
         for (int qq = 0; qq < 16; ++qq) {
             const int g = q * L0 + qq * (L0 / 16) + beta;
-            xl_blocked_load2(p.spec + (size_t)(g / 2) * p.rows * 2, yb, p.rows, g, v + qq, v + 16 + qq);
+            xl_blocked_load2<xl_lane_mask(L0)>(p.spec + (size_t)(g / 2) * p.rows * 2, yb, p.rows, g, v + qq, v + 16 + qq);
         }
     }
     XL_DEV void store_vec(int n, const cf* v) const {
@@ -278,7 +278,7 @@ template <int L0> struct XlLongHRowsOp : XlOpBase {
 #pragma unroll
         for (int qq = 0; qq < 16; ++qq) {
             const int g = q * L0 + qq * (L0 / 16) + beta;
-            xl_blocked_store2(p.spec + (size_t)(g / 2) * p.hrows * 2, yb, p.hrows, g, v[qq], v[16 + qq]);
+            xl_blocked_store2<xl_lane_mask(L0)>(p.spec + (size_t)(g / 2) * p.hrows * 2, yb, p.hrows, g, v[qq], v[16 + qq]);
         }
     }
     XL_DEV void store_vec(int, const cf*) const {}

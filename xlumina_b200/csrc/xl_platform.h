@@ -43,6 +43,7 @@ static inline float4 xl_ldg(const float4* p) { return *p; }
 static inline double xl_ldg(const double* p) { return *p; }
 static inline void xl_atomic_add(double* p, double v) { *p += v; }
 static inline void xl_prefetch_l2(const void*) {}
+static inline void xl_prefetch_l2_bulk(const void*, unsigned) {}
 // asynchronous 8-byte global -> shared copy (the emulation copies at issue time; waiting is then a no-op)
 static inline void xl_cp_async8(float2* dst, const float2* src) { *dst = *src; }
 static inline void xl_cp_async16(float2* dst, const float2* src) { dst[0] = src[0]; dst[1] = src[1]; }
@@ -69,6 +70,10 @@ XL_DEV float4 xl_ldg(const float4* p) { return __ldg(p); }
 XL_DEV double xl_ldg(const double* p) { return __ldg(p); }
 XL_DEV void xl_atomic_add(double* p, double v) { atomicAdd(p, v); }
 XL_DEV void xl_prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// one instruction asks L2 to fetch a contiguous block (bytes a multiple of 16, 16-byte aligned address)
+XL_DEV void xl_prefetch_l2_bulk(const void* p, unsigned bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
 // asynchronous 8-byte global -> shared copy (LDGSTS: no registers, completion by xl_cp_async_wait of the issuing thread,
 // visibility to the other threads of the CTA by the next barrier)
 XL_DEV void xl_cp_async8(float2* dst, const float2* src) {
@@ -79,11 +84,12 @@ XL_DEV void xl_cp_async16(float2* dst, const float2* src) {   // 16-byte aligned
 }
 XL_DEV void xl_cp_async_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 XL_DEV void xl_nanosleep(unsigned ns) { __nanosleep(ns); }
-// exchange one complex value with the neighbouring lane (lane ^ 1); callers guarantee that lanes 2k and 2k+1 are
-// active together (the host emulation runs threads one after another and uses plain 8-byte accesses instead)
-XL_DEV float2 xl_xchg1(float2 v) {
-    const unsigned m = __activemask();
-    return make_float2(__shfl_xor_sync(m, v.x, 1), __shfl_xor_sync(m, v.y, 1));
+// exchange one complex value with the neighbouring lane (lane ^ 1).  MASK = the lanes that execute the call, a compile-time
+// constant (xl_lane_mask(L): the butterfly loops of XlFft<L> run lanes [0, min(32, L/16)) of every warp).  A run-time
+// __activemask() here makes the compiler fence every exchange (VOTE + BRA.DIV) and serialise the loads around it.
+// (The host emulation runs threads one after another and uses plain 8-byte accesses instead.)
+template <unsigned MASK> XL_DEV float2 xl_xchg1(float2 v) {
+    return make_float2(__shfl_xor_sync(MASK, v.x, 1), __shfl_xor_sync(MASK, v.y, 1));
 }
 #endif
 
