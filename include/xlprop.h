@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define XLPROP_VERSION 102
+#define XLPROP_VERSION 200
 
 enum {
     XL_OK = 0,
@@ -49,7 +49,9 @@ enum {
 enum {
     XL_CONJ_IN = 1,   /* conjugate the (co)tangent operand while loading it */
     XL_CONJ_OUT = 2,  /* conjugate results while storing them */
-    XL_REUSE_H = 16   /* forward only: `H` already holds the transfer function for this z (cache hit) */
+    XL_REUSE_H = 16,  /* forward only: `H` already holds the transfer function for this z (cache hit) */
+    XL_REUSE_TABLES = 32   /* CZT family: `tables` already holds the tables of these sizes, grids and z (e.g. the backward
+                              call of a propagation whose forward call filled them) */
 };
 
 int xl_version(void);
@@ -118,27 +120,35 @@ void xl_debug_set_max_line(int sub_line_length);
 /* vectorial = 0: in (N,N) -> out (My,Mx)            CZT_jit,  wave_optics.py:333-357
  * vectorial = 1: in = [Ex,Ey] (2,N,N) -> out (3,My,Mx); Ez = ((Ex X + Ey Y)/r) z/r   VCZT, vectorized_optics.py:341-344,375-384
  * Input grid: x_j = x0 + j dx, y_i = y0 + i dy.  Output grid: Mx samples from xout0 to xoutl, My from yout0 to youtl.
- * Dm = lambda*z/dx (wave_optics.py:322). */
+ * Dm = lambda*z/dx (wave_optics.py:322).
+ * `tables` is a caller-owned buffer of xl_czt_tables_bytes() bytes (opaque, like H of the RS path): the Bluestein chirps and
+ * kernel spectra of both axes (compute_fft, wave_optics.py:385-410) and the RS factors F, F0 (:340-341) sampled on the
+ * input and output grids.  A call fills it unless XL_REUSE_TABLES is set; pass the buffer of the forward call with
+ * XL_REUSE_TABLES to the backward call (same sizes, grids, z).  `ws` is scratch (xl_czt_workspace_bytes()). */
 size_t xl_czt_workspace_bytes(int N, int Mx, int My, int vectorial);
+size_t xl_czt_tables_bytes(int N, int Mx, int My);
 int xl_czt_fwd(const void* in, void* out, const double* z, double lambda, int N, int Mx, int My, int vectorial,
                double x0, double dx, double y0, double dy, double xout0, double xoutl, double yout0, double youtl,
-               int flags, void* ws, size_t ws_bytes, void* stream);
+               int flags, void* tables, void* ws, size_t ws_bytes, void* stream);
 /* VJP with respect to the input field(s) (z, lambda and the grids are static in every reference caller). */
 int xl_czt_bwd(const void* ct_out, void* ct_in, const double* z, double lambda, int N, int Mx, int My, int vectorial,
                double x0, double dx, double y0, double dy, double xout0, double xoutl, double yout0, double youtl,
-               int flags, void* ws, size_t ws_bytes, void* stream);
+               int flags, void* tables, void* ws, size_t ws_bytes, void* stream);
 
 /* ---------------------------------------------------------------- high-NA objective ------------------------- */
 /* exy = [Ex,Ey] (2,N,N) -> out = [Ex,Ey,Ez] (3,My,Mx) in the focal plane:
  *   -i sin^2(theta_max)/(f lambda) * Bluestein_x(Bluestein_y( apod*G*RL(theta,phi) (Ex,Ey,Ez)^T )),  Dm = f lambda (N-1)/(2R).
- * optical_elements.py:515-672. */
+ * optical_elements.py:515-672.  `tables` (xl_highna_tables_bytes()) holds the Bluestein tables and the lens matrix
+ * apod*G*RL sampled on the input grid; it depends on the sizes, grids, radius, f and lambda only, so one buffer serves
+ * every call of an optical table that uses the same objective (XL_REUSE_TABLES). */
 size_t xl_highna_workspace_bytes(int N, int Mx, int My);
+size_t xl_highna_tables_bytes(int N, int Mx, int My);
 int xl_highna_fwd(const void* exy, void* out, int N, int Mx, int My, double radius, double f, double lambda,
                   double x0, double dx, double y0, double dy, double xout0, double xoutl, double yout0, double youtl,
-                  int flags, void* ws, size_t ws_bytes, void* stream);
+                  int flags, void* tables, void* ws, size_t ws_bytes, void* stream);
 int xl_highna_bwd(const void* ct_out, void* ct_exy, int N, int Mx, int My, double radius, double f, double lambda,
                   double x0, double dx, double y0, double dy, double xout0, double xoutl, double yout0, double youtl,
-                  int flags, void* ws, size_t ws_bytes, void* stream);
+                  int flags, void* tables, void* ws, size_t ws_bytes, void* stream);
 
 /* ---------------------------------------------------------------- instrumentation (bench.py) ---------------- */
 /* Number of kernels this library has launched in this process. */

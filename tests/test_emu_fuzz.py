@@ -56,8 +56,9 @@ def test_czt_forward_random(emu, N, Mx, My, half, frac, zmag, seed):
     ref = o.CZT(f, x, x, 0.6328, zmag, xo, yo)
     out = np.zeros((My, Mx), np.complex64)
     ws = np.zeros(emu.xl_czt_workspace_bytes(N, Mx, My, 0), np.uint8)
+    tb = np.zeros(emu.xl_czt_tables_bytes(N, Mx, My), np.uint8)
     zz = np.array([zmag])
     rc = emu.xl_czt_fwd(ptr(c64(f)), ptr(out), ptr(zz), 0.6328, N, Mx, My, 0, x[0], x[1] - x[0], x[0], x[1] - x[0],
-                        xo[0], xo[-1], yo[0], yo[-1], 0, ptr(ws), ws.size, None)
+                        xo[0], xo[-1], yo[0], yo[-1], 0, ptr(tb), ptr(ws), ws.size, None)
     assert rc == 0, emu.xl_last_error()
     assert rel_l2(out, ref) < TOL

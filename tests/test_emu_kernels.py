@@ -158,8 +158,9 @@ def test_vectorial_paths_at_2048(emu):
     xo = np.linspace(-10, 10, 400)
     foc = np.zeros((3, 400, 400), np.complex64)
     ws = np.zeros(emu.xl_highna_workspace_bytes(N, 400, 400), np.uint8)
+    tb = np.zeros(emu.xl_highna_tables_bytes(N, 400, 400), np.uint8)
     assert emu.xl_highna_fwd(ptr(exy), ptr(foc), N, 400, 400, 1800.0, 2000.0, 0.65, x2[0], x2[1] - x2[0], x2[0], x2[1] - x2[0],
-                             xo[0], xo[-1], xo[0], xo[-1], 0, ptr(ws), ws.size, None) == 0, emu.xl_last_error()
+                             xo[0], xo[-1], xo[0], xo[-1], 0, ptr(tb), ptr(ws), ws.size, None) == 0, emu.xl_last_error()
     fref = o.VCZT_objective_lens(exy[0].astype(np.complex128), exy[1].astype(np.complex128), x2, x2, 0.65, 1800.0, 2000.0, xo, xo)
     assert rel_l2(foc, fref) < TIGHT
 
@@ -196,14 +197,18 @@ def test_vrs_forward_and_vjp_golden(emu, name):
     assert abs(gz[0] - float(g["vjp_z"])) < TOL * abs(float(g["vjp_z"]))
 
 
-def czt_call(emu, fn, a, b, g, vect, flags=0):
+def czt_call(emu, fn, a, b, g, vect, flags=0, tables=None):
+    """One xl_czt_fwd / xl_czt_bwd call; `tables` (returned) can be passed back with flags | 32 (XL_REUSE_TABLES)."""
     x, y, xo, yo = g["x"], g["y"], g["xout"], g["yout"]
     N, Mx, My = len(x), len(xo), len(yo)
     ws = np.zeros(emu.xl_czt_workspace_bytes(N, Mx, My, vect), np.uint8)
+    if tables is None:
+        tables = np.zeros(emu.xl_czt_tables_bytes(N, Mx, My), np.uint8)
     zz = np.array([float(g["z"])])
     rc = fn(ptr(a), ptr(b), ptr(zz), float(g["wavelength"]), N, Mx, My, vect, x[0], x[1] - x[0], y[0], y[1] - y[0],
-            xo[0], xo[-1], yo[0], yo[-1], flags, ptr(ws), ws.size, None)
+            xo[0], xo[-1], yo[0], yo[-1], flags, ptr(tables), ptr(ws), ws.size, None)
     assert rc == 0, emu.xl_last_error()
+    return tables
 
 
 @pytest.mark.parametrize("name", ["czt_n32_m24x40", "czt_n24_m50", "czt_n40_same"])
@@ -276,9 +281,10 @@ def test_vczt_and_highna_odd_output_sizes(emu):
     czt_call(emu, emu.xl_czt_fwd, exy, out, g, 1)
     assert rel_l2(out, o.VCZT(ex, ey, x, x, 0.6328, 7000.0, xo, yo)) < TIGHT
     ws = np.zeros(emu.xl_highna_workspace_bytes(N, Mx, My), np.uint8)
+    tb = np.zeros(emu.xl_highna_tables_bytes(N, Mx, My), np.uint8)
     out2 = np.zeros((3, My, Mx), np.complex64)
     assert emu.xl_highna_fwd(ptr(exy), ptr(out2), N, Mx, My, 350.0, 500.0, 0.635, x[0], x[1] - x[0], x[0], x[1] - x[0],
-                             xo[0], xo[-1], yo[0], yo[-1], 0, ptr(ws), ws.size, None) == 0
+                             xo[0], xo[-1], yo[0], yo[-1], 0, ptr(tb), ptr(ws), ws.size, None) == 0
     assert rel_l2(out2, o.VCZT_objective_lens(ex, ey, x, x, 0.635, 350.0, 500.0, xo, yo)) < TIGHT
 
 
@@ -313,13 +319,15 @@ def test_highna_forward_and_vjp_golden(emu, name):
     exy = c64(np.stack([g["Ex"], g["Ey"]]))
     out = np.zeros((3, My, Mx), np.complex64)
     ws = np.zeros(emu.xl_highna_workspace_bytes(N, Mx, My), np.uint8)
-    args = (N, Mx, My, float(g["radius"]), float(g["f"]), float(g["wavelength"]), x[0], x[1] - x[0], y[0], y[1] - y[0],
-            xo[0], xo[-1], yo[0], yo[-1], 0, ptr(ws), ws.size, None)
-    assert emu.xl_highna_fwd(ptr(exy), ptr(out), *args) == 0, emu.xl_last_error()
+    tb = np.zeros(emu.xl_highna_tables_bytes(N, Mx, My), np.uint8)
+    geo = (N, Mx, My, float(g["radius"]), float(g["f"]), float(g["wavelength"]), x[0], x[1] - x[0], y[0], y[1] - y[0],
+           xo[0], xo[-1], yo[0], yo[-1])
+    assert emu.xl_highna_fwd(ptr(exy), ptr(out), *geo, 0, ptr(tb), ptr(ws), ws.size, None) == 0, emu.xl_last_error()
     assert rel_l2(out, g["out"]) < TIGHT
     if "vjp_field" in g:
         gin = np.zeros((2, N, N), np.complex64)
-        assert emu.xl_highna_bwd(ptr(c64(g["ct"])), ptr(gin), *args) == 0, emu.xl_last_error()
+        # the backward call reuses the tables of the forward call (XL_REUSE_TABLES = 32)
+        assert emu.xl_highna_bwd(ptr(c64(g["ct"])), ptr(gin), *geo, 32, ptr(tb), ptr(ws), ws.size, None) == 0, emu.xl_last_error()
         assert rel_l2(gin, g["vjp_field"]) < TIGHT
 
 
@@ -330,8 +338,9 @@ def test_highna_odd_n_nan_like_reference(emu):
     exy = np.ones((2, N, N), np.complex64)
     out = np.zeros((3, M, M), np.complex64)
     ws = np.zeros(emu.xl_highna_workspace_bytes(N, M, M), np.uint8)
+    tb = np.zeros(emu.xl_highna_tables_bytes(N, M, M), np.uint8)
     assert emu.xl_highna_fwd(ptr(exy), ptr(out), N, M, M, 90.0, 100.0, 0.635, x[0], x[1] - x[0], x[0], x[1] - x[0],
-                             xo[0], xo[-1], xo[0], xo[-1], 0, ptr(ws), ws.size, None) == 0
+                             xo[0], xo[-1], xo[0], xo[-1], 0, ptr(tb), ptr(ws), ws.size, None) == 0
     assert np.isnan(out).any()
 
 

@@ -40,19 +40,22 @@ SIGNATURES = {
     "xl_slab_rows_inv": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
     "xl_debug_set_max_line": (None, [_i]),
     "xl_czt_workspace_bytes": (_sz, [_i, _i, _i, _i]),
-    "xl_czt_fwd": (_i, [_vp, _vp, _vp, _d, _i, _i, _i, _i, _d, _d, _d, _d, _d, _d, _d, _d, _i, _vp, _sz, _vp]),
-    "xl_czt_bwd": (_i, [_vp, _vp, _vp, _d, _i, _i, _i, _i, _d, _d, _d, _d, _d, _d, _d, _d, _i, _vp, _sz, _vp]),
+    "xl_czt_tables_bytes": (_sz, [_i, _i, _i]),
+    "xl_czt_fwd": (_i, [_vp, _vp, _vp, _d, _i, _i, _i, _i, _d, _d, _d, _d, _d, _d, _d, _d, _i, _vp, _vp, _sz, _vp]),
+    "xl_czt_bwd": (_i, [_vp, _vp, _vp, _d, _i, _i, _i, _i, _d, _d, _d, _d, _d, _d, _d, _d, _i, _vp, _vp, _sz, _vp]),
     "xl_highna_workspace_bytes": (_sz, [_i, _i, _i]),
-    "xl_highna_fwd": (_i, [_vp, _vp, _i, _i, _i, _d, _d, _d, _d, _d, _d, _d, _d, _d, _d, _d, _i, _vp, _sz, _vp]),
+    "xl_highna_tables_bytes": (_sz, [_i, _i, _i]),
+    "xl_highna_fwd": (_i, [_vp, _vp, _i, _i, _i, _d, _d, _d, _d, _d, _d, _d, _d, _d, _d, _d, _i, _vp, _vp, _sz, _vp]),
     "xl_launch_count": (ctypes.c_longlong, []),
     "xl_prof_enable": (None, [_i]),
     "xl_prof_report": (_i, [ctypes.c_char_p, _i]),
-    "xl_highna_bwd": (_i, [_vp, _vp, _i, _i, _i, _d, _d, _d, _d, _d, _d, _d, _d, _d, _d, _d, _i, _vp, _sz, _vp]),
+    "xl_highna_bwd": (_i, [_vp, _vp, _i, _i, _i, _d, _d, _d, _d, _d, _d, _d, _d, _d, _d, _d, _i, _vp, _vp, _sz, _vp]),
 }
 
 XL_CONJ_IN = 1
 XL_CONJ_OUT = 2
 XL_REUSE_H = 16
+XL_REUSE_TABLES = 32
 
 
 class XlpropError(RuntimeError):

@@ -2,74 +2,16 @@
 #include "xl_host.h"
 
 // ================================================================================================ CZT family
+// Caller-owned table buffer (xl_czt_tables_bytes / xl_highna_tables_bytes): Bluestein chirps and kernel spectra of both axes
+// and the pointwise factor tables.  A forward call fills it (unless XL_REUSE_TABLES); the backward call of the same
+// propagation, and any later call with the same sizes, grids and z, reuses it.
 struct CztPlan {
-    int N, Mx, My, Ly, Lx, ncomp;
-    cf *pre_y, *post_y, *ft_y, *ftT_y, *pre_x, *post_x, *ft_x, *ftT_x;
+    int N, Mx, My, Ly, Lx, ncomp, mode;
+    cf *pre_y, *post_y, *ft_y, *ftT_y, *kin_y, *pre_x, *post_x, *ft_x, *ftT_x, *kin_x;
+    cf* T[2]; int Qx[2], Qy[2]; XlFacAxis fx[2], fy[2]; int fac_kind[2];
     cf* mid;   // [ncomp][N][My]
     cf* tmp3;  // [3][N][N]
 };
-static size_t czt_ws_bytes(int N, int Mx, int My, int ncomp) {
-    int Ly = xl_czt_padded_length(N, My), Lx = xl_czt_padded_length(N, Mx);
-    if (!Ly || !Lx) return 0;
-    size_t t = 0;
-    t += 2 * align_up((size_t)N * sizeof(cf)) + align_up((size_t)My * sizeof(cf)) + align_up((size_t)Mx * sizeof(cf));
-    t += 2 * align_up((size_t)Ly * sizeof(cf)) + 2 * align_up((size_t)Lx * sizeof(cf));
-    t += align_up((size_t)ncomp * N * My * sizeof(cf));
-    t += align_up((size_t)3 * N * N * sizeof(cf));
-    return t;
-}
-extern "C" size_t xl_czt_workspace_bytes(int N, int Mx, int My, int vectorial) { return czt_ws_bytes(N, Mx, My, vectorial ? 3 : 1); }
-extern "C" size_t xl_highna_workspace_bytes(int N, int Mx, int My) { return czt_ws_bytes(N, Mx, My, 3); }
-
-static int czt_plan(CztPlan& pl, int N, int Mx, int My, int ncomp, void* ws, size_t ws_bytes) {
-    if (N < 2 || Mx < 2 || My < 2) return xl_fail(XL_E_BAD_ARG, "czt: sizes must be >= 2%s", "");
-    pl.N = N; pl.Mx = Mx; pl.My = My; pl.ncomp = ncomp;
-    pl.Ly = xl_czt_padded_length(N, My);
-    pl.Lx = xl_czt_padded_length(N, Mx);
-    if (!pl.Ly || !pl.Lx) return xl_fail(XL_E_UNSUPPORTED, "czt: m+M-1 is a power of two or padded length outside [32,4096]%s", "");
-    if (!ws || ws_bytes < czt_ws_bytes(N, Mx, My, ncomp)) return xl_fail(XL_E_WORKSPACE, "czt: workspace too small%s", "");
-    Carver c{(char*)ws, 0, ws_bytes};
-    pl.pre_y = (cf*)c.take((size_t)N * sizeof(cf));
-    pl.pre_x = (cf*)c.take((size_t)N * sizeof(cf));
-    pl.post_y = (cf*)c.take((size_t)My * sizeof(cf));
-    pl.post_x = (cf*)c.take((size_t)Mx * sizeof(cf));
-    pl.ft_y = (cf*)c.take((size_t)pl.Ly * sizeof(cf));
-    pl.ftT_y = (cf*)c.take((size_t)pl.Ly * sizeof(cf));
-    pl.ft_x = (cf*)c.take((size_t)pl.Lx * sizeof(cf));
-    pl.ftT_x = (cf*)c.take((size_t)pl.Lx * sizeof(cf));
-    pl.mid = (cf*)c.take((size_t)ncomp * N * My * sizeof(cf));
-    pl.tmp3 = (cf*)c.take((size_t)3 * N * N * sizeof(cf));
-    return XL_OK;
-}
-
-static int czt_setup(const CztPlan& pl, const double* z, double lambda_over_dx, double Dm_static,
-                     double xout0, double xoutl, double yout0, double youtl, const cf* tw, xl_stream_t st) {
-    int rc;
-    XlCztSetup2Params sp;
-    memset(&sp, 0, sizeof(sp));
-    for (int ax = 0; ax < 2; ++ax) {
-        XlCztSetupParams& s = sp.a[ax];
-        s.z = z; s.lambda_over_dx = lambda_over_dx; s.Dm_static = Dm_static; s.tw = tw;
-        s.m = pl.N;
-        if (ax == 0) {   // y axis (first Bluestein pass, wave_optics.py:349)
-            s.L = pl.Ly; s.M = pl.My; s.out0 = yout0; s.outl = youtl;
-            s.pre = pl.pre_y; s.post = pl.post_y; s.ft = pl.ft_y; s.ftT = pl.ftT_y;
-        } else {         // x axis (second pass, :352)
-            s.L = pl.Lx; s.M = pl.Mx; s.out0 = xout0; s.outl = xoutl;
-            s.pre = pl.pre_x; s.post = pl.post_x; s.ft = pl.ft_x; s.ftT = pl.ftT_x;
-        }
-    }
-    if (pl.Ly == pl.Lx) {   // both axes in one launch (two CTAs)
-        XL_FOR_L(pl.Ly, rc = xl_launch<XlCztSetup<XL>>(XlDim{2, 1}, st, sp));
-        return rc;
-    }
-    XL_FOR_L(pl.Ly, rc = xl_launch<XlCztSetup<XL>>(XlDim{1, 1}, st, sp));
-    if (rc) return rc;
-    sp.a[0] = sp.a[1];
-    XL_FOR_L(pl.Lx, rc = xl_launch<XlCztSetup<XL>>(XlDim{1, 1}, st, sp));
-    return rc;
-}
-
 struct CztCall {
     int N, Mx, My, mode;  // mode: 0 scalar CZT, 1 VCZT, 2 high-NA
     const double* z; double lambda, k;
@@ -77,6 +19,129 @@ struct CztCall {
     double R, f, s2;
     int flags;
 };
+static int axis_sym(double x0, double dx, int n) {   // grid symmetric about 0 (toolbox.space): one quadrant of a factor is enough
+    const double span = fabs((n - 1) * dx);
+    return fabs(x0 + 0.5 * (n - 1) * dx) <= 1e-9 * (span > 0 ? span : 1.0) ? 1 : 0;
+}
+static size_t czt_ws_bytes(int N, int Mx, int My, int ncomp) {
+    int Ly = xl_czt_padded_length(N, My), Lx = xl_czt_padded_length(N, Mx);
+    if (!Ly || !Lx) return 0;
+    return align_up((size_t)ncomp * N * My * sizeof(cf)) + align_up((size_t)3 * N * N * sizeof(cf));
+}
+// upper bound that does not depend on the grids' symmetry: full-plane factor tables
+static size_t czt_tab_bytes(int N, int Mx, int My, int mode) {
+    int Ly = xl_czt_padded_length(N, My), Lx = xl_czt_padded_length(N, Mx);
+    if (!Ly || !Lx) return 0;
+    size_t t = 2 * align_up((size_t)N * sizeof(cf)) + align_up((size_t)My * sizeof(cf)) + align_up((size_t)Mx * sizeof(cf));
+    t += 4 * align_up((size_t)Ly * sizeof(cf)) + 4 * align_up((size_t)Lx * sizeof(cf));
+    if (mode == 2) t += align_up((size_t)3 * N * N * sizeof(cf));
+    else t += align_up((size_t)N * N * sizeof(cf)) + align_up((size_t)Mx * My * sizeof(cf));
+    return t;
+}
+extern "C" size_t xl_czt_workspace_bytes(int N, int Mx, int My, int vectorial) { return czt_ws_bytes(N, Mx, My, vectorial ? 3 : 1); }
+extern "C" size_t xl_highna_workspace_bytes(int N, int Mx, int My) { return czt_ws_bytes(N, Mx, My, 3); }
+extern "C" size_t xl_czt_tables_bytes(int N, int Mx, int My) { return czt_tab_bytes(N, Mx, My, 0); }
+extern "C" size_t xl_highna_tables_bytes(int N, int Mx, int My) { return czt_tab_bytes(N, Mx, My, 2); }
+
+static int czt_plan(CztPlan& pl, const CztCall& cc, void* tables, void* ws, size_t ws_bytes) {
+    const int N = cc.N, Mx = cc.Mx, My = cc.My;
+    if (N < 2 || Mx < 2 || My < 2) return xl_fail(XL_E_BAD_ARG, "czt: sizes must be >= 2%s", "");
+    pl.N = N; pl.Mx = Mx; pl.My = My; pl.mode = cc.mode; pl.ncomp = cc.mode == 0 ? 1 : 3;
+    pl.Ly = xl_czt_padded_length(N, My);
+    pl.Lx = xl_czt_padded_length(N, Mx);
+    if (!pl.Ly || !pl.Lx) return xl_fail(XL_E_UNSUPPORTED, "czt: m+M-1 is a power of two or padded length outside [32,4096]%s", "");
+    if (!tables) return xl_fail(XL_E_BAD_ARG, "czt: null table buffer%s", "");
+    if (!ws || ws_bytes < czt_ws_bytes(N, Mx, My, pl.ncomp)) return xl_fail(XL_E_WORKSPACE, "czt: workspace too small%s", "");
+    Carver t{(char*)tables, 0, czt_tab_bytes(N, Mx, My, cc.mode)};
+    pl.pre_y = (cf*)t.take((size_t)N * sizeof(cf));
+    pl.pre_x = (cf*)t.take((size_t)N * sizeof(cf));
+    pl.post_y = (cf*)t.take((size_t)My * sizeof(cf));
+    pl.post_x = (cf*)t.take((size_t)Mx * sizeof(cf));
+    pl.ft_y = (cf*)t.take((size_t)pl.Ly * sizeof(cf));
+    pl.ftT_y = (cf*)t.take((size_t)pl.Ly * sizeof(cf));
+    pl.kin_y = (cf*)t.take((size_t)2 * pl.Ly * sizeof(cf));
+    pl.ft_x = (cf*)t.take((size_t)pl.Lx * sizeof(cf));
+    pl.ftT_x = (cf*)t.take((size_t)pl.Lx * sizeof(cf));
+    pl.kin_x = (cf*)t.take((size_t)2 * pl.Lx * sizeof(cf));
+    // factor tables: [0] on the input grid, [1] on the output grid (CZT / VCZT: the RS factors F, F0; high-NA: the lens matrix)
+    const double dxo = (cc.xoutl - cc.xout0) / (Mx - 1), dyo = (cc.youtl - cc.yout0) / (My - 1);
+    pl.fx[0] = XlFacAxis{N, axis_sym(cc.x0, cc.dx, N), cc.x0, cc.dx};
+    pl.fy[0] = XlFacAxis{N, axis_sym(cc.y0, cc.dy, N), cc.y0, cc.dy};
+    pl.fx[1] = XlFacAxis{Mx, axis_sym(cc.xout0, dxo, Mx), cc.xout0, dxo};
+    pl.fy[1] = XlFacAxis{My, axis_sym(cc.yout0, dyo, My), cc.yout0, dyo};
+    for (int w = 0; w < 2; ++w) {
+        pl.Qx[w] = xl_fac_size(pl.fx[w].n, pl.fx[w].sym);
+        pl.Qy[w] = xl_fac_size(pl.fy[w].n, pl.fy[w].sym);
+    }
+    if (cc.mode == 2) {
+        pl.fac_kind[0] = XL_FAC_LENS; pl.fac_kind[1] = XL_FAC_NONE;
+        pl.T[0] = (cf*)t.take((size_t)3 * pl.Qx[0] * pl.Qy[0] * sizeof(cf));
+        pl.T[1] = 0;
+    } else {
+        pl.fac_kind[0] = XL_FAC_RS;
+        pl.T[0] = (cf*)t.take((size_t)pl.Qx[0] * pl.Qy[0] * sizeof(cf));
+        // identical input and output grids (the reference's default xout = x, yout = y): F0 is F
+        const bool same = Mx == N && My == N && pl.fx[0].sym == pl.fx[1].sym && pl.fy[0].sym == pl.fy[1].sym &&
+                          fabs(cc.xout0 - cc.x0) <= 1e-12 * fabs(cc.x0) && fabs(dxo - cc.dx) <= 1e-12 * fabs(cc.dx) &&
+                          fabs(cc.yout0 - cc.y0) <= 1e-12 * fabs(cc.y0) && fabs(dyo - cc.dy) <= 1e-12 * fabs(cc.dy);
+        if (same) { pl.fac_kind[1] = XL_FAC_NONE; pl.T[1] = pl.T[0]; }
+        else { pl.fac_kind[1] = XL_FAC_RS; pl.T[1] = (cf*)t.take((size_t)pl.Qx[1] * pl.Qy[1] * sizeof(cf)); }
+    }
+    Carver c{(char*)ws, 0, ws_bytes};
+    pl.mid = (cf*)c.take((size_t)pl.ncomp * N * My * sizeof(cf));
+    pl.tmp3 = (cf*)c.take((size_t)3 * N * N * sizeof(cf));
+    return XL_OK;
+}
+static XlFacTab fac_tab(const CztPlan& pl, int w) { return XlFacTab{pl.T[w], pl.Qx[w], pl.Qy[w], pl.fx[w], pl.fy[w]}; }
+
+// Fill the table buffer: czt_tables (one thread per entry) then czt_kernel_fft (one CTA per axis).
+static int czt_setup(const CztPlan& pl, const CztCall& cc, const cf* tw, xl_stream_t st) {
+    int rc;
+    XlCztTablesParams tp;
+    memset(&tp, 0, sizeof(tp));
+    const double Dm_static = cc.mode == 2 ? cc.f * cc.lambda * (cc.N - 1) / (2 * cc.R) : 0.0;  // optical_elements.py:663
+    for (int ax = 0; ax < 2; ++ax) {
+        XlCztAxisTab& s = tp.a[ax];
+        s.lambda_over_dx = cc.lambda / cc.dx; s.Dm_static = Dm_static;
+        s.m = pl.N;
+        if (ax == 0) {   // y axis (first Bluestein pass, wave_optics.py:349)
+            s.L = pl.Ly; s.M = pl.My; s.out0 = cc.yout0; s.outl = cc.youtl;
+            s.pre = pl.pre_y; s.post = pl.post_y; s.kin = pl.kin_y; s.ft = pl.ft_y; s.ftT = pl.ftT_y;
+        } else {         // x axis (second pass, :352)
+            s.L = pl.Lx; s.M = pl.Mx; s.out0 = cc.xout0; s.outl = cc.xoutl;
+            s.pre = pl.pre_x; s.post = pl.post_x; s.kin = pl.kin_x; s.ft = pl.ft_x; s.ftT = pl.ftT_x;
+        }
+    }
+    tp.z = cc.mode == 2 ? 0 : cc.z; tp.k = cc.k;
+    tp.lens_R = cc.R; tp.lens_f = cc.f; tp.lens_s2 = cc.s2;
+    long long e = 0;
+    for (int ax = 0; ax < 2; ++ax) {
+        tp.seg[ax * 3] = e;     e += tp.a[ax].m;
+        tp.seg[ax * 3 + 1] = e; e += tp.a[ax].M;
+        tp.seg[ax * 3 + 2] = e; e += 2LL * tp.a[ax].L;
+    }
+    for (int w = 0; w < 2; ++w) {
+        tp.fac_kind[w] = pl.fac_kind[w]; tp.T[w] = pl.T[w]; tp.Qx[w] = pl.Qx[w]; tp.Qy[w] = pl.Qy[w]; tp.fx[w] = pl.fx[w]; tp.fy[w] = pl.fy[w];
+        tp.seg[6 + w] = e;
+        if (pl.fac_kind[w] != XL_FAC_NONE) e += (long long)(pl.fac_kind[w] == XL_FAC_LENS ? 3 : 1) * pl.Qx[w] * pl.Qy[w];
+    }
+    tp.seg[8] = e;
+    // seg[] as used by the kernel: [0..2] y axis starts (pre, post, kin), [3..5] x axis, [6],[7] factor tables, [8] end;
+    // the kernel reads seg[ax*3+1], seg[ax*3+2] as the ENDS of pre and post relative to the axis base
+    rc = xl_launch<XlCztTables>(XlDim{pointwise_grid((size_t)e, XlCztTables::NT), 1}, st, tp);
+    if (rc) return rc;
+    XlCztKernelFftParams kp;
+    kp.a[0] = tp.a[0]; kp.a[1] = tp.a[1]; kp.tw = tw;
+    if (pl.Ly == pl.Lx) {   // both axes in one launch (two CTAs)
+        XL_FOR_L(pl.Ly, rc = xl_launch<XlCztKernelFft<XL>>(XlDim{2, 1}, st, kp));
+        return rc;
+    }
+    XL_FOR_L(pl.Ly, rc = xl_launch<XlCztKernelFft<XL>>(XlDim{1, 1}, st, kp));
+    if (rc) return rc;
+    kp.a[0] = kp.a[1];
+    XL_FOR_L(pl.Lx, rc = xl_launch<XlCztKernelFft<XL>>(XlDim{1, 1}, st, kp));
+    return rc;
+}
 
 static void czt_common_params(XlCztParams& a, const CztCall& cc, const cf* tw) {
     memset(&a, 0, sizeof(a));
@@ -123,18 +188,16 @@ static int czt_axis_launch(const XlCztParams& a, XlDim grid, xl_stream_t st) {
     return xl_fail(XL_E_BAD_ARG, "czt: unsupported prologue/epilogue combination%s", "");
 }
 
-static int czt_forward(const CztCall& cc, const void* in, void* out, void* ws, size_t ws_bytes, xl_stream_t st) {
+static int czt_forward(const CztCall& cc, const void* in, void* out, void* tables, void* ws, size_t ws_bytes, xl_stream_t st) {
     if (!in || !out) return xl_fail(XL_E_BAD_ARG, "czt_fwd: null pointer%s", "");
     if (cc.mode != 2 && !cc.z) return xl_fail(XL_E_BAD_ARG, "czt_fwd: null z%s", "");
-    const int ncomp = cc.mode == 0 ? 1 : 3;
     CztPlan pl;
-    int rc = czt_plan(pl, cc.N, cc.Mx, cc.My, ncomp, ws, ws_bytes);
+    int rc = czt_plan(pl, cc, tables, ws, ws_bytes);
     if (rc) return rc;
+    const int ncomp = pl.ncomp;
     const cf* tw = xl_twiddles();
     if (!tw) return xl_fail(XL_E_CUDA, "twiddle table allocation failed%s", "");
-    const double Dm_static = cc.mode == 2 ? cc.f * cc.lambda * (cc.N - 1) / (2 * cc.R) : 0.0;  // optical_elements.py:663
-    rc = czt_setup(pl, cc.mode == 2 ? 0 : cc.z, cc.lambda / cc.dx, Dm_static, cc.xout0, cc.xoutl, cc.yout0, cc.youtl, tw, st);
-    if (rc) return rc;
+    if (!(cc.flags & XL_REUSE_TABLES)) { rc = czt_setup(pl, cc, tw, st); if (rc) return rc; }
     const int N = cc.N, Mx = cc.Mx, My = cc.My;
     const double dxo = (cc.xoutl - cc.xout0) / (Mx - 1), dyo = (cc.youtl - cc.yout0) / (My - 1);
     // pass 1: Bluestein along y for every input column
@@ -146,6 +209,7 @@ static int czt_forward(const CztCall& cc, const void* in, void* out, void* ws, s
     a.pre = pl.pre_y; a.ft = pl.ft_y; a.post = pl.post_y;
     a.pro = cc.mode == 0 ? XL_PRO_RSF : (cc.mode == 1 ? XL_PRO_VCZT : XL_PRO_HIGHNA);
     a.gpro = XlGridFactor{cc.x0, cc.dx, cc.y0, cc.dy, 0};
+    a.tpro = fac_tab(pl, 0);
     a.epi = XL_EPI_NONE;
     // pass 2: Bluestein along x for every column of the intermediate
     XlCztParams b;
@@ -157,6 +221,7 @@ static int czt_forward(const CztCall& cc, const void* in, void* out, void* ws, s
     b.pro = XL_PRO_NONE;
     b.epi = cc.mode == 2 ? XL_EPI_NONE : XL_EPI_RSF;
     b.gepi = XlGridFactor{cc.xout0, dxo, cc.yout0, dyo, 1};
+    b.tepi = fac_tab(pl, 1);
     czt_out_const(b, cc);
     b.flags = cc.flags & XL_CONJ_OUT;
     rc = czt_axis_launch(a, XlDim{xl_groups(N), ncomp}, st);
@@ -164,18 +229,16 @@ static int czt_forward(const CztCall& cc, const void* in, void* out, void* ws, s
     return czt_axis_launch(b, XlDim{xl_groups(My), ncomp}, st);
 }
 
-static int czt_backward(const CztCall& cc, const void* ct_out, void* ct_in, void* ws, size_t ws_bytes, xl_stream_t st) {
+static int czt_backward(const CztCall& cc, const void* ct_out, void* ct_in, void* tables, void* ws, size_t ws_bytes, xl_stream_t st) {
     if (!ct_out || !ct_in) return xl_fail(XL_E_BAD_ARG, "czt_bwd: null pointer%s", "");
     if (cc.mode != 2 && !cc.z) return xl_fail(XL_E_BAD_ARG, "czt_bwd: null z%s", "");
-    const int ncomp = cc.mode == 0 ? 1 : 3;
     CztPlan pl;
-    int rc = czt_plan(pl, cc.N, cc.Mx, cc.My, ncomp, ws, ws_bytes);
+    int rc = czt_plan(pl, cc, tables, ws, ws_bytes);
     if (rc) return rc;
+    const int ncomp = pl.ncomp;
     const cf* tw = xl_twiddles();
     if (!tw) return xl_fail(XL_E_CUDA, "twiddle table allocation failed%s", "");
-    const double Dm_static = cc.mode == 2 ? cc.f * cc.lambda * (cc.N - 1) / (2 * cc.R) : 0.0;
-    rc = czt_setup(pl, cc.mode == 2 ? 0 : cc.z, cc.lambda / cc.dx, Dm_static, cc.xout0, cc.xoutl, cc.yout0, cc.youtl, tw, st);
-    if (rc) return rc;
+    if (!(cc.flags & XL_REUSE_TABLES)) { rc = czt_setup(pl, cc, tw, st); if (rc) return rc; }
     const int N = cc.N, Mx = cc.Mx, My = cc.My;
     const double dxo = (cc.xoutl - cc.xout0) / (Mx - 1), dyo = (cc.youtl - cc.yout0) / (My - 1);
     // transpose of pass 2: rows of ct_out (length Mx) -> columns of the intermediate cotangent
@@ -187,6 +250,7 @@ static int czt_backward(const CztCall& cc, const void* ct_out, void* ct_in, void
     b.pre = pl.post_x; b.ft = pl.ftT_x; b.post = pl.pre_x;
     b.pro = cc.mode == 2 ? XL_PRO_NONE : XL_PRO_RSF;
     b.gpro = XlGridFactor{cc.xout0, dxo, cc.yout0, dyo, 1};
+    b.tpro = fac_tab(pl, 1);
     b.epi = XL_EPI_NONE;
     czt_out_const(b, cc);
     b.flags = cc.flags & XL_CONJ_IN;
@@ -200,6 +264,7 @@ static int czt_backward(const CztCall& cc, const void* ct_out, void* ct_in, void
     a.pro = XL_PRO_NONE;
     a.epi = cc.mode == 2 ? XL_EPI_NONE : XL_EPI_RSF;
     a.gepi = XlGridFactor{cc.x0, cc.dx, cc.y0, cc.dy, 0};
+    a.tepi = fac_tab(pl, 0);
     a.flags = cc.mode == 0 ? (cc.flags & XL_CONJ_OUT) : 0;
     rc = czt_axis_launch(b, XlDim{xl_groups(My), ncomp}, st);
     if (rc) return rc;
@@ -210,7 +275,7 @@ static int czt_backward(const CztCall& cc, const void* ct_out, void* ct_in, void
     f.N = N; f.mode = cc.mode == 1 ? XL_FOLD_VCZT : XL_FOLD_HIGHNA; f.flags = cc.flags & XL_CONJ_OUT;
     f.t = pl.tmp3; f.gx = (cf*)ct_in; f.gy = (cf*)ct_in + (size_t)N * N;
     f.z = cc.mode == 1 ? cc.z : 0; f.x0 = cc.x0; f.y0 = cc.y0; f.dx = cc.dx; f.dy = cc.dy;
-    f.lens_R = cc.R; f.lens_f = cc.f; f.lens_s2 = cc.s2;
+    if (cc.mode == 2) f.lens = fac_tab(pl, 0);
     const size_t NN = (size_t)N * N;
     return xl_launch<XlFold>(XlDim{(int)((NN + XlFold::NT - 1) / XlFold::NT), 1}, st, f);
 }
@@ -230,25 +295,25 @@ static CztCall make_czt_call(int mode, const double* z, double lambda, int N, in
 
 extern "C" int xl_czt_fwd(const void* in, void* out, const double* z, double lambda, int N, int Mx, int My, int vectorial,
                           double x0, double dx, double y0, double dy, double xout0, double xoutl, double yout0, double youtl,
-                          int flags, void* ws, size_t ws_bytes, void* stream) {
+                          int flags, void* tables, void* ws, size_t ws_bytes, void* stream) {
     CztCall c = make_czt_call(vectorial ? 1 : 0, z, lambda, N, Mx, My, x0, dx, y0, dy, xout0, xoutl, yout0, youtl, 0, 0, flags);
-    return czt_forward(c, in, out, ws, ws_bytes, (xl_stream_t)stream);
+    return czt_forward(c, in, out, tables, ws, ws_bytes, (xl_stream_t)stream);
 }
 extern "C" int xl_czt_bwd(const void* ct_out, void* ct_in, const double* z, double lambda, int N, int Mx, int My, int vectorial,
                           double x0, double dx, double y0, double dy, double xout0, double xoutl, double yout0, double youtl,
-                          int flags, void* ws, size_t ws_bytes, void* stream) {
+                          int flags, void* tables, void* ws, size_t ws_bytes, void* stream) {
     CztCall c = make_czt_call(vectorial ? 1 : 0, z, lambda, N, Mx, My, x0, dx, y0, dy, xout0, xoutl, yout0, youtl, 0, 0, flags);
-    return czt_backward(c, ct_out, ct_in, ws, ws_bytes, (xl_stream_t)stream);
+    return czt_backward(c, ct_out, ct_in, tables, ws, ws_bytes, (xl_stream_t)stream);
 }
 extern "C" int xl_highna_fwd(const void* exy, void* out, int N, int Mx, int My, double radius, double f, double lambda,
                              double x0, double dx, double y0, double dy, double xout0, double xoutl, double yout0, double youtl,
-                             int flags, void* ws, size_t ws_bytes, void* stream) {
+                             int flags, void* tables, void* ws, size_t ws_bytes, void* stream) {
     CztCall c = make_czt_call(2, 0, lambda, N, Mx, My, x0, dx, y0, dy, xout0, xoutl, yout0, youtl, radius, f, flags);
-    return czt_forward(c, exy, out, ws, ws_bytes, (xl_stream_t)stream);
+    return czt_forward(c, exy, out, tables, ws, ws_bytes, (xl_stream_t)stream);
 }
 extern "C" int xl_highna_bwd(const void* ct_out, void* ct_exy, int N, int Mx, int My, double radius, double f, double lambda,
                              double x0, double dx, double y0, double dy, double xout0, double xoutl, double yout0, double youtl,
-                             int flags, void* ws, size_t ws_bytes, void* stream) {
+                             int flags, void* tables, void* ws, size_t ws_bytes, void* stream) {
     CztCall c = make_czt_call(2, 0, lambda, N, Mx, My, x0, dx, y0, dy, xout0, xoutl, yout0, youtl, radius, f, flags);
-    return czt_backward(c, ct_out, ct_exy, ws, ws_bytes, (xl_stream_t)stream);
+    return czt_backward(c, ct_out, ct_exy, tables, ws, ws_bytes, (xl_stream_t)stream);
 }

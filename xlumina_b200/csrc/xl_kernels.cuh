@@ -556,6 +556,22 @@ struct XlGridFactor {     // coordinates of (line, pos): swap=0 -> X from line, 
     int swap;
 };
 
+// Factor tables.  The pointwise factors of the CZT family -- the RS factors F / F0 of CZT_jit (wave_optics.py:340-341), the
+// lens matrix of the high-NA objective (optical_elements.py:528-594) -- depend on the grids and on z only, so they are
+// evaluated ONCE per call by czt_tables (fp64 phases, xl_rs_h / xl_lens_row) and the axis passes gather them from L2.
+// A grid that is symmetric about 0 (toolbox.space(): x_j = (j - (n-1)/2) dx) needs one quadrant only: entry q of an axis
+// stands for |x| = (q + 1/2) dx (n even) or q dx (n odd); 8.4 MB instead of 33.5 MB per factor at 2048^2.
+struct XlFacAxis { int n, sym; double x0, dx; };
+XL_HD inline int xl_fac_size(int n, int sym) { return sym ? (n + 1) / 2 : n; }
+XL_DEV int xl_fac_idx(const XlFacAxis& a, int j) {
+    if (!a.sym) return j;
+    const int m = 2 * j - (a.n - 1);
+    return (m < 0 ? -m : m) >> 1;
+}
+XL_DEV double xl_fac_coord(const XlFacAxis& a, int q) { return a.sym ? (q + ((a.n & 1) ? 0.0 : 0.5)) * a.dx : a.x0 + q * a.dx; }
+XL_DEV float xl_fac_sign(const XlFacAxis& a, int j) { return (a.sym && 2 * j < a.n - 1) ? -1.f : 1.f; }   // sign of x_j on a mirrored axis
+struct XlFacTab { const cf* T; int Qx, Qy; XlFacAxis ax, ay; };   // T[(c * Qy + iy) * Qx + ix]
+
 struct XlCztParams {
     int L, nlines, ncomp, m_in, out_off, m_out, flags;
     int c0;               // first component of this launch: component = c0 + blockIdx.y selects the Ez / lens row math,
@@ -566,6 +582,7 @@ struct XlCztParams {
     const cf* tw;
     int pro, epi;          // host-side selectors of the compiled <PRO, EPI> variant
     XlGridFactor gpro, gepi;
+    XlFacTab tpro, tepi;  // factor tables of the prologue / epilogue (czt_tables)
     const double* z;      // device scalar (RSF / VCZT factors), may be null
     double k;             // wavenumber
     double epi_cr, epi_ci; // complex constant on the output
@@ -605,11 +622,15 @@ template <int L, int PRO, int EPI, int ACC> struct XlCztOp : XlOpBase {
     // halves the unrolled prologue / epilogue code of these kernels.
     static constexpr bool kInLoHalf = ACC != XL_ACC_GENERIC;
     static constexpr bool kOutLoHalf = ACC != XL_ACC_GENERIC;
-    const XlCztParams& p; int lb, cl, comp; double z; XlRsHConst hc; cf cst;   // cl: launch-local plane, comp: component
+    const XlCztParams& p; int lb, cl, comp; float z; cf cst;   // cl: launch-local plane, comp: component
     XL_DEV bool in_lo_rt() const { return p.m_in <= L / 2; }   // zero padding fills the upper half: skip its loads and factors
-    XL_DEV void coords(const XlGridFactor& g, int line, int pos, double* X, double* Y) const {
-        if (g.swap) { *X = g.x0 + pos * g.dx; *Y = g.y0 + line * g.dy; }
-        else { *X = g.x0 + line * g.dx; *Y = g.y0 + pos * g.dy; }
+    // grid indices (jx, jy) of (line, pos): swap=0 -> x from line, y from pos; swap=1 -> x from pos, y from line
+    XL_DEV void gidx(const XlGridFactor& g, int line, int pos, int* jx, int* jy) const {
+        *jx = g.swap ? pos : line;
+        *jy = g.swap ? line : pos;
+    }
+    XL_DEV cf fac(const XlFacTab& t, int jx, int jy, int c = 0) const {
+        return xl_ldg(t.T + ((size_t)c * t.Qy + xl_fac_idx(t.ay, jy)) * t.Qx + xl_fac_idx(t.ax, jx));
     }
     // raw operand(s) of both lines at position i (branch-free: out-of-range samples read a valid address, zeroed later)
     XL_DEV void fetch(const cf* src, int i, bool ok_i, cf* a) const {
@@ -640,20 +661,25 @@ template <int L, int PRO, int EPI, int ACC> struct XlCztOp : XlOpBase {
             if (PRO == XL_PRO_NONE) {
                 x = (p.flags & XL_F_CONJ_IN) ? cf_conj(a[l]) : a[l];
             } else {
-                double X, Y;
-                coords(p.gpro, line, i, &X, &Y);
+                int jx, jy;
+                gidx(p.gpro, line, ok_i ? i : 0, &jx, &jy);
+                if (line >= p.nlines) { jx = 0; jy = 0; }
                 if (PRO == XL_PRO_RSF) {          // F = h(X, Y; z), wave_optics.py:341,344
                     x = (p.flags & XL_F_CONJ_IN) ? cf_conj(a[l]) : a[l];
-                    x = cf_mul(x, xl_rs_h(X, Y, hc, 0));
+                    x = cf_mul(x, fac(p.tpro, jx, jy));
                 } else if (PRO == XL_PRO_VCZT) {
                     // comp 0/1: Ex / Ey;  comp 2: Ez = ((Ex X + Ey Y)/r) * z/r     vectorized_optics.py:341-344
-                    const double ir = xl_rsqrt64(X * X + Y * Y + z * z), ir2 = ir * ir;
-                    const float ax = comp == 0 ? 1.f : (comp == 1 ? 0.f : (float)(X * z * ir2));
-                    const float ay = comp == 0 ? 0.f : (comp == 1 ? 1.f : (float)(Y * z * ir2));
-                    x = cf_mul(cf_lin2(a[l], ax, b[l], ay), xl_rs_h(X, Y, hc, 0));
-                } else {  // XL_PRO_HIGHNA
-                    float ax, ay;
-                    xl_lens_row(X, Y, p.lens_R, p.lens_f, p.lens_s2, comp, &ax, &ay);
+                    // (an amplitude factor: fp32 coordinates are enough; the phase lives in F)
+                    const float X = (float)(p.gpro.x0 + jx * p.gpro.dx), Y = (float)(p.gpro.y0 + jy * p.gpro.dy);
+                    const float ir2 = 1.0f / (X * X + Y * Y + z * z);
+                    const float ax = comp == 0 ? 1.f : (comp == 1 ? 0.f : X * z * ir2);
+                    const float ay = comp == 0 ? 0.f : (comp == 1 ? 1.f : Y * z * ir2);
+                    x = cf_mul(cf_lin2(a[l], ax, b[l], ay), fac(p.tpro, jx, jy));
+                } else {  // XL_PRO_HIGHNA: row `comp` of apod*G*RL(theta,phi), stored for |x|,|y| with the parity of each entry
+                    const cf w = fac(p.tpro, jx, jy, comp);
+                    const float sx = xl_fac_sign(p.tpro.ax, jx), sy = xl_fac_sign(p.tpro.ay, jy), sxy = sx * sy;
+                    const float ax = w.x * (comp == 0 ? 1.f : (comp == 1 ? sxy : sx));
+                    const float ay = w.y * (comp == 0 ? sxy : (comp == 1 ? 1.f : sy));
                     x = cf_lin2(a[l], ax, b[l], ay);
                 }
             }
@@ -669,35 +695,57 @@ template <int L, int PRO, int EPI, int ACC> struct XlCztOp : XlOpBase {
             for (int l = 0; l < XL_V; ++l) v[l * 16 + q] = cf_mul(v[l * 16 + q], w);
         }
     }
-    XL_DEV cf finish(int line, int o, cf val, cf post) const {
-        val = cf_mul(val, post);
+    // output factor of (line, o): post-chirp * F0 * constant.  Gathered for ALL outputs of a thread before its first store:
+    // the compiler may not move a load above a store to another pointer, and a load-use-store chain per output serialises
+    // one L2 round trip per output (ncu round 2: 6 long-scoreboard stall cycles per issue in the epilogue kernels).
+    XL_DEV cf out_factor(int line, int o, cf post) const {
+        cf w = post;
         if (EPI == XL_EPI_RSF) {                  // F0 = h(Xout, Yout; z), wave_optics.py:340,355
-            double X, Y;
-            coords(p.gepi, line, o, &X, &Y);
-            val = cf_mul(val, xl_rs_h(X, Y, hc, 0));
+            int jx, jy;
+            gidx(p.gepi, line < p.nlines ? line : 0, o, &jx, &jy);
+            w = cf_mul(w, fac(p.tepi, jx, jy));
         }
-        val = cf_mul(val, cst);
+        return cf_mul(w, cst);
+    }
+    XL_DEV cf finish(cf val, cf w) const {
+        val = cf_mul(val, w);
         return (p.flags & XL_F_CONJ_OUT) ? cf_conj(val) : val;
     }
     XL_DEV void store_vec(int n, const cf* v) const {
+        constexpr int NJ = kOutLoHalf ? R1 / 2 : R1;
+        constexpr int CH = NJ < 8 ? NJ : 8;          // outputs per gather-then-store chunk (2*CH factors live at once)
 #pragma unroll
-        for (int j = 0; j < (kOutLoHalf ? R1 / 2 : R1); ++j) {
-            const int o = n + S1 * j - p.out_off;
-            if (o < 0 || o >= p.m_out) continue;
-            const cf post = xl_ldg(p.post + o);
-            cf* dst = p.out + (long long)cl * p.out_comp + (long long)o * p.out_pos;
-            if (ACC == XL_ACC_PAIR_OUT) {
-                xl_st4(dst + lb, finish(lb, o, v[j], post), finish(lb + 1, o, v[R1 + j], post));
-            } else {
+        for (int j0 = 0; j0 < NJ; j0 += CH) {
+            cf w[XL_V * CH];
 #pragma unroll
-                for (int l = 0; l < XL_V; ++l)
-                    if (lb + l < p.nlines) dst[(long long)(lb + l) * p.out_line] = finish(lb + l, o, v[l * R1 + j], post);
+            for (int jj = 0; jj < CH; ++jj) {
+                const int o = n + S1 * (j0 + jj) - p.out_off;
+                const bool ok = o >= 0 && o < p.m_out;
+                const cf post = xl_ldg(p.post + (ok ? o : 0));
+#pragma unroll
+                for (int l = 0; l < XL_V; ++l) w[l * CH + jj] = out_factor(lb + l, ok ? o : 0, post);
+            }
+#pragma unroll
+            for (int jj = 0; jj < CH; ++jj) {
+                const int j = j0 + jj, o = n + S1 * j - p.out_off;
+                if (o < 0 || o >= p.m_out) continue;
+                cf* dst = p.out + (long long)cl * p.out_comp + (long long)o * p.out_pos;
+                if (ACC == XL_ACC_PAIR_OUT) {
+                    xl_st4(dst + lb, finish(v[j], w[jj]), finish(v[R1 + j], w[CH + jj]));
+                } else {
+#pragma unroll
+                    for (int l = 0; l < XL_V; ++l)
+                        if (lb + l < p.nlines) dst[(long long)(lb + l) * p.out_line] = finish(v[l * R1 + j], w[l * CH + jj]);
+                }
             }
         }
     }
 };
 template <int L, int PRO, int EPI, int ACC> struct XlCztAxis {
-    static const char* name() { return "czt_axis"; }
+    static const char* name() {   // "czt_axis<prologue,epilogue,access>": the profiling report keeps the variants apart
+        static const char n[] = {'c', 'z', 't', '_', 'a', 'x', 'i', 's', '<', char('0' + PRO), ',', char('0' + EPI), ',', char('0' + ACC), '>', 0};
+        return n;
+    }
     typedef XlCztParams Params;
     static constexpr int NT = xl_threads(L);
     static size_t smem() { return xl_smem_bytes(L, XL_V); }
@@ -707,7 +755,7 @@ template <int L, int PRO, int EPI, int ACC> struct XlCztAxis {
         const double z = p.z ? xl_ldg(p.z) : 0.0;
         double cr = p.epi_cr, ci = p.epi_ci;
         if (p.epi_times_z) { cr *= z; ci *= z; }
-        XlCztOp<L, PRO, EPI, ACC> op{{}, p, XL_BLOCK_X * XL_V, XL_BLOCK_Y, p.c0 + XL_BLOCK_Y, z, xl_rs_hconst(z, p.k), make_float2((float)cr, (float)ci)};
+        XlCztOp<L, PRO, EPI, ACC> op{{}, p, XL_BLOCK_X * XL_V, XL_BLOCK_Y, p.c0 + XL_BLOCK_Y, (float)z, make_float2((float)cr, (float)ci)};
         XlFft<L, XL_V>::conv(s, t, op);
     }
 };
@@ -718,18 +766,19 @@ template <int L, int PRO, int EPI, int ACC> struct XlCztAxis {
 //   post[l] = h_l * exp(-i 2 pi f_l (1/2 - m/2)/Dm)
 //   ft      = FFT_L(1/h[:mp+1]) / L            (slot order)         -- forward pass multiplier
 //   ftT     = FFT_L(transposed kernel) / L     (slot order)         -- adjoint pass multiplier
-struct XlCztSetupParams {
+// Two launches: czt_tables evaluates every table ENTRY (chirps, the two kernel sequences `kin`, the factor tables) with
+// one thread per entry over as many CTAs as it takes; czt_kernel_fft (one CTA per axis) transforms kin -> ft, ftT.
+struct XlCztAxisTab {
     int L, m, M;
     double out0, outl;        // first / last output coordinate of this axis
     double Dm_static;         // used when z == null
-    const double* z; double lambda_over_dx;   // Dm = lambda*z/dx   (wave_optics.py:322)
-    cf* pre; cf* post; cf* ft; cf* ftT;
-    const cf* tw;
+    double lambda_over_dx;    // Dm = lambda*z/dx   (wave_optics.py:322)
+    cf* pre; cf* post; cf* kin; cf* ft; cf* ftT;     // kin: [2][L] = {forward kernel sequence, adjoint kernel sequence}
 };
 struct XlCztAxisConsts { double Dm, D1, D2, uw; int Lh; };
-XL_DEV XlCztAxisConsts xl_czt_consts(const XlCztSetupParams& p) {
+XL_DEV XlCztAxisConsts xl_czt_consts(const XlCztAxisTab& p, const double* z) {
     XlCztAxisConsts a;
-    a.Dm = p.z ? p.lambda_over_dx * xl_ldg(p.z) : p.Dm_static;
+    a.Dm = z ? p.lambda_over_dx * xl_ldg(z) : p.Dm_static;
     const double f1 = p.out0 + a.Dm / 2, f2 = p.outl + a.Dm / 2;          // wave_optics.py:325-329
     a.D1 = f1 + (p.M * a.Dm + f2 - f1) / (2 * p.M);                       // :431
     a.D2 = f2 + (p.M * a.Dm + f2 - f1) / (2 * p.M);                       // :433
@@ -746,21 +795,86 @@ XL_DEV cf xl_chirp(double uw, double j, double sign) {   // exp(sign * 2 pi i * 
     xl_sincospi(2.0 * cyc, &s, &c);
     return make_float2((float)c, (float)(sign * s));
 }
-template <int L> struct XlCztSetupOp : XlOpBase {
-    const XlCztSetupParams& p; XlCztAxisConsts a;
-    XL_DEV cf load1(int c, int i) const {
-        int t;
-        if (c == 0) t = (i + p.m) & (L - 1);   // kernel rotated left by m: the kept slice b[m : m+M] (wave_optics.py:446) lands
-                                               // at positions [0, M) of the inverse transform, i.e. in its prunable lower half
-        else {
-            int sft;
-            if (i <= p.m - 1) sft = i; else if (i >= L - (p.M - 1)) sft = i - L; else return cf_zero();
-            t = p.m - sft;
-        }
-        if (t < 0 || t >= a.Lh) return cf_zero();
-        return xl_chirp(a.uw, (double)(t - (p.m - 1)), -1.0);  // 1/h_j = conj(h_j)
+// entry i of kernel sequence c (0: forward, 1: adjoint) of an axis
+XL_DEV cf xl_czt_kin(const XlCztAxisTab& p, const XlCztAxisConsts& a, int c, int i) {
+    const int L = p.L;
+    int t;
+    if (c == 0) t = (i + p.m) & (L - 1);   // kernel rotated left by m: the kept slice b[m : m+M] (wave_optics.py:446) lands
+                                           // at positions [0, M) of the inverse transform, i.e. in its prunable lower half
+    else {
+        int sft;
+        if (i <= p.m - 1) sft = i; else if (i >= L - (p.M - 1)) sft = i - L; else return cf_zero();
+        t = p.m - sft;
     }
-    XL_DEV void load(int i, cf* v, int stride) const { v[0] = load1(0, i); v[stride] = load1(1, i); }
+    if (t < 0 || t >= a.Lh) return cf_zero();
+    return xl_chirp(a.uw, (double)(t - (p.m - 1)), -1.0);  // 1/h_j = conj(h_j)
+}
+enum { XL_FAC_NONE = 0, XL_FAC_RS = 1, XL_FAC_LENS = 2 };
+struct XlCztTablesParams {
+    XlCztAxisTab a[2];
+    const double* z; double k;
+    int fac_kind[2];           // what the two factor tables hold (XL_FAC_*): [0] input grid, [1] output grid
+    cf* T[2]; int Qx[2], Qy[2]; XlFacAxis fx[2], fy[2];
+    double lens_R, lens_f, lens_s2;
+    long long seg[9];          // cumulative entry counts: pre_y post_y kin_y | pre_x post_x kin_x | T0 T1
+};
+struct XlCztTables {
+    static const char* name() { return "czt_tables"; }
+    typedef XlCztTablesParams Params;
+    static constexpr int NT = 256;
+    static size_t smem() { return 16; }
+    XL_DEV static void run(const Params& p, cf*) {
+        const double z = p.z ? xl_ldg(p.z) : 0.0;
+        XL_THREADS(tid, NT) {
+            const long long e = (long long)XL_BLOCK_X * NT + tid;
+            if (e < p.seg[6]) {                                     // chirp tables of one axis
+                const int ax = e < p.seg[3] ? 0 : 1;
+                const XlCztAxisTab& t = p.a[ax];
+                const XlCztAxisConsts a = xl_czt_consts(t, p.z);
+                const long long base = ax ? p.seg[3] : 0;
+                const long long r = e - base;
+                const long long n_pre = p.seg[ax * 3 + 1] - base, n_post = p.seg[ax * 3 + 2] - base;
+                if (r < n_pre) {                                    // pre[k]
+                    const int k = (int)r;
+                    double cyc = a.D1 / a.Dm;
+                    cyc -= rint(cyc);
+                    double ph = -(double)k * cyc;
+                    ph -= rint(ph);
+                    double sn, cs;
+                    xl_sincospi(2.0 * ph, &sn, &cs);
+                    t.pre[k] = cf_mul(make_float2((float)cs, (float)sn), xl_chirp(a.uw, (double)k, 1.0));
+                } else if (r < n_post) {                            // post[l]
+                    const int l = (int)(r - n_pre);
+                    double fl = (double)l / t.M * (a.D2 - a.D1) + a.D1;              // :451-453
+                    double ph = -fl * (-(double)t.m / 2 + 0.5) / a.Dm;                // :456-457
+                    ph -= rint(ph);
+                    double sn, cs;
+                    xl_sincospi(2.0 * ph, &sn, &cs);
+                    t.post[l] = cf_mul(make_float2((float)cs, (float)sn), xl_chirp(a.uw, (double)l, 1.0));
+                } else {                                            // kin[c][i]
+                    const long long q = r - n_post;
+                    t.kin[q] = xl_czt_kin(t, a, (int)(q / t.L), (int)(q % t.L));
+                }
+            } else if (e < p.seg[8]) {                              // factor tables
+                const int w = e < p.seg[7] ? 0 : 1;
+                const long long r = e - p.seg[6 + w];
+                const int Qx = p.Qx[w], Qy = p.Qy[w];
+                const int ix = (int)(r % Qx), iy = (int)((r / Qx) % Qy), c = (int)(r / ((long long)Qx * Qy));
+                const double X = xl_fac_coord(p.fx[w], ix), Y = xl_fac_coord(p.fy[w], iy);
+                if (p.fac_kind[w] == XL_FAC_RS) {
+                    p.T[w][r] = xl_rs_h(X, Y, xl_rs_hconst(z, p.k), 0);
+                } else {
+                    float ax, ay;
+                    xl_lens_row(X, Y, p.lens_R, p.lens_f, p.lens_s2, c, &ax, &ay);
+                    p.T[w][r] = make_float2(ax, ay);
+                }
+            }
+        }
+    }
+};
+template <int L> struct XlCztKernelFftOp : XlOpBase {
+    const XlCztAxisTab& p;
+    XL_DEV void load(int i, cf* v, int stride) const { v[0] = xl_ldg(p.kin + i); v[stride] = xl_ldg(p.kin + L + i); }
     XL_DEV void spec(int beta, const cf* v) const {
 #pragma unroll
         for (int q = 0; q < 16; ++q) {
@@ -770,39 +884,17 @@ template <int L> struct XlCztSetupOp : XlOpBase {
     }
     XL_DEV void store_vec(int, const cf*) const {}
 };
-struct XlCztSetup2Params { XlCztSetupParams a[2]; };   // one CTA per axis (blockIdx.x), both axes in one launch
-template <int L> struct XlCztSetup {
-    static const char* name() { return "czt_setup"; }
-    typedef XlCztSetup2Params Params;
+struct XlCztKernelFftParams { XlCztAxisTab a[2]; const cf* tw; };   // one CTA per axis (blockIdx.x), both axes in one launch
+template <int L> struct XlCztKernelFft {
+    static const char* name() { return "czt_kernel_fft"; }
+    typedef XlCztKernelFftParams Params;
     static constexpr int NT = xl_threads(L);
     static size_t smem() { return xl_smem_bytes(L, XL_V); }
     XL_DEV static void run(const Params& pp, cf* s) {
-        const XlCztSetupParams& p = pp.a[XL_BLOCK_X];
+        const XlCztAxisTab& p = pp.a[XL_BLOCK_X];
         cf* t = s + xl_tile_elems(L, XL_V);
-        XlCztAxisConsts a = xl_czt_consts(p);
-        XL_THREADS(tid, NT) {
-            for (int k = tid; k < p.m; k += NT) {  // pre[k]
-                double cyc = a.D1 / a.Dm;
-                cyc -= rint(cyc);
-                double ph = -(double)k * cyc;
-                ph -= rint(ph);
-                double sn, cs;
-                xl_sincospi(2.0 * ph, &sn, &cs);
-                cf h = xl_chirp(a.uw, (double)k, 1.0);
-                p.pre[k] = cf_mul(make_float2((float)cs, (float)sn), h);
-            }
-            for (int l = tid; l < p.M; l += NT) {  // post[l]
-                double fl = (double)l / p.M * (a.D2 - a.D1) + a.D1;              // :451-453
-                double ph = -fl * (-(double)p.m / 2 + 0.5) / a.Dm;                // :456-457
-                ph -= rint(ph);
-                double sn, cs;
-                xl_sincospi(2.0 * ph, &sn, &cs);
-                cf h = xl_chirp(a.uw, (double)l, 1.0);
-                p.post[l] = cf_mul(make_float2((float)cs, (float)sn), h);
-            }
-        }
-        XlFft<L, XL_V>::init_tw(t, p.tw);
-        XlCztSetupOp<L> op{{}, p, a};
+        XlFft<L, XL_V>::init_tw(t, pp.tw);
+        XlCztKernelFftOp<L> op{{}, p};
         XlFft<L, XL_V>::forward(s, t, op);
     }
 };
@@ -863,7 +955,7 @@ struct XlFoldParams {
     double* gz;         // += Re sum t_z * dEz/dz  (VRS only)
     const double* z;
     double x0, y0, dx, dy;
-    double lens_R, lens_f, lens_s2;
+    XlFacTab lens;      // high-NA: the lens-matrix table of czt_tables
 };
 struct XlFold {
     static const char* name() { return "fold"; }
@@ -901,10 +993,10 @@ struct XlFold {
                     gx = make_float2(t0.x + ax * t2.x, t0.y + ax * t2.y);
                     gy = make_float2(t1.x + ay * t2.x, t1.y + ay * t2.y);
                 } else {
-                    float a0x, a0y, a1x, a1y, a2x, a2y;
-                    xl_lens_row(X, Y, p.lens_R, p.lens_f, p.lens_s2, 0, &a0x, &a0y);
-                    xl_lens_row(X, Y, p.lens_R, p.lens_f, p.lens_s2, 1, &a1x, &a1y);
-                    xl_lens_row(X, Y, p.lens_R, p.lens_f, p.lens_s2, 2, &a2x, &a2y);
+                    const size_t e = (size_t)xl_fac_idx(p.lens.ay, y) * p.lens.Qx + xl_fac_idx(p.lens.ax, x), pl = (size_t)p.lens.Qx * p.lens.Qy;
+                    const cf w0 = xl_ldg(p.lens.T + e), w1 = xl_ldg(p.lens.T + pl + e), w2 = xl_ldg(p.lens.T + 2 * pl + e);
+                    const float sx = xl_fac_sign(p.lens.ax, x), sy = xl_fac_sign(p.lens.ay, y), sxy = sx * sy;
+                    const float a0x = w0.x, a0y = w0.y * sxy, a1x = w1.x * sxy, a1y = w1.y, a2x = w2.x * sx, a2y = w2.y * sy;
                     gx = make_float2(a0x * t0.x + a1x * t1.x + a2x * t2.x, a0x * t0.y + a1x * t1.y + a2x * t2.y);
                     gy = make_float2(a0y * t0.x + a1y * t1.x + a2y * t2.x, a0y * t0.y + a1y * t1.y + a2y * t2.y);
                 }

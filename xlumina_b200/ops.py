@@ -368,16 +368,18 @@ class _CZT(torch.autograd.Function):
         if need == 0:
             raise _lib.XlpropError("CZT: unsupported sizes (m+M-1 must not be a power of two; padded length <= 4096)")
         ws = _workspace(fin, need)
+        # tables: Bluestein chirps / kernel spectra and the RS factor tables of this (z, grids); the backward pass reuses them
+        tables = torch.empty(L.xl_czt_tables_bytes(N, Mx, My), dtype=torch.uint8, device=fin.device)
         _lib.check(L.xl_czt_fwd(_ptr(fin), _ptr(out), _ptr(z), lam, N, Mx, My, vect, x0, dx, y0, dy, xo0, xol, yo0, yol, 0,
-                                _ptr(ws), ws.numel(), _stream(fin)), "xl_czt_fwd")
-        ctx.save_for_backward(z)
+                                _ptr(tables), _ptr(ws), ws.numel(), _stream(fin)), "xl_czt_fwd")
+        ctx.save_for_backward(z, tables)
         ctx.meta = (lam, vect, gin, gout, N, fin.shape)
         return out
 
     @staticmethod
     @_on_device
     def backward(ctx, g):
-        (z,) = ctx.saved_tensors
+        z, tables = ctx.saved_tensors
         lam, vect, gin, gout, N, shape = ctx.meta
         (x0, dx, y0, dy) = gin
         (xo0, xol, Mx, yo0, yol, My) = gout
@@ -386,8 +388,28 @@ class _CZT(torch.autograd.Function):
         ct = torch.empty(shape, dtype=g.dtype, device=g.device)
         ws = _workspace(g, L.xl_czt_workspace_bytes(N, Mx, My, vect))
         _lib.check(L.xl_czt_bwd(_ptr(g), _ptr(ct), _ptr(z), lam, N, Mx, My, vect, x0, dx, y0, dy, xo0, xol, yo0, yol,
-                                _lib.XL_CONJ_IN | _lib.XL_CONJ_OUT, _ptr(ws), ws.numel(), _stream(g)), "xl_czt_bwd")
+                                _lib.XL_CONJ_IN | _lib.XL_CONJ_OUT | _lib.XL_REUSE_TABLES, _ptr(tables), _ptr(ws), ws.numel(),
+                                _stream(g)), "xl_czt_bwd")
         return ct, None, None, None, None, None
+
+
+# The tables of the high-NA objective (Bluestein tables + lens matrix on the input grid) depend on static arguments only:
+# every focusing of an optical table through the same objective shares one buffer (the sharp-focus table of BASELINE
+# config 3 focuses six beams through one objective).  Keyed per device and stream; a handful of entries.
+_highna_cache = collections.OrderedDict()
+
+
+def _highna_tables(L, device, N, Mx, My, radius, f, lam, gin, gout):
+    key = (device, torch.cuda.current_stream(device).cuda_stream if device.type == "cuda" else 0, N, Mx, My, radius, f, lam, gin, gout)
+    hit = _highna_cache.get(key)
+    if hit is not None:
+        _highna_cache.move_to_end(key)
+        return hit, True
+    tables = torch.empty(L.xl_highna_tables_bytes(N, Mx, My), dtype=torch.uint8, device=device)
+    _highna_cache[key] = tables
+    while len(_highna_cache) > 4:
+        _highna_cache.popitem(last=False)
+    return tables, False
 
 
 class _HighNA(torch.autograd.Function):
@@ -404,8 +426,11 @@ class _HighNA(torch.autograd.Function):
         if need == 0:
             raise _lib.XlpropError("high-NA: unsupported sizes (m+M-1 must not be a power of two; padded length <= 4096)")
         ws = _workspace(exy, need)
-        _lib.check(L.xl_highna_fwd(_ptr(exy), _ptr(out), N, Mx, My, radius, f, lam, x0, dx, y0, dy, xo0, xol, yo0, yol, 0,
-                                   _ptr(ws), ws.numel(), _stream(exy)), "xl_highna_fwd")
+        tables, reuse = _highna_tables(L, exy.device, N, Mx, My, radius, f, lam, gin, gout)
+        _lib.check(L.xl_highna_fwd(_ptr(exy), _ptr(out), N, Mx, My, radius, f, lam, x0, dx, y0, dy, xo0, xol, yo0, yol,
+                                   _lib.XL_REUSE_TABLES if reuse else 0, _ptr(tables), _ptr(ws), ws.numel(), _stream(exy)),
+                   "xl_highna_fwd")
+        ctx.save_for_backward(tables)
         ctx.meta = (radius, f, lam, gin, gout, N)
         return out
 
@@ -413,6 +438,7 @@ class _HighNA(torch.autograd.Function):
     @_on_device
     def backward(ctx, g):
         radius, f, lam, gin, gout, N = ctx.meta
+        (tables,) = ctx.saved_tensors
         (x0, dx, y0, dy) = gin
         (xo0, xol, Mx, yo0, yol, My) = gout
         L = _lib.lib()
@@ -420,7 +446,8 @@ class _HighNA(torch.autograd.Function):
         ct = torch.empty((2, N, N), dtype=g.dtype, device=g.device)
         ws = _workspace(g, L.xl_highna_workspace_bytes(N, Mx, My))
         _lib.check(L.xl_highna_bwd(_ptr(g), _ptr(ct), N, Mx, My, radius, f, lam, x0, dx, y0, dy, xo0, xol, yo0, yol,
-                                   _lib.XL_CONJ_IN | _lib.XL_CONJ_OUT, _ptr(ws), ws.numel(), _stream(g)), "xl_highna_bwd")
+                                   _lib.XL_CONJ_IN | _lib.XL_CONJ_OUT | _lib.XL_REUSE_TABLES, _ptr(tables), _ptr(ws), ws.numel(),
+                                   _stream(g)), "xl_highna_bwd")
         return ct, None, None, None, None, None
 
 
