@@ -50,6 +50,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the config 3/4/5 workloads reported under \"extra\"")
     return ap.parse_args()
 
 
@@ -169,7 +170,55 @@ def run_reference(args, rank, world):
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
+FFT_FLOP = {4096: 5.0 * 4096 * 12, 2048: 5.0 * 2048 * 11}    # 5 n log2 n per length-n complex FFT
+FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12           # 74.4 TFLOP/s: 148 SMs x 128 FMA lanes x 2 x 1.965 GHz
+
+
+def kernel_model(name, op):
+    """(algorithmic bytes, FFT count) of ONE launch of kernel `name` inside operator `op` at N = 2048, L = 4096, in units of
+    u = 8 N^2 bytes and of length-4096 FFTs (DESIGN.md section 4 states both per kernel).  F = planes per launch."""
+    N, L = N_GRID, 2 * N_GRID
+    F = 3 if op in ("vrs", "vczt") else 1
+    if name == "h_rows":
+        return 1.0, L // 2 + 1                       # analytic samples -> row spectra of the rows y >= 0, x-bins <= L/2
+    if name == "h_cols":
+        return 2.0, L // 2 + 1                       # read them, write the y-even column spectra (+ the column copies)
+    if name == "rs_rows_fwd":
+        return (2.0 + 2.0 * F) if op == "vrs" else 3.0 * F, N * F          # read the planes (VRS: Ex, Ey once), write N x L spectra
+    if name == "rs_cols":
+        return 4.0 * F + 2.0, 2 * L * F              # spectra in and out per plane + the transfer function once
+    if name == "rs_rows_inv":
+        return 3.0 * F, N * F
+    if name == "rs_rows_dual":
+        return 6.0 * F, 2 * N * F                    # cotangent + conj(field) in, interleaved spectra out
+    if name == "rs_cols_gz":
+        return 6.0 * F + 4.0, 3 * L * F              # (C, W) spectra in, C*H out; H and the reduced dH/dz once
+    if name == "dot_z":
+        return 2.0 * F, 0
+    if name == "fold":
+        return 7.0 if op == "vrs" else 5.0, 0
+    if name.startswith("czt_axis"):
+        return 2.0 * F, 2 * N * F                    # one Bluestein pass: every line read once, written once; 2 FFTs per line
+    return 0.0, 0                                    # czt_tables, czt_kernel_fft: KBs
+
+
+def ncu_class(name):
+    """Kernel class name as ncu prints it (profiles/ncu_traffic_r*.json keys are "<class>:<operator>")."""
+    fixed = {"h_rows": "XlHRows", "h_cols": "XlHCols", "rs_rows_fwd": "XlRsRowsFwd", "rs_cols": "XlRsColsAsync", "rs_rows_inv": "XlRsRowsInv",
+             "rs_rows_dual": "XlRsRowsDual", "rs_cols_gz": "XlRsColsGzAsync"}
+    if name in fixed:
+        return fixed[name] + "<4096>"
+    if name.startswith("czt_axis<"):
+        return "XlCztAxis<4096, " + ", ".join(name[9:-1].split(",")) + ">"
+    return {"dot_z": "XlDotZ", "fold": "XlFold", "czt_tables": "XlCztTables"}.get(name, name)
+
+
+def family_of(name):
+    return "czt_axis" if name.startswith("czt_axis") else name
+
+
 def run_ours(args, rank, local_rank, world):
+    import ctypes
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -200,36 +249,45 @@ def run_ours(args, rank, local_rank, world):
     h2d_bytes = sum(v.numel() * 8 for v in host_sets[0].values())
     z_base = torch.full((1,), Z_RS, dtype=torch.float64, device=dev)
 
-    def step(i, s):
-        """Public-API forward + gradient of the four propagators on input set `s`; returns device scalars."""
-        # fresh z every step, derived on the device (no pageable host-to-device copy that would make the host wait)
+    # the four propagations of a step, each forward + gradient through the public API (fresh z every call)
+    def op_rs(i, s):
         zr = (z_base + 0.37 * i).requires_grad_(True)
-        zv = (z_base + 0.53 * i).requires_grad_(True)
         u = s["u"].detach().requires_grad_(True)
-        o1 = ops.rs_propagation(u, zr, dx, dx, k)
-        o1.backward(cts["u"])
+        ops.rs_propagation(u, zr, dx, dx, k).backward(cts["u"])
+        return zr.grad, u.grad
+
+    def op_vrs(i, s):
+        zv = (z_base + 0.53 * i).requires_grad_(True)
         exy = s["exy"].detach().requires_grad_(True)
-        o2 = ops.vrs_propagation(exy, None, zv, float(x[0]), float(y[0]), dx, dx, k)
-        o2.backward(cts["v3"])
+        ops.vrs_propagation(exy, None, zv, float(x[0]), float(y[0]), dx, dx, k).backward(cts["v3"])
+        return zv.grad, exy.grad
+
+    def op_czt(i, s):
         c = s["c"].detach().requires_grad_(True)
-        o3 = ops.czt(c, Z_CZT + 0.01 * i, LAMBDA, x, y, x, y)
-        o3.backward(cts["u"])
+        ops.czt(c, Z_CZT + 0.01 * i, LAMBDA, x, y, x, y).backward(cts["u"])
+        return None, c.grad
+
+    def op_vczt(i, s):
         vxy = s["vxy"].detach().requires_grad_(True)
-        o4 = ops.vczt(vxy, None, Z_CZT + 0.02 * i, LAMBDA, x, y, x, y)
-        o4.backward(cts["v3"])
-        return zr.grad, zv.grad, u.grad, exy.grad, c.grad, vxy.grad
+        ops.vczt(vxy, None, Z_CZT + 0.02 * i, LAMBDA, x, y, x, y).backward(cts["v3"])
+        return None, vxy.grad
+
+    OPS = (("rs", op_rs), ("vrs", op_vrs), ("czt", op_czt), ("vczt", op_vczt))
+
+    def step(i, s):
+        r = [fn(i, s) for _, fn in OPS]
+        return r[0][0], r[1][0]
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident timing (value) -----------------------------------------------------------------------
+    # ---- device-resident timing (value): nothing but the steps between the two events ---------------------------------
     for i in range(args.warmup):
         step(i, dev_sets[i % NSETS])
     barrier()
     launches0 = L.xl_launch_count()
-    L.xl_prof_enable(1)
     sampler = ClockSampler(local_rank)
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -241,29 +299,25 @@ def run_ours(args, rank, local_rank, world):
     clocks = sampler.stop()
     ms = e0.elapsed_time(e1)
     launches = L.xl_launch_count() - launches0
-    buf = __import__("ctypes").create_string_buffer(1 << 16)
-    L.xl_prof_report(buf, len(buf))
-    L.xl_prof_enable(0)
-    kern = {}
-    for ln in buf.value.decode().strip().splitlines():
-        nm, cnt, tot = ln.split()
-        kern[nm] = (int(cnt), float(tot))
 
-    # ---- roofline of the dominant kernel: CUDA events around each launch of the scalar-RS column kernels (1 field per
-    # launch, the shape the committed ncu capture has), inputs rotating through sets larger than L2 -------------------
-    L.xl_prof_enable(1)
-    for i in range(max(args.steps, 5)):
-        sset = dev_sets[i % NSETS]
-        zr = (z_base + 0.11 * i).requires_grad_(True)
-        u = sset["u"].detach().requires_grad_(True)
-        ops.rs_propagation(u, zr, dx, dx, k).backward(cts["u"])
-    torch.cuda.synchronize()
-    L.xl_prof_report(buf, len(buf))
-    L.xl_prof_enable(0)
-    kern1 = {}
-    for ln in buf.value.decode().strip().splitlines():
-        nm, cnt, tot = ln.split()
-        kern1[nm] = (int(cnt), float(tot))
+    # ---- per-kernel CUDA-event times, in a SEPARATE pass per operator (events around every launch on the launching stream,
+    # include/xlprop.h xl_prof_*); input sets rotate, so every launch starts from an L2 that does not hold its inputs ------
+    buf = ctypes.create_string_buffer(1 << 16)
+    PROF_ITERS = 8
+    kern = {}                                     # (op, kernel) -> (launches per call, average microseconds per launch)
+    for opname, fn in OPS:
+        for i in range(2):
+            fn(50_000 + i, dev_sets[i % NSETS])
+        torch.cuda.synchronize()
+        L.xl_prof_enable(1)
+        for i in range(PROF_ITERS):
+            fn(60_000 + i, dev_sets[i % NSETS])
+        torch.cuda.synchronize()
+        L.xl_prof_report(buf, len(buf))
+        L.xl_prof_enable(0)
+        for ln in buf.value.decode().strip().splitlines():
+            nm, cnt, tot = ln.split()
+            kern[(opname, nm)] = (int(cnt) / PROF_ITERS, float(tot) * 1e3 / int(cnt))
 
     # ---- end-to-end timing through the public API with HOST buffers (e2e) ------------------------------------------
     copy_stream = torch.cuda.Stream(device=dev)
@@ -290,7 +344,7 @@ def run_ours(args, rank, local_rank, world):
             if i + 1 < n:
                 stage(i + 1)
             torch.cuda.current_stream(dev).wait_event(ready[b])
-            gz1, gz2, *_ = step(base + i, staged[b])
+            gz1, gz2 = step(base + i, staged[b])
             consumed[b].record(torch.cuda.current_stream(dev))
             res.copy_(torch.cat([gz1, gz2]), non_blocking=True)     # device -> host read of the step's result
             out = res
@@ -304,6 +358,11 @@ def run_ours(args, rank, local_rank, world):
     f1.record()
     barrier()
     ms_e2e = f0.elapsed_time(f1)
+    del staged, host_sets, dev_sets
+    torch.cuda.empty_cache()
+
+    # ---- the collective workloads of BASELINE.json (configs 3, 4, 5) at this GPU count, under "extra" -------------------
+    extra = {} if args.no_extra else run_extra(args, rank, local_rank, world, dev)
 
     t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
     if world > 1:
@@ -317,14 +376,29 @@ def run_ours(args, rank, local_rank, world):
         except Exception:
             pass
         peak_gbs = float(peaks.get("hbm_gbs", 6650.0))
-        peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "6650 GB/s fallback (of fallback)"
-        # Dominant kernel family: the column kernels of the RS path (rs_cols: column FFT x transfer function x inverse
-        # column FFT; rs_cols_gz: the same on the cotangent plus the column FFT of conj(U) and the Parseval sum for d/dz).
-        # Algorithmic bytes per launch (u = 8*N^2 bytes = one N x N complex64 plane):
-        #   rs_cols     per field: read 2u + write 2u of the N x L row spectra; per launch the transfer function, y-even: 2u
-        #   rs_cols_gz  per field: read 2u (cotangent spectra) + 2u (conj-field spectra) + write 2u; per launch H and Hz: 4u
+        peak_src = "MEASURED_PEAKS.json hbm_gbs (burst copy, of measured)" if "hbm_gbs" in peaks else "6650 GB/s fallback (of fallback)"
         u_bytes = 8.0 * N_GRID * N_GRID
-        roof = None
+        ms_step = ms / args.steps
+        # kernel families: time per step, algorithmic bytes and FFT flops per step, both roofline fractions
+        fam = {}
+        per_kernel = []
+        for (opname, nm), (per_call, avg_us) in kern.items():
+            ub, nfft = kernel_model(nm, opname)
+            f = fam.setdefault(family_of(nm), {"us": 0.0, "bytes": 0.0, "flop": 0.0, "launches": 0.0})
+            f["us"] += per_call * avg_us
+            f["bytes"] += per_call * ub * u_bytes
+            f["flop"] += per_call * nfft * FFT_FLOP[2 * N_GRID]
+            f["launches"] += per_call
+            per_kernel.append({"op": opname, "kernel": nm, "launches_per_call": per_call, "avg_launch_us": round(avg_us, 2),
+                               "alg_bytes_per_launch": ub * u_bytes, "fft4096_per_launch": nfft,
+                               "frac_hbm": round(ub * u_bytes / (avg_us * 1e-6) / 1e9 / peak_gbs, 4) if avg_us else None,
+                               "frac_fp32": round(nfft * FFT_FLOP[2 * N_GRID] / (avg_us * 1e-6) / 1e12 / FP32_PEAK_TFLOPS, 4) if avg_us else None})
+        tot_us = sum(f["us"] for f in fam.values())
+        families = {}
+        for nm, f in sorted(fam.items(), key=lambda kv: -kv[1]["us"]):
+            families[nm] = {"us_per_step": round(f["us"], 1), "share_of_step": round(f["us"] / tot_us, 4), "launches_per_step": f["launches"],
+                            "frac_hbm": round(f["bytes"] / (f["us"] * 1e-6) / 1e9 / peak_gbs, 4),
+                            "frac_fp32": round(f["flop"] / (f["us"] * 1e-6) / 1e12 / FP32_PEAK_TFLOPS, 4)}
         ncu_traffic = {}
         try:   # the latest committed ncu --set full capture (scripts/make_profiles.py writes one file per round)
             import glob
@@ -332,33 +406,36 @@ def run_ours(args, rank, local_rank, world):
             ncu_traffic = json.load(open(files[-1])) if files else {}
         except Exception:
             pass
-        kname = max((kk for kk in ("rs_cols", "rs_cols_gz") if kk in kern), key=lambda kk: kern[kk][1], default=None)
-        if kname and kname in kern1:
-            cnt, tot = kern1[kname]                      # scalar-RS launches only: 1 field per launch
-            cls = "XlRsCols" if kname == "rs_cols" else "XlRsColsGz"
-            alg = (6.0 if kname == "rs_cols" else 10.0) * u_bytes
-            avg_s = tot / cnt * 1e-3
-            ach = alg / avg_s / 1e9
-            roof = {"kernel": f"{kname} (xl_kernel<{cls}<4096>>, 1 field per launch)", "bound": "hbm",
-                    "achieved": ach, "peak": peak_gbs, "unit": "GB/s", "frac": ach / peak_gbs,
-                    "traffic": ncu_traffic.get(f"{cls}<4096>"),
-                    "peak_source": peak_src, "alg_bytes_per_launch": alg, "avg_launch_us": avg_s * 1e6,
-                    "share_of_step": kern[kname][1] / ms,
-                    "note": "algorithmic bytes: 2u+2u (+2u conj-field spectra for _gz) of row spectra per field + 2u per "
-                            "y-even transfer function (SURVEY 8d); the kernel is co-bound by fp32 FFT arithmetic "
-                            "(fp32 pipe 40-50% busy, profiles/summary_r01.txt); traffic = ncu dram read+write of the same launch shape"}
+        # the dominant kernel = the launch shape with the largest time per step inside the largest family
+        top_family = next(iter(families))
+        cand = [r for r in per_kernel if family_of(r["kernel"]) == top_family]
+        top = max(cand, key=lambda r: r["launches_per_call"] * r["avg_launch_us"])
+        ach = top["alg_bytes_per_launch"] / (top["avg_launch_us"] * 1e-6) / 1e9
+        roof = {"kernel": f"{top['kernel']} in {top['op']} (largest launch shape of the largest family by time, {top_family})",
+                "bound": "hbm", "achieved": ach, "peak": peak_gbs, "unit": "GB/s", "frac": ach / peak_gbs,
+                "frac_fp32": top["frac_fp32"], "fp32_peak_tflops": FP32_PEAK_TFLOPS,
+                "traffic": ncu_traffic.get(ncu_class(top["kernel"]) + ":" + top["op"]),
+                "peak_source": peak_src, "alg_bytes_per_launch": top["alg_bytes_per_launch"], "avg_launch_us": top["avg_launch_us"],
+                "family_share_of_step": families[top_family]["share_of_step"],
+                "whole_step": {"alg_bytes": 154 * u_bytes, "frac_hbm": 154 * u_bytes / (ms_step * 1e-3) / 1e9 / peak_gbs,
+                               "note": "SURVEY 8d operation totals: RS 37u + VRS 87u + CZT 8u + VCZT 22u"},
+                "note": "algorithmic bytes and FFT counts per launch: bench.py kernel_model() = DESIGN.md section 4; fp32 fraction = "
+                        "5 n log2 n flops per FFT against 74.4 TFLOP/s; per-launch times from a separate CUDA-event pass"}
         line = {
             "metric": METRIC, "value": world * PROPS_PER_STEP * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "c64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "l2": "inputs larger than L2 (no flush needed)", "sharding": "independent batches per rank, no collective"},
             "clocks": clocks,
             "e2e": {"value": world * PROPS_PER_STEP * args.steps / (ms_e2e * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 16,
-                    "note": "pinned host inputs -> H2D (double-buffered on a copy stream) -> fwd+grad via the public API -> D2H of the z-gradients"},
+                    "note": "pinned host inputs -> H2D (double-buffered on a copy stream) -> fwd+grad via the public API -> D2H of the "
+                            "step's scalar results (the two z-gradients); propagated fields and field gradients stay on the device, as in an optimizer loop"},
             "gpu_launches": int(launches),
             "roofline": roof,
-            "kernels_ms_total": {kk: round(v[1], 4) for kk, v in kern.items()},
+            "kernel_families": families,
+            "kernels": per_kernel,
+            "extra": extra,
         }
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
@@ -370,6 +447,91 @@ def run_ours(args, rank, local_rank, world):
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_extra(args, rank, local_rank, world, dev):
+    """BASELINE.json configs 3-5 at this GPU count (device-timed, max over ranks; rank 0 reports):
+    cfg3: sharp-focus table value+grad at 1024^2 -> 400^2 (16 VRS + 6 high-NA focusings, 29 parameters); candidates are
+          independent, every rank evaluates its own (replicas, no collective): loss-grads/s summed over ranks;
+    cfg4: 4f optimizer, global batch 64 at 1024^2 sharded over the ranks, shared parameters, ONE flattened gradient all-reduce
+          per step (strong scaling): steps/s;
+    cfg5: one 16384^2 scalar RS forward (fresh z), slab-decomposed over the ranks with NCCL all-to-all transposes: ms."""
+    import importlib
+    import math
+    import torch
+    import torch.distributed as dist
+    from xlumina_b200 import ops, slab
+    import xlumina_b200 as xb
+    sys.path.insert(0, os.path.join(ROOT, "scripts"))
+    out = {}
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warm):
+        for _ in range(warm):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1) / steps], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0])
+
+    try:
+        sf = importlib.import_module("sharp_focus_table")
+        ls, params, fixed = sf.build_problem(1024, 400, dev)
+        ops.set_transfer_cache(8)
+
+        def step3():
+            for p in params:
+                p.grad = None
+            sf.loss_hybrid_sharp_focus(ls, params, fixed).backward()
+        ms3 = timed(step3, 5, 2)
+        ops.set_transfer_cache(0)
+        out["cfg3_sharp_focus_1024"] = {"value": world * 1e3 / ms3, "unit": "loss-grads/s", "ms_per_loss_grad": ms3,
+                                        "propagations_per_s": world * 22 * 1e3 / ms3, "scaling": "weak (independent candidates, no collective)"}
+        del ls, params, fixed
+    except Exception as e:   # noqa: BLE001
+        out["cfg3_sharp_focus_1024"] = {"error": repr(e)[:200]}
+    torch.cuda.empty_cache()
+    try:
+        ff = importlib.import_module("four_f_sharded")
+        step4, params4, mine = ff.setup(64, 1024, dev, rank, world)
+        ms4 = timed(step4, 5, 2)
+        out["cfg4_four_f_batch64_1024"] = {"value": 1e3 / ms4, "unit": "steps/s", "ms_per_step": ms4, "samples_per_rank": mine,
+                                           "propagations_per_s": 3 * 64 * 1e3 / ms4, "scaling": "strong (global batch fixed)",
+                                           "collective": "one flattened all-reduce of the shared-parameter gradients per step" if world > 1 else "none (1 GPU)"}
+        del step4, params4
+    except Exception as e:   # noqa: BLE001
+        out["cfg4_four_f_batch64_1024"] = {"error": repr(e)[:200]}
+    torch.cuda.empty_cache()
+    try:
+        N = 16384
+        x, _ = xb.space(HALF_WINDOW, N)
+        dx5 = float(x[1] - x[0])
+        k5 = 2 * math.pi / LAMBDA
+        rows = N // world
+        g5 = torch.Generator(device="cpu").manual_seed(77 + rank)
+        mine5 = torch.view_as_complex(torch.randn(rows, N, 2, generator=g5)).to(dev)
+        group = slab._LOCAL if world == 1 else None
+        ms5 = timed(lambda: slab.rs_propagation_slab(mine5, Z_RS, dx5, dx5, k5, group=group), 3, 1)
+        ub = 8.0 * N * N
+        out["cfg5_rs_16384"] = {"value": ms5, "unit": "ms per forward (fresh z)", "higher_is_better": False, "n_gpus": world,
+                                "alg_bytes": 14 * ub, "alg_GBps_aggregate": 14 * ub / ms5 / 1e6,
+                                "collective": "3 all-to-all transposes (field spectra out and back, transfer function)" if world > 1 else "none (1 GPU, split-line chain)"}
+        del mine5
+    except Exception as e:   # noqa: BLE001
+        out["cfg5_rs_16384"] = {"error": repr(e)[:200]}
+    torch.cuda.empty_cache()
+    return out
 
 
 def main():

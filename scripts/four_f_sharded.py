@@ -59,6 +59,37 @@ def forward_loss(params, masks, targets, beam, dx, k):
     return four_f.MSE_Intensity(inten, targets).sum()
 
 
+def setup(batch, n, dev, rank, world):
+    """Build the sharded optimizer problem on `dev`; returns (step, params, samples_on_this_rank).  step() runs one optimizer
+    step (forward, backward, one flattened gradient all-reduce when world > 1, AdamW) and returns this rank's loss share."""
+    N, lam = n, 0.6328
+    x, _ = xb.space(1500.0, N)
+    dx, k = float(x[1] - x[0]), 2 * math.pi / lam
+    rng = np.random.default_rng(0)                                    # same data on every rank; each takes its slice
+    masks_all, targets_all = synthetic_circles(batch, x, rng)
+    a, b = shard_range(batch, rank, world)
+    masks = torch.as_tensor(masks_all[a:b], device=dev).to(torch.complex64)
+    targets = torch.as_tensor(targets_all[a:b], device=dev)
+    X, Y = np.meshgrid(x, x)
+    beam = torch.as_tensor(np.exp(-(X ** 2 + Y ** 2) / 1200.0 ** 2).astype(np.complex64), device=dev)   # gaussian_beam, z_w0 = 0
+    prng = np.random.default_rng(1)                                   # four_f_optimizer.py:104-109
+    params = [torch.tensor([prng.uniform(0.027, 1)], dtype=torch.float64, device=dev, requires_grad=True) for _ in range(3)]
+    params += [torch.tensor(prng.uniform(0, 1, (N, N)).astype(np.float32), device=dev, requires_grad=True) for _ in range(2)]
+    opt = torch.optim.AdamW(params, lr=0.01, weight_decay=1e-4, capturable=True)   # optax.adamw(0.01, weight_decay=1e-4), :97-98,112
+    for p in params:
+        p.grad = torch.zeros_like(p)
+
+    def step():
+        opt.zero_grad(set_to_none=False)
+        loss = forward_loss(params, masks, targets, beam, dx, k) / batch    # mean over the GLOBAL batch
+        loss.backward()
+        allreduce_grads([p.grad for p in params])
+        opt.step()
+        return loss.detach()
+
+    return step, params, b - a
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=64)
@@ -75,37 +106,14 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-
-    N, lam = args.n, 0.6328
-    x, _ = xb.space(1500.0, N)
-    dx, k = float(x[1] - x[0]), 2 * math.pi / lam
-    rng = np.random.default_rng(0)                                    # same data on every rank; each takes its slice
-    masks_all, targets_all = synthetic_circles(args.batch, x, rng)
-    a, b = shard_range(args.batch, rank, world)
-    masks = torch.as_tensor(masks_all[a:b], device=dev).to(torch.complex64)
-    targets = torch.as_tensor(targets_all[a:b], device=dev)
-    X, Y = np.meshgrid(x, x)
-    beam = torch.as_tensor(np.exp(-(X ** 2 + Y ** 2) / 1200.0 ** 2).astype(np.complex64), device=dev)   # gaussian_beam, z_w0 = 0
-    prng = np.random.default_rng(1)                                   # four_f_optimizer.py:104-109
-    params = [torch.tensor([prng.uniform(0.027, 1)], dtype=torch.float64, device=dev, requires_grad=True) for _ in range(3)]
-    params += [torch.tensor(prng.uniform(0, 1, (N, N)).astype(np.float32), device=dev, requires_grad=True) for _ in range(2)]
-    opt = torch.optim.AdamW(params, lr=0.01, weight_decay=1e-4, capturable=True)   # optax.adamw(0.01, weight_decay=1e-4), :97-98,112
-
-    def step():
-        opt.zero_grad(set_to_none=False)
-        loss = forward_loss(params, masks, targets, beam, dx, k) / args.batch    # mean over the GLOBAL batch
-        loss.backward()
-        allreduce_grads([p.grad for p in params])
-        opt.step()
-        return loss.detach()
+    N = args.n
+    step, params, mine = setup(args.batch, N, dev, rank, world)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for p in params:
-        p.grad = torch.zeros_like(p)
     if args.graph and world == 1:
         # The whole optimizer step (3 RS forward, 3 backward with d/dz and AdamW) as ONE CUDA graph: measured 3.59 -> 3.22 ms
         # per step at 8 samples per GPU.  Single GPU only: capturing the NCCL all-reduce hung in round 1 (not investigated).
@@ -142,7 +150,7 @@ def main():
         ms = float(t[0]) / args.steps
         print(json.dumps({"metric": "4f optimizer steps/s (batch %d, %d^2, 3 RS fwd+grad per sample, shared parameters)" % (args.batch, N),
                           "value": 1e3 / ms, "unit": "steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                          "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "samples_per_rank": b - a,
+                          "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "samples_per_rank": mine,
                           "propagations_per_s": 3 * args.batch * 1e3 / ms, "loss": float(lsum),
                           "collective": "one all-reduce of 2*N^2 fp32 + 3 fp64 gradients per step"}), flush=True)
     if world > 1:

@@ -15,10 +15,17 @@ out.append(f"  value {bench['value']:.1f} {bench['unit']} (device-resident), e2e
 r = bench["roofline"]
 out.append(f"  roofline: {r['kernel']}: {r['achieved']:.0f} GB/s algorithmic = {r['frac']:.3f} of measured {r['peak']} GB/s; share of step {r['share_of_step']:.3f}\n")
 steps = bench["steps"]
-out.append("## CUDA-event time per kernel family inside bench.py (ms per step, share)")
-tot = sum(bench["kernels_ms_total"].values())
-for k, v in sorted(bench["kernels_ms_total"].items(), key=lambda kv: -kv[1]):
-    out.append(f"  {k:14s} {v / steps:8.4f} ms  {100 * v / tot:5.1f} %")
+out.append(f"  roofline fp32 fraction {r.get('frac_fp32')}; whole step {r.get('whole_step')}")
+out.append("## kernel families inside a bench step (separate CUDA-event pass; us per step, share, HBM and fp32 roofline fractions)")
+for k, v in bench.get("kernel_families", {}).items():
+    out.append(f"  {k:14s} {v['us_per_step']:8.1f} us  {100 * v['share_of_step']:5.1f} %  launches {v['launches_per_step']:5.1f}  frac_hbm {v['frac_hbm']:.3f}  frac_fp32 {v['frac_fp32']:.3f}")
+out.append("## per (operator, kernel) launch shape")
+for v in bench.get("kernels", []):
+    out.append(f"  {v['op']:5s} {v['kernel']:16s} x{v['launches_per_call']:4.1f}  {v['avg_launch_us']:8.1f} us/launch  frac_hbm {v['frac_hbm']}  frac_fp32 {v['frac_fp32']}")
+if bench.get("extra"):
+    out.append("## extra (BASELINE configs 3-5 in the same run)")
+    for k, v in bench["extra"].items():
+        out.append(f"  {k}: {json.dumps(v)}")
 out.append("")
 
 # ncu launch list (cold-cache, serialised): shares
@@ -51,12 +58,13 @@ want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio", "smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio", "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio"]
 traffic = {}
-for name in ("rsgrad", "k4", "cztgrad"):
+OPS = {"rsgrad": "rs", "vrsgrad": "vrs", "cztgrad": "czt", "vcztgrad": "vczt", "highna": "highna"}
+for name in ("rsgrad", "vrsgrad", "cztgrad", "vcztgrad", "highna"):
     fn = os.path.join(G, f"ncu_{tag}_{name}_raw.csv")
     if not os.path.exists(fn): continue
     rows = list(csv.reader(open(fn)))
     hdr, units = rows[0], rows[1]
-    mode = {"rsgrad": "grad", "k4": "grad (the d/dz column kernel and the inverse row kernel that follows it)"}.get(name, name)
+    mode = {"rsgrad": "grad"}.get(name, name)
     out.append(f"## ncu --set full --clock-control none, scripts/prof_rs.py 2048 {mode} (2nd iteration; one row per launch)")
     short = [w.replace("smsp__average_warps_issue_stalled_", "stall_").replace("_per_issue_active.ratio", "").replace(".avg.pct_of_peak_sustained_active", "%").replace(".avg.pct_of_peak_sustained_elapsed", "%el") for w in want]
     for r_ in rows[2:]:
@@ -73,7 +81,8 @@ for name in ("rsgrad", "k4", "cztgrad"):
             scale = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}
             tb = float(rd[0]) * scale[rd[1]] + float(wr[0]) * scale[wr[1]]
             out.append(f"  {'traffic = dram read + write':52s} {tb / 1e6:.1f} MB")
-            traffic.setdefault(kn, tb)
+            traffic.setdefault(kn + ":" + OPS[name], tb)
+            if OPS[name] in ("rs", "czt"): traffic.setdefault(kn, tb)
         except Exception as e:
             pass
     out.append("")

@@ -18,16 +18,17 @@ timeout 90 python scripts/four_f_sharded.py > $OUT/four_f_$TAG.json 2> $OUT/four
 # launch list of the bench command itself (cold cache + serialised: shares only)
 timeout 90 ncu --metrics gpu__time_duration.sum --clock-control none -k xl_kernel -c 500 --csv \
     --log-file $OUT/launches_$TAG.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > $OUT/bench_under_ncu.log 2>&1
-# full metrics: RS forward+gradient (12 launches per iteration; second iteration) and CZT forward+gradient (6 per iteration)
-timeout 240 ncu --set full --clock-control none -k xl_kernel -s 12 -c 12 -o /tmp/prof_rsgrad_$TAG \
-    python scripts/prof_rs.py 2048 grad 2 > $OUT/ncu_rsgrad.log 2>&1
-ncu -i /tmp/prof_rsgrad_$TAG.ncu-rep --page raw --csv > $OUT/ncu_${TAG}_rsgrad_raw.csv 2>/dev/null
-timeout 180 ncu --set full --clock-control none -k xl_kernel -s 6 -c 6 -o /tmp/prof_cztgrad_$TAG \
-    python scripts/prof_rs.py 2048 cztgrad 2 > $OUT/ncu_cztgrad.log 2>&1
-ncu -i /tmp/prof_cztgrad_$TAG.ncu-rep --page raw --csv > $OUT/ncu_${TAG}_cztgrad_raw.csv 2>/dev/null
+# full metrics of one forward+gradient per operator (second iteration of scripts/prof_rs.py): launches per iteration
+# RS 11, VRS 12, CZT 6, VCZT 7, high-NA 5 (7 in the first call, which fills the cached tables)
+for spec in rsgrad:grad:11:11 vrsgrad:vrsgrad:12:12 cztgrad:cztgrad:6:6 vcztgrad:vcztgrad:7:7 highna:highna:7:5; do
+    IFS=: read name mode skip n <<< "$spec"
+    timeout 300 ncu --set full --clock-control none -k regex:xl_kernel -s $skip -c $n -o /tmp/prof_${name}_$TAG \
+        python scripts/prof_rs.py 2048 $mode 2 > $OUT/ncu_${name}.log 2>&1
+    ncu -i /tmp/prof_${name}_$TAG.ncu-rep --page raw --csv > $OUT/ncu_${TAG}_${name}_raw.csv 2>/dev/null
+done
 # shared-memory race and out-of-bounds checks of every kernel family at a small size (the host emulation runs the phases of
 # a CTA one after the other, so only the device can show a missing barrier)
-for m in grad vrsgrad cztgrad vczt; do
+for m in grad vrsgrad cztgrad vcztgrad highna; do
     timeout 120 compute-sanitizer --tool racecheck --print-limit 5 python scripts/prof_rs.py 128 $m 1 > $OUT/racecheck_${m}_$TAG.log 2>&1
     tail -2 $OUT/racecheck_${m}_$TAG.log
 done

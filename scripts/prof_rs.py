@@ -1,5 +1,5 @@
 """Profile target: a few calls of one operator at N (default 2048) -- run under ncu.
-modes: fwd (RS forward), grad (RS forward + backward with d/dz), czt, cztgrad, vrsgrad, vczt"""
+modes: fwd (RS forward), grad (RS forward + backward with d/dz), czt, cztgrad, vrsgrad, vczt, vcztgrad, highna"""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -29,4 +29,11 @@ for it in range(iters):
         o = ops.czt(uu, 5000.0, lam, x, y, x, y); o.backward(o)
     elif mode == "vczt":
         ops.vczt(exy, None, 5000.0, lam, x, y, x, y)
+    elif mode == "vcztgrad":
+        e = exy.detach().requires_grad_(True)
+        o = ops.vczt(e, None, 5000.0, lam, x, y, x, y); o.backward(o)
+    elif mode == "highna":
+        xo, yo = xb.space(10.0, 400); x2, y2 = xb.space(2500.0, N)
+        e = exy.detach().requires_grad_(True)
+        o = ops.highna_focus(e, None, 1800.0, 2000.0, 0.635, x2, y2, xo, yo); o.backward(o)
 torch.cuda.synchronize()
