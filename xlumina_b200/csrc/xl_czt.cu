@@ -8,7 +8,9 @@
 struct CztPlan {
     int N, Mx, My, Ly, Lx, ncomp, mode;
     cf *pre_y, *post_y, *ft_y, *ftT_y, *kin_y, *pre_x, *post_x, *ft_x, *ftT_x, *kin_x;
-    cf* T[2]; int Qx[2], Qy[2]; XlFacAxis fx[2], fy[2]; int fac_kind[2];
+    cf* T[3]; int Qx[3], Qy[3], tr[3]; XlFacAxis fx[3], fy[3]; int fac_kind[3];   // [0] input grid, transposed planes (the axis
+                                                                                  // passes whose lines run along y); [1] output
+                                                                                  // grid; [2] input grid row-major (high-NA fold)
     cf* mid;   // [ncomp][N][My]
     cf* tmp3;  // [3][N][N]
 };
@@ -34,7 +36,7 @@ static size_t czt_tab_bytes(int N, int Mx, int My, int mode) {
     if (!Ly || !Lx) return 0;
     size_t t = 2 * align_up((size_t)N * sizeof(cf)) + align_up((size_t)My * sizeof(cf)) + align_up((size_t)Mx * sizeof(cf));
     t += 4 * align_up((size_t)Ly * sizeof(cf)) + 4 * align_up((size_t)Lx * sizeof(cf));
-    if (mode == 2) t += align_up((size_t)3 * N * N * sizeof(cf));
+    if (mode == 2) t += 2 * align_up((size_t)3 * N * N * sizeof(cf));
     else t += align_up((size_t)N * N * sizeof(cf)) + align_up((size_t)Mx * My * sizeof(cf));
     return t;
 }
@@ -69,22 +71,27 @@ static int czt_plan(CztPlan& pl, const CztCall& cc, void* tables, void* ws, size
     pl.fy[0] = XlFacAxis{N, axis_sym(cc.y0, cc.dy, N), cc.y0, cc.dy};
     pl.fx[1] = XlFacAxis{Mx, axis_sym(cc.xout0, dxo, Mx), cc.xout0, dxo};
     pl.fy[1] = XlFacAxis{My, axis_sym(cc.yout0, dyo, My), cc.yout0, dyo};
-    for (int w = 0; w < 2; ++w) {
+    pl.fx[2] = pl.fx[0]; pl.fy[2] = pl.fy[0];
+    for (int w = 0; w < 3; ++w) {
         pl.Qx[w] = xl_fac_size(pl.fx[w].n, pl.fx[w].sym);
         pl.Qy[w] = xl_fac_size(pl.fy[w].n, pl.fy[w].sym);
+        pl.tr[w] = w == 0 ? 1 : 0;
+        pl.fac_kind[w] = XL_FAC_NONE; pl.T[w] = 0;
     }
     if (cc.mode == 2) {
-        pl.fac_kind[0] = XL_FAC_LENS; pl.fac_kind[1] = XL_FAC_NONE;
+        pl.fac_kind[0] = XL_FAC_LENS; pl.fac_kind[2] = XL_FAC_LENS;
         pl.T[0] = (cf*)t.take((size_t)3 * pl.Qx[0] * pl.Qy[0] * sizeof(cf));
-        pl.T[1] = 0;
+        pl.T[2] = (cf*)t.take((size_t)3 * pl.Qx[2] * pl.Qy[2] * sizeof(cf));
     } else {
         pl.fac_kind[0] = XL_FAC_RS;
         pl.T[0] = (cf*)t.take((size_t)pl.Qx[0] * pl.Qy[0] * sizeof(cf));
-        // identical input and output grids (the reference's default xout = x, yout = y): F0 is F
+        // Identical input and output grids (the reference's default xout = x, yout = y) whose x and y axes are the same too:
+        // F0 is F, and the transposed table IS the row-major one (h depends on X^2 + Y^2 only).
         const bool same = Mx == N && My == N && pl.fx[0].sym == pl.fx[1].sym && pl.fy[0].sym == pl.fy[1].sym &&
                           fabs(cc.xout0 - cc.x0) <= 1e-12 * fabs(cc.x0) && fabs(dxo - cc.dx) <= 1e-12 * fabs(cc.dx) &&
-                          fabs(cc.yout0 - cc.y0) <= 1e-12 * fabs(cc.y0) && fabs(dyo - cc.dy) <= 1e-12 * fabs(cc.dy);
-        if (same) { pl.fac_kind[1] = XL_FAC_NONE; pl.T[1] = pl.T[0]; }
+                          fabs(cc.yout0 - cc.y0) <= 1e-12 * fabs(cc.y0) && fabs(dyo - cc.dy) <= 1e-12 * fabs(cc.dy) &&
+                          pl.fx[0].sym == pl.fy[0].sym && fabs(cc.x0 - cc.y0) <= 1e-12 * fabs(cc.x0) && fabs(cc.dx - cc.dy) <= 1e-12 * fabs(cc.dx);
+        if (same) { pl.T[1] = pl.T[0]; }
         else { pl.fac_kind[1] = XL_FAC_RS; pl.T[1] = (cf*)t.take((size_t)pl.Qx[1] * pl.Qy[1] * sizeof(cf)); }
     }
     Carver c{(char*)ws, 0, ws_bytes};
@@ -92,7 +99,7 @@ static int czt_plan(CztPlan& pl, const CztCall& cc, void* tables, void* ws, size
     pl.tmp3 = (cf*)c.take((size_t)3 * N * N * sizeof(cf));
     return XL_OK;
 }
-static XlFacTab fac_tab(const CztPlan& pl, int w) { return XlFacTab{pl.T[w], pl.Qx[w], pl.Qy[w], pl.fx[w], pl.fy[w]}; }
+static XlFacTab fac_tab(const CztPlan& pl, int w) { return XlFacTab{pl.T[w], pl.Qx[w], pl.Qy[w], pl.fx[w], pl.fy[w], pl.tr[w]}; }
 
 // Fill the table buffer: czt_tables (one thread per entry) then czt_kernel_fft (one CTA per axis).
 static int czt_setup(const CztPlan& pl, const CztCall& cc, const cf* tw, xl_stream_t st) {
@@ -120,13 +127,14 @@ static int czt_setup(const CztPlan& pl, const CztCall& cc, const cf* tw, xl_stre
         tp.seg[ax * 3 + 1] = e; e += tp.a[ax].M;
         tp.seg[ax * 3 + 2] = e; e += 2LL * tp.a[ax].L;
     }
-    for (int w = 0; w < 2; ++w) {
-        tp.fac_kind[w] = pl.fac_kind[w]; tp.T[w] = pl.T[w]; tp.Qx[w] = pl.Qx[w]; tp.Qy[w] = pl.Qy[w]; tp.fx[w] = pl.fx[w]; tp.fy[w] = pl.fy[w];
+    for (int w = 0; w < 3; ++w) {
+        tp.fac_kind[w] = pl.fac_kind[w]; tp.T[w] = pl.T[w]; tp.Qx[w] = pl.Qx[w]; tp.Qy[w] = pl.Qy[w]; tp.tr[w] = pl.tr[w];
+        tp.fx[w] = pl.fx[w]; tp.fy[w] = pl.fy[w];
         tp.seg[6 + w] = e;
         if (pl.fac_kind[w] != XL_FAC_NONE) e += (long long)(pl.fac_kind[w] == XL_FAC_LENS ? 3 : 1) * pl.Qx[w] * pl.Qy[w];
     }
-    tp.seg[8] = e;
-    // seg[] as used by the kernel: [0..2] y axis starts (pre, post, kin), [3..5] x axis, [6],[7] factor tables, [8] end;
+    tp.seg[9] = e;
+    // seg[] as used by the kernel: [0..2] y axis starts (pre, post, kin), [3..5] x axis, [6],[7],[8] factor tables, [9] end;
     // the kernel reads seg[ax*3+1], seg[ax*3+2] as the ENDS of pre and post relative to the axis base
     rc = xl_launch<XlCztTables>(XlDim{pointwise_grid((size_t)e, XlCztTables::NT), 1}, st, tp);
     if (rc) return rc;
@@ -275,7 +283,7 @@ static int czt_backward(const CztCall& cc, const void* ct_out, void* ct_in, void
     f.N = N; f.mode = cc.mode == 1 ? XL_FOLD_VCZT : XL_FOLD_HIGHNA; f.flags = cc.flags & XL_CONJ_OUT;
     f.t = pl.tmp3; f.gx = (cf*)ct_in; f.gy = (cf*)ct_in + (size_t)N * N;
     f.z = cc.mode == 1 ? cc.z : 0; f.x0 = cc.x0; f.y0 = cc.y0; f.dx = cc.dx; f.dy = cc.dy;
-    if (cc.mode == 2) f.lens = fac_tab(pl, 0);
+    if (cc.mode == 2) f.lens = fac_tab(pl, 2);
     const size_t NN = (size_t)N * N;
     return xl_launch<XlFold>(XlDim{(int)((NN + XlFold::NT - 1) / XlFold::NT), 1}, st, f);
 }

@@ -570,7 +570,13 @@ XL_DEV int xl_fac_idx(const XlFacAxis& a, int j) {
 }
 XL_DEV double xl_fac_coord(const XlFacAxis& a, int q) { return a.sym ? (q + ((a.n & 1) ? 0.0 : 0.5)) * a.dx : a.x0 + q * a.dx; }
 XL_DEV float xl_fac_sign(const XlFacAxis& a, int j) { return (a.sym && 2 * j < a.n - 1) ? -1.f : 1.f; }   // sign of x_j on a mirrored axis
-struct XlFacTab { const cf* T; int Qx, Qy; XlFacAxis ax, ay; };   // T[(c * Qy + iy) * Qx + ix]
+// T[(c * Qy + iy) * Qx + ix], or with tr = 1 the transposed planes T[(c * Qx + ix) * Qy + iy]: an axis pass whose lines run
+// along y (line = x index, position = y index) reads consecutive entries of a transposed table with consecutive lanes
+// (ncu round 2: the strided gathers of the natural layout cost 6 long-scoreboard stall cycles per issue in those passes)
+struct XlFacTab { const cf* T; int Qx, Qy; XlFacAxis ax, ay; int tr; };
+XL_DEV size_t xl_fac_entry(const XlFacTab& t, int ix, int iy, int c) {
+    return t.tr ? ((size_t)c * t.Qx + ix) * t.Qy + iy : ((size_t)c * t.Qy + iy) * t.Qx + ix;
+}
 
 struct XlCztParams {
     int L, nlines, ncomp, m_in, out_off, m_out, flags;
@@ -630,7 +636,7 @@ template <int L, int PRO, int EPI, int ACC> struct XlCztOp : XlOpBase {
         *jy = g.swap ? line : pos;
     }
     XL_DEV cf fac(const XlFacTab& t, int jx, int jy, int c = 0) const {
-        return xl_ldg(t.T + ((size_t)c * t.Qy + xl_fac_idx(t.ay, jy)) * t.Qx + xl_fac_idx(t.ax, jx));
+        return xl_ldg(t.T + xl_fac_entry(t, xl_fac_idx(t.ax, jx), xl_fac_idx(t.ay, jy), c));
     }
     // raw operand(s) of both lines at position i (branch-free: out-of-range samples read a valid address, zeroed later)
     XL_DEV void fetch(const cf* src, int i, bool ok_i, cf* a) const {
@@ -813,10 +819,11 @@ enum { XL_FAC_NONE = 0, XL_FAC_RS = 1, XL_FAC_LENS = 2 };
 struct XlCztTablesParams {
     XlCztAxisTab a[2];
     const double* z; double k;
-    int fac_kind[2];           // what the two factor tables hold (XL_FAC_*): [0] input grid, [1] output grid
-    cf* T[2]; int Qx[2], Qy[2]; XlFacAxis fx[2], fy[2];
+    int fac_kind[3];           // what the factor tables hold (XL_FAC_*): [0] input grid, [1] output grid, [2] input grid again
+                               // in the other orientation (high-NA: the pointwise fold reads it row-major)
+    cf* T[3]; int Qx[3], Qy[3], tr[3]; XlFacAxis fx[3], fy[3];
     double lens_R, lens_f, lens_s2;
-    long long seg[9];          // cumulative entry counts: pre_y post_y kin_y | pre_x post_x kin_x | T0 T1
+    long long seg[10];         // cumulative entry counts: pre_y post_y kin_y | pre_x post_x kin_x | T0 T1 T2 | end
 };
 struct XlCztTables {
     static const char* name() { return "czt_tables"; }
@@ -855,11 +862,12 @@ struct XlCztTables {
                     const long long q = r - n_post;
                     t.kin[q] = xl_czt_kin(t, a, (int)(q / t.L), (int)(q % t.L));
                 }
-            } else if (e < p.seg[8]) {                              // factor tables
-                const int w = e < p.seg[7] ? 0 : 1;
+            } else if (e < p.seg[9]) {                              // factor tables
+                const int w = e < p.seg[7] ? 0 : (e < p.seg[8] ? 1 : 2);
                 const long long r = e - p.seg[6 + w];
                 const int Qx = p.Qx[w], Qy = p.Qy[w];
-                const int ix = (int)(r % Qx), iy = (int)((r / Qx) % Qy), c = (int)(r / ((long long)Qx * Qy));
+                const int c = (int)(r / ((long long)Qx * Qy));
+                const int ix = p.tr[w] ? (int)((r / Qy) % Qx) : (int)(r % Qx), iy = p.tr[w] ? (int)(r % Qy) : (int)((r / Qx) % Qy);
                 const double X = xl_fac_coord(p.fx[w], ix), Y = xl_fac_coord(p.fy[w], iy);
                 if (p.fac_kind[w] == XL_FAC_RS) {
                     p.T[w][r] = xl_rs_h(X, Y, xl_rs_hconst(z, p.k), 0);
@@ -993,7 +1001,7 @@ struct XlFold {
                     gx = make_float2(t0.x + ax * t2.x, t0.y + ax * t2.y);
                     gy = make_float2(t1.x + ay * t2.x, t1.y + ay * t2.y);
                 } else {
-                    const size_t e = (size_t)xl_fac_idx(p.lens.ay, y) * p.lens.Qx + xl_fac_idx(p.lens.ax, x), pl = (size_t)p.lens.Qx * p.lens.Qy;
+                    const size_t e = xl_fac_entry(p.lens, xl_fac_idx(p.lens.ax, x), xl_fac_idx(p.lens.ay, y), 0), pl = (size_t)p.lens.Qx * p.lens.Qy;
                     const cf w0 = xl_ldg(p.lens.T + e), w1 = xl_ldg(p.lens.T + pl + e), w2 = xl_ldg(p.lens.T + 2 * pl + e);
                     const float sx = xl_fac_sign(p.lens.ax, x), sy = xl_fac_sign(p.lens.ay, y), sxy = sx * sy;
                     const float a0x = w0.x, a0y = w0.y * sxy, a1x = w1.x * sxy, a1y = w1.y, a2x = w2.x * sx, a2y = w2.y * sy;
