@@ -50,6 +50,10 @@ enum {
     XL_CONJ_IN = 1,   /* conjugate the (co)tangent operand while loading it */
     XL_CONJ_OUT = 2,  /* conjugate results while storing them */
     XL_REUSE_H = 16,  /* forward only: `H` already holds the transfer function for this z (cache hit) */
+    XL_PHASE_BLIND = 64,   /* xl_rs_bwd_fused: the caller guarantees that the loss does not change when the output of THIS
+                              propagation is multiplied by a global phase (every table whose paths through this plane end
+                              in intensity detectors).  Then Im sum ct_out*out is exactly zero and the i k out part of d/dz
+                              is dropped instead of being evaluated as a complex64 cancellation residue. */
     XL_REUSE_TABLES = 32   /* CZT family: `tables` already holds the tables of these sizes, grids and z (e.g. the backward
                               call of a propagation whose forward call filled them) */
 };
@@ -93,6 +97,38 @@ int xl_vrs_fwd(const void* exy, void* out, void* H, const double* z, int N, doub
 int xl_vrs_bwd(const void* exy, const void* out, const void* ct_out, void* ct_exy, double* grad_z, const void* H,
                const double* z, int N, double x0, double y0, double dx, double dy, double k, int flags,
                void* ws, size_t ws_bytes, void* stream);
+
+/* ---------------------------------------------------------------- fused pointwise elements (scalar RS) ----- */
+/* The elements that bracket a scalar propagation in an optical table, folded into its first and last pass (SURVEY.md 8f-1,
+ * 8f-2) so that they cost no extra pass over HBM:
+ *   mod      shared complex64 [N][N] plane multiplied into EVERY field while it is loaded: a phase-only SLM exp(i phi)
+ *            (xlumina/optical_elements.py:87-103), an amplitude mask, or the beam under a batch of object masks
+ *            (experiments/four_f_optical_table.py:58-65); NULL: none
+ *   in_real  the input planes are float32 (binary object masks), not complex64
+ *   target   detection: float32 [nfields][N][N] target intensities; the last pass also accumulates
+ *            mse[f] += sum (|out[f]|^2 - target[f])^2 / N^2   (MSE of intensities, four_f_optical_table.py:129-141);
+ *            the caller zeroes `mse` (nfields float64); NULL: no detection
+ * `out` (complex) is always written: the backward pass needs it. */
+typedef struct xl_rs_fuse {
+    const void* mod;
+    int in_real;
+    const float* target;
+    double* mse;
+} xl_rs_fuse;
+int xl_rs_fwd_fused(const void* in, void* out, void* H, const double* z, int N, int nfields,
+                    double dx, double dy, double k, int flags, const xl_rs_fuse* fuse,
+                    void* ws, size_t ws_bytes, void* stream);
+/* VJP of xl_rs_fwd_fused (conventions of xl_rs_bwd).  Output cotangent: `ct_out` (complex planes), or -- when fuse->target
+ * is set -- ct_mse[f] = dL/dmse[f] (device float64): the cotangent 4 ct_mse[f]/N^2 (|out|^2 - target) out is then formed from
+ * the primal `out` while it is loaded, and the i k out part of d/dz is dropped because it vanishes identically.
+ *   ct_in   [nfields][N][N] cotangent of the (unmodulated) inputs = (A^T ct) * mod;  NULL: the inputs are constants
+ *   ct_mod  [N][N] cotangent of `mod` = sum_f (A^T ct)[f] * in[f] (overwritten);     NULL: `mod` is a constant
+ *   grad_z  += d/dz (needs `in` and `out`; see XL_PHASE_BLIND);                       NULL: z is a constant
+ * With ct_in == ct_mod == NULL only the d/dz pipeline runs (no inverse transforms). */
+int xl_rs_bwd_fused(const void* in, const void* out, const void* ct_out, const double* ct_mse, void* ct_in, void* ct_mod,
+                    double* grad_z, const void* H, const double* z, int N, int nfields,
+                    double dx, double dy, double k, int flags, const xl_rs_fuse* fuse,
+                    void* ws, size_t ws_bytes, void* stream);
 
 /* ---------------------------------------------------------------- slab-decomposed RS (multi-GPU) ------------ */
 /* One N x N field split into row slabs over G ranks (N a multiple of 2G, L/2 a multiple of G, L = xl_rs_padded_length(N)):

@@ -50,16 +50,19 @@ class _Beam:
         self.x, self.k, self.field = x, k, field
 
 
-def forward_loss(params, masks, targets, beam, dx, k):
+def forward_loss(params, masks, targets, beam, dx, k, fused=True):
     """loss_dualSLM of the reference (four_f_optical_table.py:103-141) on this rank's slice; returns the SUM of per-sample
-    MSEs (the caller divides by the GLOBAL batch).  The table itself lives in xlumina_b200/four_f.py."""
+    MSEs (the caller divides by the GLOBAL batch).  The table itself lives in xlumina_b200/four_f.py; `fused` folds the
+    beam, both SLMs and the intensity-MSE detector into the propagation kernels (four_f.loss_dualSLM_fused)."""
     x = dx * (np.arange(beam.shape[-1]) - (beam.shape[-1] - 1) / 2)
     p = [params[0], params[1], params[2], params[3], params[4]]
+    if fused:
+        return four_f.loss_dualSLM_fused(p, masks, targets, _Beam(x, k, beam)) * masks.shape[0]
     inten, _, _ = four_f.vector_dualSLM_4f_system(masks, _Beam(x, k, beam), p)
     return four_f.MSE_Intensity(inten, targets).sum()
 
 
-def setup(batch, n, dev, rank, world):
+def setup(batch, n, dev, rank, world, fused=True):
     """Build the sharded optimizer problem on `dev`; returns (step, params, samples_on_this_rank).  step() runs one optimizer
     step (forward, backward, one flattened gradient all-reduce when world > 1, AdamW) and returns this rank's loss share."""
     N, lam = n, 0.6328
@@ -81,7 +84,7 @@ def setup(batch, n, dev, rank, world):
 
     def step():
         opt.zero_grad(set_to_none=False)
-        loss = forward_loss(params, masks, targets, beam, dx, k) / batch    # mean over the GLOBAL batch
+        loss = forward_loss(params, masks, targets, beam, dx, k, fused) / batch    # mean over the GLOBAL batch
         loss.backward()
         allreduce_grads([p.grad for p in params])
         opt.step()
@@ -96,6 +99,7 @@ def main():
     ap.add_argument("--n", type=int, default=1024)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--unfused", action="store_true", help="pointwise elements and the loss as separate torch operations")
     ap.add_argument("--graph", action="store_true", help="single GPU only: capture the whole optimizer step in ONE CUDA graph "
                     "and replay it (the library neither allocates nor synchronises in steady state, so it captures as is)")
     args = ap.parse_args()
@@ -107,7 +111,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     N = args.n
-    step, params, mine = setup(args.batch, N, dev, rank, world)
+    step, params, mine = setup(args.batch, N, dev, rank, world, fused=not args.unfused)
 
     def barrier():
         if world > 1:
@@ -151,7 +155,7 @@ def main():
         print(json.dumps({"metric": "4f optimizer steps/s (batch %d, %d^2, 3 RS fwd+grad per sample, shared parameters)" % (args.batch, N),
                           "value": 1e3 / ms, "unit": "steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                           "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "samples_per_rank": mine,
-                          "propagations_per_s": 3 * args.batch * 1e3 / ms, "loss": float(lsum),
+                          "propagations_per_s": 3 * args.batch * 1e3 / ms, "loss": float(lsum), "fused_elements": not args.unfused,
                           "collective": "one all-reduce of 2*N^2 fp32 + 3 fp64 gradients per step"}), flush=True)
     if world > 1:
         dist.destroy_process_group()

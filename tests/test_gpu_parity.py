@@ -512,3 +512,73 @@ def test_four_f_module_matches_reference_fixture(xb):
     # distance gradients of a phase-blind (intensity) loss are cancellation residues: see the comment in
     # test_four_f_table_loss_and_shared_parameter_gradients and DESIGN.md section 2
     assert errs["dist"] < 3e-3
+
+
+@pytest.mark.gpu
+def test_four_f_fused_elements_on_device(xb):
+    """SURVEY 8f-1 / 8f-2 on the B200: beam x mask and both SLM multiplies folded into the first pass, the intensity MSE and its
+    cotangent into the last pass (xl_rs_fwd_fused / xl_rs_bwd_fused), every plane declared phase-blind.  Loss, phase-mask
+    gradients AND distance gradients within 1e-4 of the reference fixture (the distance gradients of the unfused table are
+    complex64 cancellation residues)."""
+    import torch
+    from xlumina_b200 import four_f
+    from test_elements import directional, four_f_problem
+    g = golden("four_f_n32")
+    src, params, masks, targets = four_f_problem(g, "cuda", torch.complex64)
+    loss_u = four_f.loss_dualSLM(params, masks, targets, src)
+    grads_u = torch.autograd.grad(loss_u, params)
+    loss = four_f.loss_dualSLM_fused(params, masks, targets, src)
+    grads = torch.autograd.grad(loss, params)
+    errs = {t: abs(directional(g, params, grads, t, "v_%s_%d") - float(g["dloss_" + t])) / abs(float(g["dloss_" + t])) for t in ("dist", "phase")}
+    print("4f fused table: loss", float(loss.detach()) / float(g["loss"]) - 1, "gradients", errs)
+    assert abs(float(loss.detach()) - float(g["loss"])) < 1e-4 * abs(float(g["loss"]))
+    assert errs["phase"] < 1e-4 and errs["dist"] < 1e-4
+    for i in (3, 4):
+        assert rel_l2(grads[i].cpu().numpy(), grads_u[i].cpu().numpy()) < 1e-4
+
+
+@pytest.mark.gpu
+def test_rs_fused_pieces_on_device(xb):
+    """Each fused piece at 1024^2 (batch of 3) against plain torch arithmetic around the unfused operator on the device:
+    complex and float32 inputs, shared modulation plane, detection; gradients in field, z, modulation; d/dz-only backward."""
+    import torch
+    from xlumina_b200 import ops
+    rng = np.random.default_rng(5)
+    N, F = 1024, 3
+    x = np.linspace(-1500.0, 1500.0, N)
+    dx, k = float(x[1] - x[0]), 2 * np.pi / 0.6328
+    dev = "cuda"
+
+    def crand(*s):
+        return torch.tensor((rng.standard_normal(s) + 1j * rng.standard_normal(s)).astype(np.complex64), device=dev)
+    z = torch.tensor([31000.0], dtype=torch.float64, device=dev, requires_grad=True)
+    u = crand(F, N, N).requires_grad_(True)
+    m = crand(N, N).requires_grad_(True)
+    ct = crand(F, N, N)
+    tgt = torch.tensor(rng.uniform(0, 2, (F, N, N)).astype(np.float32), device=dev)
+    w = torch.tensor(rng.uniform(0.5, 1.5, F), device=dev)
+    ref = ops.rs_propagation(u * m[None], z, dx, dx, k)
+    out = ops.rs_propagation_fused(u, z, dx, dx, k, mod=m)
+    assert rel_l2(out.detach().cpu().numpy(), ref.detach().cpu().numpy()) < 1e-6
+    gr = torch.autograd.grad((ct.conj() * ref).real.sum(), (u, z, m))
+    gf = torch.autograd.grad((ct.conj() * out).real.sum(), (u, z, m))
+    assert rel_l2(gf[0].cpu().numpy(), gr[0].cpu().numpy()) < 1e-5 and rel_l2(gf[2].cpu().numpy(), gr[2].cpu().numpy()) < 1e-5
+    assert abs(float(gf[1]) - float(gr[1])) < 1e-4 * abs(float(gr[1]))
+
+    def mse_ref(uu, zz, mm):
+        o = ops.rs_propagation(uu * mm[None], zz, dx, dx, k)
+        return (((o.real ** 2 + o.imag ** 2 - tgt) ** 2).sum(dim=(-2, -1)) / (N * N) * w).sum()
+    lr = mse_ref(u, z, m)
+    lf = (ops.rs_propagation_fused(u, z, dx, dx, k, mod=m, target=tgt) * w).sum()
+    assert abs(float(lf) - float(lr)) < 1e-5 * abs(float(lr))
+    gr = torch.autograd.grad(lr, (u, m))
+    gf = torch.autograd.grad(lf, (u, m))
+    assert rel_l2(gf[0].cpu().numpy(), gr[0].cpu().numpy()) < 1e-4 and rel_l2(gf[1].cpu().numpy(), gr[1].cpu().numpy()) < 1e-4
+    masks = torch.tensor((rng.uniform(0, 1, (F, N, N)) > 0.5).astype(np.float32), device=dev)
+    beam = m.detach()
+    ref = ops.rs_propagation(masks.to(torch.complex64) * beam[None], z, dx, dx, k)
+    out = ops.rs_propagation_fused(masks, z, dx, dx, k, mod=beam)
+    assert rel_l2(out.detach().cpu().numpy(), ref.detach().cpu().numpy()) < 1e-6
+    (gzr,) = torch.autograd.grad((ct.conj() * ref).real.sum(), (z,))
+    (gzf,) = torch.autograd.grad((ct.conj() * out).real.sum(), (z,))
+    assert abs(float(gzf) - float(gzr)) < 1e-4 * abs(float(gzr))

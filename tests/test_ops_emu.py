@@ -71,6 +71,72 @@ def test_four_f_table_complex64(ops_on_emu):
     assert max(errs.values()) < 1e-3
 
 
+def test_four_f_fused_elements_match_unfused_and_reference(ops_on_emu):
+    """beam x mask and both SLM multiplies folded into the first pass, the intensity MSE and its cotangent
+    into the last pass (xl_rs_fwd_fused / xl_rs_bwd_fused).  Same loss and gradients as the unfused table and the reference."""
+    g = golden("four_f_n32")
+    src, params, masks, targets = four_f_problem(g, "cpu", torch.complex64)
+    loss_u = four_f.loss_dualSLM(params, masks, targets, src)
+    grads_u = torch.autograd.grad(loss_u, params)
+    loss_f = four_f.loss_dualSLM_fused(params, masks, targets, src)
+    grads_f = torch.autograd.grad(loss_f, params)
+    assert abs(float(loss_f.detach()) - float(g["loss"])) < 1e-4 * abs(float(g["loss"]))
+    assert abs(float(loss_f.detach()) - float(loss_u.detach())) < 1e-5 * abs(float(loss_u.detach()))
+    for i in (3, 4):     # phase masks
+        assert rel_l2(grads_f[i].numpy(), grads_u[i].numpy()) < 1e-4
+    errs = {t: abs(directional(g, params, grads_f, t, "v_%s_%d") - float(g["dloss_" + t])) / abs(float(g["dloss_" + t])) for t in ("dist", "phase")}
+    print("4f fused c64: loss", float(loss_f.detach()) / float(g["loss"]) - 1, "dloss", errs,
+          "dz fused", [float(grads_f[i]) for i in range(3)], "dz unfused", [float(grads_u[i]) for i in range(3)])
+    assert max(errs.values()) < 1e-3
+
+
+def test_rs_fused_pieces(ops_on_emu):
+    """Each fused piece against plain torch arithmetic around the unfused operator: complex and float32 inputs, shared
+    modulation, detection; gradients with respect to field, z and the modulation plane; the d/dz-only backward."""
+    rng = np.random.default_rng(5)
+    N, F = 24, 3
+    x = np.linspace(-400.0, 400.0, N)
+    dx, k = float(x[1] - x[0]), 2 * np.pi / 0.6328
+    z = torch.tensor([31000.0], dtype=torch.float64, requires_grad=True)
+    u = torch.tensor((rng.standard_normal((F, N, N)) + 1j * rng.standard_normal((F, N, N))).astype(np.complex64), requires_grad=True)
+    m = torch.tensor((rng.standard_normal((N, N)) + 1j * rng.standard_normal((N, N))).astype(np.complex64), requires_grad=True)
+    ct = torch.tensor((rng.standard_normal((F, N, N)) + 1j * rng.standard_normal((F, N, N))).astype(np.complex64))
+    tgt = torch.tensor(rng.uniform(0, 2, (F, N, N)).astype(np.float32))
+    w = torch.tensor(rng.uniform(0.5, 1.5, F))
+    # (a) modulation, complex cotangent
+    ref = ops.rs_propagation(u * m[None], z, dx, dx, k)
+    out = ops.rs_propagation_fused(u, z, dx, dx, k, mod=m)
+    assert rel_l2(out.detach().numpy(), ref.detach().numpy()) < 1e-6
+    gr = torch.autograd.grad((ct.conj() * ref).real.sum(), (u, z, m))
+    gf = torch.autograd.grad((ct.conj() * out).real.sum(), (u, z, m))
+    assert rel_l2(gf[0].numpy(), gr[0].numpy()) < 1e-5 and rel_l2(gf[2].numpy(), gr[2].numpy()) < 1e-5
+    assert abs(float(gf[1]) - float(gr[1])) < 1e-4 * abs(float(gr[1]))
+    # (b) detection with modulation
+    def mse_ref(uu, zz, mm):
+        o = ops.rs_propagation(uu * mm[None], zz, dx, dx, k)
+        return (((o.real ** 2 + o.imag ** 2 - tgt) ** 2).sum(dim=(-2, -1)) / (N * N) * w).sum()
+    lr = mse_ref(u, z, m)
+    lf = (ops.rs_propagation_fused(u, z, dx, dx, k, mod=m, target=tgt) * w).sum()
+    assert abs(float(lf) - float(lr)) < 1e-5 * abs(float(lr))
+    gr = torch.autograd.grad(lr, (u, z, m))
+    gf = torch.autograd.grad(lf, (u, z, m))
+    assert rel_l2(gf[0].numpy(), gr[0].numpy()) < 1e-4 and rel_l2(gf[2].numpy(), gr[2].numpy()) < 1e-4
+    # (c) float32 object masks under a constant beam: only z needs a gradient (d/dz-only backward, no inverse transforms)
+    masks = torch.tensor((rng.uniform(0, 1, (F, N, N)) > 0.5).astype(np.float32))
+    beam = m.detach()
+    ref = ops.rs_propagation(masks.to(torch.complex64) * beam[None], z, dx, dx, k)
+    out = ops.rs_propagation_fused(masks, z, dx, dx, k, mod=beam)
+    assert rel_l2(out.detach().numpy(), ref.detach().numpy()) < 1e-6
+    (gzr,) = torch.autograd.grad((ct.conj() * ref).real.sum(), (z,))
+    (gzf,) = torch.autograd.grad((ct.conj() * out).real.sum(), (z,))
+    assert abs(float(gzf) - float(gzr)) < 1e-4 * abs(float(gzr))
+    # (d) no gradient with respect to z: forward-operator backward with the detection seed
+    z0 = z.detach()
+    gr = torch.autograd.grad(mse_ref(u, z0, m), (u, m))
+    gf = torch.autograd.grad((ops.rs_propagation_fused(u, z0, dx, dx, k, mod=m, target=tgt) * w).sum(), (u, m))
+    assert rel_l2(gf[0].numpy(), gr[0].numpy()) < 1e-4 and rel_l2(gf[1].numpy(), gr[1].numpy()) < 1e-4
+
+
 def test_leading_batch_axes_and_per_item_distances(ops_on_emu):
     """What the reference reaches with vmap (a table vmapped over masks / noisy distances): batches are independent calls,
     a shared z shares the transfer function, a z per item is honoured, gradients flow to every item and every distance."""

@@ -30,6 +30,8 @@ SIGNATURES = {
     "xl_rs_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _d, _d, _d, _i, _vp, _sz, _vp]),
     "xl_vrs_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _d, _d, _d, _d, _d, _i, _vp, _sz, _vp]),
     "xl_vrs_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _d, _d, _d, _d, _d, _i, _vp, _sz, _vp]),
+    "xl_rs_fwd_fused": (_i, [_vp, _vp, _vp, _vp, _i, _i, _d, _d, _d, _i, _vp, _vp, _sz, _vp]),
+    "xl_rs_bwd_fused": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _d, _d, _d, _i, _vp, _vp, _sz, _vp]),
     "xl_slab_padded_length": (_i, [_i]),
     "xl_slab_h_rows_per_rank": (_i, [_i, _i]),
     "xl_slab_scratch_bytes": (_sz, [_i, _i]),
@@ -56,6 +58,12 @@ XL_CONJ_IN = 1
 XL_CONJ_OUT = 2
 XL_REUSE_H = 16
 XL_REUSE_TABLES = 32
+XL_PHASE_BLIND = 64
+
+
+class RsFuse(ctypes.Structure):
+    """struct xl_rs_fuse of include/xlprop.h (pointwise elements fused into the scalar RS path)."""
+    _fields_ = [("mod", ctypes.c_void_p), ("in_real", ctypes.c_int), ("target", ctypes.c_void_p), ("mse", ctypes.c_void_p)]
 
 
 class XlpropError(RuntimeError):

@@ -215,6 +215,7 @@ template <int L> struct XlRsColsGzAsyncOp : XlOpBase {
             u[q] = cf_mul(v[q], stage[r]);
         }
         red[beta] += acc;
+        if (p.flags & XL_F_NOFIELD) return;         // d/dz only (kernel-uniform): no field cotangent, no inverse transform
         XlBfly<16, +1, false, false>::run(u);       // first inverse pass, fused; back into line 0 of the slots just read
 #pragma unroll
         for (int j = 0; j < 16; ++j) XlTileLine0Of2::st(tile2, 16 * beta + j, u + j, 16);
@@ -267,10 +268,12 @@ template <int L> struct XlRsColsGzAsync {
             }
             XlRsColsGzAsyncOp<L> op{{}, p, item_in(p, it), stage, bar, parity, s, red};
             XlFft<L, 2>::forward(s, t, op);
-            XL_SYNC();                                   // spectrum phase done: tile line 0 complete
-            XlRsColsGzOutOp<L> oo{{}, p, p.spec + (size_t)f * L * p.N + (size_t)(g >> 1) * p.N * XL_V, g & 1};
-            XlFft<L, 1, XlTileLine0Of2>::inverse_tail(s, t, oo);
-            XL_SYNC();                                   // the last pass has read the tile; staging buffer free
+            XL_SYNC();                                   // spectrum phase done: tile line 0 complete, staging buffer free
+            if (!(p.flags & XL_F_NOFIELD)) {
+                XlRsColsGzOutOp<L> oo{{}, p, p.spec + (size_t)f * L * p.N + (size_t)(g >> 1) * p.N * XL_V, g & 1};
+                XlFft<L, 1, XlTileLine0Of2>::inverse_tail(s, t, oo);
+                XL_SYNC();                               // the last pass has read the tile
+            }
         }
         // one reduction and one atomic per CTA
         XL_THREADS(tid, NT) {

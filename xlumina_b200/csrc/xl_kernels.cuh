@@ -21,6 +21,7 @@
 #define XL_F_CONJ_OUT 2   // conjugate result on store
 #define XL_F_VRS 4        // 3 fields, field 2 = Ez formed from (Ex,Ey) at load      (vectorized_optics.py:258-261)
 #define XL_F_DERIV 8      // transfer function of dh/dz instead of h
+#define XL_F_NOFIELD 16   // backward column kernel: d/dz only, the field cotangent is not needed (constant input)
 
 XL_DEV void xl_ld4(const cf* p, cf* a, cf* b) {   // two adjacent complex values with one 16-byte load (p 16-byte aligned)
     const float4 t = *reinterpret_cast<const float4*>(p);
@@ -33,6 +34,16 @@ XL_DEV void xl_ldg4(const cf* p, cf* a, cf* b) {
     *b = make_float2(t.z, t.w);
 }
 XL_DEV void xl_st4(cf* p, cf a, cf b) { *reinterpret_cast<float4*>(p) = make_float4(a.x, a.y, b.x, b.y); }
+
+// red[0] = sum of red[0..NT) by a shared-memory tree (NT a power of two); ends with a barrier.
+template <int NT, class T> XL_DEV void xl_block_sum(T* red) {
+    for (int st = NT / 2; st >= 1; st >>= 1) {
+        XL_THREADS(tid, NT) {
+            if (tid < st) red[tid] += red[tid + st];
+        }
+        XL_SYNC();
+    }
+}
 
 // Blocked pair layout  grp[y][2]  (grp = base of slot pair g/2).  The calling thread owns slot g (parity of g == parity of
 // its lane) of the two adjacent rows y0 (v0) and y0+1 (v1); rows >= nrows are not stored / read as zero.
@@ -150,14 +161,40 @@ struct XlRsParams {
     double x0, y0, dx, dy, k;
     float hscale;      // dx*dy/L^2
     unsigned stagger_ns;   // persistent kernels: the second CTA of an SM starts this much later (de-phases the two CTAs)
+    // Pointwise elements fused into the first / last pass (xl_rs_fwd_fused / xl_rs_bwd_fused):
+    const cf* mod;         // shared complex plane [N][N] multiplied into every field while it is loaded: a phase-only SLM
+                           // exp(i phi) (optical_elements.py:87-103) or the beam under a batch of masks; null: none
+    int in_real;           // the input planes are float32 (binary object masks), not complex64
+    const float* target;   // detection: target intensities [nfields][N][N] (four_f_optical_table.py:129-141)
+    double* mse;           // [nfields] += sum (|out|^2 - target)^2 / N^2, accumulated by the last pass
+    const cf* seed_out;    // backward: primal output; the cotangent of the fused detection is formed from it and `target`
+    const double* ct_mse;  // [nfields] dL/dmse
+    cf* ct_mod;            // backward: cotangent of `mod` (summed over the fields)
 };
+
+// input of the fused forward pass: plane f (complex64 or float32) x the shared complex plane
+XL_DEV cf xl_fused_in(const XlRsParams& p, const void* base, size_t fo, size_t o) {
+    cf v = p.in_real ? make_float2(((const float*)base)[fo + o], 0.f) : ((const cf*)base)[fo + o];
+    if (p.mod) v = cf_mul(v, xl_ldg(p.mod + o));
+    return v;
+}
+// Cotangent seeded by the fused detection, torch convention: L = sum_f ct_mse[f] mse[f], mse = sum (|out|^2 - T)^2 / N^2
+//   =>  dL/d out = w (|out|^2 - T) out,  w = 4 ct_mse[f] / N^2   (real factor x out: the i k out part of d/dz vanishes exactly)
+XL_DEV cf xl_seed_ct(const XlRsParams& p, float w, size_t fo, size_t o) {
+    const cf a = p.seed_out[fo + o];
+    const float d = a.x * a.x + a.y * a.y - p.target[fo + o];
+    return cf_scale(a, w * d);
+}
+XL_DEV float xl_seed_weight(const XlRsParams& p, int f) {
+    return p.seed_out ? (float)(4.0 * xl_ldg(p.ct_mse + f) / ((double)p.N * (double)p.N)) : 0.f;
+}
 
 // K1: rows of the zero-padded field -> blocked row spectra.   replaces the row half of fft2(U), wave_optics.py:286-288
 // EZ: this CTA's field is Ez = (Ex X + Ey Y)/r formed from (Ex,Ey) while loading (vectorized_optics.py:258-261).
 // The load path is branch-free so that all of a thread's global loads are in flight together.
-template <int L, bool EZ> struct XlRsRowsFwdOp : XlOpBase {
+template <int L, bool EZ, bool FUSE = false> struct XlRsRowsFwdOp : XlOpBase {
     static constexpr bool kInLoHalf = true;   // N <= L/2: the upper half of every padded row is zero
-    const XlRsParams& p; int f, yb; double z2;
+    const XlRsParams& p; int f, yb; double z2; float w;   // w: seed weight of the fused detection (FUSE backward)
     XL_DEV cf load1(int y, int i) const {
         const int N = p.N;
         const bool ok = y < p.rows && i < N;
@@ -168,6 +205,8 @@ template <int L, bool EZ> struct XlRsRowsFwdOp : XlOpBase {
             const double X = p.x0 + i * p.dx, Y = p.y0 + y * p.dy;
             const double ir = xl_rsqrt64(X * X + Y * Y + z2);
             v = cf_lin2(ex, (float)(X * ir), ey, (float)(Y * ir));
+        } else if (FUSE) {
+            v = p.seed_out ? xl_seed_ct(p, w, (size_t)f * NN, o) : xl_fused_in(p, p.in, (size_t)f * NN, o);
         } else {
             v = p.in[(size_t)f * NN + o];
         }
@@ -188,8 +227,8 @@ template <int L, bool EZ> struct XlRsRowsFwdOp : XlOpBase {
     }
     XL_DEV void store_vec(int, const cf*) const {}
 };
-template <int L> struct XlRsRowsFwd {
-    static const char* name() { return "rs_rows_fwd"; }
+template <int L, bool FUSE = false> struct XlRsRowsFwd {
+    static const char* name() { return FUSE ? "rs_rows_fwd_f" : "rs_rows_fwd"; }
     typedef XlRsParams Params;
     static constexpr int NT = xl_threads(L);
     static size_t smem() { return xl_smem_bytes(L, XL_V); }
@@ -197,12 +236,15 @@ template <int L> struct XlRsRowsFwd {
         cf* t = s + xl_tile_elems(L, XL_V);
         XlFft<L, XL_V>::init_tw(t, p.tw);
         const int f = p.f0 + XL_BLOCK_Y, yb = XL_BLOCK_X * XL_V;
-        if ((p.flags & XL_F_VRS) && f == 2) {   // CTA-uniform
+        if (FUSE) {
+            XlRsRowsFwdOp<L, false, true> op{{}, p, f, yb, 0.0, xl_seed_weight(p, f)};
+            XlFft<L, XL_V>::forward(s, t, op);
+        } else if ((p.flags & XL_F_VRS) && f == 2) {   // CTA-uniform
             const double z = xl_ldg(p.z);
-            XlRsRowsFwdOp<L, true> op{{}, p, f, yb, z * z};
+            XlRsRowsFwdOp<L, true> op{{}, p, f, yb, z * z, 0.f};
             XlFft<L, XL_V>::forward(s, t, op);
         } else {
-            XlRsRowsFwdOp<L, false> op{{}, p, f, yb, 0.0};
+            XlRsRowsFwdOp<L, false> op{{}, p, f, yb, 0.0, 0.f};
             XlFft<L, XL_V>::forward(s, t, op);
         }
     }
@@ -213,20 +255,22 @@ template <int L> struct XlRsRowsFwd {
 // one x frequency in the registers of one thread (XlRsColsGzAsync) and reads them with one 16-byte load per row; two
 // adjacent lanes (slots g, g+1) fill one 32-byte sector here.  Replaces the two separate row-spectra launches of the
 // backward pass (JAX autodiff of wave_optics.py:286-288).
-template <int L, bool EZ> struct XlRsRowsDualOp : XlOpBase {
+template <int L, bool EZ, bool FUSE = false> struct XlRsRowsDualOp : XlOpBase {
     static constexpr bool kInLoHalf = true;
-    const XlRsParams& p; int f, y; double z2;
+    const XlRsParams& p; int f, y; double z2; float sw;   // sw: seed weight of the fused detection
     XL_DEV void load(int i, cf* v, int stride) const {
         const int N = p.N;
         const bool ok = i < N;
         const size_t NN = (size_t)p.rows * N, o = ok ? (size_t)y * N + i : 0;
-        cf c = p.in[(size_t)f * NN + o], w;
+        cf c = (FUSE && p.seed_out) ? xl_seed_ct(p, sw, (size_t)f * NN, o) : p.in[(size_t)f * NN + o], w;
         if (p.flags & XL_F_CONJ_IN) c = cf_conj(c);
         if (EZ) {
             const cf ex = p.in2[o], ey = p.in2[NN + o];
             const double X = p.x0 + i * p.dx, Y = p.y0 + y * p.dy;
             const double ir = xl_rsqrt64(X * X + Y * Y + z2);
             w = cf_lin2(ex, (float)(X * ir), ey, (float)(Y * ir));
+        } else if (FUSE) {
+            w = xl_fused_in(p, p.in2, (size_t)f * NN, o);
         } else {
             w = p.in2[(size_t)f * NN + o];
         }
@@ -243,8 +287,8 @@ template <int L, bool EZ> struct XlRsRowsDualOp : XlOpBase {
     }
     XL_DEV void store_vec(int, const cf*) const {}
 };
-template <int L> struct XlRsRowsDual {
-    static const char* name() { return "rs_rows_dual"; }
+template <int L, bool FUSE = false> struct XlRsRowsDual {
+    static const char* name() { return FUSE ? "rs_rows_dual_f" : "rs_rows_dual"; }
     typedef XlRsParams Params;
     static constexpr int NT = xl_threads(L);
     static size_t smem() { return xl_smem_bytes(L, XL_V); }
@@ -252,12 +296,15 @@ template <int L> struct XlRsRowsDual {
         cf* t = s + xl_tile_elems(L, XL_V);
         XlFft<L, XL_V>::init_tw(t, p.tw);
         const int f = p.f0 + XL_BLOCK_Y, y = XL_BLOCK_X;
-        if ((p.flags & XL_F_VRS) && f == 2) {   // CTA-uniform
+        if (FUSE) {
+            XlRsRowsDualOp<L, false, true> op{{}, p, f, y, 0.0, xl_seed_weight(p, f)};
+            XlFft<L, XL_V>::forward(s, t, op);
+        } else if ((p.flags & XL_F_VRS) && f == 2) {   // CTA-uniform
             const double z = xl_ldg(p.z);
-            XlRsRowsDualOp<L, true> op{{}, p, f, y, z * z};
+            XlRsRowsDualOp<L, true> op{{}, p, f, y, z * z, 0.f};
             XlFft<L, XL_V>::forward(s, t, op);
         } else {
-            XlRsRowsDualOp<L, false> op{{}, p, f, y, 0.0};
+            XlRsRowsDualOp<L, false> op{{}, p, f, y, 0.0, 0.f};
             XlFft<L, XL_V>::forward(s, t, op);
         }
     }
@@ -368,10 +415,12 @@ template <int L> struct XlRsColsSlab {
 };
 
 // K3: inverse row FFT of the filtered spectra, crop columns [0,N).   wave_optics.py:288 (row half of ifft2 + crop)
-template <int L> struct XlRsRowsInvOp : XlOpBase {
+// DET: fused detection -- while the result is stored, sum (|out|^2 - target)^2 is accumulated per field
+// (four_f_optical_table.py:129-141, MSE of intensities): the intensity plane is never materialised.
+template <int L, bool DET = false> struct XlRsRowsInvOp : XlOpBase {
     static constexpr bool kOutLoHalf = true;
     static constexpr int R1 = xl_first_radix(L), S1 = L / R1;
-    const XlRsParams& p; int f, yb;
+    const XlRsParams& p; int f, yb; float* red;   // red[S1]: per-butterfly partial sums (DET)
     XL_DEV void load(int, cf*, int) const {}
     XL_DEV void spec(int beta, cf* v) const {
         const cf* base = p.spec + (size_t)f * L * p.rows;
@@ -382,6 +431,7 @@ template <int L> struct XlRsRowsInvOp : XlOpBase {
         }
     }
     XL_DEV void store_vec(int n, const cf* v) const {
+        float acc = 0.f;
 #pragma unroll
         for (int l = 0; l < XL_V; ++l) {
             const int y = yb + l;
@@ -391,22 +441,119 @@ template <int L> struct XlRsRowsInvOp : XlOpBase {
                 const int i = n + S1 * j;
                 if (i >= p.N) continue;
                 cf val = v[l * R1 + j];
+                const size_t o = (size_t)f * p.rows * p.N + (size_t)y * p.N + i;
+                if (DET) {
+                    const float d = val.x * val.x + val.y * val.y - p.target[o];
+                    acc += d * d;
+                }
                 if (p.flags & XL_F_CONJ_OUT) val = cf_conj(val);
-                p.out[(size_t)f * p.rows * p.N + (size_t)y * p.N + i] = val;
+                p.out[o] = val;
+            }
+        }
+        if (DET) red[n] = acc;
+    }
+};
+template <int L, bool DET = false> struct XlRsRowsInv {
+    static const char* name() { return DET ? "rs_rows_inv_det" : "rs_rows_inv"; }
+    typedef XlRsParams Params;
+    static constexpr int NT = xl_threads(L);
+    static constexpr int S1 = L / xl_first_radix(L);
+    static size_t smem() { return xl_smem_bytes(L, XL_V) + (DET ? NT * sizeof(double) + S1 * sizeof(float) : 0); }
+    XL_DEV static void run(const Params& p, cf* s) {
+        cf* t = s + xl_tile_elems(L, XL_V);
+        double* dred = (double*)(t + xl_tw_total(L));
+        float* red = (float*)(dred + NT);
+        XlFft<L, XL_V>::init_tw(t, p.tw);
+        const int f = p.f0 + XL_BLOCK_Y;
+        XlRsRowsInvOp<L, DET> op{{}, p, f, XL_BLOCK_X * XL_V, red};
+        XlFft<L, XL_V>::inverse(s, t, op);
+        if (DET) {
+            XL_SYNC();
+            XL_THREADS(tid, NT) {
+                double a = 0.0;
+                for (int n = tid; n < S1; n += NT) a += (double)red[n];
+                dred[tid] = a;
+            }
+            XL_SYNC();
+            xl_block_sum<NT>(dred);
+            XL_THREADS(tid, NT) {
+                if (tid == 0) xl_atomic_add(p.mse + f, dred[0] / ((double)p.N * (double)p.N));
             }
         }
     }
 };
-template <int L> struct XlRsRowsInv {
-    static const char* name() { return "rs_rows_inv"; }
+
+// K3m: the inverse row kernel of the fused BACKWARD pass.  v = in * mod was propagated, so with c = A^T ct_out (what the
+// inverse row FFT produces):  ct_in[f] = c[f] * mod  and  ct_mod = sum_f c[f] * in[f]  (JAX convention; XL_F_CONJ_OUT
+// conjugates both on store).  One CTA owns a row pair and walks the fields, accumulating ct_mod in shared memory: no atomics
+// and no per-field cotangent of the modulated field in HBM.  Replaces the VJP of the SLM multiply (optical_elements.py:87-103).
+template <int L> struct XlRsRowsInvModOp : XlOpBase {
+    static constexpr bool kOutLoHalf = true;
+    static constexpr int R1 = xl_first_radix(L), S1 = L / R1;
+    const XlRsParams& p; int f, yb; cf* acc;   // acc[XL_V][N]
+    XL_DEV void load(int, cf*, int) const {}
+    XL_DEV void spec(int beta, cf* v) const {
+        const cf* base = p.spec + (size_t)f * L * p.rows;
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            const int g = q * (L / 16) + beta;
+            xl_blocked_load2<xl_lane_mask(L)>(base + (size_t)(g / 2) * p.rows * 2, yb, p.rows, g, v + q, v + 16 + q);
+        }
+    }
+    XL_DEV void store_vec(int n, const cf* v) const {
+        const size_t NN = (size_t)p.rows * p.N;
+#pragma unroll
+        for (int l = 0; l < XL_V; ++l) {
+            const int y = yb + l;
+            if (y >= p.rows) continue;
+#pragma unroll
+            for (int j = 0; j < R1 / 2; ++j) {
+                const int i = n + S1 * j;
+                if (i >= p.N) continue;
+                const cf c = v[l * R1 + j];
+                const size_t o = (size_t)y * p.N + i;
+                if (p.ct_mod) {
+                    const cf a = p.in_real ? make_float2(((const float*)p.in)[(size_t)f * NN + o], 0.f) : p.in[(size_t)f * NN + o];
+                    acc[l * p.N + i] = cf_fma(c, a, acc[l * p.N + i]);
+                }
+                if (p.out) {
+                    cf r = p.mod ? cf_mul(c, xl_ldg(p.mod + o)) : c;
+                    if (p.flags & XL_F_CONJ_OUT) r = cf_conj(r);
+                    p.out[(size_t)f * NN + o] = r;
+                }
+            }
+        }
+    }
+};
+template <int L> struct XlRsRowsInvMod {
+    static const char* name() { return "rs_rows_inv_mod"; }
     typedef XlRsParams Params;
     static constexpr int NT = xl_threads(L);
-    static size_t smem() { return xl_smem_bytes(L, XL_V); }
+    static size_t smem() { return xl_smem_bytes(L, XL_V) + (size_t)L * sizeof(cf); }   // + acc[XL_V][N], N <= L/2
     XL_DEV static void run(const Params& p, cf* s) {
         cf* t = s + xl_tile_elems(L, XL_V);
-        XlFft<L, XL_V>::init_tw(t, p.tw);
-        XlRsRowsInvOp<L> op{{}, p, p.f0 + XL_BLOCK_Y, XL_BLOCK_X * XL_V};
-        XlFft<L, XL_V>::inverse(s, t, op);
+        cf* acc = t + xl_tw_total(L);
+        const int yb = XL_BLOCK_X * XL_V;
+        XL_THREADS(tid, NT) {
+            for (int e = tid; e < XL_V * p.N; e += NT) acc[e] = cf_zero();
+        }
+        XlFft<L, XL_V>::init_tw(t, p.tw);          // ends with a barrier
+        for (int f = p.f0; f < p.f0 + p.nfields; ++f) {
+            XlRsRowsInvModOp<L> op{{}, p, f, yb, acc};
+            XlFft<L, XL_V>::inverse(s, t, op);
+            XL_SYNC();                             // the last pass has read the tile; acc[] of this field is complete
+        }
+        if (p.ct_mod) {
+            XL_THREADS(tid, NT) {
+                for (int e = tid; e < XL_V * p.N; e += NT) {
+                    const int y = yb + e / p.N, i = e % p.N;
+                    if (y >= p.rows) continue;
+                    cf r = acc[e];
+                    if (p.flags & XL_F_CONJ_OUT) r = cf_conj(r);
+                    p.ct_mod[(size_t)y * p.N + i] = r;
+                }
+            }
+        }
     }
 };
 
@@ -906,16 +1053,6 @@ template <int L> struct XlCztKernelFft {
         XlFft<L, XL_V>::forward(s, t, op);
     }
 };
-
-// red[0] = sum of red[0..NT) by a shared-memory tree (NT a power of two); ends with a barrier.
-template <int NT, class T> XL_DEV void xl_block_sum(T* red) {
-    for (int st = NT / 2; st >= 1; st >>= 1) {
-        XL_THREADS(tid, NT) {
-            if (tid < st) red[tid] += red[tid + st];
-        }
-        XL_SYNC();
-    }
-}
 
 // gz += -k Im sum ct*out : the i k h part of dh/dz, evaluated exactly (fp32 x fp32 products are exact in fp64).
 struct XlDotZParams {

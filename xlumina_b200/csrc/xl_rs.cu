@@ -164,3 +164,117 @@ extern "C" int xl_vrs_bwd(const void* exy, const void* out, const void* ct_out, 
     return rs_bwd_common(exy, out, ct_out, ct_exy, grad_z, H, z, N, 3, 1, x0, y0, dx, dy, k, flags, ws, ws_bytes, (xl_stream_t)stream);
 }
 
+
+
+// ================================================================================================ fused elements (8f-1 / 8f-2)
+// xl_rs_fwd_fused / xl_rs_bwd_fused: the scalar RS path with the pointwise elements that bracket it in an optical table
+// folded into its first and last pass -- a shared complex modulation plane (phase-only SLM, optical_elements.py:87-103; the
+// beam under a batch of real object masks, four_f_optical_table.py:58-65) on the way in, and the intensity-MSE detector
+// (four_f_optical_table.py:129-141) on the way out.
+static void rs_fuse_params(XlRsParams& p, const xl_rs_fuse* fu) {
+    if (!fu) return;
+    p.mod = (const cf*)fu->mod; p.in_real = fu->in_real; p.target = fu->target; p.mse = fu->mse;
+}
+
+extern "C" int xl_rs_fwd_fused(const void* in, void* out, void* H, const double* z, int N, int nfields,
+                               double dx, double dy, double k, int flags, const xl_rs_fuse* fuse,
+                               void* ws, size_t ws_bytes, void* stream) {
+    xl_stream_t st = (xl_stream_t)stream;
+    if (nfields < 1) return xl_fail(XL_E_BAD_ARG, "xl_rs_fwd_fused: nfields < 1%s", "");
+    if (!in || !out || !H || !z || !ws) return xl_fail(XL_E_BAD_ARG, "xl_rs_fwd_fused: null pointer%s", "");
+    if (fuse && fuse->target && !fuse->mse) return xl_fail(XL_E_BAD_ARG, "xl_rs_fwd_fused: a detection target needs the mse accumulator%s", "");
+    XlRsParams p;
+    int rc = rs_base_params(p, N, dx, dy, k);
+    if (rc) return rc;
+    if (ws_bytes < xl_rs_workspace_bytes(N, nfields, 0)) return xl_fail(XL_E_WORKSPACE, "xl_rs_fwd_fused: workspace too small%s", "");
+    if (!(flags & XL_REUSE_H)) { rc = rs_transfer_impl(p, (cf*)H, z, 0, st); if (rc) return rc; }
+    Carver c{(char*)ws, 0, ws_bytes};
+    p.spec = (cf*)c.take((size_t)nfields * p.L * N * sizeof(cf));
+    p.in = (const cf*)in; p.out = (cf*)out; p.H = (cf*)H; p.z = z; p.nfields = nfields; p.f0 = 0;
+    p.flags = 0;
+    rs_fuse_params(p, fuse);
+    if (!aligned16(p.H) || !aligned16(p.spec)) return xl_fail(XL_E_BAD_ARG, "RS: the transfer-function buffer and the workspace must be 16-byte aligned%s", "");
+    const int L = p.L;
+    if (p.mod || p.in_real) { XL_FOR_L(L, rc = xl_launch<XlRsRowsFwd<XL, true>>(XlDim{xl_groups(N), nfields}, st, p)); }
+    else { XL_FOR_L(L, rc = xl_launch<XlRsRowsFwd<XL>>(XlDim{xl_groups(N), nfields}, st, p)); }
+    if (rc) return rc;
+    XL_FOR_L(L, rc = xl_launch_persistent<XlRsColsAsync<XL>>((L / XL_V) * nfields, 2, st, p));
+    if (rc) return rc;
+    if (p.target) { XL_FOR_L(L, rc = xl_launch<XlRsRowsInv<XL, true>>(XlDim{xl_groups(N), nfields}, st, p)); }
+    else { XL_FOR_L(L, rc = xl_launch<XlRsRowsInv<XL>>(XlDim{xl_groups(N), nfields}, st, p)); }
+    return rc;
+}
+
+extern "C" int xl_rs_bwd_fused(const void* in, const void* out, const void* ct_out, const double* ct_mse, void* ct_in, void* ct_mod,
+                               double* grad_z, const void* H, const double* z, int N, int nfields,
+                               double dx, double dy, double k, int flags, const xl_rs_fuse* fuse,
+                               void* ws, size_t ws_bytes, void* stream) {
+    xl_stream_t st = (xl_stream_t)stream;
+    if (nfields < 1) return xl_fail(XL_E_BAD_ARG, "xl_rs_bwd_fused: nfields < 1%s", "");
+    if (!in || !H || !ws || !z) return xl_fail(XL_E_BAD_ARG, "xl_rs_bwd_fused: null pointer%s", "");
+    const bool seed = fuse && fuse->target;
+    if (seed ? (!ct_mse || !out) : !ct_out) return xl_fail(XL_E_BAD_ARG, "xl_rs_bwd_fused: missing output cotangent%s", "");
+    if (grad_z && !out) return xl_fail(XL_E_BAD_ARG, "xl_rs_bwd_fused: grad_z needs the primal output%s", "");
+    const bool need_field = ct_in || ct_mod;
+    if (!need_field && !grad_z) return XL_OK;
+    XlRsParams p;
+    int rc = rs_base_params(p, N, dx, dy, k);
+    if (rc) return rc;
+    if (ws_bytes < xl_rs_workspace_bytes(N, nfields, grad_z != 0)) return xl_fail(XL_E_WORKSPACE, "xl_rs_bwd_fused: workspace too small%s", "");
+    if (!aligned16(H) || !aligned16(ws)) return xl_fail(XL_E_BAD_ARG, "RS: the transfer-function buffer and the workspace must be 16-byte aligned%s", "");
+    const int L = p.L;
+    Carver c{(char*)ws, 0, ws_bytes};
+    const size_t spec_bytes = (size_t)nfields * L * N * sizeof(cf);
+    p.spec = (cf*)c.take(spec_bytes);
+    c.take((size_t)3 * N * N * sizeof(cf));
+    p.nfields = nfields; p.H = (cf*)H; p.z = z; p.f0 = 0;
+    XlRsParams pc = p;                              // cotangent-side loads: read ct_out, or seed it from the detector
+    pc.in = (const cf*)ct_out;
+    pc.flags = flags & XL_CONJ_IN;
+    if (seed) { pc.seed_out = (const cf*)out; pc.target = fuse->target; pc.ct_mse = ct_mse; }
+    if (grad_z) {
+        p.spec2 = (cf*)c.take(2 * spec_bytes);
+        cf* Hz = (cf*)c.take((size_t)L * L * sizeof(cf));
+        rc = rs_transfer_impl(p, Hz, z, 1, st);
+        if (rc) return rc;
+        if (!seed && !(flags & XL_PHASE_BLIND)) {   // the i k out part of d out/dz, exactly; it vanishes identically for the fused
+                                                    // detector (xl_seed_ct) and for every phase-blind loss
+            XlDotZParams d;
+            memset(&d, 0, sizeof(d));
+            d.ct = (const cf*)ct_out; d.out = (const cf*)out; d.n = (size_t)nfields * N * N; d.flags = flags & XL_CONJ_IN;
+            d.k = k; d.gz = grad_z;
+            const size_t per = (size_t)XlDotZ::NT * XlDotZ::PER;
+            rc = xl_launch<XlDotZ>(XlDim{(int)((d.n + per - 1) / per), 1}, st, d);
+            if (rc) return rc;
+        }
+        XlRsParams pd = pc;
+        pd.in2 = (const cf*)in; pd.spec = p.spec2;
+        if (fuse) { pd.mod = (const cf*)fuse->mod; pd.in_real = fuse->in_real; }
+        XL_FOR_L(L, rc = xl_launch<XlRsRowsDual<XL, true>>(XlDim{N, nfields}, st, pd));
+        if (rc) return rc;
+        XlRsParams pg = p;
+        pg.H2 = Hz; pg.gz = grad_z;
+        pg.flags = need_field ? 0 : XL_F_NOFIELD;
+        XL_FOR_L(L, rc = xl_launch_persistent<XlRsColsGzAsync<XL>>(L * nfields, 2, st, pg));
+        if (rc) return rc;
+    } else {
+        XlRsParams pa = pc;
+        if (seed) { XL_FOR_L(L, rc = xl_launch<XlRsRowsFwd<XL, true>>(XlDim{xl_groups(N), nfields}, st, pa)); }
+        else { XL_FOR_L(L, rc = xl_launch<XlRsRowsFwd<XL>>(XlDim{xl_groups(N), nfields}, st, pa)); }
+        if (rc) return rc;
+        XL_FOR_L(L, rc = xl_launch_persistent<XlRsColsAsync<XL>>((L / XL_V) * nfields, 2, st, pa));
+        if (rc) return rc;
+    }
+    if (!need_field) return XL_OK;
+    XlRsParams po = p;
+    po.flags = flags & XL_CONJ_OUT;
+    po.out = (cf*)ct_in;
+    const cf* mod = fuse ? (const cf*)fuse->mod : 0;
+    if (mod || ct_mod) {
+        po.in = (const cf*)in; po.in_real = fuse ? fuse->in_real : 0; po.mod = mod; po.ct_mod = (cf*)ct_mod;
+        XL_FOR_L(L, rc = xl_launch<XlRsRowsInvMod<XL>>(XlDim{xl_groups(N), 1}, st, po));
+    } else {
+        XL_FOR_L(L, rc = xl_launch<XlRsRowsInv<XL>>(XlDim{xl_groups(N), nfields}, st, po));
+    }
+    return rc;
+}

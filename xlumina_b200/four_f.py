@@ -39,6 +39,22 @@ def vector_dualSLM_4f_system(input_masks, input_light, parameters):
     return f.real ** 2 + f.imag ** 2, slm_1, slm_2
 
 
+def loss_dualSLM_fused(parameters, input_masks, target_intensities, input_light):
+    """loss_dualSLM with the pointwise elements folded into the propagation kernels (ops.rs_propagation_fused): the beam is the
+    shared modulation of the real object masks, each SLM the shared modulation of the next propagation, and the intensity MSE
+    is accumulated by the last inverse pass -- no element, intensity or cotangent plane is materialised per sample.
+    input_masks (B,N,N) real (float32 or complex with zero imaginary part), target_intensities (B,N,N).  Same value and
+    gradients as loss_dualSLM (four_f_optical_table.py:36-141)."""
+    x = input_light.x
+    dx, k = float(x[1] - x[0]), input_light.k
+    masks = input_masks.real if input_masks.is_complex() else input_masks
+    # one path per sample ending in an intensity detector: the loss is blind to the global phase of every plane
+    f = ops.rs_propagation_fused(masks.to(torch.float32), _distance(parameters[0]), dx, dx, k, mod=input_light.field, phase_blind=True)
+    f = ops.rs_propagation_fused(f, _distance(parameters[1]), dx, dx, k, mod=_slm_phasor(parameters[3]), phase_blind=True)
+    mse = ops.rs_propagation_fused(f, _distance(parameters[2]), dx, dx, k, mod=_slm_phasor(parameters[4]), target=target_intensities)
+    return mse.mean()
+
+
 def batch_dualSLM_4f(input_mask, input_light, parameters):
     """One sample of vector_dualSLM_4f_system.  four_f_optical_table.py:36-83."""
     inten, slm_1, slm_2 = vector_dualSLM_4f_system(input_mask[None], input_light, parameters)

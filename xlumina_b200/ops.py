@@ -20,7 +20,7 @@ import torch
 
 from . import _lib
 
-__all__ = ["rs_propagation", "vrs_propagation", "czt", "vczt", "highna_focus", "rs_transfer", "set_transfer_cache"]
+__all__ = ["rs_propagation", "rs_propagation_fused", "vrs_propagation", "czt", "vczt", "highna_focus", "rs_transfer", "set_transfer_cache"]
 
 
 # ---------------------------------------------------------------------------------------------- plumbing
@@ -254,6 +254,82 @@ class _VRS(torch.autograd.Function):
         _lib.check(L.xl_vrs_bwd(_ptr(exy), _ptr(out), _ptr(g), _ptr(gin), _ptr(gz), _ptr(H), _ptr(z), N, x0, y0, dx, dy, k,
                                 _lib.XL_CONJ_IN | _lib.XL_CONJ_OUT, _ptr(ws), ws.numel(), _stream(exy)), "xl_vrs_bwd")
         return gin, gz, None, None, None, None, None, None, None, None
+
+
+class _RSFused(torch.autograd.Function):
+    """Scalar RS with the bracketing pointwise elements folded into its first and last pass (xl_rs_fwd_fused /
+    xl_rs_bwd_fused):  out[f] = RS(field[f] * mod; z), or -- with `target` -- the per-field MSE of
+    |out|^2 against target intensities.  field (F,N,N) complex64 or float32, mod (N,N) complex64 or None, target (F,N,N)
+    float32 or None."""
+
+    @staticmethod
+    @_on_device
+    def forward(ctx, field, z, mod, target, dx, dy, k, phase_blind):
+        _require_device(field)
+        L = _lib.lib()
+        F, N = field.shape[0], field.shape[-1]
+        ctx.phase_blind = bool(phase_blind)
+        out = torch.empty((F, N, N), dtype=torch.complex64, device=field.device)
+        mse = torch.zeros(F, dtype=torch.float64, device=field.device) if target is not None else None
+        H = torch.empty(L.xl_rs_transfer_bytes(N), dtype=torch.uint8, device=field.device)
+        ws = _workspace(field, L.xl_rs_workspace_bytes(N, F, 0))
+        fuse = _lib.RsFuse(mod.data_ptr() if mod is not None else None, 0 if field.is_complex() else 1,
+                           target.data_ptr() if target is not None else None, mse.data_ptr() if mse is not None else None)
+        _lib.check(L.xl_rs_fwd_fused(_ptr(field), _ptr(out), _ptr(H), _ptr(z), N, F, dx, dy, k, 0, ctypes.byref(fuse),
+                                     _ptr(ws), ws.numel(), _stream(field)), "xl_rs_fwd_fused")
+        ctx.save_for_backward(field, z, H, out, mod, target)
+        ctx.geom = (dx, dy, k)
+        return mse if target is not None else out
+
+    @staticmethod
+    @_on_device
+    def backward(ctx, g):
+        field, z, H, out, mod, target = ctx.saved_tensors
+        dx, dy, k = ctx.geom
+        L = _lib.lib()
+        F, N = field.shape[0], field.shape[-1]
+        want_f, want_z, want_m = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2] and mod is not None
+        g = g.resolve_conj().contiguous()
+        if target is not None:
+            ct_out, ct_mse = None, g.to(torch.float64)
+        else:
+            ct_out, ct_mse = g, None
+        gin = torch.empty((F, N, N), dtype=torch.complex64, device=field.device) if want_f else None
+        gmod = torch.empty((N, N), dtype=torch.complex64, device=field.device) if want_m else None
+        gz = torch.zeros(1, dtype=torch.float64, device=field.device) if want_z else None
+        ws = _workspace(field, L.xl_rs_workspace_bytes(N, F, 1 if want_z else 0))
+        fuse = _lib.RsFuse(mod.data_ptr() if mod is not None else None, 0 if field.is_complex() else 1,
+                           target.data_ptr() if target is not None else None, None)
+        _lib.check(L.xl_rs_bwd_fused(_ptr(field), _ptr(out), _ptr(ct_out), _ptr(ct_mse), _ptr(gin), _ptr(gmod), _ptr(gz), _ptr(H), _ptr(z),
+                                     N, F, dx, dy, k, _lib.XL_CONJ_IN | _lib.XL_CONJ_OUT | (_lib.XL_PHASE_BLIND if ctx.phase_blind else 0),
+                                     ctypes.byref(fuse), _ptr(ws), ws.numel(), _stream(field)), "xl_rs_bwd_fused")
+        if want_f and not field.is_complex():
+            gin = gin.real
+        return gin, gz, gmod, None, None, None, None, None
+
+
+def rs_propagation_fused(field, z, dx, dy, k, mod=None, target=None, phase_blind=False):
+    """Scalar RS propagation of a batch `field` (F,N,N) with the pointwise elements around it fused into the kernels
+    (N <= 2048): every field is multiplied by the shared complex plane `mod` (N,N) while it is loaded -- a phase-only SLM
+    exp(i phi), an amplitude mask, the beam under a batch of real object masks (then `field` may be float32) -- and, with
+    `target` (F,N,N) float32, the detector is folded into the last pass: the call returns the F per-field values
+    mean((|out|^2 - target)^2) (float64) instead of the fields.  Differentiable in field, z and mod.
+    `phase_blind=True` is the caller's guarantee that the loss is invariant under a global phase of this propagation's output
+    (a single path that ends in an intensity detector): the i*k*out part of d/dz, which is then exactly zero, is dropped
+    instead of being evaluated as a complex64 cancellation residue."""
+    N = field.shape[-1]
+    if field.dim() != 3 or field.shape[-2] != N:
+        raise ValueError("rs_propagation_fused needs a batch of square fields (F, N, N)")
+    if N > FUSED_MAX_N:
+        raise _lib.XlpropError(f"rs_propagation_fused: N <= {FUSED_MAX_N}")
+    f = field.contiguous() if field.dtype == torch.float32 else _c64(field)
+    m = None if mod is None else _c64(mod)
+    t = None if target is None else target.to(torch.float32).contiguous()
+    if m is not None and m.shape != (N, N):
+        raise ValueError("mod must be one (N, N) plane shared by the batch")
+    if t is not None and t.shape != f.shape:
+        raise ValueError("target must have the shape of the batch")
+    return _RSFused.apply(f, _as_z(z, f), m, t, float(dx), float(dy), float(k), bool(phase_blind))
 
 
 FUSED_MAX_N = 2048   # largest grid of the fused single-pass path (padded length 4096); above it: the stage chain of slab.py
