@@ -166,10 +166,22 @@ size_t xl_czt_tables_bytes(int N, int Mx, int My);
 int xl_czt_fwd(const void* in, void* out, const double* z, double lambda, int N, int Mx, int My, int vectorial,
                double x0, double dx, double y0, double dy, double xout0, double xoutl, double yout0, double youtl,
                int flags, void* tables, void* ws, size_t ws_bytes, void* stream);
-/* VJP with respect to the input field(s) (z, lambda and the grids are static in every reference caller). */
+/* VJP with respect to the input field(s) (z, lambda and the grids are static in every reference caller; xl_czt_bwd_z below
+ * also returns the gradient with respect to z). */
 int xl_czt_bwd(const void* ct_out, void* ct_in, const double* z, double lambda, int N, int Mx, int My, int vectorial,
                double x0, double dx, double y0, double dy, double xout0, double xoutl, double yout0, double youtl,
                int flags, void* tables, void* ws, size_t ws_bytes, void* stream);
+
+/* Field VJP AND the gradient with respect to the distance: JAX differentiates CZT_jit / VCZT_jit through F, F0,
+ * the constant z dx dy lambda and, via Dm = lambda z/dx, every Bluestein chirp (wave_optics.py:322, 340-355, 393-403).
+ * `in` / `out` are the primal input and result of the forward call; *grad_z += Re sum ct_out * d out/dz.  The workspace is
+ * larger (xl_czt_workspace_bytes_z): two more forward chains run on index-weighted inputs (the chirp-z kernel of an axis is
+ * exp(i Phi(l,k)) with dPhi/dDm bilinear in the output and input index). */
+size_t xl_czt_workspace_bytes_z(int N, int Mx, int My, int vectorial);
+int xl_czt_bwd_z(const void* in, const void* out, const void* ct_out, void* ct_in, double* grad_z,
+                 const double* z, double lambda, int N, int Mx, int My, int vectorial,
+                 double x0, double dx, double y0, double dy, double xout0, double xoutl, double yout0, double youtl,
+                 int flags, void* tables, void* ws, size_t ws_bytes, void* stream);
 
 /* ---------------------------------------------------------------- high-NA objective ------------------------- */
 /* exy = [Ex,Ey] (2,N,N) -> out = [Ex,Ey,Ez] (3,My,Mx) in the focal plane:

@@ -582,3 +582,39 @@ def test_rs_fused_pieces_on_device(xb):
     (gzr,) = torch.autograd.grad((ct.conj() * ref).real.sum(), (z,))
     (gzf,) = torch.autograd.grad((ct.conj() * out).real.sum(), (z,))
     assert abs(float(gzf) - float(gzr)) < 1e-4 * abs(float(gzr))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("vect", [0, 1])
+def test_czt_distance_gradient_on_device(xb, vect):
+    """SURVEY.md 8f-4 on the B200: d/dz of CZT / VCZT (256^2 -> 200 x 180 region of interest) against a 4th-order central
+    difference of the complex128 NumPy oracle, random cotangent; the field gradient of the same backward call against the
+    call without d/dz."""
+    import torch
+    from oracle import oracle_np as o
+    from xlumina_b200 import ops
+    rng = np.random.default_rng(13 + vect)
+    N, lam, z0 = 256, 0.6328, 9000.0
+    x = np.linspace(-1200.0, 1200.0, N)
+    xo, yo = np.linspace(-150.0, 190.0, 200), np.linspace(-120.0, 160.0, 180)
+    shp = (2, N, N) if vect else (N, N)
+    u = (rng.standard_normal(shp) + 1j * rng.standard_normal(shp)).astype(np.complex64)
+    oshp = (3, len(yo), len(xo)) if vect else (len(yo), len(xo))
+    ct = (rng.standard_normal(oshp) + 1j * rng.standard_normal(oshp)).astype(np.complex64)
+
+    def L_ref(z):
+        uu = u.astype(np.complex128)
+        out = o.VCZT(uu[0], uu[1], x, x, lam, z, xo, yo) if vect else o.CZT(uu, x, x, lam, z, xo, yo)
+        return float(np.real(np.sum(np.conj(ct) * out)))
+    eps = 2e-5
+    gz_ref = (8 * (L_ref(z0 + eps) - L_ref(z0 - eps)) - (L_ref(z0 + 2 * eps) - L_ref(z0 - 2 * eps))) / (12 * eps)
+    ut = torch.tensor(u, device="cuda", requires_grad=True)
+    zt = torch.tensor([z0], dtype=torch.float64, device="cuda", requires_grad=True)
+    ctt = torch.tensor(ct, device="cuda")
+    out = ops.vczt(ut, None, zt, lam, x, x, xo, yo) if vect else ops.czt(ut, zt, lam, x, x, xo, yo)
+    gu, gz = torch.autograd.grad((ctt.conj() * out).real.sum(), (ut, zt))
+    out0 = ops.vczt(ut, None, z0, lam, x, x, xo, yo) if vect else ops.czt(ut, z0, lam, x, x, xo, yo)
+    (gu0,) = torch.autograd.grad((ctt.conj() * out0).real.sum(), (ut,))
+    print("CZT d/dz on device:", "vect" if vect else "scalar", float(gz), gz_ref, abs(float(gz) - gz_ref) / abs(gz_ref))
+    assert abs(float(gz) - gz_ref) < 1e-4 * abs(gz_ref)
+    assert rel_l2(gu.cpu().numpy(), gu0.cpu().numpy()) < 1e-6

@@ -45,6 +45,8 @@ SIGNATURES = {
     "xl_czt_tables_bytes": (_sz, [_i, _i, _i]),
     "xl_czt_fwd": (_i, [_vp, _vp, _vp, _d, _i, _i, _i, _i, _d, _d, _d, _d, _d, _d, _d, _d, _i, _vp, _vp, _sz, _vp]),
     "xl_czt_bwd": (_i, [_vp, _vp, _vp, _d, _i, _i, _i, _i, _d, _d, _d, _d, _d, _d, _d, _d, _i, _vp, _vp, _sz, _vp]),
+    "xl_czt_workspace_bytes_z": (_sz, [_i, _i, _i, _i]),
+    "xl_czt_bwd_z": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _d, _i, _i, _i, _i, _d, _d, _d, _d, _d, _d, _d, _d, _i, _vp, _vp, _sz, _vp]),
     "xl_highna_workspace_bytes": (_sz, [_i, _i, _i]),
     "xl_highna_tables_bytes": (_sz, [_i, _i, _i]),
     "xl_highna_fwd": (_i, [_vp, _vp, _i, _i, _i, _d, _d, _d, _d, _d, _d, _d, _d, _d, _d, _d, _i, _vp, _vp, _sz, _vp]),

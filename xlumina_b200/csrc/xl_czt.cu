@@ -196,7 +196,7 @@ static int czt_axis_launch(const XlCztParams& a, XlDim grid, xl_stream_t st) {
     return xl_fail(XL_E_BAD_ARG, "czt: unsupported prologue/epilogue combination%s", "");
 }
 
-static int czt_forward(const CztCall& cc, const void* in, void* out, void* tables, void* ws, size_t ws_bytes, xl_stream_t st) {
+static int czt_forward(const CztCall& cc, const void* in, void* out, void* tables, void* ws, size_t ws_bytes, xl_stream_t st, int in_weight = 0) {
     if (!in || !out) return xl_fail(XL_E_BAD_ARG, "czt_fwd: null pointer%s", "");
     if (cc.mode != 2 && !cc.z) return xl_fail(XL_E_BAD_ARG, "czt_fwd: null z%s", "");
     CztPlan pl;
@@ -219,6 +219,7 @@ static int czt_forward(const CztCall& cc, const void* in, void* out, void* table
     a.gpro = XlGridFactor{cc.x0, cc.dx, cc.y0, cc.dy, 0};
     a.tpro = fac_tab(pl, 0);
     a.epi = XL_EPI_NONE;
+    a.in_weight = in_weight;
     // pass 2: Bluestein along x for every column of the intermediate
     XlCztParams b;
     czt_common_params(b, cc, tw);
@@ -288,6 +289,45 @@ static int czt_backward(const CztCall& cc, const void* ct_out, void* ct_in, void
     return xl_launch<XlFold>(XlDim{(int)((NN + XlFold::NT - 1) / XlFold::NT), 1}, st, f);
 }
 
+// Field VJP + d/dz (XlCztDotZ, xl_kernels.cuh): the backward chain, two more forward chains on index-weighted inputs, one
+// pointwise reduction.  CZT / VCZT only (the high-NA focus has no distance).
+static int czt_backward_z(const CztCall& cc, const void* in, const void* out, const void* ct_out, void* ct_in, double* grad_z,
+                          void* tables, void* ws, size_t ws_bytes, xl_stream_t st) {
+    if (!in || !out || !grad_z) return xl_fail(XL_E_BAD_ARG, "czt_bwd_z: null pointer%s", "");
+    if (cc.mode == 2) return xl_fail(XL_E_BAD_ARG, "czt_bwd_z: the high-NA focus has no propagation distance%s", "");
+    const int N = cc.N, Mx = cc.Mx, My = cc.My, ncomp = cc.mode == 0 ? 1 : 3;
+    const size_t base = czt_ws_bytes(N, Mx, My, ncomp), plane = align_up((size_t)ncomp * My * Mx * sizeof(cf));
+    if (!base || ws_bytes < base + 2 * plane) return xl_fail(XL_E_WORKSPACE, "czt_bwd_z: workspace too small%s", "");
+    int rc = czt_backward(cc, ct_out, ct_in, tables, ws, ws_bytes, st);
+    if (rc) return rc;
+    cf* O1 = (cf*)((char*)ws + base);
+    cf* O2 = (cf*)((char*)ws + base + plane);
+    CztCall cf_ = cc;
+    cf_.flags = XL_REUSE_TABLES;
+    rc = czt_forward(cf_, in, O1, tables, ws, ws_bytes, st, 1);   // A(k_y U): the position index of the first (y) pass
+    if (rc) return rc;
+    rc = czt_forward(cf_, in, O2, tables, ws, ws_bytes, st, 2);   // A(k_x U): its line index
+    if (rc) return rc;
+    CztPlan pl;
+    rc = czt_plan(pl, cc, tables, ws, ws_bytes);
+    if (rc) return rc;
+    XlCztDotZParams d;
+    memset(&d, 0, sizeof(d));
+    d.N = N; d.Mx = Mx; d.My = My; d.ncomp = ncomp;
+    d.flags = (cc.flags & XL_CONJ_IN) | (cc.mode == 0 ? (cc.flags & XL_CONJ_OUT) : 0);
+    d.ct_out = (const cf*)ct_out; d.out = (const cf*)out; d.O1 = O1; d.O2 = O2;
+    d.ct_in = cc.mode == 0 ? (const cf*)ct_in : pl.tmp3;
+    d.in = (const cf*)in; d.z = cc.z; d.k = cc.k;
+    d.lambda_over_dx = cc.lambda / cc.dx; d.dDm_dz = cc.lambda / cc.dx;      // Dm = lambda z / dx, wave_optics.py:322
+    d.ay = XlCztAxisDz{cc.yout0, (cc.youtl - cc.yout0) / My, N};
+    d.ax = XlCztAxisDz{cc.xout0, (cc.xoutl - cc.xout0) / Mx, N};
+    d.x0 = cc.x0; d.dx = cc.dx; d.y0 = cc.y0; d.dy = cc.dy;
+    d.xo0 = cc.xout0; d.dxo = (cc.xoutl - cc.xout0) / (Mx - 1); d.yo0 = cc.yout0; d.dyo = (cc.youtl - cc.yout0) / (My - 1);
+    d.gz = grad_z;
+    const size_t n = (size_t)ncomp * ((size_t)My * Mx > (size_t)N * N ? (size_t)My * Mx : (size_t)N * N);
+    return xl_launch<XlCztDotZ>(XlDim{pointwise_grid(n, XlCztDotZ::NT), 1}, st, d);
+}
+
 static CztCall make_czt_call(int mode, const double* z, double lambda, int N, int Mx, int My,
                              double x0, double dx, double y0, double dy, double xout0, double xoutl, double yout0, double youtl,
                              double R, double f, int flags) {
@@ -312,6 +352,18 @@ extern "C" int xl_czt_bwd(const void* ct_out, void* ct_in, const double* z, doub
                           int flags, void* tables, void* ws, size_t ws_bytes, void* stream) {
     CztCall c = make_czt_call(vectorial ? 1 : 0, z, lambda, N, Mx, My, x0, dx, y0, dy, xout0, xoutl, yout0, youtl, 0, 0, flags);
     return czt_backward(c, ct_out, ct_in, tables, ws, ws_bytes, (xl_stream_t)stream);
+}
+extern "C" size_t xl_czt_workspace_bytes_z(int N, int Mx, int My, int vectorial) {
+    const int ncomp = vectorial ? 3 : 1;
+    const size_t base = czt_ws_bytes(N, Mx, My, ncomp);
+    return base ? base + 2 * align_up((size_t)ncomp * My * Mx * sizeof(cf)) : 0;
+}
+extern "C" int xl_czt_bwd_z(const void* in, const void* out, const void* ct_out, void* ct_in, double* grad_z,
+                            const double* z, double lambda, int N, int Mx, int My, int vectorial,
+                            double x0, double dx, double y0, double dy, double xout0, double xoutl, double yout0, double youtl,
+                            int flags, void* tables, void* ws, size_t ws_bytes, void* stream) {
+    CztCall c = make_czt_call(vectorial ? 1 : 0, z, lambda, N, Mx, My, x0, dx, y0, dy, xout0, xoutl, yout0, youtl, 0, 0, flags);
+    return czt_backward_z(c, in, out, ct_out, ct_in, grad_z, tables, ws, ws_bytes, (xl_stream_t)stream);
 }
 extern "C" int xl_highna_fwd(const void* exy, void* out, int N, int Mx, int My, double radius, double f, double lambda,
                              double x0, double dx, double y0, double dy, double xout0, double xoutl, double yout0, double youtl,

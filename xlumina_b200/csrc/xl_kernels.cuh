@@ -734,6 +734,7 @@ struct XlCztParams {
     const cf* pre; const cf* ft; const cf* post;
     const cf* tw;
     int pro, epi;          // host-side selectors of the compiled <PRO, EPI> variant
+    int in_weight;         // d/dz chains (xl_czt_bwd_z): multiply the input by its position index (1) or its line index (2)
     XlGridFactor gpro, gepi;
     XlFacTab tpro, tepi;  // factor tables of the prologue / epilogue (czt_tables)
     const double* z;      // device scalar (RSF / VCZT factors), may be null
@@ -836,6 +837,7 @@ template <int L, int PRO, int EPI, int ACC> struct XlCztOp : XlOpBase {
                     x = cf_lin2(a[l], ax, b[l], ay);
                 }
             }
+            if (p.in_weight) x = cf_scale(x, (float)(p.in_weight == 1 ? i : line));   // kernel-uniform
             x = cf_mul(x, pre);
             v[l * stride] = (ok_i && line < p.nlines) ? x : cf_zero();
         }
@@ -1084,6 +1086,107 @@ struct XlDotZ {
         xl_block_sum<NT>(red);
         XL_THREADS(tid, NT) {
             if (tid == 0) xl_atomic_add(p.gz, -p.k * red[0]);
+        }
+    }
+};
+
+// ==================================================================================================================
+// d/dz of CZT / VCZT.  JAX differentiates CZT_jit through F, F0, the constant z dx dy lambda and, via
+// Dm = lambda z / dx, through every Bluestein chirp (wave_optics.py:322, 340-355, 393-403).  In closed form the transform of
+// one axis is K[l,k] = exp(i Phi(l,k)) on its valid entries, with (the off-by-one slice included)
+//     Phi = theta ((l+1) k - l - 1/2) - 2 pi k D1/Dm - 2 pi f_l (1/2 - m/2)/Dm,   theta = -2 pi Delta/Dm (principal branch),
+//     D1 = out0 + Dm + Delta/2,  f_l = l Delta + D1,  Delta = (out_last - out0)/M,
+// so   dPhi/dDm = alpha l k + beta k + gamma l + delta   is bilinear in (l, k):
+//     alpha = 2 pi Delta/Dm^2,  beta = 2 pi (out0 + 3 Delta/2)/Dm^2,  gamma = -pi Delta (m+1)/Dm^2,
+//     delta = 2 pi (-Delta/2 + (1/2 - m/2)(out0 + Delta/2))/Dm^2.
+// With A the whole forward operator (out = A U), O1 = A(k_y U) and O2 = A(k_x U) (two more forward chains with an index
+// weight on the input, XlCztParams::in_weight) give
+//     d out/dz = out [d ln F0/dz + 1/z + i Dm' (gamma_y l_y + delta_y + gamma_x l_x + delta_x)]
+//              + i Dm' [(alpha_y l_y + beta_y) O1 + (alpha_x l_x + beta_x) O2]  +  A((d ln F/dz) U),        Dm' = lambda/dx,
+// and the last term is folded onto the input side with the field cotangent:  sum ct_out A(D U) = sum ct_in D U.
+// This kernel forms  gz += Re[ sum_out ct_out (...) + sum_in ct_in (d ln F/dz) U ]  in fp64 (+ the dEz/dz term of VCZT).
+// ==================================================================================================================
+// d ln h / dz of the RS factor h = (1/2pi)(z/r^2)(1/r - i k) exp(sgn(z) i k r)   (wave_optics.py:291-297)
+XL_DEV void xl_rs_dlnh(double X, double Y, double z, double k, double* re, double* im) {
+    const double r2 = X * X + Y * Y + z * z, r = sqrt(r2), ir = 1.0 / r;
+    // d/dz ln(1/r - i k) = (-z/r^3) / (1/r - i k) = (-z/r^3) (1/r + i k) / (1/r^2 + k^2)
+    const double q = -z * ir * ir * ir / (ir * ir + k * k);
+    const double sg = z > 0 ? 1.0 : -1.0;
+    *re = 1.0 / z - 2.0 * z / r2 + q * ir;
+    *im = q * k + sg * k * z * ir;
+}
+struct XlCztAxisDz { double out0, Delta; int m; };
+struct XlCztDotZParams {
+    int N, Mx, My, ncomp, flags;   // XL_F_CONJ_IN: ct_out is conjugated on load; XL_F_CONJ_OUT: ct_in was stored conjugated
+    const cf* ct_out; const cf* out; const cf* O1; const cf* O2;   // [ncomp][My][Mx]
+    const cf* ct_in;     // [ncomp][N][N] cotangent of the component planes (scalar: the caller's ct_in; vectorial: before the fold)
+    const cf* in;        // [1][N][N] or [2][N][N] = Ex, Ey
+    const double* z; double k, dDm_dz, lambda_over_dx;
+    XlCztAxisDz ay, ax;
+    double x0, dx, y0, dy, xo0, dxo, yo0, dyo;
+    double* gz;
+};
+struct XlCztDotZ {
+    static const char* name() { return "czt_dot_z"; }
+    typedef XlCztDotZParams Params;
+    static constexpr int NT = 256;
+    static size_t smem() { return NT * sizeof(double); }
+    XL_DEV static void run(const Params& p, cf* s) {
+        double* red = (double*)s;
+        const double z = xl_ldg(p.z), Dm = p.lambda_over_dx * z, w = 6.283185307179586 / (Dm * Dm);
+        const double a_y = w * p.ay.Delta, b_y = w * (p.ay.out0 + 1.5 * p.ay.Delta), g_y = -0.5 * w * p.ay.Delta * (p.ay.m + 1),
+                     d_y = w * (-0.5 * p.ay.Delta + (0.5 - 0.5 * p.ay.m) * (p.ay.out0 + 0.5 * p.ay.Delta));
+        const double a_x = w * p.ax.Delta, b_x = w * (p.ax.out0 + 1.5 * p.ax.Delta), g_x = -0.5 * w * p.ax.Delta * (p.ax.m + 1),
+                     d_x = w * (-0.5 * p.ax.Delta + (0.5 - 0.5 * p.ax.m) * (p.ax.out0 + 0.5 * p.ax.Delta));
+        const size_t MM = (size_t)p.My * p.Mx, NN = (size_t)p.N * p.N;
+        XL_THREADS(tid, NT) {
+            const size_t e = (size_t)XL_BLOCK_X * NT + tid;
+            double acc = 0.0;
+            if (e < MM * p.ncomp) {                                   // output side
+                const size_t o = e % MM;
+                const int ly = (int)(o / p.Mx), lx = (int)(o % p.Mx);
+                double cr = (double)p.ct_out[e].x, ci = (double)p.ct_out[e].y;
+                if (p.flags & XL_F_CONJ_IN) ci = -ci;
+                double fr, fi;
+                xl_rs_dlnh(p.xo0 + lx * p.dxo, p.yo0 + ly * p.dyo, z, p.k, &fr, &fi);
+                fr += 1.0 / z;
+                fi += p.dDm_dz * (g_y * ly + d_y + g_x * lx + d_x);
+                const double w1 = p.dDm_dz * (a_y * ly + b_y), w2 = p.dDm_dz * (a_x * lx + b_x);
+                const cf u = p.out[e], o1 = p.O1[e], o2 = p.O2[e];
+                // t = out (fr + i fi) + i (w1 O1 + w2 O2)
+                const double tr = (double)u.x * fr - (double)u.y * fi - (w1 * (double)o1.y + w2 * (double)o2.y);
+                const double ti = (double)u.x * fi + (double)u.y * fr + (w1 * (double)o1.x + w2 * (double)o2.x);
+                acc += cr * tr - ci * ti;                             // Re(ct * t)
+            }
+            if (e < NN * p.ncomp) {                                   // input side
+                const int c = (int)(e / NN);
+                const size_t o = e % NN;
+                const int iy = (int)(o / p.N), ix = (int)(o % p.N);
+                const double X = p.x0 + ix * p.dx, Y = p.y0 + iy * p.dy;
+                double cr = (double)p.ct_in[e].x, ci = (double)p.ct_in[e].y;
+                if (p.flags & XL_F_CONJ_OUT) ci = -ci;
+                double ur, ui, er = 0.0, ei = 0.0;                    // component plane U_c and (c == 2) dEz/dz
+                if (c < 2) {
+                    ur = (double)p.in[e].x; ui = (double)p.in[e].y;
+                } else {                                              // Ez = (Ex X + Ey Y) z / r^2, vectorized_optics.py:341-344
+                    const cf ex = p.in[o], ey = p.in[NN + o];
+                    const double ir2 = 1.0 / (X * X + Y * Y + z * z);
+                    const double sr = (double)ex.x * X + (double)ey.x * Y, si = (double)ex.y * X + (double)ey.y * Y;
+                    ur = sr * z * ir2; ui = si * z * ir2;
+                    const double dz = ir2 - 2.0 * z * z * ir2 * ir2;
+                    er = sr * dz; ei = si * dz;
+                }
+                double fr, fi;
+                xl_rs_dlnh(X, Y, z, p.k, &fr, &fi);
+                const double tr = ur * fr - ui * fi + er, ti = ur * fi + ui * fr + ei;
+                acc += cr * tr - ci * ti;
+            }
+            red[tid] = acc;
+        }
+        XL_SYNC();
+        xl_block_sum<NT>(red);
+        XL_THREADS(tid, NT) {
+            if (tid == 0) xl_atomic_add(p.gz, red[0]);
         }
     }
 };

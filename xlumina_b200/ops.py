@@ -448,20 +448,30 @@ class _CZT(torch.autograd.Function):
         tables = torch.empty(L.xl_czt_tables_bytes(N, Mx, My), dtype=torch.uint8, device=fin.device)
         _lib.check(L.xl_czt_fwd(_ptr(fin), _ptr(out), _ptr(z), lam, N, Mx, My, vect, x0, dx, y0, dy, xo0, xol, yo0, yol, 0,
                                 _ptr(tables), _ptr(ws), ws.numel(), _stream(fin)), "xl_czt_fwd")
-        ctx.save_for_backward(z, tables)
+        want_z = ctx.needs_input_grad[1]
+        ctx.save_for_backward(z, tables, *((fin, out) if want_z else ()))   # d/dz needs the primal input and result
         ctx.meta = (lam, vect, gin, gout, N, fin.shape)
         return out
 
     @staticmethod
     @_on_device
     def backward(ctx, g):
-        z, tables = ctx.saved_tensors
+        z, tables = ctx.saved_tensors[:2]
         lam, vect, gin, gout, N, shape = ctx.meta
         (x0, dx, y0, dy) = gin
         (xo0, xol, Mx, yo0, yol, My) = gout
         L = _lib.lib()
         g = g.resolve_conj().contiguous()
         ct = torch.empty(shape, dtype=g.dtype, device=g.device)
+        if ctx.needs_input_grad[1]:
+            fin, out = ctx.saved_tensors[2:]
+            gz = torch.zeros(1, dtype=torch.float64, device=g.device)
+            ws = _workspace(g, L.xl_czt_workspace_bytes_z(N, Mx, My, vect))
+            _lib.check(L.xl_czt_bwd_z(_ptr(fin), _ptr(out), _ptr(g), _ptr(ct), _ptr(gz), _ptr(z), lam, N, Mx, My, vect,
+                                      x0, dx, y0, dy, xo0, xol, yo0, yol,
+                                      _lib.XL_CONJ_IN | _lib.XL_CONJ_OUT | _lib.XL_REUSE_TABLES, _ptr(tables), _ptr(ws), ws.numel(),
+                                      _stream(g)), "xl_czt_bwd_z")
+            return ct, gz, None, None, None, None
         ws = _workspace(g, L.xl_czt_workspace_bytes(N, Mx, My, vect))
         _lib.check(L.xl_czt_bwd(_ptr(g), _ptr(ct), _ptr(z), lam, N, Mx, My, vect, x0, dx, y0, dy, xo0, xol, yo0, yol,
                                 _lib.XL_CONJ_IN | _lib.XL_CONJ_OUT | _lib.XL_REUSE_TABLES, _ptr(tables), _ptr(ws), ws.numel(),
@@ -542,15 +552,14 @@ def _gin(x, y, N):
 
 
 def czt(field, z, wavelength, x, y, xout, yout):
-    """Scalar chirped z-transform propagation (N,N) -> (len(yout), len(xout)); differentiable in `field`.
+    """Scalar chirped z-transform propagation (N,N) -> (len(yout), len(xout)); differentiable in `field` and `z`.
     A leading batch axis (B,N,N) is propagated item by item (z shared or one per item)."""
     if field.dim() == 3:
         zs = _z_per_item(z, field.shape[0])
         return torch.stack([czt(field[i], z if zs is None else zs[i], wavelength, x, y, xout, yout) for i in range(field.shape[0])])
-    _refuse_z_gradient(z, "czt")
     dt = field.dtype
     f = _c64(field)
-    out = _CZT.apply(f, _as_z(z, f).detach(), float(wavelength), 0, _gin(x, y, f.shape[-1]), _gout(xout, yout))
+    out = _CZT.apply(f, _as_z(z, f), float(wavelength), 0, _gin(x, y, f.shape[-1]), _gout(xout, yout))
     return out if dt == torch.complex64 or not torch.is_complex(field) else out.to(dt)
 
 
@@ -559,10 +568,9 @@ def vczt(Ex, Ey, z, wavelength, x, y, xout, yout):
     Pass Ey=None if `Ex` is already the stacked (2,N,N) pair; a leading batch axis gives (B,3,...)."""
     if Ex.dim() == (4 if Ey is None else 3):
         return _batch_of_pairs(lambda a, b, zz, hs: vczt(a, b, zz, wavelength, x, y, xout, yout), Ex, Ey, z)
-    _refuse_z_gradient(z, "vczt")
     dt = Ex.dtype
     exy = _c64(Ex) if Ey is None else torch.stack([_c64(Ex), _c64(Ey)], dim=0)
-    out = _CZT.apply(exy, _as_z(z, exy).detach(), float(wavelength), 1, _gin(x, y, exy.shape[-1]), _gout(xout, yout))
+    out = _CZT.apply(exy, _as_z(z, exy), float(wavelength), 1, _gin(x, y, exy.shape[-1]), _gout(xout, yout))
     return out if dt == torch.complex64 or not torch.is_complex(Ex) else out.to(dt)
 
 
