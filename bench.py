@@ -504,10 +504,10 @@ def run_extra(args, rank, local_rank, world, dev):
     torch.cuda.empty_cache()
     try:
         ff = importlib.import_module("four_f_sharded")
-        step4, params4, mine = ff.setup(64, 1024, dev, rank, world)
+        step4, params4, mine = ff.setup(64, 1024, dev, rank, world, fused=True, graph=True)
         ms4 = timed(step4, 5, 2)
         out["cfg4_four_f_batch64_1024"] = {"value": 1e3 / ms4, "unit": "steps/s", "ms_per_step": ms4, "samples_per_rank": mine,
-                                           "propagations_per_s": 3 * 64 * 1e3 / ms4, "scaling": "strong (global batch fixed)",
+                                           "propagations_per_s": 3 * 64 * 1e3 / ms4, "scaling": "strong (global batch fixed)", "fused_elements": True, "cuda_graphs": True,
                                            "collective": "one flattened all-reduce of the shared-parameter gradients per step" if world > 1 else "none (1 GPU)"}
         del step4, params4
     except Exception as e:   # noqa: BLE001

@@ -62,7 +62,7 @@ def forward_loss(params, masks, targets, beam, dx, k, fused=True):
     return four_f.MSE_Intensity(inten, targets).sum()
 
 
-def setup(batch, n, dev, rank, world, fused=True):
+def setup(batch, n, dev, rank, world, fused=True, graph=False):
     """Build the sharded optimizer problem on `dev`; returns (step, params, samples_on_this_rank).  step() runs one optimizer
     step (forward, backward, one flattened gradient all-reduce when world > 1, AdamW) and returns this rank's loss share."""
     N, lam = n, 0.6328
@@ -82,13 +82,40 @@ def setup(batch, n, dev, rank, world, fused=True):
     for p in params:
         p.grad = torch.zeros_like(p)
 
-    def step():
+    def compute():
         opt.zero_grad(set_to_none=False)
         loss = forward_loss(params, masks, targets, beam, dx, k, fused) / batch    # mean over the GLOBAL batch
         loss.backward()
+        return loss.detach()
+
+    def step():
+        loss = compute()
         allreduce_grads([p.grad for p in params])
         opt.step()
-        return loss.detach()
+        return loss
+
+    if graph:
+        # Forward + backward of this rank's slice as ONE CUDA graph and AdamW as a second one (the library neither allocates nor
+        # synchronises in steady state, so it captures as is); the gradient all-reduce stays an eager NCCL call between them.
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                compute()
+                opt.step()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        g_compute, g_opt = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g_compute):
+            static_loss = compute()
+        with torch.cuda.graph(g_opt):
+            opt.step()
+
+        def step():   # noqa: F811
+            g_compute.replay()
+            allreduce_grads([p.grad for p in params])
+            g_opt.replay()
+            return static_loss
 
     return step, params, b - a
 
@@ -100,8 +127,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--unfused", action="store_true", help="pointwise elements and the loss as separate torch operations")
-    ap.add_argument("--graph", action="store_true", help="single GPU only: capture the whole optimizer step in ONE CUDA graph "
-                    "and replay it (the library neither allocates nor synchronises in steady state, so it captures as is)")
+    ap.add_argument("--graph", action="store_true", help="replay forward+backward and AdamW as CUDA graphs (the all-reduce stays eager)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -111,31 +137,13 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     N = args.n
-    step, params, mine = setup(args.batch, N, dev, rank, world, fused=not args.unfused)
+    step, params, mine = setup(args.batch, N, dev, rank, world, fused=not args.unfused, graph=args.graph)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    if args.graph and world == 1:
-        # The whole optimizer step (3 RS forward, 3 backward with d/dz and AdamW) as ONE CUDA graph: measured 3.59 -> 3.22 ms
-        # per step at 8 samples per GPU.  Single GPU only: capturing the NCCL all-reduce hung in round 1 (not investigated).
-        side = torch.cuda.Stream(device=dev)
-        side.wait_stream(torch.cuda.current_stream(dev))
-        with torch.cuda.stream(side):
-            for _ in range(3):
-                step()
-        torch.cuda.current_stream(dev).wait_stream(side)
-        barrier()
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
-            static_loss = step()
-        eager_step = step
-
-        def step():   # noqa: F811
-            graph.replay()
-            return static_loss
     for _ in range(args.warmup):
         step()
     barrier()
@@ -155,7 +163,7 @@ def main():
         print(json.dumps({"metric": "4f optimizer steps/s (batch %d, %d^2, 3 RS fwd+grad per sample, shared parameters)" % (args.batch, N),
                           "value": 1e3 / ms, "unit": "steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                           "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "samples_per_rank": mine,
-                          "propagations_per_s": 3 * args.batch * 1e3 / ms, "loss": float(lsum), "fused_elements": not args.unfused,
+                          "propagations_per_s": 3 * args.batch * 1e3 / ms, "loss": float(lsum), "fused_elements": not args.unfused, "cuda_graphs": bool(args.graph),
                           "collective": "one all-reduce of 2*N^2 fp32 + 3 fp64 gradients per step"}), flush=True)
     if world > 1:
         dist.destroy_process_group()
