@@ -67,7 +67,7 @@ static ffi::Error VrsFwd(cudaStream_t stream, ffi::ScratchAllocator scratch, C64
   const int n = Side(exy);
   const size_t wsb = xl_rs_workspace_bytes(n, 3, 0);
   XL_SCRATCH(ws, wsb);
-  return Status(xl_vrs_fwd(exy.typed_data(), out->typed_data(), H->typed_data(), z.typed_data(), n, x0, y0, dx, dy, k, 0, ws, wsb, stream));
+  return Status(xl_vrs_fwd(exy.typed_data(), nullptr, out->typed_data(), H->typed_data(), z.typed_data(), n, x0, y0, dx, dy, k, 0, ws, wsb, stream));
 }
 static ffi::Error VrsBwd(cudaStream_t stream, ffi::ScratchAllocator scratch, C64 exy, C64 primal_out, C64 ct_out, U8 H, F64 z,
                          double x0, double y0, double dx, double dy, double k, Res<C64> ct_exy, Res<F64> ct_z) {
@@ -76,7 +76,7 @@ static ffi::Error VrsBwd(cudaStream_t stream, ffi::ScratchAllocator scratch, C64
   XL_SCRATCH(ws, wsb);
   if (cudaMemsetAsync(ct_z->typed_data(), 0, sizeof(double), stream) != cudaSuccess)
     return ffi::Error(ffi::ErrorCode::kInternal, "xlprop: cudaMemsetAsync");
-  return Status(xl_vrs_bwd(exy.typed_data(), primal_out.typed_data(), ct_out.typed_data(), ct_exy->typed_data(), ct_z->typed_data(),
+  return Status(xl_vrs_bwd(exy.typed_data(), nullptr, primal_out.typed_data(), ct_out.typed_data(), ct_exy->typed_data(), ct_z->typed_data(),
                            H.typed_data(), z.typed_data(), n, x0, y0, dx, dy, k, 0, ws, wsb, stream));
 }
 
@@ -92,7 +92,7 @@ static ffi::Error CztFwd(cudaStream_t stream, ffi::ScratchAllocator scratch, C64
   const size_t wsb = xl_czt_workspace_bytes(n, mx, my, static_cast<int>(vectorial));
   if (wsb == 0) return ffi::Error(ffi::ErrorCode::kInvalidArgument, "xlprop: CZT sizes unsupported (m+M-1 a power of two, or padded length > 4096)");
   XL_SCRATCH(ws, wsb);
-  return Status(xl_czt_fwd(in.typed_data(), out->typed_data(), z.typed_data(), wavelength, n, mx, my, static_cast<int>(vectorial),
+  return Status(xl_czt_fwd(in.typed_data(), nullptr, out->typed_data(), z.typed_data(), wavelength, n, mx, my, static_cast<int>(vectorial),
                            x0, dx, y0, dy, xo0, xol, yo0, yol, 0, ws, wsb, stream));
 }
 static ffi::Error CztBwd(cudaStream_t stream, ffi::ScratchAllocator scratch, C64 ct_out, F64 z, double wavelength, int64_t vectorial,
@@ -116,7 +116,7 @@ static ffi::Error HighnaFwd(cudaStream_t stream, ffi::ScratchAllocator scratch, 
   const size_t wsb = xl_highna_workspace_bytes(n, mx, my);
   if (wsb == 0) return ffi::Error(ffi::ErrorCode::kInvalidArgument, "xlprop: high-NA sizes unsupported");
   XL_SCRATCH(ws, wsb);
-  return Status(xl_highna_fwd(exy.typed_data(), out->typed_data(), n, mx, my, radius, f, wavelength, x0, dx, y0, dy, xo0, xol, yo0, yol,
+  return Status(xl_highna_fwd(exy.typed_data(), nullptr, out->typed_data(), n, mx, my, radius, f, wavelength, x0, dx, y0, dy, xo0, xol, yo0, yol,
                               0, ws, wsb, stream));
 }
 static ffi::Error HighnaBwd(cudaStream_t stream, ffi::ScratchAllocator scratch, C64 ct_out, double radius, double f, double wavelength,

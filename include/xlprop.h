@@ -90,11 +90,14 @@ int xl_rs_bwd(const void* in, const void* out, const void* ct_out, void* ct_in, 
               const double* z, int N, int nfields, double dx, double dy, double k, int flags,
               void* ws, size_t ws_bytes, void* stream);
 
-/* exy = [Ex, Ey] (2,N,N) -> out = [Ex', Ey', Ez'] (3,N,N); Ez = (Ex X + Ey Y)/sqrt(X^2+Y^2+z^2) is formed while loading
- * (vectorized_optics.py:258-261); x0,y0 = first grid coordinates.  Replaces VRS_propagation_jit (:364-373). */
-int xl_vrs_fwd(const void* exy, void* out, void* H, const double* z, int N, double x0, double y0,
+/* (Ex, Ey) (N,N) each -> out = [Ex', Ey', Ez'] (3,N,N); Ez = (Ex X + Ey Y)/sqrt(X^2+Y^2+z^2) is formed while loading
+ * (vectorized_optics.py:258-261); x0,y0 = first grid coordinates.  Replaces VRS_propagation_jit (:364-373).
+ * `ex` and `ey` are the two input planes wherever they live (the elements of an optical table produce them separately, so no
+ * stacking copy is needed); ey == NULL means ey = ex + N*N (a stacked (2,N,N) pair).  The same convention holds for every
+ * vectorial entry point below.  ct_exy is one (2,N,N) buffer = the cotangents of Ex and Ey. */
+int xl_vrs_fwd(const void* ex, const void* ey, void* out, void* H, const double* z, int N, double x0, double y0,
                double dx, double dy, double k, int flags, void* ws, size_t ws_bytes, void* stream);
-int xl_vrs_bwd(const void* exy, const void* out, const void* ct_out, void* ct_exy, double* grad_z, const void* H,
+int xl_vrs_bwd(const void* ex, const void* ey, const void* out, const void* ct_out, void* ct_exy, double* grad_z, const void* H,
                const double* z, int N, double x0, double y0, double dx, double dy, double k, int flags,
                void* ws, size_t ws_bytes, void* stream);
 
@@ -153,8 +156,8 @@ int xl_slab_rows_inv(const void* S, void* out_local, int N, int G, int flags, vo
 void xl_debug_set_max_line(int sub_line_length);
 
 /* ---------------------------------------------------------------- CZT / VCZT -------------------------------- */
-/* vectorial = 0: in (N,N) -> out (My,Mx)            CZT_jit,  wave_optics.py:333-357
- * vectorial = 1: in = [Ex,Ey] (2,N,N) -> out (3,My,Mx); Ez = ((Ex X + Ey Y)/r) z/r   VCZT, vectorized_optics.py:341-344,375-384
+/* vectorial = 0: in (N,N) -> out (My,Mx); ey ignored         CZT_jit,  wave_optics.py:333-357
+ * vectorial = 1: in = Ex, ey = Ey (NULL: in + N*N) -> out (3,My,Mx); Ez = ((Ex X + Ey Y)/r) z/r   VCZT, vectorized_optics.py:341-344,375-384
  * Input grid: x_j = x0 + j dx, y_i = y0 + i dy.  Output grid: Mx samples from xout0 to xoutl, My from yout0 to youtl.
  * Dm = lambda*z/dx (wave_optics.py:322).
  * `tables` is a caller-owned buffer of xl_czt_tables_bytes() bytes (opaque, like H of the RS path): the Bluestein chirps and
@@ -163,7 +166,7 @@ void xl_debug_set_max_line(int sub_line_length);
  * XL_REUSE_TABLES to the backward call (same sizes, grids, z).  `ws` is scratch (xl_czt_workspace_bytes()). */
 size_t xl_czt_workspace_bytes(int N, int Mx, int My, int vectorial);
 size_t xl_czt_tables_bytes(int N, int Mx, int My);
-int xl_czt_fwd(const void* in, void* out, const double* z, double lambda, int N, int Mx, int My, int vectorial,
+int xl_czt_fwd(const void* in, const void* ey, void* out, const double* z, double lambda, int N, int Mx, int My, int vectorial,
                double x0, double dx, double y0, double dy, double xout0, double xoutl, double yout0, double youtl,
                int flags, void* tables, void* ws, size_t ws_bytes, void* stream);
 /* VJP with respect to the input field(s) (z, lambda and the grids are static in every reference caller; xl_czt_bwd_z below
@@ -178,20 +181,20 @@ int xl_czt_bwd(const void* ct_out, void* ct_in, const double* z, double lambda, 
  * larger (xl_czt_workspace_bytes_z): two more forward chains run on index-weighted inputs (the chirp-z kernel of an axis is
  * exp(i Phi(l,k)) with dPhi/dDm bilinear in the output and input index). */
 size_t xl_czt_workspace_bytes_z(int N, int Mx, int My, int vectorial);
-int xl_czt_bwd_z(const void* in, const void* out, const void* ct_out, void* ct_in, double* grad_z,
+int xl_czt_bwd_z(const void* in, const void* ey, const void* out, const void* ct_out, void* ct_in, double* grad_z,
                  const double* z, double lambda, int N, int Mx, int My, int vectorial,
                  double x0, double dx, double y0, double dy, double xout0, double xoutl, double yout0, double youtl,
                  int flags, void* tables, void* ws, size_t ws_bytes, void* stream);
 
 /* ---------------------------------------------------------------- high-NA objective ------------------------- */
-/* exy = [Ex,Ey] (2,N,N) -> out = [Ex,Ey,Ez] (3,My,Mx) in the focal plane:
+/* (Ex, Ey) (ey == NULL: ex + N*N) -> out = [Ex,Ey,Ez] (3,My,Mx) in the focal plane:
  *   -i sin^2(theta_max)/(f lambda) * Bluestein_x(Bluestein_y( apod*G*RL(theta,phi) (Ex,Ey,Ez)^T )),  Dm = f lambda (N-1)/(2R).
  * optical_elements.py:515-672.  `tables` (xl_highna_tables_bytes()) holds the Bluestein tables and the lens matrix
  * apod*G*RL sampled on the input grid; it depends on the sizes, grids, radius, f and lambda only, so one buffer serves
  * every call of an optical table that uses the same objective (XL_REUSE_TABLES). */
 size_t xl_highna_workspace_bytes(int N, int Mx, int My);
 size_t xl_highna_tables_bytes(int N, int Mx, int My);
-int xl_highna_fwd(const void* exy, void* out, int N, int Mx, int My, double radius, double f, double lambda,
+int xl_highna_fwd(const void* ex, const void* ey, void* out, int N, int Mx, int My, double radius, double f, double lambda,
                   double x0, double dx, double y0, double dy, double xout0, double xoutl, double yout0, double youtl,
                   int flags, void* tables, void* ws, size_t ws_bytes, void* stream);
 int xl_highna_bwd(const void* ct_out, void* ct_exy, int N, int Mx, int My, double radius, double f, double lambda,

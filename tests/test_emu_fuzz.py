@@ -58,7 +58,7 @@ def test_czt_forward_random(emu, N, Mx, My, half, frac, zmag, seed):
     ws = np.zeros(emu.xl_czt_workspace_bytes(N, Mx, My, 0), np.uint8)
     tb = np.zeros(emu.xl_czt_tables_bytes(N, Mx, My), np.uint8)
     zz = np.array([zmag])
-    rc = emu.xl_czt_fwd(ptr(c64(f)), ptr(out), ptr(zz), 0.6328, N, Mx, My, 0, x[0], x[1] - x[0], x[0], x[1] - x[0],
+    rc = emu.xl_czt_fwd(ptr(c64(f)), None, ptr(out), ptr(zz), 0.6328, N, Mx, My, 0, x[0], x[1] - x[0], x[0], x[1] - x[0],
                         xo[0], xo[-1], yo[0], yo[-1], 0, ptr(tb), ptr(ws), ws.size, None)
     assert rc == 0, emu.xl_last_error()
     assert rel_l2(out, ref) < TOL

@@ -150,7 +150,7 @@ def test_vectorial_paths_at_2048(emu):
     H = np.zeros(emu.xl_rs_transfer_bytes(N), np.uint8)
     ws = np.zeros(emu.xl_rs_workspace_bytes(N, 3, 0), np.uint8)
     zz = np.array([50000.0])
-    assert emu.xl_vrs_fwd(ptr(exy), ptr(out), ptr(H), ptr(zz), N, x[0], x[0], x[1] - x[0], x[1] - x[0], k, 0, ptr(ws), ws.size, None) == 0
+    assert emu.xl_vrs_fwd(ptr(exy), None, ptr(out), ptr(H), ptr(zz), N, x[0], x[0], x[1] - x[0], x[1] - x[0], k, 0, ptr(ws), ws.size, None) == 0
     ref, _ = o.VRS_propagation(exy[0].astype(np.complex128), exy[1].astype(np.complex128), x, x, lam, 50000.0)
     assert rel_l2(out, ref) < TIGHT
     del out, H, ws, ref
@@ -159,7 +159,7 @@ def test_vectorial_paths_at_2048(emu):
     foc = np.zeros((3, 400, 400), np.complex64)
     ws = np.zeros(emu.xl_highna_workspace_bytes(N, 400, 400), np.uint8)
     tb = np.zeros(emu.xl_highna_tables_bytes(N, 400, 400), np.uint8)
-    assert emu.xl_highna_fwd(ptr(exy), ptr(foc), N, 400, 400, 1800.0, 2000.0, 0.65, x2[0], x2[1] - x2[0], x2[0], x2[1] - x2[0],
+    assert emu.xl_highna_fwd(ptr(exy), None, ptr(foc), N, 400, 400, 1800.0, 2000.0, 0.65, x2[0], x2[1] - x2[0], x2[0], x2[1] - x2[0],
                              xo[0], xo[-1], xo[0], xo[-1], 0, ptr(tb), ptr(ws), ws.size, None) == 0, emu.xl_last_error()
     fref = o.VCZT_objective_lens(exy[0].astype(np.complex128), exy[1].astype(np.complex128), x2, x2, 0.65, 1800.0, 2000.0, xo, xo)
     assert rel_l2(foc, fref) < TIGHT
@@ -186,11 +186,11 @@ def test_vrs_forward_and_vjp_golden(emu, name):
     ws = np.zeros(emu.xl_rs_workspace_bytes(N, 3, 1), np.uint8)
     zz = np.array([z])
     k = 2 * np.pi / lam
-    assert emu.xl_vrs_fwd(ptr(exy), ptr(out), ptr(H), ptr(zz), N, x[0], y[0], x[1] - x[0], y[1] - y[0], k, 0, ptr(ws), ws.size, None) == 0
+    assert emu.xl_vrs_fwd(ptr(exy), None, ptr(out), ptr(H), ptr(zz), N, x[0], y[0], x[1] - x[0], y[1] - y[0], k, 0, ptr(ws), ws.size, None) == 0
     assert rel_l2(out, g["out"]) < TIGHT
     gin = np.zeros((2, N, N), np.complex64)
     gz = np.zeros(1)
-    assert emu.xl_vrs_bwd(ptr(exy), ptr(out), ptr(c64(g["ct"])), ptr(gin), ptr(gz), ptr(H), ptr(zz), N, x[0], y[0], x[1] - x[0], y[1] - y[0],
+    assert emu.xl_vrs_bwd(ptr(exy), None, ptr(out), ptr(c64(g["ct"])), ptr(gin), ptr(gz), ptr(H), ptr(zz), N, x[0], y[0], x[1] - x[0], y[1] - y[0],
                           k, 0, ptr(ws), ws.size, None) == 0
     if "vjp_field" in g:
         assert rel_l2(gin, g["vjp_field"]) < TIGHT
@@ -205,7 +205,8 @@ def czt_call(emu, fn, a, b, g, vect, flags=0, tables=None):
     if tables is None:
         tables = np.zeros(emu.xl_czt_tables_bytes(N, Mx, My), np.uint8)
     zz = np.array([float(g["z"])])
-    rc = fn(ptr(a), ptr(b), ptr(zz), float(g["wavelength"]), N, Mx, My, vect, x[0], x[1] - x[0], y[0], y[1] - y[0],
+    extra = (None,) if fn is emu.xl_czt_fwd or getattr(fn, "__name__", "") == "xl_czt_fwd" else ()   # forward: (in, ey = NULL: stacked pair)
+    rc = fn(ptr(a), *extra, ptr(b), ptr(zz), float(g["wavelength"]), N, Mx, My, vect, x[0], x[1] - x[0], y[0], y[1] - y[0],
             xo[0], xo[-1], yo[0], yo[-1], flags, ptr(tables), ptr(ws), ws.size, None)
     assert rc == 0, emu.xl_last_error()
     return tables
@@ -283,7 +284,7 @@ def test_vczt_and_highna_odd_output_sizes(emu):
     ws = np.zeros(emu.xl_highna_workspace_bytes(N, Mx, My), np.uint8)
     tb = np.zeros(emu.xl_highna_tables_bytes(N, Mx, My), np.uint8)
     out2 = np.zeros((3, My, Mx), np.complex64)
-    assert emu.xl_highna_fwd(ptr(exy), ptr(out2), N, Mx, My, 350.0, 500.0, 0.635, x[0], x[1] - x[0], x[0], x[1] - x[0],
+    assert emu.xl_highna_fwd(ptr(exy), None, ptr(out2), N, Mx, My, 350.0, 500.0, 0.635, x[0], x[1] - x[0], x[0], x[1] - x[0],
                              xo[0], xo[-1], yo[0], yo[-1], 0, ptr(tb), ptr(ws), ws.size, None) == 0
     assert rel_l2(out2, o.VCZT_objective_lens(ex, ey, x, x, 0.635, 350.0, 500.0, xo, yo)) < TIGHT
 
@@ -322,7 +323,7 @@ def test_highna_forward_and_vjp_golden(emu, name):
     tb = np.zeros(emu.xl_highna_tables_bytes(N, Mx, My), np.uint8)
     geo = (N, Mx, My, float(g["radius"]), float(g["f"]), float(g["wavelength"]), x[0], x[1] - x[0], y[0], y[1] - y[0],
            xo[0], xo[-1], yo[0], yo[-1])
-    assert emu.xl_highna_fwd(ptr(exy), ptr(out), *geo, 0, ptr(tb), ptr(ws), ws.size, None) == 0, emu.xl_last_error()
+    assert emu.xl_highna_fwd(ptr(exy), None, ptr(out), *geo, 0, ptr(tb), ptr(ws), ws.size, None) == 0, emu.xl_last_error()
     assert rel_l2(out, g["out"]) < TIGHT
     if "vjp_field" in g:
         gin = np.zeros((2, N, N), np.complex64)
@@ -339,7 +340,7 @@ def test_highna_odd_n_nan_like_reference(emu):
     out = np.zeros((3, M, M), np.complex64)
     ws = np.zeros(emu.xl_highna_workspace_bytes(N, M, M), np.uint8)
     tb = np.zeros(emu.xl_highna_tables_bytes(N, M, M), np.uint8)
-    assert emu.xl_highna_fwd(ptr(exy), ptr(out), N, M, M, 90.0, 100.0, 0.635, x[0], x[1] - x[0], x[0], x[1] - x[0],
+    assert emu.xl_highna_fwd(ptr(exy), None, ptr(out), N, M, M, 90.0, 100.0, 0.635, x[0], x[1] - x[0], x[0], x[1] - x[0],
                              xo[0], xo[-1], xo[0], xo[-1], 0, ptr(tb), ptr(ws), ws.size, None) == 0
     assert np.isnan(out).any()
 

@@ -275,6 +275,35 @@ def test_czt_family_autograd_random(ops_on_emu, emu, N, Mx, My, kind, seed):
     assert rel_l2(got[0], ref[0]) < 2e-5 and rel_l2(got[1], ref[1]) < 2e-5
 
 
+def test_separate_planes_need_no_stacking(ops_on_emu):
+    """The vectorial entry points take Ex and Ey where they live (include/xlprop.h: `ex`, `ey` pointers): planes that are NOT
+    adjacent in memory -- what the elements of an optical table produce -- give the same results and gradients as a stacked
+    (2,N,N) pair, without a torch.stack copy."""
+    rng = np.random.default_rng(21)
+    N, lam = 16, 0.6328
+    x = np.linspace(-300.0, 300.0, N)
+    xo = np.linspace(-40.0, 40.0, 12)
+    dx, k = float(x[1] - x[0]), 2 * np.pi / lam
+    pool = torch.tensor((rng.standard_normal((5, N, N)) + 1j * rng.standard_normal((5, N, N))).astype(np.complex64))
+    calls = {
+        "vrs": lambda a, b: ops.vrs_propagation(a, b, torch.tensor([9000.0], dtype=torch.float64, requires_grad=True), x[0], x[0], dx, dx, k),
+        "vczt": lambda a, b: ops.vczt(a, b, 9000.0, lam, x, x, xo, xo),
+        "highna": lambda a, b: ops.highna_focus(a, b, 500.0, 700.0, lam, x, x, xo, xo),
+    }
+    for name, fn in calls.items():
+        for (ia, ib) in ((3, 0), (0, 4)):          # Ey before Ex in memory, and three planes apart
+            ex = pool[ia].clone().requires_grad_(True)
+            ey = pool[ib].clone().requires_grad_(True)
+            out = fn(ex, ey)
+            ct = torch.tensor((rng.standard_normal(tuple(out.shape)) + 1j * rng.standard_normal(tuple(out.shape))).astype(np.complex64))
+            gx, gy = torch.autograd.grad((ct.conj() * out).real.sum(), (ex, ey))
+            st = torch.stack([pool[ia], pool[ib]]).requires_grad_(True)
+            out2 = fn(st, None)
+            (gs,) = torch.autograd.grad((ct.conj() * out2).real.sum(), (st,))
+            assert rel_l2(out.detach().numpy(), out2.detach().numpy()) < 1e-6, name
+            assert rel_l2(torch.stack([gx, gy]).numpy(), gs.numpy()) < 1e-6, name
+
+
 def _fd_dz(fn, z, eps):
     """4th-order central difference of a real functional of z."""
     return (8 * (fn(z + eps) - fn(z - eps)) - (fn(z + 2 * eps) - fn(z - 2 * eps))) / (12 * eps)

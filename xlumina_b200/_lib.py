@@ -28,8 +28,8 @@ SIGNATURES = {
     "xl_rs_transfer": (_i, [_vp, _vp, _i, _d, _d, _d, _i, _vp]),
     "xl_rs_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _d, _d, _d, _i, _vp, _sz, _vp]),
     "xl_rs_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _d, _d, _d, _i, _vp, _sz, _vp]),
-    "xl_vrs_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _d, _d, _d, _d, _d, _i, _vp, _sz, _vp]),
-    "xl_vrs_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _d, _d, _d, _d, _d, _i, _vp, _sz, _vp]),
+    "xl_vrs_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _d, _d, _d, _d, _d, _i, _vp, _sz, _vp]),
+    "xl_vrs_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _d, _d, _d, _d, _d, _i, _vp, _sz, _vp]),
     "xl_rs_fwd_fused": (_i, [_vp, _vp, _vp, _vp, _i, _i, _d, _d, _d, _i, _vp, _vp, _sz, _vp]),
     "xl_rs_bwd_fused": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _d, _d, _d, _i, _vp, _vp, _sz, _vp]),
     "xl_slab_padded_length": (_i, [_i]),
@@ -43,13 +43,13 @@ SIGNATURES = {
     "xl_debug_set_max_line": (None, [_i]),
     "xl_czt_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "xl_czt_tables_bytes": (_sz, [_i, _i, _i]),
-    "xl_czt_fwd": (_i, [_vp, _vp, _vp, _d, _i, _i, _i, _i, _d, _d, _d, _d, _d, _d, _d, _d, _i, _vp, _vp, _sz, _vp]),
+    "xl_czt_fwd": (_i, [_vp, _vp, _vp, _vp, _d, _i, _i, _i, _i, _d, _d, _d, _d, _d, _d, _d, _d, _i, _vp, _vp, _sz, _vp]),
     "xl_czt_bwd": (_i, [_vp, _vp, _vp, _d, _i, _i, _i, _i, _d, _d, _d, _d, _d, _d, _d, _d, _i, _vp, _vp, _sz, _vp]),
     "xl_czt_workspace_bytes_z": (_sz, [_i, _i, _i, _i]),
-    "xl_czt_bwd_z": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _d, _i, _i, _i, _i, _d, _d, _d, _d, _d, _d, _d, _d, _i, _vp, _vp, _sz, _vp]),
+    "xl_czt_bwd_z": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _d, _i, _i, _i, _i, _d, _d, _d, _d, _d, _d, _d, _d, _i, _vp, _vp, _sz, _vp]),
     "xl_highna_workspace_bytes": (_sz, [_i, _i, _i]),
     "xl_highna_tables_bytes": (_sz, [_i, _i, _i]),
-    "xl_highna_fwd": (_i, [_vp, _vp, _i, _i, _i, _d, _d, _d, _d, _d, _d, _d, _d, _d, _d, _d, _i, _vp, _vp, _sz, _vp]),
+    "xl_highna_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _d, _d, _d, _d, _d, _d, _d, _d, _d, _d, _d, _i, _vp, _vp, _sz, _vp]),
     "xl_launch_count": (ctypes.c_longlong, []),
     "xl_prof_enable": (None, [_i]),
     "xl_prof_report": (_i, [ctypes.c_char_p, _i]),

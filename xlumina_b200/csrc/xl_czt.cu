@@ -20,6 +20,7 @@ struct CztCall {
     double x0, dx, y0, dy, xout0, xoutl, yout0, youtl;
     double R, f, s2;
     int flags;
+    long long ey_off;     // vectorial inputs: elements from the Ex plane to the Ey plane (N*N when stacked)
 };
 static int axis_sym(double x0, double dx, int n) {   // grid symmetric about 0 (toolbox.space): one quadrant of a factor is enough
     const double span = fabs((n - 1) * dx);
@@ -212,7 +213,7 @@ static int czt_forward(const CztCall& cc, const void* in, void* out, void* table
     XlCztParams a;
     czt_common_params(a, cc, tw);
     a.L = pl.Ly; a.nlines = N; a.ncomp = ncomp; a.m_in = N; a.out_off = 0; a.m_out = My;
-    a.in = (const cf*)in; a.in_line = 1; a.in_pos = N; a.in_comp = (long long)N * N;
+    a.in = (const cf*)in; a.in_line = 1; a.in_pos = N; a.in_comp = cc.mode == 0 ? (long long)N * N : cc.ey_off;
     a.out = pl.mid; a.out_line = My; a.out_pos = 1; a.out_comp = (long long)N * My;
     a.pre = pl.pre_y; a.ft = pl.ft_y; a.post = pl.post_y;
     a.pro = cc.mode == 0 ? XL_PRO_RSF : (cc.mode == 1 ? XL_PRO_VCZT : XL_PRO_HIGHNA);
@@ -317,7 +318,7 @@ static int czt_backward_z(const CztCall& cc, const void* in, const void* out, co
     d.flags = (cc.flags & XL_CONJ_IN) | (cc.mode == 0 ? (cc.flags & XL_CONJ_OUT) : 0);
     d.ct_out = (const cf*)ct_out; d.out = (const cf*)out; d.O1 = O1; d.O2 = O2;
     d.ct_in = cc.mode == 0 ? (const cf*)ct_in : pl.tmp3;
-    d.in = (const cf*)in; d.z = cc.z; d.k = cc.k;
+    d.in = (const cf*)in; d.ey_off = cc.ey_off; d.z = cc.z; d.k = cc.k;
     d.lambda_over_dx = cc.lambda / cc.dx; d.dDm_dz = cc.lambda / cc.dx;      // Dm = lambda z / dx, wave_optics.py:322
     d.ay = XlCztAxisDz{cc.yout0, (cc.youtl - cc.yout0) / My, N};
     d.ax = XlCztAxisDz{cc.xout0, (cc.xoutl - cc.xout0) / Mx, N};
@@ -338,13 +339,22 @@ static CztCall make_czt_call(int mode, const double* z, double lambda, int N, in
     c.R = R; c.f = f;
     if (mode == 2) { double st = R / sqrt(R * R + f * f); c.s2 = st * st; }  // optical_elements.py:528
     c.flags = flags;
+    c.ey_off = (long long)N * N;
     return c;
 }
+static int set_planes(CztCall& c, const void* ex, const void* ey) {
+    if (!ey || !ex) return XL_OK;
+    const long long d = (const char*)ey - (const char*)ex;
+    if (d % (long long)sizeof(cf)) return xl_fail(XL_E_BAD_ARG, "czt: Ex and Ey must be 8-byte aligned%s", "");
+    c.ey_off = d / (long long)sizeof(cf);
+    return XL_OK;
+}
 
-extern "C" int xl_czt_fwd(const void* in, void* out, const double* z, double lambda, int N, int Mx, int My, int vectorial,
+extern "C" int xl_czt_fwd(const void* in, const void* ey, void* out, const double* z, double lambda, int N, int Mx, int My, int vectorial,
                           double x0, double dx, double y0, double dy, double xout0, double xoutl, double yout0, double youtl,
                           int flags, void* tables, void* ws, size_t ws_bytes, void* stream) {
     CztCall c = make_czt_call(vectorial ? 1 : 0, z, lambda, N, Mx, My, x0, dx, y0, dy, xout0, xoutl, yout0, youtl, 0, 0, flags);
+    if (vectorial) { int rc = set_planes(c, in, ey); if (rc) return rc; }
     return czt_forward(c, in, out, tables, ws, ws_bytes, (xl_stream_t)stream);
 }
 extern "C" int xl_czt_bwd(const void* ct_out, void* ct_in, const double* z, double lambda, int N, int Mx, int My, int vectorial,
@@ -358,18 +368,20 @@ extern "C" size_t xl_czt_workspace_bytes_z(int N, int Mx, int My, int vectorial)
     const size_t base = czt_ws_bytes(N, Mx, My, ncomp);
     return base ? base + 2 * align_up((size_t)ncomp * My * Mx * sizeof(cf)) : 0;
 }
-extern "C" int xl_czt_bwd_z(const void* in, const void* out, const void* ct_out, void* ct_in, double* grad_z,
+extern "C" int xl_czt_bwd_z(const void* in, const void* ey, const void* out, const void* ct_out, void* ct_in, double* grad_z,
                             const double* z, double lambda, int N, int Mx, int My, int vectorial,
                             double x0, double dx, double y0, double dy, double xout0, double xoutl, double yout0, double youtl,
                             int flags, void* tables, void* ws, size_t ws_bytes, void* stream) {
     CztCall c = make_czt_call(vectorial ? 1 : 0, z, lambda, N, Mx, My, x0, dx, y0, dy, xout0, xoutl, yout0, youtl, 0, 0, flags);
+    if (vectorial) { int rc = set_planes(c, in, ey); if (rc) return rc; }
     return czt_backward_z(c, in, out, ct_out, ct_in, grad_z, tables, ws, ws_bytes, (xl_stream_t)stream);
 }
-extern "C" int xl_highna_fwd(const void* exy, void* out, int N, int Mx, int My, double radius, double f, double lambda,
+extern "C" int xl_highna_fwd(const void* ex, const void* ey, void* out, int N, int Mx, int My, double radius, double f, double lambda,
                              double x0, double dx, double y0, double dy, double xout0, double xoutl, double yout0, double youtl,
                              int flags, void* tables, void* ws, size_t ws_bytes, void* stream) {
     CztCall c = make_czt_call(2, 0, lambda, N, Mx, My, x0, dx, y0, dy, xout0, xoutl, yout0, youtl, radius, f, flags);
-    return czt_forward(c, exy, out, tables, ws, ws_bytes, (xl_stream_t)stream);
+    { int rc = set_planes(c, ex, ey); if (rc) return rc; }
+    return czt_forward(c, ex, out, tables, ws, ws_bytes, (xl_stream_t)stream);
 }
 extern "C" int xl_highna_bwd(const void* ct_out, void* ct_exy, int N, int Mx, int My, double radius, double f, double lambda,
                              double x0, double dx, double y0, double dy, double xout0, double xoutl, double yout0, double youtl,

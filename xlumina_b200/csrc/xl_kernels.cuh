@@ -148,7 +148,8 @@ struct XlRsParams {
     int rows;          // rows of this launch's slab == row count of the blocked layouts (N on a single GPU)
     int chunk_rows;    // slab column kernels: rows per source rank in the exchanged layout [rank][pair][chunk_rows][2]
     int hrow0, hstore_all;   // slab h_rows: first y row of this rank; store every x slot pair (no x-mirror skipping)
-    const cf* in;      // [nfields][N][N]   (XL_F_VRS: [2][N][N] = Ex,Ey)
+    const cf* in;      // [nfields][N][N]   (XL_F_VRS: the Ex plane; Ey starts ey_off elements later)
+    long long ey_off;  // XL_F_VRS: elements from the Ex plane to the Ey plane of the primal input (N*N when they are stacked)
     const cf* in2;     // rs_rows_dual: the primal field(s) whose conjugate is the second line (same shape rules as `in`)
     cf* out;           // [nfields][N][N]
     cf* spec;          // [nfields][L/2][N][2]
@@ -201,14 +202,14 @@ template <int L, bool EZ, bool FUSE = false> struct XlRsRowsFwdOp : XlOpBase {
         const size_t NN = (size_t)p.rows * N, o = ok ? (size_t)y * N + i : 0;
         cf v;
         if (EZ) {
-            const cf ex = p.in[o], ey = p.in[NN + o];
+            const cf ex = p.in[o], ey = p.in[p.ey_off + (long long)o];
             const double X = p.x0 + i * p.dx, Y = p.y0 + y * p.dy;
             const double ir = xl_rsqrt64(X * X + Y * Y + z2);
             v = cf_lin2(ex, (float)(X * ir), ey, (float)(Y * ir));
         } else if (FUSE) {
             v = p.seed_out ? xl_seed_ct(p, w, (size_t)f * NN, o) : xl_fused_in(p, p.in, (size_t)f * NN, o);
         } else {
-            v = p.in[(size_t)f * NN + o];
+            v = p.in[((p.flags & XL_F_VRS) ? (long long)f * p.ey_off : (long long)((size_t)f * NN)) + (long long)o];   // VRS: f is 0 or 1 here
         }
         if (p.flags & XL_F_CONJ_IN) v = cf_conj(v);
         return ok ? v : cf_zero();
@@ -265,14 +266,14 @@ template <int L, bool EZ, bool FUSE = false> struct XlRsRowsDualOp : XlOpBase {
         cf c = (FUSE && p.seed_out) ? xl_seed_ct(p, sw, (size_t)f * NN, o) : p.in[(size_t)f * NN + o], w;
         if (p.flags & XL_F_CONJ_IN) c = cf_conj(c);
         if (EZ) {
-            const cf ex = p.in2[o], ey = p.in2[NN + o];
+            const cf ex = p.in2[o], ey = p.in2[p.ey_off + (long long)o];
             const double X = p.x0 + i * p.dx, Y = p.y0 + y * p.dy;
             const double ir = xl_rsqrt64(X * X + Y * Y + z2);
             w = cf_lin2(ex, (float)(X * ir), ey, (float)(Y * ir));
         } else if (FUSE) {
             w = xl_fused_in(p, p.in2, (size_t)f * NN, o);
         } else {
-            w = p.in2[(size_t)f * NN + o];
+            w = p.in2[((p.flags & XL_F_VRS) ? (long long)f * p.ey_off : (long long)((size_t)f * NN)) + (long long)o];
         }
         v[0] = ok ? c : cf_zero();
         v[stride] = ok ? cf_conj(w) : cf_zero();
@@ -1120,7 +1121,8 @@ struct XlCztDotZParams {
     int N, Mx, My, ncomp, flags;   // XL_F_CONJ_IN: ct_out is conjugated on load; XL_F_CONJ_OUT: ct_in was stored conjugated
     const cf* ct_out; const cf* out; const cf* O1; const cf* O2;   // [ncomp][My][Mx]
     const cf* ct_in;     // [ncomp][N][N] cotangent of the component planes (scalar: the caller's ct_in; vectorial: before the fold)
-    const cf* in;        // [1][N][N] or [2][N][N] = Ex, Ey
+    const cf* in;        // [N][N], or the Ex plane with the Ey plane ey_off elements later
+    long long ey_off;
     const double* z; double k, dDm_dz, lambda_over_dx;
     XlCztAxisDz ay, ax;
     double x0, dx, y0, dy, xo0, dxo, yo0, dyo;
@@ -1167,9 +1169,10 @@ struct XlCztDotZ {
                 if (p.flags & XL_F_CONJ_OUT) ci = -ci;
                 double ur, ui, er = 0.0, ei = 0.0;                    // component plane U_c and (c == 2) dEz/dz
                 if (c < 2) {
-                    ur = (double)p.in[e].x; ui = (double)p.in[e].y;
+                    const cf a = p.in[(long long)c * p.ey_off + (long long)o];
+                    ur = (double)a.x; ui = (double)a.y;
                 } else {                                              // Ez = (Ex X + Ey Y) z / r^2, vectorized_optics.py:341-344
-                    const cf ex = p.in[o], ey = p.in[NN + o];
+                    const cf ex = p.in[o], ey = p.in[p.ey_off + (long long)o];
                     const double ir2 = 1.0 / (X * X + Y * Y + z * z);
                     const double sr = (double)ex.x * X + (double)ey.x * Y, si = (double)ex.y * X + (double)ey.y * Y;
                     ur = sr * z * ir2; ui = si * z * ir2;

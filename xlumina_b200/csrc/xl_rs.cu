@@ -55,7 +55,10 @@ static int rs_apply_impl(XlRsParams p, xl_stream_t st) {
     return rc;
 }
 
-static int rs_fwd_common(const void* in, void* out, void* H, const double* z, int N, int nfields, int vrs,
+static long long plane_offset(const void* ex, const void* ey, int N) {   // elements from the Ex plane to the Ey plane
+    return ey ? (long long)((const cf*)ey - (const cf*)ex) : (long long)N * N;
+}
+static int rs_fwd_common(const void* in, const void* ey, void* out, void* H, const double* z, int N, int nfields, int vrs,
                          double x0, double y0, double dx, double dy, double k, int flags,
                          void* ws, size_t ws_bytes, xl_stream_t st) {
     if (!in || !out || !H || !z || !ws) return xl_fail(XL_E_BAD_ARG, "rs_fwd: null pointer%s", "");
@@ -67,6 +70,7 @@ static int rs_fwd_common(const void* in, void* out, void* H, const double* z, in
     Carver c{(char*)ws, 0, ws_bytes};
     p.spec = (cf*)c.take((size_t)nfields * p.L * N * sizeof(cf));
     p.in = (const cf*)in; p.out = (cf*)out; p.H = (cf*)H; p.z = z;
+    p.ey_off = plane_offset(in, ey, N);
     p.nfields = nfields; p.x0 = x0; p.y0 = y0;
     p.flags = (flags & (XL_CONJ_IN | XL_CONJ_OUT)) | (vrs ? XL_F_VRS : 0);
     return rs_apply_impl(p, st);
@@ -75,14 +79,15 @@ static int rs_fwd_common(const void* in, void* out, void* H, const double* z, in
 extern "C" int xl_rs_fwd(const void* in, void* out, void* H, const double* z, int N, int nfields,
                          double dx, double dy, double k, int flags, void* ws, size_t ws_bytes, void* stream) {
     if (nfields < 1) return xl_fail(XL_E_BAD_ARG, "xl_rs_fwd: nfields < 1%s", "");
-    return rs_fwd_common(in, out, H, z, N, nfields, 0, 0.0, 0.0, dx, dy, k, flags, ws, ws_bytes, (xl_stream_t)stream);
+    return rs_fwd_common(in, 0, out, H, z, N, nfields, 0, 0.0, 0.0, dx, dy, k, flags, ws, ws_bytes, (xl_stream_t)stream);
 }
-extern "C" int xl_vrs_fwd(const void* exy, void* out, void* H, const double* z, int N, double x0, double y0,
+extern "C" int xl_vrs_fwd(const void* ex, const void* ey, void* out, void* H, const double* z, int N, double x0, double y0,
                           double dx, double dy, double k, int flags, void* ws, size_t ws_bytes, void* stream) {
-    return rs_fwd_common(exy, out, H, z, N, 3, 1, x0, y0, dx, dy, k, flags, ws, ws_bytes, (xl_stream_t)stream);
+    if (ey && (((const char*)ey - (const char*)ex) % (long long)sizeof(cf))) return xl_fail(XL_E_BAD_ARG, "xl_vrs_fwd: Ex and Ey must be 8-byte aligned%s", "");
+    return rs_fwd_common(ex, ey, out, H, z, N, 3, 1, x0, y0, dx, dy, k, flags, ws, ws_bytes, (xl_stream_t)stream);
 }
 
-static int rs_bwd_common(const void* in, const void* out, const void* ct_out, void* ct_in, double* grad_z, const void* H,
+static int rs_bwd_common(const void* in, const void* ey, const void* out, const void* ct_out, void* ct_in, double* grad_z, const void* H,
                          const double* z, int N, int nfields, int vrs, double x0, double y0, double dx, double dy, double k,
                          int flags, void* ws, size_t ws_bytes, xl_stream_t st) {
     if (!ct_out || !ct_in || !H || !ws || !z) return xl_fail(XL_E_BAD_ARG, "rs_bwd: null pointer%s", "");
@@ -97,6 +102,7 @@ static int rs_bwd_common(const void* in, const void* out, const void* ct_out, vo
     p.spec = (cf*)c.take(spec_bytes);
     cf* tmp3 = (cf*)c.take((size_t)3 * N * N * sizeof(cf));
     p.nfields = nfields; p.H = (cf*)H; p.z = z; p.x0 = x0; p.y0 = y0;
+    p.ey_off = in ? plane_offset(in, ey, N) : (long long)N * N;
     cf* dst = vrs ? tmp3 : (cf*)ct_in;
 
     if (grad_z) {
@@ -143,7 +149,7 @@ static int rs_bwd_common(const void* in, const void* out, const void* ct_out, vo
         memset(&f, 0, sizeof(f));
         f.N = N; f.mode = XL_FOLD_VRS; f.flags = flags & XL_CONJ_OUT;
         f.t = tmp3;
-        f.ex = (const cf*)in; f.ey = in ? (const cf*)in + (size_t)N * N : 0;
+        f.ex = (const cf*)in; f.ey = in ? (const cf*)in + p.ey_off : 0;
         f.gx = (cf*)ct_in; f.gy = (cf*)ct_in + (size_t)N * N;
         f.gz = grad_z; f.z = z; f.x0 = x0; f.y0 = y0; f.dx = dx; f.dy = dy;
         const size_t NN = (size_t)N * N;
@@ -156,12 +162,12 @@ extern "C" int xl_rs_bwd(const void* in, const void* out, const void* ct_out, vo
                          const double* z, int N, int nfields, double dx, double dy, double k, int flags,
                          void* ws, size_t ws_bytes, void* stream) {
     if (nfields < 1) return xl_fail(XL_E_BAD_ARG, "xl_rs_bwd: nfields < 1%s", "");
-    return rs_bwd_common(in, out, ct_out, ct_in, grad_z, H, z, N, nfields, 0, 0.0, 0.0, dx, dy, k, flags, ws, ws_bytes, (xl_stream_t)stream);
+    return rs_bwd_common(in, 0, out, ct_out, ct_in, grad_z, H, z, N, nfields, 0, 0.0, 0.0, dx, dy, k, flags, ws, ws_bytes, (xl_stream_t)stream);
 }
-extern "C" int xl_vrs_bwd(const void* exy, const void* out, const void* ct_out, void* ct_exy, double* grad_z, const void* H,
+extern "C" int xl_vrs_bwd(const void* ex, const void* ey, const void* out, const void* ct_out, void* ct_exy, double* grad_z, const void* H,
                           const double* z, int N, double x0, double y0, double dx, double dy, double k, int flags,
                           void* ws, size_t ws_bytes, void* stream) {
-    return rs_bwd_common(exy, out, ct_out, ct_exy, grad_z, H, z, N, 3, 1, x0, y0, dx, dy, k, flags, ws, ws_bytes, (xl_stream_t)stream);
+    return rs_bwd_common(ex, ey, out, ct_out, ct_exy, grad_z, H, z, N, 3, 1, x0, y0, dx, dy, k, flags, ws, ws_bytes, (xl_stream_t)stream);
 }
 
 

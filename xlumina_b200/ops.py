@@ -217,43 +217,44 @@ class _RS(torch.autograd.Function):
 
 
 class _VRS(torch.autograd.Function):
-    """exy (2,N,N) -> (3,N,N); Ez = (Ex X + Ey Y)/r formed at load (vectorized_optics.py:258-261)."""
+    """(Ex, Ey) (N,N) each -> (3,N,N); Ez = (Ex X + Ey Y)/r formed at load (vectorized_optics.py:258-261).  The two planes are
+    passed to the library where they live: no stacking copy."""
 
     @staticmethod
     @_on_device
-    def forward(ctx, exy, z, x0, y0, dx, dy, k, zkey=None, zobj=None, hshare=None):
-        _require_device(exy)
+    def forward(ctx, ex, ey, z, x0, y0, dx, dy, k, zkey=None, zobj=None, hshare=None):
+        _require_device(ex)
         L = _lib.lib()
-        N = exy.shape[-1]
-        out = torch.empty((3, N, N), dtype=exy.dtype, device=exy.device)
+        N = ex.shape[-1]
+        out = torch.empty((3, N, N), dtype=ex.dtype, device=ex.device)
         if hshare is not None and hshare[0] is not None:       # later item of a batch that shares z: reuse its transfer function
             H, reuse = hshare[0], True
         else:
-            H, reuse = _cached_transfer(zkey, zobj, N, dx, dy, k, exy.device, L.xl_rs_transfer_bytes(N))
+            H, reuse = _cached_transfer(zkey, zobj, N, dx, dy, k, ex.device, L.xl_rs_transfer_bytes(N))
             if hshare is not None:
                 hshare[0] = H
-        ws = _workspace(exy, L.xl_rs_workspace_bytes(N, 3, 0))
-        _lib.check(L.xl_vrs_fwd(_ptr(exy), _ptr(out), _ptr(H), _ptr(z), N, x0, y0, dx, dy, k, _lib.XL_REUSE_H if reuse else 0,
-                                _ptr(ws), ws.numel(), _stream(exy)), "xl_vrs_fwd")
-        ctx.save_for_backward(exy, z, H, out)
+        ws = _workspace(ex, L.xl_rs_workspace_bytes(N, 3, 0))
+        _lib.check(L.xl_vrs_fwd(_ptr(ex), _ptr(ey), _ptr(out), _ptr(H), _ptr(z), N, x0, y0, dx, dy, k, _lib.XL_REUSE_H if reuse else 0,
+                                _ptr(ws), ws.numel(), _stream(ex)), "xl_vrs_fwd")
+        ctx.save_for_backward(ex, ey, z, H, out)
         ctx.geom = (x0, y0, dx, dy, k)
         return out
 
     @staticmethod
     @_on_device
     def backward(ctx, g):
-        exy, z, H, out = ctx.saved_tensors
+        ex, ey, z, H, out = ctx.saved_tensors
         x0, y0, dx, dy, k = ctx.geom
         L = _lib.lib()
-        N = exy.shape[-1]
+        N = ex.shape[-1]
         g = g.resolve_conj().contiguous()
-        want_z = ctx.needs_input_grad[1]
-        gin = torch.empty_like(exy)
-        gz = torch.zeros(1, dtype=torch.float64, device=exy.device) if want_z else None
-        ws = _workspace(exy, L.xl_rs_workspace_bytes(N, 3, 1 if want_z else 0))
-        _lib.check(L.xl_vrs_bwd(_ptr(exy), _ptr(out), _ptr(g), _ptr(gin), _ptr(gz), _ptr(H), _ptr(z), N, x0, y0, dx, dy, k,
-                                _lib.XL_CONJ_IN | _lib.XL_CONJ_OUT, _ptr(ws), ws.numel(), _stream(exy)), "xl_vrs_bwd")
-        return gin, gz, None, None, None, None, None, None, None, None
+        want_z = ctx.needs_input_grad[2]
+        gin = torch.empty((2, N, N), dtype=ex.dtype, device=ex.device)
+        gz = torch.zeros(1, dtype=torch.float64, device=ex.device) if want_z else None
+        ws = _workspace(ex, L.xl_rs_workspace_bytes(N, 3, 1 if want_z else 0))
+        _lib.check(L.xl_vrs_bwd(_ptr(ex), _ptr(ey), _ptr(out), _ptr(g), _ptr(gin), _ptr(gz), _ptr(H), _ptr(z), N, x0, y0, dx, dy, k,
+                                _lib.XL_CONJ_IN | _lib.XL_CONJ_OUT, _ptr(ws), ws.numel(), _stream(ex)), "xl_vrs_bwd")
+        return gin[0], gin[1], gz, None, None, None, None, None, None, None, None
 
 
 class _RSFused(torch.autograd.Function):
@@ -385,6 +386,15 @@ def rs_propagation(field, z, dx, dy, k):
     return out if dt == torch.complex64 or not torch.is_complex(field) else out.to(dt)
 
 
+def _planes(Ex, Ey):
+    """The two input planes of a vectorial operator as contiguous complex64 (N,N) tensors: views when `Ex` is a stacked
+    (2,N,N) pair (Ey=None), the caller's own tensors otherwise -- never a stacking copy."""
+    if Ey is None:
+        e = _c64(Ex)
+        return e[0], e[1]
+    return _c64(Ex), _c64(Ey)
+
+
 def _batch_of_pairs(fn, Ex, Ey, z):
     """Leading batch axis for the vectorial operators: Ex, Ey (B,N,N) or a stacked (B,2,N,N) -> (B,3,...); `z` shared
     or one per item.  Items are independent library calls; fn(ex, ey, z, hshare)."""
@@ -400,10 +410,11 @@ def vrs_propagation(Ex, Ey, z, x0, y0, dx, dy, k, _hshare=None):
     if Ex.dim() == (4 if Ey is None else 3):
         return _batch_of_pairs(lambda a, b, zz, hs: vrs_propagation(a, b, zz, x0, y0, dx, dy, k, hs), Ex, Ey, z)
     dt = Ex.dtype
-    exy = _c64(Ex) if Ey is None else torch.stack([_c64(Ex), _c64(Ey)], dim=0)
-    zt = _as_z(z, exy)
-    N = exy.shape[-1]
+    ex, ey = _planes(Ex, Ey)
+    zt = _as_z(z, ex)
+    N = ex.shape[-1]
     if N > FUSED_MAX_N:
+        exy = torch.stack([ex, ey])
         # large grids: Ez = (Ex X + Ey Y)/r (vectorized_optics.py:258-261) is formed pointwise here and the three components
         # go through the stage chain as one batch sharing the transfer function (differentiable in Ex, Ey only)
         xs = float(x0) + float(dx) * torch.arange(N, dtype=torch.float64, device=exy.device)
@@ -412,7 +423,7 @@ def vrs_propagation(Ex, Ey, z, x0, y0, dx, dy, k, _hshare=None):
         ez = exy[0] * (xs[None, :] / r).to(torch.float32) + exy[1] * (ys[:, None] / r).to(torch.float32)
         out = _RSLarge.apply(torch.stack([exy[0], exy[1], ez]), zt, float(dx), float(dy), float(k))
         return out if dt == torch.complex64 or not torch.is_complex(Ex) else out.to(dt)
-    out = _VRS.apply(exy, zt, float(x0), float(y0), float(dx), float(dy), float(k),
+    out = _VRS.apply(ex, ey, zt, float(x0), float(y0), float(dx), float(dy), float(k),
                      _z_key(z) if _transfer_cache_size else None, z, _hshare)
     return out if dt == torch.complex64 or not torch.is_complex(Ex) else out.to(dt)
 
@@ -433,7 +444,8 @@ def rs_transfer(z, N, dx, dy, k, device, deriv=False):
 class _CZT(torch.autograd.Function):
     @staticmethod
     @_on_device
-    def forward(ctx, fin, z, lam, vect, gin, gout):
+    def forward(ctx, fin, ey, z, lam, vect, gin, gout):
+        """fin: the scalar field, or Ex with `ey` = Ey (vect = 1)."""
         _require_device(fin)
         L = _lib.lib()
         N = fin.shape[-1]
@@ -446,37 +458,38 @@ class _CZT(torch.autograd.Function):
         ws = _workspace(fin, need)
         # tables: Bluestein chirps / kernel spectra and the RS factor tables of this (z, grids); the backward pass reuses them
         tables = torch.empty(L.xl_czt_tables_bytes(N, Mx, My), dtype=torch.uint8, device=fin.device)
-        _lib.check(L.xl_czt_fwd(_ptr(fin), _ptr(out), _ptr(z), lam, N, Mx, My, vect, x0, dx, y0, dy, xo0, xol, yo0, yol, 0,
+        _lib.check(L.xl_czt_fwd(_ptr(fin), _ptr(ey), _ptr(out), _ptr(z), lam, N, Mx, My, vect, x0, dx, y0, dy, xo0, xol, yo0, yol, 0,
                                 _ptr(tables), _ptr(ws), ws.numel(), _stream(fin)), "xl_czt_fwd")
-        want_z = ctx.needs_input_grad[1]
-        ctx.save_for_backward(z, tables, *((fin, out) if want_z else ()))   # d/dz needs the primal input and result
-        ctx.meta = (lam, vect, gin, gout, N, fin.shape)
+        want_z = ctx.needs_input_grad[2]
+        ctx.save_for_backward(z, tables, *((fin, ey, out) if want_z else ()))   # d/dz needs the primal input and result
+        ctx.meta = (lam, vect, gin, gout, N)
         return out
 
     @staticmethod
     @_on_device
     def backward(ctx, g):
         z, tables = ctx.saved_tensors[:2]
-        lam, vect, gin, gout, N, shape = ctx.meta
+        lam, vect, gin, gout, N = ctx.meta
         (x0, dx, y0, dy) = gin
         (xo0, xol, Mx, yo0, yol, My) = gout
         L = _lib.lib()
         g = g.resolve_conj().contiguous()
-        ct = torch.empty(shape, dtype=g.dtype, device=g.device)
-        if ctx.needs_input_grad[1]:
-            fin, out = ctx.saved_tensors[2:]
+        ct = torch.empty((2, N, N) if vect else (N, N), dtype=g.dtype, device=g.device)
+        grads = (lambda gz: (ct[0], ct[1], gz, None, None, None, None)) if vect else (lambda gz: (ct, None, gz, None, None, None, None))
+        if ctx.needs_input_grad[2]:
+            fin, ey, out = ctx.saved_tensors[2:]
             gz = torch.zeros(1, dtype=torch.float64, device=g.device)
             ws = _workspace(g, L.xl_czt_workspace_bytes_z(N, Mx, My, vect))
-            _lib.check(L.xl_czt_bwd_z(_ptr(fin), _ptr(out), _ptr(g), _ptr(ct), _ptr(gz), _ptr(z), lam, N, Mx, My, vect,
+            _lib.check(L.xl_czt_bwd_z(_ptr(fin), _ptr(ey), _ptr(out), _ptr(g), _ptr(ct), _ptr(gz), _ptr(z), lam, N, Mx, My, vect,
                                       x0, dx, y0, dy, xo0, xol, yo0, yol,
                                       _lib.XL_CONJ_IN | _lib.XL_CONJ_OUT | _lib.XL_REUSE_TABLES, _ptr(tables), _ptr(ws), ws.numel(),
                                       _stream(g)), "xl_czt_bwd_z")
-            return ct, gz, None, None, None, None
+            return grads(gz)
         ws = _workspace(g, L.xl_czt_workspace_bytes(N, Mx, My, vect))
         _lib.check(L.xl_czt_bwd(_ptr(g), _ptr(ct), _ptr(z), lam, N, Mx, My, vect, x0, dx, y0, dy, xo0, xol, yo0, yol,
                                 _lib.XL_CONJ_IN | _lib.XL_CONJ_OUT | _lib.XL_REUSE_TABLES, _ptr(tables), _ptr(ws), ws.numel(),
                                 _stream(g)), "xl_czt_bwd")
-        return ct, None, None, None, None, None
+        return grads(None)
 
 
 # The tables of the high-NA objective (Bluestein tables + lens matrix on the input grid) depend on static arguments only:
@@ -501,7 +514,8 @@ def _highna_tables(L, device, N, Mx, My, radius, f, lam, gin, gout):
 class _HighNA(torch.autograd.Function):
     @staticmethod
     @_on_device
-    def forward(ctx, exy, radius, f, lam, gin, gout):
+    def forward(ctx, exy, ey, radius, f, lam, gin, gout):
+        """exy: the Ex plane, ey: the Ey plane."""
         _require_device(exy)
         L = _lib.lib()
         N = exy.shape[-1]
@@ -513,7 +527,7 @@ class _HighNA(torch.autograd.Function):
             raise _lib.XlpropError("high-NA: unsupported sizes (m+M-1 must not be a power of two; padded length <= 4096)")
         ws = _workspace(exy, need)
         tables, reuse = _highna_tables(L, exy.device, N, Mx, My, radius, f, lam, gin, gout)
-        _lib.check(L.xl_highna_fwd(_ptr(exy), _ptr(out), N, Mx, My, radius, f, lam, x0, dx, y0, dy, xo0, xol, yo0, yol,
+        _lib.check(L.xl_highna_fwd(_ptr(exy), _ptr(ey), _ptr(out), N, Mx, My, radius, f, lam, x0, dx, y0, dy, xo0, xol, yo0, yol,
                                    _lib.XL_REUSE_TABLES if reuse else 0, _ptr(tables), _ptr(ws), ws.numel(), _stream(exy)),
                    "xl_highna_fwd")
         ctx.save_for_backward(tables)
@@ -534,7 +548,7 @@ class _HighNA(torch.autograd.Function):
         _lib.check(L.xl_highna_bwd(_ptr(g), _ptr(ct), N, Mx, My, radius, f, lam, x0, dx, y0, dy, xo0, xol, yo0, yol,
                                    _lib.XL_CONJ_IN | _lib.XL_CONJ_OUT | _lib.XL_REUSE_TABLES, _ptr(tables), _ptr(ws), ws.numel(),
                                    _stream(g)), "xl_highna_bwd")
-        return ct, None, None, None, None, None
+        return ct[0], ct[1], None, None, None, None, None
 
 
 def _gout(xout, yout):
@@ -559,7 +573,7 @@ def czt(field, z, wavelength, x, y, xout, yout):
         return torch.stack([czt(field[i], z if zs is None else zs[i], wavelength, x, y, xout, yout) for i in range(field.shape[0])])
     dt = field.dtype
     f = _c64(field)
-    out = _CZT.apply(f, _as_z(z, f), float(wavelength), 0, _gin(x, y, f.shape[-1]), _gout(xout, yout))
+    out = _CZT.apply(f, None, _as_z(z, f), float(wavelength), 0, _gin(x, y, f.shape[-1]), _gout(xout, yout))
     return out if dt == torch.complex64 or not torch.is_complex(field) else out.to(dt)
 
 
@@ -569,8 +583,8 @@ def vczt(Ex, Ey, z, wavelength, x, y, xout, yout):
     if Ex.dim() == (4 if Ey is None else 3):
         return _batch_of_pairs(lambda a, b, zz, hs: vczt(a, b, zz, wavelength, x, y, xout, yout), Ex, Ey, z)
     dt = Ex.dtype
-    exy = _c64(Ex) if Ey is None else torch.stack([_c64(Ex), _c64(Ey)], dim=0)
-    out = _CZT.apply(exy, _as_z(z, exy), float(wavelength), 1, _gin(x, y, exy.shape[-1]), _gout(xout, yout))
+    ex, ey = _planes(Ex, Ey)
+    out = _CZT.apply(ex, ey, _as_z(z, ex), float(wavelength), 1, _gin(x, y, ex.shape[-1]), _gout(xout, yout))
     return out if dt == torch.complex64 or not torch.is_complex(Ex) else out.to(dt)
 
 
@@ -580,6 +594,6 @@ def highna_focus(Ex, Ey, radius, f, wavelength, x, y, xout, yout):
     if Ex.dim() == (4 if Ey is None else 3):
         return _batch_of_pairs(lambda a, b, zz, hs: highna_focus(a, b, radius, f, wavelength, x, y, xout, yout), Ex, Ey, None)
     dt = Ex.dtype
-    exy = _c64(Ex) if Ey is None else torch.stack([_c64(Ex), _c64(Ey)], dim=0)
-    out = _HighNA.apply(exy, float(radius), float(f), float(wavelength), _gin(x, y, exy.shape[-1]), _gout(xout, yout))
+    ex, ey = _planes(Ex, Ey)
+    out = _HighNA.apply(ex, ey, float(radius), float(f), float(wavelength), _gin(x, y, ex.shape[-1]), _gout(xout, yout))
     return out if dt == torch.complex64 or not torch.is_complex(Ex) else out.to(dt)
