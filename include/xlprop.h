@@ -76,6 +76,13 @@ size_t xl_rs_workspace_bytes(int N, int nfields, int want_grad_z);
  * Replaces transfer_function_RS + fft2(H), wave_optics.py:285,288,291-297. */
 int xl_rs_transfer(void* H, const double* z, int N, double dx, double dy, double k, int deriv, void* stream);
 
+/* `count` transfer functions in ONE launch pair (the fixed per-step cost of an optimizer whose distances are all known at the
+ * start of a step): buffer i lives at H + i*h_stride_bytes (>= xl_rs_transfer_bytes(N), a multiple of 16).  pairs == 0:
+ * buffer i = H(z[i]) (deriv as in xl_rs_transfer).  pairs == 1 (count even): buffer 2j = H(z[j]), buffer 2j+1 = the reduced
+ * dH/dz of z[j] that xl_rs_bwd_fused takes through xl_rs_fuse.Hz. */
+int xl_rs_transfer_multi(void* H, size_t h_stride_bytes, const double* z, int count, int pairs, int N,
+                         double dx, double dy, double k, int deriv, void* stream);
+
 /* out[f] = (ifft2(fft2(pad(in[f])) * fft2(H)) * dx*dy)[N-1:, N-1:]  for f < nfields.      wave_optics.py:286-288
  * H is written unless XL_REUSE_H is set (keep it for the backward call). */
 int xl_rs_fwd(const void* in, void* out, void* H, const double* z, int N, int nfields,
@@ -117,6 +124,8 @@ typedef struct xl_rs_fuse {
     int in_real;
     const float* target;
     double* mse;
+    const void* Hz;   /* backward only: the reduced dH/dz transfer function of this z, generated ahead (xl_rs_transfer_multi);
+                         NULL: the backward call generates it */
 } xl_rs_fuse;
 int xl_rs_fwd_fused(const void* in, void* out, void* H, const double* z, int N, int nfields,
                     double dx, double dy, double k, int flags, const xl_rs_fuse* fuse,

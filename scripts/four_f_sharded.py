@@ -29,7 +29,7 @@ import torch.distributed as dist
 
 import xlumina_b200 as xb
 from xlumina_b200 import four_f
-from xlumina_b200.sharding import allreduce_grads, shard_range
+from xlumina_b200.sharding import allreduce_flat, flat_grad_buffers, shard_range
 
 
 def synthetic_circles(n_samples, x, rng):
@@ -79,8 +79,7 @@ def setup(batch, n, dev, rank, world, fused=True, graph=False):
     params = [torch.tensor([prng.uniform(0.027, 1)], dtype=torch.float64, device=dev, requires_grad=True) for _ in range(3)]
     params += [torch.tensor(prng.uniform(0, 1, (N, N)).astype(np.float32), device=dev, requires_grad=True) for _ in range(2)]
     opt = torch.optim.AdamW(params, lr=0.01, weight_decay=1e-4, capturable=True)   # optax.adamw(0.01, weight_decay=1e-4), :97-98,112
-    for p in params:
-        p.grad = torch.zeros_like(p)
+    flats = flat_grad_buffers(params)       # .grad of every parameter = a view of one flat buffer per dtype
 
     def compute():
         opt.zero_grad(set_to_none=False)
@@ -90,7 +89,7 @@ def setup(batch, n, dev, rank, world, fused=True, graph=False):
 
     def step():
         loss = compute()
-        allreduce_grads([p.grad for p in params])
+        allreduce_flat(flats)
         opt.step()
         return loss
 
@@ -105,17 +104,30 @@ def setup(batch, n, dev, rank, world, fused=True, graph=False):
                 opt.step()
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
-        g_compute, g_opt = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g_compute):
-            static_loss = compute()
-        with torch.cuda.graph(g_opt):
-            opt.step()
+        if graph == "nccl":
+            # the whole step INCLUDING the NCCL all-reduce as one graph (thread-local capture mode: the NCCL watchdog thread
+            # may query events while this thread captures)
+            g_all = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g_all, capture_error_mode="thread_local"):
+                static_loss = compute()
+                allreduce_flat(flats)
+                opt.step()
 
-        def step():   # noqa: F811
-            g_compute.replay()
-            allreduce_grads([p.grad for p in params])
-            g_opt.replay()
-            return static_loss
+            def step():   # noqa: F811
+                g_all.replay()
+                return static_loss
+        else:
+            g_compute, g_opt = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g_compute):
+                static_loss = compute()
+            with torch.cuda.graph(g_opt):
+                opt.step()
+
+            def step():   # noqa: F811
+                g_compute.replay()
+                allreduce_flat(flats)
+                g_opt.replay()
+                return static_loss
 
     return step, params, b - a
 
@@ -128,6 +140,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--unfused", action="store_true", help="pointwise elements and the loss as separate torch operations")
     ap.add_argument("--graph", action="store_true", help="replay forward+backward and AdamW as CUDA graphs (the all-reduce stays eager)")
+    ap.add_argument("--graph-nccl", action="store_true", help="one CUDA graph for the whole step, the NCCL all-reduce captured too")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -137,7 +150,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     N = args.n
-    step, params, mine = setup(args.batch, N, dev, rank, world, fused=not args.unfused, graph=args.graph)
+    step, params, mine = setup(args.batch, N, dev, rank, world, fused=not args.unfused, graph=("nccl" if args.graph_nccl else args.graph))
 
     def barrier():
         if world > 1:
@@ -163,7 +176,7 @@ def main():
         print(json.dumps({"metric": "4f optimizer steps/s (batch %d, %d^2, 3 RS fwd+grad per sample, shared parameters)" % (args.batch, N),
                           "value": 1e3 / ms, "unit": "steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                           "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "samples_per_rank": mine,
-                          "propagations_per_s": 3 * args.batch * 1e3 / ms, "loss": float(lsum), "fused_elements": not args.unfused, "cuda_graphs": bool(args.graph),
+                          "propagations_per_s": 3 * args.batch * 1e3 / ms, "loss": float(lsum), "fused_elements": not args.unfused, "cuda_graphs": "with nccl" if args.graph_nccl else bool(args.graph),
                           "collective": "one all-reduce of 2*N^2 fp32 + 3 fp64 gradients per step"}), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -117,3 +117,25 @@ def test_two_rank_four_f_table_equals_single_process(emu, tmp_path):
             # same kernels, different batch grouping: distances see fp32 summation-order noise of the cancelling terms only
             tol = 2e-3 if i < 3 else 1e-5
             assert np.linalg.norm(two[f"g{i}"] - one[f"g{i}"]) <= tol * np.linalg.norm(one[f"g{i}"]), i
+
+
+def test_flat_grad_buffers_are_accumulated_in_place():
+    """sharding.flat_grad_buffers: every .grad is a view of one flat buffer per dtype, autograd accumulates into it in place
+    and zero_grad(set_to_none=False) keeps the views -- so the step's all-reduce runs on the flat buffers directly."""
+    import torch
+    from xlumina_b200.sharding import allreduce_flat, flat_grad_buffers
+    a = torch.randn(4, 5, requires_grad=True)
+    b = torch.randn(3, dtype=torch.float64, requires_grad=True)
+    c = torch.randn(7, requires_grad=True)
+    flats = flat_grad_buffers([a, b, c])
+    assert sorted(f.numel() for f in flats) == [3, 27]
+    ptrs = [p.grad.data_ptr() for p in (a, b, c)]
+    opt = torch.optim.AdamW([a, b, c], lr=0.01)
+    for _ in range(2):
+        opt.zero_grad(set_to_none=False)
+        ((a ** 2).sum() + (b ** 3).sum() + c.sum()).backward()
+        assert [p.grad.data_ptr() for p in (a, b, c)] == ptrs
+        f32 = next(f for f in flats if f.dtype == torch.float32)
+        assert torch.allclose(f32[:20].view(4, 5), 2 * a.detach()) and torch.allclose(f32[20:], torch.ones(7))
+        allreduce_flat(flats)          # no process group: a no-op
+        opt.step()

@@ -26,6 +26,7 @@ SIGNATURES = {
     "xl_rs_transfer_bytes": (_sz, [_i]),
     "xl_rs_workspace_bytes": (_sz, [_i, _i, _i]),
     "xl_rs_transfer": (_i, [_vp, _vp, _i, _d, _d, _d, _i, _vp]),
+    "xl_rs_transfer_multi": (_i, [_vp, _sz, _vp, _i, _i, _i, _d, _d, _d, _i, _vp]),
     "xl_rs_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _d, _d, _d, _i, _vp, _sz, _vp]),
     "xl_rs_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _d, _d, _d, _i, _vp, _sz, _vp]),
     "xl_vrs_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _d, _d, _d, _d, _d, _i, _vp, _sz, _vp]),
@@ -65,7 +66,8 @@ XL_PHASE_BLIND = 64
 
 class RsFuse(ctypes.Structure):
     """struct xl_rs_fuse of include/xlprop.h (pointwise elements fused into the scalar RS path)."""
-    _fields_ = [("mod", ctypes.c_void_p), ("in_real", ctypes.c_int), ("target", ctypes.c_void_p), ("mse", ctypes.c_void_p)]
+    _fields_ = [("mod", ctypes.c_void_p), ("in_real", ctypes.c_int), ("target", ctypes.c_void_p), ("mse", ctypes.c_void_p),
+                ("Hz", ctypes.c_void_p)]
 
 
 class XlpropError(RuntimeError):

@@ -148,6 +148,9 @@ struct XlRsParams {
     int rows;          // rows of this launch's slab == row count of the blocked layouts (N on a single GPU)
     int chunk_rows;    // slab column kernels: rows per source rank in the exchanged layout [rank][pair][chunk_rows][2]
     int hrow0, hstore_all;   // slab h_rows: first y row of this rank; store every x slot pair (no x-mirror skipping)
+    // several transfer functions in one launch pair (xl_rs_transfer_multi): item = blockIdx.y, buffer H + item * h_stride,
+    // distance z[item / h_per_z]; h_per_z == 2: even items hold H, odd items the reduced dH/dz of the same distance
+    long long h_stride; int h_per_z;
     const cf* in;      // [nfields][N][N]   (XL_F_VRS: the Ex plane; Ey starts ey_off elements later)
     long long ey_off;  // XL_F_VRS: elements from the Ex plane to the Ey plane of the primal input (N*N when they are stacked)
     const cf* in2;     // rs_rows_dual: the primal field(s) whose conjugate is the second line (same shape rules as `in`)
@@ -564,6 +567,7 @@ template <int L> struct XlRsRowsInvMod {
 template <int L> struct XlHRowsOp : XlOpBase {
     const XlRsParams& p; int yb; const cf* stage;   // stage[(L/2+1)][XL_V]
     int nvalid;   // local rows that exist (global row <= L/2)
+    cf* H;        // this item's buffer
     XL_DEV void load(int i, cf* v, int stride) const {
         const int xi = i <= L / 2 ? i : L - i;
         xl_ld4(stage + (size_t)xi * XL_V, v, v + stride);
@@ -575,7 +579,7 @@ template <int L> struct XlHRowsOp : XlOpBase {
             // rest is mirrored.  slab: every slot pair, rows in a [pair][rows][2] buffer of this rank's y rows.
             const int g = q * (L / 16) + beta;
             if (!p.hstore_all && (q > 8 || (q == 8 && beta >= 2))) continue;
-            xl_blocked_store2<xl_lane_mask(L)>(p.H + (size_t)(g / 2) * p.rows * 2, yb, nvalid, g, v[q], v[16 + q]);
+            xl_blocked_store2<xl_lane_mask(L)>(H + (size_t)(g / 2) * p.rows * 2, yb, nvalid, g, v[q], v[16 + q]);
         }
     }
     XL_DEV void store_vec(int, const cf*) const {}
@@ -590,8 +594,9 @@ template <int L> struct XlHRows {
         cf* t = s + xl_tile_elems(L, XL_V);
         cf* stage = t + xl_tw_total(L);
         const int yb = XL_BLOCK_X * XL_V;
-        const XlRsHConst hc = xl_rs_hconst(xl_ldg(p.z), p.k);
-        const int deriv = (p.flags & XL_F_DERIV) ? 1 : 0;
+        const int item = XL_BLOCK_Y, per = p.h_per_z > 0 ? p.h_per_z : 1;
+        const XlRsHConst hc = xl_rs_hconst(xl_ldg(p.z + item / per), p.k);
+        const int deriv = per == 2 ? (item & 1) : ((p.flags & XL_F_DERIV) ? 1 : 0);
         XL_THREADS(tid, NT) {
             for (int e = tid; e < (L / 2 + 1) * XL_V; e += NT) {
                 const int xi = e / XL_V, l = e % XL_V, yi = p.hrow0 + yb + l;   // global y row
@@ -601,7 +606,7 @@ template <int L> struct XlHRows {
         XlFft<L, XL_V>::init_tw(t, p.tw);   // ends with a barrier: stage[] is visible
         int nvalid = L / 2 + 1 - p.hrow0;
         if (nvalid > p.rows) nvalid = p.rows;
-        XlHRowsOp<L> op{{}, p, yb, stage, nvalid};
+        XlHRowsOp<L> op{{}, p, yb, stage, nvalid, p.H + (long long)item * p.h_stride};
         XlFft<L, XL_V>::forward(s, t, op);
     }
 };
@@ -666,8 +671,9 @@ template <int L> struct XlHCols {
         if (!xl_h_pair_needed<L>(XL_BLOCK_X)) return;   // CTA-uniform: mirrored columns are never read
         cf* t = s + xl_tile_elems(L, XL_V);
         XlFft<L, XL_V>::init_tw(t, p.tw);
-        cf* Hc = p.H + xl_hc_offset(L) + (size_t)XL_BLOCK_X * XL_V * xl_hc_stride(L);
-        XlHColsOp<L> op{{}, p, p.H + (size_t)XL_BLOCK_X * L * XL_V, Hc, Hc + xl_hc_stride(L)};
+        cf* H = p.H + (long long)XL_BLOCK_Y * p.h_stride;      // this item's buffer (xl_rs_transfer_multi)
+        cf* Hc = H + xl_hc_offset(L) + (size_t)XL_BLOCK_X * XL_V * xl_hc_stride(L);
+        XlHColsOp<L> op{{}, p, H + (size_t)XL_BLOCK_X * L * XL_V, Hc, Hc + xl_hc_stride(L)};
         // the in-place update is safe: every load of the first pass happens before the barrier that precedes the stores
         XlFft<L, XL_V>::forward(s, t, op);
     }

@@ -29,6 +29,28 @@ static int rs_transfer_impl(XlRsParams p, cf* H, const double* z, int deriv, xl_
     return rc;
 }
 
+// Several transfer functions in ONE launch pair: buffer i (i < count, h_stride_bytes apart) holds, for pairs == 0, H(z[i]) (or
+// its reduced z-derivative when deriv), and for pairs == 1 alternately H(z[i/2]) (even i) and the reduced dH/dz (odd i).
+extern "C" int xl_rs_transfer_multi(void* H, size_t h_stride_bytes, const double* z, int count, int pairs, int N,
+                                    double dx, double dy, double k, int deriv, void* stream) {
+    if (!H || !z || count < 1) return xl_fail(XL_E_BAD_ARG, "xl_rs_transfer_multi: bad argument%s", "");
+    if (h_stride_bytes % 16 || h_stride_bytes < xl_rs_transfer_bytes(N)) return xl_fail(XL_E_BAD_ARG, "xl_rs_transfer_multi: buffer stride too small or not a multiple of 16%s", "");
+    if (pairs && (count & 1)) return xl_fail(XL_E_BAD_ARG, "xl_rs_transfer_multi: pairs need an even count%s", "");
+    XlRsParams p;
+    int rc = rs_base_params(p, N, dx, dy, k);
+    if (rc) return rc;
+    xl_stream_t st = (xl_stream_t)stream;
+    p.H = (cf*)H; p.z = z;
+    p.flags = deriv ? XL_F_DERIV : 0;
+    p.h_stride = (long long)(h_stride_bytes / sizeof(cf)); p.h_per_z = pairs ? 2 : 1;
+    const int L = p.L;
+    p.rows = L; p.hrow0 = 0; p.hstore_all = 0;
+    XL_FOR_L(L, rc = xl_launch<XlHRows<XL>>(XlDim{xl_groups(L / 2 + 1), count}, st, p));
+    if (rc) return rc;
+    XL_FOR_L(L, rc = xl_launch<XlHCols<XL>>(XlDim{L / XL_V, count}, st, p));
+    return rc;
+}
+
 extern "C" int xl_rs_transfer(void* H, const double* z, int N, double dx, double dy, double k, int deriv, void* stream) {
     if (!H || !z) return xl_fail(XL_E_BAD_ARG, "xl_rs_transfer: null pointer%s", "");
     XlRsParams p;
@@ -241,8 +263,13 @@ extern "C" int xl_rs_bwd_fused(const void* in, const void* out, const void* ct_o
     if (grad_z) {
         p.spec2 = (cf*)c.take(2 * spec_bytes);
         cf* Hz = (cf*)c.take((size_t)L * L * sizeof(cf));
-        rc = rs_transfer_impl(p, Hz, z, 1, st);
-        if (rc) return rc;
+        if (fuse && fuse->Hz) {                     // generated ahead by xl_rs_transfer_multi
+            if (!aligned16(fuse->Hz)) return xl_fail(XL_E_BAD_ARG, "xl_rs_bwd_fused: Hz must be 16-byte aligned%s", "");
+            Hz = (cf*)fuse->Hz;
+        } else {
+            rc = rs_transfer_impl(p, Hz, z, 1, st);
+            if (rc) return rc;
+        }
         if (!seed && !(flags & XL_PHASE_BLIND)) {   // the i k out part of d out/dz, exactly; it vanishes identically for the fused
                                                     // detector (xl_seed_ct) and for every phase-blind loss
             XlDotZParams d;

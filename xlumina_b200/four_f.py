@@ -48,10 +48,13 @@ def loss_dualSLM_fused(parameters, input_masks, target_intensities, input_light)
     x = input_light.x
     dx, k = float(x[1] - x[0]), input_light.k
     masks = input_masks.real if input_masks.is_complex() else input_masks
+    zs = [_distance(parameters[i]) for i in range(3)]
+    # the three transfer functions and their z-derivatives in one launch pair (they do not depend on the batch)
+    pre = ops.rs_transfer_pairs(zs, masks.shape[-1], dx, dx, k, masks.device)
     # one path per sample ending in an intensity detector: the loss is blind to the global phase of every plane
-    f = ops.rs_propagation_fused(masks.to(torch.float32), _distance(parameters[0]), dx, dx, k, mod=input_light.field, phase_blind=True)
-    f = ops.rs_propagation_fused(f, _distance(parameters[1]), dx, dx, k, mod=_slm_phasor(parameters[3]), phase_blind=True)
-    mse = ops.rs_propagation_fused(f, _distance(parameters[2]), dx, dx, k, mod=_slm_phasor(parameters[4]), target=target_intensities)
+    f = ops.rs_propagation_fused(masks.to(torch.float32), zs[0], dx, dx, k, mod=input_light.field, phase_blind=True, pre=pre[0])
+    f = ops.rs_propagation_fused(f, zs[1], dx, dx, k, mod=_slm_phasor(parameters[3]), phase_blind=True, pre=pre[1])
+    mse = ops.rs_propagation_fused(f, zs[2], dx, dx, k, mod=_slm_phasor(parameters[4]), target=target_intensities, pre=pre[2])
     return mse.mean()
 
 

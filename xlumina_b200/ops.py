@@ -265,27 +265,30 @@ class _RSFused(torch.autograd.Function):
 
     @staticmethod
     @_on_device
-    def forward(ctx, field, z, mod, target, dx, dy, k, phase_blind):
+    def forward(ctx, field, z, mod, target, dx, dy, k, phase_blind, pre):
         _require_device(field)
         L = _lib.lib()
         F, N = field.shape[0], field.shape[-1]
         ctx.phase_blind = bool(phase_blind)
         out = torch.empty((F, N, N), dtype=torch.complex64, device=field.device)
         mse = torch.zeros(F, dtype=torch.float64, device=field.device) if target is not None else None
-        H = torch.empty(L.xl_rs_transfer_bytes(N), dtype=torch.uint8, device=field.device)
+        if pre is not None:       # (H, reduced dH/dz) of this z, generated ahead by rs_transfer_pairs
+            H, Hz = pre
+        else:
+            H, Hz = torch.empty(L.xl_rs_transfer_bytes(N), dtype=torch.uint8, device=field.device), None
         ws = _workspace(field, L.xl_rs_workspace_bytes(N, F, 0))
         fuse = _lib.RsFuse(mod.data_ptr() if mod is not None else None, 0 if field.is_complex() else 1,
-                           target.data_ptr() if target is not None else None, mse.data_ptr() if mse is not None else None)
-        _lib.check(L.xl_rs_fwd_fused(_ptr(field), _ptr(out), _ptr(H), _ptr(z), N, F, dx, dy, k, 0, ctypes.byref(fuse),
-                                     _ptr(ws), ws.numel(), _stream(field)), "xl_rs_fwd_fused")
-        ctx.save_for_backward(field, z, H, out, mod, target)
+                           target.data_ptr() if target is not None else None, mse.data_ptr() if mse is not None else None, None)
+        _lib.check(L.xl_rs_fwd_fused(_ptr(field), _ptr(out), _ptr(H), _ptr(z), N, F, dx, dy, k, _lib.XL_REUSE_H if pre is not None else 0,
+                                     ctypes.byref(fuse), _ptr(ws), ws.numel(), _stream(field)), "xl_rs_fwd_fused")
+        ctx.save_for_backward(field, z, H, out, mod, target, Hz)
         ctx.geom = (dx, dy, k)
         return mse if target is not None else out
 
     @staticmethod
     @_on_device
     def backward(ctx, g):
-        field, z, H, out, mod, target = ctx.saved_tensors
+        field, z, H, out, mod, target, Hz = ctx.saved_tensors
         dx, dy, k = ctx.geom
         L = _lib.lib()
         F, N = field.shape[0], field.shape[-1]
@@ -300,16 +303,33 @@ class _RSFused(torch.autograd.Function):
         gz = torch.zeros(1, dtype=torch.float64, device=field.device) if want_z else None
         ws = _workspace(field, L.xl_rs_workspace_bytes(N, F, 1 if want_z else 0))
         fuse = _lib.RsFuse(mod.data_ptr() if mod is not None else None, 0 if field.is_complex() else 1,
-                           target.data_ptr() if target is not None else None, None)
+                           target.data_ptr() if target is not None else None, None, Hz.data_ptr() if Hz is not None else None)
         _lib.check(L.xl_rs_bwd_fused(_ptr(field), _ptr(out), _ptr(ct_out), _ptr(ct_mse), _ptr(gin), _ptr(gmod), _ptr(gz), _ptr(H), _ptr(z),
                                      N, F, dx, dy, k, _lib.XL_CONJ_IN | _lib.XL_CONJ_OUT | (_lib.XL_PHASE_BLIND if ctx.phase_blind else 0),
                                      ctypes.byref(fuse), _ptr(ws), ws.numel(), _stream(field)), "xl_rs_bwd_fused")
         if want_f and not field.is_complex():
             gin = gin.real
-        return gin, gz, gmod, None, None, None, None, None
+        return gin, gz, gmod, None, None, None, None, None, None
 
 
-def rs_propagation_fused(field, z, dx, dy, k, mod=None, target=None, phase_blind=False):
+def rs_transfer_pairs(zs, N, dx, dy, k, device):
+    """The transfer function AND its reduced z-derivative for every distance in `zs` (floats or one-element tensors), all in
+    ONE launch pair (xl_rs_transfer_multi) instead of two launches per propagation and pass: the fixed per-step cost of an
+    optimizer whose distances are known when the step starts.  Returns [(H, Hz), ...] for rs_propagation_fused(pre=...)."""
+    L = _lib.lib()
+    ref = torch.empty(0, device=device)
+    _require_device(ref)
+    nb = int(L.xl_rs_transfer_bytes(N))
+    stride = (nb + 255) // 256 * 256
+    zcat = torch.cat([_as_z(z, ref).detach() for z in zs])
+    buf = torch.empty(2 * len(zs) * stride, dtype=torch.uint8, device=device)
+    with (torch.cuda.device(ref.device) if ref.is_cuda else contextlib.nullcontext()):
+        _lib.check(L.xl_rs_transfer_multi(_ptr(buf), stride, _ptr(zcat), 2 * len(zs), 1, N, float(dx), float(dy), float(k), 0,
+                                          _stream(ref)), "xl_rs_transfer_multi")
+    return [(buf[2 * i * stride:2 * i * stride + nb], buf[(2 * i + 1) * stride:(2 * i + 1) * stride + nb]) for i in range(len(zs))]
+
+
+def rs_propagation_fused(field, z, dx, dy, k, mod=None, target=None, phase_blind=False, pre=None):
     """Scalar RS propagation of a batch `field` (F,N,N) with the pointwise elements around it fused into the kernels
     (N <= 2048): every field is multiplied by the shared complex plane `mod` (N,N) while it is loaded -- a phase-only SLM
     exp(i phi), an amplitude mask, the beam under a batch of real object masks (then `field` may be float32) -- and, with
@@ -317,7 +337,8 @@ def rs_propagation_fused(field, z, dx, dy, k, mod=None, target=None, phase_blind
     mean((|out|^2 - target)^2) (float64) instead of the fields.  Differentiable in field, z and mod.
     `phase_blind=True` is the caller's guarantee that the loss is invariant under a global phase of this propagation's output
     (a single path that ends in an intensity detector): the i*k*out part of d/dz, which is then exactly zero, is dropped
-    instead of being evaluated as a complex64 cancellation residue."""
+    instead of being evaluated as a complex64 cancellation residue.  `pre` = one entry of
+    rs_transfer_pairs() for this z: the call then generates no transfer function itself."""
     N = field.shape[-1]
     if field.dim() != 3 or field.shape[-2] != N:
         raise ValueError("rs_propagation_fused needs a batch of square fields (F, N, N)")
@@ -330,7 +351,7 @@ def rs_propagation_fused(field, z, dx, dy, k, mod=None, target=None, phase_blind
         raise ValueError("mod must be one (N, N) plane shared by the batch")
     if t is not None and t.shape != f.shape:
         raise ValueError("target must have the shape of the batch")
-    return _RSFused.apply(f, _as_z(z, f), m, t, float(dx), float(dy), float(k), bool(phase_blind))
+    return _RSFused.apply(f, _as_z(z, f), m, t, float(dx), float(dy), float(k), bool(phase_blind), pre)
 
 
 FUSED_MAX_N = 2048   # largest grid of the fused single-pass path (padded length 4096); above it: the stage chain of slab.py

@@ -12,7 +12,7 @@ Host logic only (torch.distributed is plumbing); works with the gloo backend on 
 import torch
 import torch.distributed as dist
 
-__all__ = ["shard_range", "shard", "allreduce_grads"]
+__all__ = ["shard_range", "shard", "allreduce_grads", "flat_grad_buffers", "allreduce_flat"]
 
 
 def shard_range(n_units, rank, world):
@@ -57,3 +57,32 @@ def allreduce_grads(grads, average=False):
             r.copy_(flat[off:off + r.numel()].view_as(r))
             off += r.numel()
     return grads
+
+
+def flat_grad_buffers(params):
+    """Give every parameter a persistent `.grad` that is a VIEW of one flat buffer per dtype (autograd accumulates into an
+    existing .grad in place, optimizers read it in place): the per-step gradient all-reduce is then one collective per dtype
+    on the flat buffers themselves -- no concatenation before and no scatter after (`allreduce_flat`).  Returns the buffers."""
+    groups = {}
+    for p in params:
+        groups.setdefault((p.dtype, p.device), []).append(p)
+    flats = []
+    for (dtype, device), ps in groups.items():
+        flat = torch.zeros(sum(p.numel() for p in ps), dtype=dtype, device=device)
+        off = 0
+        for p in ps:
+            p.grad = flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+        flats.append(flat)
+    return flats
+
+
+def allreduce_flat(flats, average=False):
+    """Sum (or average) the flat gradient buffers of `flat_grad_buffers` over all ranks; no-op without a process group."""
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return flats
+    for flat in flats:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+        if average:
+            flat /= dist.get_world_size()
+    return flats
