@@ -79,6 +79,11 @@ template <class Body> static int xl_launch_persistent(int items, int per_sm, xl_
 #ifdef XL_HOST_EMU
     const int slots = 3;
 #else
+    // resident CTAs per SM: what the register budget of the launch bounds (XlMinBlocks: 512 threads per SM) and the shared
+    // memory (227 KB per SM, 1 KB reserved per CTA) allow -- 2 at L = 4096, 4 at L = 2048, 8 at L = 1024
+    int fit = (int)((227u * 1024u) / (Body::smem() + 1024u));
+    if (fit > XlMinBlocks<Body>::value) fit = XlMinBlocks<Body>::value;
+    if (fit > per_sm) per_sm = fit;
     const int slots = per_sm * xl_sm_count();
 #endif
     (void)per_sm;
