@@ -54,6 +54,11 @@ enum {
                               propagation is multiplied by a global phase (every table whose paths through this plane end
                               in intensity detectors).  Then Im sum ct_out*out is exactly zero and the i k out part of d/dz
                               is dropped instead of being evaluated as a complex64 cancellation residue. */
+    XL_WITH_HZ = 128, /* RS / VRS, forward AND backward call of one propagation: `H` is twice xl_rs_transfer_bytes(N) and also
+                         holds the reduced dH/dz of the same distance.  The forward call generates both together (the
+                         impulse response and its derivative share r, exp(i k r) and the powers of 1/r: one launch pair
+                         instead of two), the backward call with grad_z takes dH/dz from there instead of generating it.
+                         For callers that know at forward time that z needs a gradient. */
     XL_REUSE_TABLES = 32   /* CZT family: `tables` already holds the tables of these sizes, grids and z (e.g. the backward
                               call of a propagation whose forward call filled them) */
 };

@@ -62,6 +62,7 @@ XL_CONJ_OUT = 2
 XL_REUSE_H = 16
 XL_REUSE_TABLES = 32
 XL_PHASE_BLIND = 64
+XL_WITH_HZ = 128
 
 
 class RsFuse(ctypes.Structure):

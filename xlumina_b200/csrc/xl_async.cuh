@@ -80,6 +80,7 @@ XL_DEV void xl_bulk_tile(void* dst, const void* src, size_t bytes, xl_mbar_t* b)
 // ==================================================================================================================
 template <int L> struct XlRsColsAsyncOp : XlOpBase {
     static constexpr bool kInLoHalf = true, kOutLoHalf = true;
+    static constexpr bool kSpecSyncCta = true;   // after_spec_sync() overwrites the staging buffer every thread has just read
     static constexpr int R1 = xl_first_radix(L), S1 = L / R1;
     static constexpr int HCR = xl_hc_rows(L);
     const XlRsParams& p;
@@ -268,12 +269,15 @@ template <int L> struct XlRsColsGzAsync {
             }
             XlRsColsGzAsyncOp<L> op{{}, p, item_in(p, it), stage, bar, parity, s, red};
             XlFft<L, 2>::forward(s, t, op);
-            XL_SYNC();                                   // spectrum phase done: tile line 0 complete, staging buffer free
             if (!(p.flags & XL_F_NOFIELD)) {
+                // spectrum phase done.  The first inverse pass went back into the slots this thread had read, and the B = 256
+                // level that follows stays inside the half-warp's block of 256 positions: a warp-level barrier is enough
+                // (the staging buffer is not reused before the CTA barrier that ends the item)
+                XlFft<L, 2>::template sync_local<XlFft<L, 2>::kHasMid>();
                 XlRsColsGzOutOp<L> oo{{}, p, p.spec + (size_t)f * L * p.N + (size_t)(g >> 1) * p.N * XL_V, g & 1};
                 XlFft<L, 1, XlTileLine0Of2>::inverse_tail(s, t, oo);
-                XL_SYNC();                               // the last pass has read the tile
             }
+            XL_SYNC();                                   // the last pass has read the tile; the staging buffer is free
         }
         // one reduction and one atomic per CTA
         XL_THREADS(tid, NT) {

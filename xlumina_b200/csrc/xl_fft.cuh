@@ -215,6 +215,7 @@ template <int NQ, int DIR> XL_DEV void xl_twiddle(cf* v, const cf* w) {
 struct XlOpBase {
     static constexpr bool kInLoHalf = false;   // load() is identically zero for i >= L/2 (compile-time pruning)
     static constexpr bool kOutLoHalf = false;  // store_vec() only receives positions < L/2
+    static constexpr bool kSpecSyncCta = false; // conv(): after_spec_sync() needs every thread of the CTA past the spectrum phase
     // run-time (CTA-uniform) version of kInLoHalf: skips the loads and prologue math of the upper half, keeps the full
     // butterfly -- for ops whose sizes are not known at compile time and whose variants are too many to double
     XL_DEV bool in_lo_rt() const { return false; }
@@ -258,6 +259,20 @@ template <int L, int V, class Tile = XlTile<V>> struct XlFft {
         }
         XL_SYNC();
     }
+
+    // Barrier between two passes.  The passes inside a block of 256 positions (the B = 256 level and the contiguous-16 pass,
+    // forward and inverse) are private to one half-warp: the thread that owns butterfly beta of the contiguous pass reads
+    // positions 16 beta + j, which the B = 256 level wrote from threads 16 (beta / 16) + j -- and the other way round on the
+    // way back.  A warp-level barrier is enough there (XL_NO_SYNCWARP: A/B switch back to CTA barriers), so the warps of a
+    // CTA drift apart and their shared-memory and butterfly phases overlap instead of alternating in lock-step.
+    template <bool HALF_WARP_LOCAL> XL_DEV static void sync_local() {
+#ifdef XL_NO_SYNCWARP
+        XL_SYNC();
+#else
+        if (HALF_WARP_LOCAL) XL_SYNCWARP(); else XL_SYNC();
+#endif
+    }
+    static constexpr bool kHasMid = (L / R1) >= 256;   // a B = 256 level exists: spectrum <-> next pass is half-warp local
 
     // ---- forward ----
     template <class Op> XL_DEV static void fwd_first(cf* s, const cf* t, const Op& op) {
@@ -309,7 +324,7 @@ template <int L, int V, class Tile = XlTile<V>> struct XlFft {
                 for (int q = 0; q < 16; ++q) Tile::st(s, base + S * q, v + q, 16);
             }
         }
-        XL_SYNC();
+        sync_local<B == 256>();   // the pass after the B = 256 level is the contiguous-16 pass
     }
     template <int B> XL_DEV static void fwd_mids(cf* s, const cf* tw) {
         if constexpr (B >= 256) { fwd_mid<B>(s, tw); fwd_mids<B / 16>(s, tw); }
@@ -394,7 +409,8 @@ template <int L, int V, class Tile = XlTile<V>> struct XlFft {
                 for (int j = 0; j < 16; ++j) Tile::st(s, 16 * beta + j, v + j, 16);
             }
         }
-        XL_SYNC();
+        // ops that hand their staging buffer to the asynchronous proxy here (after_spec_sync) need the CTA barrier
+        sync_local<kHasMid && !Op::kSpecSyncCta>();
         XL_THREADS(tid, NT) { op.after_spec_sync(tid); }
         inv_mids<L / R1>(s, t);
         inv_last(s, t, op);
@@ -416,7 +432,7 @@ template <int L, int V, class Tile = XlTile<V>> struct XlFft {
                 for (int j = 0; j < 16; ++j) Tile::st(s, 16 * beta + j, v + j, 16);
             }
         }
-        XL_SYNC();
+        sync_local<kHasMid>();
         inv_mids<L / R1>(s, t);
         inv_last(s, t, op);
     }

@@ -11,10 +11,6 @@ static inline int rs_base_params(XlRsParams& p, int N, double dx, double dy, dou
     p.rows = N; p.chunk_rows = N;
     p.dx = dx; p.dy = dy; p.k = k;
     p.hscale = (float)(dx * dy / ((double)p.L * (double)p.L));
-    {   // development knob (experiments only): XL_STAGGER_NS de-phases the two persistent CTAs of an SM
-        static const char* e = getenv("XL_STAGGER_NS");
-        p.stagger_ns = e ? (unsigned)atoi(e) : 0;
-    }
     p.tw = xl_twiddles();
     if (!p.tw) return xl_fail(XL_E_CUDA, "twiddle table allocation failed%s", "");
     return XL_OK;

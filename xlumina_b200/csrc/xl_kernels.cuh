@@ -75,6 +75,18 @@ template <unsigned MASK> XL_DEV void xl_blocked_load2(const cf* grp, int y0, int
 #endif
 }
 
+// Two planes with the blocked pair layout: the calling thread owns slot g of row y of plane A (va) and of plane B (vb).
+// GPU: lanes 2k and 2k+1 swap one value; the even lane stores slots (g, g+1) of A, the odd lane slots (g-1, g) of B.
+template <unsigned MASK> XL_DEV void xl_blocked_store_ab(cf* grpA, cf* grpB, int y, bool ok, int g, cf va, cf vb) {
+#ifdef XL_HOST_EMU
+    if (ok) { grpA[(size_t)y * 2 + (g & 1)] = va; grpB[(size_t)y * 2 + (g & 1)] = vb; }
+#else
+    const bool odd = g & 1;
+    const cf got = xl_xchg1<MASK>(odd ? va : vb);
+    if (ok) xl_st4((odd ? grpB : grpA) + (size_t)y * 2, odd ? got : va, odd ? vb : got);
+#endif
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // Rayleigh-Sommerfeld impulse response, reference wave_optics.py:291-297:
 //   h = (1/2pi) * z/r^2 * (1/r - i k) * exp(sgn(z) i k r),  r = sqrt(X^2+Y^2+z^2)
@@ -84,7 +96,7 @@ template <unsigned MASK> XL_DEV void xl_blocked_load2(const cf* grp, int y0, int
 // g' = -3/r^4 + 2 i k/r^3:   h_z - i k h = (e/2pi) [ g + (z^2/r) g' + i k g z (|z|/r - 1) ],  |z|/r - 1 = -rho^2/(r (r + |z|)).
 // dh/dz is dominated by i k h (a pure phase rotation), whose contribution to the gradient of any intensity-type loss
 // cancels identically; in complex64 the cancellation residue of that term buries the answer.  The library therefore
-// evaluates it exactly in real space (gz += -k Im sum ct*out, XlDotZ) and pushes only the reduced kernel, 1e2-1e4 times
+// evaluates it exactly in real space (gz += -k Im sum ct*out, on the way through rs_rows_dual) and pushes only the reduced kernel, 1e2-1e4 times
 // smaller, through the FFT pipeline.
 // ------------------------------------------------------------------------------------------------------------------
 // 1/sqrt(r2) to ~1e-13 relative, branch-free (fp32 rsqrt seed + one fp64 Newton step); NaN for r2 == 0
@@ -108,7 +120,8 @@ XL_DEV XlRsHConst xl_rs_hconst(double z, double k) {
     c.sg = z > 0 ? 1.0 : -1.0;
     return c;
 }
-XL_DEV cf xl_rs_h(double X, double Y, const XlRsHConst& c, int deriv) {
+// WHICH: bit 0 = h, bit 1 = the reduced derivative; both share r, the phase factor and the powers of 1/r
+template <int WHICH> XL_DEV void xl_rs_h_eval(double X, double Y, const XlRsHConst& c, cf* h, cf* hz) {
     const double inv2pi = 0.15915494309189535;
     const double r2 = X * X + Y * Y + c.z2;
     const double y = xl_rsqrt64(r2);                  // 1/r
@@ -121,22 +134,25 @@ XL_DEV cf xl_rs_h(double X, double Y, const XlRsHConst& c, int deriv) {
     // amplitude (complex, multiplies the phase factor) in fp64, rounded once: gradients of intensity-type losses with
     // respect to z cancel the leading term of dh/dz, which amplifies amplitude rounding by ~k*r
     const double ir2 = y * y, ir3 = ir2 * y;
-    double ar, ai;
-    if (!deriv) {
-        ar = c.z * inv2pi * ir3;
-        ai = -c.z * inv2pi * c.k * ir2;
-    } else {
+    if (WHICH & 1) {
+        const float far = (float)(c.z * inv2pi * ir3), fai = (float)(-c.z * inv2pi * c.k * ir2);
+        *h = make_float2(far * cs - fai * sn, far * sn + fai * cs);
+    }
+    if (WHICH & 2) {
         const double gr = ir3, gi = -c.k * ir2;
         const double gpr = -3.0 * ir2 * ir2, gpi = 2.0 * c.k * ir3;
         const double f = c.z2 * y;                                   // z^2/r
         const double az = c.z < 0 ? -c.z : c.z;
         const double w = -c.k * c.z * (X * X + Y * Y) * y / (r + az);   // k z (|z|/r - 1)
         // g + (z^2/r) g' + i w g
-        ar = (gr + f * gpr - w * gi) * inv2pi;
-        ai = (gi + f * gpi + w * gr) * inv2pi;
+        const float far = (float)((gr + f * gpr - w * gi) * inv2pi), fai = (float)((gi + f * gpi + w * gr) * inv2pi);
+        *hz = make_float2(far * cs - fai * sn, far * sn + fai * cs);
     }
-    const float far = (float)ar, fai = (float)ai;
-    return make_float2(far * cs - fai * sn, far * sn + fai * cs);
+}
+XL_DEV cf xl_rs_h(double X, double Y, const XlRsHConst& c, int deriv) {
+    cf h = cf_zero(), hz = cf_zero();
+    if (deriv) xl_rs_h_eval<2>(X, Y, c, &h, &hz); else xl_rs_h_eval<1>(X, Y, c, &h, &hz);
+    return deriv ? hz : h;
 }
 
 // ==================================================================================================================
@@ -164,7 +180,6 @@ struct XlRsParams {
     const double* z;   // device scalar
     double x0, y0, dx, dy, k;
     float hscale;      // dx*dy/L^2
-    unsigned stagger_ns;   // persistent kernels: the second CTA of an SM starts this much later (de-phases the two CTAs)
     // Pointwise elements fused into the first / last pass (xl_rs_fwd_fused / xl_rs_bwd_fused):
     const cf* mod;         // shared complex plane [N][N] multiplied into every field while it is loaded: a phase-only SLM
                            // exp(i phi) (optical_elements.py:87-103) or the beam under a batch of masks; null: none
@@ -174,6 +189,8 @@ struct XlRsParams {
     const cf* seed_out;    // backward: primal output; the cotangent of the fused detection is formed from it and `target`
     const double* ct_mse;  // [nfields] dL/dmse
     cf* ct_mod;            // backward: cotangent of `mod` (summed over the fields)
+    const cf* dz_out;      // rs_rows_dual: primal output [nfields][N][N]; gz += -k Im sum ct*out (the i k h part of dh/dz, exactly:
+                           // fp32 x fp32 products are exact in fp64) while the cotangent is loaded anyway; null: not wanted
 };
 
 // input of the fused forward pass: plane f (complex64 or float32) x the shared complex plane
@@ -262,12 +279,18 @@ template <int L, bool FUSE = false> struct XlRsRowsFwd {
 template <int L, bool EZ, bool FUSE = false> struct XlRsRowsDualOp : XlOpBase {
     static constexpr bool kInLoHalf = true;
     const XlRsParams& p; int f, y; double z2; float sw;   // sw: seed weight of the fused detection
+    mutable double dz;   // this thread's partial sum of Im(ct*out) (dz_out); the host emulation shares one op between the threads
     XL_DEV void load(int i, cf* v, int stride) const {
         const int N = p.N;
         const bool ok = i < N;
         const size_t NN = (size_t)p.rows * N, o = ok ? (size_t)y * N + i : 0;
         cf c = (FUSE && p.seed_out) ? xl_seed_ct(p, sw, (size_t)f * NN, o) : p.in[(size_t)f * NN + o], w;
         if (p.flags & XL_F_CONJ_IN) c = cf_conj(c);
+        if (p.dz_out) {   // kernel-uniform
+            const cf u = p.dz_out[(size_t)f * NN + o];
+            const double t = (double)c.x * (double)u.y + (double)c.y * (double)u.x;   // Im(ct*out)
+            dz += ok ? t : 0.0;
+        }
         if (EZ) {
             const cf ex = p.in2[o], ey = p.in2[p.ey_off + (long long)o];
             const double X = p.x0 + i * p.dx, Y = p.y0 + y * p.dy;
@@ -295,21 +318,34 @@ template <int L, bool FUSE = false> struct XlRsRowsDual {
     static const char* name() { return FUSE ? "rs_rows_dual_f" : "rs_rows_dual"; }
     typedef XlRsParams Params;
     static constexpr int NT = xl_threads(L);
-    static size_t smem() { return xl_smem_bytes(L, XL_V); }
+    static size_t smem() { return xl_smem_bytes(L, XL_V) + NT * sizeof(double); }
+    // gz += -k * (sum over the CTA of the per-thread partial sums `acc`)
+    XL_DEV static void dz_flush(const Params& p, double* red, double acc) {
+        XL_THREADS(tid, NT) { red[tid] = XL_PER_THREAD(tid, acc); }
+        XL_SYNC();
+        xl_block_sum<NT>(red);
+        XL_THREADS(tid, NT) {
+            if (tid == 0) xl_atomic_add(p.gz, -p.k * red[0]);
+        }
+    }
     XL_DEV static void run(const Params& p, cf* s) {
         cf* t = s + xl_tile_elems(L, XL_V);
+        double* red = (double*)(t + xl_tw_total(L));
         XlFft<L, XL_V>::init_tw(t, p.tw);
         const int f = p.f0 + XL_BLOCK_Y, y = XL_BLOCK_X;
         if (FUSE) {
-            XlRsRowsDualOp<L, false, true> op{{}, p, f, y, 0.0, xl_seed_weight(p, f)};
+            XlRsRowsDualOp<L, false, true> op{{}, p, f, y, 0.0, xl_seed_weight(p, f), 0.0};
             XlFft<L, XL_V>::forward(s, t, op);
+            if (p.dz_out) dz_flush(p, red, op.dz);     // kernel-uniform
         } else if ((p.flags & XL_F_VRS) && f == 2) {   // CTA-uniform
             const double z = xl_ldg(p.z);
-            XlRsRowsDualOp<L, true> op{{}, p, f, y, z * z, 0.f};
+            XlRsRowsDualOp<L, true> op{{}, p, f, y, z * z, 0.f, 0.0};
             XlFft<L, XL_V>::forward(s, t, op);
+            if (p.dz_out) dz_flush(p, red, op.dz);
         } else {
-            XlRsRowsDualOp<L, false> op{{}, p, f, y, 0.0, 0.f};
+            XlRsRowsDualOp<L, false> op{{}, p, f, y, 0.0, 0.f, 0.0};
             XlFft<L, XL_V>::forward(s, t, op);
+            if (p.dz_out) dz_flush(p, red, op.dz);
         }
     }
 };
@@ -568,6 +604,7 @@ template <int L> struct XlHRowsOp : XlOpBase {
     const XlRsParams& p; int yb; const cf* stage;   // stage[(L/2+1)][XL_V]
     int nvalid;   // local rows that exist (global row <= L/2)
     cf* H;        // this item's buffer
+    cf* Hz;       // dual mode: the two lines are row yb of h and of its reduced z-derivative, which goes here; else null
     XL_DEV void load(int i, cf* v, int stride) const {
         const int xi = i <= L / 2 ? i : L - i;
         xl_ld4(stage + (size_t)xi * XL_V, v, v + stride);
@@ -579,7 +616,9 @@ template <int L> struct XlHRowsOp : XlOpBase {
             // rest is mirrored.  slab: every slot pair, rows in a [pair][rows][2] buffer of this rank's y rows.
             const int g = q * (L / 16) + beta;
             if (!p.hstore_all && (q > 8 || (q == 8 && beta >= 2))) continue;
-            xl_blocked_store2<xl_lane_mask(L)>(H + (size_t)(g / 2) * p.rows * 2, yb, nvalid, g, v[q], v[16 + q]);
+            const size_t o = (size_t)(g / 2) * p.rows * 2;
+            if (Hz) xl_blocked_store_ab<xl_lane_mask(L)>(H + o, Hz + o, yb, yb < nvalid, g, v[q], v[16 + q]);
+            else xl_blocked_store2<xl_lane_mask(L)>(H + o, yb, nvalid, g, v[q], v[16 + q]);
         }
     }
     XL_DEV void store_vec(int, const cf*) const {}
@@ -590,23 +629,35 @@ template <int L> struct XlHRows {
     static constexpr int NT = xl_threads(L);
     static constexpr int NSTAGE = (L / 2 + 2) * XL_V;   // +1 sample of slack keeps the size even (16-byte rows)
     static size_t smem() { return xl_smem_bytes(L, XL_V) + (size_t)NSTAGE * sizeof(cf); }
+    // h_per_z == 2 (H and the reduced dH/dz of the same distance, buffers 2j and 2j+1): one CTA transforms row y of BOTH as
+    // its two lines, so r, exp(i k r) and the powers of 1/r of a sample are evaluated once (blockIdx.x = y, blockIdx.y = j).
     XL_DEV static void run(const Params& p, cf* s) {
         cf* t = s + xl_tile_elems(L, XL_V);
         cf* stage = t + xl_tw_total(L);
-        const int yb = XL_BLOCK_X * XL_V;
-        const int item = XL_BLOCK_Y, per = p.h_per_z > 0 ? p.h_per_z : 1;
-        const XlRsHConst hc = xl_rs_hconst(xl_ldg(p.z + item / per), p.k);
-        const int deriv = per == 2 ? (item & 1) : ((p.flags & XL_F_DERIV) ? 1 : 0);
+        const bool dual = p.h_per_z == 2;
+        const int yb = dual ? XL_BLOCK_X : XL_BLOCK_X * XL_V;
+        const int item = XL_BLOCK_Y;
+        const XlRsHConst hc = xl_rs_hconst(xl_ldg(p.z + item), p.k);
+        const int deriv = (p.flags & XL_F_DERIV) ? 1 : 0;
         XL_THREADS(tid, NT) {
-            for (int e = tid; e < (L / 2 + 1) * XL_V; e += NT) {
-                const int xi = e / XL_V, l = e % XL_V, yi = p.hrow0 + yb + l;   // global y row
-                stage[e] = yi <= L / 2 ? xl_rs_h(xi * p.dx, yi * p.dy, hc, deriv) : cf_zero();
+            if (dual) {
+                for (int xi = tid; xi < L / 2 + 1; xi += NT) {
+                    cf h, hz;
+                    xl_rs_h_eval<3>(xi * p.dx, (p.hrow0 + yb) * p.dy, hc, &h, &hz);
+                    xl_st4(stage + (size_t)xi * XL_V, h, hz);
+                }
+            } else {
+                for (int e = tid; e < (L / 2 + 1) * XL_V; e += NT) {
+                    const int xi = e / XL_V, l = e % XL_V, yi = p.hrow0 + yb + l;   // global y row
+                    stage[e] = yi <= L / 2 ? xl_rs_h(xi * p.dx, yi * p.dy, hc, deriv) : cf_zero();
+                }
             }
         }
         XlFft<L, XL_V>::init_tw(t, p.tw);   // ends with a barrier: stage[] is visible
         int nvalid = L / 2 + 1 - p.hrow0;
         if (nvalid > p.rows) nvalid = p.rows;
-        XlHRowsOp<L> op{{}, p, yb, stage, nvalid, p.H + (long long)item * p.h_stride};
+        cf* H = p.H + (long long)item * (dual ? 2 : 1) * p.h_stride;
+        XlHRowsOp<L> op{{}, p, yb, stage, nvalid, H, dual ? H + p.h_stride : (cf*)0};
         XlFft<L, XL_V>::forward(s, t, op);
     }
 };
@@ -911,6 +962,9 @@ template <int L, int PRO, int EPI, int ACC> struct XlCztAxis {
     typedef XlCztParams Params;
     static constexpr int NT = xl_threads(L);
     static size_t smem() { return xl_smem_bytes(L, XL_V); }
+    // One CTA per (line pair, component).  A persistent variant (resident CTAs walking the items, twiddles and the kernel
+    // spectrum staged once per CTA) was measured in round 2 and lost 20-35 %: without asynchronous staging of the next
+    // item's input the two CTAs of an SM stay in lock-step, while CTAs handed out by the hardware start out of phase.
     XL_DEV static void run(const Params& p, cf* s) {
         cf* t = s + xl_tile_elems(L, XL_V);
         XlFft<L, XL_V>::init_tw(t, p.tw);
@@ -1060,40 +1114,6 @@ template <int L> struct XlCztKernelFft {
         XlFft<L, XL_V>::init_tw(t, pp.tw);
         XlCztKernelFftOp<L> op{{}, p};
         XlFft<L, XL_V>::forward(s, t, op);
-    }
-};
-
-// gz += -k Im sum ct*out : the i k h part of dh/dz, evaluated exactly (fp32 x fp32 products are exact in fp64).
-struct XlDotZParams {
-    const cf* ct; const cf* out; size_t n; int flags; double k; double* gz;
-};
-struct XlDotZ {
-    static const char* name() { return "dot_z"; }
-    typedef XlDotZParams Params;
-    static constexpr int NT = 256;
-    static constexpr int PER = 8;   // elements per thread
-    static size_t smem() { return NT * sizeof(double); }
-    XL_DEV static void run(const Params& p, cf* s) {
-        double* red = (double*)s;
-        XL_THREADS(tid, NT) {
-            double acc = 0.0;
-            const size_t base = (size_t)XL_BLOCK_X * NT * PER + tid;
-#pragma unroll
-            for (int e = 0; e < PER; ++e) {
-                const size_t idx = base + (size_t)e * NT;
-                if (idx < p.n) {
-                    const cf c = p.ct[idx], o = p.out[idx];
-                    const double ci = (p.flags & XL_F_CONJ_IN) ? -(double)c.y : (double)c.y;
-                    acc += (double)c.x * (double)o.y + ci * (double)o.x;   // Im(ct*out)
-                }
-            }
-            red[tid] = acc;
-        }
-        XL_SYNC();
-        xl_block_sum<NT>(red);
-        XL_THREADS(tid, NT) {
-            if (tid == 0) xl_atomic_add(p.gz, -p.k * red[0]);
-        }
     }
 };
 

@@ -34,6 +34,9 @@ extern thread_local xl_dim3 xl_emu_gridDim;
 #define XL_BLOCK_Z (xl_emu_blockIdx.z)
 #define XL_THREADS(tid, nthr) for (int tid = 0; tid < (nthr); ++tid)
 #define XL_SYNC() do { } while (0)
+#define XL_SYNCWARP() do { } while (0)
+// a value every GPU thread holds in its own register; the emulation shares one copy between the threads of a phase
+#define XL_PER_THREAD(tid, v) ((tid) == 0 ? (v) : 0)
 static inline void xl_sincospi(double a, double* s, double* c) { *s = sin(M_PI * a); *c = cos(M_PI * a); }
 static inline void xl_sincospif(float a, float* s, float* c) { *s = (float)sin(M_PI * (double)a); *c = (float)cos(M_PI * (double)a); }
 static inline void xl_sincosf(float a, float* s, float* c) { *s = sinf(a); *c = cosf(a); }
@@ -61,6 +64,8 @@ static inline void xl_nanosleep(unsigned) {}
 #define XL_BLOCK_Z ((int)blockIdx.z)
 #define XL_THREADS(tid, nthr) for (int tid = (int)threadIdx.x, _xl_once = 1; _xl_once; _xl_once = 0)
 #define XL_SYNC() __syncthreads()
+#define XL_SYNCWARP() __syncwarp()
+#define XL_PER_THREAD(tid, v) (v)
 XL_DEV void xl_sincospi(double a, double* s, double* c) { sincospi(a, s, c); }
 XL_DEV void xl_sincospif(float a, float* s, float* c) { sincospif(a, s, c); }
 XL_DEV void xl_sincosf(float a, float* s, float* c) { sincosf(a, s, c); }

@@ -162,11 +162,12 @@ def _z_key(z):
     return ("t", id(z), z._version) if isinstance(z, torch.Tensor) else ("f", float(z))
 
 
-def _cached_transfer(zkey, zobj, N, dx, dy, k, device, nbytes):
-    """(H, reuse): H is a device buffer for the transfer function, reuse says whether it already holds it."""
+def _cached_transfer(zkey, zobj, N, dx, dy, k, device, nbytes, with_hz=0):
+    """(H, reuse): H is a device buffer for the transfer function (with_hz: followed by the reduced dH/dz of the same
+    distance), reuse says whether it already holds it."""
     if _transfer_cache_size == 0 or zkey is None:
         return torch.empty(nbytes, dtype=torch.uint8, device=device), False
-    key = (zkey, N, dx, dy, k, device, torch.cuda.current_stream(device).cuda_stream)
+    key = (zkey, N, dx, dy, k, device, torch.cuda.current_stream(device).cuda_stream, with_hz)
     hit = _transfer_cache.get(key)
     if hit is not None:
         _transfer_cache.move_to_end(key)
@@ -189,13 +190,16 @@ class _RS(torch.autograd.Function):
         L = _lib.lib()
         F, N = field.shape[0], field.shape[-1]
         out = torch.empty_like(field)
-        H, reuse = _cached_transfer(zkey, zobj, N, dx, dy, k, field.device, L.xl_rs_transfer_bytes(N))
+        # z needs a gradient: H and the reduced dH/dz are generated together, in one launch pair (XL_WITH_HZ)
+        hz = _lib.XL_WITH_HZ if z.requires_grad else 0
+        H, reuse = _cached_transfer(zkey, zobj, N, dx, dy, k, field.device, L.xl_rs_transfer_bytes(N) * (2 if hz else 1), hz)
         need = L.xl_rs_workspace_bytes(N, F, 0)
         ws = _workspace(field, need)
-        _lib.check(L.xl_rs_fwd(_ptr(field), _ptr(out), _ptr(H), _ptr(z), N, F, dx, dy, k, _lib.XL_REUSE_H if reuse else 0,
+        _lib.check(L.xl_rs_fwd(_ptr(field), _ptr(out), _ptr(H), _ptr(z), N, F, dx, dy, k, (_lib.XL_REUSE_H if reuse else 0) | hz,
                                _ptr(ws), ws.numel(), _stream(field)), "xl_rs_fwd")
         ctx.save_for_backward(field, z, H, out)      # out: the exact i*k*out part of d out/dz (include/xlprop.h)
         ctx.geom = (dx, dy, k)
+        ctx.hz = hz
         return out
 
     @staticmethod
@@ -212,7 +216,7 @@ class _RS(torch.autograd.Function):
         need = L.xl_rs_workspace_bytes(N, F, 1 if want_z else 0)
         ws = _workspace(field, need)
         _lib.check(L.xl_rs_bwd(_ptr(field), _ptr(out), _ptr(g), _ptr(gin), _ptr(gz), _ptr(H), _ptr(z), N, F, dx, dy, k,
-                               _lib.XL_CONJ_IN | _lib.XL_CONJ_OUT, _ptr(ws), ws.numel(), _stream(field)), "xl_rs_bwd")
+                               _lib.XL_CONJ_IN | _lib.XL_CONJ_OUT | ctx.hz, _ptr(ws), ws.numel(), _stream(field)), "xl_rs_bwd")
         return gin, gz, None, None, None, None, None
 
 
@@ -227,17 +231,19 @@ class _VRS(torch.autograd.Function):
         L = _lib.lib()
         N = ex.shape[-1]
         out = torch.empty((3, N, N), dtype=ex.dtype, device=ex.device)
+        hz = _lib.XL_WITH_HZ if z.requires_grad else 0         # H and the reduced dH/dz generated together
         if hshare is not None and hshare[0] is not None:       # later item of a batch that shares z: reuse its transfer function
             H, reuse = hshare[0], True
         else:
-            H, reuse = _cached_transfer(zkey, zobj, N, dx, dy, k, ex.device, L.xl_rs_transfer_bytes(N))
+            H, reuse = _cached_transfer(zkey, zobj, N, dx, dy, k, ex.device, L.xl_rs_transfer_bytes(N) * (2 if hz else 1), hz)
             if hshare is not None:
                 hshare[0] = H
         ws = _workspace(ex, L.xl_rs_workspace_bytes(N, 3, 0))
-        _lib.check(L.xl_vrs_fwd(_ptr(ex), _ptr(ey), _ptr(out), _ptr(H), _ptr(z), N, x0, y0, dx, dy, k, _lib.XL_REUSE_H if reuse else 0,
+        _lib.check(L.xl_vrs_fwd(_ptr(ex), _ptr(ey), _ptr(out), _ptr(H), _ptr(z), N, x0, y0, dx, dy, k, (_lib.XL_REUSE_H if reuse else 0) | hz,
                                 _ptr(ws), ws.numel(), _stream(ex)), "xl_vrs_fwd")
         ctx.save_for_backward(ex, ey, z, H, out)
         ctx.geom = (x0, y0, dx, dy, k)
+        ctx.hz = hz
         return out
 
     @staticmethod
@@ -253,8 +259,8 @@ class _VRS(torch.autograd.Function):
         gz = torch.zeros(1, dtype=torch.float64, device=ex.device) if want_z else None
         ws = _workspace(ex, L.xl_rs_workspace_bytes(N, 3, 1 if want_z else 0))
         _lib.check(L.xl_vrs_bwd(_ptr(ex), _ptr(ey), _ptr(out), _ptr(g), _ptr(gin), _ptr(gz), _ptr(H), _ptr(z), N, x0, y0, dx, dy, k,
-                                _lib.XL_CONJ_IN | _lib.XL_CONJ_OUT, _ptr(ws), ws.numel(), _stream(ex)), "xl_vrs_bwd")
-        return gin[0], gin[1], gz, None, None, None, None, None, None, None, None
+                                _lib.XL_CONJ_IN | _lib.XL_CONJ_OUT | ctx.hz, _ptr(ws), ws.numel(), _stream(ex)), "xl_vrs_bwd")
+        return ((gin, None) if ey is None else (gin[0], gin[1])) + (gz, None, None, None, None, None, None, None, None)
 
 
 class _RSFused(torch.autograd.Function):
@@ -408,11 +414,11 @@ def rs_propagation(field, z, dx, dy, k):
 
 
 def _planes(Ex, Ey):
-    """The two input planes of a vectorial operator as contiguous complex64 (N,N) tensors: views when `Ex` is a stacked
-    (2,N,N) pair (Ey=None), the caller's own tensors otherwise -- never a stacking copy."""
+    """The input of a vectorial operator as contiguous complex64: the caller's two (N,N) planes, or -- `Ex` a stacked (2,N,N)
+    pair, Ey=None -- the pair itself with None (the library then takes Ey = Ex + N*N, and the autograd node has ONE input
+    whose gradient is the (2,N,N) buffer the library fills: no per-plane select / accumulate kernels).  Never a copy."""
     if Ey is None:
-        e = _c64(Ex)
-        return e[0], e[1]
+        return _c64(Ex), None
     return _c64(Ex), _c64(Ey)
 
 
@@ -435,7 +441,7 @@ def vrs_propagation(Ex, Ey, z, x0, y0, dx, dy, k, _hshare=None):
     zt = _as_z(z, ex)
     N = ex.shape[-1]
     if N > FUSED_MAX_N:
-        exy = torch.stack([ex, ey])
+        exy = ex if ey is None else torch.stack([ex, ey])
         # large grids: Ez = (Ex X + Ey Y)/r (vectorized_optics.py:258-261) is formed pointwise here and the three components
         # go through the stage chain as one batch sharing the transfer function (differentiable in Ex, Ey only)
         xs = float(x0) + float(dx) * torch.arange(N, dtype=torch.float64, device=exy.device)
@@ -484,6 +490,7 @@ class _CZT(torch.autograd.Function):
         want_z = ctx.needs_input_grad[2]
         ctx.save_for_backward(z, tables, *((fin, ey, out) if want_z else ()))   # d/dz needs the primal input and result
         ctx.meta = (lam, vect, gin, gout, N)
+        ctx.stacked = bool(vect) and ey is None
         return out
 
     @staticmethod
@@ -496,7 +503,10 @@ class _CZT(torch.autograd.Function):
         L = _lib.lib()
         g = g.resolve_conj().contiguous()
         ct = torch.empty((2, N, N) if vect else (N, N), dtype=g.dtype, device=g.device)
-        grads = (lambda gz: (ct[0], ct[1], gz, None, None, None, None)) if vect else (lambda gz: (ct, None, gz, None, None, None, None))
+        if vect and not ctx.stacked:
+            grads = lambda gz: (ct[0], ct[1], gz, None, None, None, None)
+        else:
+            grads = lambda gz: (ct, None, gz, None, None, None, None)
         if ctx.needs_input_grad[2]:
             fin, ey, out = ctx.saved_tensors[2:]
             gz = torch.zeros(1, dtype=torch.float64, device=g.device)
@@ -553,6 +563,7 @@ class _HighNA(torch.autograd.Function):
                    "xl_highna_fwd")
         ctx.save_for_backward(tables)
         ctx.meta = (radius, f, lam, gin, gout, N)
+        ctx.stacked = ey is None
         return out
 
     @staticmethod
@@ -569,7 +580,7 @@ class _HighNA(torch.autograd.Function):
         _lib.check(L.xl_highna_bwd(_ptr(g), _ptr(ct), N, Mx, My, radius, f, lam, x0, dx, y0, dy, xo0, xol, yo0, yol,
                                    _lib.XL_CONJ_IN | _lib.XL_CONJ_OUT | _lib.XL_REUSE_TABLES, _ptr(tables), _ptr(ws), ws.numel(),
                                    _stream(g)), "xl_highna_bwd")
-        return ct[0], ct[1], None, None, None, None, None
+        return ((ct, None) if ctx.stacked else (ct[0], ct[1])) + (None, None, None, None, None)
 
 
 def _gout(xout, yout):
