@@ -62,7 +62,7 @@ def forward_loss(params, masks, targets, beam, dx, k, fused=True):
     return four_f.MSE_Intensity(inten, targets).sum()
 
 
-def setup(batch, n, dev, rank, world, fused=True, graph=False):
+def setup(batch, n, dev, rank, world, fused=True, graph=False, fused_adam=True):
     """Build the sharded optimizer problem on `dev`; returns (step, params, samples_on_this_rank).  step() runs one optimizer
     step (forward, backward, one flattened gradient all-reduce when world > 1, AdamW) and returns this rank's loss share."""
     N, lam = n, 0.6328
@@ -78,7 +78,8 @@ def setup(batch, n, dev, rank, world, fused=True, graph=False):
     prng = np.random.default_rng(1)                                   # four_f_optimizer.py:104-109
     params = [torch.tensor([prng.uniform(0.027, 1)], dtype=torch.float64, device=dev, requires_grad=True) for _ in range(3)]
     params += [torch.tensor(prng.uniform(0, 1, (N, N)).astype(np.float32), device=dev, requires_grad=True) for _ in range(2)]
-    opt = torch.optim.AdamW(params, lr=0.01, weight_decay=1e-4, capturable=True)   # optax.adamw(0.01, weight_decay=1e-4), :97-98,112
+    # optax.adamw(0.01, weight_decay=1e-4), four_f_optimizer.py:97-98,112; fused_adam: torch's single-kernel multi-tensor AdamW
+    opt = torch.optim.AdamW(params, lr=0.01, weight_decay=1e-4, capturable=True, fused=True if fused_adam else None)
     flats = flat_grad_buffers(params)       # .grad of every parameter = a view of one flat buffer per dtype
 
     def compute():
@@ -140,6 +141,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--unfused", action="store_true", help="pointwise elements and the loss as separate torch operations")
     ap.add_argument("--graph", action="store_true", help="replay forward+backward and AdamW as CUDA graphs (the all-reduce stays eager)")
+    ap.add_argument("--unfused-adam", action="store_true", help="torch.optim.AdamW without fused=True (the multi-tensor foreach kernels; round 2: +0.12 ms per step)")
     ap.add_argument("--graph-nccl", action="store_true", help="one CUDA graph for the whole step, the NCCL all-reduce captured too")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -150,7 +152,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     N = args.n
-    step, params, mine = setup(args.batch, N, dev, rank, world, fused=not args.unfused, graph=("nccl" if args.graph_nccl else args.graph))
+    step, params, mine = setup(args.batch, N, dev, rank, world, fused=not args.unfused, graph=("nccl" if args.graph_nccl else args.graph), fused_adam=not args.unfused_adam)
 
     def barrier():
         if world > 1:

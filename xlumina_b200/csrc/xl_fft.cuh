@@ -260,6 +260,48 @@ template <int L, int V, class Tile = XlTile<V>> struct XlFft {
         XL_SYNC();
     }
 
+    // The same tables, with the global loads (tw_fetch) and the shared-memory stores (tw_store) split so that a kernel can
+    // put its own first-pass global loads between them: the CTA start then pays ONE memory latency instead of two (ncu round
+    // 2: ~10 % of the samples of every one-item-per-CTA kernel sat on the stores of init_tw waiting for the twiddle loads).
+    // Each thread fetches exactly the entries it stores; entries [0, kTw0) are the level-0 twiddles of ITS butterflies
+    // n = tid + i NT of the first pass (w1, and w8 when R1 == 16), which fwd_first_g takes from the registers.
+    static constexpr int kTw0Iter = (S1 + NT - 1) / NT;
+    static constexpr int kTw0 = kTw0Iter * (R1 == 16 ? 2 : 1);
+    static constexpr int kTwRegs = kTw0 + 2 * ((L / R1) >= 4096 ? 2 : ((L / R1) >= 256 ? 1 : 0));
+    XL_DEV static void tw_fetch(int tid, const cf* XL_RESTRICT gtw, cf* r) {
+        int k = 0;
+#pragma unroll
+        for (int i = 0; i < kTw0Iter; ++i) {
+            const int n = tid + i * NT, m = n < S1 ? n : 0;
+            r[k++] = xl_ldg(gtw + m * (XL_TWN / L));
+            if (R1 == 16) r[k++] = xl_ldg(gtw + 8 * m * (XL_TWN / L));
+        }
+#pragma unroll
+        for (int B = L / R1; B >= 256; B /= 16) {
+            const int m = tid < B / 16 ? tid : 0;
+            r[k++] = xl_ldg(gtw + m * (XL_TWN / B));
+            r[k++] = xl_ldg(gtw + 8 * m * (XL_TWN / B));
+        }
+    }
+    XL_DEV static void tw_store(int tid, cf* t, const cf* r) {
+        int k = 0;
+#pragma unroll
+        for (int i = 0; i < kTw0Iter; ++i) {
+            const int n = tid + i * NT;
+            if (n < S1) t[n] = r[k];
+            ++k;
+            if (R1 == 16) { if (n < S1) t[S1 + n] = r[k]; ++k; }
+        }
+        int off = xl_tw_level0(L);
+#pragma unroll
+        for (int B = L / R1; B >= 256; B /= 16) {
+            const int nb = B / 16;
+            if (tid < nb) { t[off + tid] = r[k]; t[off + nb + tid] = r[k + 1]; }
+            k += 2;
+            off += 2 * nb;
+        }
+    }
+
     // Barrier between two passes.  The passes inside a block of 256 positions (the B = 256 level and the contiguous-16 pass,
     // forward and inverse) are private to one half-warp: the thread that owns butterfly beta of the contiguous pass reads
     // positions 16 beta + j, which the B = 256 level wrote from threads 16 (beta / 16) + j -- and the other way round on the
@@ -303,6 +345,44 @@ template <int L, int V, class Tile = XlTile<V>> struct XlFft {
         }
         XL_SYNC();
         XL_THREADS(tid, NT) { op.after_first_sync(tid); }   // every load() of this transform has completed in every thread
+    }
+    // first pass of a CTA that has NOT run init_tw: fetches the tables itself, behind the op's own global loads
+    template <class Op> XL_DEV static void fwd_first_g(cf* s, cf* t, const cf* XL_RESTRICT gtw, const Op& op) {
+        XL_THREADS(tid, NT) {
+            op.before_first();
+            cf tr[kTwRegs];
+            tw_fetch(tid, gtw, tr);
+            int it = 0;
+            for (int n = tid; n < S1; n += NT, ++it) {
+                cf v[V * R1];
+#pragma unroll
+                for (int j = 0; j < (Op::kInLoHalf ? R1 / 2 : R1); ++j) {   // line l -> v[l*R1 + j]
+                    if (!Op::kInLoHalf && j >= R1 / 2 && op.in_lo_rt()) {
+#pragma unroll
+                        for (int l = 0; l < V; ++l) v[l * R1 + j] = cf_zero();
+                    } else {
+                        op.load(n + S1 * j, v + j, R1);
+                    }
+                }
+                cf w[R1];
+                cf w1 = tr[0], w8 = cf_zero();
+#pragma unroll
+                for (int i = 0; i < kTw0Iter; ++i)      // compile-time register index
+                    if (i == it) { w1 = tr[i * (R1 == 16 ? 2 : 1)]; if (R1 == 16) w8 = tr[i * 2 + 1]; }
+                xl_tw_powers<R1>(w, w1, w8);
+#pragma unroll
+                for (int l = 0; l < V; ++l) {
+                    XlBfly<R1, -1, Op::kInLoHalf, false>::run(v + l * R1);
+                    xl_twiddle<R1, -1>(v + l * R1, w);
+                }
+#pragma unroll
+                for (int q = 0; q < R1; ++q) Tile::st(s, n + S1 * q, v + q, R1);
+            }
+            tw_store(tid, t, tr);
+            op.before_first_sync();
+        }
+        XL_SYNC();
+        XL_THREADS(tid, NT) { op.after_first_sync(tid); }
     }
     template <int B> XL_DEV static void fwd_mid(cf* s, const cf* tw) {
         constexpr int S = B / 16;
@@ -374,9 +454,9 @@ template <int L, int V, class Tile = XlTile<V>> struct XlFft {
     }
 
     // ---- whole-tile drivers (s = tile of xl_tile_elems(L,V) cf, t = twiddle tables filled by init_tw) ----
+    // The *_g drivers are for CTAs that have not run init_tw: they take the global master table and fill `t` on the way.
     // FWD: op.load -> spectrum; op.spec(beta, v) consumes v[l*16 + q] = bin at slot q*(L/16)+beta of line l.
-    template <class Op> XL_DEV static void forward(cf* s, const cf* t, const Op& op) {
-        fwd_first(s, t, op);
+    template <class Op> XL_DEV static void forward_rest(cf* s, const cf* t, const Op& op) {
         fwd_mids<L / R1>(s, t);
         XL_THREADS(tid, NT) {
             op.before_spec();
@@ -390,9 +470,16 @@ template <int L, int V, class Tile = XlTile<V>> struct XlFft {
             }
         }
     }
-    // CONV: op.load -> forward -> op.spec multiplies in registers -> inverse -> op.store_vec.  (1/L is the op's business.)
-    template <class Op> XL_DEV static void conv(cf* s, const cf* t, const Op& op) {
+    template <class Op> XL_DEV static void forward(cf* s, const cf* t, const Op& op) {
         fwd_first(s, t, op);
+        forward_rest(s, t, op);
+    }
+    template <class Op> XL_DEV static void forward_g(cf* s, cf* t, const cf* gtw, const Op& op) {
+        fwd_first_g(s, t, gtw, op);
+        forward_rest(s, t, op);
+    }
+    // CONV: op.load -> forward -> op.spec multiplies in registers -> inverse -> op.store_vec.  (1/L is the op's business.)
+    template <class Op> XL_DEV static void conv_rest(cf* s, const cf* t, const Op& op) {
         fwd_mids<L / R1>(s, t);
         XL_THREADS(tid, NT) {
             op.before_spec();
@@ -415,14 +502,24 @@ template <int L, int V, class Tile = XlTile<V>> struct XlFft {
         inv_mids<L / R1>(s, t);
         inv_last(s, t, op);
     }
+    template <class Op> XL_DEV static void conv(cf* s, const cf* t, const Op& op) {
+        fwd_first(s, t, op);
+        conv_rest(s, t, op);
+    }
+    template <class Op> XL_DEV static void conv_g(cf* s, cf* t, const cf* gtw, const Op& op) {
+        fwd_first_g(s, t, gtw, op);
+        conv_rest(s, t, op);
+    }
     // the inverse passes after the first (whose output the caller has already put into the tile) -> op.store_vec
     template <class Op> XL_DEV static void inverse_tail(cf* s, const cf* t, const Op& op) {
         inv_mids<L / R1>(s, t);
         inv_last(s, t, op);
     }
-    // INV: op.spec fills v from a stored spectrum -> inverse -> op.store_vec.
-    template <class Op> XL_DEV static void inverse(cf* s, const cf* t, const Op& op) {
+    // INV: op.spec fills v from a stored spectrum -> inverse -> op.store_vec.  G: fill the tables on the way (no init_tw).
+    template <bool G, class Op> XL_DEV static void inverse_impl(cf* s, cf* t, const cf* gtw, const Op& op) {
         XL_THREADS(tid, NT) {
+            cf tr[G ? kTwRegs : 1];
+            if (G) tw_fetch(tid, gtw, tr);
             for (int beta = tid; beta < L / 16; beta += NT) {
                 cf v[V * 16];
                 op.spec(beta, v);
@@ -431,9 +528,13 @@ template <int L, int V, class Tile = XlTile<V>> struct XlFft {
 #pragma unroll
                 for (int j = 0; j < 16; ++j) Tile::st(s, 16 * beta + j, v + j, 16);
             }
+            if (G) tw_store(tid, t, tr);
         }
-        sync_local<kHasMid>();
+        // with G the CTA barrier also publishes the tables (when there is no B = 256 level the barrier is a CTA barrier anyway)
+        sync_local<kHasMid && !G>();
         inv_mids<L / R1>(s, t);
         inv_last(s, t, op);
     }
+    template <class Op> XL_DEV static void inverse(cf* s, const cf* t, const Op& op) { inverse_impl<false>(s, const_cast<cf*>(t), (const cf*)0, op); }
+    template <class Op> XL_DEV static void inverse_g(cf* s, cf* t, const cf* gtw, const Op& op) { inverse_impl<true>(s, t, gtw, op); }
 };

@@ -255,18 +255,17 @@ template <int L, bool FUSE = false> struct XlRsRowsFwd {
     static size_t smem() { return xl_smem_bytes(L, XL_V); }
     XL_DEV static void run(const Params& p, cf* s) {
         cf* t = s + xl_tile_elems(L, XL_V);
-        XlFft<L, XL_V>::init_tw(t, p.tw);
         const int f = p.f0 + XL_BLOCK_Y, yb = XL_BLOCK_X * XL_V;
         if (FUSE) {
             XlRsRowsFwdOp<L, false, true> op{{}, p, f, yb, 0.0, xl_seed_weight(p, f)};
-            XlFft<L, XL_V>::forward(s, t, op);
+            XlFft<L, XL_V>::forward_g(s, t, p.tw, op);
         } else if ((p.flags & XL_F_VRS) && f == 2) {   // CTA-uniform
             const double z = xl_ldg(p.z);
             XlRsRowsFwdOp<L, true> op{{}, p, f, yb, z * z, 0.f};
-            XlFft<L, XL_V>::forward(s, t, op);
+            XlFft<L, XL_V>::forward_g(s, t, p.tw, op);
         } else {
             XlRsRowsFwdOp<L, false> op{{}, p, f, yb, 0.0, 0.f};
-            XlFft<L, XL_V>::forward(s, t, op);
+            XlFft<L, XL_V>::forward_g(s, t, p.tw, op);
         }
     }
 };
@@ -331,20 +330,19 @@ template <int L, bool FUSE = false> struct XlRsRowsDual {
     XL_DEV static void run(const Params& p, cf* s) {
         cf* t = s + xl_tile_elems(L, XL_V);
         double* red = (double*)(t + xl_tw_total(L));
-        XlFft<L, XL_V>::init_tw(t, p.tw);
         const int f = p.f0 + XL_BLOCK_Y, y = XL_BLOCK_X;
         if (FUSE) {
             XlRsRowsDualOp<L, false, true> op{{}, p, f, y, 0.0, xl_seed_weight(p, f), 0.0};
-            XlFft<L, XL_V>::forward(s, t, op);
+            XlFft<L, XL_V>::forward_g(s, t, p.tw, op);
             if (p.dz_out) dz_flush(p, red, op.dz);     // kernel-uniform
         } else if ((p.flags & XL_F_VRS) && f == 2) {   // CTA-uniform
             const double z = xl_ldg(p.z);
             XlRsRowsDualOp<L, true> op{{}, p, f, y, z * z, 0.f, 0.0};
-            XlFft<L, XL_V>::forward(s, t, op);
+            XlFft<L, XL_V>::forward_g(s, t, p.tw, op);
             if (p.dz_out) dz_flush(p, red, op.dz);
         } else {
             XlRsRowsDualOp<L, false> op{{}, p, f, y, 0.0, 0.f, 0.0};
-            XlFft<L, XL_V>::forward(s, t, op);
+            XlFft<L, XL_V>::forward_g(s, t, p.tw, op);
             if (p.dz_out) dz_flush(p, red, op.dz);
         }
     }
@@ -503,10 +501,9 @@ template <int L, bool DET = false> struct XlRsRowsInv {
         cf* t = s + xl_tile_elems(L, XL_V);
         double* dred = (double*)(t + xl_tw_total(L));
         float* red = (float*)(dred + NT);
-        XlFft<L, XL_V>::init_tw(t, p.tw);
         const int f = p.f0 + XL_BLOCK_Y;
         XlRsRowsInvOp<L, DET> op{{}, p, f, XL_BLOCK_X * XL_V, red};
-        XlFft<L, XL_V>::inverse(s, t, op);
+        XlFft<L, XL_V>::inverse_g(s, t, p.tw, op);
         if (DET) {
             XL_SYNC();
             XL_THREADS(tid, NT) {
@@ -640,6 +637,8 @@ template <int L> struct XlHRows {
         const XlRsHConst hc = xl_rs_hconst(xl_ldg(p.z + item), p.k);
         const int deriv = (p.flags & XL_F_DERIV) ? 1 : 0;
         XL_THREADS(tid, NT) {
+            cf tr[XlFft<L, XL_V>::kTwRegs];
+            XlFft<L, XL_V>::tw_fetch(tid, p.tw, tr);   // the twiddle loads fly while the samples are evaluated
             if (dual) {
                 for (int xi = tid; xi < L / 2 + 1; xi += NT) {
                     cf h, hz;
@@ -652,8 +651,9 @@ template <int L> struct XlHRows {
                     stage[e] = yi <= L / 2 ? xl_rs_h(xi * p.dx, yi * p.dy, hc, deriv) : cf_zero();
                 }
             }
+            XlFft<L, XL_V>::tw_store(tid, t, tr);
         }
-        XlFft<L, XL_V>::init_tw(t, p.tw);   // ends with a barrier: stage[] is visible
+        XL_SYNC();                          // stage[] and the tables are visible
         int nvalid = L / 2 + 1 - p.hrow0;
         if (nvalid > p.rows) nvalid = p.rows;
         cf* H = p.H + (long long)item * (dual ? 2 : 1) * p.h_stride;
@@ -721,12 +721,11 @@ template <int L> struct XlHCols {
     XL_DEV static void run(const Params& p, cf* s) {
         if (!xl_h_pair_needed<L>(XL_BLOCK_X)) return;   // CTA-uniform: mirrored columns are never read
         cf* t = s + xl_tile_elems(L, XL_V);
-        XlFft<L, XL_V>::init_tw(t, p.tw);
         cf* H = p.H + (long long)XL_BLOCK_Y * p.h_stride;      // this item's buffer (xl_rs_transfer_multi)
         cf* Hc = H + xl_hc_offset(L) + (size_t)XL_BLOCK_X * XL_V * xl_hc_stride(L);
         XlHColsOp<L> op{{}, p, H + (size_t)XL_BLOCK_X * L * XL_V, Hc, Hc + xl_hc_stride(L)};
         // the in-place update is safe: every load of the first pass happens before the barrier that precedes the stores
-        XlFft<L, XL_V>::forward(s, t, op);
+        XlFft<L, XL_V>::forward_g(s, t, p.tw, op);
     }
 };
 
@@ -967,12 +966,11 @@ template <int L, int PRO, int EPI, int ACC> struct XlCztAxis {
     // item's input the two CTAs of an SM stay in lock-step, while CTAs handed out by the hardware start out of phase.
     XL_DEV static void run(const Params& p, cf* s) {
         cf* t = s + xl_tile_elems(L, XL_V);
-        XlFft<L, XL_V>::init_tw(t, p.tw);
         const double z = p.z ? xl_ldg(p.z) : 0.0;
         double cr = p.epi_cr, ci = p.epi_ci;
         if (p.epi_times_z) { cr *= z; ci *= z; }
         XlCztOp<L, PRO, EPI, ACC> op{{}, p, XL_BLOCK_X * XL_V, XL_BLOCK_Y, p.c0 + XL_BLOCK_Y, (float)z, make_float2((float)cr, (float)ci)};
-        XlFft<L, XL_V>::conv(s, t, op);
+        XlFft<L, XL_V>::conv_g(s, t, p.tw, op);
     }
 };
 
