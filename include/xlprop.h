@@ -215,6 +215,39 @@ int xl_highna_bwd(const void* ct_out, void* ct_exy, int N, int Mx, int My, doubl
                   double x0, double dx, double y0, double dy, double xout0, double xoutl, double yout0, double youtl,
                   int flags, void* tables, void* ws, size_t ws_bytes, void* stream);
 
+/* ---------------------------------------------------------------- pointwise Jones elements (vectorial tables) */
+/* The elements that sit between the propagations of a vectorial optical table, each as ONE pass over the
+ * planes it changes, forward and VJP, with the reference's parameter maps and the reductions of the scalar-parameter
+ * gradients inside the kernels.  Planes are complex64 [n] (n = N*N pixels); cotangents follow torch's convention
+ * (g = dL/dRe + i dL/dIm of a real loss), any cotangent pointer may be NULL (a zero cotangent on input, an unwanted
+ * gradient on output; the Ex and Ey planes of one beam come together).  Scalar parameters are float64 in device memory and
+ * enter as the optimizer's raw values p: angle = scale * p + offset (the reference maps p in (0,1) to p*2pi - pi,
+ * optical_elements.py:1556-1592; scale = 1, offset = 0 passes angles through).  Parameter gradients are ACCUMULATED (+=).
+ * `scratch`: xl_el_scratch_bytes() bytes of device memory (needed when a scalar-parameter gradient is requested). */
+size_t xl_el_scratch_bytes(void);
+/* sSLM: ox = ex * exp(i (scale*alpha + offset)), oy = ey * exp(i (scale*phi + offset)); alpha, phi float32 [n] planes.
+ * optical_elements.py:186-222.  VJP: g_ex, g_ey and the per-pixel g_alpha, g_phi (float32, overwritten). */
+int xl_el_sslm(const void* ex, const void* ey, const float* alpha, const float* phi, double scale, double offset,
+               void* ox, void* oy, size_t n, void* stream);
+int xl_el_sslm_bwd(const void* ex, const void* ey, const float* alpha, const float* phi, double scale, double offset,
+                   const void* g_ox, const void* g_oy, void* g_ex, void* g_ey, float* g_alpha, float* g_phi,
+                   size_t n, void* stream);
+/* LCD: uniform retarder eta with its fast axis at theta: (ox, oy) = [[a, b], [b, d]] (ex, ey), a = cos(eta/2) - i sin(eta/2) cos 2theta,
+ * b = -i sin(eta/2) sin 2theta, d = conj-mirror of a.  optical_elements.py:123-140, 170-180, 266-305. */
+int xl_el_lcd(const void* ex, const void* ey, const double* eta, const double* theta, double scale, double offset,
+              void* ox, void* oy, size_t n, void* stream);
+int xl_el_lcd_bwd(const void* ex, const void* ey, const double* eta, const double* theta, double scale, double offset,
+                  const void* g_ox, const void* g_oy, void* g_ex, void* g_ey, double* g_eta, double* g_theta,
+                  void* scratch, size_t n, void* stream);
+/* BS_symmetric: c = R a + i T b, d = i T a + R b, T = 0.99 |cos theta|, R = |sin theta| - 0.01 |cos theta|.
+ * optical_elements.py:334-392. */
+int xl_el_bs(const void* a_ex, const void* a_ey, const void* b_ex, const void* b_ey, const double* theta, double scale, double offset,
+             void* c_ex, void* c_ey, void* d_ex, void* d_ey, size_t n, void* stream);
+int xl_el_bs_bwd(const void* a_ex, const void* a_ey, const void* b_ex, const void* b_ey, const double* theta, double scale, double offset,
+                 const void* g_c_ex, const void* g_c_ey, const void* g_d_ex, const void* g_d_ey,
+                 void* g_a_ex, void* g_a_ey, void* g_b_ex, void* g_b_ey, double* g_theta,
+                 void* scratch, size_t n, void* stream);
+
 /* ---------------------------------------------------------------- instrumentation (bench.py) ---------------- */
 /* Number of kernels this library has launched in this process. */
 long long xl_launch_count(void);

@@ -256,3 +256,55 @@ def test_reference_toolbox_tests_for_the_mirrored_helpers():
     l2.Ex = 0 * l2.Ex
     assert float(is_conserving_energy(l1, l2)) == 0
     assert float(softmin(torch.tensor([1.0, 2.0, 3.0], dtype=torch.float64))) == 1.0
+
+
+def _torch_elements(kind, planes, params):
+    """The elements as the reference composes them (complex128 torch arithmetic), for checking the element kernels."""
+    from xlumina_b200 import optical_elements as oe
+
+    def light(ex, ey):
+        l = oe.VectorizedLight(np.zeros(2), np.zeros(2), 1.0, ex.device, _alloc=False)
+        l.Ex, l.Ey, l.Ez = ex, ey, torch.zeros_like(ex)
+        return l
+    if kind == "sslm":
+        o = oe.sSLM(light(planes[0], planes[1]), params[0], params[1])
+        return o.Ex, o.Ey
+    if kind == "lcd":
+        o = oe.LCD(light(planes[0], planes[1]), params[0], params[1])
+        return o.Ex, o.Ey
+    c, d = oe.BS_symmetric(light(planes[0], planes[1]), light(planes[2], planes[3]), params[0])
+    return c.Ex, c.Ey, d.Ex, d.Ey
+
+
+def check_element_kernels(kind, device):
+    """xl_el_sslm / xl_el_lcd / xl_el_bs (forward, field VJP, parameter gradients with the map p -> p*2pi - pi inside) against
+    the same elements composed from complex128 torch arithmetic (the path this file pins to the reference).  Shared by
+    tests/test_ops_emu.py (host-emulated kernels) and tests/test_gpu_parity.py (CUDA build)."""
+    from xlumina_b200 import ops
+    rng = np.random.default_rng(5)
+    n = 37          # not a multiple of anything in the kernels
+    nplanes = 4 if kind == "bs" else 2
+    planes64 = [torch.tensor((rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))).astype(np.complex64), requires_grad=True, device=device) for _ in range(nplanes)]
+    planes128 = [p.detach().to(torch.complex128).requires_grad_(True) for p in planes64]
+    if kind == "sslm":
+        raw = [torch.tensor(rng.uniform(0, 1, (n, n)).astype(np.float32), requires_grad=True, device=device) for _ in range(2)]
+    else:
+        raw = [torch.tensor(rng.uniform(0, 1, (1,)), dtype=torch.float64, requires_grad=True, device=device) for _ in range(1 if kind == "bs" else 2)]
+    raw_ref = [r.detach().to(torch.float64).requires_grad_(True) for r in raw]
+    two_pi = 2 * np.pi
+    fn = {"sslm": ops.el_sslm, "lcd": ops.el_lcd, "bs": ops.el_bs}[kind]
+    outs = fn(*planes64, *raw, two_pi, -np.pi)
+    refs = _torch_elements(kind, planes128, [r * two_pi - np.pi for r in raw_ref])
+    cts = [torch.tensor((rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))).astype(np.complex64), device=device) for _ in outs]
+    for o, r in zip(outs, refs):
+        assert rel_l2(o.detach().cpu().numpy(), r.detach().cpu().numpy()) < 2e-6
+    # drop one output from the loss of the beam splitter: its cotangent arrives as None
+    use = range(len(outs)) if kind != "bs" else (0, 1, 2)
+    loss = sum((torch.conj(cts[i]) * outs[i]).real.sum() for i in use)
+    loss_ref = sum((torch.conj(cts[i].to(torch.complex128)) * refs[i]).real.sum() for i in use)
+    g = torch.autograd.grad(loss, planes64 + raw)
+    g_ref = torch.autograd.grad(loss_ref, planes128 + raw_ref)
+    for a, b in zip(g[:nplanes], g_ref[:nplanes]):
+        assert rel_l2(a.cpu().numpy(), b.cpu().numpy()) < 2e-6
+    for a, b in zip(g[nplanes:], g_ref[nplanes:]):
+        assert rel_l2(a.double().cpu().numpy(), b.cpu().numpy()) < 2e-5

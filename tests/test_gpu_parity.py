@@ -622,3 +622,12 @@ def test_czt_distance_gradient_on_device(xb, vect):
     print("CZT d/dz on device:", "vect" if vect else "scalar", float(gz), gz_ref, abs(float(gz) - gz_ref) / abs(gz_ref))
     assert abs(float(gz) - gz_ref) < 1e-4 * abs(gz_ref)
     assert rel_l2(gu.cpu().numpy(), gu0.cpu().numpy()) < 1e-6
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["sslm", "lcd", "bs"])
+def test_element_kernels_on_device(kind):
+    """SURVEY 8f-1, vectorial tables: xl_el_sslm / xl_el_lcd / xl_el_bs (forward, field VJP, parameter gradients) on the B200
+    against the same elements composed from complex128 torch arithmetic."""
+    from test_elements import check_element_kernels
+    check_element_kernels(kind, "cuda:0")

@@ -12,7 +12,7 @@ import torch
 from conftest import golden, rel_l2
 
 from xlumina_b200 import _lib, four_f, ops
-from test_elements import (directional, four_f_problem, sharp_focus_losses, sharp_focus_problem)
+from test_elements import (check_element_kernels, directional, four_f_problem, sharp_focus_losses, sharp_focus_problem)
 
 
 @pytest.fixture
@@ -23,6 +23,7 @@ def ops_on_emu(monkeypatch, emu):
     monkeypatch.setattr(ops, "_stream_key", lambda t: ("cpu", 0))
     monkeypatch.setattr(ops, "_workspaces", {})
     monkeypatch.setattr(ops, "_z_cache", {})
+    monkeypatch.setattr(ops, "_cpu_kernels", True)      # complex64 CPU planes go through the emulated element kernels (xl_el_*)
     yield
 
 
@@ -344,3 +345,9 @@ def test_czt_distance_gradient(ops_on_emu, vect, case):
     # the field gradient of the same call equals the one of a call without d/dz
     (gu0,) = torch.autograd.grad((torch.tensor(ct).conj() * (ops.vczt(ut, None, z0, lam, x, y, xo, yo) if vect else ops.czt(ut, z0, lam, x, y, xo, yo))).real.sum(), (ut,))
     assert rel_l2(gu.numpy(), gu0.numpy()) < 1e-6
+
+
+@pytest.mark.parametrize("kind", ["sslm", "lcd", "bs"])
+def test_element_kernels_match_torch_arithmetic(ops_on_emu, kind):
+    """xl_el_sslm / xl_el_lcd / xl_el_bs on the host-emulated kernels (see test_elements.check_element_kernels)."""
+    check_element_kernels(kind, "cpu")

@@ -51,6 +51,13 @@ SIGNATURES = {
     "xl_highna_workspace_bytes": (_sz, [_i, _i, _i]),
     "xl_highna_tables_bytes": (_sz, [_i, _i, _i]),
     "xl_highna_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _d, _d, _d, _d, _d, _d, _d, _d, _d, _d, _d, _i, _vp, _vp, _sz, _vp]),
+    "xl_el_scratch_bytes": (_sz, []),
+    "xl_el_sslm": (_i, [_vp, _vp, _vp, _vp, _d, _d, _vp, _vp, _sz, _vp]),
+    "xl_el_sslm_bwd": (_i, [_vp, _vp, _vp, _vp, _d, _d, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "xl_el_lcd": (_i, [_vp, _vp, _vp, _vp, _d, _d, _vp, _vp, _sz, _vp]),
+    "xl_el_lcd_bwd": (_i, [_vp, _vp, _vp, _vp, _d, _d, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "xl_el_bs": (_i, [_vp, _vp, _vp, _vp, _vp, _d, _d, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "xl_el_bs_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _d, _d, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "xl_launch_count": (ctypes.c_longlong, []),
     "xl_prof_enable": (None, [_i]),
     "xl_prof_report": (_i, [ctypes.c_char_p, _i]),

@@ -1,6 +1,6 @@
 """Build libxlprop.so in-tree with nvcc for sm_100a (the only target).  Used by __graft_entry__.build().
 
-One translation unit per kernel family (csrc/xl_core.cu, xl_rs.cu, xl_slab.cu, xl_czt.cu), each compiled by its own nvcc
+One translation unit per kernel family (csrc/xl_core.cu, xl_rs.cu, xl_slab.cu, xl_czt.cu, xl_elements.cu), each compiled by its own nvcc
 process WITHOUT -split-compile, so the binary is reproducible: identical sources and flags give identical per-kernel SASS
 (round 1 used one unit with -split-compile 8, whose partitioning -- and with it every kernel's register allocation --
 changed from run to run).  The units are compiled in parallel and linked into one shared object."""
@@ -13,7 +13,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-UNITS = ["xl_core.cu", "xl_rs.cu", "xl_slab.cu", "xl_czt.cu"]
+UNITS = ["xl_core.cu", "xl_rs.cu", "xl_slab.cu", "xl_czt.cu", "xl_elements.cu"]
 OUT = os.path.join(HERE, "libxlprop.so")
 OBJ_DIR = os.path.join(os.path.dirname(HERE), "build", "obj")
 

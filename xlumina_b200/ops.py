@@ -20,7 +20,8 @@ import torch
 
 from . import _lib
 
-__all__ = ["rs_propagation", "rs_propagation_fused", "vrs_propagation", "czt", "vczt", "highna_focus", "rs_transfer", "set_transfer_cache"]
+__all__ = ["rs_propagation", "rs_propagation_fused", "vrs_propagation", "czt", "vczt", "highna_focus", "rs_transfer", "set_transfer_cache",
+           "el_sslm", "el_lcd", "el_bs", "elements_on"]
 
 
 # ---------------------------------------------------------------------------------------------- plumbing
@@ -629,3 +630,165 @@ def highna_focus(Ex, Ey, radius, f, wavelength, x, y, xout, yout):
     ex, ey = _planes(Ex, Ey)
     out = _HighNA.apply(ex, ey, float(radius), float(f), float(wavelength), _gin(x, y, ex.shape[-1]), _gout(xout, yout))
     return out if dt == torch.complex64 or not torch.is_complex(Ex) else out.to(dt)
+
+
+# ---------------------------------------------------------------------------------------------- pointwise Jones elements
+# sSLM, LCD and BS_symmetric of a vectorial table as single-pass kernels (xl_el_*, include/xlprop.h): one
+# launch forward, one backward, parameter maps and scalar-parameter reductions inside.  Planes are complex64; scalar
+# parameters are float64 (1,) device tensors holding the optimizer's raw values (angle = scale * p + offset).
+_cpu_kernels = False     # tests only: CPU tensors go to the host-emulated library (tests/test_ops_emu.py)
+
+
+def elements_on(t):
+    """True when the planes of `t`'s table go through the element kernels: complex64 on a CUDA device."""
+    return isinstance(t, torch.Tensor) and t.dtype == torch.complex64 and (t.is_cuda or _cpu_kernels)
+
+
+def _plane(t):
+    return t.resolve_conj().contiguous()
+
+
+def _f64_scalar(v, ref):
+    if isinstance(v, torch.Tensor):
+        return v.to(device=ref.device, dtype=torch.float64).reshape(1)
+    return torch.full((1,), float(v), dtype=torch.float64, device=ref.device)
+
+
+def _pair_or_none(a, b):
+    """Cotangents of the two planes of one beam come together: both None, or a missing one replaced by zeros."""
+    if a is None and b is None:
+        return None, None
+    a = torch.zeros_like(b) if a is None else _plane(a)
+    b = torch.zeros_like(a) if b is None else _plane(b)
+    return a, b
+
+
+class _ElSSLM(torch.autograd.Function):
+    @staticmethod
+    @_on_device
+    def forward(ctx, ex, ey, alpha, phi, scale, offset):
+        _require_device(ex)
+        L = _lib.lib()
+        ox, oy = torch.empty_like(ex), torch.empty_like(ey)
+        _lib.check(L.xl_el_sslm(_ptr(ex), _ptr(ey), _ptr(alpha), _ptr(phi), scale, offset, _ptr(ox), _ptr(oy), ex.numel(), _stream(ex)), "xl_el_sslm")
+        ctx.save_for_backward(ex, ey, alpha, phi)
+        ctx.map = (scale, offset)
+        ctx.set_materialize_grads(False)
+        return ox, oy
+
+    @staticmethod
+    @_on_device
+    def backward(ctx, gox, goy):
+        ex, ey, alpha, phi = ctx.saved_tensors
+        scale, offset = ctx.map
+        if gox is None and goy is None:
+            return None, None, None, None, None, None
+        L = _lib.lib()
+        gox = None if gox is None else _plane(gox)
+        goy = None if goy is None else _plane(goy)
+        want_f = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        gex = torch.empty_like(ex) if want_f else None
+        gey = torch.empty_like(ey) if want_f else None
+        ga = torch.empty_like(alpha) if ctx.needs_input_grad[2] else None
+        gp = torch.empty_like(phi) if ctx.needs_input_grad[3] else None
+        _lib.check(L.xl_el_sslm_bwd(_ptr(ex), _ptr(ey), _ptr(alpha), _ptr(phi), scale, offset, _ptr(gox), _ptr(goy), _ptr(gex), _ptr(gey),
+                                    _ptr(ga), _ptr(gp), ex.numel(), _stream(ex)), "xl_el_sslm_bwd")
+        return gex, gey, ga, gp, None, None
+
+
+class _ElLCD(torch.autograd.Function):
+    @staticmethod
+    @_on_device
+    def forward(ctx, ex, ey, eta, theta, scale, offset):
+        _require_device(ex)
+        L = _lib.lib()
+        ox, oy = torch.empty_like(ex), torch.empty_like(ey)
+        _lib.check(L.xl_el_lcd(_ptr(ex), _ptr(ey), _ptr(eta), _ptr(theta), scale, offset, _ptr(ox), _ptr(oy), ex.numel(), _stream(ex)), "xl_el_lcd")
+        ctx.save_for_backward(ex, ey, eta, theta)
+        ctx.map = (scale, offset)
+        ctx.set_materialize_grads(False)
+        return ox, oy
+
+    @staticmethod
+    @_on_device
+    def backward(ctx, gox, goy):
+        ex, ey, eta, theta = ctx.saved_tensors
+        scale, offset = ctx.map
+        gox, goy = _pair_or_none(gox, goy)
+        if gox is None:
+            return None, None, None, None, None, None
+        L = _lib.lib()
+        want_f = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        gex = torch.empty_like(ex) if want_f else None
+        gey = torch.empty_like(ey) if want_f else None
+        ge = torch.zeros(1, dtype=torch.float64, device=ex.device) if ctx.needs_input_grad[2] else None
+        gt = torch.zeros(1, dtype=torch.float64, device=ex.device) if ctx.needs_input_grad[3] else None
+        ws = _workspace(ex, L.xl_el_scratch_bytes())
+        _lib.check(L.xl_el_lcd_bwd(_ptr(ex), _ptr(ey), _ptr(eta), _ptr(theta), scale, offset, _ptr(gox), _ptr(goy), _ptr(gex), _ptr(gey),
+                                   _ptr(ge), _ptr(gt), _ptr(ws), ex.numel(), _stream(ex)), "xl_el_lcd_bwd")
+        return gex, gey, ge, gt, None, None
+
+
+class _ElBS(torch.autograd.Function):
+    @staticmethod
+    @_on_device
+    def forward(ctx, a_ex, a_ey, b_ex, b_ey, theta, scale, offset):
+        _require_device(a_ex)
+        L = _lib.lib()
+        outs = [torch.empty_like(a_ex) for _ in range(4)]
+        _lib.check(L.xl_el_bs(_ptr(a_ex), _ptr(a_ey), _ptr(b_ex), _ptr(b_ey), _ptr(theta), scale, offset,
+                              _ptr(outs[0]), _ptr(outs[1]), _ptr(outs[2]), _ptr(outs[3]), a_ex.numel(), _stream(a_ex)), "xl_el_bs")
+        ctx.save_for_backward(a_ex, a_ey, b_ex, b_ey, theta)
+        ctx.map = (scale, offset)
+        ctx.set_materialize_grads(False)
+        return tuple(outs)
+
+    @staticmethod
+    @_on_device
+    def backward(ctx, gcx, gcy, gdx, gdy):
+        a_ex, a_ey, b_ex, b_ey, theta = ctx.saved_tensors
+        scale, offset = ctx.map
+        gcx, gcy = _pair_or_none(gcx, gcy)
+        gdx, gdy = _pair_or_none(gdx, gdy)
+        if gcx is None and gdx is None:
+            return (None,) * 7
+        L = _lib.lib()
+        want_a = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        want_b = ctx.needs_input_grad[2] or ctx.needs_input_grad[3]
+        gax = torch.empty_like(a_ex) if want_a else None
+        gay = torch.empty_like(a_ex) if want_a else None
+        gbx = torch.empty_like(a_ex) if want_b else None
+        gby = torch.empty_like(a_ex) if want_b else None
+        gt = torch.zeros(1, dtype=torch.float64, device=a_ex.device) if ctx.needs_input_grad[4] else None
+        ws = _workspace(a_ex, L.xl_el_scratch_bytes())
+        _lib.check(L.xl_el_bs_bwd(_ptr(a_ex), _ptr(a_ey), _ptr(b_ex), _ptr(b_ey), _ptr(theta), scale, offset,
+                                  _ptr(gcx), _ptr(gcy), _ptr(gdx), _ptr(gdy), _ptr(gax), _ptr(gay), _ptr(gbx), _ptr(gby), _ptr(gt),
+                                  _ptr(ws), a_ex.numel(), _stream(a_ex)), "xl_el_bs_bwd")
+        return gax, gay, gbx, gby, gt, None, None
+
+
+def _phase_plane(v, ref):
+    """A per-pixel phase parameter as a contiguous float32 plane on the device of `ref` (scalars are broadcast)."""
+    if not isinstance(v, torch.Tensor):
+        import numpy as np
+        v = torch.as_tensor(np.asarray(v, dtype=np.float64))
+    v = v.to(device=ref.device, dtype=torch.float32)
+    return v.expand(ref.shape).contiguous()
+
+
+def el_sslm(ex, ey, alpha, phi, scale=1.0, offset=0.0):
+    """(ex e^{i(scale alpha + offset)}, ey e^{i(scale phi + offset)}): the super-SLM, optical_elements.py:186-222."""
+    ex, ey = _plane(ex), _plane(ey)
+    return _ElSSLM.apply(ex, ey, _phase_plane(alpha, ex), _phase_plane(phi, ey), float(scale), float(offset))
+
+
+def el_lcd(ex, ey, eta, theta, scale=1.0, offset=0.0):
+    """Uniform wave plate (retardance scale*eta + offset, fast axis at scale*theta + offset): optical_elements.py:266-305."""
+    ex, ey = _plane(ex), _plane(ey)
+    return _ElLCD.apply(ex, ey, _f64_scalar(eta, ex), _f64_scalar(theta, ex), float(scale), float(offset))
+
+
+def el_bs(a_ex, a_ey, b_ex, b_ey, theta, scale=1.0, offset=0.0):
+    """Lossy symmetric beam splitter, optical_elements.py:334-392: returns (c_ex, c_ey, d_ex, d_ey)."""
+    a_ex, a_ey, b_ex, b_ey = _plane(a_ex), _plane(a_ey), _plane(b_ex), _plane(b_ey)
+    return _ElBS.apply(a_ex, a_ey, b_ex, b_ey, _f64_scalar(theta, a_ex), float(scale), float(offset))

@@ -63,8 +63,19 @@ def _new_vector(src):
     return VectorizedLight(src.x, src.y, src.wavelength, src.device, _alloc=False)
 
 
+_zero_planes = {}
+
+
 def _zeros_like_plane(t):
-    return torch.zeros_like(t)
+    """The zero Ez plane the reference attaches to the output of most elements.  Nothing on the path reads the input Ez (the
+    propagators recompute it from Ex, Ey), so one shared read-only plane per (device, dtype, shape) stands for all of them."""
+    key = (t.device, t.dtype, tuple(t.shape))
+    z = _zero_planes.get(key)
+    if z is None:
+        if len(_zero_planes) > 16:
+            _zero_planes.clear()
+        z = _zero_planes[key] = torch.zeros_like(t).detach()
+    return z
 
 
 def phase_scalar_SLM(phase):
@@ -84,9 +95,17 @@ def SLM(input_field, phase_array, shape=None):
 def sSLM(input_field, alpha_array=None, phi_array=None):
     """Super-SLM: independent phase masks on Ex (alpha) and Ey (phi); Ez is carried over.  optical_elements.py:186-222,
     Jones matrix diag(e^{i alpha}, e^{i phi}) (:142-153)."""
+    return _sslm(input_field, alpha_array, phi_array, 1.0, 0.0)
+
+
+def _sslm(input_field, alpha, phi, scale, offset):
+    """sSLM with the phases scale * alpha + offset, scale * phi + offset (the tables pass the optimizer's raw masks)."""
     out = _new_vector(input_field)
-    out.Ex = input_field.Ex * _phasor(alpha_array, input_field.Ex)
-    out.Ey = input_field.Ey * _phasor(phi_array, input_field.Ey)
+    if ops.elements_on(input_field.Ex):       # one kernel, forward and backward (xl_el_sslm)
+        out.Ex, out.Ey = ops.el_sslm(input_field.Ex, input_field.Ey, alpha, phi, scale, offset)
+    else:
+        out.Ex = input_field.Ex * _phasor(_real(alpha, input_field.Ex, torch.float64) * scale + offset, input_field.Ex)
+        out.Ey = input_field.Ey * _phasor(_real(phi, input_field.Ey, torch.float64) * scale + offset, input_field.Ey)
     out.Ez = input_field.Ez
     return out
 
@@ -119,10 +138,18 @@ def jones_LCD(eta, theta, like):
 def LCD(input_field, eta, theta):
     """Liquid-crystal device = uniform linear wave plate of retardance eta with its fast axis at theta; Ez carried over.
     optical_elements.py:266-305 (the constant (N, N) eta/theta cell of toolbox.build_LCD_cell is never built)."""
-    a, b, d = jones_LCD(eta, theta, input_field.Ex)
+    return _lcd(input_field, eta, theta, 1.0, 0.0)
+
+
+def _lcd(input_field, eta, theta, scale, offset):
     out = _new_vector(input_field)
-    out.Ex = a * input_field.Ex + b * input_field.Ey
-    out.Ey = b * input_field.Ex + d * input_field.Ey
+    if ops.elements_on(input_field.Ex):       # xl_el_lcd: Jones matrix, VJP and the (eta, theta) reductions in the kernels
+        out.Ex, out.Ey = ops.el_lcd(input_field.Ex, input_field.Ey, eta, theta, scale, offset)
+    else:
+        like = input_field.Ex
+        a, b, d = jones_LCD(_real(eta, like, torch.float64) * scale + offset, _real(theta, like, torch.float64) * scale + offset, like)
+        out.Ex = a * input_field.Ex + b * input_field.Ey
+        out.Ey = b * input_field.Ex + d * input_field.Ey
     out.Ez = input_field.Ez
     return out
 
@@ -143,7 +170,17 @@ def linear_polarizer(input_field, alpha):
 def BS_symmetric(a, b, theta):
     """Lossy symmetric beam splitter: c = R a + i T b, d = i T a + R b with T = |cos theta|, R = |sin theta|, both reduced by
     0.01 T; the outputs' Ez are zero.  optical_elements.py:334-392."""
-    th = _real(theta, a.Ex, torch.float64).reshape(())
+    return _bs(a, b, theta, 1.0, 0.0)
+
+
+def _bs(a, b, theta, scale, offset):
+    if ops.elements_on(a.Ex):                 # xl_el_bs: both outputs, the VJP and the theta reduction in the kernels
+        c, d = _new_vector(a), _new_vector(a)
+        c.Ex, c.Ey, d.Ex, d.Ey = ops.el_bs(a.Ex, a.Ey, b.Ex, b.Ey, theta, scale, offset)
+        c.Ez = _zeros_like_plane(a.Ex)
+        d.Ez = _zeros_like_plane(a.Ex)
+        return c, d
+    th = (_real(theta, a.Ex, torch.float64) * scale + offset).reshape(())
     T = torch.abs(torch.cos(th))
     R = torch.abs(torch.sin(th))
     noise = T * 0.01
@@ -254,51 +291,67 @@ def hybrid_setup_sharp_focus(ls1, ls2, ls3, ls4, ls5, ls6, parameters, fixed_par
     ops.set_transfer_cache(n >= 5) every repeat reuses the transfer function."""
     r, f, xout, yout = fixed_params[0], fixed_params[1], fixed_params[2], fixed_params[3]
     dev = ls1.device
-    P = [_param(p, dev) for p in parameters]
     two_pi = 2 * math.pi
+    cache = {}
+
+    def P(i):                                  # float64 view of parameter i, made on first use
+        if i not in cache:
+            cache[i] = _param(parameters[i], dev)
+        return cache[i]
 
     def angle(i):
-        return P[i] * two_pi - math.pi
+        return P(i) * two_pi - math.pi
 
     def dist(i):
-        return (torch.abs(P[i]) * 100 + distance_offset) * cm
+        return (torch.abs(P(i)) * 100 + distance_offset) * cm
 
-    phase1_1, phase1_2, eta1, theta1, z1_1, z1_2 = angle(0), angle(1), angle(2), angle(3), dist(4), dist(5)
-    phase2_1, phase2_2, eta2, theta2, z2_1, z2_2 = angle(6), angle(7), angle(8), angle(9), dist(10), dist(11)
-    phase3_1, phase3_2, eta3, theta3, z3_1, z3_2 = angle(12), angle(13), angle(14), angle(15), dist(16), dist(17)
-    bs = [angle(18 + i) for i in range(9)]
+    # With complex64 planes on the GPU the elements are single kernels that take the optimizer's RAW parameters and apply
+    # the map p -> p*2pi - pi themselves (xl_el_*): no per-pixel float64 copies of the masks, no scalar-algebra launches.
+    raw = ops.elements_on(ls1.Ex)
+
+    def BS(a, b, i):
+        return _bs(a, b, P(18 + i), two_pi, -math.pi) if raw else BS_symmetric(a, b, angle(18 + i))
+
+    def block(light, i0, z):                   # sSLM(masks i0, i0+1) -> VRS(z) -> LCD(i0+2, i0+3): building_block
+        if not raw:
+            return building_block(light, angle(i0), angle(i0 + 1), z, angle(i0 + 2), angle(i0 + 3))
+        l_modulated = _sslm(light, parameters[i0], parameters[i0 + 1], two_pi, -math.pi)
+        l_propagated, _ = l_modulated.VRS_propagation(z)
+        return _lcd(l_propagated, P(i0 + 2), P(i0 + 3), two_pi, -math.pi)
+
+    z1_1, z1_2, z2_1, z2_2, z3_1, z3_2 = dist(4), dist(5), dist(10), dist(11), dist(16), dist(17)
     z4, z5 = dist(27), dist(28)
     z1s, z2s, z3s = z1_1 + z1_2, z2_1 + z2_2, z3_1 + z3_2
 
     # 1st row
-    c1, d1 = BS_symmetric(ls1, ls4, bs[0])
-    b2, _ = building_block(c1, phase1_1, phase1_2, z1_1, eta1, theta1).VRS_propagation(z1_2)
-    c2, d2 = BS_symmetric(ls2, b2, bs[1])
+    c1, d1 = BS(ls1, ls4, 0)
+    b2, _ = block(c1, 0, z1_1).VRS_propagation(z1_2)
+    c2, d2 = BS(ls2, b2, 1)
     b3, _ = c2.VRS_propagation(z2s)
-    c3, d3 = BS_symmetric(ls3, b3, bs[2])
+    c3, d3 = BS(ls3, b3, 2)
     b_det1, _ = c3.VRS_propagation(z3s)
     det_1 = VCZT_objective_lens(b_det1, r, f, xout, yout)
     # mid space
     a5, _ = d2.VRS_propagation(z4)
     a6, _ = d3.VRS_propagation(z4)
     # 2nd row
-    c4, d4 = BS_symmetric(d1, ls5, bs[3])
+    c4, d4 = BS(d1, ls5, 3)
     b5, _ = c4.VRS_propagation(z1s)
-    c5, d5 = BS_symmetric(a5, b5, bs[4])
-    b6, _ = building_block(c5, phase2_1, phase2_2, z2_1, eta2, theta2).VRS_propagation(z2_2)
-    c6, d6 = BS_symmetric(a6, b6, bs[5])
+    c5, d5 = BS(a5, b5, 4)
+    b6, _ = block(c5, 6, z2_1).VRS_propagation(z2_2)
+    c6, d6 = BS(a6, b6, 5)
     b_det2, _ = c6.VRS_propagation(z3s)
     det_2 = VCZT_objective_lens(b_det2, r, f, xout, yout)
     # mid space
     a8, _ = d5.VRS_propagation(z5)
     a9, _ = d6.VRS_propagation(z5)
     # 3rd row
-    c7, d7 = BS_symmetric(d4, ls6, bs[6])
+    c7, d7 = BS(d4, ls6, 6)
     b8, _ = c7.VRS_propagation(z1s)
-    c8, d8 = BS_symmetric(a8, b8, bs[7])
+    c8, d8 = BS(a8, b8, 7)
     b9, _ = c8.VRS_propagation(z2s)
-    c9, d9 = BS_symmetric(a9, b9, bs[8])
-    b_det3, _ = building_block(c9, phase3_1, phase3_2, z3_1, eta3, theta3).VRS_propagation(z3_2)
+    c9, d9 = BS(a9, b9, 8)
+    b_det3, _ = block(c9, 12, z3_1).VRS_propagation(z3_2)
     det_3 = VCZT_objective_lens(b_det3, r, f, xout, yout)
     # detector row
     det_4 = VCZT_objective_lens(d7, r, f, xout, yout)
