@@ -179,10 +179,12 @@ def kernel_model(name, op):
     u = 8 N^2 bytes and of length-4096 FFTs (DESIGN.md section 4 states both per kernel).  F = planes per launch."""
     N, L = N_GRID, 2 * N_GRID
     F = 3 if op in ("vrs", "vczt") else 1
+    # the bench operators differentiate with respect to z: H and the reduced dH/dz are generated together (XL_WITH_HZ), one
+    # h_rows launch (row y of both per CTA) and one h_cols launch over both buffers
     if name == "h_rows":
-        return 1.0, L // 2 + 1                       # analytic samples -> row spectra of the rows y >= 0, x-bins <= L/2
+        return 2.0, 2 * (L // 2 + 1)                 # analytic samples -> row spectra of the rows y >= 0, x-bins <= L/2, of H and dH/dz
     if name == "h_cols":
-        return 2.0, L // 2 + 1                       # read them, write the y-even column spectra (+ the column copies)
+        return 4.0, 2 * (L // 2 + 1)                 # read them, write the y-even column spectra (+ the column copies), both buffers
     if name == "rs_rows_fwd":
         return (2.0 + 2.0 * F) if op == "vrs" else 3.0 * F, N * F          # read the planes (VRS: Ex, Ey once), write N x L spectra
     if name == "rs_cols":
@@ -190,11 +192,9 @@ def kernel_model(name, op):
     if name == "rs_rows_inv":
         return 3.0 * F, N * F
     if name == "rs_rows_dual":
-        return 6.0 * F, 2 * N * F                    # cotangent + conj(field) in, interleaved spectra out
+        return 7.0 * F, 2 * N * F                    # cotangent + conj(field) + primal output (exact i k out term of d/dz) in, interleaved spectra out
     if name == "rs_cols_gz":
         return 6.0 * F + 4.0, 3 * L * F              # (C, W) spectra in, C*H out; H and the reduced dH/dz once
-    if name == "dot_z":
-        return 2.0 * F, 0
     if name == "fold":
         return 7.0 if op == "vrs" else 5.0, 0
     if name.startswith("czt_axis"):
@@ -210,7 +210,7 @@ def ncu_class(name):
         return fixed[name] + "<4096>"
     if name.startswith("czt_axis<"):
         return "XlCztAxis<4096, " + ", ".join(name[9:-1].split(",")) + ">"
-    return {"dot_z": "XlDotZ", "fold": "XlFold", "czt_tables": "XlCztTables"}.get(name, name)
+    return {"fold": "XlFold", "czt_tables": "XlCztTables"}.get(name, name)
 
 
 def family_of(name):

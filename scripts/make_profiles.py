@@ -13,7 +13,7 @@ out.append(f"bench.py (N=1 B200, {bench['steps']} steps, {bench['warmup']} warm-
 out.append(f"  value {bench['value']:.1f} {bench['unit']} (device-resident), e2e {bench['e2e']['value']:.1f}, {bench['ms_per_step']:.3f} ms/step, "
            f"{bench['gpu_launches']} launches; cpu_baseline {bench.get('cpu_baseline', {}).get('value')} on {bench.get('cpu_baseline', {}).get('cores')} cores")
 r = bench["roofline"]
-out.append(f"  roofline: {r['kernel']}: {r['achieved']:.0f} GB/s algorithmic = {r['frac']:.3f} of measured {r['peak']} GB/s; share of step {r['share_of_step']:.3f}\n")
+out.append(f"  roofline: {r['kernel']}: {r['achieved']:.0f} GB/s algorithmic = {r['frac']:.3f} of measured {r['peak']} GB/s; family share of step {r.get('family_share_of_step', r.get('share_of_step', 0)):.3f}\n")
 steps = bench["steps"]
 out.append(f"  roofline fp32 fraction {r.get('frac_fp32')}; whole step {r.get('whole_step')}")
 out.append("## kernel families inside a bench step (separate CUDA-event pass; us per step, share, HBM and fp32 roofline fractions)")

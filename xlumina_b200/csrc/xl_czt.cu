@@ -165,7 +165,7 @@ static void czt_out_const(XlCztParams& a, const CztCall& cc) {
 
 template <int PRO, int EPI, int ACC> static int czt_axis_launch_t(const XlCztParams& a, XlDim grid, xl_stream_t st) {
     int rc;
-    XL_FOR_L(a.L, rc = xl_launch<XlCztAxis<XL, PRO, EPI, ACC>>(grid, st, a));
+    XL_FOR_L(a.L, rc = xl_launch<XlCztAxis<XL, PRO, EPI, ACC>>(XlDim{grid.x * grid.y, 1}, st, a));   // component-minor order
     return rc;
 }
 // The (prologue, epilogue, access shape) combinations the forward and adjoint chains use, each compiled branch-free.

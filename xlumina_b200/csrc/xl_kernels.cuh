@@ -834,24 +834,65 @@ template <int L, int PRO, int EPI, int ACC> struct XlCztOp : XlOpBase {
     static constexpr bool kInLoHalf = ACC != XL_ACC_GENERIC;
     static constexpr bool kOutLoHalf = ACC != XL_ACC_GENERIC;
     const XlCztParams& p; int lb, cl, comp; float z; cf cst;   // cl: launch-local plane, comp: component
-    XL_DEV bool in_lo_rt() const { return p.m_in <= L / 2; }   // zero padding fills the upper half: skip its loads and factors
-    // grid indices (jx, jy) of (line, pos): swap=0 -> x from line, y from pos; swap=1 -> x from pos, y from line
-    XL_DEV void gidx(const XlGridFactor& g, int line, int pos, int* jx, int* jy) const {
-        *jx = g.swap ? pos : line;
-        *jy = g.swap ? line : pos;
+    // Hoisted out of the per-element code (all CTA-uniform): a factor-table entry is  line_part + fac_idx(pos) * pos_stride,
+    // whichever way the (line, position) pair maps onto (x, y) and whichever way the table is laid out.
+    struct Tab { long long line_part[XL_V]; int pos_stride, pos_n, pos_mask; float sline[XL_V]; };   // pos_mask: -1 on a mirrored axis
+    Tab tp, te;              // prologue / epilogue table
+    float lcoord[XL_V];      // VCZT: coordinate of each line along its own axis
+    double pos0, dpos;       // VCZT: coordinates along the position axis
+    // index and sign of position j on the table's position axis, branch-free (a branch here would split the first pass's loads)
+    XL_DEV static int pos_idx(const Tab& t, int j) {
+        int m = 2 * j - (t.pos_n - 1);
+        m = (m < 0 ? -m : m) >> 1;
+        return (m & t.pos_mask) | (j & ~t.pos_mask);
     }
-    XL_DEV cf fac(const XlFacTab& t, int jx, int jy, int c = 0) const {
-        return xl_ldg(t.T + xl_fac_entry(t, xl_fac_idx(t.ax, jx), xl_fac_idx(t.ay, jy), c));
+    XL_DEV static float pos_sign(const Tab& t, int j) { return ((2 * j < t.pos_n - 1) & (t.pos_mask != 0)) ? -1.f : 1.f; }
+    XL_DEV bool in_lo_rt() const { return p.m_in <= L / 2; }   // zero padding fills the upper half: skip its loads and factors
+    XL_DEV static Tab tab_split(const XlFacTab& t, const XlGridFactor& g, int lb, int nlines, int c) {
+        Tab r;
+#pragma unroll
+        for (int l = 0; l < XL_V; ++l) {
+            const int line = lb + l < nlines ? lb + l : 0;
+            if (!g.swap) {       // x from the line, y from the position
+                const int ix = xl_fac_idx(t.ax, line);
+                r.line_part[l] = t.tr ? ((long long)c * t.Qx + ix) * t.Qy : (long long)c * t.Qy * t.Qx + ix;
+                r.sline[l] = xl_fac_sign(t.ax, line);
+            } else {             // y from the line, x from the position
+                const int iy = xl_fac_idx(t.ay, line);
+                r.line_part[l] = t.tr ? (long long)c * t.Qx * t.Qy + iy : ((long long)c * t.Qy + iy) * t.Qx;
+                r.sline[l] = xl_fac_sign(t.ay, line);
+            }
+        }
+        r.pos_stride = g.swap ? (t.tr ? t.Qy : 1) : (t.tr ? 1 : t.Qx);
+        r.pos_n = g.swap ? t.ax.n : t.ay.n;
+        r.pos_mask = (g.swap ? t.ax.sym : t.ay.sym) ? -1 : 0;
+        return r;
+    }
+    XL_DEV void prepare() {
+        if (PRO != XL_PRO_NONE) tp = tab_split(p.tpro, p.gpro, lb, p.nlines, PRO == XL_PRO_HIGHNA ? comp : 0);
+        if (EPI == XL_EPI_RSF) te = tab_split(p.tepi, p.gepi, lb, p.nlines, 0);
+#pragma unroll
+        for (int l = 0; l < XL_V; ++l) {
+            const int line = lb + l < p.nlines ? lb + l : 0;
+            lcoord[l] = p.gpro.swap ? (float)(p.gpro.y0 + line * p.gpro.dy) : (float)(p.gpro.x0 + line * p.gpro.dx);
+        }
+        pos0 = p.gpro.swap ? p.gpro.x0 : p.gpro.y0;
+        dpos = p.gpro.swap ? p.gpro.dx : p.gpro.dy;
+    }
+    XL_DEV cf fac(const XlFacTab& t, const Tab& tb, int l, int ipos) const {
+        return xl_ldg(t.T + tb.line_part[l] + (long long)ipos * tb.pos_stride);
     }
     // raw operand(s) of both lines at position i (branch-free: out-of-range samples read a valid address, zeroed later)
     XL_DEV void fetch(const cf* src, int i, bool ok_i, cf* a) const {
         if (ACC == XL_ACC_PAIR_IN) {
-            xl_ld4(src + (ok_i ? (long long)lb + (long long)i * p.in_pos : 0), a, a + 1);
+            xl_ld4(src + (((long long)lb + (long long)i * p.in_pos) & -(long long)ok_i), a, a + 1);
         } else {
 #pragma unroll
             for (int l = 0; l < XL_V; ++l) {
                 const bool ok = ok_i && lb + l < p.nlines;
-                a[l] = src[ok ? (long long)(lb + l) * p.in_line + (long long)i * p.in_pos : 0];
+                // masked, not selected: the compiler turns a select around a 64-bit address into a branch, and a branch
+                // here splits the first pass's loads into dependent groups (round 2: +18 % on the row-input passes)
+                a[l] = src[((long long)(lb + l) * p.in_line + (long long)i * p.in_pos) & -(long long)ok];
             }
         }
     }
@@ -865,34 +906,37 @@ template <int L, int PRO, int EPI, int ACC> struct XlCztOp : XlOpBase {
             fetch(p.in + p.in_comp, i, ok_i, b);     // Ey
         }
         const cf pre = xl_ldg(p.pre + (ok_i ? i : 0));
+        const int pi = ok_i ? i : 0;
+        int ipos = 0;
+        float spos = 1.f, cpos = 0.f;
+        if (PRO != XL_PRO_NONE) {
+            ipos = pos_idx(tp, pi);
+            if (PRO == XL_PRO_HIGHNA) spos = pos_sign(tp, pi);
+            if (PRO == XL_PRO_VCZT) cpos = (float)(pos0 + pi * dpos);
+        }
 #pragma unroll
         for (int l = 0; l < XL_V; ++l) {
             const int line = lb + l;
             cf x;
             if (PRO == XL_PRO_NONE) {
                 x = (p.flags & XL_F_CONJ_IN) ? cf_conj(a[l]) : a[l];
-            } else {
-                int jx, jy;
-                gidx(p.gpro, line, ok_i ? i : 0, &jx, &jy);
-                if (line >= p.nlines) { jx = 0; jy = 0; }
-                if (PRO == XL_PRO_RSF) {          // F = h(X, Y; z), wave_optics.py:341,344
-                    x = (p.flags & XL_F_CONJ_IN) ? cf_conj(a[l]) : a[l];
-                    x = cf_mul(x, fac(p.tpro, jx, jy));
-                } else if (PRO == XL_PRO_VCZT) {
-                    // comp 0/1: Ex / Ey;  comp 2: Ez = ((Ex X + Ey Y)/r) * z/r     vectorized_optics.py:341-344
-                    // (an amplitude factor: fp32 coordinates are enough; the phase lives in F)
-                    const float X = (float)(p.gpro.x0 + jx * p.gpro.dx), Y = (float)(p.gpro.y0 + jy * p.gpro.dy);
-                    const float ir2 = 1.0f / (X * X + Y * Y + z * z);
-                    const float ax = comp == 0 ? 1.f : (comp == 1 ? 0.f : X * z * ir2);
-                    const float ay = comp == 0 ? 0.f : (comp == 1 ? 1.f : Y * z * ir2);
-                    x = cf_mul(cf_lin2(a[l], ax, b[l], ay), fac(p.tpro, jx, jy));
-                } else {  // XL_PRO_HIGHNA: row `comp` of apod*G*RL(theta,phi), stored for |x|,|y| with the parity of each entry
-                    const cf w = fac(p.tpro, jx, jy, comp);
-                    const float sx = xl_fac_sign(p.tpro.ax, jx), sy = xl_fac_sign(p.tpro.ay, jy), sxy = sx * sy;
-                    const float ax = w.x * (comp == 0 ? 1.f : (comp == 1 ? sxy : sx));
-                    const float ay = w.y * (comp == 0 ? sxy : (comp == 1 ? 1.f : sy));
-                    x = cf_lin2(a[l], ax, b[l], ay);
-                }
+            } else if (PRO == XL_PRO_RSF) {          // F = h(X, Y; z), wave_optics.py:341,344
+                x = (p.flags & XL_F_CONJ_IN) ? cf_conj(a[l]) : a[l];
+                x = cf_mul(x, fac(p.tpro, tp, l, ipos));
+            } else if (PRO == XL_PRO_VCZT) {
+                // comp 0/1: Ex / Ey;  comp 2: Ez = ((Ex X + Ey Y)/r) * z/r     vectorized_optics.py:341-344
+                // (an amplitude factor: fp32 coordinates are enough; the phase lives in F)
+                const float X = p.gpro.swap ? cpos : lcoord[l], Y = p.gpro.swap ? lcoord[l] : cpos;
+                const float ir2 = 1.0f / (X * X + Y * Y + z * z);
+                const float ax = comp == 0 ? 1.f : (comp == 1 ? 0.f : X * z * ir2);
+                const float ay = comp == 0 ? 0.f : (comp == 1 ? 1.f : Y * z * ir2);
+                x = cf_mul(cf_lin2(a[l], ax, b[l], ay), fac(p.tpro, tp, l, ipos));
+            } else {  // XL_PRO_HIGHNA: row `comp` of apod*G*RL(theta,phi), stored for |x|,|y| with the parity of each entry
+                const cf w = fac(p.tpro, tp, l, ipos);
+                const float sx = p.gpro.swap ? spos : tp.sline[l], sy = p.gpro.swap ? tp.sline[l] : spos, sxy = sx * sy;
+                const float ax = w.x * (comp == 0 ? 1.f : (comp == 1 ? sxy : sx));
+                const float ay = w.y * (comp == 0 ? sxy : (comp == 1 ? 1.f : sy));
+                x = cf_lin2(a[l], ax, b[l], ay);
             }
             if (p.in_weight) x = cf_scale(x, (float)(p.in_weight == 1 ? i : line));   // kernel-uniform
             x = cf_mul(x, pre);
@@ -910,13 +954,9 @@ template <int L, int PRO, int EPI, int ACC> struct XlCztOp : XlOpBase {
     // output factor of (line, o): post-chirp * F0 * constant.  Gathered for ALL outputs of a thread before its first store:
     // the compiler may not move a load above a store to another pointer, and a load-use-store chain per output serialises
     // one L2 round trip per output (ncu round 2: 6 long-scoreboard stall cycles per issue in the epilogue kernels).
-    XL_DEV cf out_factor(int line, int o, cf post) const {
+    XL_DEV cf out_factor(int l, int ipos, cf post) const {
         cf w = post;
-        if (EPI == XL_EPI_RSF) {                  // F0 = h(Xout, Yout; z), wave_optics.py:340,355
-            int jx, jy;
-            gidx(p.gepi, line < p.nlines ? line : 0, o, &jx, &jy);
-            w = cf_mul(w, fac(p.tepi, jx, jy));
-        }
+        if (EPI == XL_EPI_RSF) w = cf_mul(w, fac(p.tepi, te, l, ipos));   // F0 = h(Xout, Yout; z), wave_optics.py:340,355
         return cf_mul(w, cst);
     }
     XL_DEV cf finish(cf val, cf w) const {
@@ -934,8 +974,9 @@ template <int L, int PRO, int EPI, int ACC> struct XlCztOp : XlOpBase {
                 const int o = n + S1 * (j0 + jj) - p.out_off;
                 const bool ok = o >= 0 && o < p.m_out;
                 const cf post = xl_ldg(p.post + (ok ? o : 0));
+                const int ipos = EPI == XL_EPI_RSF ? pos_idx(te, ok ? o : 0) : 0;
 #pragma unroll
-                for (int l = 0; l < XL_V; ++l) w[l * CH + jj] = out_factor(lb + l, ok ? o : 0, post);
+                for (int l = 0; l < XL_V; ++l) w[l * CH + jj] = out_factor(l, ipos, post);
             }
 #pragma unroll
             for (int jj = 0; jj < CH; ++jj) {
@@ -969,7 +1010,11 @@ template <int L, int PRO, int EPI, int ACC> struct XlCztAxis {
         const double z = p.z ? xl_ldg(p.z) : 0.0;
         double cr = p.epi_cr, ci = p.epi_ci;
         if (p.epi_times_z) { cr *= z; ci *= z; }
-        XlCztOp<L, PRO, EPI, ACC> op{{}, p, XL_BLOCK_X * XL_V, XL_BLOCK_Y, p.c0 + XL_BLOCK_Y, (float)z, make_float2((float)cr, (float)ci)};
+        // component-minor CTA order: the CTAs that read the same (Ex, Ey) samples of a line pair run together (ncu round 2: the
+        // vectorial first pass read 3.3x its algorithmic bytes from DRAM when blockIdx.y carried the component)
+        const int cl = XL_BLOCK_X % p.ncomp, lb = (XL_BLOCK_X / p.ncomp) * XL_V;
+        XlCztOp<L, PRO, EPI, ACC> op{{}, p, lb, cl, p.c0 + cl, (float)z, make_float2((float)cr, (float)ci)};
+        op.prepare();
         XlFft<L, XL_V>::conv_g(s, t, p.tw, op);
     }
 };
