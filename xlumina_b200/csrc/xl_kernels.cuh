@@ -110,6 +110,13 @@ XL_DEV double xl_rsqrt64(double r2) {
     const double e = fma(-(r2 * y), 0.5 * y, 0.5);   // 0.5 - 0.5*r2*y^2
     return fma(y, e, y);
 }
+// 1/d for d > 0 to ~1e-15 relative, branch-free (fp32 reciprocal seed + two fp64 Newton steps; the library division carries
+// a slow path)
+XL_DEV double xl_rcp64(double d) {
+    double y = (double)xl_rcpf((float)d);
+    y = fma(y, fma(-d, y, 1.0), y);
+    return fma(y, fma(-d, y, 1.0), y);
+}
 struct XlRsHConst { double z, z2, k, kcyc, sg; };   // per-z constants shared by all samples
 XL_DEV XlRsHConst xl_rs_hconst(double z, double k) {
     XlRsHConst c;
@@ -143,7 +150,7 @@ template <int WHICH> XL_DEV void xl_rs_h_eval(double X, double Y, const XlRsHCon
         const double gpr = -3.0 * ir2 * ir2, gpi = 2.0 * c.k * ir3;
         const double f = c.z2 * y;                                   // z^2/r
         const double az = c.z < 0 ? -c.z : c.z;
-        const double w = -c.k * c.z * (X * X + Y * Y) * y / (r + az);   // k z (|z|/r - 1)
+        const double w = -c.k * c.z * (X * X + Y * Y) * y * xl_rcp64(r + az);   // k z (|z|/r - 1)
         // g + (z^2/r) g' + i w g
         const float far = (float)((gr + f * gpr - w * gi) * inv2pi), fai = (float)((gi + f * gpi + w * gr) * inv2pi);
         *hz = make_float2(far * cs - fai * sn, far * sn + fai * cs);
@@ -927,7 +934,7 @@ template <int L, int PRO, int EPI, int ACC> struct XlCztOp : XlOpBase {
                 // comp 0/1: Ex / Ey;  comp 2: Ez = ((Ex X + Ey Y)/r) * z/r     vectorized_optics.py:341-344
                 // (an amplitude factor: fp32 coordinates are enough; the phase lives in F)
                 const float X = p.gpro.swap ? cpos : lcoord[l], Y = p.gpro.swap ? lcoord[l] : cpos;
-                const float ir2 = 1.0f / (X * X + Y * Y + z * z);
+                const float ir2 = xl_rcpf(X * X + Y * Y + z * z);   // MUFU.RCP: an IEEE division carries a slow-path branch that splits the loads
                 const float ax = comp == 0 ? 1.f : (comp == 1 ? 0.f : X * z * ir2);
                 const float ay = comp == 0 ? 0.f : (comp == 1 ? 1.f : Y * z * ir2);
                 x = cf_mul(cf_lin2(a[l], ax, b[l], ay), fac(p.tpro, tp, l, ipos));
@@ -938,7 +945,8 @@ template <int L, int PRO, int EPI, int ACC> struct XlCztOp : XlOpBase {
                 const float ay = w.y * (comp == 0 ? sxy : (comp == 1 ? 1.f : sy));
                 x = cf_lin2(a[l], ax, b[l], ay);
             }
-            if (p.in_weight) x = cf_scale(x, (float)(p.in_weight == 1 ? i : line));   // kernel-uniform
+            // index weight of the d/dz chains; a multiply by 1 otherwise (a branch here, even a uniform one, splits the loads)
+            x = cf_scale(x, p.in_weight == 0 ? 1.f : (float)(p.in_weight == 1 ? i : line));
             x = cf_mul(x, pre);
             v[l * stride] = (ok_i && line < p.nlines) ? x : cf_zero();
         }
