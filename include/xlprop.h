@@ -215,6 +215,46 @@ int xl_highna_bwd(const void* ct_out, void* ct_exy, int N, int Mx, int My, doubl
                   double x0, double dx, double y0, double dy, double xout0, double xoutl, double yout0, double youtl,
                   int flags, void* tables, void* ws, size_t ws_bytes, void* stream);
 
+/* ---------------------------------------------------------------- batched entry points --------------------- */
+/* The reference vmaps its seam functions over masks, candidate set-ups and noisy distances (experiments/four_f_optical_table.py:98,
+ * examples/noisy_optimization.ipynb cell 7): `nbatch` independent propagations in ONE library call.
+ *   - outputs, cotangents and gradients gain a contiguous leading batch axis; vectorial inputs keep the (ex, ey) convention of
+ *     the single-item calls with `in_bstride` ELEMENTS between the Ex planes (and between the Ey planes) of consecutive items
+ *     (2*N*N for a stacked (B,2,N,N) array with ey == NULL, N*N for two (B,N,N) arrays);
+ *   - z[b * z_stride] is item b's distance.  z_stride == 0: ONE distance -- one transfer function / one set of tables, and for the
+ *     scalar operators single launches over all the planes of the batch; grad_z then receives the sum over the batch.
+ *     z_stride != 0: one distance per item -- `H` holds nbatch buffers xl_rs_transfer_bytes(N) apart (2 * that with XL_WITH_HZ),
+ *     all generated in ONE launch pair; `tables` holds nbatch buffers xl_czt_tables_bytes() apart; grad_z[b * gz_stride] per item.
+ *   - `ws`: xl_rs_workspace_bytes(N, nfields * nbatch, .) for the scalar RS calls with z_stride == 0, xl_czt_workspace_bytes_batch()
+ *     for the CZT calls, otherwise the single-item size (the items reuse it in stream order).
+ * Flags as in the single-item calls. */
+int xl_rs_fwd_batch(const void* in, void* out, void* H, const double* z, int z_stride, int N, int nfields, int nbatch,
+                    double dx, double dy, double k, int flags, void* ws, size_t ws_bytes, void* stream);
+int xl_rs_bwd_batch(const void* in, const void* out, const void* ct_out, void* ct_in, double* grad_z, int gz_stride, const void* H,
+                    const double* z, int z_stride, int N, int nfields, int nbatch, double dx, double dy, double k, int flags,
+                    void* ws, size_t ws_bytes, void* stream);
+int xl_vrs_fwd_batch(const void* ex, const void* ey, long long in_bstride, void* out, void* H, const double* z, int z_stride,
+                     int N, int nbatch, double x0, double y0, double dx, double dy, double k, int flags,
+                     void* ws, size_t ws_bytes, void* stream);
+int xl_vrs_bwd_batch(const void* ex, const void* ey, long long in_bstride, const void* out, const void* ct_out, void* ct_exy,
+                     double* grad_z, int gz_stride, const void* H, const double* z, int z_stride, int N, int nbatch,
+                     double x0, double y0, double dx, double dy, double k, int flags, void* ws, size_t ws_bytes, void* stream);
+size_t xl_czt_workspace_bytes_batch(int N, int Mx, int My, int vectorial, int nbatch);
+int xl_czt_fwd_batch(const void* in, const void* ey, long long in_bstride, void* out, const double* z, int z_stride, double lambda,
+                     int N, int Mx, int My, int vectorial, int nbatch,
+                     double x0, double dx, double y0, double dy, double xout0, double xoutl, double yout0, double youtl,
+                     int flags, void* tables, void* ws, size_t ws_bytes, void* stream);
+int xl_czt_bwd_batch(const void* ct_out, void* ct_in, const double* z, int z_stride, double lambda,
+                     int N, int Mx, int My, int vectorial, int nbatch,
+                     double x0, double dx, double y0, double dy, double xout0, double xoutl, double yout0, double youtl,
+                     int flags, void* tables, void* ws, size_t ws_bytes, void* stream);
+int xl_highna_fwd_batch(const void* ex, const void* ey, long long in_bstride, void* out, int N, int Mx, int My, int nbatch,
+                        double radius, double f, double lambda, double x0, double dx, double y0, double dy,
+                        double xout0, double xoutl, double yout0, double youtl, int flags, void* tables, void* ws, size_t ws_bytes, void* stream);
+int xl_highna_bwd_batch(const void* ct_out, void* ct_exy, int N, int Mx, int My, int nbatch, double radius, double f, double lambda,
+                        double x0, double dx, double y0, double dy, double xout0, double xoutl, double yout0, double youtl,
+                        int flags, void* tables, void* ws, size_t ws_bytes, void* stream);
+
 /* ---------------------------------------------------------------- pointwise Jones elements (vectorial tables) */
 /* The elements that sit between the propagations of a vectorial optical table, each as ONE pass over the
  * planes it changes, forward and VJP, with the reference's parameter maps and the reductions of the scalar-parameter

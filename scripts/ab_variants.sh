@@ -1,6 +1,6 @@
 #!/usr/bin/env bash
 # A/B timing of experiment variants of the library (experiment queue).
-#   1. here (build container):   bash scripts/ab_variants.sh build all        (or a list: XL_EXP_TREE_REDUCE split=2 A,B ...)
+#   1. here (build container):   bash scripts/ab_variants.sh build MACRO...   (e.g. XL_NO_SYNCWARP: CTA barriers instead of the warp-level ones)
 #        -> build/libxlprop_<macro>.so per macro (build/ is git-ignored but travels with gpurun)
 #   2. on the GPU:   gpurun --timeout 600 -- 'bash scripts/ab_variants.sh time'
 #        -> gpurun_out/ab_<name>.log: scripts/gpu_probe.py timings of every operation for the product library and each variant,
@@ -12,15 +12,8 @@ cd "$(dirname "$0")/.."
 case "${1:-}" in
 build)
     shift
-    # "all": every experiment of DESIGN.md's queue that exists in the tree, one library each, plus the other partitioning
-    if [ "${1:-}" = "all" ]; then
-        set -- XL_EXP_K4_PERSIST XL_EXP_K4_STAGE XL_EXP_K2_PERSIST XL_EXP_K2_STAGE XL_EXP_CZT_PERSIST XL_EXP_KEEP_SPECTRA \
-               XL_EXP_K4_PREFETCH XL_EXP_TREE_REDUCE XL_EXP_ROWS_3CTA XL_EXP_FIELD_MINOR split=2 \
-               XL_EXP_K4_PERSIST,XL_EXP_K2_PERSIST,XL_EXP_CZT_PERSIST,XL_EXP_TREE_REDUCE
-    fi
     for m in "$@"; do
         case "$m" in
-        split=*) python -m xlumina_b200.build --split "${m#split=}" --out "build/libxlprop_split${m#split=}.so" || exit 1 ;;   # same source, other -split-compile partitioning
         *)       python -m xlumina_b200.build --exp "$m" --out "build/libxlprop_$m.so" || exit 1 ;;
         esac
     done

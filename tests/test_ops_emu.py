@@ -174,6 +174,18 @@ def test_leading_batch_axes_and_per_item_distances(ops_on_emu):
     assert torch.equal(ob[1], ops.vrs_propagation(ex[1], ey[1], 3000.0, float(x[0]), float(x[0]), dx, dx, k))
     g, = torch.autograd.grad((ob * c(2, 3, N, N)).real.sum(), ex)
     assert g.shape == ex.shape and float(g.abs().min()) > 0
+    # one batched call (xl_vrs_*_batch) with a distance per item: field and distance gradients equal the single-item calls
+    zv = torch.tensor([3000.0, 3300.0], dtype=torch.float64, requires_grad=True)
+    eyg = ey.clone().requires_grad_(True)
+    ctv = c(2, 3, N, N)
+    ob = ops.vrs_propagation(ex, eyg, zv, float(x[0]), float(x[0]), dx, dx, k)
+    gx, gy, gzv = torch.autograd.grad((ob * ctv).real.sum(), (ex, eyg, zv))
+    for i in range(2):
+        exi, eyi = ex.detach()[i].clone().requires_grad_(True), ey[i].clone().requires_grad_(True)
+        zi = zv.detach()[i:i + 1].clone().requires_grad_(True)
+        oi = ops.vrs_propagation(exi, eyi, zi, float(x[0]), float(x[0]), dx, dx, k)
+        gxi, gyi, gzi = torch.autograd.grad((oi * ctv[i]).real.sum(), (exi, eyi, zi))
+        assert torch.equal(gxi, gx[i]) and torch.equal(gyi, gy[i]) and float(gzi) == float(gzv[i])
 
     cb = ops.czt(u.detach(), torch.tensor([9000.0, 9500.0, 8000.0], dtype=torch.float64), lam, x, x, xo, xo)
     assert cb.shape == (3, M, M) and torch.equal(cb[2], ops.czt(u.detach()[2], 8000.0, lam, x, x, xo, xo))

@@ -16,6 +16,7 @@ _vp = ctypes.c_void_p
 _i = ctypes.c_int
 _d = ctypes.c_double
 _sz = ctypes.c_size_t
+_ll = ctypes.c_longlong
 
 # name -> (restype, argtypes); mirrors include/xlprop.h one to one
 SIGNATURES = {
@@ -51,6 +52,15 @@ SIGNATURES = {
     "xl_highna_workspace_bytes": (_sz, [_i, _i, _i]),
     "xl_highna_tables_bytes": (_sz, [_i, _i, _i]),
     "xl_highna_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _d, _d, _d, _d, _d, _d, _d, _d, _d, _d, _d, _i, _vp, _vp, _sz, _vp]),
+    "xl_rs_fwd_batch": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _d, _d, _d, _i, _vp, _sz, _vp]),
+    "xl_rs_bwd_batch": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _d, _d, _d, _i, _vp, _sz, _vp]),
+    "xl_vrs_fwd_batch": (_i, [_vp, _vp, _ll, _vp, _vp, _vp, _i, _i, _i, _d, _d, _d, _d, _d, _i, _vp, _sz, _vp]),
+    "xl_vrs_bwd_batch": (_i, [_vp, _vp, _ll, _vp, _vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _d, _d, _d, _d, _d, _i, _vp, _sz, _vp]),
+    "xl_czt_workspace_bytes_batch": (_sz, [_i, _i, _i, _i, _i]),
+    "xl_czt_fwd_batch": (_i, [_vp, _vp, _ll, _vp, _vp, _i, _d, _i, _i, _i, _i, _i, _d, _d, _d, _d, _d, _d, _d, _d, _i, _vp, _vp, _sz, _vp]),
+    "xl_czt_bwd_batch": (_i, [_vp, _vp, _vp, _i, _d, _i, _i, _i, _i, _i, _d, _d, _d, _d, _d, _d, _d, _d, _i, _vp, _vp, _sz, _vp]),
+    "xl_highna_fwd_batch": (_i, [_vp, _vp, _ll, _vp, _i, _i, _i, _i, _d, _d, _d, _d, _d, _d, _d, _d, _d, _d, _d, _i, _vp, _vp, _sz, _vp]),
+    "xl_highna_bwd_batch": (_i, [_vp, _vp, _i, _i, _i, _i, _d, _d, _d, _d, _d, _d, _d, _d, _d, _d, _d, _i, _vp, _vp, _sz, _vp]),
     "xl_el_scratch_bytes": (_sz, []),
     "xl_el_sslm": (_i, [_vp, _vp, _vp, _vp, _d, _d, _vp, _vp, _sz, _vp]),
     "xl_el_sslm_bwd": (_i, [_vp, _vp, _vp, _vp, _d, _d, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),

@@ -21,6 +21,7 @@ struct CztCall {
     double R, f, s2;
     int flags;
     long long ey_off;     // vectorial inputs: elements from the Ex plane to the Ey plane (N*N when stacked)
+    int batch;            // scalar CZT only: this many contiguous planes in ONE set of launches (0 or 1: a single plane)
 };
 static int axis_sym(double x0, double dx, int n) {   // grid symmetric about 0 (toolbox.space): one quadrant of a factor is enough
     const double span = fabs((n - 1) * dx);
@@ -49,7 +50,7 @@ extern "C" size_t xl_highna_tables_bytes(int N, int Mx, int My) { return czt_tab
 static int czt_plan(CztPlan& pl, const CztCall& cc, void* tables, void* ws, size_t ws_bytes) {
     const int N = cc.N, Mx = cc.Mx, My = cc.My;
     if (N < 2 || Mx < 2 || My < 2) return xl_fail(XL_E_BAD_ARG, "czt: sizes must be >= 2%s", "");
-    pl.N = N; pl.Mx = Mx; pl.My = My; pl.mode = cc.mode; pl.ncomp = cc.mode == 0 ? 1 : 3;
+    pl.N = N; pl.Mx = Mx; pl.My = My; pl.mode = cc.mode; pl.ncomp = cc.mode == 0 ? (cc.batch > 1 ? cc.batch : 1) : 3;
     pl.Ly = xl_czt_padded_length(N, My);
     pl.Lx = xl_czt_padded_length(N, Mx);
     if (!pl.Ly || !pl.Lx) return xl_fail(XL_E_UNSUPPORTED, "czt: m+M-1 is a power of two or padded length outside [32,4096]%s", "");
@@ -388,4 +389,84 @@ extern "C" int xl_highna_bwd(const void* ct_out, void* ct_exy, int N, int Mx, in
                              int flags, void* tables, void* ws, size_t ws_bytes, void* stream) {
     CztCall c = make_czt_call(2, 0, lambda, N, Mx, My, x0, dx, y0, dy, xout0, xoutl, yout0, youtl, radius, f, flags);
     return czt_backward(c, ct_out, ct_exy, tables, ws, ws_bytes, (xl_stream_t)stream);
+}
+
+
+// ================================================================================================ batched entry points
+// `nbatch` independent propagations in ONE call (the reference vmaps the seam functions, include/xlprop.h).  Scalar CZT with a
+// shared distance runs all the planes in a single set of launches; the other shapes walk the items inside the library
+// (shared distance: the tables are filled once).
+extern "C" size_t xl_czt_workspace_bytes_batch(int N, int Mx, int My, int vectorial, int nbatch) {
+    if (nbatch < 1) return 0;
+    return czt_ws_bytes(N, Mx, My, vectorial ? 3 : nbatch);
+}
+extern "C" int xl_czt_fwd_batch(const void* in, const void* ey, long long in_bstride, void* out, const double* z, int z_stride, double lambda,
+                                int N, int Mx, int My, int vectorial, int nbatch,
+                                double x0, double dx, double y0, double dy, double xout0, double xoutl, double yout0, double youtl,
+                                int flags, void* tables, void* ws, size_t ws_bytes, void* stream) {
+    if (nbatch < 1 || z_stride < 0 || !z) return xl_fail(XL_E_BAD_ARG, "xl_czt_fwd_batch: bad batch shape%s", "");
+    xl_stream_t st = (xl_stream_t)stream;
+    if (!vectorial && z_stride == 0 && in_bstride == (long long)N * N) {
+        CztCall c = make_czt_call(0, z, lambda, N, Mx, My, x0, dx, y0, dy, xout0, xoutl, yout0, youtl, 0, 0, flags);
+        c.batch = nbatch;
+        return czt_forward(c, in, out, tables, ws, ws_bytes, st);
+    }
+    const size_t tb = czt_tab_bytes(N, Mx, My, 0), oplane = (size_t)(vectorial ? 3 : 1) * My * Mx * sizeof(cf);
+    for (int b = 0; b < nbatch; ++b) {
+        const int f = flags | ((z_stride == 0 && b > 0) ? XL_REUSE_TABLES : 0);
+        CztCall c = make_czt_call(vectorial ? 1 : 0, z + (size_t)b * z_stride, lambda, N, Mx, My, x0, dx, y0, dy, xout0, xoutl, yout0, youtl, 0, 0, f);
+        const char* inb = (const char*)in + (size_t)b * in_bstride * sizeof(cf);
+        const char* eyb = ey ? (const char*)ey + (size_t)b * in_bstride * sizeof(cf) : 0;
+        if (vectorial) { int rc = set_planes(c, inb, eyb); if (rc) return rc; }
+        int rc = czt_forward(c, inb, (char*)out + b * oplane, (char*)tables + (z_stride ? b * tb : 0), ws, ws_bytes, st);
+        if (rc) return rc;
+    }
+    return XL_OK;
+}
+extern "C" int xl_czt_bwd_batch(const void* ct_out, void* ct_in, const double* z, int z_stride, double lambda,
+                                int N, int Mx, int My, int vectorial, int nbatch,
+                                double x0, double dx, double y0, double dy, double xout0, double xoutl, double yout0, double youtl,
+                                int flags, void* tables, void* ws, size_t ws_bytes, void* stream) {
+    if (nbatch < 1 || z_stride < 0 || !z) return xl_fail(XL_E_BAD_ARG, "xl_czt_bwd_batch: bad batch shape%s", "");
+    xl_stream_t st = (xl_stream_t)stream;
+    if (!vectorial && z_stride == 0) {
+        CztCall c = make_czt_call(0, z, lambda, N, Mx, My, x0, dx, y0, dy, xout0, xoutl, yout0, youtl, 0, 0, flags);
+        c.batch = nbatch;
+        return czt_backward(c, ct_out, ct_in, tables, ws, ws_bytes, st);
+    }
+    const size_t tb = czt_tab_bytes(N, Mx, My, 0), oplane = (size_t)(vectorial ? 3 : 1) * My * Mx * sizeof(cf),
+                 iplane = (size_t)(vectorial ? 2 : 1) * N * N * sizeof(cf);
+    for (int b = 0; b < nbatch; ++b) {
+        const int f = flags | ((z_stride == 0 && b > 0) ? XL_REUSE_TABLES : 0);
+        CztCall c = make_czt_call(vectorial ? 1 : 0, z + (size_t)b * z_stride, lambda, N, Mx, My, x0, dx, y0, dy, xout0, xoutl, yout0, youtl, 0, 0, f);
+        int rc = czt_backward(c, (const char*)ct_out + b * oplane, (char*)ct_in + b * iplane, (char*)tables + (z_stride ? b * tb : 0), ws, ws_bytes, st);
+        if (rc) return rc;
+    }
+    return XL_OK;
+}
+extern "C" int xl_highna_fwd_batch(const void* ex, const void* ey, long long in_bstride, void* out, int N, int Mx, int My, int nbatch,
+                                   double radius, double f, double lambda, double x0, double dx, double y0, double dy,
+                                   double xout0, double xoutl, double yout0, double youtl, int flags, void* tables, void* ws, size_t ws_bytes, void* stream) {
+    if (nbatch < 1) return xl_fail(XL_E_BAD_ARG, "xl_highna_fwd_batch: bad batch shape%s", "");
+    const size_t oplane = (size_t)3 * My * Mx * sizeof(cf);
+    for (int b = 0; b < nbatch; ++b) {
+        const char* exb = (const char*)ex + (size_t)b * in_bstride * sizeof(cf);
+        const char* eyb = ey ? (const char*)ey + (size_t)b * in_bstride * sizeof(cf) : 0;
+        int rc = xl_highna_fwd(exb, eyb, (char*)out + b * oplane, N, Mx, My, radius, f, lambda, x0, dx, y0, dy, xout0, xoutl, yout0, youtl,
+                               flags | (b > 0 ? XL_REUSE_TABLES : 0), tables, ws, ws_bytes, stream);   // the objective's tables serve every item
+        if (rc) return rc;
+    }
+    return XL_OK;
+}
+extern "C" int xl_highna_bwd_batch(const void* ct_out, void* ct_exy, int N, int Mx, int My, int nbatch, double radius, double f, double lambda,
+                                   double x0, double dx, double y0, double dy, double xout0, double xoutl, double yout0, double youtl,
+                                   int flags, void* tables, void* ws, size_t ws_bytes, void* stream) {
+    if (nbatch < 1) return xl_fail(XL_E_BAD_ARG, "xl_highna_bwd_batch: bad batch shape%s", "");
+    const size_t oplane = (size_t)3 * My * Mx * sizeof(cf), iplane = (size_t)2 * N * N * sizeof(cf);
+    for (int b = 0; b < nbatch; ++b) {
+        int rc = xl_highna_bwd((const char*)ct_out + b * oplane, (char*)ct_exy + b * iplane, N, Mx, My, radius, f, lambda, x0, dx, y0, dy,
+                               xout0, xoutl, yout0, youtl, flags | (b > 0 ? XL_REUSE_TABLES : 0), tables, ws, ws_bytes, stream);
+        if (rc) return rc;
+    }
+    return XL_OK;
 }

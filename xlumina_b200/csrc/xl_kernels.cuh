@@ -174,6 +174,7 @@ struct XlRsParams {
     // several transfer functions in one launch pair (xl_rs_transfer_multi): item = blockIdx.y, buffer H + item * h_stride,
     // distance z[item / h_per_z]; h_per_z == 2: even items hold H, odd items the reduced dH/dz of the same distance
     long long h_stride; int h_per_z;
+    int z_item_stride;   // xl_rs_transfer_multi from a batched call: item i (pair i) takes z[i * z_item_stride]; 0 means 1
     const cf* in;      // [nfields][N][N]   (XL_F_VRS: the Ex plane; Ey starts ey_off elements later)
     long long ey_off;  // XL_F_VRS: elements from the Ex plane to the Ey plane of the primal input (N*N when they are stacked)
     const cf* in2;     // rs_rows_dual: the primal field(s) whose conjugate is the second line (same shape rules as `in`)
@@ -641,7 +642,7 @@ template <int L> struct XlHRows {
         const bool dual = p.h_per_z == 2;
         const int yb = dual ? XL_BLOCK_X : XL_BLOCK_X * XL_V;
         const int item = XL_BLOCK_Y;
-        const XlRsHConst hc = xl_rs_hconst(xl_ldg(p.z + item), p.k);
+        const XlRsHConst hc = xl_rs_hconst(xl_ldg(p.z + (long long)item * (p.z_item_stride ? p.z_item_stride : 1)), p.k);
         const int deriv = (p.flags & XL_F_DERIV) ? 1 : 0;
         XL_THREADS(tid, NT) {
             cf tr[XlFft<L, XL_V>::kTwRegs];

@@ -221,6 +221,85 @@ class _RS(torch.autograd.Function):
         return gin, gz, None, None, None, None, None
 
 
+class _RSItems(torch.autograd.Function):
+    """field (B,N,N) c64, z (B,) f64 -- one distance per item (what vmapping a table over noisy distances gives the reference,
+    examples/noisy_optimization.ipynb cell 7) -> (B,N,N): ONE library call each way (xl_rs_fwd_batch / xl_rs_bwd_batch with
+    z_stride = 1); the B transfer functions (and reduced dH/dz) are generated in one launch pair."""
+
+    @staticmethod
+    @_on_device
+    def forward(ctx, field, z, dx, dy, k):
+        _require_device(field)
+        L = _lib.lib()
+        B, N = field.shape[0], field.shape[-1]
+        out = torch.empty_like(field)
+        hz = _lib.XL_WITH_HZ if z.requires_grad else 0
+        H = torch.empty(B * L.xl_rs_transfer_bytes(N) * (2 if hz else 1), dtype=torch.uint8, device=field.device)
+        ws = _workspace(field, L.xl_rs_workspace_bytes(N, 1, 0))
+        _lib.check(L.xl_rs_fwd_batch(_ptr(field), _ptr(out), _ptr(H), _ptr(z), 1, N, 1, B, dx, dy, k, hz, _ptr(ws), ws.numel(), _stream(field)),
+                   "xl_rs_fwd_batch")
+        ctx.save_for_backward(field, z, H, out)
+        ctx.geom = (dx, dy, k, hz)
+        return out
+
+    @staticmethod
+    @_on_device
+    def backward(ctx, g):
+        field, z, H, out = ctx.saved_tensors
+        dx, dy, k, hz = ctx.geom
+        L = _lib.lib()
+        B, N = field.shape[0], field.shape[-1]
+        g = g.resolve_conj().contiguous()
+        want_z = ctx.needs_input_grad[1]
+        gin = torch.empty_like(field)
+        gz = torch.zeros(B, dtype=torch.float64, device=field.device) if want_z else None
+        ws = _workspace(field, L.xl_rs_workspace_bytes(N, 1, 1 if want_z else 0))
+        _lib.check(L.xl_rs_bwd_batch(_ptr(field), _ptr(out), _ptr(g), _ptr(gin), _ptr(gz), 1, _ptr(H), _ptr(z), 1, N, 1, B, dx, dy, k,
+                                     _lib.XL_CONJ_IN | _lib.XL_CONJ_OUT | hz, _ptr(ws), ws.numel(), _stream(field)), "xl_rs_bwd_batch")
+        return gin, gz, None, None, None
+
+
+class _VRSBatch(torch.autograd.Function):
+    """A batch of vectorial RS propagations in ONE library call each way (xl_vrs_fwd_batch / xl_vrs_bwd_batch): `ex` is
+    (B,N,N) with `ey` (B,N,N), or a stacked (B,2,N,N) array with ey = None; z is one shared distance (1,) -- one transfer
+    function for the batch -- or one per item (B,).  Returns (B,3,N,N)."""
+
+    @staticmethod
+    @_on_device
+    def forward(ctx, ex, ey, z, x0, y0, dx, dy, k):
+        _require_device(ex)
+        L = _lib.lib()
+        B, N = ex.shape[0], ex.shape[-1]
+        zstr = 0 if z.numel() == 1 else 1
+        out = torch.empty((B, 3, N, N), dtype=ex.dtype, device=ex.device)
+        hz = _lib.XL_WITH_HZ if z.requires_grad else 0
+        H = torch.empty((B if zstr else 1) * L.xl_rs_transfer_bytes(N) * (2 if hz else 1), dtype=torch.uint8, device=ex.device)
+        bstride = N * N if ey is not None else 2 * N * N
+        ws = _workspace(ex, L.xl_rs_workspace_bytes(N, 3, 0))
+        _lib.check(L.xl_vrs_fwd_batch(_ptr(ex), _ptr(ey), bstride, _ptr(out), _ptr(H), _ptr(z), zstr, N, B, x0, y0, dx, dy, k, hz,
+                                      _ptr(ws), ws.numel(), _stream(ex)), "xl_vrs_fwd_batch")
+        ctx.save_for_backward(ex, ey, z, H, out)
+        ctx.geom = (x0, y0, dx, dy, k, hz, zstr, bstride)
+        return out
+
+    @staticmethod
+    @_on_device
+    def backward(ctx, g):
+        ex, ey, z, H, out = ctx.saved_tensors
+        x0, y0, dx, dy, k, hz, zstr, bstride = ctx.geom
+        L = _lib.lib()
+        B, N = ex.shape[0], ex.shape[-1]
+        g = g.resolve_conj().contiguous()
+        want_z = ctx.needs_input_grad[2]
+        gin = torch.empty((B, 2, N, N), dtype=ex.dtype, device=ex.device)
+        gz = torch.zeros(B if zstr else 1, dtype=torch.float64, device=ex.device) if want_z else None
+        ws = _workspace(ex, L.xl_rs_workspace_bytes(N, 3, 1 if want_z else 0))
+        _lib.check(L.xl_vrs_bwd_batch(_ptr(ex), _ptr(ey), bstride, _ptr(out), _ptr(g), _ptr(gin), _ptr(gz), zstr, _ptr(H), _ptr(z), zstr, N, B,
+                                      x0, y0, dx, dy, k, _lib.XL_CONJ_IN | _lib.XL_CONJ_OUT | hz, _ptr(ws), ws.numel(), _stream(ex)),
+                   "xl_vrs_bwd_batch")
+        return ((gin, None) if ey is None else (gin[:, 0], gin[:, 1])) + (gz, None, None, None, None, None)
+
+
 class _VRS(torch.autograd.Function):
     """(Ex, Ey) (N,N) each -> (3,N,N); Ez = (Ex X + Ey Y)/r formed at load (vectorized_optics.py:258-261).  The two planes are
     passed to the library where they live: no stacking copy."""
@@ -403,7 +482,11 @@ def rs_propagation(field, z, dx, dy, k):
         raise ValueError("RS propagation needs square fields")
     f = _c64(field).reshape(-1, N, N)
     zs = _z_per_item(z, f.shape[0])
-    if zs is not None:                      # one distance per field: one call each (every item has its own transfer function)
+    if zs is not None and N <= FUSED_MAX_N:  # one distance per field: ONE batched library call (every item has its own transfer function)
+        zv = z.to(device=f.device, dtype=torch.float64).reshape(-1).contiguous()
+        out = _RSItems.apply(f, zv, float(dx), float(dy), float(k)).reshape(field.shape)
+        return out if dt == torch.complex64 or not torch.is_complex(field) else out.to(dt)
+    if zs is not None:
         out = torch.stack([rs_propagation(f[i], zs[i], dx, dy, k) for i in range(f.shape[0])]).reshape(field.shape)
         return out if dt == torch.complex64 or not torch.is_complex(field) else out.to(dt)
     zt = _as_z(z, f)
@@ -436,6 +519,18 @@ def vrs_propagation(Ex, Ey, z, x0, y0, dx, dy, k, _hshare=None):
     """Vectorial RS: returns (3,N,N) = propagated [Ex, Ey, Ez].  Pass Ey=None if `Ex` is already the stacked (2,N,N) pair.
     With a leading batch axis (Ex, Ey (B,N,N) or stacked (B,2,N,N)) returns (B,3,N,N); z shared or one per item."""
     if Ex.dim() == (4 if Ey is None else 3):
+        if Ex.shape[-1] <= FUSED_MAX_N:       # the whole batch in ONE library call (shared or per-item distances)
+            dt = Ex.dtype
+            ex, ey = _planes(Ex, Ey)
+            B = ex.shape[0]
+            if isinstance(z, torch.Tensor) and z.numel() > 1:
+                if z.numel() != B:
+                    raise ValueError(f"z has {z.numel()} elements for a batch of {B} fields: pass one distance or one per field")
+                zt = z.to(device=ex.device, dtype=torch.float64).reshape(-1).contiguous()
+            else:
+                zt = _as_z(z, ex)
+            out = _VRSBatch.apply(ex, ey, zt, float(x0), float(y0), float(dx), float(dy), float(k))
+            return out if dt == torch.complex64 or not torch.is_complex(Ex) else out.to(dt)
         return _batch_of_pairs(lambda a, b, zz, hs: vrs_propagation(a, b, zz, x0, y0, dx, dy, k, hs), Ex, Ey, z)
     dt = Ex.dtype
     ex, ey = _planes(Ex, Ey)
