@@ -631,3 +631,46 @@ def test_element_kernels_on_device(kind):
     against the same elements composed from complex128 torch arithmetic."""
     from test_elements import check_element_kernels
     check_element_kernels(kind, "cuda:0")
+
+
+@pytest.mark.gpu
+def test_batched_entry_points_on_device():
+    """one library call for a batch (xl_rs_*_batch with a distance per item, xl_vrs_*_batch with a shared distance and
+    with one per item): outputs, field gradients and distance gradients equal the single-item calls."""
+    from xlumina_b200 import ops
+    dev = torch.device("cuda:0")
+    rng = np.random.default_rng(21)
+    N = 96
+    x = np.linspace(-900.0, 900.0, N)
+    dx, k = float(x[1] - x[0]), 2 * np.pi / 0.6328
+    c = lambda *s: torch.tensor((rng.standard_normal(s) + 1j * rng.standard_normal(s)).astype(np.complex64), device=dev)   # noqa: E731
+    u = c(3, N, N).requires_grad_(True)
+    zs = torch.tensor([9000.0, 11000.0, -8000.0], dtype=torch.float64, device=dev, requires_grad=True)
+    ct = c(3, N, N)
+    out = ops.rs_propagation(u, zs, dx, dx, k)
+    gu, gz = torch.autograd.grad((out * ct).real.sum(), (u, zs))
+    for i in range(3):
+        ui = u.detach()[i].clone().requires_grad_(True)
+        zi = zs.detach()[i:i + 1].clone().requires_grad_(True)
+        oi = ops.rs_propagation(ui, zi, dx, dx, k)
+        gui, gzi = torch.autograd.grad((oi * ct[i]).real.sum(), (ui, zi))
+        assert torch.equal(oi.detach(), out.detach()[i]) and torch.equal(gui, gu[i])
+        assert abs(float(gzi) - float(gz[i])) <= 1e-9 * abs(float(gzi))
+    ex, ey = c(2, N, N).requires_grad_(True), c(2, N, N).requires_grad_(True)
+    ctv = c(2, 3, N, N)
+    for z in (torch.tensor([9000.0], dtype=torch.float64, device=dev, requires_grad=True),
+              torch.tensor([9000.0, 9900.0], dtype=torch.float64, device=dev, requires_grad=True)):
+        ob = ops.vrs_propagation(ex, ey, z, float(x[0]), float(x[0]), dx, dx, k)
+        gx, gy, gzv = torch.autograd.grad((ob * ctv).real.sum(), (ex, ey, z))
+        tot = 0.0
+        for i in range(2):
+            exi, eyi = ex.detach()[i].clone().requires_grad_(True), ey.detach()[i].clone().requires_grad_(True)
+            zi = z.detach()[(i if z.numel() > 1 else 0):(i if z.numel() > 1 else 0) + 1].clone().requires_grad_(True)
+            oi = ops.vrs_propagation(exi, eyi, zi, float(x[0]), float(x[0]), dx, dx, k)
+            gxi, gyi, gzi = torch.autograd.grad((oi * ctv[i]).real.sum(), (exi, eyi, zi))
+            assert torch.equal(oi.detach(), ob.detach()[i]) and torch.equal(gxi, gx[i]) and torch.equal(gyi, gy[i])
+            if z.numel() > 1:
+                assert abs(float(gzi) - float(gzv[i])) <= 1e-9 * abs(float(gzi))
+            tot += float(gzi)
+        if z.numel() == 1:      # the shared distance receives the sum over the batch
+            assert abs(tot - float(gzv)) <= 1e-6 * abs(tot)
