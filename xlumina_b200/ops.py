@@ -144,7 +144,11 @@ def _grid(coords):
 # hybrid_setup_sharp_focus uses z1_1 + z1_2 three times, optical_elements.py:1609,1622; the 6x6 ansatz uses each of
 # z8..z12 six times): SURVEY.md 8f-3.  With the cache on, calls that pass the same z OBJECT (same tensor, unmodified, or
 # the same Python float) on the same grid reuse one transfer function instead of regenerating it (XL_REUSE_H).
-# Off by default: every entry pins xl_rs_transfer_bytes(N) of device memory (128 MiB at N = 2048).
+# Off by default: every entry pins xl_rs_transfer_bytes(N) of device memory (128 MiB at N = 2048; twice that when z needs a
+# gradient, because the reduced dH/dz is generated with H).  Memory model with the cache off: every RS / VRS autograd node
+# keeps its own H for its backward call (16 VRS nodes of the sharp-focus table at N = 1024: 16 x 32 MiB, x2 with d/dz).
+# Caveat: a tensor distance is keyed on (id(z), z._version) -- an update that bypasses the version counter (writing through
+# z.data) would reuse a stale transfer function; optimizers that update parameters in place (torch.optim) bump the version.
 import collections
 
 _transfer_cache = collections.OrderedDict()

@@ -241,7 +241,8 @@ def cylindrical_lens(input_field, focal_length, refractive_index=1.5, angle=0):
     """Plano-convex cylindrical lens rotated by `angle`; returns (light, lens mask).  optical_elements.py:705-744."""
     X = input_field.X.to(torch.float64)
     Y = input_field.Y.to(torch.float64)
-    Xrot = X * math.cos(angle) + Y * math.sin(angle)
+    ang = _real(angle, X, torch.float64)               # a tensor parameter keeps its gradient (the reference is differentiable in it)
+    Xrot = X * torch.cos(ang) + Y * torch.sin(ang)
     R = focal_length * (refractive_index - 1)
     thickness = R - torch.sqrt(R ** 2 - Xrot ** 2)
     phase = input_field.k * (refractive_index - 1) * (Xrot ** 2 / (2 * focal_length) + thickness)
@@ -253,7 +254,8 @@ def axicon_lens(input_field, alpha, n=1.5):
     X = input_field.X.to(torch.float64)
     Y = input_field.Y.to(torch.float64)
     r = torch.sqrt(X ** 2 + Y ** 2)
-    phase_shift = input_field.k * r * (n - 1) * math.sin(alpha) * math.tan(alpha)
+    al = _real(alpha, X, torch.float64)                # a tensor parameter keeps its gradient
+    phase_shift = input_field.k * r * (n - 1) * torch.sin(al) * torch.tan(al)
     return _apply_mask(input_field, _unit_phasor(-phase_shift))
 
 
