@@ -29,28 +29,56 @@ struct XlLongParams {
     double dx, dy, k;
     float hscale;
     int hrow0, hrows;       // h kernels: first global y row of this rank, rows per rank
+    unsigned chunk_magic;   // ceil(2^32 / chunk_rows): n / chunk_rows == umulhi(n, chunk_magic) for n, chunk_rows in [2, 65536)
 };
+XL_HD inline unsigned xl_div_magic(int d) { return (unsigned)((0x100000000ull + (unsigned long long)d - 1) / (unsigned long long)d); }
 
+// The first pass of every split kernel forms  y_q[i] = w_P^{i q} * sum_j x[i + L0 j] w_R^{j q}  from R (or R/2) strided global
+// loads per position.  Round 2 (profiles/long_probe_r02q.txt): written with `if (ok)` guards, selected 64-bit addresses, run-time
+// integer divisions and a twiddle-table lookup per (position, j), the loads of a thread came out of ptxas as ~100 dependent
+// groups behind branches (68-113 BSSY regions per kernel) and the kernels were bound by that serialised L2 latency:
+// long_rows_fwd 14.3 ms against 2.3 ms for long_rows_inv over the same 4.3 GB of spectra at 16384^2.  Now every address is a
+// masked offset (no select, no branch), out-of-range samples are zeroed by a select on the DATA, w_R^{j q} (CTA-uniform) is
+// hoisted into the functor, and n / chunk_rows is a multiply-high by a host-made reciprocal -- all loads of a thread's 16
+// positions are independent and issue back to back.
 // w_den^{num} = exp(-2 pi i num/den), den a power of two <= XL_TWN, num >= 0
 XL_DEV cf xl_tw_at(const cf* tw, int num, int den) { return xl_ldg(tw + (size_t)(num & (den - 1)) * (XL_TWN / den)); }
+struct XlLongWr { cf w[8]; };   // w_R^{j q}, j < 8 (entries >= R repeat w^0, never used with a non-zero operand)
+XL_DEV XlLongWr xl_long_wr(const XlLongParams& p, int q) {
+    XlLongWr r;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r.w[j] = xl_tw_at(p.tw, (j < p.R ? j : 0) * q, p.R);
+    return r;
+}
+// x where ok, 0 elsewhere (a select on the loaded DATA; the address was masked); cj = -1 conjugates
+XL_DEV cf xl_sel(bool ok, cf x, float cj = 1.f) { return make_float2(ok ? x.x : 0.f, ok ? x.y * cj : 0.f); }
+// element offset of row n of a column pair in the exchanged layout [source rank][pairs][chunk_rows][2]; cstride = elements
+// per source rank (chunk_rows == N on a single rank: offset n * 2)
+XL_DEV size_t xl_long_col_off(const XlLongParams& p, size_t cstride, int n) {
+    const unsigned c = xl_umulhi((unsigned)n, p.chunk_magic);
+    return (size_t)c * cstride + (size_t)(n - (int)c * p.chunk_rows) * XL_V;
+}
 
 // ------------------------------------------------------------------------------------------------ row kernels
 template <int L0> struct XlLongRowsFwdOp : XlOpBase {
-    const XlLongParams& p; int q, yb;
+    const XlLongParams& p; int q, yb; XlLongWr wr; float cj;   // cj: -1 conjugates the input (XL_F_CONJ_IN), +1 otherwise
     XL_DEV void load(int i, cf* v, int stride) const {
         const cf wiq = xl_tw_at(p.tw, i * q, p.P);
+        cf x[XL_V][4];
+        bool ok[XL_V][4];
 #pragma unroll
-        for (int l = 0; l < XL_V; ++l) {
-            const int y = yb + l;
-            cf acc = cf_zero();
+        for (int l = 0; l < XL_V; ++l)
 #pragma unroll
             for (int j = 0; j < 4; ++j) {          // x[n] = 0 for n >= N (N <= P/2): j < R/2 <= 4
                 const int n = i + L0 * j;
-                const bool ok = 2 * j < p.R && n < p.N && y < p.rows;
-                cf x = p.in[ok ? (size_t)y * p.N + n : 0];
-                if (p.flags & XL_F_CONJ_IN) x = cf_conj(x);
-                if (ok) acc = j == 0 ? x : cf_fma(x, xl_tw_at(p.tw, j * q, p.R), acc);
+                ok[l][j] = (2 * j < p.R) & (n < p.N) & (yb + l < p.rows);
+                x[l][j] = p.in[((long long)(yb + l) * p.N + n) & -(long long)ok[l][j]];
             }
+#pragma unroll
+        for (int l = 0; l < XL_V; ++l) {
+            cf acc = xl_sel(ok[l][0], x[l][0], cj);
+#pragma unroll
+            for (int j = 1; j < 4; ++j) acc = cf_fma(xl_sel(ok[l][j], x[l][j], cj), wr.w[j], acc);
             v[l * stride] = cf_mul(acc, wiq);
         }
     }
@@ -71,8 +99,8 @@ template <int L0> struct XlLongRowsFwd {
     XL_DEV static void run(const Params& p, cf* s) {
         cf* t = s + xl_tile_elems(L0, XL_V);
         XlFft<L0, XL_V>::init_tw(t, p.tw);
-        XlLongRowsFwdOp<L0> op{{}, p, XL_BLOCK_X, XL_BLOCK_Y * XL_V};   // sub-line q varies fastest: the R CTAs that re-read one
-                                                                         // row pair are neighbours in launch order (L2 hits)
+        // sub-line q varies fastest: the R CTAs that re-read one row pair are neighbours in launch order (L2 hits)
+        XlLongRowsFwdOp<L0> op{{}, p, XL_BLOCK_X, XL_BLOCK_Y * XL_V, xl_long_wr(p, XL_BLOCK_X), (p.flags & XL_F_CONJ_IN) ? -1.f : 1.f};
         XlFft<L0, XL_V>::forward(s, t, op);
     }
 };
@@ -126,15 +154,15 @@ struct XlLongRowsCombine {
                 const int y = (int)(idx / p.L0), i = (int)(idx % p.L0);
                 cf zq[8];
 #pragma unroll
-                for (int q = 0; q < 8; ++q) zq[q] = q < p.R ? p.scratch[((size_t)y * p.R + q) * p.L0 + i] : cf_zero();
+                for (int q = 0; q < 8; ++q)
+                    zq[q] = xl_sel(q < p.R, p.scratch[(((size_t)y * p.R + q) * p.L0 + i) & -(size_t)(q < p.R)]);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const int n = i + p.L0 * j;
                     if (2 * j >= p.R || n >= p.N) continue;
                     cf acc = zq[0];
 #pragma unroll
-                    for (int q = 1; q < 8; ++q)
-                        if (q < p.R) acc = cf_fma(zq[q], cf_conj(xl_tw_at(p.tw, j * q, p.R)), acc);
+                    for (int q = 1; q < 8; ++q) acc = cf_fma(zq[q], cf_conj(xl_tw_at(p.tw, j * q, p.R)), acc);   // zq[q >= R] == 0
                     if (p.flags & XL_F_CONJ_OUT) acc = cf_conj(acc);
                     p.out[(size_t)y * p.N + n] = acc;
                 }
@@ -144,47 +172,69 @@ struct XlLongRowsCombine {
 };
 
 // ------------------------------------------------------------------------------------------------ column kernels
-// rows of a column pair in the exchanged layout (chunk_rows == N on a single rank)
-XL_DEV cf* xl_long_col_row(const XlLongParams& p, cf* tile, int i) {
-    return tile + (size_t)(i / p.chunk_rows) * ((size_t)p.pairs * p.chunk_rows * XL_V) + (size_t)(i % p.chunk_rows) * XL_V;
-}
-template <int L0> struct XlLongColsOp : XlOpBase {
-    static constexpr int R1 = xl_first_radix(L0), S1 = L0 / R1;
-    const XlLongParams& p; int G, q; cf* tile; const cf* Ht;
-    XL_DEV void load(int i, cf* v, int stride) const {
-        cf a0 = cf_zero(), a1 = cf_zero();
+// Column kernels, three launches per stage:
+//   long_cols_split   (pointwise)  Y[G][q][i] = w_P^{i q} sum_{j < R/2} x[i + L0 j] w_R^{j q}      the radix-R DIF step, ONCE per
+//                                  position for all R sub-lines (scratch, [pairs][R][L0][2])
+//   long_cols         (FFT)        z_q = IDFT_L0( DFT_L0(Y_q) * H_q ), in place in the scratch block of (G, q)
+//   long_cols_combine (pointwise)  x[i + L0 j] = sum_q w_R^{-j q} w_P^{-i q} z_q[i]                  the radix-R DIT step
+// Until round 2 the DIF step was fused into the first pass of long_cols: every one of the R CTAs of a column pair re-read the
+// R/2 input blocks and spent as many instructions on addresses, selects and twiddles as on its convolution (14.4 ms for
+// long_cols at 16384^2 against 5.9 ms of convolutions at the rate of rs_cols; profiles/long_probe_r02r.txt).  The split pass
+// costs one more write + read of the column tile (contiguous, 16-byte coalesced) and leaves a plain convolution kernel.
+struct XlLongColsSplit {
+    static const char* name() { return "long_cols_split"; }
+    typedef XlLongParams Params;
+    static constexpr int NT = 256;
+    static size_t smem() { return 0; }
+    XL_DEV static void run(const Params& p, cf*) {
+        const int G = XL_BLOCK_Y;
+        const cf* tile = p.spec + (size_t)G * p.chunk_rows * XL_V;
+        const size_t cstride = (size_t)p.pairs * p.chunk_rows * XL_V;
+        XL_THREADS(tid, NT) {
+            const int i = XL_BLOCK_X * NT + tid;
+            if (i < p.L0) {
+                cf x0[4], x1[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {              // rows >= N are zero padding: j < R/2
-            const int n = i + L0 * j;
-            const bool ok = 2 * j < p.R && n < p.N;
-            cf x0, x1;
-            xl_ld4(xl_long_col_row(p, tile, ok ? n : 0), &x0, &x1);
-            if (ok) {
-                if (j == 0) { a0 = x0; a1 = x1; }
-                else { const cf w = xl_tw_at(p.tw, j * q, p.R); a0 = cf_fma(x0, w, a0); a1 = cf_fma(x1, w, a1); }
+                for (int j = 0; j < 4; ++j) {              // rows >= N are zero padding: j < R/2
+                    const int n = i + p.L0 * j;
+                    const bool ok = (2 * j < p.R) & (n < p.N);
+                    xl_ld4(tile + (xl_long_col_off(p, cstride, n) & -(size_t)ok), &x0[j], &x1[j]);
+                    x0[j] = xl_sel(ok, x0[j]); x1[j] = xl_sel(ok, x1[j]);
+                }
+                cf* Y = p.scratch + ((size_t)G * p.R * p.L0 + i) * XL_V;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    if (q >= p.R) break;
+                    cf a0 = x0[0], a1 = x1[0];
+#pragma unroll
+                    for (int j = 1; j < 4; ++j) {
+                        const cf w = xl_tw_at(p.tw, j * q, p.R);
+                        a0 = cf_fma(x0[j], w, a0); a1 = cf_fma(x1[j], w, a1);
+                    }
+                    const cf wiq = xl_tw_at(p.tw, i * q, p.P);
+                    xl_st4(Y + (size_t)q * p.L0 * XL_V, cf_mul(a0, wiq), cf_mul(a1, wiq));
+                }
             }
         }
-        const cf wiq = xl_tw_at(p.tw, i * q, p.P);
-        v[0] = cf_mul(a0, wiq);
-        v[stride] = cf_mul(a1, wiq);
     }
+};
+template <int L0> struct XlLongColsOp : XlOpBase {
+    static constexpr int R1 = xl_first_radix(L0), S1 = L0 / R1;
+    cf* Yq; const cf* Hq;     // this CTA's block of the scratch buffer (in place) and of the transfer-function slab
+    XL_DEV void load(int i, cf* v, int stride) const { xl_ld4(Yq + (size_t)i * XL_V, v, v + stride); }
     XL_DEV void spec(int beta, cf* v) const {
 #pragma unroll
         for (int qq = 0; qq < 16; ++qq) {
             cf h0, h1;
-            xl_ldg4(Ht + (size_t)(q * L0 + qq * (L0 / 16) + beta) * XL_V, &h0, &h1);
+            xl_ldg4(Hq + (size_t)(qq * (L0 / 16) + beta) * XL_V, &h0, &h1);
             v[qq] = cf_mul(v[qq], h0);
             v[16 + qq] = cf_mul(v[16 + qq], h1);
         }
     }
+    // in place: every load() of the CTA happened before the first barrier of the transform
     XL_DEV void store_vec(int n, const cf* v) const {
-        cf* zc = p.scratch + ((size_t)G * p.R + q) * L0 * XL_V;
 #pragma unroll
-        for (int j = 0; j < R1; ++j) {
-            const int i = n + S1 * j;
-            const cf w = cf_conj(xl_tw_at(p.tw, i * q, p.P));
-            xl_st4(zc + (size_t)i * XL_V, cf_mul(v[j], w), cf_mul(v[R1 + j], w));
-        }
+        for (int j = 0; j < R1; ++j) xl_st4(Yq + (size_t)(n + S1 * j) * XL_V, v[j], v[R1 + j]);
     }
 };
 template <int L0> struct XlLongCols {
@@ -194,13 +244,17 @@ template <int L0> struct XlLongCols {
     static size_t smem() { return xl_smem_bytes(L0, XL_V); }
     XL_DEV static void run(const Params& p, cf* s) {
         cf* t = s + xl_tile_elems(L0, XL_V);
-        XlFft<L0, XL_V>::init_tw(t, p.tw);
-        const int G = XL_BLOCK_Y;   // sub-line on blockIdx.x: the R CTAs of one column pair run back to back
-        XlLongColsOp<L0> op{{}, p, G, XL_BLOCK_X, p.spec + (size_t)G * p.chunk_rows * XL_V, p.H + (size_t)G * p.P * XL_V};
-        XlFft<L0, XL_V>::conv(s, t, op);
+        const size_t blk = ((size_t)XL_BLOCK_Y * p.R + XL_BLOCK_X) * L0 * XL_V;   // (pair G = blockIdx.y, sub-line q = blockIdx.x)
+        XlLongColsOp<L0> op{{}, p.scratch + blk, p.H + blk};
+        XL_THREADS(tid, NT) {      // the transfer-function block is needed in the spectrum phase: ask L2 for it now
+            constexpr unsigned BYTES = L0 * XL_V * sizeof(cf), CH = BYTES < 32768 ? BYTES : 32768;
+            if (tid == 0)
+                for (unsigned o = 0; o < BYTES; o += CH) xl_prefetch_l2_bulk((const char*)(p.H + blk) + o, CH);
+        }
+        XlFft<L0, XL_V>::conv_g(s, t, p.tw, op);
     }
 };
-// column tile rows i + L0 j (< N)  <-  sum_q w_R^{-j q} z_q[i]
+// column tile rows i + L0 j (< N)  <-  sum_q w_R^{-j q} w_P^{-i q} z_q[i]
 struct XlLongColsCombine {
     static const char* name() { return "long_cols_combine"; }
     typedef XlLongParams Params;
@@ -214,19 +268,22 @@ struct XlLongColsCombine {
                 cf z0[8], z1[8];
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
-                    z0[q] = cf_zero(); z1[q] = cf_zero();
-                    if (q < p.R) xl_ld4(p.scratch + (((size_t)G * p.R + q) * p.L0 + i) * XL_V, &z0[q], &z1[q]);
+                    xl_ld4(p.scratch + (((((size_t)G * p.R + q) * p.L0 + i) * XL_V) & -(size_t)(q < p.R)), &z0[q], &z1[q]);
+                    const cf w = cf_conj(xl_tw_at(p.tw, i * q, p.P));      // w_P^{-i q} (long_cols stores the bare IDFT)
+                    z0[q] = xl_sel(q < p.R, cf_mul(z0[q], w)); z1[q] = xl_sel(q < p.R, cf_mul(z1[q], w));
                 }
                 cf* tile = p.spec + (size_t)G * p.chunk_rows * XL_V;
+                const size_t cstride = (size_t)p.pairs * p.chunk_rows * XL_V;
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const int n = i + p.L0 * j;
                     if (2 * j >= p.R || n >= p.N) continue;
                     cf a0 = z0[0], a1 = z1[0];
 #pragma unroll
-                    for (int q = 1; q < 8; ++q)
-                        if (q < p.R) { const cf w = cf_conj(xl_tw_at(p.tw, j * q, p.R)); a0 = cf_fma(z0[q], w, a0); a1 = cf_fma(z1[q], w, a1); }
-                    xl_st4(xl_long_col_row(p, tile, n), a0, a1);
+                    for (int q = 1; q < 8; ++q) {   // z[q >= R] == 0
+                        const cf w = cf_conj(xl_tw_at(p.tw, j * q, p.R)); a0 = cf_fma(z0[q], w, a0); a1 = cf_fma(z1[q], w, a1);
+                    }
+                    xl_st4(tile + xl_long_col_off(p, cstride, n), a0, a1);
                 }
             }
         }
@@ -254,35 +311,47 @@ struct XlHEval {
 };
 // row spectra of the impulse response: all R input blocks are populated (the wrapped kernel fills the whole line)
 template <int L0> struct XlLongHRowsOp : XlOpBase {
-    const XlLongParams& p; int q, yb;
+    const XlLongParams& p; int q, yb; XlLongWr wr; int mq;   // mq: the sub-line that mirrors q (== q: none), see XlLongHRows
     XL_DEV void load(int i, cf* v, int stride) const {
         const int W = p.P / 2 + 1;
         const cf wiq = xl_tw_at(p.tw, i * q, p.P);
+        cf x[XL_V][8];
 #pragma unroll
-        for (int l = 0; l < XL_V; ++l) {
-            const int yl = yb + l;
-            const bool rowok = yl < p.hrows;
-            cf acc = cf_zero();
+        for (int l = 0; l < XL_V; ++l)
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const int n = i + L0 * j;
-                const bool ok = j < p.R && rowok;
+                const bool ok = (j < p.R) & (yb + l < p.hrows);
                 const int xi = n <= p.P / 2 ? n : p.P - n;
-                const cf x = p.scratch[ok ? (size_t)yl * W + xi : 0];
-                if (ok) acc = j == 0 ? x : cf_fma(x, xl_tw_at(p.tw, j * q, p.R), acc);
+                x[l][j] = xl_sel(ok, p.scratch[((size_t)(yb + l) * W + xi) & -(size_t)ok]);
             }
+#pragma unroll
+        for (int l = 0; l < XL_V; ++l) {
+            cf acc = x[l][0];
+#pragma unroll
+            for (int j = 1; j < 8; ++j) acc = cf_fma(x[l][j], wr.w[j], acc);
             v[l * stride] = cf_mul(acc, wiq);
         }
     }
     XL_DEV void spec(int beta, const cf* v) const {
 #pragma unroll
         for (int qq = 0; qq < 16; ++qq) {
-            const int g = q * L0 + qq * (L0 / 16) + beta;
+            const int slot = qq * (L0 / 16) + beta, g = q * L0 + slot;
             xl_blocked_store2<xl_lane_mask(L0)>(p.spec + (size_t)(g / 2) * p.hrows * 2, yb, p.hrows, g, v[qq], v[16 + qq]);
+            if (mq != q) {   // CTA-uniform
+                const int gm = mq * L0 + (L0 - 1 - slot);   // the two lanes of a pair still hold the two slots of one pair
+                xl_blocked_store2<xl_lane_mask(L0)>(p.spec + (size_t)(gm / 2) * p.hrows * 2, yb, p.hrows, gm, v[qq], v[16 + qq]);
+            }
         }
     }
     XL_DEV void store_vec(int, const cf*) const {}
 };
+// The impulse response is even in x (and in y): x[n] == x[P - n], so its spectrum is even too, X[b] == X[P - b].  Sub-line q
+// holds the bins q + R k and sub-line R - q the bins (R - q) + R k' == P - (q + R k) for k' = L0 - 1 - k; the slot map is a
+// digit permutation, so slot(L0 - 1 - k) == L0 - 1 - slot(k): sub-line R - q is sub-line q in reverse slot order.  The CTAs
+// of the sub-lines 0 < q < R/2 therefore store their spectrum twice and those of q > R/2 exit at once (3/8 of the transforms
+// of both transfer-function kernels at R = 8).
+XL_DEV int xl_long_mirror(int q, int R) { return (q > 0 && 2 * q < R) ? R - q : q; }
 template <int L0> struct XlLongHRows {
     static const char* name() { return "long_h_rows"; }
     typedef XlLongParams Params;
@@ -290,37 +359,65 @@ template <int L0> struct XlLongHRows {
     static size_t smem() { return xl_smem_bytes(L0, XL_V); }
     XL_DEV static void run(const Params& p, cf* s) {
         cf* t = s + xl_tile_elems(L0, XL_V);
+        if (2 * XL_BLOCK_X > p.R) return;   // CTA-uniform: written by the CTA of the mirror sub-line
         XlFft<L0, XL_V>::init_tw(t, p.tw);
-        XlLongHRowsOp<L0> op{{}, p, XL_BLOCK_X, XL_BLOCK_Y * XL_V};
+        XlLongHRowsOp<L0> op{{}, p, XL_BLOCK_X, XL_BLOCK_Y * XL_V, xl_long_wr(p, XL_BLOCK_X), xl_long_mirror(XL_BLOCK_X, p.R)};
         XlFft<L0, XL_V>::forward(s, t, op);
     }
 };
-// column spectra of the impulse-response row spectra (even in y: row P - y == row y), exchanged layout in, H slab out
-template <int L0> struct XlLongHColsOp : XlOpBase {
-    const XlLongParams& p; int q; const cf* src; cf* Ht;
-    XL_DEV void load(int i, cf* v, int stride) const {
-        cf a0 = cf_zero(), a1 = cf_zero();
+// column spectra of the impulse-response row spectra (even in y: row P - y == row y), exchanged layout in, H slab out.
+// Two launches, as for the field: long_h_split writes the radix-R DIF step of every needed sub-line (q <= R/2, the others are
+// mirrors) into the block of the transfer-function slab where that sub-line's spectrum will live, long_h_cols transforms the
+// blocks in place.
+struct XlLongHSplit {
+    static const char* name() { return "long_h_split"; }
+    typedef XlLongParams Params;
+    static constexpr int NT = 256;
+    static size_t smem() { return 0; }
+    XL_DEV static void run(const Params& p, cf*) {
+        const int G = XL_BLOCK_Y;
+        const cf* src = p.spec + (size_t)G * p.chunk_rows * XL_V;
+        const size_t cstride = (size_t)p.pairs * p.chunk_rows * XL_V;
+        XL_THREADS(tid, NT) {
+            const int i = XL_BLOCK_X * NT + tid;
+            if (i < p.L0) {
+                cf x0[8], x1[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int n = i + L0 * j;
-            const bool ok = j < p.R;
-            const int r = n <= p.P / 2 ? n : p.P - n;
-            cf x0, x1;
-            xl_ld4(src + (size_t)((ok ? r : 0) / p.chunk_rows) * ((size_t)p.pairs * p.chunk_rows * XL_V) +
-                       (size_t)((ok ? r : 0) % p.chunk_rows) * XL_V, &x0, &x1);
-            if (ok) {
-                if (j == 0) { a0 = x0; a1 = x1; }
-                else { const cf w = xl_tw_at(p.tw, j * q, p.R); a0 = cf_fma(x0, w, a0); a1 = cf_fma(x1, w, a1); }
+                for (int j = 0; j < 8; ++j) {
+                    const int n = i + p.L0 * j;
+                    const bool ok = j < p.R;
+                    const int r = n <= p.P / 2 ? n : p.P - n;
+                    xl_ld4(src + (xl_long_col_off(p, cstride, r) & -(size_t)ok), &x0[j], &x1[j]);
+                    x0[j] = xl_sel(ok, x0[j]); x1[j] = xl_sel(ok, x1[j]);
+                }
+                cf* Y = p.H + ((size_t)G * p.P + i) * XL_V;
+#pragma unroll
+                for (int q = 0; q <= 4; ++q) {
+                    if (2 * q > p.R) break;
+                    cf a0 = x0[0], a1 = x1[0];
+#pragma unroll
+                    for (int j = 1; j < 8; ++j) {          // x[j >= R] == 0
+                        const cf w = xl_tw_at(p.tw, j * q, p.R);
+                        a0 = cf_fma(x0[j], w, a0); a1 = cf_fma(x1[j], w, a1);
+                    }
+                    const cf wiq = xl_tw_at(p.tw, i * q, p.P);
+                    xl_st4(Y + (size_t)q * p.L0 * XL_V, cf_mul(a0, wiq), cf_mul(a1, wiq));
+                }
             }
         }
-        const cf wiq = xl_tw_at(p.tw, i * q, p.P);
-        v[0] = cf_mul(a0, wiq);
-        v[stride] = cf_mul(a1, wiq);
     }
+};
+template <int L0> struct XlLongHColsOp : XlOpBase {
+    cf* Hq; cf* Hm; float hscale;     // this sub-line's block (in place) and the block of its mirror sub-line (null: none)
+    XL_DEV void load(int i, cf* v, int stride) const { xl_ld4(Hq + (size_t)i * XL_V, v, v + stride); }
     XL_DEV void spec(int beta, const cf* v) const {
 #pragma unroll
-        for (int qq = 0; qq < 16; ++qq)
-            xl_st4(Ht + (size_t)(q * L0 + qq * (L0 / 16) + beta) * XL_V, cf_scale(v[qq], p.hscale), cf_scale(v[16 + qq], p.hscale));
+        for (int qq = 0; qq < 16; ++qq) {
+            const int slot = qq * (L0 / 16) + beta;
+            const cf a = cf_scale(v[qq], hscale), b = cf_scale(v[16 + qq], hscale);
+            xl_st4(Hq + (size_t)slot * XL_V, a, b);
+            if (Hm) xl_st4(Hm + (size_t)(L0 - 1 - slot) * XL_V, a, b);   // CTA-uniform (XlLongHRows)
+        }
     }
     XL_DEV void store_vec(int, const cf*) const {}
 };
@@ -330,10 +427,12 @@ template <int L0> struct XlLongHCols {
     static constexpr int NT = xl_threads(L0);
     static size_t smem() { return xl_smem_bytes(L0, XL_V); }
     XL_DEV static void run(const Params& p, cf* s) {
+        const int q = XL_BLOCK_X, mq = xl_long_mirror(q, p.R);
+        if (2 * q > p.R) return;   // CTA-uniform: written by the CTA of the mirror sub-line (even in y)
         cf* t = s + xl_tile_elems(L0, XL_V);
-        XlFft<L0, XL_V>::init_tw(t, p.tw);
-        const int G = XL_BLOCK_Y;
-        XlLongHColsOp<L0> op{{}, p, XL_BLOCK_X, p.spec + (size_t)G * p.chunk_rows * XL_V, p.H + (size_t)G * p.P * XL_V};
-        XlFft<L0, XL_V>::forward(s, t, op);
+        cf* Hg = p.H + (size_t)XL_BLOCK_Y * p.P * XL_V;
+        XlLongHColsOp<L0> op{{}, Hg + (size_t)q * L0 * XL_V, mq != q ? Hg + (size_t)mq * L0 * XL_V : (cf*)0, p.hscale};
+        // the in-place update is safe: every load of the first pass happens before the barrier that precedes the stores
+        XlFft<L0, XL_V>::forward_g(s, t, p.tw, op);
     }
 };

@@ -53,6 +53,7 @@ static inline void xl_cp_async16(float2* dst, const float2* src) { dst[0] = src[
 static inline void xl_cp_async_wait() {}
 static inline void xl_nanosleep(unsigned) {}
 static inline float xl_rcpf(float x) { return 1.0f / x; }
+static inline unsigned xl_umulhi(unsigned a, unsigned b) { return (unsigned)(((unsigned long long)a * b) >> 32); }
 #else
 #include <cuda_runtime.h>
 #define XL_DEV __device__ __forceinline__
@@ -91,6 +92,7 @@ XL_DEV void xl_cp_async16(float2* dst, const float2* src) {   // 16-byte aligned
 XL_DEV void xl_cp_async_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 XL_DEV void xl_nanosleep(unsigned ns) { __nanosleep(ns); }
 XL_DEV float xl_rcpf(float x) { return __fdividef(1.0f, x); }   // approximate reciprocal (2 ulp), branch-free
+XL_DEV unsigned xl_umulhi(unsigned a, unsigned b) { return __umulhi(a, b); }
 // exchange one complex value with the neighbouring lane (lane ^ 1).  MASK = the lanes that execute the call, a compile-time
 // constant (xl_lane_mask(L): the butterfly loops of XlFft<L> run lanes [0, min(32, L/16)) of every warp).  A run-time
 // __activemask() here makes the compiler fence every exchange (VOTE + BRA.DIV) and serialise the loads around it.

@@ -54,10 +54,12 @@ static int long_params(XlLongParams& q, const SlabGeo& g, int N, double dx, doub
     q.N = N; q.P = g.P; q.R = g.R; q.L0 = g.L0; q.rows = g.rows; q.chunk_rows = g.rows; q.pairs = g.pairs;
     q.dx = dx; q.dy = dy; q.k = k;
     q.hscale = (float)(dx * dy / ((double)g.P * (double)g.P));
+    q.chunk_magic = xl_div_magic(q.chunk_rows);
     q.tw = xl_twiddles();
     if (!q.tw) return xl_fail(XL_E_CUDA, "twiddle table allocation failed%s", "");
     return XL_OK;
 }
+static void long_set_chunk(XlLongParams& q, int chunk_rows) { q.chunk_rows = chunk_rows; q.chunk_magic = xl_div_magic(chunk_rows); }
 
 // row spectra of this rank's y rows [rank*hrows, (rank+1)*hrows) of the impulse response: R[P/2][hrows][2]
 extern "C" int xl_slab_h_rows(void* Rb, const double* z, int N, int G, int rank, double dx, double dy, double k,
@@ -102,8 +104,10 @@ extern "C" int xl_slab_h_cols(const void* Th, void* Hloc, int N, int G, double d
     }
     XlLongParams q;
     if ((rc = long_params(q, g, N, dx, dy, 0.0))) return rc;
-    q.spec = (cf*)Th; q.H = (cf*)Hloc; q.chunk_rows = g.hrows;
-    XL_FOR_L0(g.L0, rc = xl_launch<XlLongHCols<XL>>(XlDim{g.R, g.pairs}, st, q));
+    q.spec = (cf*)Th; q.H = (cf*)Hloc; long_set_chunk(q, g.hrows);
+    rc = xl_launch<XlLongHSplit>(XlDim{pointwise_grid((size_t)g.L0, XlLongHSplit::NT), g.pairs}, st, q);
+    if (rc) return rc;
+    XL_FOR_L0(g.L0, rc = xl_launch<XlLongHCols<XL>>(XlDim{g.R / 2 + 1, g.pairs}, st, q));
     return rc;
 }
 // this rank's field rows in_local[rows][N]  ->  row spectra S[P/2][rows][2]
@@ -146,6 +150,8 @@ extern "C" int xl_slab_cols(void* T, const void* Hloc, int N, int G, void* scrat
     XlLongParams q;
     if ((rc = long_params(q, g, N, 1.0, 1.0, 0.0))) return rc;
     q.spec = (cf*)T; q.H = (cf*)Hloc; q.scratch = (cf*)scratch;
+    rc = xl_launch<XlLongColsSplit>(XlDim{pointwise_grid((size_t)g.L0, XlLongColsSplit::NT), g.pairs}, st, q);
+    if (rc) return rc;
     XL_FOR_L0(g.L0, rc = xl_launch<XlLongCols<XL>>(XlDim{g.R, g.pairs}, st, q));
     if (rc) return rc;
     return xl_launch<XlLongColsCombine>(XlDim{pointwise_grid((size_t)g.pairs * g.L0, XlLongColsCombine::NT), 1}, st, q);
