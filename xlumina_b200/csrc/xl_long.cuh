@@ -22,8 +22,8 @@ struct XlLongParams {
     int flags;
     const cf* in; cf* out;  // field rows [rows][N]
     cf* spec;               // row side: [P/2][rows][2]; column side: exchanged layout
-    cf* H;                  // transfer-function slab [pairs][P][2]  (h kernels: destination)
-    cf* scratch;            // z_q parking: rows [rows][R][L0], columns [pairs][R][L0][2]; h_eval: plane [hrows][P/2+1]
+    cf* H;                  // transfer-function slab [pairs][P][2], of which the sub-line blocks q <= R/2 are written / read
+    cf* scratch;            // z_q parking: rows [rows][R][L0], columns [pairs][R][L0][2]; h_eval: Y[hrows][R/2+1][L0]
     const cf* tw;           // master table tw[k] = exp(-2 pi i k / XL_TWN)
     const double* z;
     double dx, dy, k;
@@ -220,13 +220,14 @@ struct XlLongColsSplit {
 };
 template <int L0> struct XlLongColsOp : XlOpBase {
     static constexpr int R1 = xl_first_radix(L0), S1 = L0 / R1;
-    cf* Yq; const cf* Hq;     // this CTA's block of the scratch buffer (in place) and of the transfer-function slab
+    cf* Yq; const cf* Hq; int rev;   // this CTA's block of the scratch buffer (in place); the transfer-function block of this
+                                      // sub-line, or (rev = L0 - 1) of its mirror sub-line, read in reverse slot order
     XL_DEV void load(int i, cf* v, int stride) const { xl_ld4(Yq + (size_t)i * XL_V, v, v + stride); }
     XL_DEV void spec(int beta, cf* v) const {
 #pragma unroll
         for (int qq = 0; qq < 16; ++qq) {
             cf h0, h1;
-            xl_ldg4(Hq + (size_t)(qq * (L0 / 16) + beta) * XL_V, &h0, &h1);
+            xl_ldg4(Hq + (size_t)((qq * (L0 / 16) + beta) ^ rev) * XL_V, &h0, &h1);   // L0 - 1 - slot == slot ^ (L0 - 1)
             v[qq] = cf_mul(v[qq], h0);
             v[16 + qq] = cf_mul(v[16 + qq], h1);
         }
@@ -244,12 +245,17 @@ template <int L0> struct XlLongCols {
     static size_t smem() { return xl_smem_bytes(L0, XL_V); }
     XL_DEV static void run(const Params& p, cf* s) {
         cf* t = s + xl_tile_elems(L0, XL_V);
-        const size_t blk = ((size_t)XL_BLOCK_Y * p.R + XL_BLOCK_X) * L0 * XL_V;   // (pair G = blockIdx.y, sub-line q = blockIdx.x)
-        XlLongColsOp<L0> op{{}, p.scratch + blk, p.H + blk};
+        const int q = XL_BLOCK_X;                                                   // (pair G = blockIdx.y, sub-line q = blockIdx.x)
+        const size_t blk = ((size_t)XL_BLOCK_Y * p.R + q) * L0 * XL_V;
+        // the transfer function is even in y: the slab holds the sub-lines q <= R/2 only, sub-line R - q is sub-line q in
+        // reverse slot order (XlLongHRows); the two CTAs run side by side and share the block in L2
+        const bool mir = 2 * q > p.R;
+        const cf* Hq = p.H + ((size_t)XL_BLOCK_Y * p.R + (mir ? p.R - q : q)) * L0 * XL_V;
+        XlLongColsOp<L0> op{{}, p.scratch + blk, Hq, mir ? L0 - 1 : 0};
         XL_THREADS(tid, NT) {      // the transfer-function block is needed in the spectrum phase: ask L2 for it now
             constexpr unsigned BYTES = L0 * XL_V * sizeof(cf), CH = BYTES < 32768 ? BYTES : 32768;
             if (tid == 0)
-                for (unsigned o = 0; o < BYTES; o += CH) xl_prefetch_l2_bulk((const char*)(p.H + blk) + o, CH);
+                for (unsigned o = 0; o < BYTES; o += CH) xl_prefetch_l2_bulk((const char*)Hq + o, CH);
         }
         XlFft<L0, XL_V>::conv_g(s, t, p.tw, op);
     }
@@ -291,47 +297,82 @@ struct XlLongColsCombine {
 };
 
 // ------------------------------------------------------------------------------------------------ transfer function
-// samples of the impulse response on this rank's y rows, x in [0, P/2] (h is even in x): plane[hrows][P/2+1]
+// h_eval: the impulse response of this rank's y rows AND the radix-R DIF step of their row transforms in one pointwise pass:
+//     Y[y][q][i] = w_P^{i q} sum_{j < R} x_y[i + L0 j] w_R^{j q},   x_y[n] = h(min(n, P - n) dx, y dy)   (h is even in x),
+// for the sub-lines q <= R/2 (the others are mirrors, XlLongHRows).  Positions i = t and i = L0 - t need the SAME R samples --
+// |x| = t + L0 j (j < R/2) and |x| = L0 j - t (1 <= j <= R/2) -- so one thread serves both and every sample is evaluated
+// exactly once.  (Until round 2: a plane of samples written by h_eval and re-read R times by the R sub-line CTAs of
+// long_h_rows, 256 strided loads per thread; 1.3 + 3.7 ms at 16384^2.)   scratch: Y[hrows][R/2 + 1][L0]
 struct XlHEval {
     static const char* name() { return "h_eval"; }
     typedef XlLongParams Params;
     static constexpr int NT = 256;
     static size_t smem() { return 0; }
+    XL_DEV static cf pick(const cf* a, int k) {      // a[k], k in [0, 5), without a run-time register index
+        cf r = a[0];
+#pragma unroll
+        for (int m = 1; m < 5; ++m) r = k == m ? a[m] : r;
+        return r;
+    }
+    XL_DEV static void emit(const Params& p, cf* Yrow, int i, const cf* x) {   // x[j] = x_y[i + L0 j], j < R (0 beyond)
+#pragma unroll
+        for (int q = 0; q <= 4; ++q) {
+            if (2 * q > p.R) break;
+            cf acc = x[0];
+#pragma unroll
+            for (int j = 1; j < 8; ++j) acc = cf_fma(x[j], xl_tw_at(p.tw, (j < p.R ? j : 0) * q, p.R), acc);
+            Yrow[(size_t)q * p.L0 + i] = cf_mul(acc, xl_tw_at(p.tw, i * q, p.P));
+        }
+    }
     XL_DEV static void run(const Params& p, cf*) {
         const XlRsHConst hc = xl_rs_hconst(xl_ldg(p.z), p.k);
-        const int W = p.P / 2 + 1;
+        const int half = p.R / 2, yl = XL_BLOCK_Y, y = p.hrow0 + yl;
+        const bool row = y <= p.P / 2;            // the rows beyond P/2 only pad the row count to an even number
+        cf* Yrow = p.scratch + (size_t)yl * (half + 1) * p.L0;
         XL_THREADS(tid, NT) {
-            const size_t idx = (size_t)XL_BLOCK_X * NT + tid;
-            if (idx < (size_t)p.hrows * W) {
-                const int yl = (int)(idx / W), xi = (int)(idx % W), y = p.hrow0 + yl;
-                p.scratch[idx] = y <= p.P / 2 ? xl_rs_h(xi * p.dx, y * p.dy, hc, 0) : cf_zero();
+            const int t = XL_BLOCK_X * NT + tid;
+            if (t <= p.L0 / 2) {
+                cf A[5], B[5];
+#pragma unroll
+                for (int j = 0; j <= 4; ++j) {
+                    A[j] = cf_zero(); B[j] = cf_zero();
+                    if (row && (j < half || (j == half && t == 0))) A[j] = xl_rs_h((t + p.L0 * j) * p.dx, y * p.dy, hc, 0);
+                    if (row && j >= 1 && j <= half && t > 0) B[j] = xl_rs_h((p.L0 * j - t) * p.dx, y * p.dy, hc, 0);
+                }
+                if (t == 0) {                     // |x| = L0 j - 0 is the sample A[j]
+#pragma unroll
+                    for (int j = 1; j <= 4; ++j) B[j] = A[j];
+                }
+                cf x[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {     // position t:  n = t + L0 j,  mirrored beyond P/2
+                    x[j] = cf_zero();
+                    if (j < half) x[j] = A[j < 5 ? j : 0];
+                    else if (j == half) x[j] = B[j < 5 ? j : 0];       // t == 0: B == A
+                    else if (j < p.R) x[j] = pick(B, p.R - j);
+                }
+                emit(p, Yrow, t, x);
+                if (t > 0 && 2 * t < p.L0) {      // position L0 - t:  n = L0 (j + 1) - t
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        x[j] = cf_zero();
+                        if (j + 1 <= half) x[j] = B[(j + 1) < 5 ? (j + 1) : 0];
+                        else if (j < p.R) x[j] = pick(A, p.R - j - 1);
+                    }
+                    emit(p, Yrow, p.L0 - t, x);
+                }
             }
         }
     }
 };
-// row spectra of the impulse response: all R input blocks are populated (the wrapped kernel fills the whole line)
+// row spectra of the impulse response from the blocks h_eval wrote
 template <int L0> struct XlLongHRowsOp : XlOpBase {
-    const XlLongParams& p; int q, yb; XlLongWr wr; int mq;   // mq: the sub-line that mirrors q (== q: none), see XlLongHRows
+    const XlLongParams& p; int q, yb; int mq;   // mq: the sub-line that mirrors q (== q: none), see XlLongHRows
     XL_DEV void load(int i, cf* v, int stride) const {
-        const int W = p.P / 2 + 1;
-        const cf wiq = xl_tw_at(p.tw, i * q, p.P);
-        cf x[XL_V][8];
+        const size_t rs = (size_t)(p.R / 2 + 1) * L0;          // elements per row of Y (hrows is even: both rows exist)
+        const cf* y0 = p.scratch + ((size_t)yb * (p.R / 2 + 1) + q) * L0 + i;
 #pragma unroll
-        for (int l = 0; l < XL_V; ++l)
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int n = i + L0 * j;
-                const bool ok = (j < p.R) & (yb + l < p.hrows);
-                const int xi = n <= p.P / 2 ? n : p.P - n;
-                x[l][j] = xl_sel(ok, p.scratch[((size_t)(yb + l) * W + xi) & -(size_t)ok]);
-            }
-#pragma unroll
-        for (int l = 0; l < XL_V; ++l) {
-            cf acc = x[l][0];
-#pragma unroll
-            for (int j = 1; j < 8; ++j) acc = cf_fma(x[l][j], wr.w[j], acc);
-            v[l * stride] = cf_mul(acc, wiq);
-        }
+        for (int l = 0; l < XL_V; ++l) v[l * stride] = y0[l * rs];
     }
     XL_DEV void spec(int beta, const cf* v) const {
 #pragma unroll
@@ -360,9 +401,8 @@ template <int L0> struct XlLongHRows {
     XL_DEV static void run(const Params& p, cf* s) {
         cf* t = s + xl_tile_elems(L0, XL_V);
         if (2 * XL_BLOCK_X > p.R) return;   // CTA-uniform: written by the CTA of the mirror sub-line
-        XlFft<L0, XL_V>::init_tw(t, p.tw);
-        XlLongHRowsOp<L0> op{{}, p, XL_BLOCK_X, XL_BLOCK_Y * XL_V, xl_long_wr(p, XL_BLOCK_X), xl_long_mirror(XL_BLOCK_X, p.R)};
-        XlFft<L0, XL_V>::forward(s, t, op);
+        XlLongHRowsOp<L0> op{{}, p, XL_BLOCK_X, XL_BLOCK_Y * XL_V, xl_long_mirror(XL_BLOCK_X, p.R)};
+        XlFft<L0, XL_V>::forward_g(s, t, p.tw, op);
     }
 };
 // column spectra of the impulse-response row spectra (even in y: row P - y == row y), exchanged layout in, H slab out.
@@ -408,15 +448,12 @@ struct XlLongHSplit {
     }
 };
 template <int L0> struct XlLongHColsOp : XlOpBase {
-    cf* Hq; cf* Hm; float hscale;     // this sub-line's block (in place) and the block of its mirror sub-line (null: none)
+    cf* Hq; float hscale;     // this sub-line's block (in place); the mirror sub-lines are never stored (XlLongCols reads q reversed)
     XL_DEV void load(int i, cf* v, int stride) const { xl_ld4(Hq + (size_t)i * XL_V, v, v + stride); }
     XL_DEV void spec(int beta, const cf* v) const {
 #pragma unroll
         for (int qq = 0; qq < 16; ++qq) {
-            const int slot = qq * (L0 / 16) + beta;
-            const cf a = cf_scale(v[qq], hscale), b = cf_scale(v[16 + qq], hscale);
-            xl_st4(Hq + (size_t)slot * XL_V, a, b);
-            if (Hm) xl_st4(Hm + (size_t)(L0 - 1 - slot) * XL_V, a, b);   // CTA-uniform (XlLongHRows)
+            xl_st4(Hq + (size_t)(qq * (L0 / 16) + beta) * XL_V, cf_scale(v[qq], hscale), cf_scale(v[16 + qq], hscale));
         }
     }
     XL_DEV void store_vec(int, const cf*) const {}
@@ -427,11 +464,9 @@ template <int L0> struct XlLongHCols {
     static constexpr int NT = xl_threads(L0);
     static size_t smem() { return xl_smem_bytes(L0, XL_V); }
     XL_DEV static void run(const Params& p, cf* s) {
-        const int q = XL_BLOCK_X, mq = xl_long_mirror(q, p.R);
-        if (2 * q > p.R) return;   // CTA-uniform: written by the CTA of the mirror sub-line (even in y)
+        const int q = XL_BLOCK_X;  // <= R/2 (the grid of xl_slab_h_cols)
         cf* t = s + xl_tile_elems(L0, XL_V);
-        cf* Hg = p.H + (size_t)XL_BLOCK_Y * p.P * XL_V;
-        XlLongHColsOp<L0> op{{}, Hg + (size_t)q * L0 * XL_V, mq != q ? Hg + (size_t)mq * L0 * XL_V : (cf*)0, p.hscale};
+        XlLongHColsOp<L0> op{{}, p.H + ((size_t)XL_BLOCK_Y * p.R + q) * L0 * XL_V, p.hscale};
         // the in-place update is safe: every load of the first pass happens before the barrier that precedes the stores
         XlFft<L0, XL_V>::forward_g(s, t, p.tw, op);
     }

@@ -39,7 +39,7 @@ extern "C" int xl_slab_h_rows_per_rank(int N, int G) {
 extern "C" size_t xl_slab_scratch_bytes(int N, int G) {
     SlabGeo g;
     if (slab_geo(g, N, G) || g.R == 1) return 256;
-    size_t a = (size_t)g.rows * g.P, b = (size_t)g.pairs * g.P * 2, c = (size_t)g.hrows * (g.P / 2 + 1);
+    size_t a = (size_t)g.rows * g.P, b = (size_t)g.pairs * g.P * 2, c = (size_t)g.hrows * (g.P / 2 + g.L0);
     size_t m = a > b ? a : b;
     return (m > c ? m : c) * sizeof(cf);
 }
@@ -82,9 +82,9 @@ extern "C" int xl_slab_h_rows(void* Rb, const double* z, int N, int G, int rank,
     XlLongParams q;
     if ((rc = long_params(q, g, N, dx, dy, k))) return rc;
     q.z = z; q.hrow0 = rank * g.hrows; q.hrows = g.hrows; q.scratch = (cf*)scratch; q.spec = (cf*)Rb;
-    rc = xl_launch<XlHEval>(XlDim{pointwise_grid((size_t)g.hrows * (g.P / 2 + 1), XlHEval::NT), 1}, st, q);
+    rc = xl_launch<XlHEval>(XlDim{pointwise_grid((size_t)g.L0 / 2 + 1, XlHEval::NT), g.hrows}, st, q);
     if (rc) return rc;
-    XL_FOR_L0(g.L0, rc = xl_launch<XlLongHRows<XL>>(XlDim{g.R, xl_groups(g.hrows)}, st, q));
+    XL_FOR_L0(g.L0, rc = xl_launch<XlLongHRows<XL>>(XlDim{g.R / 2 + 1, xl_groups(g.hrows)}, st, q));
     return rc;
 }
 // Th = exchanged row spectra of h [G][pairs][hrows][2]  ->  this rank's transfer-function slab Hloc[pairs][P][2]
