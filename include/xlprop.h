@@ -156,12 +156,17 @@ int xl_rs_bwd_fused(const void* in, const void* out, const void* ct_out, const d
  * Buffers: a spectra buffer on the row side is [L/2 slot pairs][rows of this rank][2] complex64; after an all-to-all that
  * sends peer r the slot pairs [r P, (r+1) P), P = (L/2)/G, it is [source rank][P][rows of that rank][2] on the column side,
  * and the second all-to-all is the exact inverse.  The VJP with respect to the field is the same chain applied to the
- * cotangent (the operator is complex-symmetric); d/dz is single-GPU only in this version.
+ * cotangent (the operator is complex-symmetric).  d/dz (JAX differentiates wave_optics.py:285-297 with respect to z):
+ *     d out/dz = i k out + (in conv h_red),   h_red = dh/dz - i k h  (the reduced kernel, see xl_rs_bwd)
+ * -- xl_slab_h_rows_dz -> all-to-all -> xl_slab_h_cols give the transfer-function slab of h_red, the same forward chain
+ * applies it to the primal input, and the two dot products with the cotangent are the caller's (xlumina_b200/slab.py:
+ * rs_slab_grad_z, the first one in fp64 from the saved output, summed over the ranks with one all-reduce).
  * Replaces the same reference lines as xl_rs_fwd (wave_optics.py:281-297). */
 int xl_slab_padded_length(int N);            /* 2^ceil(log2(2N-1)) up to 32768 (N <= 16384); 0 if unsupported */
 int xl_slab_h_rows_per_rank(int N, int G);   /* rows of the y >= 0 half of the impulse response each rank transforms */
 size_t xl_slab_scratch_bytes(int N, int G);  /* scratch of the split kernels (padded length > 4096); small otherwise */
 int xl_slab_h_rows(void* R, const double* z, int N, int G, int rank, double dx, double dy, double k, void* scratch, void* stream);
+int xl_slab_h_rows_dz(void* R, const double* z, int N, int G, int rank, double dx, double dy, double k, void* scratch, void* stream);
 int xl_slab_h_cols(const void* Th, void* Hloc, int N, int G, double dx, double dy, void* stream);
 int xl_slab_rows_fwd(const void* in_local, void* S, int N, int G, int flags, void* stream);
 int xl_slab_cols(void* T, const void* Hloc, int N, int G, void* scratch, void* stream);

@@ -43,6 +43,57 @@ def test_rs_autograd_matches_reference(ops_on_emu):
     assert abs(float(gz) - float(g["vjp_z"])) < 1e-4 * abs(float(g["vjp_z"]))
 
 
+@pytest.mark.parametrize("name,max_line", [("rs_n32_zpos", 32), ("rs_n32_zpos", 4096), ("rs_n32_zneg", 32), ("rs_n48_far", 32)])
+def test_rs_large_grid_route_autograd_matches_reference(ops_on_emu, monkeypatch, emu, name, max_line):
+    """ops.rs_propagation above FUSED_MAX_N (lowered here): the slab / split-line stage chain with one rank, differentiable in
+    the field AND in z (slab.rs_slab_grad_z) -- against the reference-generated fixture (forward, field VJP, d/dz)."""
+    from xlumina_b200 import slab
+    g = golden(name)
+    x = g["x"]
+    dx, k = float(x[1] - x[0]), 2 * np.pi / float(g["wavelength"])
+    monkeypatch.setattr(ops, "FUSED_MAX_N", 16)
+    monkeypatch.setattr(slab, "_require_device", lambda t, lib: None)
+    emu.xl_debug_set_max_line(max_line)          # 32: padded length 64 / 128 = 2 / 4 sub-lines through csrc/xl_long.cuh
+    try:
+        u = torch.tensor(g["field"].astype(np.complex64), requires_grad=True)
+        z = torch.tensor([float(g["z"])], dtype=torch.float64, requires_grad=True)
+        out = ops.rs_propagation(u, z, dx, dx, k)
+        ct = torch.tensor(g["ct"].astype(np.complex64))
+        loss = (ct * out).real.sum()                              # Re sum(ct * out): JAX cotangent convention of the fixture
+        gu, gz = torch.autograd.grad(loss, (u, z))
+    finally:
+        emu.xl_debug_set_max_line(4096)
+    assert rel_l2(out.detach().numpy(), g["out"]) < 1e-5
+    if "vjp_field" in g:
+        assert rel_l2(np.conj(gu.numpy()), g["vjp_field"]) < 1e-5
+    assert abs(float(gz) - float(g["vjp_z"])) < 1e-4 * abs(float(g["vjp_z"]))
+
+
+@pytest.mark.parametrize("name", ["vrs_n24", "vrs_n40_zneg"])
+def test_vrs_large_grid_route_autograd_matches_reference(ops_on_emu, monkeypatch, emu, name):
+    """vrs_propagation above FUSED_MAX_N (lowered here): Ez formed pointwise, three components through the split-line stage
+    chain; forward, field VJP and d/dz (chain + d Ez/dz) against the reference-generated fixture."""
+    from xlumina_b200 import slab
+    g = golden(name)
+    x, y = g["x"], g["y"]
+    dx, dy, k = float(x[1] - x[0]), float(y[1] - y[0]), 2 * np.pi / float(g["wavelength"])
+    monkeypatch.setattr(ops, "FUSED_MAX_N", 16)
+    monkeypatch.setattr(slab, "_require_device", lambda t, lib: None)
+    emu.xl_debug_set_max_line(32)
+    try:
+        e = torch.tensor(np.stack([g["Ex"], g["Ey"]]).astype(np.complex64), requires_grad=True)
+        z = torch.tensor([float(g["z"])], dtype=torch.float64, requires_grad=True)
+        out = ops.vrs_propagation(e, None, z, float(x[0]), float(y[0]), dx, dy, k)
+        ct = torch.tensor(g["ct"].astype(np.complex64))
+        ge, gz = torch.autograd.grad((ct * out).real.sum(), (e, z))
+    finally:
+        emu.xl_debug_set_max_line(4096)
+    assert rel_l2(out.detach().numpy(), g["out"]) < 1e-5
+    if "vjp_field" in g:
+        assert rel_l2(np.conj(ge.numpy()), g["vjp_field"]) < 1e-5
+    assert abs(float(gz) - float(g["vjp_z"])) < 1e-4 * abs(float(g["vjp_z"]))
+
+
 def test_sharp_focus_table_complex64(ops_on_emu):
     g = golden("sharp_focus_n32")
     ls, params, fixed = sharp_focus_problem(g, "cpu", torch.complex64)

@@ -40,9 +40,12 @@ def _worker(rank, world, port, emu_path, N, z, out_dir, max_line=4096):
         rows = N // world
         mine = torch.as_tensor(field[rank * rows:(rank + 1) * rows].copy())
         out, H = slab.rs_propagation_slab(mine, z, dx, dx, k, lib=emu, return_transfer=True)
-        vjp = slab.rs_slab_vjp(torch.as_tensor(ct[rank * rows:(rank + 1) * rows].copy()), H, lib=emu)
+        ct_mine = torch.as_tensor(ct[rank * rows:(rank + 1) * rows].copy())
+        vjp = slab.rs_slab_vjp(ct_mine, H, lib=emu)
+        gz = slab.rs_slab_grad_z(mine, ct_mine, out, z, dx, dx, k, lib=emu)     # all-reduced: every rank holds the total
         np.save(os.path.join(out_dir, f"out{rank}.npy"), out.numpy())
         np.save(os.path.join(out_dir, f"vjp{rank}.npy"), vjp.numpy())
+        np.save(os.path.join(out_dir, f"gz{rank}.npy"), gz.numpy())
     finally:
         dist.destroy_process_group()
 
@@ -83,6 +86,30 @@ def test_slab_rs_split_lines_match_oracle(emu, tmp_path, world, N, z):
     vref, _ = o.RS_propagation(ct.astype(np.complex128), x, x, 0.6328, z)
     vgot = np.concatenate([np.load(tmp_path / f"vjp{r}.npy") for r in range(world)])
     assert rel_l2(vgot, vref) < 5e-6
+
+
+def _grad_z_oracle(field, ct, x, z):
+    """d/dz Re sum(ct * RS(field, z)) by autograd through the complex128 torch oracle."""
+    from oracle import oracle_torch as ot
+    zt = torch.tensor(float(z), dtype=torch.float64, requires_grad=True)
+    out = ot.RS_propagation(torch.as_tensor(field.astype(np.complex128)), x, x, 0.6328, zt)
+    (torch.as_tensor(ct.astype(np.complex128)) * out).real.sum().backward()
+    return float(zt.grad)
+
+
+@pytest.mark.parametrize("world,N,z,max_line", [(2, 32, 2500.0, 4096), (4, 64, 6000.0, 4096), (2, 64, -4000.0, 32), (4, 128, 6000.0, 32)])
+def test_slab_grad_z_matches_oracle(emu, tmp_path, world, N, z, max_line):
+    """d/dz on the slab path (slab.rs_slab_grad_z: per-rank partial sums + one all-reduce), single-pass and split-line
+    kernels, against autograd through the complex128 oracle."""
+    emu_path = os.path.join(ROOT, "tests", "emu", "libxlprop_emu.so")
+    mp.spawn(_worker, args=(world, _free_port(), emu_path, N, z, str(tmp_path), max_line), nprocs=world, join=True)
+    rng = np.random.default_rng(7)
+    field = (rng.standard_normal((N, N)) + 1j * rng.standard_normal((N, N))).astype(np.complex64)
+    ct = (rng.standard_normal((N, N)) + 1j * rng.standard_normal((N, N))).astype(np.complex64)
+    ref = _grad_z_oracle(field, ct, np.linspace(-300.0, 300.0, N), z)
+    got = [float(np.load(tmp_path / f"gz{r}.npy")) for r in range(world)]
+    assert max(got) == min(got)                      # the all-reduce left the same total on every rank
+    assert abs(got[0] - ref) < 1e-4 * abs(ref)
 
 
 def test_slab_plan_rejects_bad_partitions(emu):

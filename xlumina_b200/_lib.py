@@ -38,6 +38,7 @@ SIGNATURES = {
     "xl_slab_h_rows_per_rank": (_i, [_i, _i]),
     "xl_slab_scratch_bytes": (_sz, [_i, _i]),
     "xl_slab_h_rows": (_i, [_vp, _vp, _i, _i, _i, _d, _d, _d, _vp, _vp]),
+    "xl_slab_h_rows_dz": (_i, [_vp, _vp, _i, _i, _i, _d, _d, _d, _vp, _vp]),
     "xl_slab_h_cols": (_i, [_vp, _vp, _i, _i, _d, _d, _vp]),
     "xl_slab_rows_fwd": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "xl_slab_cols": (_i, [_vp, _vp, _i, _i, _vp, _vp]),

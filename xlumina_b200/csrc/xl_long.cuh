@@ -326,7 +326,7 @@ struct XlHEval {
     }
     XL_DEV static void run(const Params& p, cf*) {
         const XlRsHConst hc = xl_rs_hconst(xl_ldg(p.z), p.k);
-        const int half = p.R / 2, yl = XL_BLOCK_Y, y = p.hrow0 + yl;
+        const int half = p.R / 2, yl = XL_BLOCK_Y, y = p.hrow0 + yl, deriv = (p.flags & XL_F_DERIV) ? 1 : 0;
         const bool row = y <= p.P / 2;            // the rows beyond P/2 only pad the row count to an even number
         cf* Yrow = p.scratch + (size_t)yl * (half + 1) * p.L0;
         XL_THREADS(tid, NT) {
@@ -336,8 +336,8 @@ struct XlHEval {
 #pragma unroll
                 for (int j = 0; j <= 4; ++j) {
                     A[j] = cf_zero(); B[j] = cf_zero();
-                    if (row && (j < half || (j == half && t == 0))) A[j] = xl_rs_h((t + p.L0 * j) * p.dx, y * p.dy, hc, 0);
-                    if (row && j >= 1 && j <= half && t > 0) B[j] = xl_rs_h((p.L0 * j - t) * p.dx, y * p.dy, hc, 0);
+                    if (row && (j < half || (j == half && t == 0))) A[j] = xl_rs_h((t + p.L0 * j) * p.dx, y * p.dy, hc, deriv);
+                    if (row && j >= 1 && j <= half && t > 0) B[j] = xl_rs_h((p.L0 * j - t) * p.dx, y * p.dy, hc, deriv);
                 }
                 if (t == 0) {                     // |x| = L0 j - 0 is the sample A[j]
 #pragma unroll

@@ -62,8 +62,9 @@ static int long_params(XlLongParams& q, const SlabGeo& g, int N, double dx, doub
 static void long_set_chunk(XlLongParams& q, int chunk_rows) { q.chunk_rows = chunk_rows; q.chunk_magic = xl_div_magic(chunk_rows); }
 
 // row spectra of this rank's y rows [rank*hrows, (rank+1)*hrows) of the impulse response: R[P/2][hrows][2]
-extern "C" int xl_slab_h_rows(void* Rb, const double* z, int N, int G, int rank, double dx, double dy, double k,
-                              void* scratch, void* stream) {
+// deriv: the rows of the REDUCED z-derivative h_z - i k h (xl_rs_h, xl_kernels.cuh) instead of h -- even in x and y like h
+static int slab_h_rows(void* Rb, const double* z, int N, int G, int rank, double dx, double dy, double k,
+                       void* scratch, void* stream, int deriv) {
     if (!Rb || !z) return xl_fail(XL_E_BAD_ARG, "xl_slab_h_rows: null pointer%s", "");
     SlabGeo g;
     int rc = slab_geo(g, N, G);
@@ -72,7 +73,7 @@ extern "C" int xl_slab_h_rows(void* Rb, const double* z, int N, int G, int rank,
     if (g.R == 1) {
         XlRsParams p;
         if ((rc = rs_base_params(p, N, dx, dy, k))) return rc;
-        p.H = (cf*)Rb; p.z = z; p.flags = 0;
+        p.H = (cf*)Rb; p.z = z; p.flags = deriv ? XL_F_DERIV : 0;
         p.rows = g.hrows; p.hrow0 = rank * g.hrows; p.hstore_all = 1;
         const int L = p.L;
         XL_FOR_L(L, rc = xl_launch<XlHRows<XL>>(XlDim{xl_groups(g.hrows), 1}, st, p));
@@ -82,10 +83,19 @@ extern "C" int xl_slab_h_rows(void* Rb, const double* z, int N, int G, int rank,
     XlLongParams q;
     if ((rc = long_params(q, g, N, dx, dy, k))) return rc;
     q.z = z; q.hrow0 = rank * g.hrows; q.hrows = g.hrows; q.scratch = (cf*)scratch; q.spec = (cf*)Rb;
+    q.flags = deriv ? XL_F_DERIV : 0;
     rc = xl_launch<XlHEval>(XlDim{pointwise_grid((size_t)g.L0 / 2 + 1, XlHEval::NT), g.hrows}, st, q);
     if (rc) return rc;
     XL_FOR_L0(g.L0, rc = xl_launch<XlLongHRows<XL>>(XlDim{g.R / 2 + 1, xl_groups(g.hrows)}, st, q));
     return rc;
+}
+extern "C" int xl_slab_h_rows(void* Rb, const double* z, int N, int G, int rank, double dx, double dy, double k,
+                              void* scratch, void* stream) {
+    return slab_h_rows(Rb, z, N, G, rank, dx, dy, k, scratch, stream, 0);
+}
+extern "C" int xl_slab_h_rows_dz(void* Rb, const double* z, int N, int G, int rank, double dx, double dy, double k,
+                                 void* scratch, void* stream) {
+    return slab_h_rows(Rb, z, N, G, rank, dx, dy, k, scratch, stream, 1);
 }
 // Th = exchanged row spectra of h [G][pairs][hrows][2]  ->  this rank's transfer-function slab Hloc[pairs][P][2]
 extern "C" int xl_slab_h_cols(const void* Th, void* Hloc, int N, int G, double dx, double dy, void* stream) {

@@ -449,7 +449,8 @@ FUSED_MAX_N = 2048   # largest grid of the fused single-pass path (padded length
 
 class _RSLarge(torch.autograd.Function):
     """Grids above FUSED_MAX_N (up to 16384^2): the slab / split-line stage chain of xlumina_b200/slab.py with one rank.
-    Differentiable in the field (the operator is complex-symmetric); d/dz is not available on this path."""
+    Differentiable in the field (the operator is complex-symmetric) and in z (slab.rs_slab_grad_z: the exact i k out term
+    in float64 plus one more chain with the transfer function of the reduced kernel, per field)."""
 
     @staticmethod
     @_on_device
@@ -460,25 +461,35 @@ class _RSLarge(torch.autograd.Function):
         for f in field:                                   # the fields of a batch share one transfer-function slab
             o, H = slab.rs_propagation_slab(f, z, dx, dy, k, transfer=H, return_transfer=True, group=slab._LOCAL)
             outs.append(o)
-        ctx.save_for_backward(H)
-        return torch.stack(outs)
+        out = torch.stack(outs)
+        ctx.geo = (dx, dy, k)
+        if z.requires_grad:
+            ctx.save_for_backward(H, field, out, z)
+        else:
+            ctx.save_for_backward(H)
+        return out
 
     @staticmethod
     @_on_device
     def backward(ctx, g):
         from . import slab
-        if ctx.needs_input_grad[1]:
-            raise _lib.XlpropError(f"RS propagation above {FUSED_MAX_N}^2 is not differentiable in z in this version")
-        (H,) = ctx.saved_tensors
+        H = ctx.saved_tensors[0]
         # torch convention: conj(A^T conj(g)); A^T = A
-        gin = torch.stack([torch.conj_physical(slab.rs_slab_vjp(torch.conj_physical(gi), H, group=slab._LOCAL)) for gi in g])
-        return gin, None, None, None, None
+        gin = None
+        if ctx.needs_input_grad[0]:
+            gin = torch.stack([torch.conj_physical(slab.rs_slab_vjp(torch.conj_physical(gi), H, group=slab._LOCAL)) for gi in g])
+        gz = None
+        if ctx.needs_input_grad[1]:
+            _, field, out, z = ctx.saved_tensors
+            dx, dy, k = ctx.geo
+            gz = sum(slab.rs_slab_grad_z(field[i], torch.conj_physical(g[i]), out[i], z, dx, dy, k, group=slab._LOCAL)
+                     for i in range(g.shape[0])).reshape(z.shape).to(z.dtype)
+        return gin, gz, None, None, None
 
 
 
 def rs_propagation(field, z, dx, dy, k):
-    """Scalar Rayleigh-Sommerfeld propagation of `field` (..., N, N) over distance z (differentiable in field and z; above
-    FUSED_MAX_N^2 in the field only).  `z`: one distance shared by all the fields (one transfer function, one library call),
+    """Scalar Rayleigh-Sommerfeld propagation of `field` (..., N, N) over distance z (differentiable in field and z).  `z`: one distance shared by all the fields (one transfer function, one library call),
     or a tensor with one distance per field."""
     dt = field.dtype
     N = field.shape[-1]
@@ -543,10 +554,11 @@ def vrs_propagation(Ex, Ey, z, x0, y0, dx, dy, k, _hshare=None):
     if N > FUSED_MAX_N:
         exy = ex if ey is None else torch.stack([ex, ey])
         # large grids: Ez = (Ex X + Ey Y)/r (vectorized_optics.py:258-261) is formed pointwise here and the three components
-        # go through the stage chain as one batch sharing the transfer function (differentiable in Ex, Ey only)
+        # go through the stage chain as one batch sharing the transfer function; z stays on the autograd tape through r
+        # (d Ez/dz) and through the chain (_RSLarge), so the route is differentiable in Ex, Ey and z
         xs = float(x0) + float(dx) * torch.arange(N, dtype=torch.float64, device=exy.device)
         ys = float(y0) + float(dy) * torch.arange(N, dtype=torch.float64, device=exy.device)
-        r = torch.sqrt(xs[None, :] ** 2 + ys[:, None] ** 2 + zt.detach() ** 2)
+        r = torch.sqrt(xs[None, :] ** 2 + ys[:, None] ** 2 + zt ** 2)
         ez = exy[0] * (xs[None, :] / r).to(torch.float32) + exy[1] * (ys[:, None] / r).to(torch.float32)
         out = _RSLarge.apply(torch.stack([exy[0], exy[1], ez]), zt, float(dx), float(dy), float(k))
         return out if dt == torch.complex64 or not torch.is_complex(Ex) else out.to(dt)

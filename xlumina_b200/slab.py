@@ -15,8 +15,9 @@ exact inverse of the first: row side [L/2 pairs][rows][2], column side [source r
 Padded lengths up to 4096 (N <= 2048) run the single-pass FFT kernels; longer lines, up to 32768 (N <= 16384, the 16384^2
 configuration), are split into R <= 8 sub-lines of 4096 (csrc/xl_long.cuh: the forward radix-R step is fused into the
 loads, the inverse one is a pointwise combine kernel over a scratch buffer).  With one rank the same chain is the
-single-GPU path for grids above 2048^2.  Round-1 limits: scalar fields, forward and field-VJP (the operator is
-complex-symmetric: `rs_slab_vjp`); d/dz is available on the fused single-GPU path (N <= 2048) only.
+single-GPU path for grids above 2048^2.  Scalar fields; forward, field-VJP (the operator is complex-symmetric:
+`rs_slab_vjp`) and d/dz (`rs_slab_grad_z`: one more transfer-function slab -- of the reduced kernel dh/dz - i k h -- and one
+more forward chain on the primal input; the fused single-GPU path for N <= 2048 gets d/dz from a Parseval sum instead).
 """
 import contextlib
 import ctypes
@@ -26,7 +27,7 @@ import torch.distributed as dist
 
 from . import _lib
 
-__all__ = ["rs_propagation_slab", "rs_slab_vjp", "SlabPlan"]
+__all__ = ["rs_propagation_slab", "rs_slab_vjp", "rs_slab_grad_z", "SlabPlan"]
 
 
 def _ptr(t):
@@ -36,6 +37,13 @@ def _ptr(t):
 def _device_of(t):
     """Context that makes the tensor's CUDA device current (the library keys its tables on the current device)."""
     return torch.cuda.device(t.device) if t.is_cuda else contextlib.nullcontext()
+
+
+def _require_device(t, lib):
+    """The product library takes CUDA tensors only (no CPU fallback); only the host-emulation library of the tests, passed
+    explicitly as `lib`, runs on CPU tensors."""
+    if lib is _lib._lib and not t.is_cuda:
+        raise _lib.XlpropError("xlumina_b200 operators need CUDA tensors (no CPU fallback)")
 
 
 def _stream_of(t):
@@ -83,10 +91,11 @@ def _scratch(plan, ref):
     return torch.empty(plan.scratch_bytes, dtype=torch.uint8, device=ref.device)
 
 
-def _transfer_slab(plan, z, dx, dy, k, rank, ref, lib, group):
+def _transfer_slab(plan, z, dx, dy, k, rank, ref, lib, group, deriv=False):
     R = torch.empty(plan.hspec_elems, dtype=torch.complex64, device=ref.device)
     scr = _scratch(plan, ref)
-    _lib.check(lib.xl_slab_h_rows(_ptr(R), _ptr(z), plan.N, plan.G, rank, dx, dy, k, _ptr(scr), _stream_of(ref)), "xl_slab_h_rows")
+    rows = lib.xl_slab_h_rows_dz if deriv else lib.xl_slab_h_rows      # deriv: the reduced kernel dh/dz - i k h
+    _lib.check(rows(_ptr(R), _ptr(z), plan.N, plan.G, rank, dx, dy, k, _ptr(scr), _stream_of(ref)), "xl_slab_h_rows")
     Th = _all_to_all(R, group)
     H = torch.empty(plan.hloc_elems, dtype=torch.complex64, device=ref.device)
     _lib.check(lib.xl_slab_h_cols(_ptr(Th), _ptr(H), plan.N, plan.G, dx, dy, _stream_of(ref)), "xl_slab_h_cols")
@@ -112,8 +121,7 @@ def rs_propagation_slab(field_local, z, dx, dy, k, group=None, lib=None, transfe
     `return_transfer`, to be passed back as `transfer` for another field or the VJP at the same z)."""
     lib = lib or _lib.lib()
     world, rank = _world_rank(group)
-    if lib is _lib._lib and not field_local.is_cuda:
-        raise _lib.XlpropError("xlumina_b200 operators need CUDA tensors (no CPU fallback)")
+    _require_device(field_local, lib)
     f = field_local.to(torch.complex64).resolve_conj().contiguous()
     N = f.shape[-1]
     plan = SlabPlan(N, world, lib)
@@ -137,3 +145,34 @@ def rs_slab_vjp(ct_local, transfer, group=None, lib=None):
     plan = SlabPlan(c.shape[-1], world, lib)
     with _device_of(c):
         return _apply(plan, c, transfer, 0, lib, group)
+
+
+def rs_slab_grad_z(field_local, ct_local, out_local, z, dx, dy, k, group=None, lib=None):
+    """d/dz of  Re sum(ct * out)  for  out = rs_propagation_slab(field, z)  -- `ct_local` is this rank's slab of the cotangent
+    in the JAX convention (no conjugate; torch callers pass conj(grad_output)), `out_local` the saved primal output.
+        d out/dz = i k out + field (*) (dh/dz - i k h)
+    The first term is a pure phase rotation: its contribution, -k Im sum(ct * out), is accumulated in float64 from complex64
+    operands (every product is exact), so it cancels exactly for intensity-type losses; only the
+    reduced kernel, 1e2-1e4 times smaller, goes through the complex64 FFT chain.  Returns a float64 scalar tensor; with
+    more than one rank the partial sums are all-reduced (every rank gets the total)."""
+    lib = lib or _lib.lib()
+    world, rank = _world_rank(group)
+    _require_device(field_local, lib)
+    f = field_local.to(torch.complex64).resolve_conj().contiguous()
+    c = ct_local.to(torch.complex64).resolve_conj().contiguous()
+    o = out_local.to(torch.complex64).resolve_conj().contiguous()
+    plan = SlabPlan(f.shape[-1], world, lib)
+    with _device_of(f):
+        zt = z if isinstance(z, torch.Tensor) else torch.full((1,), float(z), dtype=torch.float64, device=f.device)
+        zt = zt.detach().to(device=f.device, dtype=torch.float64).reshape(1)
+        Hz = _transfer_slab(plan, zt, float(dx), float(dy), float(k), rank, f, lib, group, deriv=True)
+        d = _apply(plan, f, Hz, 0, lib, group)
+        del Hz
+        gz = torch.zeros((), dtype=torch.float64, device=f.device)
+        step = max(1, (1 << 24) // f.shape[-1])                       # rows per chunk: bounds the float64 temporaries
+        for r0 in range(0, f.shape[0], step):
+            cc = c[r0:r0 + step].to(torch.complex128)
+            gz += (cc * d[r0:r0 + step]).real.sum() - float(k) * (cc * o[r0:r0 + step]).imag.sum()
+    if world > 1:
+        dist.all_reduce(gz, group=group)
+    return gz
