@@ -87,6 +87,22 @@ def _all_to_all(buf, group):
     return out
 
 
+def _all_to_all_start(buf, group):
+    """The same exchange, issued asynchronously: returns (received buffer, work handle or None).  The collective runs on the
+    backend's own stream behind everything already queued on the current stream; kernels launched after this call overlap
+    with it, and `_wait` makes the current stream wait for the exchanged data."""
+    if _world_rank(group)[0] == 1:
+        return buf, None
+    out = torch.empty_like(buf)
+    work = dist.all_to_all_single(torch.view_as_real(out).reshape(-1), torch.view_as_real(buf).reshape(-1), group=group, async_op=True)
+    return out, work
+
+
+def _wait(work):
+    if work is not None:
+        work.wait()
+
+
 def _scratch(plan, ref):
     return torch.empty(plan.scratch_bytes, dtype=torch.uint8, device=ref.device)
 
@@ -115,6 +131,30 @@ def _apply(plan, field_local, H, flags, lib, group):
     return out
 
 
+def _transfer_and_apply(plan, field_local, z, dx, dy, k, rank, lib, group):
+    """Fresh distance on several ranks: the transfer-function chain and the field chain interleaved so that each of the
+    first two exchanges has independent work behind it -- the row FFTs of the field run while the row spectra of the impulse
+    response are exchanged, the column FFTs of the transfer function while the field's row spectra are.  Same stages, same
+    buffers and the same results as _transfer_slab followed by _apply."""
+    dev, st = field_local.device, _stream_of(field_local)
+    R = torch.empty(plan.hspec_elems, dtype=torch.complex64, device=dev)
+    scr = _scratch(plan, field_local)
+    _lib.check(lib.xl_slab_h_rows(_ptr(R), _ptr(z), plan.N, plan.G, rank, dx, dy, k, _ptr(scr), st), "xl_slab_h_rows")
+    Th, w_h = _all_to_all_start(R, group)
+    S = torch.empty(plan.spec_elems, dtype=torch.complex64, device=dev)
+    _lib.check(lib.xl_slab_rows_fwd(_ptr(field_local), _ptr(S), plan.N, plan.G, 0, st), "xl_slab_rows_fwd")
+    T, w_s = _all_to_all_start(S, group)
+    _wait(w_h)
+    H = torch.empty(plan.hloc_elems, dtype=torch.complex64, device=dev)
+    _lib.check(lib.xl_slab_h_cols(_ptr(Th), _ptr(H), plan.N, plan.G, dx, dy, st), "xl_slab_h_cols")
+    _wait(w_s)
+    _lib.check(lib.xl_slab_cols(_ptr(T), _ptr(H), plan.N, plan.G, _ptr(scr), st), "xl_slab_cols")
+    S2 = _all_to_all(T, group)
+    out = torch.empty_like(field_local)
+    _lib.check(lib.xl_slab_rows_inv(_ptr(S2), _ptr(out), plan.N, plan.G, 0, _ptr(scr), st), "xl_slab_rows_inv")
+    return out, H
+
+
 def rs_propagation_slab(field_local, z, dx, dy, k, group=None, lib=None, transfer=None, return_transfer=False):
     """Propagate the row slab `field_local` (N/G, N) complex64 of an N x N field by z; every rank of `group` calls this with
     its own slab and the same z, dx, dy, k (`group=slab._LOCAL`: this process alone, whole field, no collective).  Returns this rank's rows of the result (and the transfer-function slab when
@@ -131,8 +171,9 @@ def rs_propagation_slab(field_local, z, dx, dy, k, group=None, lib=None, transfe
         if transfer is None:
             zt = z if isinstance(z, torch.Tensor) else torch.full((1,), float(z), dtype=torch.float64, device=f.device)
             zt = zt.to(device=f.device, dtype=torch.float64).reshape(1)
-            transfer = _transfer_slab(plan, zt, float(dx), float(dy), float(k), rank, f, lib, group)
-        out = _apply(plan, f, transfer, 0, lib, group)
+            out, transfer = _transfer_and_apply(plan, f, zt, float(dx), float(dy), float(k), rank, lib, group)
+        else:
+            out = _apply(plan, f, transfer, 0, lib, group)
     return (out, transfer) if return_transfer else out
 
 
