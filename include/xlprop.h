@@ -173,6 +173,9 @@ int xl_slab_cols(void* T, const void* Hloc, int N, int G, void* scratch, void* s
 int xl_slab_rows_inv(const void* S, void* out_local, int N, int G, int flags, void* scratch, void* stream);
 /* Test hook: sub-line length of the split kernels (32 or 4096, default 4096), so that tests reach them at small N. */
 void xl_debug_set_max_line(int sub_line_length);
+/* Test / A-B hook: inverse radix step of the split kernels inside a thread-block cluster (1) or as a second launch through
+ * the scratch buffer (0); -1 (default): clusters when the split factor is <= 4 (padded length <= 16384). */
+void xl_debug_set_long_cluster(int on);
 
 /* ---------------------------------------------------------------- CZT / VCZT -------------------------------- */
 /* vectorial = 0: in (N,N) -> out (My,Mx); ey ignored         CZT_jit,  wave_optics.py:333-357

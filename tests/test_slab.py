@@ -23,7 +23,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, emu_path, N, z, out_dir, max_line=4096):
+def _worker(rank, world, port, emu_path, N, z, out_dir, max_line=4096, cluster=-1):
     sys.path.insert(0, ROOT)
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -32,6 +32,7 @@ def _worker(rank, world, port, emu_path, N, z, out_dir, max_line=4096):
         from xlumina_b200 import _lib, slab
         emu = _lib.declare(ctypes.CDLL(emu_path))
         emu.xl_debug_set_max_line(max_line)
+        emu.xl_debug_set_long_cluster(cluster)
         rng = np.random.default_rng(7)
         field = (rng.standard_normal((N, N)) + 1j * rng.standard_normal((N, N))).astype(np.complex64)
         ct = (rng.standard_normal((N, N)) + 1j * rng.standard_normal((N, N))).astype(np.complex64)
@@ -86,6 +87,22 @@ def test_slab_rs_split_lines_match_oracle(emu, tmp_path, world, N, z):
     vref, _ = o.RS_propagation(ct.astype(np.complex128), x, x, 0.6328, z)
     vgot = np.concatenate([np.load(tmp_path / f"vjp{r}.npy") for r in range(world)])
     assert rel_l2(vgot, vref) < 5e-6
+
+
+@pytest.mark.parametrize("world,N,z,cluster", [(1, 128, 9000.0, 1), (1, 64, 5000.0, 0), (2, 128, -4000.0, 1), (2, 24, 1500.0, 0)])
+def test_slab_rs_split_lines_both_inverse_forms(emu, tmp_path, world, N, z, cluster):
+    """The inverse radix step of the split kernels as a cluster kernel (forced on: also for 8 sub-lines) and as the two-launch
+    form through the scratch buffer (forced off: also for 2 and 4 sub-lines); the default picks by the split factor."""
+    from conftest import rel_l2
+    from oracle import oracle_np as o
+    emu_path = os.path.join(ROOT, "tests", "emu", "libxlprop_emu.so")
+    mp.spawn(_worker, args=(world, _free_port(), emu_path, N, z, str(tmp_path), 32, cluster), nprocs=world, join=True)
+    rng = np.random.default_rng(7)
+    field = (rng.standard_normal((N, N)) + 1j * rng.standard_normal((N, N))).astype(np.complex64)
+    x = np.linspace(-300.0, 300.0, N)
+    ref, _ = o.RS_propagation(field.astype(np.complex128), x, x, 0.6328, z)
+    got = np.concatenate([np.load(tmp_path / f"out{r}.npy") for r in range(world)])
+    assert rel_l2(got, ref) < 5e-6
 
 
 def _grad_z_oracle(field, ct, x, z):

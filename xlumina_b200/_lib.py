@@ -44,6 +44,7 @@ SIGNATURES = {
     "xl_slab_cols": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
     "xl_slab_rows_inv": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
     "xl_debug_set_max_line": (None, [_i]),
+    "xl_debug_set_long_cluster": (None, [_i]),
     "xl_czt_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "xl_czt_tables_bytes": (_sz, [_i, _i, _i]),
     "xl_czt_fwd": (_i, [_vp, _vp, _vp, _vp, _d, _i, _i, _i, _i, _d, _d, _d, _d, _d, _d, _d, _d, _i, _vp, _vp, _sz, _vp]),

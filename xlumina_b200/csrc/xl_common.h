@@ -73,6 +73,70 @@ template <class Body> static int xl_launch(XlDim grid, xl_stream_t stream, const
 #endif
 }
 
+// Cluster kernels: the grid.x CTAs of one blockIdx.y form a thread-block cluster (grid.x <= 8).  Body::run1 is everything
+// before the cluster barrier (it leaves its result in the CTA's shared memory), Body::run2 reads the peers' shared memory
+// (xl_peer_ld4); a second cluster barrier keeps every CTA's shared memory alive until its peers have finished reading.
+#ifndef XL_HOST_EMU
+template <class Body> __global__ void __launch_bounds__(Body::NT, XlMinBlocks<Body>::value) xl_kernel_cluster(const typename Body::Params p) {
+    extern __shared__ float4 xl_smem[];
+    Body::run1(p, (float2*)xl_smem);
+    xl_cluster_sync();
+    const XlPeers pr{(unsigned)__cvta_generic_to_shared(xl_smem)};
+    Body::run2(p, (float2*)xl_smem, pr);
+    xl_cluster_sync();
+}
+#endif
+template <class Body> static int xl_launch_cluster(XlDim grid, xl_stream_t stream, const typename Body::Params& p) {
+    if (grid.x <= 0 || grid.y <= 0) return XL_OK;
+    if (grid.x > 8) return xl_fail(XL_E_UNSUPPORTED, "cluster of %s%lld CTAs (portable limit 8)", "", (long long)grid.x);
+    const size_t smem = Body::smem();
+    xl_count_launch();
+#ifdef XL_HOST_EMU
+    (void)stream;
+    std::vector<std::vector<char>> bufs((size_t)grid.x, std::vector<char>(smem + 64));
+    float2* ptrs[8];
+    for (int bx = 0; bx < grid.x; ++bx) ptrs[bx] = (float2*)bufs[(size_t)bx].data();
+    xl_emu_gridDim.x = grid.x; xl_emu_gridDim.y = grid.y; xl_emu_gridDim.z = 1;
+    for (int by = 0; by < grid.y; ++by) {
+        for (int bx = 0; bx < grid.x; ++bx) {
+            xl_emu_blockIdx.x = bx; xl_emu_blockIdx.y = by; xl_emu_blockIdx.z = 0;
+            Body::run1(p, ptrs[bx]);
+        }
+        for (int bx = 0; bx < grid.x; ++bx) {
+            xl_emu_blockIdx.x = bx; xl_emu_blockIdx.y = by; xl_emu_blockIdx.z = 0;
+            Body::run2(p, ptrs[bx], XlPeers{ptrs});
+        }
+    }
+    return XL_OK;
+#else
+    static std::atomic<unsigned long long> attr_mask{0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 64 && !((attr_mask.load(std::memory_order_acquire) >> dev) & 1ull)) {
+        cudaError_t e = cudaFuncSetAttribute(xl_kernel_cluster<Body>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return xl_fail(XL_E_CUDA, "cudaFuncSetAttribute: %s (smem %lld)", cudaGetErrorString(e), (long long)smem);
+        attr_mask.fetch_or(1ull << dev, std::memory_order_release);
+    }
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid.x, grid.y, 1);
+    cfg.blockDim = dim3(Body::NT, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned)grid.x; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    void* rec = xl_prof_begin(Body::name(), stream);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, xl_kernel_cluster<Body>, p);
+    if (rec) xl_prof_end(rec, stream);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) return xl_fail(XL_E_CUDA, "cluster kernel launch: %s", cudaGetErrorString(e));
+    return XL_OK;
+#endif
+}
+
 // Persistent kernels: `per_sm` resident CTAs per SM walk `items` work items (blockIdx.x, blockIdx.x + gridDim.x, ...).
 // The host emulation uses 3 CTAs so that every CTA walks several items.
 template <class Body> static int xl_launch_persistent(int items, int per_sm, xl_stream_t stream, const typename Body::Params& p) {

@@ -171,6 +171,71 @@ struct XlLongRowsCombine {
     }
 };
 
+// long_rows_inv + long_rows_combine as ONE cluster kernel: the R CTAs of a row pair are a thread-block cluster; each leaves
+// w_P^{-i q} IDFT_L0(X_q)[i] of both rows in its own tile, and after the cluster barrier CTA c finishes the positions
+// i in [c L0/R, (c+1) L0/R): it gathers z_q[i] from the R tiles over distributed shared memory (one 16-byte load per peer
+// brings both rows) and writes the kept samples.  No scratch round trip (4.3 GB written + read at 16384^2), no second launch.
+template <int L0> struct XlLongRowsInvZOp : XlOpBase {
+    static constexpr int R1 = xl_first_radix(L0), S1 = L0 / R1;
+    const XlLongParams& p; int q, yb; cf* s;
+    XL_DEV void load(int, cf*, int) const {}
+    XL_DEV void spec(int beta, cf* v) const {
+#pragma unroll
+        for (int qq = 0; qq < 16; ++qq) {
+            const int g = q * L0 + qq * (L0 / 16) + beta;
+            xl_blocked_load2<xl_lane_mask(L0)>(p.spec + (size_t)(g / 2) * p.rows * 2, yb, p.rows, g, v + qq, v + 16 + qq);
+        }
+    }
+    // in place: the thread that owns n reads and writes the positions n + S1 j only
+    XL_DEV void store_vec(int n, const cf* v) const {
+#pragma unroll
+        for (int j = 0; j < R1; ++j) {
+            const int i = n + S1 * j;
+            const cf w = cf_conj(xl_tw_at(p.tw, i * q, p.P));     // w_P^{-i q}
+            const cf o[2] = {cf_mul(v[j], w), cf_mul(v[R1 + j], w)};
+            XlTile<2>::st(s, i, o, 1);
+        }
+    }
+};
+template <int L0> struct XlLongRowsInvC {
+    static const char* name() { return "long_rows_inv"; }
+    typedef XlLongParams Params;
+    static constexpr int NT = xl_threads(L0);
+    static size_t smem() { return xl_smem_bytes(L0, XL_V); }
+    XL_DEV static void run1(const Params& p, cf* s) {
+        cf* t = s + xl_tile_elems(L0, XL_V);
+        XlLongRowsInvZOp<L0> op{{}, p, XL_BLOCK_X, XL_BLOCK_Y * XL_V, s};
+        XlFft<L0, XL_V>::inverse_g(s, t, p.tw, op);
+    }
+    XL_DEV static void run2(const Params& p, cf*, const XlPeers& pr) {
+        const int c = XL_BLOCK_X, yb = XL_BLOCK_Y * XL_V, slice = L0 / p.R;
+        XL_THREADS(tid, NT) {
+            for (int ii = tid; ii < slice; ii += NT) {
+                const int i = c * slice + ii;
+                cf z0[8], z1[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    z0[q] = cf_zero(); z1[q] = cf_zero();
+                    if (q < p.R) xl_peer_ld4(pr, q, 2 * xl_pad(i), &z0[q], &z1[q]);
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int n = i + L0 * j;
+                    if (2 * j >= p.R || n >= p.N) continue;
+                    cf a0 = z0[0], a1 = z1[0];
+#pragma unroll
+                    for (int q = 1; q < 8; ++q) {   // z[q >= R] == 0
+                        const cf w = cf_conj(xl_tw_at(p.tw, j * q, p.R)); a0 = cf_fma(z0[q], w, a0); a1 = cf_fma(z1[q], w, a1);
+                    }
+                    if (p.flags & XL_F_CONJ_OUT) { a0 = cf_conj(a0); a1 = cf_conj(a1); }
+                    if (yb < p.rows) p.out[(size_t)yb * p.N + n] = a0;
+                    if (yb + 1 < p.rows) p.out[(size_t)(yb + 1) * p.N + n] = a1;
+                }
+            }
+        }
+    }
+};
+
 // ------------------------------------------------------------------------------------------------ column kernels
 // Column kernels, three launches per stage:
 //   long_cols_split   (pointwise)  Y[G][q][i] = w_P^{i q} sum_{j < R/2} x[i + L0 j] w_R^{j q}      the radix-R DIF step, ONCE per
@@ -283,6 +348,80 @@ struct XlLongColsCombine {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const int n = i + p.L0 * j;
+                    if (2 * j >= p.R || n >= p.N) continue;
+                    cf a0 = z0[0], a1 = z1[0];
+#pragma unroll
+                    for (int q = 1; q < 8; ++q) {   // z[q >= R] == 0
+                        const cf w = cf_conj(xl_tw_at(p.tw, j * q, p.R)); a0 = cf_fma(z0[q], w, a0); a1 = cf_fma(z1[q], w, a1);
+                    }
+                    xl_st4(tile + xl_long_col_off(p, cstride, n), a0, a1);
+                }
+            }
+        }
+    }
+};
+
+// long_cols + long_cols_combine as ONE cluster kernel (see XlLongRowsInvC): the R CTAs of a column pair park
+// w_P^{-i q} z_q[i] in their tiles, CTA c combines the positions of its slice from the R tiles over distributed shared memory
+// and writes the kept rows of the column tile.  Saves the write + read of the z_q scratch (2 x 8.6 GB at 16384^2).
+template <int L0> struct XlLongColsZOp : XlOpBase {
+    static constexpr int R1 = xl_first_radix(L0), S1 = L0 / R1;
+    const XlLongParams& p; int q; const cf* Yq; const cf* Hq; int rev; cf* s;
+    XL_DEV void load(int i, cf* v, int stride) const { xl_ld4(Yq + (size_t)i * XL_V, v, v + stride); }
+    XL_DEV void spec(int beta, cf* v) const {
+#pragma unroll
+        for (int qq = 0; qq < 16; ++qq) {
+            cf h0, h1;
+            xl_ldg4(Hq + (size_t)((qq * (L0 / 16) + beta) ^ rev) * XL_V, &h0, &h1);   // L0 - 1 - slot == slot ^ (L0 - 1)
+            v[qq] = cf_mul(v[qq], h0);
+            v[16 + qq] = cf_mul(v[16 + qq], h1);
+        }
+    }
+    XL_DEV void store_vec(int n, const cf* v) const {
+#pragma unroll
+        for (int j = 0; j < R1; ++j) {
+            const int i = n + S1 * j;
+            const cf w = cf_conj(xl_tw_at(p.tw, i * q, p.P));     // w_P^{-i q}
+            const cf o[2] = {cf_mul(v[j], w), cf_mul(v[R1 + j], w)};
+            XlTile<2>::st(s, i, o, 1);
+        }
+    }
+};
+template <int L0> struct XlLongColsC {
+    static const char* name() { return "long_cols"; }
+    typedef XlLongParams Params;
+    static constexpr int NT = xl_threads(L0);
+    static size_t smem() { return xl_smem_bytes(L0, XL_V); }
+    XL_DEV static void run1(const Params& p, cf* s) {
+        cf* t = s + xl_tile_elems(L0, XL_V);
+        const int q = XL_BLOCK_X;                                                   // (pair G = blockIdx.y, sub-line q = blockIdx.x)
+        const size_t blk = ((size_t)XL_BLOCK_Y * p.R + q) * L0 * XL_V;
+        const bool mir = 2 * q > p.R;                                               // even in y: see XlLongCols
+        const cf* Hq = p.H + ((size_t)XL_BLOCK_Y * p.R + (mir ? p.R - q : q)) * L0 * XL_V;
+        XlLongColsZOp<L0> op{{}, p, q, p.scratch + blk, Hq, mir ? L0 - 1 : 0, s};
+        XL_THREADS(tid, NT) {
+            constexpr unsigned BYTES = L0 * XL_V * sizeof(cf), CH = BYTES < 32768 ? BYTES : 32768;
+            if (tid == 0)
+                for (unsigned o = 0; o < BYTES; o += CH) xl_prefetch_l2_bulk((const char*)Hq + o, CH);
+        }
+        XlFft<L0, XL_V>::conv_g(s, t, p.tw, op);
+    }
+    XL_DEV static void run2(const Params& p, cf*, const XlPeers& pr) {
+        const int c = XL_BLOCK_X, G = XL_BLOCK_Y, slice = L0 / p.R;
+        cf* tile = p.spec + (size_t)G * p.chunk_rows * XL_V;
+        const size_t cstride = (size_t)p.pairs * p.chunk_rows * XL_V;
+        XL_THREADS(tid, NT) {
+            for (int ii = tid; ii < slice; ii += NT) {
+                const int i = c * slice + ii;
+                cf z0[8], z1[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    z0[q] = cf_zero(); z1[q] = cf_zero();
+                    if (q < p.R) xl_peer_ld4(pr, q, 2 * xl_pad(i), &z0[q], &z1[q]);
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int n = i + L0 * j;
                     if (2 * j >= p.R || n >= p.N) continue;
                     cf a0 = z0[0], a1 = z1[0];
 #pragma unroll

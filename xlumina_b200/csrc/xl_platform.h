@@ -54,6 +54,10 @@ static inline void xl_cp_async_wait() {}
 static inline void xl_nanosleep(unsigned) {}
 static inline float xl_rcpf(float x) { return 1.0f / x; }
 static inline unsigned xl_umulhi(unsigned a, unsigned b) { return (unsigned)(((unsigned long long)a * b) >> 32); }
+// Thread-block clusters (xl_launch_cluster): the emulation runs phase 1 of every CTA of a cluster, then phase 2, each CTA on
+// its own shared-memory buffer; a peer's distributed shared memory is that buffer.
+struct XlPeers { float2* const* base; };
+static inline void xl_peer_ld4(const XlPeers& pr, int rank, int off, float2* a, float2* b) { *a = pr.base[rank][off]; *b = pr.base[rank][off + 1]; }
 #else
 #include <cuda_runtime.h>
 #define XL_DEV __device__ __forceinline__
@@ -93,6 +97,21 @@ XL_DEV void xl_cp_async_wait() { asm volatile("cp.async.wait_all;" ::: "memory")
 XL_DEV void xl_nanosleep(unsigned ns) { __nanosleep(ns); }
 XL_DEV float xl_rcpf(float x) { return __fdividef(1.0f, x); }   // approximate reciprocal (2 ulp), branch-free
 XL_DEV unsigned xl_umulhi(unsigned a, unsigned b) { return __umulhi(a, b); }
+// Thread-block clusters: barrier with release / acquire semantics at cluster scope (shared-memory writes made before it are
+// visible to the peers' ld.shared::cluster after it), and 16-byte loads from a peer CTA's shared memory (DSMEM).
+XL_DEV void xl_cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+struct XlPeers { unsigned base; };   // shared-window address of this CTA's dynamic shared memory (the same offset in every peer)
+// two adjacent complex values at float2 index `off` (even) of the dynamic shared memory of CTA `rank` of this cluster
+XL_DEV void xl_peer_ld4(const XlPeers& pr, int rank, int off, float2* a, float2* b) {
+    unsigned addr;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(addr) : "r"(pr.base + (unsigned)off * 8u), "r"(rank));
+    float4 t;
+    asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(t.x), "=f"(t.y), "=f"(t.z), "=f"(t.w) : "r"(addr) : "memory");
+    *a = make_float2(t.x, t.y);
+    *b = make_float2(t.z, t.w);
+}
 // exchange one complex value with the neighbouring lane (lane ^ 1).  MASK = the lanes that execute the call, a compile-time
 // constant (xl_lane_mask(L): the butterfly loops of XlFft<L> run lanes [0, min(32, L/16)) of every warp).  A run-time
 // __activemask() here makes the compiler fence every exchange (VOTE + BRA.DIV) and serialise the loads around it.

@@ -10,6 +10,14 @@
 // response per rank.   exchanged layout of a spectra buffer:  [source rank][pairs][rows of that rank][2].
 // P <= 4096 runs the single-pass kernels of xl_kernels.cuh; longer lines (up to 32768: N <= 16384) run the split kernels of
 // xl_long.cuh (P = R * L0) and need the scratch buffer of xl_slab_scratch_bytes().
+// The inverse radix-R step of the split kernels: inside a thread-block cluster over distributed shared memory, or as a second
+// launch through the scratch buffer.  Measured on B200 (profiles/long_probe_r02v.txt): clusters of R = 4 CTAs win (8192^2:
+// long_cols 1.67 against 1.15 + 0.73 ms, long_rows_inv 0.82 against 0.59 + 0.40 ms), clusters of R = 8 lose (16384^2: 7.70
+// against 4.75 + 2.13 ms -- eight 74 KB CTAs must find four SMs of one GPC and wait for each other at the barrier).
+// -1 (default): clusters for R <= 4;  0 / 1: force the two-launch / the cluster form (tests, A/B timing).
+static int g_long_cluster = -1;
+extern "C" void xl_debug_set_long_cluster(int on) { g_long_cluster = on < 0 ? -1 : (on ? 1 : 0); }
+static bool long_use_cluster(int R) { return g_long_cluster < 0 ? R <= 4 : g_long_cluster != 0; }
 static int g_max_line = 4096;   // sub-line length of the split kernels; tests set 32 to exercise them at small sizes
 extern "C" void xl_debug_set_max_line(int l) { g_max_line = l == 32 ? 32 : 4096; }
 extern "C" int xl_slab_padded_length(int N) {
@@ -162,6 +170,10 @@ extern "C" int xl_slab_cols(void* T, const void* Hloc, int N, int G, void* scrat
     q.spec = (cf*)T; q.H = (cf*)Hloc; q.scratch = (cf*)scratch;
     rc = xl_launch<XlLongColsSplit>(XlDim{pointwise_grid((size_t)g.L0, XlLongColsSplit::NT), g.pairs}, st, q);
     if (rc) return rc;
+    if (long_use_cluster(g.R)) {      // convolution + radix-R DIT step in one cluster kernel (no scratch round trip)
+        XL_FOR_L0(g.L0, rc = xl_launch_cluster<XlLongColsC<XL>>(XlDim{g.R, g.pairs}, st, q));
+        return rc;
+    }
     XL_FOR_L0(g.L0, rc = xl_launch<XlLongCols<XL>>(XlDim{g.R, g.pairs}, st, q));
     if (rc) return rc;
     return xl_launch<XlLongColsCombine>(XlDim{pointwise_grid((size_t)g.pairs * g.L0, XlLongColsCombine::NT), 1}, st, q);
@@ -185,6 +197,10 @@ extern "C" int xl_slab_rows_inv(const void* S, void* out_local, int N, int G, in
     XlLongParams q;
     if ((rc = long_params(q, g, N, 1.0, 1.0, 0.0))) return rc;
     q.spec = (cf*)S; q.out = (cf*)out_local; q.scratch = (cf*)scratch; q.flags = flags & XL_CONJ_OUT;
+    if (long_use_cluster(g.R)) {
+        XL_FOR_L0(g.L0, rc = xl_launch_cluster<XlLongRowsInvC<XL>>(XlDim{g.R, xl_groups(g.rows)}, st, q));
+        return rc;
+    }
     XL_FOR_L0(g.L0, rc = xl_launch<XlLongRowsInv<XL>>(XlDim{g.R, xl_groups(g.rows)}, st, q));
     if (rc) return rc;
     return xl_launch<XlLongRowsCombine>(XlDim{pointwise_grid((size_t)g.rows * g.L0, XlLongRowsCombine::NT), 1}, st, q);
