@@ -105,6 +105,10 @@ template <int L0> struct XlLongRowsFwd {
     }
 };
 
+// Measured and dropped (profiles/long_probe_r02w.txt): the sub-lines q and q + R/2 of ONE row as the two lines of a CTA
+// (w_R^{j(q+R/2)} = (-1)^j w_R^{jq}: one set of loads and products serves both, half the first-pass loads) -- 5.0 ms against
+// 3.6 ms at 16384^2: each lane pair then writes 16 bytes of a 32-byte sector and the other half arrives from another CTA.
+
 template <int L0> struct XlLongRowsInvOp : XlOpBase {
     static constexpr int R1 = xl_first_radix(L0), S1 = L0 / R1;
     const XlLongParams& p; int q, yb;
