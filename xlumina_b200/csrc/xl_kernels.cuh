@@ -909,14 +909,6 @@ template <int L, int PRO, int EPI, int ACC> struct XlCztOp : XlOpBase {
         cf a[XL_V], b[XL_V];
         if (PRO == XL_PRO_NONE || PRO == XL_PRO_RSF) {
             fetch(p.in + (long long)cl * p.in_comp, i, ok_i, a);
-        } else if (PRO == XL_PRO_VCZT) {
-            // component 0 needs Ex only, component 1 Ey only, component 2 both: the unused operand repeats the used one (the
-            // same addresses, served by L1) instead of pulling the other plane through L2 -- pointers selected once per CTA,
-            // no branch in the load path
-            const cf* pa = comp == 1 ? p.in + p.in_comp : p.in;
-            const cf* pb = comp == 2 ? p.in + p.in_comp : pa;
-            fetch(pa, i, ok_i, a);
-            fetch(pb, i, ok_i, b);
         } else {
             fetch(p.in, i, ok_i, a);                 // Ex
             fetch(p.in + p.in_comp, i, ok_i, b);     // Ey
@@ -944,8 +936,11 @@ template <int L, int PRO, int EPI, int ACC> struct XlCztOp : XlOpBase {
                 // (an amplitude factor: fp32 coordinates are enough; the phase lives in F)
                 const float X = p.gpro.swap ? cpos : lcoord[l], Y = p.gpro.swap ? lcoord[l] : cpos;
                 const float ir2 = xl_rcpf(X * X + Y * Y + z * z);   // MUFU.RCP: an IEEE division carries a slow-path branch that splits the loads
-                const float ax = comp == 2 ? X * z * ir2 : 1.f;      // components 0 / 1: a[] already is the plane they need
-                const float ay = comp == 2 ? Y * z * ir2 : 0.f;
+                // every component loads both planes: selecting, per CTA, only the plane components 0 / 1 need (the unused
+                // operand repeating the used one) was measured in bench.py's per-kernel pass and lost, 174 against 161 us
+                // for this pass at 2048^2 (profiles/ab_vczt_loads_r02w.txt)
+                const float ax = comp == 0 ? 1.f : (comp == 1 ? 0.f : X * z * ir2);
+                const float ay = comp == 0 ? 0.f : (comp == 1 ? 1.f : Y * z * ir2);
                 x = cf_mul(cf_lin2(a[l], ax, b[l], ay), fac(p.tpro, tp, l, ipos));
             } else {  // XL_PRO_HIGHNA: row `comp` of apod*G*RL(theta,phi), stored for |x|,|y| with the parity of each entry
                 const cf w = fac(p.tpro, tp, l, ipos);
