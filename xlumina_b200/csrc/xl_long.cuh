@@ -4,13 +4,19 @@
 // One decimation step splits a length-P DFT into R DFTs of length L0 that the shared-memory engine (xl_fft.cuh) runs:
 //   forward   X[q + R k] = FFT_L0( y_q )[k],   y_q[i] = w_P^{i q} * sum_{j<R} x[i + L0 j] w_R^{j q}       (DIF; i < L0, q < R)
 //   inverse   x[i + L0 j] = sum_q w_R^{-j q} z_q[i],   z_q[i] = w_P^{-i q} * IDFT_L0( X_q )[i]                (DIT)
-// The forward radix-R step needs only the CTA's own inputs, so it is fused into the first pass's LOAD (R, or R/2 when
-// the upper half of the line is zero padding, strided global loads per element -- they hit L2, the line was just read by
-// the R-1 sibling CTAs).  The inverse radix-R step needs the R sub-lines of R different CTAs: they park z_q in a scratch
-// buffer and a pointwise "combine" kernel finishes the line (and drops the discarded half).
+// Where the two radix-R steps run (round 2, measured per kernel with scripts/long_probe.py):
+//   rows, forward      fused into the first pass's LOAD of long_rows_fwd (R/2 strided loads per element: the upper half of the
+//                      line is zero padding; they hit L2, the line was just read by the R-1 sibling CTAs)
+//   columns, forward   its own pointwise pass (long_cols_split, long_h_split): once per position instead of once per sub-line CTA
+//   impulse response   inside h_eval, which evaluates every sample once (positions t and L0 - t share their R samples)
+//   inverse (DIT)      needs the R sub-lines of R different CTAs: for R <= 4 they are a thread-block cluster and combine over
+//                      distributed shared memory (XlLongColsC, XlLongRowsInvC); for R = 8 they park z_q in a scratch buffer
+//                      and a pointwise "combine" kernel finishes the line (and drops the discarded half)
 // "Super-slot" order of a length-P spectrum: bin q + R k lives at q*L0 + slot_L0(k); adjacent super-slots pair up exactly
 // as in the short case, so the blocked layouts, the exchanged layouts of the slab path and the transfer-function layout
-// [pair][P][2] carry over (no x/y mirroring of the transfer function in this mode).
+// [pair][P][2] carry over.  The transfer function is even in x and y; in this mode only the evenness along the transformed
+// axis is used: sub-line R - q of a spectrum is sub-line q in reverse slot order (XlLongHRows), so the sub-lines q > R/2 are
+// neither transformed nor (for the column spectra) stored.
 #pragma once
 #include "xl_kernels.cuh"
 
