@@ -482,8 +482,12 @@ class _RSLarge(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             _, field, out, z = ctx.saved_tensors
             dx, dy, k = ctx.geo
-            gz = sum(slab.rs_slab_grad_z(field[i], torch.conj_physical(g[i]), out[i], z, dx, dy, k, group=slab._LOCAL)
-                     for i in range(g.shape[0])).reshape(z.shape).to(z.dtype)
+            gz, Hz = None, None
+            for i in range(g.shape[0]):                   # the fields of a batch share the slab of the reduced kernel
+                gi, Hz = slab.rs_slab_grad_z(field[i], torch.conj_physical(g[i]), out[i], z, dx, dy, k, group=slab._LOCAL,
+                                             transfer_dz=Hz, return_transfer=True)
+                gz = gi if gz is None else gz + gi
+            gz = gz.reshape(z.shape).to(z.dtype)
         return gin, gz, None, None, None
 
 

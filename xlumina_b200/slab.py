@@ -188,14 +188,15 @@ def rs_slab_vjp(ct_local, transfer, group=None, lib=None):
         return _apply(plan, c, transfer, 0, lib, group)
 
 
-def rs_slab_grad_z(field_local, ct_local, out_local, z, dx, dy, k, group=None, lib=None):
+def rs_slab_grad_z(field_local, ct_local, out_local, z, dx, dy, k, group=None, lib=None, transfer_dz=None, return_transfer=False):
     """d/dz of  Re sum(ct * out)  for  out = rs_propagation_slab(field, z)  -- `ct_local` is this rank's slab of the cotangent
     in the JAX convention (no conjugate; torch callers pass conj(grad_output)), `out_local` the saved primal output.
         d out/dz = i k out + field (*) (dh/dz - i k h)
     The first term is a pure phase rotation: its contribution, -k Im sum(ct * out), is accumulated in float64 from complex64
     operands (every product is exact), so it cancels exactly for intensity-type losses; only the
     reduced kernel, 1e2-1e4 times smaller, goes through the complex64 FFT chain.  Returns a float64 scalar tensor; with
-    more than one rank the partial sums are all-reduced (every rank gets the total)."""
+    more than one rank the partial sums are all-reduced (every rank gets the total).  `transfer_dz` / `return_transfer`: the
+    transfer-function slab of the reduced kernel, to be reused for the other fields of a batch at the same z."""
     lib = lib or _lib.lib()
     world, rank = _world_rank(group)
     _require_device(field_local, lib)
@@ -206,9 +207,10 @@ def rs_slab_grad_z(field_local, ct_local, out_local, z, dx, dy, k, group=None, l
     with _device_of(f):
         zt = z if isinstance(z, torch.Tensor) else torch.full((1,), float(z), dtype=torch.float64, device=f.device)
         zt = zt.detach().to(device=f.device, dtype=torch.float64).reshape(1)
-        Hz = _transfer_slab(plan, zt, float(dx), float(dy), float(k), rank, f, lib, group, deriv=True)
+        Hz = transfer_dz
+        if Hz is None:
+            Hz = _transfer_slab(plan, zt, float(dx), float(dy), float(k), rank, f, lib, group, deriv=True)
         d = _apply(plan, f, Hz, 0, lib, group)
-        del Hz
         gz = torch.zeros((), dtype=torch.float64, device=f.device)
         step = max(1, (1 << 24) // f.shape[-1])                       # rows per chunk: bounds the float64 temporaries
         for r0 in range(0, f.shape[0], step):
@@ -216,4 +218,4 @@ def rs_slab_grad_z(field_local, ct_local, out_local, z, dx, dy, k, group=None, l
             gz += (cc * d[r0:r0 + step]).real.sum() - float(k) * (cc * o[r0:r0 + step]).imag.sum()
     if world > 1:
         dist.all_reduce(gz, group=group)
-    return gz
+    return (gz, Hz) if return_transfer else gz
