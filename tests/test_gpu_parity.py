@@ -424,6 +424,42 @@ def test_public_api_routes_large_grids_through_stage_chain(xb):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("N", [2304, 4608, 8704])
+def test_split_line_chain_point_source_at_production_sub_lines(xb, N):
+    """csrc/xl_long.cuh with sub-lines of 4096 (padded length 8192 / 16384 / 32768 = 2 / 4 / 8 sub-lines: cluster kernels for
+    the first two, the two-launch inverse step for the last): a point source must reproduce the sampled impulse response,
+    out[p,q] = dx dy h((q - j0) dx, (p - i0) dy; z) (wave_optics.py:291-297), and propagation must stay linear."""
+    import math
+    from xlumina_b200 import slab
+    lam, z = 0.6328, 5.0e4
+    k = 2 * math.pi / lam
+    x, _ = xb.space(15000.0, N)
+    dx = float(x[1] - x[0])
+    assert slab.SlabPlan(N, 1, __import__("xlumina_b200")._lib.lib()).L == {2304: 8192, 4608: 16384, 8704: 32768}[N]
+    i0, j0 = N // 3, (2 * N) // 5
+    f = torch.zeros(N, N, dtype=torch.complex64, device="cuda")
+    f[i0, j0] = 1.0
+    out, H = slab.rs_propagation_slab(f, z, dx, dx, k, return_transfer=True, group=slab._LOCAL)
+    q = (torch.arange(N, device="cuda", dtype=torch.float64) - j0) * dx
+    p = (torch.arange(N, device="cuda", dtype=torch.float64) - i0) * dx
+    r = torch.sqrt(p[:, None] ** 2 + q[None, :] ** 2 + z * z)
+    ref = (1 / (2 * math.pi)) * z / r ** 2 * (1 / r - 1j * k) * torch.exp(1j * k * r) * dx * dx
+    err = float(torch.linalg.norm(out.to(torch.complex128) - ref) / torch.linalg.norm(ref))
+    del ref, r
+    assert err < 2e-6
+    g = torch.Generator(device="cpu").manual_seed(N)
+    u = torch.view_as_complex(torch.randn(N, N, 2, generator=g)).to("cuda")
+    a = slab.rs_propagation_slab(u, z, dx, dx, k, transfer=H, group=slab._LOCAL)
+    b = slab.rs_propagation_slab(u + float(N) * f, z, dx, dx, k, transfer=H, group=slab._LOCAL)   # a source as strong as the field
+    assert float(torch.linalg.norm(b - a - float(N) * out) / torch.linalg.norm(float(N) * out)) < 1e-5
+    # adjoint identity of the complex-symmetric operator: sum(ct * A u) == sum(A ct * u)
+    ct = torch.view_as_complex(torch.randn(N, N, 2, generator=g)).to("cuda")
+    v = slab.rs_slab_vjp(ct, H, group=slab._LOCAL)
+    lhs, rhs = (ct.to(torch.complex128) * a).sum(), (v.to(torch.complex128) * u).sum()
+    assert abs(lhs - rhs) < 1e-5 * abs(lhs)
+
+
+@pytest.mark.gpu
 def test_lazily_conjugated_inputs_are_resolved(xb):
     """torch's .conj() is a lazy view over the unconjugated storage: the raw-pointer boundary must materialise it."""
     from xlumina_b200 import ops

@@ -105,6 +105,27 @@ def test_slab_rs_split_lines_both_inverse_forms(emu, tmp_path, world, N, z, clus
     assert rel_l2(got, ref) < 5e-6
 
 
+def test_split_lines_at_the_production_sub_line_length(emu):
+    """The split-line kernels with the sub-line length of production (4096): N = 2304 -> padded length 8192 = 2 sub-lines (the
+    cluster form of the inverse step), one rank, against the complex128 oracle.  The other tests force sub-lines of 32."""
+    from conftest import rel_l2
+    from oracle import oracle_np as o
+    from xlumina_b200 import slab
+    o.set_workers(8)
+    emu.xl_debug_set_max_line(4096)
+    emu.xl_debug_set_long_cluster(-1)
+    N, lam, z = 2304, 0.6328, 50000.0
+    x = np.linspace(-15000.0, 15000.0, N)
+    rng = np.random.default_rng(2304)
+    X, Y = np.meshgrid(x, x)
+    f = (np.exp(-(X ** 2 + Y ** 2) / 4000.0 ** 2) * (rng.standard_normal((N, N)) + 1j * rng.standard_normal((N, N)))).astype(np.complex64)
+    assert slab.SlabPlan(N, 1, emu).L == 8192
+    out = slab.rs_propagation_slab(torch.as_tensor(f), z, float(x[1] - x[0]), float(x[1] - x[0]), 2 * np.pi / lam,
+                                   group=slab._LOCAL, lib=emu)
+    ref, _ = o.RS_propagation(f.astype(np.complex128), x, x, lam, z)
+    assert rel_l2(out.numpy(), ref) < 5e-6
+
+
 def _grad_z_oracle(field, ct, x, z):
     """d/dz Re sum(ct * RS(field, z)) by autograd through the complex128 torch oracle."""
     from oracle import oracle_torch as ot
